@@ -1,0 +1,242 @@
+"""Generate the golden fixtures by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container:   python tests/golden/make_golden.py
+For every case it (1) runs the reference classes (NoiseNetwork / Denoiser / rotate / Shift2d /
+compute_ramped_lrate / torch.optim.Adam as train.py uses it), (2) asserts that oracle/ssdn_oracle.py
+reproduces the reference, and (3) writes tests/golden/<case>.npz with the reference outputs.
+The fixtures are what pins the oracle (and through it the CUDA engine) to the reference."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from _ref_shim import import_reference  # noqa: E402
+
+ssdn = import_reference()
+import cases as C  # noqa: E402
+import ssdn_oracle as O  # noqa: E402
+from ssdn.datasets import NoisyDataset  # noqa: E402
+from ssdn.denoiser import Denoiser  # noqa: E402
+from ssdn.models import NoiseNetwork  # noqa: E402
+from ssdn.models.utility import Shift2d  # noqa: E402
+from ssdn.params import ConfigValue, NoiseAlgorithm, NoiseValue, PipelineOutput  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def save(name, **arrs):
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: np.asarray(v.detach().numpy() if torch.is_tensor(v) else v) for k, v in arrs.items()})
+    print("wrote", name, {k: tuple(np.asarray(v.detach().numpy() if torch.is_tensor(v) else v).shape) for k, v in arrs.items()})
+
+
+def close(a, b, tol, what):
+    err = (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+    assert err <= tol, f"oracle != reference for {what}: rel err {err:.3e}"
+    return err
+
+
+def load_into(net, params):
+    sd = {k: v.clone() for k, v in params.items()}
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and set(missing) <= {"output_block.4.weight", "output_block.4.bias"}
+
+
+# ------------------------------------------------------------------ index ops
+def index_ops():
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(2, 3, 8, 8, generator=g)
+    for a in (0, 90, 180, 270):
+        r = ssdn.utils.rotate(x, a)
+        assert torch.equal(r, O.rotate(x, a)) and np.array_equal(r.numpy(), O.rotate_np(x.numpy(), a))
+    for a, b in ((0, 0), (90, 270), (180, 180), (270, 90)):
+        assert torch.equal(ssdn.utils.rotate(ssdn.utils.rotate(x, a), b), x)
+    for v, h in ((1, 0), (2, 0), (0, 1), (-1, 0), (0, -2), (1, 1)):
+        assert torch.equal(Shift2d((v, h))(x), O.shift2d(x, v, h)), (v, h)
+    # fixture: rotations + shifted/un-rotated concat of a 4-group stack
+    y = torch.rand(8, 2, 8, 8, generator=g)
+    shifted = Shift2d((1, 0))(y)
+    parts = torch.chunk(shifted, 4, dim=0)
+    cat = torch.cat([ssdn.utils.rotate(p, a) for p, a in zip(parts, (0, 270, 180, 90))], dim=1)
+    assert torch.equal(cat, O.shift_unrot_concat(y))
+    stack = torch.cat([ssdn.utils.rotate(x, a) for a in (0, 90, 180, 270)], dim=0)
+    assert torch.equal(stack, O.rot4_stack(x))
+    save("index_ops", x=x, rot4=stack, y=y, unrot=cat)
+
+
+# ------------------------------------------------------------------ networks
+def networks():
+    for name, (cin, cout, blind, n, size) in C.NETWORK_CASES.items():
+        params, x, dout = C.network_inputs(name)
+        net = NoiseNetwork(cin, cout, blindspot=blind)
+        load_into(net, params)
+        xr = x.clone().requires_grad_(True)
+        out = net(xr)
+        out.backward(dout)
+        grads = {k: dict(net.named_parameters())[k].grad for k in O.param_order(cin, cout, blind)}
+        # oracle check (autograd through the oracle's functional graph)
+        po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        xo = x.clone().requires_grad_(True)
+        oo = O.noise_network_forward(po, xo, blind)
+        oo.backward(dout)
+        close(oo, out, 1e-6, name + " fwd")
+        for k in grads:
+            close(po[k].grad, grads[k], 2e-5, name + " grad " + k)
+        close(xo.grad, xr.grad, 2e-5, name + " dx")
+        save(name, out=out, dx=xr.grad, grad_summary=C.grad_summary(grads),
+             g_first_w=grads["encode_block_1.0.weight"], g_first_b=grads["encode_block_1.0.bias"],
+             g_out_w=grads["output_conv.weight"], g_out_b=grads["output_conv.bias"],
+             g_dec5a_b=grads["decode_block_5.0.bias"], g_enc6_w=grads["encode_block_6.0.weight"])
+
+
+# ------------------------------------------------------------------ pipelines
+def make_cfg(algo, mode, channels):
+    cfg = ssdn.cfg.base()
+    cfg[ConfigValue.ALGORITHM] = {"ssdn": NoiseAlgorithm.SELFSUPERVISED_DENOISING, "n2c": NoiseAlgorithm.NOISE_TO_CLEAN,
+                                  "n2n": NoiseAlgorithm.NOISE_TO_NOISE, "n2v": NoiseAlgorithm.NOISE_TO_VOID}[algo]
+    cfg[ConfigValue.NOISE_STYLE] = "gauss25"
+    cfg[ConfigValue.NOISE_VALUE] = {"known": NoiseValue.KNOWN, "const": NoiseValue.UNKNOWN_CONSTANT,
+                                    "var": NoiseValue.UNKNOWN_VARIABLE, None: NoiseValue.KNOWN}[mode]
+    cfg[ConfigValue.IMAGE_CHANNELS] = channels
+    ssdn.cfg.infer(cfg, model_only=True)
+    return cfg
+
+
+def ref_denoiser(d):
+    den = Denoiser(make_cfg(d["algorithm"], d["sigma_mode"], d["channels"]), device="cpu")
+    load_into(den.get_model(Denoiser.MODEL, parallelised=False), d["params"])
+    if "est_params" in d:
+        load_into(den.get_model(Denoiser.SIGMA_ESTIMATOR, parallelised=False), d["est_params"])
+    if "est_sigma" in d:
+        den.l_params[Denoiser.ESTIMATED_SIGMA].data.copy_(d["est_sigma"])
+    return den
+
+
+def ref_data(d):
+    M = NoisyDataset.Metadata
+    n, c, h, w = d["noisy"].shape
+    md = {M.IMAGE_SHAPE: torch.tensor([[c, h, w]] * n), M.CLEAN: d["clean"]}
+    if "noise_values" in d:
+        md[M.INPUT_NOISE_VALUES] = d["noise_values"]
+    if "coords" in d:
+        md[M.MASK_COORDS] = d["coords"]
+    return [d["noisy"].clone(), d.get("ref", torch.zeros(0)).clone(), md]
+
+
+def oracle_run(d):
+    p = {k: v.clone().requires_grad_(True) for k, v in d["params"].items()}
+    ep = {k: v.clone().requires_grad_(True) for k, v in d["est_params"].items()} if "est_params" in d else None
+    es = d["est_sigma"].clone().requires_grad_(True) if "est_sigma" in d else None
+    if d["algorithm"] == "ssdn":
+        out = O.ssdn_pipeline(p, d["noisy"], d["noise_values"], d["sigma_mode"], ep, es)
+    elif d["algorithm"] == "n2v":
+        out = O.mask_mse_pipeline(p, d["noisy"], d["ref"], d["coords"])
+    else:
+        out = O.mse_pipeline(p, d["noisy"], d["ref"])
+    out["loss"].mean().backward()
+    return out, p, ep, es
+
+
+def pipelines():
+    for name in C.PIPELINE_CASES:
+        d = C.pipeline_inputs(name)
+        den = ref_denoiser(d)
+        den.train()
+        outs = den.run_pipeline(ref_data(d))
+        outs[PipelineOutput.LOSS].mean().backward()
+        main = den.get_model(Denoiser.MODEL, parallelised=False)
+        c = d["channels"]
+        names = O.param_order(c, c + c * (c + 1) // 2 if d["algorithm"] == "ssdn" else c, d["algorithm"] == "ssdn")
+        g_main = {k: dict(main.named_parameters())[k].grad for k in names}
+        arrs = dict(loss=outs[PipelineOutput.LOSS], out=outs[PipelineOutput.IMG_DENOISED], grad_summary=C.grad_summary(g_main),
+                    g_first_w=g_main["encode_block_1.0.weight"], g_out_w=g_main["output_conv.weight"], g_out_b=g_main["output_conv.bias"])
+        oo, po, epo, eso = oracle_run(d)
+        close(oo["loss"], outs[PipelineOutput.LOSS], 1e-6, name + " loss")
+        for k in names:
+            close(po[k].grad, g_main[k], 5e-5, name + " grad " + k)
+        if d["algorithm"] == "ssdn":
+            arrs.update(mu=outs[PipelineOutput.IMG_MU], model_std=outs[PipelineOutput.MODEL_STD_DEV], noise_std=outs[PipelineOutput.NOISE_STD_DEV])
+            close(oo["pme"], outs[PipelineOutput.IMG_DENOISED], 1e-5, name + " pme")
+            close(oo["model_std"], outs[PipelineOutput.MODEL_STD_DEV], 1e-5, name + " model_std")
+            close(oo["noise_std"].reshape(-1), outs[PipelineOutput.NOISE_STD_DEV].reshape(-1), 1e-6, name + " noise_std")
+        else:
+            close(oo["out"], outs[PipelineOutput.IMG_DENOISED], 1e-6, name + " out")
+        psnr_ref = ssdn.utils.calculate_psnr(outs[PipelineOutput.IMG_DENOISED].detach(), d["clean"])
+        close(O.psnr(outs[PipelineOutput.IMG_DENOISED].detach(), d["clean"]), psnr_ref, 1e-6, name + " psnr")
+        arrs["psnr"] = psnr_ref
+        if "est_params" in d:
+            est = den.get_model(Denoiser.SIGMA_ESTIMATOR, parallelised=False)
+            g_est = {k: dict(est.named_parameters())[k].grad for k in O.param_order(c, 1, False)}
+            for k in g_est:
+                close(epo[k].grad, g_est[k], 5e-5, name + " est grad " + k)
+            arrs.update(est_grad_summary=C.grad_summary(g_est), g_est_out_w=g_est["output_conv.weight"])
+        if "est_sigma" in d:
+            gs = den.l_params[Denoiser.ESTIMATED_SIGMA].grad
+            close(eso.grad, gs, 1e-5, name + " est sigma grad")
+            arrs["g_est_sigma"] = gs
+        save(name, **arrs)
+
+
+# ------------------------------------------------------------------ optimiser side
+def optimiser():
+    its = 2_000_000
+    pts = [0, its // 20, its // 10, its // 2, int(its * 0.7), int(its * 0.85), its]
+    cfg = ssdn.cfg.base()
+    lr = [ssdn.utils.compute_ramped_lrate(i, its, cfg[ConfigValue.LR_RAMPDOWN_FRACTION], cfg[ConfigValue.LR_RAMPUP_FRACTION],
+                                          cfg[ConfigValue.LEARNING_RATE]) for i in pts]  # argument order of train.py:276-282
+    for i, v in zip(pts, lr):
+        assert abs(O.effective_lrate(i, its) - v) < 1e-12
+    g = torch.Generator().manual_seed(5)
+    p0 = torch.randn(1000, generator=g)
+    grads = [torch.randn(1000, generator=g) * (10.0 ** (k - 2)) for k in range(4)]
+    p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p], betas=[0.9, 0.99])   # train.py:107
+    po, m, v = p0.clone(), torch.zeros(1000), torch.zeros(1000)
+    traj = []
+    for k, gr in enumerate(grads):
+        for grp in opt.param_groups:
+            grp["lr"] = 3e-4 * (k + 1)
+        p.grad = gr.clone()
+        opt.step()
+        O.adam_step(po, gr, m, v, k + 1, 3e-4 * (k + 1))
+        close(po, p.data, 1e-6, "adam step %d" % k)
+        traj.append(p.data.clone())
+    save("optimiser", lr_points=np.array(pts, dtype=np.float64), lr_values=np.array(lr, dtype=np.float64), adam_traj=torch.stack(traj))
+
+
+def training_trajectory():
+    """Three optimiser steps exactly as train.py:197-202 on the ssdn_known_rgb case."""
+    d = C.pipeline_inputs("ssdn_known_rgb")
+    den = ref_denoiser(d)
+    den.train()
+    opt = torch.optim.Adam(den.parameters(), betas=[0.9, 0.99])
+    tr = O.CpuTrainer("ssdn", "known", 3)
+    tr.params = {k: v.clone().requires_grad_(True) for k, v in d["params"].items()}
+    tr.leaves = list(tr.params.values())
+    tr.m = [torch.zeros_like(t) for t in tr.leaves]
+    tr.v = [torch.zeros_like(t) for t in tr.leaves]
+    losses = []
+    for k in range(3):
+        for grp in opt.param_groups:
+            grp["lr"] = 3e-4
+        opt.zero_grad()
+        outs = den.run_pipeline(ref_data(d))
+        torch.mean(outs[PipelineOutput.LOSS]).backward()
+        opt.step()
+        losses.append(outs[PipelineOutput.LOSS].detach().clone())
+        oo = tr.step(d["noisy"], d["noise_values"], lr=3e-4)
+        close(oo["loss"].detach(), losses[-1], 2e-5, "trajectory loss %d" % k)
+    main = den.get_model(Denoiser.MODEL, parallelised=False)
+    final = {k: dict(main.named_parameters())[k].data for k in O.param_order(3, 9, True)}
+    save("trajectory_ssdn_known_rgb", losses=torch.stack(losses), final_summary=C.grad_summary(final))
+
+
+if __name__ == "__main__":
+    index_ops()
+    optimiser()
+    networks()
+    pipelines()
+    training_trajectory()
+    print("all oracle-vs-reference assertions passed")
