@@ -1,0 +1,190 @@
+// HBM-bound kernels of the U-Net: layout packing (with the 4-rotation stack), shifted max-pool
+// forward/backward, upsample backward, weight slab preparation, bias gradients.
+// All of them stream each byte once; accesses are float4 along the channel axis where the channel
+// count allows it.  Index work is exact integer arithmetic (bit-exact versus the oracle).
+#pragma once
+#include "common.cuh"
+
+namespace pw {
+
+constexpr int kBlock = 256;
+static inline int grid_for(long long n, int block = kBlock) { return (int)((n + block - 1) / block); }
+
+// ---------------------------------------------------------------------------- NCHW -> padded flat
+// rot4 != 0: the output holds 4*B images, image (r*B + b) = rotate(x[b], 90*r)   (utils/data.py:42-67)
+__global__ void pack_nchw_kernel(const float* __restrict__ x, float* __restrict__ v, float* __restrict__ lo,
+                                 int B, int C, int H, int W, Geom g, int cpitch, int coff, int rot4) {
+  const long long n = (long long)(rot4 ? 4 : 1) * B * C * H * W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int j = (int)(idx % W); long long t = idx / W;
+  const int i = (int)(t % H); t /= H;
+  const int c = (int)(t % C); const int bo = (int)(t / C);
+  const int r = rot4 ? bo / B : 0, b = rot4 ? bo % B : bo;
+  int si = i, sj = j;
+  if (r == 1) { si = j; sj = W - 1 - i; } else if (r == 2) { si = H - 1 - i; sj = W - 1 - j; }
+  else if (r == 3) { si = H - 1 - j; sj = i; }
+  const float val = __ldg(x + (((long long)b * C + c) * H + si) * W + sj);
+  const long long o = ((long long)bo * g.S + (i + g.row0) * g.P + j) * cpitch + coff + c;
+  v[o] = val;
+  if (lo) lo[o] = tf32_lo(val);
+}
+
+// padded flat -> dense NCHW (tests / gradients w.r.t. the input)
+__global__ void unpack_nchw_kernel(const float* __restrict__ v, float* __restrict__ y, int B, int C, int H, int W,
+                                   Geom g, int cpitch, int coff) {
+  const long long n = (long long)B * C * H * W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int j = (int)(idx % W); long long t = idx / W;
+  const int i = (int)(t % H); t /= H;
+  const int c = (int)(t % C); const int b = (int)(t / C);
+  y[idx] = v[((long long)b * g.S + (i + g.row0) * g.P + j) * cpitch + coff + c];
+}
+
+// ---------------------------------------------------------------------------- max-pool 2x2
+// blind != 0: Shift2d((1,0)) then MaxPool2d(2)  (models/noise_network.py:64-67): window rows (2i-1, 2i),
+// row -1 is the zero halo row of the padded layout.  One thread = one output pixel x 4 channels.
+__global__ void pool_fwd_kernel(const float* __restrict__ src, Geom gs, int s_cpitch, int s_coff,
+                                float* __restrict__ dv, float* __restrict__ dlo, Geom gd, int d_cpitch, int d_coff,
+                                int C, int blind) {
+  const int c4n = C / 4;
+  const long long n = (long long)gd.B * gd.H * gd.W * c4n;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int c = (int)(idx % c4n) * 4; long long t = idx / c4n;
+  const int xo = (int)(t % gd.W); t /= gd.W;
+  const int yo = (int)(t % gd.H); const int b = (int)(t / gd.H);
+  const int y0 = 2 * yo - (blind ? 1 : 0);
+  const long long s0 = ((long long)b * gs.S + (y0 + gs.row0) * gs.P + 2 * xo) * s_cpitch + s_coff + c;
+  const float4 a = *reinterpret_cast<const float4*>(src + s0);
+  const float4 bq = *reinterpret_cast<const float4*>(src + s0 + s_cpitch);
+  const float4 cq = *reinterpret_cast<const float4*>(src + s0 + (long long)gs.P * s_cpitch);
+  const float4 dq = *reinterpret_cast<const float4*>(src + s0 + (long long)(gs.P + 1) * s_cpitch);
+  float4 m;
+  m.x = fmaxf(fmaxf(a.x, bq.x), fmaxf(cq.x, dq.x)); m.y = fmaxf(fmaxf(a.y, bq.y), fmaxf(cq.y, dq.y));
+  m.z = fmaxf(fmaxf(a.z, bq.z), fmaxf(cq.z, dq.z)); m.w = fmaxf(fmaxf(a.w, bq.w), fmaxf(cq.w, dq.w));
+  const long long o = ((long long)b * gd.S + (yo + gd.row0) * gd.P + xo) * d_cpitch + d_coff + c;
+  *reinterpret_cast<float4*>(dv + o) = m;
+  *reinterpret_cast<float4*>(dlo + o) = make_float4(tf32_lo(m.x), tf32_lo(m.y), tf32_lo(m.z), tf32_lo(m.w));
+}
+
+// Backward of [LeakyReLU -> (shift) -> max-pool]: routes g = ga (+ gb) to the arg-max of each window
+// (first maximum in row-major window order wins, as in ATen's max_pool2d; a winning zero-halo element
+// swallows the gradient), multiplies by LeakyReLU'(act) and writes dZ = d(loss)/d(pre-activation) for
+// the full-resolution tensor (zeros elsewhere).  One thread = one window x one channel.
+__global__ void pool_bwd_kernel(const float* __restrict__ act, Geom ga_, int a_cpitch, int a_coff,
+                                const float* __restrict__ g1, int g1_cpitch, int g1_coff,
+                                const float* __restrict__ g2, int g2_cpitch, int g2_coff, Geom gp,
+                                float* __restrict__ dv, float* __restrict__ dlo, int d_cpitch, int d_coff,
+                                int C, int blind) {
+  const long long n = (long long)gp.B * gp.H * gp.W * C;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int c = (int)(idx % C); long long t = idx / C;
+  const int xo = (int)(t % gp.W); t /= gp.W;
+  const int yo = (int)(t % gp.H); const int b = (int)(t / gp.H);
+  const long long pflat = (long long)b * gp.S + (yo + gp.row0) * gp.P + xo;
+  float g = __ldg(g1 + pflat * g1_cpitch + g1_coff + c);
+  if (g2) g += __ldg(g2 + pflat * g2_cpitch + g2_coff + c);
+  const int y0 = 2 * yo - (blind ? 1 : 0);
+  const long long f0 = (long long)b * ga_.S + (y0 + ga_.row0) * ga_.P + 2 * xo;
+  const long long fl[4] = {f0, f0 + 1, f0 + ga_.P, f0 + ga_.P + 1};
+  float best = -INFINITY; int arg = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float a = __ldg(act + fl[k] * a_cpitch + a_coff + c);
+    if (a > best || a != a) { best = a; arg = k; }
+  }
+  const bool halo_row = blind && yo == 0;   // window rows (-1, 0): elements 0,1 are padding
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (halo_row && k < 2) continue;        // never write the halo
+    float o = 0.f;
+    if (k == arg) o = best > 0.f ? g : SSDN_LRELU_SLOPE * g;
+    const long long di = fl[k] * d_cpitch + d_coff + c;
+    dv[di] = o; dlo[di] = tf32_lo(o);
+  }
+}
+
+// Backward of [LeakyReLU -> nearest 2x upsample]: dZ[b,y,x,c] = LeakyReLU'(act) * sum of the 2x2 block of g.
+__global__ void up_bwd_kernel(const float* __restrict__ g, Geom gg, int g_cpitch, int g_coff,
+                              const float* __restrict__ act, int a_cpitch, int a_coff, Geom gl,
+                              float* __restrict__ dv, float* __restrict__ dlo, int d_cpitch, int d_coff, int C) {
+  const int c4n = C / 4;
+  const long long n = (long long)gl.B * gl.H * gl.W * c4n;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int c = (int)(idx % c4n) * 4; long long t = idx / c4n;
+  const int x = (int)(t % gl.W); t /= gl.W;
+  const int y = (int)(t % gl.H); const int b = (int)(t / gl.H);
+  const long long s0 = ((long long)b * gg.S + (2 * y + gg.row0) * gg.P + 2 * x) * g_cpitch + g_coff + c;
+  const float4 a = *reinterpret_cast<const float4*>(g + s0);
+  const float4 bq = *reinterpret_cast<const float4*>(g + s0 + g_cpitch);
+  const float4 cq = *reinterpret_cast<const float4*>(g + s0 + (long long)gg.P * g_cpitch);
+  const float4 dq = *reinterpret_cast<const float4*>(g + s0 + (long long)(gg.P + 1) * g_cpitch);
+  const long long lf = (long long)b * gl.S + (y + gl.row0) * gl.P + x;
+  const float4 av = *reinterpret_cast<const float4*>(act + lf * a_cpitch + a_coff + c);
+  float4 s;
+  s.x = (a.x + bq.x) + (cq.x + dq.x); s.y = (a.y + bq.y) + (cq.y + dq.y);
+  s.z = (a.z + bq.z) + (cq.z + dq.z); s.w = (a.w + bq.w) + (cq.w + dq.w);
+  s.x = av.x > 0.f ? s.x : SSDN_LRELU_SLOPE * s.x; s.y = av.y > 0.f ? s.y : SSDN_LRELU_SLOPE * s.y;
+  s.z = av.z > 0.f ? s.z : SSDN_LRELU_SLOPE * s.z; s.w = av.w > 0.f ? s.w : SSDN_LRELU_SLOPE * s.w;
+  const long long o = lf * d_cpitch + d_coff + c;
+  *reinterpret_cast<float4*>(dv + o) = s;
+  *reinterpret_cast<float4*>(dlo + o) = make_float4(tf32_lo(s.x), tf32_lo(s.y), tf32_lo(s.z), tf32_lo(s.w));
+}
+
+// ---------------------------------------------------------------------------- weights
+// Builds the K-major weight slab [n_tile][chunk][tap][N][16] (v and lo planes) from PyTorch-layout
+// weights W[cout][cin][taps].  transpose == 0 (forward):  slab[n][k] = W[n][k][tap]
+//                              transpose == 1 (data-grad): slab[n][k] = W[k][n][tap]   (n = cin, k = cout)
+__global__ void weight_prep_kernel(const float* __restrict__ w, float* __restrict__ sv, float* __restrict__ slo,
+                                   int cout, int cin, int ntaps, int n_valid, int k_valid, int n_tiles, int n_chunks,
+                                   int N, int transpose) {
+  const long long total = (long long)n_tiles * n_chunks * ntaps * N * 16;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int kk = (int)(idx % 16); long long t = idx / 16;
+  const int n = (int)(t % N); t /= N;
+  const int tap = (int)(t % ntaps); t /= ntaps;
+  const int ch = (int)(t % n_chunks); const int nt = (int)(t / n_chunks);
+  const int ng = nt * N + n, k = ch * 16 + kk;
+  float val = 0.f;
+  if (ng < n_valid && k < k_valid) {
+    const long long wi = transpose ? ((long long)k * cin + ng) * ntaps + tap : ((long long)ng * cin + k) * ntaps + tap;
+    val = __ldg(w + wi);
+  }
+  sv[idx] = val; slo[idx] = tf32_lo(val);
+}
+
+// ---------------------------------------------------------------------------- bias gradient
+// db[c] = sum over flat pixels of dZ[flat][c].  Two deterministic stages.
+__global__ void colsum_stage1_kernel(const float* __restrict__ dz, long long rows, int cpitch, int coff, int C,
+                                     float* __restrict__ partial, int rows_per_block) {
+  extern __shared__ float sm[];   // [warps][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  for (int c = lane; c < C; c += 32) {
+    float acc = 0.f;
+    for (long long r = r0 + warp; r < r1; r += nwarps) acc += __ldg(dz + r * cpitch + coff + c);
+    sm[warp * C + c] = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int w = 0; w < nwarps; ++w) acc += sm[w * C + c];
+    partial[(long long)blockIdx.x * C + c] = acc;
+  }
+}
+__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out,
+                                     int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblk; ++b) acc += partial[(long long)b * C + c];
+  out[c] = accumulate ? out[c] + acc : acc;
+}
+
+}  // namespace pw
