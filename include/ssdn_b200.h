@@ -29,6 +29,11 @@ int ssdn_conv2d_forward(void* ws, size_t ws_bytes, const float* x, const float* 
 int ssdn_conv2d_backward_data(void* ws, size_t ws_bytes, const float* dy, const float* w, float* dx, int n, int cin,
                               int h, int wd, int cout, int ksize, int blind, void* stream);
 
+/* dw [cout][cin][k][k] and db [cout] (either may be NULL): convolution_backward wgrad + bias reduction. */
+size_t ssdn_conv2d_backward_weight_workspace_bytes(int n, int cin, int h, int w, int cout, int ksize);
+int ssdn_conv2d_backward_weight(void* ws, size_t ws_bytes, const float* x, const float* dy, float* dw, float* db,
+                                int n, int cin, int h, int wd, int cout, int ksize, int blind, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

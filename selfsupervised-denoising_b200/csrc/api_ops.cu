@@ -94,3 +94,55 @@ extern "C" int ssdn_conv2d_backward_data(void* ws, size_t ws_bytes, const float*
   return run_conv(ws, ws_bytes, dy, w, nullptr, dx, n, cout, h, wd, cin, ksize, blind != 0, true, 0, cout, cin,
                   (cudaStream_t)stream);
 }
+
+extern "C" size_t ssdn_conv2d_backward_weight_workspace_bytes(int n, int cin, int h, int w, int cout, int ksize) {
+  Geom g = make_geom(n, h, w, ksize == 3);
+  const int ks = wgrad_pick_ksplit(g.total(), cout, cin, ksize * ksize, 148);
+  Arena a(nullptr, 0);
+  a.take<float>((size_t)g.total() * round_up(cin, 4) * 2); a.take<float>((size_t)g.total() * round_up(cout, 4) * 2);
+  a.take<float>(wgrad_partial_floats(ks, ksize * ksize, cout, cin)); a.take<float>((size_t)1024 * round_up(cout, 4)); a.take<int>(1);
+  return a.off + 4096;
+}
+
+/* dw[cout][cin][k][k], db[cout] (either may be NULL) from x and dy = d(loss)/d(conv output). */
+extern "C" int ssdn_conv2d_backward_weight(void* ws, size_t ws_bytes, const float* x, const float* dy, float* dw, float* db,
+                                           int n, int cin, int h, int wd, int cout, int ksize, int blind, void* stream) {
+  if (ksize != 1 && ksize != 3) return fail(-1, "ksize must be 1 or 3");
+  cudaStream_t st = (cudaStream_t)stream;
+  Geom g = make_geom(n, h, wd, ksize == 3);
+  const int xp = round_up(cin, 4), yp = round_up(cout, 4), ntaps = ksize * ksize;
+  const int ks = wgrad_pick_ksplit(g.total(), cout, cin, ntaps, num_sms());
+  Arena a(ws, ws_bytes);
+  const size_t xf = (size_t)g.total() * xp, yf = (size_t)g.total() * yp;
+  float* xv = a.take<float>(xf * 2); float* xl = xv + xf;
+  float* yv = a.take<float>(yf * 2); float* yl = yv + yf;
+  float* partial = a.take<float>(wgrad_partial_floats(ks, ntaps, cout, cin));
+  float* colpart = a.take<float>((size_t)1024 * yp);
+  int* flag = a.take<int>(1);
+  if (!a.ok()) return fail(-3, "workspace too small: need %zu bytes, have %zu", a.off, ws_bytes);
+  SSDN_CUDA(cudaMemsetAsync(xv, 0, xf * 8, st));
+  SSDN_CUDA(cudaMemsetAsync(yv, 0, yf * 8, st));
+  SSDN_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+  pw::pack_nchw_kernel<<<pw::grid_for((long long)n * cin * h * wd), pw::kBlock, 0, st>>>(x, xv, xl, n, cin, h, wd, g, xp, 0, 0);
+  pw::pack_nchw_kernel<<<pw::grid_for((long long)n * cout * h * wd), pw::kBlock, 0, st>>>(dy, yv, yl, n, cout, h, wd, g, yp, 0, 0);
+  if (dw) {
+    WgradPlan plan;
+    int r = wgrad_plan_init(&plan, g.total(), yv, yl, yp, 0, cout, xv, xl, xp, 0, cin, make_taps(ksize, blind != 0, false, g.P), ks,
+                            partial, flag, num_sms());
+    if (r) return fail(r, "wgrad_plan_init failed (%d)", r);
+    SSDN_CUDA(wgrad_launch(plan, st));
+    wgradk::wgrad_reduce_kernel<<<pw::grid_for((long long)cout * cin * ntaps), pw::kBlock, 0, st>>>(partial, ks, ntaps, cout, cin, dw, 0);
+  }
+  if (db) {
+    const long long rows = g.total();
+    const int rpb = (int)((rows + 1023) / 1024);
+    const int nblk = (int)((rows + rpb - 1) / rpb);
+    pw::colsum_stage1_kernel<<<nblk, 256, 8 * cout * sizeof(float), st>>>(yv, rows, yp, 0, cout, colpart, rpb);
+    pw::colsum_stage2_kernel<<<(cout + 127) / 128, 128, 0, st>>>(colpart, nblk, cout, db, 0);
+  }
+  int hflag = 0;
+  SSDN_CUDA(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
+  SSDN_CUDA(cudaStreamSynchronize(st));
+  if (hflag) return fail(-4, "wgrad kernel pipeline timeout (role %d)", hflag);
+  return 0;
+}

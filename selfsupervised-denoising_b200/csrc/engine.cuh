@@ -7,6 +7,7 @@
 
 #include "conv_igemm.cuh"
 #include "pointwise.cuh"
+#include "wgrad_igemm.cuh"
 
 namespace eng {
 

@@ -1,0 +1,262 @@
+// Weight-gradient implicit GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   dW[tap][co][ci] = sum over flat pixels j of  dZ[j][co] * X[j + off_tap][ci]
+//
+// Both operands are padded-flat NHWC tensors (common.cuh), so the reduction (K) dimension is the
+// flat pixel index and both operands are "MN-major" for the tensor core: a smem row is one pixel,
+// 32 channels (128 bytes) wide.  For tf32 the only MN-major shared-memory layout is the 128-byte
+// swizzle with a 32-byte atom (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B / UMMA layout type 1), verified
+// on hardware by csrc/probe/umma_probe.cu, including start addresses shifted by whole pixel rows -
+// which is how the taps of one stencil row share a single staged window of X.
+//   unit  = (128-wide co tile) x (ci block, N <= 96) x (tap group) x (K split)
+//   stage = KC flat pixels of dZ (4 blocks of 32 co) + KC+halo pixels of X (<= 3 blocks of 32 ci)
+// Accumulators [co lane][tap][ci] live in TMEM for the whole K range of the unit; partial results go
+// to a workspace and a second, fixed-order reduction kernel produces dW (deterministic, no atomics).
+// Precision: 3xTF32 as in the forward kernel.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+struct WgradGroup { int row_off; int ntaps; int tap_rel[9]; int tap_id[9]; };
+
+struct WgradParams {
+  long long k_total;
+  int KC, n_kchunks, ksplit, chunks_per_split;
+  int n_co_tiles, cout, cin;
+  int n_ci_blocks, ci_start[4], ci_n[4], ci_nblk[4];
+  int n_groups, ntaps_total;
+  WgradGroup groups[9];
+  int b_rows, stages;
+  uint32_t a_plane_bytes, b_plane_bytes;
+  float* partial;     // [ksplit][ntaps][cout][cin]
+  int* error_flag;
+};
+
+struct WgradPlan {
+  WgradParams p;
+  CUtensorMap dz_v, dz_lo, x_v, x_lo;
+  int grid; size_t smem;
+};
+
+namespace wgradk {
+
+constexpr int kThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM alloc, warps 2..5: epilogue
+constexpr int kMaxStages = 6;
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz_v, const __grid_constant__ CUtensorMap map_dz_lo,
+                   const __grid_constant__ CUtensorMap map_x_v, const __grid_constant__ CUtensorMap map_x_lo,
+                   const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2];
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = umma::smem_u32(smem);
+  const uint32_t stage_bytes = 2 * (p.a_plane_bytes + p.b_plane_bytes);
+  auto full = [&](int s) { return umma::smem_u32(&bars[s]); };
+  auto empty = [&](int s) { return umma::smem_u32(&bars[kMaxStages + s]); };
+  const uint32_t acc_full = umma::smem_u32(&bars[2 * kMaxStages]), acc_empty = umma::smem_u32(&bars[2 * kMaxStages + 1]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full(s), 1); umma::mbar_init(empty(s), 1); }
+    umma::mbar_init(acc_full, 1); umma::mbar_init(acc_empty, 128);
+    umma::fence_mbar_init();
+  }
+  if (warp == 1) { umma::tmem_alloc(umma::smem_u32(&tmem_slot), 512); umma::tmem_relinquish(); }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  const int n_units = p.n_co_tiles * p.n_ci_blocks * p.n_groups * p.ksplit;
+  auto decode = [&](int u, int& ks, int& g, int& cb, int& ct) {
+    ks = u % p.ksplit; u /= p.ksplit; g = u % p.n_groups; u /= p.n_groups; cb = u % p.n_ci_blocks; ct = u / p.n_ci_blocks;
+  };
+  bool ok = true;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x) {
+        int ks, g, cb, ct; decode(u, ks, g, cb, ct);
+        const int c0 = ks * p.chunks_per_split, c1 = min(p.n_kchunks, c0 + p.chunks_per_split);
+        const int nb = p.ci_nblk[cb];
+        const uint32_t a_blk = p.KC * 128, b_blk = p.b_rows * 128;
+        for (int c = c0; c < c1; ++c) {
+          if (!(ok = umma::mbar_wait(empty(stage), phase ^ 1))) break;
+          umma::mbar_expect_tx(full(stage), 2 * (4 * a_blk + nb * b_blk));
+          const uint32_t av = sbase + stage * stage_bytes, al = av + p.a_plane_bytes;
+          const uint32_t bv = al + p.a_plane_bytes, bl = bv + p.b_plane_bytes;
+          const int row = c * p.KC;
+          for (int k = 0; k < 4; ++k) {
+            umma::tma_load_2d(av + k * a_blk, &map_dz_v, full(stage), ct * 128 + k * 32, row);
+            umma::tma_load_2d(al + k * a_blk, &map_dz_lo, full(stage), ct * 128 + k * 32, row);
+          }
+          for (int k = 0; k < nb; ++k) {
+            umma::tma_load_2d(bv + k * b_blk, &map_x_v, full(stage), p.ci_start[cb] + k * 32, row + p.groups[g].row_off);
+            umma::tma_load_2d(bl + k * b_blk, &map_x_lo, full(stage), p.ci_start[cb] + k * 32, row + p.groups[g].row_off);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (!ok) atomicExch(p.error_flag, 11);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x, ++it) {
+        int ks, g, cb, ct; decode(u, ks, g, cb, ct);
+        const int c0 = ks * p.chunks_per_split, c1 = min(p.n_kchunks, c0 + p.chunks_per_split);
+        const int N = p.ci_n[cb];
+        const uint64_t adesc = umma::make_desc_base(p.KC * 128, 512, 1);
+        const uint64_t bdesc = umma::make_desc_base(p.b_rows * 128, 512, 1);
+        const uint32_t idesc = umma::make_idesc_tf32(128, N, 1, 1);
+        if (!(ok = umma::mbar_wait(acc_empty, (it & 1) ^ 1))) break;
+        umma::tc_fence_after();
+        for (int c = c0; c < c1 && ok; ++c) {
+          if (!(ok = umma::mbar_wait(full(stage), phase))) break;
+          umma::tc_fence_after();
+          const uint32_t av = sbase + stage * stage_bytes, al = av + p.a_plane_bytes;
+          const uint32_t bv = al + p.a_plane_bytes, bl = bv + p.b_plane_bytes;
+          for (int t = 0; t < p.groups[g].ntaps; ++t) {
+            const uint32_t d = tmem + t * N;
+            for (int k = 0; k < p.KC / 8; ++k) {
+              const uint32_t ao = k * 8 * 128, bo = (p.groups[g].tap_rel[t] + k * 8) * 128;
+              umma::mma_tf32_ss(d, umma::desc_at(adesc, al + ao), umma::desc_at(bdesc, bv + bo), idesc, !(c == c0 && k == 0));
+              umma::mma_tf32_ss(d, umma::desc_at(adesc, av + ao), umma::desc_at(bdesc, bl + bo), idesc, 1);
+              umma::mma_tf32_ss(d, umma::desc_at(adesc, av + ao), umma::desc_at(bdesc, bv + bo), idesc, 1);
+            }
+          }
+          umma::mma_commit(empty(stage));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma::mma_commit(acc_full);
+      }
+      if (!ok) atomicExch(p.error_flag, 12);
+    }
+  } else {
+    const int ew = warp & 3;   // TMEM sub-partition of this warp (warps 2,3,4,5 -> 2,3,0,1)
+    int it = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+      int ks, g, cb, ct; decode(u, ks, g, cb, ct);
+      const int N = p.ci_n[cb];
+      if (!umma::mbar_wait(acc_full, it & 1)) ok = false;
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) { if (lane == 0) atomicExch(p.error_flag, 13); break; }
+      umma::tc_fence_after();
+      const int co = ct * 128 + ew * 32 + lane;
+      for (int t = 0; t < p.groups[g].ntaps; ++t) {
+        const int tap = p.groups[g].tap_id[t];
+        float* dst = p.partial + (((long long)ks * p.ntaps_total + tap) * p.cout + co) * p.cin + p.ci_start[cb];
+        for (int n0 = 0; n0 < N; n0 += 16) {
+          uint32_t r[16];
+          umma::tmem_ld16(tmem + (uint32_t(ew * 32) << 16) + t * N + n0, r);
+          umma::tmem_ld_wait();
+          if (co < p.cout) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (p.ci_start[cb] + n0 + i < p.cin) dst[n0 + i] = __uint_as_float(r[i]);
+          }
+        }
+      }
+      umma::tc_fence_before();
+      umma::mbar_arrive(acc_empty);
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
+// dW[co][ci][tap] (PyTorch layout) = (accumulate ? dW : 0) + sum_ks partial[ks][tap][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int ksplit, int ntaps, int cout, int cin,
+                                    float* __restrict__ dw, int accumulate) {
+  const long long n = (long long)cout * cin * ntaps;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // over [tap][co][ci] (coalesced reads)
+  if (idx >= n) return;
+  const int ci = (int)(idx % cin); long long t = idx / cin;
+  const int co = (int)(t % cout); const int tap = (int)(t / cout);
+  float acc = 0.f;
+  for (int k = 0; k < ksplit; ++k) acc += partial[(long long)k * n + idx];
+  const long long o = ((long long)co * cin + ci) * ntaps + tap;
+  dw[o] = accumulate ? dw[o] + acc : acc;
+}
+
+}  // namespace wgradk
+
+// ------------------------------------------------------------------------------------------ host
+#include <algorithm>
+
+static inline size_t wgrad_partial_floats(int ksplit, int ntaps, int cout, int cin) {
+  return (size_t)ksplit * ntaps * cout * cin;
+}
+
+// Decides the K split for a layer (so that the grid fills the chip) without needing pointers.
+static inline int wgrad_pick_ksplit(long long k_total, int cout, int cin, int ntaps, int num_sms, int KC = 32) {
+  const int n_kchunks = (int)((k_total + KC - 1) / KC);
+  const int n_co_tiles = (cout + 127) / 128, n_ci_blocks = (cin + 95) / 96, n_groups = ntaps == 9 ? 3 : ntaps;
+  const int others = n_co_tiles * n_ci_blocks * n_groups;
+  int ks = std::max(1, (2 * num_sms + others - 1) / others);
+  ks = std::min(ks, std::max(1, n_kchunks / 4));
+  ks = std::max(1, std::min(ks, n_kchunks));
+  const int cps = (n_kchunks + ks - 1) / ks;      // no K split may be empty: its accumulator would be undefined
+  return (n_kchunks + cps - 1) / cps;
+}
+
+// taps: flat offsets of X relative to dZ for each weight tap (the FORWARD offsets of the conv).
+static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const float* dz_v, const float* dz_lo, int dz_cpitch,
+                                  int dz_coff, int cout, const float* x_v, const float* x_lo, int x_cpitch, int x_coff,
+                                  int cin, const ConvTaps& taps, int ksplit, float* partial, int* error_flag, int num_sms) {
+  WgradParams& p = plan->p;
+  p = WgradParams{};
+  p.k_total = k_total; p.KC = 32; p.n_kchunks = (int)((k_total + p.KC - 1) / p.KC);
+  p.ksplit = ksplit; p.chunks_per_split = (p.n_kchunks + ksplit - 1) / ksplit;
+  p.cout = cout; p.cin = cin; p.n_co_tiles = (cout + 127) / 128;
+  p.n_ci_blocks = 0;
+  for (int c = 0; c < cin; c += 96) {
+    const int rem = std::min(96, cin - c);
+    p.ci_start[p.n_ci_blocks] = c; p.ci_n[p.n_ci_blocks] = (rem + 15) / 16 * 16; p.ci_nblk[p.n_ci_blocks] = (rem + 31) / 32;
+    ++p.n_ci_blocks;
+  }
+  p.ntaps_total = taps.n;
+  int span = 0;
+  if (taps.n == 9) {
+    p.n_groups = 3;
+    for (int g = 0; g < 3; ++g) {
+      int lo = std::min({taps.off[3 * g], taps.off[3 * g + 1], taps.off[3 * g + 2]});
+      p.groups[g].row_off = lo; p.groups[g].ntaps = 3;
+      for (int k = 0; k < 3; ++k) { p.groups[g].tap_id[k] = 3 * g + k; p.groups[g].tap_rel[k] = taps.off[3 * g + k] - lo; span = std::max(span, taps.off[3 * g + k] - lo); }
+    }
+  } else {
+    p.n_groups = taps.n;
+    for (int g = 0; g < taps.n; ++g) { p.groups[g].row_off = taps.off[g]; p.groups[g].ntaps = 1; p.groups[g].tap_id[0] = g; p.groups[g].tap_rel[0] = 0; }
+  }
+  p.b_rows = (p.KC + span + 7) / 8 * 8;
+  p.a_plane_bytes = 4 * p.KC * 128;
+  p.b_plane_bytes = (uint32_t)((3 * p.b_rows * 128 + 1023) / 1024 * 1024);
+  const uint32_t stage_bytes = 2 * (p.a_plane_bytes + p.b_plane_bytes);
+  p.stages = std::min(4, (int)((200 * 1024) / stage_bytes));
+  plan->smem = (size_t)p.stages * stage_bytes + 1024;
+  p.partial = partial; p.error_flag = error_flag;
+  plan->grid = std::min(p.n_co_tiles * p.n_ci_blocks * p.n_groups * p.ksplit, num_sms);
+  uint64_t d1[2] = {(uint64_t)cout, (uint64_t)k_total}; uint64_t s1[1] = {(uint64_t)dz_cpitch * 4}; uint32_t b1[2] = {32, (uint32_t)p.KC};
+  uint64_t d2[2] = {(uint64_t)cin, (uint64_t)k_total}; uint64_t s2[1] = {(uint64_t)x_cpitch * 4}; uint32_t b2[2] = {32, (uint32_t)p.b_rows};
+  int r;
+  if ((r = umma::encode_f32(&plan->dz_v, (void*)(dz_v + dz_coff), 2, d1, s1, b1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
+  if ((r = umma::encode_f32(&plan->dz_lo, (void*)(dz_lo + dz_coff), 2, d1, s1, b1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
+  if ((r = umma::encode_f32(&plan->x_v, (void*)(x_v + x_coff), 2, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
+  if ((r = umma::encode_f32(&plan->x_lo, (void*)(x_lo + x_coff), 2, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
+  return 0;
+}
+
+static inline cudaError_t wgrad_launch(const WgradPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgradk::wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  wgradk::wgrad_igemm_kernel<<<plan.grid, wgradk::kThreads, plan.smem, stream>>>(plan.dz_v, plan.dz_lo, plan.x_v, plan.x_lo, plan.p);
+  return cudaGetLastError();
+}

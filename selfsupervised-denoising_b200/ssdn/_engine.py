@@ -28,6 +28,7 @@ def lib() -> ctypes.CDLL:
         L = ctypes.CDLL(LIB_PATH)
         L.ssdn_b200_last_error.restype = ctypes.c_char_p
         L.ssdn_conv2d_workspace_bytes.restype = ctypes.c_size_t
+        L.ssdn_conv2d_backward_weight_workspace_bytes.restype = ctypes.c_size_t
         _lib = L
     return _lib
 
@@ -83,3 +84,16 @@ def conv2d_backward_data(dy, w, blind=True):
     check(lib().ssdn_conv2d_backward_data(_ptr(ws), ctypes.c_size_t(ws.numel()), _ptr(dy.contiguous()), _ptr(w.contiguous()),
                                           _ptr(dx), n, cin, h, wd, cout, k, int(blind), _stream()))
     return dx
+
+
+def conv2d_backward_weight(x, dy, ksize, blind=True):
+    _require_cuda(x, dy)
+    n, cin, h, wd = x.shape
+    cout = dy.shape[1]
+    dw = torch.empty(cout, cin, ksize, ksize, device=x.device, dtype=torch.float32)
+    db = torch.empty(cout, device=x.device, dtype=torch.float32)
+    nb = lib().ssdn_conv2d_backward_weight_workspace_bytes(n, cin, h, wd, cout, ksize)
+    ws = _workspace(nb, x.device)
+    check(lib().ssdn_conv2d_backward_weight(_ptr(ws), ctypes.c_size_t(ws.numel()), _ptr(x.contiguous()), _ptr(dy.contiguous()),
+                                            _ptr(dw), _ptr(db), n, cin, h, wd, cout, ksize, int(blind), _stream()))
+    return dw, db

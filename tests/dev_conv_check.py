@@ -26,8 +26,12 @@ for (n, cin, h, w, cout, k, blind) in cases:
     yo.backward(dy.double())
     dx = E.conv2d_backward_data(dy.cuda(), wt.cuda(), blind=blind).cpu()
     e2 = rel(dx, xg.grad.float())
-    ok = e < 2e-5 and e2 < 2e-5
+    wg = wt.double().requires_grad_(True); bg = b.double().requires_grad_(True)
+    (O.shift_conv2d if blind else O.conv2d_same)(x.double(), wg, bg).backward(dy.double())
+    dw, db = E.conv2d_backward_weight(x.cuda(), dy.cuda(), k, blind=blind)
+    e3 = rel(dw.cpu(), wg.grad.float()); e4 = rel(db.cpu(), bg.grad.float())
+    ok = e < 2e-5 and e2 < 2e-5 and e3 < 2e-5 and e4 < 2e-5
     bad += (not ok)
-    print(f"n{n} cin{cin} {h}x{w} cout{cout} k{k} blind{int(blind)}: fwd rel {e:.2e}  dgrad rel {e2:.2e}  {'OK' if ok else 'FAIL'}  ({time.time()-t0:.2f}s)", flush=True)
+    print(f"n{n} cin{cin} {h}x{w} cout{cout} k{k} blind{int(blind)}: fwd rel {e:.2e}  dgrad rel {e2:.2e}  wgrad rel {e3:.2e}  bgrad rel {e4:.2e}  {'OK' if ok else 'FAIL'}  ({time.time()-t0:.2f}s)", flush=True)
 print("FAILED" if bad else "ALL OK")
 sys.exit(1 if bad else 0)
