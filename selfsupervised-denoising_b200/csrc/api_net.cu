@@ -1,0 +1,210 @@
+// C-ABI: whole-network forward/backward, pipeline losses, index operators, flat Adam.
+// Everything here is asynchronous on `stream` unless noted.  See include/ssdn_b200.h.
+#include "loss.cuh"
+#include "net.cuh"
+#include "../../include/ssdn_b200.h"
+
+using namespace eng;
+
+// ------------------------------------------------------------------------------------ network
+extern "C" int ssdn_net_create(int n, int cin, int cout, int h, int w, int blindspot, void** handle) {
+  if (!handle) return fail(-1, "null handle");
+  if (n <= 0 || cin <= 0 || cout <= 0) return fail(-1, "bad batch/channel count");
+  if (h % 32 || w % 32 || h <= 0 || w <= 0) return fail(-1, "input height and width must be positive multiples of 32 (got %dx%d)", h, w);
+  if (blindspot && h != w) return fail(-1, "blind-spot network needs square inputs (got %dx%d)", h, w);
+  if (cin > 16 || cout > 16) return fail(-1, "at most 16 image channels are supported");
+  *handle = new net::Net(n, cin, cout, h, w, blindspot != 0, num_sms());
+  return 0;
+}
+extern "C" void ssdn_net_destroy(void* handle) { delete (net::Net*)handle; }
+extern "C" size_t ssdn_net_workspace_bytes(void* handle) { return ((net::Net*)handle)->ws_bytes; }
+extern "C" size_t ssdn_net_param_count(void* handle) { return ((net::Net*)handle)->n_params; }
+extern "C" int ssdn_net_bind(void* handle, void* ws, size_t bytes, void* stream) {
+  return ((net::Net*)handle)->bind(ws, bytes, (cudaStream_t)stream);
+}
+extern "C" int ssdn_net_forward(void* handle, const float* params, const float* x, float* out, int training, void* stream) {
+  return ((net::Net*)handle)->forward(params, x, out, (cudaStream_t)stream, training != 0);
+}
+extern "C" int ssdn_net_backward(void* handle, const float* params, const float* dout, float* grads, void* stream) {
+  return ((net::Net*)handle)->backward(params, dout, grads, (cudaStream_t)stream);
+}
+// Synchronises the stream and reports device-side pipeline errors (bounded mbarrier waits that expired).
+extern "C" int ssdn_net_check(void* handle, void* stream) {
+  net::Net* nn = (net::Net*)handle;
+  if (!nn->ws) return fail(-5, "network workspace not bound");
+  int h = 0;
+  SSDN_CUDA(cudaMemcpyAsync(&h, nn->flag, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  SSDN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (h) return fail(-4, "kernel pipeline timeout (role %d)", h);
+  return 0;
+}
+// Debug/test helper: copies channels [0, c) of a named internal buffer (plane 0 = v, 1 = lo) into a dense
+// NCHW tensor [B][c][H][W] of that buffer's own geometry.  Returns B*H*W*c through *count when out == NULL.
+extern "C" int ssdn_net_debug_read(void* handle, const char* name, int plane, int c, float* out, int* dims, void* stream) {
+  net::Net* nn = (net::Net*)handle;
+  const net::Buf* b = nn->find_buf(name);
+  if (!b) return fail(-1, "unknown buffer '%s'", name);
+  if (plane == 1 && !b->lo) return fail(-1, "buffer '%s' has no lo plane", name);
+  if (c > b->cpitch) return fail(-1, "buffer '%s' has only %d channels", name, b->cpitch);
+  if (dims) { dims[0] = b->g.B; dims[1] = c; dims[2] = b->g.H; dims[3] = b->g.W; }
+  if (!out) return 0;
+  const long long n = (long long)b->g.B * c * b->g.H * b->g.W;
+  pw::unpack_nchw_kernel<<<pw::grid_for(n), pw::kBlock, 0, (cudaStream_t)stream>>>(plane ? b->lo : b->v, out, b->g.B, c, b->g.H, b->g.W, b->g,
+                                                                                 b->cpitch, 0);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+// Test helper: overwrites channels [0, c) of a named internal buffer (both planes) from a dense NCHW tensor
+// [B][c][H][W].  Used by the parity tests to run the backward pass on the oracle's forward activations.
+extern "C" int ssdn_net_debug_write(void* handle, const char* name, int c, const float* src, void* stream) {
+  net::Net* nn = (net::Net*)handle;
+  net::Buf* b = const_cast<net::Buf*>(nn->find_buf(name));
+  if (!b) return fail(-1, "unknown buffer '%s'", name);
+  if (c > b->cpitch) return fail(-1, "buffer '%s' has only %d channels", name, b->cpitch);
+  const long long n = (long long)b->g.B * c * b->g.H * b->g.W;
+  pw::pack_nchw_kernel<<<pw::grid_for(n), pw::kBlock, 0, (cudaStream_t)stream>>>(src, b->v, b->lo, b->g.B, c, b->g.H, b->g.W, b->g, b->cpitch, 0, 0);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int ssdn_net_kernel_launches(void* handle, int training) {
+  net::Net* nn = (net::Net*)handle;
+  int fwd = (int)nn->layers.size() /*conv*/ + 5 /*pool*/ + 1 /*pack*/ + (int)nn->layers.size() * (training ? 2 : 1) - (training ? 1 : 0);
+  int bwd = 1 + (int)nn->layers.size() * 4 /*wgrad, reduce, colsum x2*/ + ((int)nn->layers.size() - 1) /*dgrad*/ + 5 + 5;
+  return training ? fwd + bwd : fwd;
+}
+
+// ------------------------------------------------------------------------------------ index operators (standalone)
+namespace {
+__global__ void rot4_stack_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int H, int W) {
+  const long long n = 4LL * B * C * H * W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int j = (int)(idx % W); long long t = idx / W;
+  const int i = (int)(t % H); t /= H;
+  const int c = (int)(t % C); const int bo = (int)(t / C);
+  const int r = bo / B, b = bo % B;
+  int si = i, sj = j;
+  if (r == 1) { si = j; sj = W - 1 - i; } else if (r == 2) { si = H - 1 - i; sj = W - 1 - j; } else if (r == 3) { si = H - 1 - j; sj = i; }
+  y[idx] = x[(((long long)b * C + c) * H + si) * W + sj];
+}
+// y[n, r*C + c, i, j] = rotate(shift_down_1(x[r*N + n]), inv_angle_r)[c, i, j]
+__global__ void shift_unrot_concat_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int C, int H, int W) {
+  const long long n = 4LL * N * C * H * W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int j = (int)(idx % W); long long t = idx / W;
+  const int i = (int)(t % H); t /= H;
+  const int cc = (int)(t % (4 * C)); const int b = (int)(t / (4 * C));
+  const int r = cc / C, c = cc % C;
+  int p, q;   // position in the shifted branch image
+  if (r == 0) { p = i; q = j; } else if (r == 1) { p = H - 1 - j; q = i; } else if (r == 2) { p = H - 1 - i; q = W - 1 - j; } else { p = j; q = W - 1 - i; }
+  y[idx] = p == 0 ? 0.f : x[((((long long)r * N + b) * C + c) * H + (p - 1)) * W + q];
+}
+}  // namespace
+
+extern "C" int ssdn_rot4_stack(const float* x, float* y, int n, int c, int h, int w, void* stream) {
+  if (h != w) return fail(-1, "rot4_stack needs square images");
+  rot4_stack_kernel<<<pw::grid_for(4LL * n * c * h * w), pw::kBlock, 0, (cudaStream_t)stream>>>(x, y, n, c, h, w);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int ssdn_shift_unrot_concat(const float* x, float* y, int n, int c, int h, int w, void* stream) {
+  if (h != w) return fail(-1, "shift_unrot_concat needs square images");
+  shift_unrot_concat_kernel<<<pw::grid_for(4LL * n * c * h * w), pw::kBlock, 0, (cudaStream_t)stream>>>(x, y, n, c, h, w);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ losses
+static inline int loss_blocks(int hw) { int b = (hw + 511) / 512; return b < 1 ? 1 : (b > 64 ? 64 : b); }
+
+extern "C" size_t ssdn_loss_workspace_bytes(int n, int c) { return (size_t)n * 64 * 4 * sizeof(float) + (size_t)n * c * sizeof(float) + 1024; }
+
+extern "C" int ssdn_posterior_forward(void* ws, const float* net_out, const float* noisy, const float* sigma_raw, int n, int c, int h,
+                                      int w, int cs, int sigma_known, float* pme, float* loss, float* model_std, float* noise_std,
+                                      void* stream) {
+  if (c != 1 && c != 3) return fail(-1, "num_channels must be 1 or 3");
+  if (cs != 1 && cs != c) return fail(-1, "sigma must have 1 or C values per sample");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int hw = h * w, nblk = loss_blocks(hw);
+  float* partial = (float*)ws;
+  dim3 grid(nblk, n);
+  if (c == 1) lossk::posterior_fwd_kernel<1><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, hw, pme, model_std, partial);
+  else lossk::posterior_fwd_kernel<3><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, hw, pme, model_std, partial);
+  lossk::posterior_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, nblk, hw, sigma_raw, cs, sigma_known, c, n, loss, noise_std);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ssdn_posterior_backward(void* ws, const float* net_out, const float* noisy, const float* sigma_raw, const float* gloss,
+                                       int n, int c, int h, int w, int cs, int sigma_known, float* dnet, float* dsigma_raw, void* stream) {
+  if (c != 1 && c != 3) return fail(-1, "num_channels must be 1 or 3");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int hw = h * w, nblk = loss_blocks(hw);
+  float* partial = (float*)ws;
+  dim3 grid(nblk, n);
+  float* dp = (dsigma_raw && !sigma_known) ? partial : nullptr;
+  if (c == 1) lossk::posterior_bwd_kernel<1><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, hw, gloss, dnet, dp);
+  else lossk::posterior_bwd_kernel<3><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, hw, gloss, dnet, dp);
+  if (dp) lossk::posterior_bwd_finalize_kernel<<<(n * cs + 127) / 128, 128, 0, st>>>(partial, nblk, sigma_raw, cs, c, n, gloss, dsigma_raw);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ssdn_spatial_mean_forward(const float* x, int rows, int hw, float* out, void* stream) {
+  lossk::spatial_mean_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, hw, out);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int ssdn_spatial_mean_backward(const float* g, int rows, int hw, float* dx, void* stream) {
+  const long long total = (long long)rows * hw;
+  lossk::spatial_mean_bwd_kernel<<<pw::grid_for(total), pw::kBlock, 0, (cudaStream_t)stream>>>(g, hw, total, dx);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ssdn_mse_forward(void* ws, const float* a, const float* b, int n, int chw, float* loss, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = loss_blocks(chw);
+  dim3 grid(nblk, n);
+  lossk::mse_fwd_kernel<<<grid, lossk::kBlock, 0, st>>>(a, b, chw, (float*)ws);
+  lossk::mean_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>((float*)ws, nblk, (float)chw, n, loss);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int ssdn_mse_backward(const float* a, const float* b, const float* gloss, int n, int chw, float* da, void* stream) {
+  const long long total = (long long)n * chw;
+  lossk::mse_bwd_kernel<<<pw::grid_for(total), pw::kBlock, 0, (cudaStream_t)stream>>>(a, b, gloss, chw, total, da);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ssdn_masked_mse_forward(void* ws, const float* out, const float* ref, const long long* coords, int k, int n, int c, int h,
+                                       int w, float* loss, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  float* per_nc = (float*)ws;
+  lossk::masked_mse_fwd_kernel<<<(n * c + 127) / 128, 128, 0, st>>>(out, ref, coords, k, n * c, h, w, per_nc);
+  lossk::masked_mse_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(per_nc, n, c, loss);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int ssdn_masked_mse_backward(const float* out, const float* ref, const long long* coords, int k, const float* gloss, int n,
+                                        int c, int h, int w, float* dout, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SSDN_CUDA(cudaMemsetAsync(dout, 0, (size_t)n * c * h * w * sizeof(float), st));
+  lossk::masked_mse_bwd_kernel<<<(n * c + 127) / 128, 128, 0, st>>>(out, ref, coords, k, n * c, c, h, w, gloss, dout);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ optimiser
+#include <math.h>
+extern "C" int ssdn_adam_step(float* p, const float* g, float* m, float* v, long long count, double lr, double beta1, double beta2,
+                              double eps, long long step, double grad_scale, void* stream) {
+  if (step < 1) return fail(-1, "Adam step count starts at 1");
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  lossk::adam_kernel<<<pw::grid_for(count), pw::kBlock, 0, (cudaStream_t)stream>>>(p, g, m, v, count, (float)(lr / bc1), (float)beta1, (float)beta2,
+                                                                                  (float)eps, (float)sqrt(bc2), (float)grad_scale);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -52,7 +52,8 @@ enum : int {
   EP_BIAS = 1,        // add bias[c]
   EP_LRELU = 2,       // LeakyReLU(0.1)
   EP_ACT_GRAD = 4,    // multiply by LeakyReLU'(act) where act is the forward activation at the destination
-  EP_WRITE_LO = 8     // also write the lo plane
+  EP_WRITE_LO = 8,    // also write the lo plane
+  EP_ACT_AT_SRC = 16  // EP_ACT_GRAD reads the activation at the SOURCE pixel / true GEMM channel
 };
 
 struct ConvDst {

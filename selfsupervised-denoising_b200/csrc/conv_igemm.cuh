@@ -56,23 +56,23 @@ struct Ring {
   __device__ void advance() { if (++stage == n) { stage = 0; phase ^= 1; } }
 };
 
-__device__ __forceinline__ void store_pixel(const ConvDst& d, long long dflat, int cbase, const float (&val)[16],
-                                            bool write_zero) {
-  // cbase: first channel (within the conv's output channels) of the 16 values
+// Writes 16 consecutive output channels [cbase, cbase+16) of one destination pixel.
+//   act_index: flat float index of the forward activation for channel cbase (EP_ACT_GRAD), else unused.
+__device__ __forceinline__ void store_pixel(const ConvDst& d, long long dflat, int coff, int cbase, long long act_index,
+                                            const float (&val)[16], bool write_zero) {
   float out[16];
   const bool full = (cbase + 16 <= d.cvalid);
-  const long long abase = dflat * d.act_cpitch + d.act_coff + cbase;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float x = val[i];
     if (d.flags & EP_ACT_GRAD) {
-      float a = (full || cbase + i < d.cvalid) ? __ldg(d.act + abase + i) : 1.f;
+      float a = (full || cbase + i < d.cvalid) ? __ldg(d.act + act_index + i) : 1.f;
       x = a > 0.f ? x : SSDN_LRELU_SLOPE * x;
     }
     out[i] = write_zero ? 0.f : x;
   }
-  float* pv = d.v + dflat * d.cpitch + d.coff + cbase;
-  float* pl = d.lo + dflat * d.cpitch + d.coff + cbase;
+  float* pv = d.v + dflat * d.cpitch + coff + cbase;
+  float* pl = d.lo + dflat * d.cpitch + coff + cbase;
   if (full) {
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
@@ -288,8 +288,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_v, const __grid_cons
               if (cg + i < d.cvalid)
                 d.v[(((long long)b * d.cvalid + cg + i) * sg.H + y) * sg.W + x] = val[i];
           } else {
-            ConvDst dd = d; dd.coff = d.coff + cshift;
-            for (int k = 0; k < ndst; ++k) store_pixel(dd, dflat[k], cg, val, zero);
+            for (int k = 0; k < ndst; ++k) {
+              // forward activation for the LeakyReLU' mask: at the destination pixel, or (EP_ACT_AT_SRC) at the
+              // source pixel with the GEMM's true output channel (head input holds the un-rotated branch outputs)
+              const long long ai = (d.flags & EP_ACT_AT_SRC) ? j * d.act_cpitch + d.act_coff + nt * p.N + c0
+                                                             : dflat[k] * d.act_cpitch + d.act_coff + cg;
+              store_pixel(d, dflat[k], d.coff + cshift, cg, ai, val, zero);
+            }
           }
         }
       }

@@ -1,0 +1,387 @@
+// The blind-spot / plain U-Net of the reference (ssdn/ssdn/models/noise_network.py:48-226) as a
+// static plan of kernel launches over one caller-owned workspace.
+//
+// Concatenations, nearest-neighbour upsampling, the final Shift2d + un-rotate + channel concat and
+// their backward counterparts are never separate passes: every producer writes straight into the
+// (strided) slot of the consumer's concat buffer from its epilogue, and every consumer reads
+// channel-slice views through TMA tensor maps.  See common.cuh for the memory layout.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace net {
+
+using eng::Arena;
+using eng::round_up;
+
+struct Buf {                 // one padded-flat tensor (two planes when lo != nullptr)
+  float* v = nullptr; float* lo = nullptr;
+  Geom g{}; int cpitch = 0;
+  size_t floats() const { return (size_t)g.total() * cpitch; }
+};
+
+struct Layer {               // one convolution of the network
+  std::string name;
+  int cin, cout, ksize;
+  size_t w_off, b_off;       // offsets (floats) into the flat parameter / gradient buffers
+  // forward
+  ConvPlan fwd; float* slab_f_v; float* slab_f_lo; int n_f; int coutp_f;
+  // data gradient (has_dgrad == false for the first conv: nobody consumes d(input))
+  bool has_dgrad = false;
+  ConvPlan dgrad; float* slab_d_v; float* slab_d_lo; int n_d; int cinp_d; int dgrad_nvalid;
+  // weight gradient
+  WgradPlan wgrad; int ksplit;
+  const Buf* x; int x_coff;          // conv input (channel slice [x_coff, x_coff+cin))
+  const Buf* dz;                     // gradient w.r.t. this conv's pre-activation output
+};
+
+struct PoolOp { const Buf* src; const Buf* dst; int dst_coff; };
+struct PoolBwdOp { const Buf* act; const Buf* g1; const Buf* g2; int g2_coff; const Buf* dz; Geom gp; };
+struct UpBwdOp { const Buf* g; const Buf* act_up; const Buf* dz; int C; };
+
+class Net {
+ public:
+  int N, Cin, Cout, H, W; bool blind; int B;      // B = images inside the network (4N when blind)
+  int sms;
+  Geom g[6], gh;                                   // padded geometries of the 6 levels, dense head geometry
+  std::vector<Layer> layers;                       // in PARAMETER order (noise_network.py registration order)
+  size_t n_params = 0;
+  // buffers
+  Buf cat[6], e[6], e1a, p5, d_a[6], head_in, h1, h2;
+  Buf g_out, dz_h2, dz_h1, dz_db[6], dz_da[6], gcat[6], dz_e[7], dz_e1a, g_p[6];
+  float* partial = nullptr; float* colpart = nullptr; int* flag = nullptr;
+  size_t partial_floats = 0;
+  size_t ws_bytes = 0; void* ws = nullptr;
+  std::vector<PoolOp> pools; std::vector<PoolBwdOp> pool_bwds; std::vector<UpBwdOp> up_bwds;
+  int nin;                                         // head width (384 blind, 96 plain)
+
+  Net(int n, int cin, int cout, int h, int w, bool blind_, int sms_) : N(n), Cin(cin), Cout(cout), H(h), W(w), blind(blind_), sms(sms_) {
+    B = blind ? 4 * N : N;
+    nin = blind ? 384 : 96;
+    for (int l = 0; l < 6; ++l) g[l] = make_geom(B, H >> l, W >> l, true);
+    gh = make_geom(N, H, W, false);
+    build_layers();
+    ws_bytes = carve(nullptr, 0);
+  }
+
+  const Buf* find_buf(const std::string& nm) const {
+    auto idx = [&](const char* pre) -> int { return (nm.rfind(pre, 0) == 0 && nm.size() == strlen(pre) + 1) ? nm.back() - '0' : -1; };
+    int i;
+    if (nm == "e1a") return &e1a; if (nm == "p5") return &p5; if (nm == "head_in") return &head_in;
+    if (nm == "h1") return &h1; if (nm == "h2") return &h2; if (nm == "g_out") return &g_out;
+    if (nm == "dz_h2") return &dz_h2; if (nm == "dz_h1") return &dz_h1; if (nm == "dz_e1a") return &dz_e1a;
+    if ((i = idx("cat")) >= 1 && i <= 5) return &cat[i];
+    if ((i = idx("gcat")) >= 1 && i <= 5) return &gcat[i];
+    if ((i = idx("e")) >= 1 && i <= 5) return &e[i];
+    if ((i = idx("d_a")) >= 1 && i <= 5) return &d_a[i];
+    if ((i = idx("dz_db")) >= 1 && i <= 5) return &dz_db[i];
+    if ((i = idx("dz_da")) >= 1 && i <= 5) return &dz_da[i];
+    if ((i = idx("dz_e")) >= 1 && i <= 6) return &dz_e[i];
+    if ((i = idx("g_p")) >= 1 && i <= 5) return &g_p[i];
+    return nullptr;
+  }
+
+  Layer& L(const std::string& name) { for (auto& l : layers) if (l.name == name) return l; return layers[0]; }
+
+  void build_layers() {
+    auto add = [&](const std::string& nm, int ci, int co, int k) {
+      Layer l; l.name = nm; l.cin = ci; l.cout = co; l.ksize = k;
+      l.w_off = n_params; n_params += (size_t)co * ci * k * k;
+      l.b_off = n_params; n_params += co;
+      layers.push_back(l);
+    };
+    add("encode_block_1.0", Cin, 48, 3); add("encode_block_1.2", 48, 48, 3);
+    for (int i = 2; i <= 6; ++i) add("encode_block_" + std::to_string(i) + ".0", 48, 48, 3);
+    add("decode_block_5.0", 96, 96, 3); add("decode_block_5.2", 96, 96, 3);
+    for (int i = 4; i >= 2; --i) { add("decode_block_" + std::to_string(i) + ".0", 144, 96, 3); add("decode_block_" + std::to_string(i) + ".2", 96, 96, 3); }
+    add("decode_block_1.0", 96 + Cin, 96, 3); add("decode_block_1.2", 96, 96, 3);
+    add("output_conv", 96, Cout, 1); add("output_block.0", nin, nin, 1); add("output_block.2", nin, 96, 1);
+  }
+
+  // Lays every buffer out in the workspace; with base == nullptr only measures.
+  size_t carve(void* base, size_t cap) {
+    Arena a(base, cap);
+    auto mk = [&](Buf& b, const Geom& gg, int cp, bool lo) {
+      b.g = gg; b.cpitch = cp;
+      b.v = a.take<float>(b.floats()); b.lo = lo ? a.take<float>(b.floats()) : nullptr;
+      if (!lo) b.lo = nullptr;
+    };
+    const int c1 = round_up(96 + Cin, 4);
+    mk(cat[1], g[0], c1, true); mk(e1a, g[0], 48, true); mk(e[1], g[0], 48, true);
+    mk(cat[2], g[1], 144, true); mk(e[2], g[1], 48, true);
+    mk(cat[3], g[2], 144, true); mk(e[3], g[2], 48, true);
+    mk(cat[4], g[3], 144, true); mk(e[4], g[3], 48, true);
+    mk(cat[5], g[4], 96, true); mk(e[5], g[4], 48, true);
+    mk(p5, g[5], 48, true);
+    for (int l = 1; l <= 5; ++l) mk(d_a[l], g[l - 1], 96, true);        // dec{l}a output lives at level l-1
+    mk(head_in, gh, nin, true); mk(h1, gh, nin, true); mk(h2, gh, 96, true);
+    // backward
+    mk(g_out, gh, round_up(Cout, 4), true); mk(dz_h2, gh, 96, true); mk(dz_h1, gh, nin, true);
+    for (int l = 1; l <= 5; ++l) { mk(dz_db[l], g[l - 1], 96, true); mk(dz_da[l], g[l - 1], 96, true); }
+    mk(gcat[1], g[0], 96, false);
+    for (int l = 2; l <= 4; ++l) mk(gcat[l], g[l - 1], 144, false);
+    mk(gcat[5], g[4], 96, false);
+    for (int l = 1; l <= 5; ++l) mk(dz_e[l], g[l - 1], 48, true);       // dZ of the conv that feeds pool l
+    mk(dz_e[6], g[5], 48, true); mk(dz_e1a, g[0], 48, true);
+    for (int l = 1; l <= 5; ++l) mk(g_p[l], g[l], 48, false);           // d(pool l) coming from the next encoder conv
+    // weight slabs
+    for (auto& l : layers) {
+      const int nt = l.ksize * l.ksize;
+      l.coutp_f = round_up(l.cout, 16);
+      l.n_f = (l.cout == 384) ? 96 : eng::pick_n(l.coutp_f);
+      size_t f = conv_weight_slab_floats(l.cin, l.coutp_f, nt);
+      l.slab_f_v = a.take<float>(f); l.slab_f_lo = a.take<float>(f);
+      l.has_dgrad = (l.name != "encode_block_1.0");
+      l.dgrad_nvalid = (l.name == "decode_block_1.0") ? 96 : l.cin;       // d(x) part of the last concat is never used
+      l.cinp_d = round_up(l.dgrad_nvalid, 16);
+      l.n_d = (l.cinp_d == 384) ? 96 : eng::pick_n(l.cinp_d);
+      if (l.cinp_d == 144) l.n_d = 144;   // one N=144 tile (T = 1) instead of three smem-bound N=48 tiles
+      size_t fd = conv_weight_slab_floats(l.cout, l.cinp_d, nt);
+      l.slab_d_v = a.take<float>(fd); l.slab_d_lo = a.take<float>(fd);
+    }
+    // wgrad partials: one buffer, sized for the largest layer
+    partial_floats = 0;
+    for (auto& l : layers) {
+      const Geom& gg = (l.ksize == 1) ? gh : g[level_of(l.name)];
+      l.ksplit = wgrad_pick_ksplit(gg.total(), l.cout, l.cin, l.ksize * l.ksize, sms);
+      partial_floats = std::max(partial_floats, wgrad_partial_floats(l.ksplit, l.ksize * l.ksize, l.cout, l.cin));
+    }
+    partial = a.take<float>(partial_floats);
+    colpart = a.take<float>((size_t)1024 * 384);
+    flag = a.take<int>(64);
+    return a.off;
+  }
+
+  int level_of(const std::string& nm) const {   // spatial level (0 = full resolution) at which a 3x3 conv runs
+    if (nm.rfind("encode_block_", 0) == 0) return nm[13] - '1';
+    if (nm.rfind("decode_block_", 0) == 0) return nm[13] - '1';
+    return 0;
+  }
+
+  // ------------------------------------------------------------------ plan construction
+  int bind(void* workspace, size_t bytes, cudaStream_t st) {
+    if (bytes < ws_bytes) return eng::fail(-3, "workspace too small: need %zu bytes, have %zu", ws_bytes, bytes);
+    ws = workspace;
+    carve(workspace, bytes);
+    cudaError_t ce = cudaMemsetAsync(workspace, 0, ws_bytes, st);   // zero halos (never written afterwards)
+    if (ce != cudaSuccess) return eng::fail(-2, "memset failed: %s", cudaGetErrorString(ce));
+    pools.clear(); pool_bwds.clear(); up_bwds.clear();
+    int r;
+    const int act = EP_BIAS | EP_LRELU | EP_WRITE_LO;
+    // ---- encoder
+    if ((r = plan_fwd(L("encode_block_1.0"), cat[1], 96, dst(e1a, 0, MAP_IDENT, act, 48)))) return r;
+    if ((r = plan_fwd(L("encode_block_1.2"), e1a, 0, dst(e[1], 0, MAP_IDENT, act, 48)))) return r;
+    pools.push_back({&e[1], &cat[2], 96});
+    for (int i = 2; i <= 4; ++i) {
+      if ((r = plan_fwd(L("encode_block_" + std::to_string(i) + ".0"), cat[i], 96, dst(e[i], 0, MAP_IDENT, act, 48)))) return r;
+      pools.push_back({&e[i], &cat[i + 1], i == 4 ? 48 : 96});
+    }
+    if ((r = plan_fwd(L("encode_block_5.0"), cat[5], 48, dst(e[5], 0, MAP_IDENT, act, 48)))) return r;
+    pools.push_back({&e[5], &p5, 0});
+    if ((r = plan_fwd(L("encode_block_6.0"), p5, 0, dst(cat[5], 0, MAP_UP2, act, 48)))) return r;
+    // ---- decoder
+    for (int i = 5; i >= 1; --i) {
+      const std::string a_nm = "decode_block_" + std::to_string(i) + ".0", b_nm = "decode_block_" + std::to_string(i) + ".2";
+      if ((r = plan_fwd(L(a_nm), cat[i], 0, dst(d_a[i], 0, MAP_IDENT, act, 96)))) return r;
+      ConvDst d2 = (i > 1) ? dst(cat[i - 1], 0, MAP_UP2, act, 96)
+                           : dst(head_in, 0, blind ? MAP_UNROT : MAP_IDENT, act, 96);
+      if ((r = plan_fwd(L(b_nm), d_a[i], 0, d2))) return r;
+    }
+    // ---- head
+    if ((r = plan_fwd(L("output_block.0"), head_in, 0, dst(h1, 0, MAP_IDENT, act, nin)))) return r;
+    if ((r = plan_fwd(L("output_block.2"), h1, 0, dst(h2, 0, MAP_IDENT, act, 96)))) return r;
+    { ConvDst d = dst(h2, 0, MAP_NCHW, EP_BIAS, Cout); d.v = nullptr; d.lo = nullptr; d.g = gh;
+      if ((r = plan_fwd(L("output_conv"), h2, 0, d))) return r; }
+
+    // ---- backward: data gradients
+    const int gact = EP_ACT_GRAD | EP_WRITE_LO;
+    if ((r = plan_dgrad(L("output_conv"), g_out, dst_act(dz_h2, MAP_IDENT, gact, 96, h2, 0)))) return r;
+    if ((r = plan_dgrad(L("output_block.2"), dz_h2, dst_act(dz_h1, MAP_IDENT, gact, nin, h1, 0)))) return r;
+    { ConvDst d = dst_act(dz_db[1], blind ? MAP_UNROT_INV : MAP_IDENT, gact | EP_ACT_AT_SRC, 96, head_in, 0);
+      if ((r = plan_dgrad(L("output_block.0"), dz_h1, d))) return r; }
+    for (int i = 1; i <= 5; ++i) {
+      const std::string a_nm = "decode_block_" + std::to_string(i) + ".0", b_nm = "decode_block_" + std::to_string(i) + ".2";
+      if ((r = plan_dgrad(L(b_nm), dz_db[i], dst_act(dz_da[i], MAP_IDENT, gact, 96, d_a[i], 0)))) return r;
+      if ((r = plan_dgrad(L(a_nm), dz_da[i], dst(gcat[i], 0, MAP_IDENT, 0, L(a_nm).dgrad_nvalid)))) return r;
+      if (i < 5) up_bwds.push_back({&gcat[i], &cat[i], &dz_db[i + 1], 96});
+    }
+    up_bwds.push_back({&gcat[5], &cat[5], &dz_e[6], 48});
+    if ((r = plan_dgrad(L("encode_block_6.0"), dz_e[6], dst(g_p[5], 0, MAP_IDENT, 0, 48)))) return r;
+    for (int i = 5; i >= 2; --i) {
+      // dZ of the conv feeding pool i: gradient from the next encoder conv (+ the skip path for i <= 4)
+      pool_bwds.push_back({&e[i], &g_p[i], i <= 4 ? &gcat[i + 1] : nullptr, i == 4 ? 48 : 96, &dz_e[i], g[i]});
+      if ((r = plan_dgrad(L("encode_block_" + std::to_string(i) + ".0"), dz_e[i], dst(g_p[i - 1], 0, MAP_IDENT, 0, 48)))) return r;
+    }
+    pool_bwds.push_back({&e[1], &g_p[1], &gcat[2], 96, &dz_e[1], g[1]});
+    if ((r = plan_dgrad(L("encode_block_1.2"), dz_e[1], dst_act(dz_e1a, MAP_IDENT, gact, 48, e1a, 0)))) return r;
+
+    // ---- backward: weight gradients
+    struct WG { const char* nm; const Buf* x; int xoff; const Buf* dz; };
+    const WG wg[] = {
+        {"encode_block_1.0", &cat[1], 96, &dz_e1a}, {"encode_block_1.2", &e1a, 0, &dz_e[1]},
+        {"encode_block_2.0", &cat[2], 96, &dz_e[2]}, {"encode_block_3.0", &cat[3], 96, &dz_e[3]},
+        {"encode_block_4.0", &cat[4], 96, &dz_e[4]}, {"encode_block_5.0", &cat[5], 48, &dz_e[5]},
+        {"encode_block_6.0", &p5, 0, &dz_e[6]},
+        {"decode_block_5.0", &cat[5], 0, &dz_da[5]}, {"decode_block_5.2", &d_a[5], 0, &dz_db[5]},
+        {"decode_block_4.0", &cat[4], 0, &dz_da[4]}, {"decode_block_4.2", &d_a[4], 0, &dz_db[4]},
+        {"decode_block_3.0", &cat[3], 0, &dz_da[3]}, {"decode_block_3.2", &d_a[3], 0, &dz_db[3]},
+        {"decode_block_2.0", &cat[2], 0, &dz_da[2]}, {"decode_block_2.2", &d_a[2], 0, &dz_db[2]},
+        {"decode_block_1.0", &cat[1], 0, &dz_da[1]}, {"decode_block_1.2", &d_a[1], 0, &dz_db[1]},
+        {"output_conv", &h2, 0, &g_out}, {"output_block.0", &head_in, 0, &dz_h1}, {"output_block.2", &h1, 0, &dz_h2}};
+    for (const WG& w : wg) {
+      Layer& l = L(w.nm);
+      l.x = w.x; l.x_coff = w.xoff; l.dz = w.dz;
+      const Geom& gg = w.x->g;
+      ConvTaps taps = eng::make_taps(l.ksize, blind, false, gg.P);
+      if ((r = wgrad_plan_init(&l.wgrad, gg.total(), w.dz->v, w.dz->lo, w.dz->cpitch, 0, l.cout, w.x->v, w.x->lo, w.x->cpitch,
+                               w.xoff, l.cin, taps, l.ksplit, partial, flag, sms)))
+        return eng::fail(r, "wgrad plan for %s failed (%d)", w.nm, r);
+    }
+    return 0;
+  }
+
+  ConvDst dst(Buf& b, int coff, int map, int flags, int cvalid) {
+    ConvDst d{}; d.v = b.v; d.lo = b.lo; d.cpitch = b.cpitch; d.coff = coff; d.g = b.g; d.map = map; d.flags = flags;
+    if (!b.lo) d.flags &= ~EP_WRITE_LO;
+    d.cvalid = cvalid; d.nimg = N; d.bias = nullptr; d.act = nullptr; d.act_cpitch = 0; d.act_coff = 0;
+    return d;
+  }
+  ConvDst dst_act(Buf& b, int map, int flags, int cvalid, Buf& act, int act_coff) {
+    ConvDst d = dst(b, 0, map, flags, cvalid); d.act = act.v; d.act_cpitch = act.cpitch; d.act_coff = act_coff; return d;
+  }
+
+  int plan_fwd(Layer& l, Buf& src, int coff, ConvDst d) {
+    ConvTaps taps = eng::make_taps(l.ksize, blind, false, src.g.P);
+    int r = conv_plan_init(&l.fwd, src.g, src.v, src.lo, src.cpitch, coff, l.cin, l.slab_f_v, l.slab_f_lo, l.coutp_f, l.n_f, taps, d,
+                           flag, sms);
+    if (r) return eng::fail(r, "forward plan for %s failed (%d)", l.name.c_str(), r);
+    return 0;
+  }
+  int plan_dgrad(Layer& l, Buf& src, ConvDst d) {
+    ConvTaps taps = eng::make_taps(l.ksize, blind, true, src.g.P);
+    int r = conv_plan_init(&l.dgrad, src.g, src.v, src.lo, src.cpitch, 0, l.cout, l.slab_d_v, l.slab_d_lo, l.cinp_d, l.n_d, taps, d,
+                           flag, sms);
+    if (r) return eng::fail(r, "dgrad plan for %s failed (%d)", l.name.c_str(), r);
+    return 0;
+  }
+
+  // ------------------------------------------------------------------ execution
+  int prep_weights(const float* params, cudaStream_t st, bool with_dgrad) {
+    for (auto& l : layers) {
+      const int nt = l.ksize * l.ksize;
+      int nc, kl; conv_chunks(l.cin, &nc, &kl);
+      long long n1 = (long long)conv_weight_slab_floats(l.cin, l.coutp_f, nt);
+      pw::weight_prep_kernel<<<pw::grid_for(n1), pw::kBlock, 0, st>>>(params + l.w_off, l.slab_f_v, l.slab_f_lo, l.cout, l.cin, nt, l.cout,
+                                                                      l.cin, l.coutp_f / l.n_f, nc, l.n_f, 0);
+      if (with_dgrad && l.has_dgrad) {
+        conv_chunks(l.cout, &nc, &kl);
+        long long n2 = (long long)conv_weight_slab_floats(l.cout, l.cinp_d, nt);
+        pw::weight_prep_kernel<<<pw::grid_for(n2), pw::kBlock, 0, st>>>(params + l.w_off, l.slab_d_v, l.slab_d_lo, l.cout, l.cin, nt,
+                                                                        l.dgrad_nvalid, l.cout, l.cinp_d / l.n_d, nc, l.n_d, 1);
+      }
+    }
+    SSDN_CUDA(cudaGetLastError());
+    return 0;
+  }
+
+  int run_fwd(Layer& l, const float* params, cudaStream_t st, float* nchw_out = nullptr) {
+    l.fwd.p.dst.bias = params + l.b_off;
+    if (nchw_out) l.fwd.p.dst.v = nchw_out;
+    SSDN_CUDA(conv_launch(l.fwd, st));
+    return 0;
+  }
+
+  int forward(const float* params, const float* x, float* out, cudaStream_t st, bool training) {
+    if (!ws) return eng::fail(-5, "network workspace not bound");
+    int r;
+    if ((r = prep_weights(params, st, training))) return r;
+    pw::pack_nchw_kernel<<<pw::grid_for((long long)B * Cin * H * W), pw::kBlock, 0, st>>>(x, cat[1].v, cat[1].lo, N, Cin, H, W, g[0],
+                                                                                          cat[1].cpitch, 96, blind ? 1 : 0);
+    size_t pi = 0;
+    auto pool = [&]() {
+      const PoolOp& p = pools[pi++];
+      const long long n = (long long)p.dst->g.B * p.dst->g.H * p.dst->g.W * 12;
+      pw::pool_fwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(p.src->v, p.src->g, p.src->cpitch, 0, p.dst->v, p.dst->lo, p.dst->g,
+                                                                  p.dst->cpitch, p.dst_coff, 48, blind ? 1 : 0);
+    };
+    if ((r = run_fwd(L("encode_block_1.0"), params, st))) return r;
+    if ((r = run_fwd(L("encode_block_1.2"), params, st))) return r;
+    pool();
+    for (int i = 2; i <= 5; ++i) { if ((r = run_fwd(L("encode_block_" + std::to_string(i) + ".0"), params, st))) return r; pool(); }
+    if ((r = run_fwd(L("encode_block_6.0"), params, st))) return r;
+    for (int i = 5; i >= 1; --i) {
+      if ((r = run_fwd(L("decode_block_" + std::to_string(i) + ".0"), params, st))) return r;
+      if ((r = run_fwd(L("decode_block_" + std::to_string(i) + ".2"), params, st))) return r;
+    }
+    if ((r = run_fwd(L("output_block.0"), params, st))) return r;
+    if ((r = run_fwd(L("output_block.2"), params, st))) return r;
+    if ((r = run_fwd(L("output_conv"), params, st, out))) return r;
+    SSDN_CUDA(cudaGetLastError());
+    return 0;
+  }
+
+  int run_wgrad(Layer& l, float* grads, cudaStream_t st) {
+    const int nt = l.ksize * l.ksize;
+    SSDN_CUDA(wgrad_launch(l.wgrad, st));
+    wgradk::wgrad_reduce_kernel<<<pw::grid_for((long long)l.cout * l.cin * nt), pw::kBlock, 0, st>>>(partial, l.wgrad.p.ksplit, nt, l.cout,
+                                                                                                   l.cin, grads + l.w_off, 0);
+    const long long rows = l.dz->g.total();
+    const int rpb = (int)((rows + 1023) / 1024);
+    const int nblk = (int)((rows + rpb - 1) / rpb);
+    pw::colsum_stage1_kernel<<<nblk, 256, 8 * l.cout * sizeof(float), st>>>(l.dz->v, rows, l.dz->cpitch, 0, l.cout, colpart, rpb);
+    pw::colsum_stage2_kernel<<<(l.cout + 127) / 128, 128, 0, st>>>(colpart, nblk, l.cout, grads + l.b_off, 0);
+    return 0;
+  }
+  int run_dgrad(Layer& l, cudaStream_t st) { SSDN_CUDA(conv_launch(l.dgrad, st)); return 0; }
+
+  // grads: flat buffer with the layout of params; every element is overwritten.
+  int backward(const float* params, const float* dout, float* grads, cudaStream_t st) {
+    if (!ws) return eng::fail(-5, "network workspace not bound");
+    int r;
+    pw::pack_nchw_kernel<<<pw::grid_for((long long)N * Cout * H * W), pw::kBlock, 0, st>>>(dout, g_out.v, g_out.lo, N, Cout, H, W, gh,
+                                                                                           g_out.cpitch, 0, 0);
+    auto both = [&](const std::string& nm, bool dgrad) -> int {
+      Layer& l = L(nm);
+      int rr = run_wgrad(l, grads, st);
+      if (rr) return rr;
+      return dgrad ? run_dgrad(l, st) : 0;
+    };
+    if ((r = both("output_conv", true))) return r;
+    if ((r = both("output_block.2", true))) return r;
+    if ((r = both("output_block.0", true))) return r;
+    size_t ui = 0, qi = 0;
+    auto up_bwd = [&]() {
+      const UpBwdOp& u = up_bwds[ui++];
+      const Geom& gl = u.dz->g;
+      const long long n = (long long)gl.B * gl.H * gl.W * (u.C / 4);
+      pw::up_bwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(u.g->v, u.g->g, u.g->cpitch, 0, u.act_up->v, u.act_up->cpitch, 0, gl, u.dz->v,
+                                                                u.dz->lo, u.dz->cpitch, 0, u.C);
+    };
+    auto pool_bwd = [&]() {
+      const PoolBwdOp& q = pool_bwds[qi++];
+      const long long n = (long long)q.gp.B * q.gp.H * q.gp.W * 48;
+      pw::pool_bwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(q.act->v, q.act->g, q.act->cpitch, 0, q.g1->v, q.g1->cpitch, 0,
+                                                                  q.g2 ? q.g2->v : nullptr, q.g2 ? q.g2->cpitch : 0, q.g2_coff, q.gp, q.dz->v,
+                                                                  q.dz->lo, q.dz->cpitch, 0, 48, blind ? 1 : 0);
+    };
+    for (int i = 1; i <= 5; ++i) {
+      if ((r = both("decode_block_" + std::to_string(i) + ".2", true))) return r;
+      if ((r = both("decode_block_" + std::to_string(i) + ".0", true))) return r;
+      up_bwd();
+    }
+    if ((r = both("encode_block_6.0", true))) return r;
+    for (int i = 5; i >= 2; --i) {
+      pool_bwd();
+      if ((r = both("encode_block_" + std::to_string(i) + ".0", true))) return r;
+    }
+    pool_bwd();
+    if ((r = both("encode_block_1.2", true))) return r;
+    if ((r = both("encode_block_1.0", false))) return r;
+    SSDN_CUDA(cudaGetLastError());
+    return 0;
+  }
+};
+
+}  // namespace net

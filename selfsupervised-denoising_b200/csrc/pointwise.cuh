@@ -108,6 +108,7 @@ __global__ void pool_bwd_kernel(const float* __restrict__ act, Geom ga_, int a_c
 }
 
 // Backward of [LeakyReLU -> nearest 2x upsample]: dZ[b,y,x,c] = LeakyReLU'(act) * sum of the 2x2 block of g.
+// The forward activation is read from its upsampled copy (geometry gg, pixel (2y, 2x)).
 __global__ void up_bwd_kernel(const float* __restrict__ g, Geom gg, int g_cpitch, int g_coff,
                               const float* __restrict__ act, int a_cpitch, int a_coff, Geom gl,
                               float* __restrict__ dv, float* __restrict__ dlo, int d_cpitch, int d_coff, int C) {
@@ -124,7 +125,8 @@ __global__ void up_bwd_kernel(const float* __restrict__ g, Geom gg, int g_cpitch
   const float4 cq = *reinterpret_cast<const float4*>(g + s0 + (long long)gg.P * g_cpitch);
   const float4 dq = *reinterpret_cast<const float4*>(g + s0 + (long long)(gg.P + 1) * g_cpitch);
   const long long lf = (long long)b * gl.S + (y + gl.row0) * gl.P + x;
-  const float4 av = *reinterpret_cast<const float4*>(act + lf * a_cpitch + a_coff + c);
+  const float4 av = *reinterpret_cast<const float4*>(
+      act + ((long long)b * gg.S + (2 * y + gg.row0) * gg.P + 2 * x) * a_cpitch + a_coff + c);
   float4 s;
   s.x = (a.x + bq.x) + (cq.x + dq.x); s.y = (a.y + bq.y) + (cq.y + dq.y);
   s.z = (a.z + bq.z) + (cq.z + dq.z); s.w = (a.w + bq.w) + (cq.w + dq.w);

@@ -1,17 +1,54 @@
 """ctypes binding of libssdn_b200.so (the C-ABI of the CUDA engine, include/ssdn_b200.h).
 
-PyTorch is used for device memory and streams only.  There is no CPU fallback: if the shared
-library is missing or a CUDA device is absent, every operator raises."""
+PyTorch is used for device memory, streams and autograd bookkeeping only.  There is no CPU
+fallback: if the shared library is missing or a tensor is not on a CUDA device, every operator raises."""
 from __future__ import annotations
 
 import ctypes
 import os
+from ctypes import c_double, c_int, c_longlong, c_size_t, c_void_p
 
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libssdn_b200.so")
 _lib = None
+
+_P, _I, _Z, _LL, _D = c_void_p, c_int, c_size_t, c_longlong, c_double
+# name -> (restype, argtypes); mirrors include/ssdn_b200.h
+_SIGNATURES = {
+    "ssdn_b200_last_error": (ctypes.c_char_p, []),
+    "ssdn_b200_version": (_I, []),
+    "ssdn_conv2d_workspace_bytes": (_Z, [_I] * 6),
+    "ssdn_conv2d_forward": (_I, [_P, _Z, _P, _P, _P, _P] + [_I] * 8 + [_P]),
+    "ssdn_conv2d_backward_data": (_I, [_P, _Z, _P, _P, _P] + [_I] * 7 + [_P]),
+    "ssdn_conv2d_backward_weight_workspace_bytes": (_Z, [_I] * 6),
+    "ssdn_conv2d_backward_weight": (_I, [_P, _Z, _P, _P, _P, _P] + [_I] * 7 + [_P]),
+    "ssdn_net_create": (_I, [_I] * 6 + [ctypes.POINTER(c_void_p)]),
+    "ssdn_net_destroy": (None, [_P]),
+    "ssdn_net_workspace_bytes": (_Z, [_P]),
+    "ssdn_net_param_count": (_Z, [_P]),
+    "ssdn_net_bind": (_I, [_P, _P, _Z, _P]),
+    "ssdn_net_forward": (_I, [_P, _P, _P, _P, _I, _P]),
+    "ssdn_net_backward": (_I, [_P, _P, _P, _P, _P]),
+    "ssdn_net_check": (_I, [_P, _P]),
+    "ssdn_net_kernel_launches": (_I, [_P, _I]),
+    "ssdn_net_debug_write": (_I, [_P, ctypes.c_char_p, _I, _P, _P]),
+    "ssdn_net_debug_read": (_I, [_P, ctypes.c_char_p, _I, _I, _P, ctypes.POINTER(c_int), _P]),
+    "ssdn_rot4_stack": (_I, [_P, _P] + [_I] * 4 + [_P]),
+    "ssdn_shift_unrot_concat": (_I, [_P, _P] + [_I] * 4 + [_P]),
+    "ssdn_loss_workspace_bytes": (_Z, [_I, _I]),
+    "ssdn_posterior_forward": (_I, [_P, _P, _P, _P] + [_I] * 6 + [_P, _P, _P, _P, _P]),
+    "ssdn_posterior_backward": (_I, [_P, _P, _P, _P, _P] + [_I] * 6 + [_P, _P, _P]),
+    "ssdn_spatial_mean_forward": (_I, [_P, _I, _I, _P, _P]),
+    "ssdn_spatial_mean_backward": (_I, [_P, _I, _I, _P, _P]),
+    "ssdn_mse_forward": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "ssdn_mse_backward": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "ssdn_masked_mse_forward": (_I, [_P, _P, _P, _P] + [_I] * 5 + [_P, _P]),
+    "ssdn_masked_mse_backward": (_I, [_P, _P, _P, _I, _P] + [_I] * 4 + [_P, _P]),
+    "ssdn_adam_step": (_I, [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _LL, _D, _P]),
+}
+EXPORTS = tuple(_SIGNATURES)
 
 
 class EngineError(RuntimeError):
@@ -26,74 +63,235 @@ def lib() -> ctypes.CDLL:
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(the engine has no CPU or PyTorch fallback)")
         L = ctypes.CDLL(LIB_PATH)
-        L.ssdn_b200_last_error.restype = ctypes.c_char_p
-        L.ssdn_conv2d_workspace_bytes.restype = ctypes.c_size_t
-        L.ssdn_conv2d_backward_weight_workspace_bytes.restype = ctypes.c_size_t
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
 
 
 def check(rc: int):
     if rc != 0:
-        raise EngineError(f"ssdn_b200 error {rc}: {lib().ssdn_b200_last_error().decode()}")
+        msg = lib().ssdn_b200_last_error().decode()
+        if rc == -1:
+            raise ValueError(f"ssdn_b200: {msg}")
+        raise EngineError(f"ssdn_b200 error {rc}: {msg}")
 
 
 def _ptr(t):
     if t is None:
-        return ctypes.c_void_p(0)
-    assert t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.int32, torch.int64, torch.uint8), \
-        "engine tensors must be contiguous CUDA tensors"
-    return ctypes.c_void_p(t.data_ptr())
+        return None
+    if not t.is_cuda:
+        raise EngineError("ssdn_b200 operators need CUDA tensors (no CPU fallback exists)")
+    assert t.is_contiguous(), "engine tensors must be contiguous"
+    return t.data_ptr()
+
+
+def _f32(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise EngineError("ssdn_b200 operators need CUDA tensors (no CPU fallback exists)")
+    return t.detach().contiguous().float()
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-
-def _require_cuda(*ts):
-    for t in ts:
-        if t is not None and not t.is_cuda:
-            raise EngineError("ssdn_b200 operators need CUDA tensors (no CPU fallback exists)")
+    return torch.cuda.current_stream().cuda_stream
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-# ------------------------------------------------------------------------------------ operators
+# ------------------------------------------------------------------------------------ conv operators
 def conv2d_forward(x, w, bias=None, blind=True, lrelu=True):
     """ShiftConv2d / Conv2d (+LeakyReLU 0.1).  x [N,Cin,H,W], w [Cout,Cin,k,k]."""
-    _require_cuda(x, w, bias)
+    x, w, bias = _f32(x), _f32(w), _f32(bias)
     n, cin, h, wd = x.shape
     cout, _, k, _ = w.shape
     y = torch.empty(n, cout, h, wd, device=x.device, dtype=torch.float32)
-    nb = lib().ssdn_conv2d_workspace_bytes(n, cin, h, wd, cout, k)
-    ws = _workspace(nb, x.device)
-    check(lib().ssdn_conv2d_forward(_ptr(ws), ctypes.c_size_t(ws.numel()), _ptr(x.contiguous()), _ptr(w.contiguous()),
-                                    _ptr(bias), _ptr(y), n, cin, h, wd, cout, k, int(blind), int(lrelu), _stream()))
+    ws = _workspace(lib().ssdn_conv2d_workspace_bytes(n, cin, h, wd, cout, k), x.device)
+    check(lib().ssdn_conv2d_forward(_ptr(ws), ws.numel(), _ptr(x), _ptr(w), _ptr(bias), _ptr(y), n, cin, h, wd, cout, k,
+                                    int(blind), int(lrelu), _stream()))
     return y
 
 
 def conv2d_backward_data(dy, w, blind=True):
-    _require_cuda(dy, w)
+    dy, w = _f32(dy), _f32(w)
     n, cout, h, wd = dy.shape
     _, cin, k, _ = w.shape
     dx = torch.empty(n, cin, h, wd, device=dy.device, dtype=torch.float32)
-    nb = lib().ssdn_conv2d_workspace_bytes(n, cin, h, wd, cout, k)
-    ws = _workspace(nb, dy.device)
-    check(lib().ssdn_conv2d_backward_data(_ptr(ws), ctypes.c_size_t(ws.numel()), _ptr(dy.contiguous()), _ptr(w.contiguous()),
-                                          _ptr(dx), n, cin, h, wd, cout, k, int(blind), _stream()))
+    ws = _workspace(lib().ssdn_conv2d_workspace_bytes(n, cin, h, wd, cout, k), dy.device)
+    check(lib().ssdn_conv2d_backward_data(_ptr(ws), ws.numel(), _ptr(dy), _ptr(w), _ptr(dx), n, cin, h, wd, cout, k,
+                                          int(blind), _stream()))
     return dx
 
 
 def conv2d_backward_weight(x, dy, ksize, blind=True):
-    _require_cuda(x, dy)
+    x, dy = _f32(x), _f32(dy)
     n, cin, h, wd = x.shape
     cout = dy.shape[1]
     dw = torch.empty(cout, cin, ksize, ksize, device=x.device, dtype=torch.float32)
     db = torch.empty(cout, device=x.device, dtype=torch.float32)
-    nb = lib().ssdn_conv2d_backward_weight_workspace_bytes(n, cin, h, wd, cout, ksize)
-    ws = _workspace(nb, x.device)
-    check(lib().ssdn_conv2d_backward_weight(_ptr(ws), ctypes.c_size_t(ws.numel()), _ptr(x.contiguous()), _ptr(dy.contiguous()),
-                                            _ptr(dw), _ptr(db), n, cin, h, wd, cout, ksize, int(blind), _stream()))
+    ws = _workspace(lib().ssdn_conv2d_backward_weight_workspace_bytes(n, cin, h, wd, cout, ksize), x.device)
+    check(lib().ssdn_conv2d_backward_weight(_ptr(ws), ws.numel(), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), n, cin, h, wd, cout,
+                                            ksize, int(blind), _stream()))
     return dw, db
+
+
+# ------------------------------------------------------------------------------------ index operators
+def rot4_stack(x):
+    x = _f32(x)
+    n, c, h, w = x.shape
+    y = torch.empty(4 * n, c, h, w, device=x.device, dtype=torch.float32)
+    check(lib().ssdn_rot4_stack(_ptr(x), _ptr(y), n, c, h, w, _stream()))
+    return y
+
+
+def shift_unrot_concat(x):
+    x = _f32(x)
+    b, c, h, w = x.shape
+    assert b % 4 == 0
+    y = torch.empty(b // 4, 4 * c, h, w, device=x.device, dtype=torch.float32)
+    check(lib().ssdn_shift_unrot_concat(_ptr(x), _ptr(y), b // 4, c, h, w, _stream()))
+    return y
+
+
+# ------------------------------------------------------------------------------------ whole network
+class NetPlan:
+    """One U-Net execution plan for a fixed (N, Cin, Cout, H, W, blindspot): owns the workspace."""
+
+    def __init__(self, n, cin, cout, h, w, blindspot, device):
+        self.key = (n, cin, cout, h, w, bool(blindspot))
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise EngineError("the ssdn_b200 network runs on CUDA devices only (no CPU fallback exists)")
+        handle = c_void_p()
+        check(lib().ssdn_net_create(n, cin, cout, h, w, int(blindspot), ctypes.byref(handle)))
+        self.handle = handle
+        self.n_params = lib().ssdn_net_param_count(handle)
+        with torch.cuda.device(self.device):
+            self.ws = _workspace(lib().ssdn_net_workspace_bytes(handle), self.device)
+            check(lib().ssdn_net_bind(handle, _ptr(self.ws), self.ws.numel(), _stream()))
+        self.out_shape = (n, cout, h, w)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().ssdn_net_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def forward(self, flat_params, x, training=True):
+        assert flat_params.numel() == self.n_params and flat_params.dtype == torch.float32
+        out = torch.empty(self.out_shape, device=self.device, dtype=torch.float32)
+        check(lib().ssdn_net_forward(self.handle, _ptr(flat_params), _ptr(x), _ptr(out), int(training), _stream()))
+        return out
+
+    def backward(self, flat_params, dout, grads=None):
+        if grads is None:
+            grads = torch.empty(self.n_params, device=self.device, dtype=torch.float32)
+        check(lib().ssdn_net_backward(self.handle, _ptr(flat_params), _ptr(dout), _ptr(grads), _stream()))
+        return grads
+
+    def check(self):
+        check(lib().ssdn_net_check(self.handle, _stream()))
+
+    def debug_read(self, name, channels, plane=0):
+        """Internal activation / gradient buffer `name` (see net.cuh) as a dense [B, channels, H, W] tensor."""
+        dims = (c_int * 4)()
+        check(lib().ssdn_net_debug_read(self.handle, name.encode(), plane, channels, None, dims, _stream()))
+        out = torch.empty(tuple(dims), device=self.device, dtype=torch.float32)
+        check(lib().ssdn_net_debug_read(self.handle, name.encode(), plane, channels, _ptr(out), dims, _stream()))
+        return out
+
+    def debug_write(self, name, tensor):
+        """Overwrite the first tensor.shape[1] channels of internal buffer `name` (test hook)."""
+        t = _f32(tensor)
+        check(lib().ssdn_net_debug_write(self.handle, name.encode(), t.shape[1], _ptr(t), _stream()))
+
+    def kernel_launches(self, training=True):
+        return lib().ssdn_net_kernel_launches(self.handle, int(training))
+
+
+# ------------------------------------------------------------------------------------ losses
+def _loss_ws(n, c, device):
+    return _workspace(lib().ssdn_loss_workspace_bytes(n, c), device)
+
+
+def posterior_forward(net_out, noisy, sigma_raw, sigma_known):
+    n, c, h, w = noisy.shape
+    cs = sigma_raw.numel() // n
+    dev = noisy.device
+    pme = torch.empty_like(noisy)
+    loss = torch.empty(n, 1, device=dev)
+    model_std = torch.empty(n, h, w, device=dev)
+    noise_std = torch.empty(n, 1, 1, device=dev)
+    ws = _loss_ws(n, c, dev)
+    check(lib().ssdn_posterior_forward(_ptr(ws), _ptr(net_out), _ptr(noisy), _ptr(sigma_raw), n, c, h, w, cs, int(sigma_known),
+                                       _ptr(pme), _ptr(loss), _ptr(model_std), _ptr(noise_std), _stream()))
+    return pme, loss, model_std, noise_std
+
+
+def posterior_backward(net_out, noisy, sigma_raw, gloss, sigma_known):
+    n, c, h, w = noisy.shape
+    cs = sigma_raw.numel() // n
+    dnet = torch.empty_like(net_out)
+    dsig = None if sigma_known else torch.empty_like(sigma_raw)
+    ws = _loss_ws(n, c, noisy.device)
+    check(lib().ssdn_posterior_backward(_ptr(ws), _ptr(net_out), _ptr(noisy), _ptr(sigma_raw), _ptr(gloss), n, c, h, w, cs,
+                                        int(sigma_known), _ptr(dnet), _ptr(dsig), _stream()))
+    return dnet, dsig
+
+
+def spatial_mean_forward(x):
+    n, c, h, w = x.shape
+    out = torch.empty(n, c, 1, 1, device=x.device)
+    check(lib().ssdn_spatial_mean_forward(_ptr(x), n * c, h * w, _ptr(out), _stream()))
+    return out
+
+
+def spatial_mean_backward(g, shape):
+    n, c, h, w = shape
+    dx = torch.empty(shape, device=g.device)
+    check(lib().ssdn_spatial_mean_backward(_ptr(g), n * c, h * w, _ptr(dx), _stream()))
+    return dx
+
+
+def mse_forward(a, b):
+    n = a.shape[0]
+    loss = torch.empty(n, 1, device=a.device)
+    ws = _loss_ws(n, 1, a.device)
+    check(lib().ssdn_mse_forward(_ptr(ws), _ptr(a), _ptr(b), n, a.numel() // n, _ptr(loss), _stream()))
+    return loss
+
+
+def mse_backward(a, b, gloss):
+    n = a.shape[0]
+    da = torch.empty_like(a)
+    check(lib().ssdn_mse_backward(_ptr(a), _ptr(b), _ptr(gloss), n, a.numel() // n, _ptr(da), _stream()))
+    return da
+
+
+def masked_mse_forward(out, ref, coords):
+    n, c, h, w = out.shape
+    loss = torch.empty(n, 1, device=out.device)
+    ws = _loss_ws(n, c, out.device)
+    check(lib().ssdn_masked_mse_forward(_ptr(ws), _ptr(out), _ptr(ref), _ptr(coords), coords.shape[0], n, c, h, w, _ptr(loss),
+                                        _stream()))
+    return loss
+
+
+def masked_mse_backward(out, ref, coords, gloss):
+    n, c, h, w = out.shape
+    dout = torch.empty_like(out)
+    check(lib().ssdn_masked_mse_backward(_ptr(out), _ptr(ref), _ptr(coords), coords.shape[0], _ptr(gloss), n, c, h, w, _ptr(dout),
+                                         _stream()))
+    return dout
+
+
+def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.99, eps=1e-8, grad_scale=1.0):
+    """In-place torch.optim.Adam update of the flat fp32 buffer p (train.py:100-107 hyper-parameters)."""
+    check(lib().ssdn_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), beta1, beta2, eps, int(step),
+                               float(grad_scale), _stream()))
