@@ -251,7 +251,7 @@ def ssdn_posterior(net_out: torch.Tensor, noisy: torch.Tensor, noise_std: torch.
         c22 = a5 ** 2
         sx = torch.stack([torch.stack([c00, c01, c02], -1), torch.stack([c01, c11, c12], -1),
                           torch.stack([c02, c12, c22], -1)], -1)  # N H W 3 3
-        eye = torch.eye(3).reshape(1, 1, 1, 3, 3)
+        eye = torch.eye(3, dtype=noisy.dtype).reshape(1, 1, 1, 3, 3)
         sn = (noise_std ** 2).permute(0, 2, 3, 1)[..., None] * eye
         sy = sx + sn
         sy_inv = _inv3(sy)
@@ -282,7 +282,7 @@ def ssdn_pipeline(params: Dict[str, torch.Tensor], noisy: torch.Tensor, noise_va
     c = noisy.shape[1]
     net_out = noise_network_forward(params, noisy, blindspot=True)
     if sigma_mode == "known":
-        noise_std = torch.max(noise_values, torch.tensor(1e-3))
+        noise_std = torch.max(noise_values, torch.tensor(1e-3, dtype=noise_values.dtype))
     elif sigma_mode == "const":
         noise_std = softplus_sigma(est_sigma)
     elif sigma_mode == "var":

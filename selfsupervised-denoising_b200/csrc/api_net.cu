@@ -66,6 +66,23 @@ extern "C" int ssdn_net_debug_write(void* handle, const char* name, int c, const
   SSDN_CUDA(cudaGetLastError());
   return 0;
 }
+// Per-launch timing of the tensor-core kernels (bench.py roofline).  profile_begin() switches CUDA-event bracketing of
+// every conv / wgrad launch on; profile_end() synchronises and returns, per kind (0 forward conv, 1 data-gradient conv,
+// 2 weight-gradient), the launch count, the summed device time in ms and the summed algorithmic FLOPs: out[kind*3 + {0,1,2}].
+extern "C" int ssdn_profile_begin(void) { profiler().recs.clear(); profiler().on = true; return 0; }
+extern "C" int ssdn_profile_end(double* out9) {
+  LaunchProfiler& pr = profiler();
+  pr.on = false;
+  for (int i = 0; i < 9; ++i) out9[i] = 0;
+  SSDN_CUDA(cudaDeviceSynchronize());
+  for (auto& r : pr.recs) {
+    float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+    out9[r.kind * 3 + 0] += 1; out9[r.kind * 3 + 1] += ms; out9[r.kind * 3 + 2] += r.flops;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  pr.recs.clear();
+  return 0;
+}
 extern "C" int ssdn_net_kernel_launches(void* handle, int training) {
   net::Net* nn = (net::Net*)handle;
   int fwd = (int)nn->layers.size() /*conv*/ + 5 /*pool*/ + 1 /*pack*/ + (int)nn->layers.size() * (training ? 2 : 1) - (training ? 1 : 0);

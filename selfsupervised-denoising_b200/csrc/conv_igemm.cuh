@@ -41,6 +41,7 @@ struct ConvParams {
 
 struct ConvPlan {
   ConvParams p;
+  double flops = 0;   // algorithmic 2*MAC of this launch (valid pixels, real channels); filled by the owner
   CUtensorMap a_v, a_lo, b_v, b_lo;
   int grid; size_t smem;
 };
@@ -394,13 +395,25 @@ static inline size_t conv_weight_slab_floats(int cin, int cout_padded, int ntaps
   return (size_t)cout_padded * nc * ntaps * 16;
 }
 
-static inline cudaError_t conv_launch(const ConvPlan& plan, cudaStream_t stream) {
+// Optional per-launch timing (bench.py roofline): when enabled every GEMM launch is bracketed by CUDA events.
+struct LaunchProfiler {
+  bool on = false;
+  struct Rec { int kind; double flops; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  void begin(int kind, double flops, cudaStream_t st) { Rec r{kind, flops, nullptr, nullptr}; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, st); recs.push_back(r); }
+  void end(cudaStream_t st) { cudaEventRecord(recs.back().b, st); }
+};
+inline LaunchProfiler& profiler() { static LaunchProfiler p; return p; }
+
+static inline cudaError_t conv_launch(const ConvPlan& plan, cudaStream_t stream, int kind = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(convk::conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  if (profiler().on) profiler().begin(kind, plan.flops, stream);
   convk::conv_igemm_kernel<<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a_v, plan.a_lo, plan.b_v, plan.b_lo, plan.p);
+  if (profiler().on) profiler().end(stream);
   return cudaGetLastError();
 }

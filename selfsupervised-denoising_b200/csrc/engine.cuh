@@ -7,7 +7,7 @@
 
 #include "conv_igemm.cuh"
 #include "pointwise.cuh"
-#include "wgrad_igemm.cuh"
+#include "wgrad_igemm.cuh"   // uses the LaunchProfiler declared in conv_igemm.cuh
 
 namespace eng {
 

@@ -238,9 +238,12 @@ class Net {
       if ((r = wgrad_plan_init(&l.wgrad, gg.total(), w.dz->v, w.dz->lo, w.dz->cpitch, 0, l.cout, w.x->v, w.x->lo, w.x->cpitch,
                                w.xoff, l.cin, taps, l.ksplit, partial, flag, sms)))
         return eng::fail(r, "wgrad plan for %s failed (%d)", w.nm, r);
+      l.wgrad.flops = 2.0 * B0(gg) * l.cin * l.cout * l.ksize * l.ksize;
     }
     return 0;
   }
+
+  static double B0(const Geom& gg) { return (double)gg.B * gg.H * gg.W; }   // valid pixels of a geometry
 
   ConvDst dst(Buf& b, int coff, int map, int flags, int cvalid) {
     ConvDst d{}; d.v = b.v; d.lo = b.lo; d.cpitch = b.cpitch; d.coff = coff; d.g = b.g; d.map = map; d.flags = flags;
@@ -257,6 +260,7 @@ class Net {
     int r = conv_plan_init(&l.fwd, src.g, src.v, src.lo, src.cpitch, coff, l.cin, l.slab_f_v, l.slab_f_lo, l.coutp_f, l.n_f, taps, d,
                            flag, sms);
     if (r) return eng::fail(r, "forward plan for %s failed (%d)", l.name.c_str(), r);
+    l.fwd.flops = 2.0 * B0(src.g) * l.cin * l.cout * l.ksize * l.ksize;
     return 0;
   }
   int plan_dgrad(Layer& l, Buf& src, ConvDst d) {
@@ -264,6 +268,7 @@ class Net {
     int r = conv_plan_init(&l.dgrad, src.g, src.v, src.lo, src.cpitch, 0, l.cout, l.slab_d_v, l.slab_d_lo, l.cinp_d, l.n_d, taps, d,
                            flag, sms);
     if (r) return eng::fail(r, "dgrad plan for %s failed (%d)", l.name.c_str(), r);
+    l.dgrad.flops = 2.0 * B0(src.g) * l.dgrad_nvalid * l.cout * l.ksize * l.ksize;
     return 0;
   }
 
@@ -334,7 +339,7 @@ class Net {
     pw::colsum_stage2_kernel<<<(l.cout + 127) / 128, 128, 0, st>>>(colpart, nblk, l.cout, grads + l.b_off, 0);
     return 0;
   }
-  int run_dgrad(Layer& l, cudaStream_t st) { SSDN_CUDA(conv_launch(l.dgrad, st)); return 0; }
+  int run_dgrad(Layer& l, cudaStream_t st) { SSDN_CUDA(conv_launch(l.dgrad, st, 1)); return 0; }
 
   // grads: flat buffer with the layout of params; every element is overwritten.
   int backward(const float* params, const float* dout, float* grads, cudaStream_t st) {

@@ -34,6 +34,7 @@ struct WgradParams {
 
 struct WgradPlan {
   WgradParams p;
+  double flops = 0;
   CUtensorMap dz_v, dz_lo, x_v, x_lo;
   int grid; size_t smem;
 };
@@ -257,6 +258,8 @@ static inline cudaError_t wgrad_launch(const WgradPlan& plan, cudaStream_t strea
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  if (profiler().on) profiler().begin(2, plan.flops, stream);
   wgradk::wgrad_igemm_kernel<<<plan.grid, wgradk::kThreads, plan.smem, stream>>>(plan.dz_v, plan.dz_lo, plan.x_v, plan.x_lo, plan.p);
+  if (profiler().on) profiler().end(stream);
   return cudaGetLastError();
 }

@@ -33,6 +33,8 @@ _SIGNATURES = {
     "ssdn_net_backward": (_I, [_P, _P, _P, _P, _P]),
     "ssdn_net_check": (_I, [_P, _P]),
     "ssdn_net_kernel_launches": (_I, [_P, _I]),
+    "ssdn_profile_begin": (_I, []),
+    "ssdn_profile_end": (_I, [ctypes.POINTER(c_double)]),
     "ssdn_net_debug_write": (_I, [_P, ctypes.c_char_p, _I, _P, _P]),
     "ssdn_net_debug_read": (_I, [_P, ctypes.c_char_p, _I, _I, _P, ctypes.POINTER(c_int), _P]),
     "ssdn_rot4_stack": (_I, [_P, _P] + [_I] * 4 + [_P]),
@@ -295,3 +297,14 @@ def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.99, eps=1e-8, grad_scale=
     """In-place torch.optim.Adam update of the flat fp32 buffer p (train.py:100-107 hyper-parameters)."""
     check(lib().ssdn_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), beta1, beta2, eps, int(step),
                                float(grad_scale), _stream()))
+
+
+def profile_begin():
+    check(lib().ssdn_profile_begin())
+
+
+def profile_end():
+    """-> {kind: (launches, device ms, algorithmic FLOPs)} for kinds conv_fwd / conv_dgrad / wgrad."""
+    buf = (c_double * 9)()
+    check(lib().ssdn_profile_end(buf))
+    return {k: (int(buf[3 * i]), buf[3 * i + 1], buf[3 * i + 2]) for i, k in enumerate(("conv_fwd", "conv_dgrad", "wgrad"))}

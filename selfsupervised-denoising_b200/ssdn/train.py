@@ -1,0 +1,237 @@
+"""Training step, flat Adam optimiser, LR schedule and a compact DenoiserTrainer
+(reference: ssdn/ssdn/train.py).
+
+The hot loop of the reference is  zero_grad -> run_pipeline -> mean(loss).backward() -> Adam.step()
+(train.py:197-202).  Here the parameters of all networks are views of one flat fp32 buffer, the engine
+writes gradients into a matching flat buffer, and data parallelism is one process per GPU with exactly
+one NCCL all-reduce of that buffer per step (the mean over ranks is folded into the Adam kernel)."""
+from __future__ import annotations
+
+import glob
+import os
+import re
+from typing import Callable, Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+import ssdn
+from ssdn import _engine as E
+from ssdn.datasets import NoisyDataset
+from ssdn.denoiser import Denoiser
+from ssdn.params import ConfigValue, HistoryValue, PipelineOutput, StateValue
+from ssdn.utils import Metric, MetricDict, TrackedTime, compute_ramped_lrate
+
+DEFAULT_RUN_DIR = ssdn.cfg.DEFAULT_RUN_DIR
+
+
+class FlatAdam:
+    """torch.optim.Adam(betas=(0.9, 0.99)) over the Denoiser's flat parameter buffer: one kernel per step."""
+
+    def __init__(self, denoiser: Denoiser, lr: float = 1e-3, betas=(0.9, 0.99), eps: float = 1e-8):
+        self.denoiser = denoiser
+        self.param_groups = [{"lr": lr, "betas": tuple(betas), "eps": eps}]
+        self.step_count = 0
+        self.exp_avg = None
+        self.exp_avg_sq = None
+
+    def _ensure_state(self, flat):
+        if self.exp_avg is None or self.exp_avg.shape != flat.shape or self.exp_avg.device != flat.device:
+            self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat), torch.zeros_like(flat)
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.denoiser.parameters():
+            p.grad = None
+
+    def step(self, grad_scale: float = 1.0):
+        flat = self.denoiser.flat_parameters()
+        grads = self.denoiser.flat_gradients()
+        self._ensure_state(flat)
+        self.step_count += 1
+        g = self.param_groups[0]
+        E.adam_step(flat, grads, self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count, g["betas"][0], g["betas"][1], g["eps"],
+                    grad_scale)
+
+    def state_dict(self) -> Dict:
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "param_groups": self.param_groups}
+
+    def load_state_dict(self, state: Dict):
+        self.step_count = state["step"]
+        self.param_groups = state["param_groups"]
+        dev = self.denoiser.device
+        self.exp_avg = None if state["exp_avg"] is None else state["exp_avg"].to(dev)
+        self.exp_avg_sq = None if state["exp_avg_sq"] is None else state["exp_avg_sq"].to(dev)
+
+
+def train_step(denoiser: Denoiser, optimizer: FlatAdam, data: List, world_size: int = 1) -> Dict:
+    """One optimisation step on this rank's shard of the batch.  With world_size > 1 every rank holds an equal shard,
+    the local loss is the mean over the shard, and gradients are summed by ONE all-reduce then scaled by 1/world_size
+    inside the Adam kernel - identical to the gradient of the mean over the global batch."""
+    optimizer.zero_grad()
+    outputs = denoiser.run_pipeline(data)
+    torch.mean(outputs[PipelineOutput.LOSS]).backward()
+    if world_size > 1:
+        dist.all_reduce(denoiser.flat_gradients(), op=dist.ReduceOp.SUM)
+    optimizer.step(grad_scale=1.0 / world_size)
+    return outputs
+
+
+def learning_rate(cfg: Dict, iteration: int) -> float:
+    """The reference passes (RAMPDOWN, RAMPUP) into (ramp_up, ramp_down) (train.py:276-282) with the default values
+    0.1 / 0.3 (cfg.py:18-19): the effective schedule ramps up over the first 10 % of the images and down over the last
+    30 %.  Reproduced as is."""
+    return compute_ramped_lrate(iteration, cfg[ConfigValue.TRAIN_ITERATIONS], cfg[ConfigValue.LR_RAMPDOWN_FRACTION],
+                                cfg[ConfigValue.LR_RAMPUP_FRACTION], cfg[ConfigValue.LEARNING_RATE])
+
+
+class DenoiserTrainer:
+    """Compact counterpart of the reference trainer: drives train_step over any iterable of NoisyDataset-style batches,
+    keeps the iteration counter in IMAGES (train.py:221), accumulates the same metrics, snapshots and resumes.
+    TensorBoard, image dumps and the HDF5/folder dataset readers of the reference are outside the hot path and are
+    not reproduced."""
+
+    def __init__(self, cfg: Dict, state: Optional[Dict] = None, runs_dir: str = DEFAULT_RUN_DIR, run_dir: str = None):
+        self.runs_dir = os.path.abspath(runs_dir)
+        self._run_dir = run_dir
+        self.cfg = cfg
+        if self.cfg:
+            ssdn.cfg.infer(self.cfg, model_only=self.cfg.get(ConfigValue.TRAIN_DATA_PATH) is None)
+        self.state = state if state is not None else {}
+        self._denoiser: Optional[Denoiser] = None
+        self._optimizer: Optional[FlatAdam] = None
+        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    @property
+    def denoiser(self) -> Denoiser:
+        return self._denoiser
+
+    @denoiser.setter
+    def denoiser(self, denoiser: Denoiser):
+        self._denoiser = denoiser
+        self.init_optimiser()
+
+    def init_optimiser(self):
+        self._optimizer = FlatAdam(self.denoiser, betas=[0.9, 0.99])
+
+    def new_target(self, device: str = None):
+        self.denoiser = Denoiser(self.cfg, device=device)
+        self.init_state()
+
+    def init_state(self):
+        self.state[StateValue.INITIALISED] = True
+        self.state[StateValue.ITERATION] = 0
+        self.state[StateValue.HISTORY] = {HistoryValue.TRAIN: MetricDict(), HistoryValue.EVAL: MetricDict(),
+                                          HistoryValue.TIMINGS: {"total": TrackedTime()}}
+
+    @property
+    def learning_rate(self) -> float:
+        return learning_rate(self.cfg, self.state[StateValue.ITERATION])
+
+    @property
+    def optimizer(self) -> FlatAdam:
+        for group in self._optimizer.param_groups:
+            group["lr"] = self.learning_rate
+        return self._optimizer
+
+    def train(self, batches: Iterable, on_step: Callable[[int, Dict], None] = None):
+        """Consume batches until TRAIN_ITERATIONS images have been seen."""
+        if self.denoiser is None:
+            self.new_target()
+        history = self.state[StateValue.HISTORY][HistoryValue.TRAIN]
+        self.denoiser.train()
+        for data in batches:
+            if self.state[StateValue.ITERATION] >= self.cfg[ConfigValue.TRAIN_ITERATIONS]:
+                break
+            outputs = train_step(self.denoiser, self.optimizer, data, self.world_size)
+            n = data[NoisyDataset.INPUT].shape[0]
+            with torch.no_grad():
+                history["n"] += torch.full((n,), 1.0)
+                history["loss"] += outputs[PipelineOutput.LOSS]
+                clean = self._clean(data)
+                if clean is not None:
+                    history["psnr_out"] += ssdn.utils.calculate_psnr(outputs[PipelineOutput.IMG_DENOISED], clean)
+                    if PipelineOutput.IMG_MU in outputs:
+                        history["psnr_mu_out"] += ssdn.utils.calculate_psnr(outputs[PipelineOutput.IMG_MU].contiguous(), clean)
+                for key in (PipelineOutput.NOISE_STD_DEV, PipelineOutput.MODEL_STD_DEV):
+                    if key in outputs:
+                        history[key.value] += outputs[key] * 255
+            self.state[StateValue.ITERATION] += n * self.world_size
+            if on_step:
+                on_step(self.state[StateValue.ITERATION], outputs)
+
+    def _clean(self, data):
+        md = data[NoisyDataset.METADATA] if len(data) > NoisyDataset.METADATA else None
+        if md and NoisyDataset.Metadata.CLEAN in md and md[NoisyDataset.Metadata.CLEAN] is not None:
+            return md[NoisyDataset.Metadata.CLEAN].to(self.denoiser.device)
+        return None
+
+    def evaluate(self, batches: Iterable, output_callback: Callable[[int, Dict], None] = None) -> Dict:
+        """Forward-only pass; returns mean PSNR of the denoised output (and of mu for SSDN) on the unpadded region."""
+        self.denoiser.eval()
+        metrics = MetricDict()
+        idx = 0
+        with torch.no_grad():
+            for data in batches:
+                outputs = self.denoiser.run_pipeline(data)
+                clean = self._clean(data)
+                md = data[NoisyDataset.METADATA]
+                for key, name in ((PipelineOutput.IMG_DENOISED, "psnr_out"), (PipelineOutput.IMG_MU, "psnr_mu_out")):
+                    if key not in outputs or clean is None:
+                        continue
+                    imgs = NoisyDataset.unpad(outputs[key], md)
+                    refs = NoisyDataset.unpad(clean, md)
+                    vals = [ssdn.utils.calculate_psnr(i.contiguous()[None], r.contiguous()[None]) for i, r in zip(imgs, refs)]
+                    metrics[name] += torch.cat(vals)
+                if output_callback:
+                    output_callback(idx, outputs)
+                idx += data[NoisyDataset.INPUT].shape[0]
+        self.denoiser.train()
+        return {k: float(v.accumulated()) for k, v in metrics.items()}
+
+    # ------------------------------------------------------------------ persistence (train.py:378-408, 711-745, 871-909)
+    @property
+    def run_dir_path(self) -> str:
+        if self._run_dir is None:
+            os.makedirs(self.runs_dir, exist_ok=True)
+            ids = [int(m.group(1)) for d in os.listdir(self.runs_dir) if (m := re.match(r"^(\d+)-", d))]
+            self._run_dir = "{:05d}-train-{}".format(max(ids) + 1 if ids else 0, self.denoiser.config_name())
+        return os.path.join(self.runs_dir, self._run_dir)
+
+    def state_dict(self) -> Dict:
+        return {"denoiser": self.denoiser.state_dict(), "state": self.state, "optimizer": self._optimizer.state_dict(),
+                "rng": torch.get_rng_state()}
+
+    def load_state_dict(self, state_dict, device: str = None):
+        if isinstance(state_dict, str):
+            state_dict = torch.load(state_dict, map_location="cpu", weights_only=False)
+        self.denoiser = Denoiser.from_state_dict(state_dict["denoiser"], device=device)
+        self.cfg = self.denoiser.cfg
+        self.state = state_dict["state"]
+        self._optimizer.load_state_dict(state_dict["optimizer"])
+        torch.set_rng_state(state_dict["rng"])
+
+    def snapshot(self, output_name: str = None, subdir: str = "training", model_only: bool = False) -> str:
+        if output_name is None:
+            output_name = "model_{:08d}.{}".format(self.state[StateValue.ITERATION], "wt" if model_only else "training")
+        path = os.path.join(self.run_dir_path, subdir, output_name)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        torch.save(self.denoiser.state_dict() if model_only else self.state_dict(), path)
+        return path
+
+
+def resume_run(run_dir: str, iteration: int = None, device: str = None) -> DenoiserTrainer:
+    """Restore the trainer from the newest (or the requested) ``training/model_<iter>.training`` snapshot of a run."""
+    snaps = {}
+    for p in glob.glob(os.path.join(run_dir, "training", "*.training")):
+        m = re.search(r"model_(\d+)\.training$", p)
+        if m:
+            snaps[int(m.group(1))] = p
+    if not snaps:
+        raise ValueError("Run directory contains no training files.")
+    it = max(snaps) if iteration is None else iteration
+    if it not in snaps:
+        raise ValueError("Training file for iteration {} not found.".format(it))
+    run_dir = os.path.abspath(run_dir)
+    trainer = DenoiserTrainer(None, runs_dir=os.path.dirname(run_dir), run_dir=os.path.basename(run_dir))
+    trainer.load_state_dict(snaps[it], device=device)
+    return trainer
