@@ -1,12 +1,18 @@
-/* ssdn_b200 — C ABI of the B200-native blind-spot denoising engine.
+/* ssdn_b200 — C ABI of the B200-native blind-spot denoising engine (libssdn_b200.so).
  *
  * The reference (COMP6248-Reproducability-Challenge/selfsupervised-denoising) has no FFI: its
  * boundary is the Python class API of ssdn/ssdn/models/noise_network.py and ssdn/ssdn/denoiser.py.
- * Each entry point below names the reference operator / method it replaces.  All pointers are raw
- * DEVICE pointers to float32 unless stated; tensors at the boundary are dense NCHW; `stream` is a
- * cudaStream_t.  Functions return 0 on success and a negative code on error, in which case
- * ssdn_b200_last_error() returns a thread-local description.  The library never allocates or frees
- * caller memory: scratch comes from caller-owned workspaces sized by the *_workspace_bytes queries.
+ * Each entry point below names the reference operator / method it replaces (file:line relative to
+ * the reference repository).  Conventions:
+ *   - all pointers are raw DEVICE pointers to float32 unless stated otherwise; boundary tensors are
+ *     dense NCHW; `stream` is a cudaStream_t passed as void*;
+ *   - functions return 0 on success, < 0 on error (-1 invalid argument, -2 CUDA error, -3 workspace
+ *     too small, -4 device-side pipeline timeout, -5 not bound); ssdn_b200_last_error() returns a
+ *     thread-local description.  No C++ exception crosses the boundary;
+ *   - the library never allocates or frees caller memory: scratch comes from caller-owned
+ *     workspaces sized by the *_workspace_bytes queries (PyTorch's caching allocator stays in charge);
+ *   - one handle per (process, device), single caller thread; work is enqueued on the given stream.
+ * There is no CPU implementation behind any of these functions.
  */
 #ifndef SSDN_B200_H
 #define SSDN_B200_H
@@ -18,21 +24,87 @@ extern "C" {
 const char* ssdn_b200_last_error(void);
 int ssdn_b200_version(void);
 
-/* ---- ShiftConv2d / nn.Conv2d (+ LeakyReLU) — models/noise_network.py:241-260, :70-156 ----------
+/* ---- ShiftConv2d / nn.Conv2d (+ LeakyReLU 0.1) — models/noise_network.py:241-260, :70-156 ------------------
  * blind != 0: half-plane "shift" convolution (output row h sees input rows h-2..h for ksize 3);
  * blind == 0: ordinary 'same' convolution.  ksize in {1, 3}.  w is [cout][cin][k][k], bias [cout] or NULL.
- * Synchronous with respect to `stream`. */
+ * These three operator-level calls are synchronous with respect to `stream`. */
 size_t ssdn_conv2d_workspace_bytes(int n, int cin, int h, int w, int cout, int ksize);
 int ssdn_conv2d_forward(void* ws, size_t ws_bytes, const float* x, const float* w, const float* bias, float* y,
                         int n, int cin, int h, int wd, int cout, int ksize, int blind, int lrelu_act, void* stream);
-/* dx = d(loss)/dx given dy = d(loss)/d(conv output) (autograd of the op above, convolution_backward dgrad). */
+/* dx = d(loss)/dx given dy = d(loss)/d(conv output)  (autograd: convolution_backward, data gradient). */
 int ssdn_conv2d_backward_data(void* ws, size_t ws_bytes, const float* dy, const float* w, float* dx, int n, int cin,
                               int h, int wd, int cout, int ksize, int blind, void* stream);
-
-/* dw [cout][cin][k][k] and db [cout] (either may be NULL): convolution_backward wgrad + bias reduction. */
+/* dw [cout][cin][k][k] and db [cout] (either may be NULL)  (autograd: convolution_backward, weight + bias gradient). */
 size_t ssdn_conv2d_backward_weight_workspace_bytes(int n, int cin, int h, int w, int cout, int ksize);
 int ssdn_conv2d_backward_weight(void* ws, size_t ws_bytes, const float* x, const float* dy, float* dw, float* db,
                                 int n, int cin, int h, int wd, int cout, int ksize, int blind, void* stream);
+
+/* ---- index operators ------------------------------------------------------------------------------------
+ * ssdn.utils.rotate x4 + torch.cat(dim=0) — models/noise_network.py:187-189, utils/data.py:42-67.
+ *   y[r*n + b] = rotate(x[b], 90*r), x [n][c][h][w] (h == w), y [4n][c][h][w].  Bit exact. */
+int ssdn_rot4_stack(const float* x, float* y, int n, int c, int h, int w, void* stream);
+/* Shift2d((1,0)) + chunk(4) + rotate back (0, 270, 180, 90) + cat(dim=1) — models/noise_network.py:213-222.
+ *   x [4n][c][h][w] -> y [n][4c][h][w].  Bit exact. */
+int ssdn_shift_unrot_concat(const float* x, float* y, int n, int c, int h, int w, void* stream);
+
+/* ---- NoiseNetwork — models/noise_network.py:48-226 ----------------------------------------------------------
+ * A handle is an execution plan for one fixed (n, cin, cout, h, w, blindspot).  `params` / `grads` are flat fp32
+ * buffers in nn.Module.parameters() order (for every conv: weight [cout][cin][k][k] then bias), see
+ * ssdn_net_param_count.  h and w must be multiples of 32 (input_wh_mul, :228-238); blind-spot needs h == w.
+ *   forward : NoiseNetwork.forward (:186-226); `training` != 0 also prepares what backward needs.
+ *   backward: autograd of forward w.r.t. all parameters given dout = d(loss)/d(out); overwrites grads.
+ *             Must follow the forward whose activations it differentiates (they live in the workspace). */
+int ssdn_net_create(int n, int cin, int cout, int h, int w, int blindspot, void** handle);
+void ssdn_net_destroy(void* handle);
+size_t ssdn_net_workspace_bytes(void* handle);
+size_t ssdn_net_param_count(void* handle);
+int ssdn_net_bind(void* handle, void* workspace, size_t workspace_bytes, void* stream);
+int ssdn_net_forward(void* handle, const float* params, const float* x, float* out, int training, void* stream);
+int ssdn_net_backward(void* handle, const float* params, const float* dout, float* grads, void* stream);
+/* Synchronises `stream` and reports device-side errors (a bounded mbarrier wait that expired). */
+int ssdn_net_check(void* handle, void* stream);
+/* Number of kernels one forward (+ backward when training != 0) launches. */
+int ssdn_net_kernel_launches(void* handle, int training);
+/* Test hooks: copy the first c channels of a named internal buffer (plane 0 = value, 1 = tf32 residual) to / from a
+ * dense [B][c][H][W] tensor; with out == NULL only dims[4] = {B, c, H, W} is filled. */
+int ssdn_net_debug_read(void* handle, const char* name, int plane, int c, float* out, int* dims, void* stream);
+int ssdn_net_debug_write(void* handle, const char* name, int c, const float* src, void* stream);
+/* Per-launch CUDA-event timing of the tensor-core kernels; out9[kind*3 + {0,1,2}] = {launches, ms, algorithmic FLOPs}
+ * for kind 0 forward conv, 1 data-gradient conv, 2 weight-gradient. */
+int ssdn_profile_begin(void);
+int ssdn_profile_end(double* out9);
+
+/* ---- Denoiser._ssdn_pipeline maths — denoiser.py:222-397 (Gaussian noise) -----------------------------------
+ * net_out [n][c + c(c+1)/2][h][w] (mean, then the triangular factor of Sigma_x), noisy [n][c][h][w], c in {1, 3};
+ * sigma_raw [n][cs], cs in {1, c}: sigma_known != 0 -> sigma = max(raw, 1e-3) (:279-282), else
+ * sigma = softplus(raw - 4) + 1e-3 (:272-275) and the -0.1 sigma regulariser is applied (:333, :360-363).
+ * Outputs: pme [n][c][h][w] posterior mean (:328-330, :366-372), loss [n] per-sample mean NLL (:323-363, :388),
+ * model_std [n][h][w] (:331, :375-377), noise_std [n] (:332, :378-380; may be NULL). */
+size_t ssdn_loss_workspace_bytes(int n, int c);
+int ssdn_posterior_forward(void* ws, const float* net_out, const float* noisy, const float* sigma_raw, int n, int c, int h, int w,
+                           int cs, int sigma_known, float* pme, float* loss, float* model_std, float* noise_std, void* stream);
+/* Gradient of sum_n gloss[n] * loss[n]: dnet like net_out; dsigma_raw [n][cs] (NULL or sigma_known: not computed). */
+int ssdn_posterior_backward(void* ws, const float* net_out, const float* noisy, const float* sigma_raw, const float* gloss, int n,
+                            int c, int h, int w, int cs, int sigma_known, float* dnet, float* dsigma_raw, void* stream);
+/* torch.mean(x, dim=(2,3)) of the sigma-estimator output — denoiser.py:263-265.  x [rows][hw] -> out [rows]. */
+int ssdn_spatial_mean_forward(const float* x, int rows, int hw, float* out, void* stream);
+int ssdn_spatial_mean_backward(const float* g, int rows, int hw, float* dx, void* stream);
+
+/* ---- Denoiser._mse_pipeline loss — denoiser.py:153-154: loss[n] = mean over chw of (a - b)^2 -------------------- */
+int ssdn_mse_forward(void* ws, const float* a, const float* b, int n, int chw, float* loss, void* stream);
+int ssdn_mse_backward(const float* a, const float* b, const float* gloss, int n, int chw, float* da, void* stream);
+/* ---- loss_mask_mse — utils/n2v_loss.py:6-17 + denoiser.py:176-178.  coords: DEVICE int64 [k][2] (the FIRST sample's
+ * coordinate list, used for the whole batch, indexing [:, :, c0, c1]); loss[n] = mean_c sum_k (ref - out)^2. */
+int ssdn_masked_mse_forward(void* ws, const float* out, const float* ref, const long long* coords, int k, int n, int c, int h, int w,
+                            float* loss, void* stream);
+int ssdn_masked_mse_backward(const float* out, const float* ref, const long long* coords, int k, const float* gloss, int n, int c,
+                             int h, int w, float* dout, void* stream);
+
+/* ---- optim.Adam(betas=[0.9, 0.99]) over a flat buffer — train.py:100-107, :202 ------------------------------------
+ * In place on p/m/v; `step` is the 1-based step count; the gradient is multiplied by grad_scale first (1/world_size
+ * after the data-parallel all-reduce). */
+int ssdn_adam_step(float* p, const float* g, float* m, float* v, long long count, double lr, double beta1, double beta2, double eps,
+                   long long step, double grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

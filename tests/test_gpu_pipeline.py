@@ -1,0 +1,113 @@
+"""GPU: Denoiser pipelines through the public Python API against the reference fixtures and the oracle."""
+import pytest
+import torch
+
+import cases as C
+import ssdn
+import ssdn_oracle as O
+from ssdn.datasets import NoisyDataset
+from ssdn.params import PipelineOutput
+from ssdn.train import FlatAdam, train_step
+from util import TOL, as_accurate_as_reference, data_for_case, denoiser_for_case, make_cfg, oracle_case, rel, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", list(C.PIPELINE_CASES))
+def test_pipeline_outputs_and_gradients(engine, name):
+    d = C.pipeline_inputs(name)
+    gold = C.load_golden(name)
+    den = denoiser_for_case(d)
+    out = den.run_pipeline(data_for_case(d))
+    out[PipelineOutput.LOSS].mean().backward()
+    torch.cuda.synchronize()
+    o32, g32, ge32, gs32 = oracle_case(d, torch.float32)
+    o64, g64, ge64, gs64 = oracle_case(d, torch.float64)
+    # well-conditioned outputs: straight against the reference fixture
+    assert rel(out[PipelineOutput.LOSS], gold["loss"]) < TOL
+    assert out[PipelineOutput.LOSS].shape == gold["loss"].shape
+    if d["algorithm"] == "ssdn":
+        assert rel(out[PipelineOutput.IMG_MU], gold["mu"]) < TOL
+        assert rel(out[PipelineOutput.NOISE_STD_DEV].reshape(-1), gold["noise_std"].reshape(-1)) < TOL
+        assert out[PipelineOutput.NOISE_STD_DEV].shape == gold["noise_std"].shape
+        assert out[PipelineOutput.MODEL_STD_DEV].shape == gold["model_std"].shape
+        # posterior mean / model std invert or take the determinant of Sigma_x, near-singular for an untrained net:
+        # the fp32 reference is itself only accurate to e_ref there (LAPACK LU in fp32), the engine works in fp64 registers
+        for key, okey in ((PipelineOutput.IMG_DENOISED, "pme"), (PipelineOutput.MODEL_STD_DEV, "model_std")):
+            ok, errs = as_accurate_as_reference(out[key], o32[okey], o64[okey], slack=1.0)
+            assert ok, (key, errs)
+    else:
+        assert rel(out[PipelineOutput.IMG_DENOISED], gold["out"]) < TOL
+    psnr = ssdn.utils.calculate_psnr(out[PipelineOutput.IMG_DENOISED].detach(), d["clean"].cuda())
+    assert rel(psnr, O.psnr(o64["pme"] if "pme" in o64 else o64["out"], d["clean"].double())) < 1e-3
+    # gradients: as accurate as the fp32 reference w.r.t. the fp64 oracle (LeakyReLU-derivative flips, see test_gpu_network)
+    main = den.get_model(ssdn.Denoiser.MODEL, False)
+    for k, p in main.named_parameters():
+        ok, errs = as_accurate_as_reference(p.grad, g32[k], g64[k], slack=4.0, norm=rel_l2)
+        assert ok, (k, errs)
+    assert rel(dict(main.named_parameters())["output_conv.weight"].grad, gold["g_out_w"]) < 2e-3
+    if ge64 is not None:
+        est = den.get_model(ssdn.Denoiser.SIGMA_ESTIMATOR, False)
+        for k, p in est.named_parameters():
+            ok, errs = as_accurate_as_reference(p.grad, ge32[k], ge64[k], slack=4.0, norm=rel_l2)
+            assert ok, ("estimator", k, errs)
+    if gs64 is not None:
+        assert rel(den.l_params[ssdn.Denoiser.ESTIMATED_SIGMA].grad, gold["g_est_sigma"]) < TOL
+
+
+def test_training_trajectory_matches_reference(engine):
+    """Three optimiser steps (train.py:197-202) from the fixture weights: per-sample losses of every step."""
+    d = C.pipeline_inputs("ssdn_known_rgb")
+    gold = C.load_golden("trajectory_ssdn_known_rgb")
+    den = denoiser_for_case(d)
+    opt = FlatAdam(den)
+    opt.param_groups[0]["lr"] = 3e-4
+    for k in range(3):
+        out = train_step(den, opt, data_for_case(d))
+        assert rel(out[PipelineOutput.LOSS], gold["losses"][k]) < 2e-4, k
+    main = den.get_model(ssdn.Denoiser.MODEL, False)
+    final = {k: p.data for k, p in main.named_parameters()}
+    assert rel(C.grad_summary(final), gold["final_summary"]) < 1e-3
+
+
+def test_train_step_reduces_loss_at_baseline_size(engine):
+    """BASELINE config 2 shape (32 x 3 x 64 x 64, sigma known): loss goes down over a few steps and stays finite."""
+    torch.manual_seed(0)
+    den = ssdn.Denoiser(make_cfg("ssdn", "known"), device="cuda")
+    opt = FlatAdam(den)
+    opt.param_groups[0]["lr"] = 3e-4
+    clean, noisy = O.synthetic_batch(32, 3, 64, seed=1234)
+    M = NoisyDataset.Metadata
+    data = [noisy, torch.zeros(0), {M.INPUT_NOISE_VALUES: torch.full((32, 1, 1, 1), 25 / 255), M.CLEAN: clean}]
+    losses = [float(train_step(den, opt, data)[PipelineOutput.LOSS].mean()) for _ in range(6)]
+    assert all(map(lambda v: v == v and abs(v) < 1e6, losses)) and losses[-1] < losses[0]
+    # first step equals the oracle on the same initial weights
+    torch.manual_seed(0)
+    ref = O.CpuTrainer("ssdn", "known", 3, seed=0)
+    assert abs(losses[0] - float(ref.loss(noisy, data[2][M.INPUT_NOISE_VALUES])["loss"].mean())) < 1e-4 * abs(losses[0]) + 1e-5
+
+
+def test_inference_forward_and_eval_mode(engine):
+    d = C.pipeline_inputs("n2c_mono")
+    den = denoiser_for_case(d)
+    den.eval()
+    out = den(d["noisy"])
+    assert rel(out, C.load_golden("n2c_mono")["out"]) < TOL
+    s = C.pipeline_inputs("ssdn_known_rgb")
+    den = denoiser_for_case(s)
+    with pytest.raises(ValueError):
+        den(s["noisy"])
+    pme = den(s["noisy"], s["noise_values"])
+    assert pme.shape == s["noisy"].shape and torch.isfinite(pme).all()
+
+
+def test_gradients_are_written_into_the_flat_buffer(engine):
+    d = C.pipeline_inputs("ssdn_const_rgb")
+    den = denoiser_for_case(d)
+    den.run_pipeline(data_for_case(d))[PipelineOutput.LOSS].mean().backward()
+    flat_g = den.flat_gradients()
+    off = 0
+    for p in den.parameters():
+        assert torch.equal(flat_g[off:off + p.numel()], p.grad.reshape(-1))
+        off += p.numel()
+    assert off == flat_g.numel() == 1269130
