@@ -218,7 +218,7 @@ def run_engine(args):
         top = max(prof, key=lambda k: prof[k][1])
         ach = prof[top][2] / (prof[top][1] * 1e-3) / 1e12 if prof[top][1] > 0 else 0.0
         launches = sum(p.kernel_launches(True) for net in den._models.values() for p in net._plans.values()) + 5
-        cpu_rate, cpu_step = cpu_oracle_rate(args.config, BATCH, 3, 1)
+        cpu_rate, cpu_step = (0.0, 0.0) if args.no_cpu_baseline else cpu_oracle_rate(args.config, BATCH, 3, 1)
         line = {
             "metric": "64x64 patches/sec (ssdn gauss25, bs32)", "value": BATCH * world * args.steps / t_res, "unit": "patches/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_res / args.steps * 1e3,
@@ -259,6 +259,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--config", default="known", choices=["known", "var"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -38,7 +38,7 @@ extern "C" int ssdn_net_check(void* handle, void* stream) {
   if (h) return fail(-4, "kernel pipeline timeout (role %d)", h);
   return 0;
 }
-// Debug/test helper: copies channels [0, c) of a named internal buffer (plane 0 = v, 1 = lo) into a dense
+// Debug/test helper: copies channels [0, c) of a named internal buffer (plane 0 = value = hi + lo, 1 = lo, 2 = hi) into a dense
 // NCHW tensor [B][c][H][W] of that buffer's own geometry.  Returns B*H*W*c through *count when out == NULL.
 extern "C" int ssdn_net_debug_read(void* handle, const char* name, int plane, int c, float* out, int* dims, void* stream) {
   net::Net* nn = (net::Net*)handle;
@@ -49,8 +49,9 @@ extern "C" int ssdn_net_debug_read(void* handle, const char* name, int plane, in
   if (dims) { dims[0] = b->g.B; dims[1] = c; dims[2] = b->g.H; dims[3] = b->g.W; }
   if (!out) return 0;
   const long long n = (long long)b->g.B * c * b->g.H * b->g.W;
-  pw::unpack_nchw_kernel<<<pw::grid_for(n), pw::kBlock, 0, (cudaStream_t)stream>>>(plane ? b->lo : b->v, out, b->g.B, c, b->g.H, b->g.W, b->g,
-                                                                                 b->cpitch, 0);
+  const float* p0 = plane == 1 ? b->lo : b->v;
+  const float* p1 = plane == 0 ? b->lo : nullptr;
+  pw::unpack_nchw_kernel<<<pw::grid_for(n), pw::kBlock, 0, (cudaStream_t)stream>>>(p0, p1, out, b->g.B, c, b->g.H, b->g.W, b->g, b->cpitch, 0);
   SSDN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -137,7 +137,7 @@ extern "C" int ssdn_conv2d_backward_weight(void* ws, size_t ws_bytes, const floa
     const long long rows = g.total();
     const int rpb = (int)((rows + 1023) / 1024);
     const int nblk = (int)((rows + rpb - 1) / rpb);
-    pw::colsum_stage1_kernel<<<nblk, 256, 8 * cout * sizeof(float), st>>>(yv, rows, yp, 0, cout, colpart, rpb);
+    pw::colsum_stage1_kernel<<<nblk, 256, 8 * cout * sizeof(float), st>>>(yv, yl, rows, yp, 0, cout, colpart, rpb);
     pw::colsum_stage2_kernel<<<(cout + 127) / 128, 128, 0, st>>>(colpart, nblk, cout, db, 0);
   }
   int hflag = 0;

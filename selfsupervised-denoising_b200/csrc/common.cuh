@@ -12,10 +12,13 @@
 //   in the halo.  Kernels never write halo pixels, so they stay zero for the life of the buffer.
 //   1x1 convolutions (the output head) use the same code with H+0 rows / pitch W ("dense" geometry).
 //
-//   Each tensor has two planes:  v  = the fp32 value,  lo = v - trunc_tf32(v).
-//   The tensor cores truncate fp32 operands to tf32 (measured, profiles/r01_umma_probe_full.log),
-//   so  a*b ~= v_a*v_b (hardware: hi*hi) + lo_a*v_b + v_a*lo_b  reproduces fp32-grade products
-//   ("3xTF32", error ~6e-7) without ever materialising a separate "hi" plane.
+//   Each GEMM operand tensor has two planes:  hi = round_tf32(v)  and  lo = round_tf32(v - hi)  (round to nearest).
+//   hi + lo reproduces the fp32 value v to 2^-24 relative, and
+//       a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b          (dropped lo*lo term <= 2^-24)
+//   gives fp32-grade products from three tf32 tensor-core MMAs ("3xTF32"); both planes are exactly representable in
+//   tf32, so the tensor core's own fp32->tf32 truncation (measured: profiles/r01_umma_probe_full.log) is a no-op.
+//   Kernels that need the value itself (pooling, reductions) read hi + lo; sign tests read hi alone.
+//   Tensors that are only consumed by pointwise kernels ("raw" gradients) have a single plain fp32 plane.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,8 +38,14 @@ static inline Geom make_geom(int B, int H, int W, bool padded) {
   return g;
 }
 
-__device__ __forceinline__ float tf32_lo(float v) {
-  return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t o;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(v));
+  return __uint_as_float(o);
+}
+__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
+  hi = tf32_rn(v);
+  lo = tf32_rn(v - hi);
 }
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : SSDN_LRELU_SLOPE * v; }
 
@@ -52,12 +61,12 @@ enum : int {
   EP_BIAS = 1,        // add bias[c]
   EP_LRELU = 2,       // LeakyReLU(0.1)
   EP_ACT_GRAD = 4,    // multiply by LeakyReLU'(act) where act is the forward activation at the destination
-  EP_WRITE_LO = 8,    // also write the lo plane
+  EP_WRITE_LO = 8,    // destination is a GEMM operand: write the (hi, lo) tf32 split instead of the plain value
   EP_ACT_AT_SRC = 16  // EP_ACT_GRAD reads the activation at the SOURCE pixel / true GEMM channel
 };
 
 struct ConvDst {
-  float* v; float* lo;           // destination planes
+  float* v; float* lo;           // destination planes: (hi, lo) when EP_WRITE_LO, else v = plain fp32
   int cpitch, coff;              // channels per destination pixel, channel offset of this conv's output
   Geom g;                        // destination geometry
   int map, flags;

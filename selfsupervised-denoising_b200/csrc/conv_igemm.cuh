@@ -74,20 +74,23 @@ __device__ __forceinline__ void store_pixel(const ConvDst& d, long long dflat, i
   }
   float* pv = d.v + dflat * d.cpitch + coff + cbase;
   float* pl = d.lo + dflat * d.cpitch + coff + cbase;
+  float lo[16];
+  if (d.flags & EP_WRITE_LO) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { float h; tf32_split(out[i], h, lo[i]); out[i] = h; }
+  }
   if (full) {
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
       *reinterpret_cast<float4*>(pv + i) = make_float4(out[i], out[i + 1], out[i + 2], out[i + 3]);
-      if (d.flags & EP_WRITE_LO)
-        *reinterpret_cast<float4*>(pl + i) =
-            make_float4(tf32_lo(out[i]), tf32_lo(out[i + 1]), tf32_lo(out[i + 2]), tf32_lo(out[i + 3]));
+      if (d.flags & EP_WRITE_LO) *reinterpret_cast<float4*>(pl + i) = make_float4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i)
       if (cbase + i < d.cvalid) {
         pv[i] = out[i];
-        if (d.flags & EP_WRITE_LO) pl[i] = tf32_lo(out[i]);
+        if (d.flags & EP_WRITE_LO) pl[i] = lo[i];
       }
   }
 }

@@ -308,7 +308,7 @@ class Net {
     auto pool = [&]() {
       const PoolOp& p = pools[pi++];
       const long long n = (long long)p.dst->g.B * p.dst->g.H * p.dst->g.W * 12;
-      pw::pool_fwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(p.src->v, p.src->g, p.src->cpitch, 0, p.dst->v, p.dst->lo, p.dst->g,
+      pw::pool_fwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(p.src->v, p.src->lo, p.src->g, p.src->cpitch, 0, p.dst->v, p.dst->lo, p.dst->g,
                                                                   p.dst->cpitch, p.dst_coff, 48, blind ? 1 : 0);
     };
     if ((r = run_fwd(L("encode_block_1.0"), params, st))) return r;
@@ -335,7 +335,7 @@ class Net {
     const long long rows = l.dz->g.total();
     const int rpb = (int)((rows + 1023) / 1024);
     const int nblk = (int)((rows + rpb - 1) / rpb);
-    pw::colsum_stage1_kernel<<<nblk, 256, 8 * l.cout * sizeof(float), st>>>(l.dz->v, rows, l.dz->cpitch, 0, l.cout, colpart, rpb);
+    pw::colsum_stage1_kernel<<<nblk, 256, 8 * l.cout * sizeof(float), st>>>(l.dz->v, l.dz->lo, rows, l.dz->cpitch, 0, l.cout, colpart, rpb);
     pw::colsum_stage2_kernel<<<(l.cout + 127) / 128, 128, 0, st>>>(colpart, nblk, l.cout, grads + l.b_off, 0);
     return 0;
   }
@@ -367,7 +367,7 @@ class Net {
     auto pool_bwd = [&]() {
       const PoolBwdOp& q = pool_bwds[qi++];
       const long long n = (long long)q.gp.B * q.gp.H * q.gp.W * 48;
-      pw::pool_bwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(q.act->v, q.act->g, q.act->cpitch, 0, q.g1->v, q.g1->cpitch, 0,
+      pw::pool_bwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(q.act->v, q.act->lo, q.act->g, q.act->cpitch, 0, q.g1->v, q.g1->cpitch, 0,
                                                                   q.g2 ? q.g2->v : nullptr, q.g2 ? q.g2->cpitch : 0, q.g2_coff, q.gp, q.dz->v,
                                                                   q.dz->lo, q.dz->cpitch, 0, 48, blind ? 1 : 0);
     };

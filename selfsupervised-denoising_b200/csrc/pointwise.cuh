@@ -26,26 +26,37 @@ __global__ void pack_nchw_kernel(const float* __restrict__ x, float* __restrict_
   else if (r == 3) { si = H - 1 - j; sj = i; }
   const float val = __ldg(x + (((long long)b * C + c) * H + si) * W + sj);
   const long long o = ((long long)bo * g.S + (i + g.row0) * g.P + j) * cpitch + coff + c;
-  v[o] = val;
-  if (lo) lo[o] = tf32_lo(val);
+  if (lo) { float h, l; tf32_split(val, h, l); v[o] = h; lo[o] = l; }
+  else v[o] = val;
 }
 
 // padded flat -> dense NCHW (tests / gradients w.r.t. the input)
-__global__ void unpack_nchw_kernel(const float* __restrict__ v, float* __restrict__ y, int B, int C, int H, int W,
-                                   Geom g, int cpitch, int coff) {
+__global__ void unpack_nchw_kernel(const float* __restrict__ v, const float* __restrict__ lo, float* __restrict__ y, int B, int C,
+                                   int H, int W, Geom g, int cpitch, int coff) {
   const long long n = (long long)B * C * H * W;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const int j = (int)(idx % W); long long t = idx / W;
   const int i = (int)(t % H); t /= H;
   const int c = (int)(t % C); const int b = (int)(t / C);
-  y[idx] = v[((long long)b * g.S + (i + g.row0) * g.P + j) * cpitch + coff + c];
+  const long long o = ((long long)b * g.S + (i + g.row0) * g.P + j) * cpitch + coff + c;
+  y[idx] = lo ? v[o] + lo[o] : v[o];
 }
 
 // ---------------------------------------------------------------------------- max-pool 2x2
 // blind != 0: Shift2d((1,0)) then MaxPool2d(2)  (models/noise_network.py:64-67): window rows (2i-1, 2i),
 // row -1 is the zero halo row of the padded layout.  One thread = one output pixel x 4 channels.
-__global__ void pool_fwd_kernel(const float* __restrict__ src, Geom gs, int s_cpitch, int s_coff,
+__device__ __forceinline__ float4 ld2(const float* __restrict__ hi, const float* __restrict__ lo, long long i) {
+  const float4 a = *reinterpret_cast<const float4*>(hi + i), b = *reinterpret_cast<const float4*>(lo + i);
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ void st2(float* __restrict__ hi, float* __restrict__ lo, long long i, float4 v) {
+  float4 h, l;
+  tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
+  *reinterpret_cast<float4*>(hi + i) = h; *reinterpret_cast<float4*>(lo + i) = l;
+}
+
+__global__ void pool_fwd_kernel(const float* __restrict__ src, const float* __restrict__ src_lo, Geom gs, int s_cpitch, int s_coff,
                                 float* __restrict__ dv, float* __restrict__ dlo, Geom gd, int d_cpitch, int d_coff,
                                 int C, int blind) {
   const int c4n = C / 4;
@@ -57,23 +68,21 @@ __global__ void pool_fwd_kernel(const float* __restrict__ src, Geom gs, int s_cp
   const int yo = (int)(t % gd.H); const int b = (int)(t / gd.H);
   const int y0 = 2 * yo - (blind ? 1 : 0);
   const long long s0 = ((long long)b * gs.S + (y0 + gs.row0) * gs.P + 2 * xo) * s_cpitch + s_coff + c;
-  const float4 a = *reinterpret_cast<const float4*>(src + s0);
-  const float4 bq = *reinterpret_cast<const float4*>(src + s0 + s_cpitch);
-  const float4 cq = *reinterpret_cast<const float4*>(src + s0 + (long long)gs.P * s_cpitch);
-  const float4 dq = *reinterpret_cast<const float4*>(src + s0 + (long long)(gs.P + 1) * s_cpitch);
+  const float4 a = ld2(src, src_lo, s0);
+  const float4 bq = ld2(src, src_lo, s0 + s_cpitch);
+  const float4 cq = ld2(src, src_lo, s0 + (long long)gs.P * s_cpitch);
+  const float4 dq = ld2(src, src_lo, s0 + (long long)(gs.P + 1) * s_cpitch);
   float4 m;
   m.x = fmaxf(fmaxf(a.x, bq.x), fmaxf(cq.x, dq.x)); m.y = fmaxf(fmaxf(a.y, bq.y), fmaxf(cq.y, dq.y));
   m.z = fmaxf(fmaxf(a.z, bq.z), fmaxf(cq.z, dq.z)); m.w = fmaxf(fmaxf(a.w, bq.w), fmaxf(cq.w, dq.w));
-  const long long o = ((long long)b * gd.S + (yo + gd.row0) * gd.P + xo) * d_cpitch + d_coff + c;
-  *reinterpret_cast<float4*>(dv + o) = m;
-  *reinterpret_cast<float4*>(dlo + o) = make_float4(tf32_lo(m.x), tf32_lo(m.y), tf32_lo(m.z), tf32_lo(m.w));
+  st2(dv, dlo, ((long long)b * gd.S + (yo + gd.row0) * gd.P + xo) * d_cpitch + d_coff + c, m);
 }
 
 // Backward of [LeakyReLU -> (shift) -> max-pool]: routes g = ga (+ gb) to the arg-max of each window
 // (first maximum in row-major window order wins, as in ATen's max_pool2d; a winning zero-halo element
 // swallows the gradient), multiplies by LeakyReLU'(act) and writes dZ = d(loss)/d(pre-activation) for
 // the full-resolution tensor (zeros elsewhere).  One thread = one window x one channel.
-__global__ void pool_bwd_kernel(const float* __restrict__ act, Geom ga_, int a_cpitch, int a_coff,
+__global__ void pool_bwd_kernel(const float* __restrict__ act, const float* __restrict__ act_lo, Geom ga_, int a_cpitch, int a_coff,
                                 const float* __restrict__ g1, int g1_cpitch, int g1_coff,
                                 const float* __restrict__ g2, int g2_cpitch, int g2_coff, Geom gp,
                                 float* __restrict__ dv, float* __restrict__ dlo, int d_cpitch, int d_coff,
@@ -93,7 +102,7 @@ __global__ void pool_bwd_kernel(const float* __restrict__ act, Geom ga_, int a_c
   float best = -INFINITY; int arg = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float a = __ldg(act + fl[k] * a_cpitch + a_coff + c);
+    const float a = __ldg(act + fl[k] * a_cpitch + a_coff + c) + __ldg(act_lo + fl[k] * a_cpitch + a_coff + c);
     if (a > best || a != a) { best = a; arg = k; }
   }
   const bool halo_row = blind && yo == 0;   // window rows (-1, 0): elements 0,1 are padding
@@ -103,7 +112,7 @@ __global__ void pool_bwd_kernel(const float* __restrict__ act, Geom ga_, int a_c
     float o = 0.f;
     if (k == arg) o = best > 0.f ? g : SSDN_LRELU_SLOPE * g;
     const long long di = fl[k] * d_cpitch + d_coff + c;
-    dv[di] = o; dlo[di] = tf32_lo(o);
+    tf32_split(o, dv[di], dlo[di]);
   }
 }
 
@@ -132,9 +141,7 @@ __global__ void up_bwd_kernel(const float* __restrict__ g, Geom gg, int g_cpitch
   s.z = (a.z + bq.z) + (cq.z + dq.z); s.w = (a.w + bq.w) + (cq.w + dq.w);
   s.x = av.x > 0.f ? s.x : SSDN_LRELU_SLOPE * s.x; s.y = av.y > 0.f ? s.y : SSDN_LRELU_SLOPE * s.y;
   s.z = av.z > 0.f ? s.z : SSDN_LRELU_SLOPE * s.z; s.w = av.w > 0.f ? s.w : SSDN_LRELU_SLOPE * s.w;
-  const long long o = lf * d_cpitch + d_coff + c;
-  *reinterpret_cast<float4*>(dv + o) = s;
-  *reinterpret_cast<float4*>(dlo + o) = make_float4(tf32_lo(s.x), tf32_lo(s.y), tf32_lo(s.z), tf32_lo(s.w));
+  st2(dv, dlo, lf * d_cpitch + d_coff + c, s);
 }
 
 // ---------------------------------------------------------------------------- weights
@@ -157,12 +164,12 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, float* __restric
     const long long wi = transpose ? ((long long)k * cin + ng) * ntaps + tap : ((long long)ng * cin + k) * ntaps + tap;
     val = __ldg(w + wi);
   }
-  sv[idx] = val; slo[idx] = tf32_lo(val);
+  tf32_split(val, sv[idx], slo[idx]);
 }
 
 // ---------------------------------------------------------------------------- bias gradient
 // db[c] = sum over flat pixels of dZ[flat][c].  Two deterministic stages.
-__global__ void colsum_stage1_kernel(const float* __restrict__ dz, long long rows, int cpitch, int coff, int C,
+__global__ void colsum_stage1_kernel(const float* __restrict__ dz, const float* __restrict__ dz_lo, long long rows, int cpitch, int coff, int C,
                                      float* __restrict__ partial, int rows_per_block) {
   extern __shared__ float sm[];   // [warps][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -170,7 +177,7 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ dz, long long row
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   for (int c = lane; c < C; c += 32) {
     float acc = 0.f;
-    for (long long r = r0 + warp; r < r1; r += nwarps) acc += __ldg(dz + r * cpitch + coff + c);
+    for (long long r = r0 + warp; r < r1; r += nwarps) acc += __ldg(dz + r * cpitch + coff + c) + __ldg(dz_lo + r * cpitch + coff + c);
     sm[warp * C + c] = acc;
   }
   __syncthreads();

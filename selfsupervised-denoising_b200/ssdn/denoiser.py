@@ -104,10 +104,24 @@ class Denoiser(nn.Module):
         return self._flat
 
     def flat_gradients(self) -> Tensor:
-        """Flat gradient buffer matching flat_parameters(); network gradients are written into it directly by the
-        engine, the few scalar parameters are copied in."""
+        """Flat gradient buffer matching flat_parameters().  The engine writes each network's gradients straight into
+        its slice (p.grad are views of it); anything that is not already in place - the scalar parameters, or gradients
+        produced before the flat storage existed - is copied in."""
         self.flat_parameters()
-        off = sum(p.numel() for net in self._models.values() for p in net.parameters())
+        off = 0
+        for net in self._models.values():
+            params = list(net.parameters())
+            first = params[0].grad
+            if first is None or first.data_ptr() != self._flat_grad.data_ptr() + 4 * off:
+                o = off
+                for p in params:
+                    g = self._flat_grad[o:o + p.numel()]
+                    if p.grad is None:
+                        g.zero_()
+                    elif p.grad.data_ptr() != g.data_ptr():
+                        g.copy_(p.grad.reshape(-1))
+                    o += p.numel()
+            off += sum(p.numel() for p in params)
         for p in self.l_params.values():
             g = self._flat_grad[off:off + p.numel()]
             if p.grad is None:
@@ -129,6 +143,8 @@ class Denoiser(nn.Module):
             return self.run_pipeline([data, None, md])[PipelineOutput.IMG_DENOISED]
 
     def run_pipeline(self, data: List, **kwargs) -> Dict:
+        if self.device.type == "cuda":
+            self.flat_parameters()       # parameters / gradient slots must be in their flat home BEFORE autograd records them
         pipeline = self.cfg[ConfigValue.PIPELINE]
         if pipeline == Pipeline.MSE:
             return self._mse_pipeline(data, **kwargs)

@@ -56,11 +56,20 @@ def test_backward_kernels_on_oracle_activations(engine, name):
     assert rel(C.grad_summary(grads), gold["grad_summary"]) < TOL
 
 
-@pytest.mark.parametrize("name", ["net_blind_rgb", "net_plain_rgb"])
-def test_end_to_end_gradients_as_accurate_as_reference(engine, name):
-    """Engine forward + backward with its own activations.  A pre-activation within rounding error of zero flips a
-    LeakyReLU derivative (x10) in ANY fp32 implementation, so the yardstick is the fp64 oracle: the engine must be as
-    close to it as the fp32 reference is."""
+ACT_BUFFERS = [("e1a", "encode_block_1.0", 48), ("e1", "encode_block_1.2", 48), ("e2", "encode_block_2.0", 48), ("e3", "encode_block_3.0", 48),
+               ("e4", "encode_block_4.0", 48), ("e5", "encode_block_5.0", 48), ("d_a5", "decode_block_5.0", 96), ("d_a4", "decode_block_4.0", 96),
+               ("d_a3", "decode_block_3.0", 96), ("d_a2", "decode_block_2.0", 96), ("d_a1", "decode_block_1.0", 96), ("h2", "output_block.2", 96)]
+
+
+@pytest.mark.parametrize("name", ["net_blind_rgb", "net_plain_rgb", "net_blind_rgb_64"])
+def test_end_to_end_gradients_and_mask_flips(engine, name):
+    """Engine forward + backward on its OWN activations versus autograd of the fp32 oracle.
+
+    Given identical activations every gradient matches to 1e-4 (test above).  End to end, the only additional
+    difference is the LeakyReLU derivative (1.0 vs 0.1) of pre-activations that are within the forward tolerance of
+    zero: the engine's 3xTF32 forward agrees with the reference to ~4e-5 of the layer's range, so an activation that
+    small may come out with the other sign.  This test pins exactly that: activations agree to TOL, sign flips happen
+    ONLY on elements with |a| <= TOL * max|a| and are rare, and the gradients stay within a few 1e-3 in relative L2."""
     cin, cout, blind, n, size = C.NETWORK_CASES[name]
     params, x, dout = C.network_inputs(name)
     order = O.param_order(cin, cout, blind)
@@ -69,17 +78,24 @@ def test_end_to_end_gradients_as_accurate_as_reference(engine, name):
     plan.forward(flat, x.cuda(), training=True)
     grads = _split(plan.backward(flat, dout.cuda()), params, order)
     plan.check()
-    g32, g64 = {}, {}
-    for dt, store in ((torch.float32, g32), (torch.float64, g64)):
-        po = {k: v.to(dt).clone().requires_grad_(True) for k, v in params.items()}
-        O.noise_network_forward(po, x.to(dt), blind).backward(dout.to(dt))
-        store.update({k: po[k].grad for k in order})
-    worst = 0.0
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    oo, T = oracle_trace(po, x, blind)
+    oo.backward(dout)
+    total = flips = 0
+    for buf, layer, ch in ACT_BUFFERS:
+        ref = T[layer][1].detach()
+        got = plan.debug_read(buf, ch).cpu()
+        scale = ref.abs().max()
+        assert (got - ref).abs().max() <= TOL * scale, buf
+        flipped = (got > 0) != (ref > 0)
+        assert (ref[flipped].abs() <= TOL * scale).all(), buf       # flips only where the reference activation is ~0
+        total += ref.numel()
+        flips += int(flipped.sum())
+    assert flips <= 1e-4 * total, (flips, total)
     for k in order:
-        ok, (e_eng, e_ref) = as_accurate_as_reference(grads[k], g32[k], g64[k], slack=4.0, norm=rel_l2)
-        worst = max(worst, e_eng)
-        assert ok, (k, e_eng, e_ref)
-    assert worst < 5e-2
+        assert rel_l2(grads[k], po[k].grad) < 2e-2, k
+    gold = C.load_golden(name)
+    assert rel_l2(C.grad_summary(grads)[:, :2], gold["grad_summary"][:, :2]) < 2e-2
 
 
 def test_blindspot_property_on_engine(engine):
