@@ -73,6 +73,8 @@ int ssdn_net_debug_write(void* handle, const char* name, int c, const float* src
  * for kind 0 forward conv, 1 data-gradient conv, 2 weight-gradient. */
 int ssdn_profile_begin(void);
 int ssdn_profile_end(double* out9);
+/* Per-launch records of the last profiled region in launch order: out[3*i + {0,1,2}] = {kind, ms, FLOPs}; returns the count. */
+int ssdn_profile_records(double* out, int max_records);
 
 /* ---- Denoiser._ssdn_pipeline maths — denoiser.py:222-397 (Gaussian noise) -----------------------------------
  * net_out [n][c + c(c+1)/2][h][w] (mean, then the triangular factor of Sigma_x), noisy [n][c][h][w], c in {1, 3};

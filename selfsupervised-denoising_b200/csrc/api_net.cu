@@ -71,18 +71,28 @@ extern "C" int ssdn_net_debug_write(void* handle, const char* name, int c, const
 // every conv / wgrad launch on; profile_end() synchronises and returns, per kind (0 forward conv, 1 data-gradient conv,
 // 2 weight-gradient), the launch count, the summed device time in ms and the summed algorithmic FLOPs: out[kind*3 + {0,1,2}].
 extern "C" int ssdn_profile_begin(void) { profiler().recs.clear(); profiler().on = true; return 0; }
+static std::vector<double> g_last_records;   // (kind, ms, flops) per launch of the last profiled region
 extern "C" int ssdn_profile_end(double* out9) {
   LaunchProfiler& pr = profiler();
   pr.on = false;
   for (int i = 0; i < 9; ++i) out9[i] = 0;
   SSDN_CUDA(cudaDeviceSynchronize());
+  g_last_records.clear();
   for (auto& r : pr.recs) {
     float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
     out9[r.kind * 3 + 0] += 1; out9[r.kind * 3 + 1] += ms; out9[r.kind * 3 + 2] += r.flops;
+    g_last_records.push_back(r.kind); g_last_records.push_back(ms); g_last_records.push_back(r.flops);
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
   pr.recs.clear();
   return 0;
+}
+// Per-launch records of the last profiled region, in launch order: out[3*i + {0,1,2}] = {kind, ms, algorithmic FLOPs}.
+// Returns the number of records (copies at most max_records).
+extern "C" int ssdn_profile_records(double* out, int max_records) {
+  const int n = (int)(g_last_records.size() / 3);
+  for (int i = 0; i < n && i < max_records; ++i) for (int k = 0; k < 3; ++k) out[3 * i + k] = g_last_records[3 * i + k];
+  return n;
 }
 extern "C" int ssdn_net_kernel_launches(void* handle, int training) {
   net::Net* nn = (net::Net*)handle;

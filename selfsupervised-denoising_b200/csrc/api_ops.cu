@@ -35,7 +35,7 @@ int run_conv(void* ws, size_t ws_bytes, const float* x, const float* w, const fl
   ConvOpLayout L = conv_layout(n, cin, h, wd, cout, ksize, blind, dgrad);
   Arena a(ws, ws_bytes);
   float* av = a.take<float>(L.act_floats); float* al = a.take<float>(L.act_floats);
-  float* sv = a.take<float>(L.slab_floats); float* sl = a.take<float>(L.slab_floats);
+  float* slab = a.take<float>(L.slab_floats);
   int* flag = a.take<int>(1);
   if (!ws) return (int)0;
   if (!a.ok()) return fail(-3, "workspace too small: need %zu bytes, have %zu", a.off, ws_bytes);
@@ -46,14 +46,14 @@ int run_conv(void* ws, size_t ws_bytes, const float* x, const float* w, const fl
   pw::pack_nchw_kernel<<<pw::grid_for(ne), pw::kBlock, 0, st>>>(x, av, al, n, cin, h, wd, L.g, L.cin_pitch, 0, 0);
   int nc, kl; conv_chunks(cin, &nc, &kl);
   const int n_tiles = L.cout_padded / L.N;
-  const long long ns = (long long)L.slab_floats;
-  pw::weight_prep_kernel<<<pw::grid_for(ns), pw::kBlock, 0, st>>>(w, sv, sl, w_cout, w_cin, L.taps.n, cout, cin, n_tiles, nc,
+  const long long ns = (long long)L.slab_floats / 2;
+  pw::weight_prep_kernel<<<pw::grid_for(ns), pw::kBlock, 0, st>>>(w, slab, w_cout, w_cin, L.taps.n, cout, cin, n_tiles, nc,
                                                                   L.N, dgrad ? 1 : 0);
   ConvDst d{};
   d.v = y; d.lo = nullptr; d.cpitch = 0; d.coff = 0; d.g = L.g; d.map = MAP_NCHW;
   d.flags = (bias ? EP_BIAS : 0) | (lrelu_act ? EP_LRELU : 0); d.cvalid = cout; d.nimg = n; d.bias = bias;
   ConvPlan plan;
-  int r = conv_plan_init(&plan, L.g, av, al, L.cin_pitch, 0, cin, sv, sl, L.cout_padded, L.N, L.taps, d, flag, num_sms());
+  int r = conv_plan_init(&plan, L.g, av, al, L.cin_pitch, 0, cin, slab, L.cout_padded, L.N, L.taps, d, flag, num_sms());
   if (r) return fail(r, "conv_plan_init failed (%d)", r);
   SSDN_CUDA(conv_launch(plan, st));
   int hflag = 0;
@@ -66,7 +66,7 @@ int run_conv(void* ws, size_t ws_bytes, const float* x, const float* w, const fl
 size_t conv_ws_bytes(int n, int cin, int h, int w, int cout, int ksize, bool blind, bool dgrad) {
   ConvOpLayout L = conv_layout(n, cin, h, w, cout, ksize, blind, dgrad);
   Arena a(nullptr, 0);
-  a.take<float>(L.act_floats); a.take<float>(L.act_floats); a.take<float>(L.slab_floats); a.take<float>(L.slab_floats);
+  a.take<float>(L.act_floats); a.take<float>(L.act_floats); a.take<float>(L.slab_floats);
   a.take<int>(1);
   return a.off;
 }

@@ -32,17 +32,20 @@ struct ConvParams {
   int n_chunks, ksteps_last;
   int n_groups, ntaps_total;
   TapGroup groups[9];
-  int nbox, box_rows; // every group window is loaded as nbox TMA boxes of box_rows rows
+  int nbox, box_rows; // every group window is loaded as nbox TMA boxes of box_rows rows (one op for both planes if nbox == 1)
   int a_stages, b_stages;
-  uint32_t a_plane_bytes, b_plane_bytes;   // smem bytes of one plane of one stage (1024-aligned)
+  int bg;             // weight slabs ((chunk, tap) pairs, in consumption order) per B stage: ONE TMA op loads bg x 2 planes
+  uint32_t a_plane_bytes, b_stage_bytes;   // smem bytes of one A plane of one stage / of one B stage
+  uint32_t epi_off;   // byte offset of the epilogue staging area (4 warps x 32 pixels x 36 floats) in dynamic smem
   ConvDst dst;
   int* error_flag;
+  int debug;          // experiments only: 2 = skip MMA issue
 };
 
 struct ConvPlan {
   ConvParams p;
   double flops = 0;   // algorithmic 2*MAC of this launch (valid pixels, real channels); filled by the owner
-  CUtensorMap a_v, a_lo, b_v, b_lo;
+  CUtensorMap a, b;   // a: [plane][flat pixel][channel] (3-D), b: weight slabs [slab x plane][N][16] (3-D)
   int grid; size_t smem;
 };
 
@@ -57,66 +60,34 @@ struct Ring {
   __device__ void advance() { if (++stage == n) { stage = 0; phase ^= 1; } }
 };
 
-// Writes 16 consecutive output channels [cbase, cbase+16) of one destination pixel.
-//   act_index: flat float index of the forward activation for channel cbase (EP_ACT_GRAD), else unused.
-__device__ __forceinline__ void store_pixel(const ConvDst& d, long long dflat, int coff, int cbase, long long act_index,
-                                            const float (&val)[16], bool write_zero) {
-  float out[16];
-  const bool full = (cbase + 16 <= d.cvalid);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float x = val[i];
-    if (d.flags & EP_ACT_GRAD) {
-      float a = (full || cbase + i < d.cvalid) ? __ldg(d.act + act_index + i) : 1.f;
-      x = a > 0.f ? x : SSDN_LRELU_SLOPE * x;
-    }
-    out[i] = write_zero ? 0.f : x;
-  }
-  float* pv = d.v + dflat * d.cpitch + coff + cbase;
-  float* pl = d.lo + dflat * d.cpitch + coff + cbase;
-  float lo[16];
-  if (d.flags & EP_WRITE_LO) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { float h; tf32_split(out[i], h, lo[i]); out[i] = h; }
-  }
-  if (full) {
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      *reinterpret_cast<float4*>(pv + i) = make_float4(out[i], out[i + 1], out[i + 2], out[i + 3]);
-      if (d.flags & EP_WRITE_LO) *reinterpret_cast<float4*>(pl + i) = make_float4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (cbase + i < d.cvalid) {
-        pv[i] = out[i];
-        if (d.flags & EP_WRITE_LO) pl[i] = lo[i];
-      }
-  }
-}
+constexpr int kStagePitch = 36;   // floats per staged pixel row (32 channels + 4 pad: conflict-free float4 access)
 
+template <int T>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_v, const __grid_constant__ CUtensorMap map_a_lo,
-                  const __grid_constant__ CUtensorMap map_b_v, const __grid_constant__ CUtensorMap map_b_lo,
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 4];
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t abort_word;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = umma::smem_u32(smem);
-  const uint32_t a_stage_bytes = 2 * p.a_plane_bytes, b_stage_bytes = 2 * p.b_plane_bytes;
+  const uint32_t a_stage_bytes = 2 * p.a_plane_bytes, b_stage_bytes = p.b_stage_bytes;
   const uint32_t a_base = sbase, b_base = sbase + p.a_stages * a_stage_bytes;
-  auto full_a = [&](int s) { return umma::smem_u32(&bars[s]); };
-  auto empty_a = [&](int s) { return umma::smem_u32(&bars[kMaxStages + s]); };
-  auto full_b = [&](int s) { return umma::smem_u32(&bars[2 * kMaxStages + s]); };
-  auto empty_b = [&](int s) { return umma::smem_u32(&bars[3 * kMaxStages + s]); };
-  auto tmem_full = [&](int b) { return umma::smem_u32(&bars[4 * kMaxStages + b]); };
-  auto tmem_empty = [&](int b) { return umma::smem_u32(&bars[4 * kMaxStages + 2 + b]); };
+  const uint32_t bar0 = umma::smem_u32(&bars[0]);
+  auto full_a = [&](int s) { return bar0 + 8 * s; };
+  auto empty_a = [&](int s) { return bar0 + 8 * (kMaxStages + s); };
+  auto full_b = [&](int s) { return bar0 + 8 * (2 * kMaxStages + s); };
+  auto empty_b = [&](int s) { return bar0 + 8 * (3 * kMaxStages + s); };
+  auto tmem_full = [&](int b) { return bar0 + 8 * (4 * kMaxStages + b); };
+  auto tmem_empty = [&](int b) { return bar0 + 8 * (4 * kMaxStages + 2 + b); };
+  const uint32_t abort_addr = umma::smem_u32(&abort_word);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = p.n_units_m * p.n_tiles_n;
 
   if (threadIdx.x == 0) {
+    abort_word = 0;
     for (int s = 0; s < p.a_stages; ++s) { umma::mbar_init(full_a(s), 1); umma::mbar_init(empty_a(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { umma::mbar_init(full_b(s), 1); umma::mbar_init(empty_b(s), 1); }
     for (int b = 0; b < 2; ++b) { umma::mbar_init(tmem_full(b), 1); umma::mbar_init(tmem_empty(b), 128); }
@@ -126,180 +97,238 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_v, const __grid_cons
     umma::tmem_alloc(umma::smem_u32(&tmem_slot), 512);
     umma::tmem_relinquish();
   }
-  if (warp == 0 && lane == 0) { umma::tma_prefetch_desc(&map_a_v); umma::tma_prefetch_desc(&map_a_lo); }
-  if (warp == 1 && lane == 0) { umma::tma_prefetch_desc(&map_b_v); umma::tma_prefetch_desc(&map_b_lo); }
+  if (warp == 0 && lane == 0) umma::tma_prefetch_desc(&map_a);
+  if (warp == 1 && lane == 0) umma::tma_prefetch_desc(&map_b);
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  bool ok = true;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ A producer
-    if (lane == 0) {
-      Ring ra(p.a_stages);
-      const uint32_t box_bytes = p.box_rows * 64;
-      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x) {
-        const int um = u / p.n_tiles_n;
-        const long long j0 = (long long)um * 128 * p.T;
-        for (int ch = 0; ch < p.n_chunks && ok; ++ch)
-          for (int g = 0; g < p.n_groups; ++g) {
-            if (!(ok = umma::mbar_wait(empty_a(ra.stage), ra.phase ^ 1))) break;
+    // ------------------------------------------------------------ A producer (warp-uniform loop, elected issue)
+    Ring ra(p.a_stages);
+    const uint32_t box_bytes = p.box_rows * 64;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int um = u / p.n_tiles_n;
+      const int j0 = um * 128 * T;
+      for (int ch = 0; ch < p.n_chunks; ++ch)
+        for (int g = 0; g < p.n_groups; ++g) {
+          umma::mbar_wait(empty_a(ra.stage), ra.phase ^ 1, abort_addr, p.error_flag, 1);
+          const uint32_t dst = a_base + ra.stage * a_stage_bytes;
+          const int row = j0 + p.groups[g].row_off;
+          if (umma::elect_one()) {
             umma::mbar_expect_tx(full_a(ra.stage), 2 * p.nbox * box_bytes);
-            const uint32_t dst = a_base + ra.stage * a_stage_bytes;
-            const int row = (int)(j0 + p.groups[g].row_off);
-            for (int bx = 0; bx < p.nbox; ++bx) {
-              umma::tma_load_2d(dst + bx * box_bytes, &map_a_v, full_a(ra.stage), ch * 16, row + bx * p.box_rows);
-              umma::tma_load_2d(dst + p.a_plane_bytes + bx * box_bytes, &map_a_lo, full_a(ra.stage), ch * 16,
-                                row + bx * p.box_rows);
+            if (p.nbox == 1) {      // one op brings both planes: box (16 ch, rows, 2 planes)
+              umma::tma_load_3d(dst, &map_a, full_a(ra.stage), ch * 16, row, 0);
+            } else {
+              for (int bx = 0; bx < p.nbox; ++bx) {
+                umma::tma_load_3d(dst + bx * box_bytes, &map_a, full_a(ra.stage), ch * 16, row + bx * p.box_rows, 0);
+                umma::tma_load_3d(dst + p.a_plane_bytes + bx * box_bytes, &map_a, full_a(ra.stage), ch * 16, row + bx * p.box_rows, 1);
+              }
             }
-            ra.advance();
           }
-      }
-      if (!ok) atomicExch(p.error_flag, 1);
+          __syncwarp();
+          ra.advance();
+        }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ B producer
-    if (lane == 0) {
-      Ring rb(p.b_stages);
-      const uint32_t tile_bytes = p.N * 64;
-      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x) {
-        const int nt = u % p.n_tiles_n;
-        for (int ch = 0; ch < p.n_chunks && ok; ++ch)
-          for (int g = 0; g < p.n_groups && ok; ++g)
-            for (int t = 0; t < p.groups[g].ntaps; ++t) {
-              if (!(ok = umma::mbar_wait(empty_b(rb.stage), rb.phase ^ 1))) break;
-              umma::mbar_expect_tx(full_b(rb.stage), 2 * tile_bytes);
-              const uint32_t dst = b_base + rb.stage * b_stage_bytes;
-              const int row = ((nt * p.n_chunks + ch) * p.ntaps_total + p.groups[g].tap_id[t]) * p.N;
-              umma::tma_load_2d(dst, &map_b_v, full_b(rb.stage), 0, row);
-              umma::tma_load_2d(dst + p.b_plane_bytes, &map_b_lo, full_b(rb.stage), 0, row);
-              rb.advance();
-            }
+    // ------------------------------------------------------------ B producer: one TMA per stage = bg slabs x 2 planes
+    Ring rb(p.b_stages);
+    const int n_slabs = p.n_chunks * p.ntaps_total, n_bstages = n_slabs / p.bg;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int nt = u % p.n_tiles_n;
+      for (int i = 0; i < n_bstages; ++i) {
+        umma::mbar_wait(empty_b(rb.stage), rb.phase ^ 1, abort_addr, p.error_flag, 2);
+        if (umma::elect_one()) {
+          umma::mbar_expect_tx(full_b(rb.stage), b_stage_bytes);
+          umma::tma_load_3d(b_base + rb.stage * b_stage_bytes, &map_b, full_b(rb.stage), 0, 0, 2 * (nt * n_slabs + i * p.bg));
+        }
+        __syncwarp();
+        rb.advance();
       }
-      if (!ok) atomicExch(p.error_flag, 2);
     }
   } else if (warp == 2) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      Ring ra(p.a_stages), rb(p.b_stages);
-      const uint64_t desc = umma::make_desc_base(16, 512, umma::LAYOUT_SW64);
-      const uint32_t idesc = umma::make_idesc_tf32(128, p.N, 0, 0);
-      int it = 0;
-      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x, ++it) {
-        const int buf = it & 1;
-        if (!(ok = umma::mbar_wait(tmem_empty(buf), ((it >> 1) & 1) ^ 1))) break;
-        umma::tc_fence_after();
-        bool first = true;
-        for (int ch = 0; ch < p.n_chunks && ok; ++ch) {
-          const int ks = (ch == p.n_chunks - 1) ? p.ksteps_last : 2;
-          for (int g = 0; g < p.n_groups && ok; ++g) {
-            if (!(ok = umma::mbar_wait(full_a(ra.stage), ra.phase))) break;
-            const uint32_t av = a_base + ra.stage * a_stage_bytes, al = av + p.a_plane_bytes;
-            for (int t = 0; t < p.groups[g].ntaps; ++t) {
-              if (!(ok = umma::mbar_wait(full_b(rb.stage), rb.phase))) break;
-              umma::tc_fence_after();
-              const uint32_t bv = b_base + rb.stage * b_stage_bytes, bl = bv + p.b_plane_bytes;
-              const uint32_t rel = p.groups[g].tap_rel[t] * 64;
-              for (int tile = 0; tile < p.T; ++tile) {
-                const uint32_t d = tmem + (buf * p.T + tile) * p.N;
-                for (int k = 0; k < ks; ++k) {
-                  const uint32_t ao = rel + tile * (128 * 64) + k * 32, bo = k * 32;
-                  umma::mma_tf32_ss(d, umma::desc_at(desc, al + ao), umma::desc_at(desc, bv + bo), idesc,
-                                    !(first && k == 0));
-                  umma::mma_tf32_ss(d, umma::desc_at(desc, av + ao), umma::desc_at(desc, bl + bo), idesc, 1);
-                  umma::mma_tf32_ss(d, umma::desc_at(desc, av + ao), umma::desc_at(desc, bv + bo), idesc, 1);
+    // ------------------------------------------------------------ MMA issuer: uniform loops, one elected lane issues a fully
+    // unrolled block of T x 2 x 3 MMAs per (chunk, tap) whose descriptors are base + compile-time offsets
+    Ring ra(p.a_stages), rb(p.b_stages);
+    constexpr uint64_t desc = umma::make_desc_base(16, 512, umma::LAYOUT_SW64);
+    const uint32_t idesc = umma::make_idesc_tf32(128, p.N, 0, 0);
+    int it = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+      const int buf = it & 1;
+      umma::mbar_wait(tmem_empty(buf), ((it >> 1) & 1) ^ 1, abort_addr, p.error_flag, 3);
+      umma::tc_fence_after();
+      const uint32_t d0 = tmem + buf * T * p.N;
+      uint32_t first = 0;       // becomes 1 after the first tap: accumulate flag of the very first MMA of each tile
+      int sb = 0;               // slab index inside the current B stage
+      const uint32_t slab_bytes = 2 * p.N * 64;
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        const bool two = (ch != p.n_chunks - 1) || (p.ksteps_last == 2);
+        for (int g = 0; g < p.n_groups; ++g) {
+          umma::mbar_wait(full_a(ra.stage), ra.phase, abort_addr, p.error_flag, 3);
+          const uint32_t av0 = a_base + ra.stage * a_stage_bytes;
+          for (int t = 0; t < p.groups[g].ntaps; ++t) {
+            if (sb == 0) umma::mbar_wait(full_b(rb.stage), rb.phase, abort_addr, p.error_flag, 3);
+            umma::tc_fence_after();
+            const uint32_t av = av0 + p.groups[g].tap_rel[t] * 64, al = av + p.a_plane_bytes;
+            const uint32_t bv = b_base + rb.stage * b_stage_bytes + sb * slab_bytes, bl = bv + p.N * 64;
+            const bool last_slab = (sb + 1 == p.bg);
+            if (umma::elect_one()) {
+              if (!(p.debug & 2))
+#pragma unroll
+              for (int tile = 0; tile < T; ++tile) {
+                const uint32_t d = d0 + tile * p.N;
+                const uint32_t ao = tile * (128 * 64);
+                umma::mma_tf32_ss(d, umma::desc_at(desc, al + ao), umma::desc_at(desc, bv), idesc, first);
+                umma::mma_tf32_ss(d, umma::desc_at(desc, av + ao), umma::desc_at(desc, bl), idesc, 1);
+                umma::mma_tf32_ss(d, umma::desc_at(desc, av + ao), umma::desc_at(desc, bv), idesc, 1);
+                if (two) {
+                  umma::mma_tf32_ss(d, umma::desc_at(desc, al + ao + 32), umma::desc_at(desc, bv + 32), idesc, 1);
+                  umma::mma_tf32_ss(d, umma::desc_at(desc, av + ao + 32), umma::desc_at(desc, bl + 32), idesc, 1);
+                  umma::mma_tf32_ss(d, umma::desc_at(desc, av + ao + 32), umma::desc_at(desc, bv + 32), idesc, 1);
                 }
               }
-              first = false;
-              umma::mma_commit(empty_b(rb.stage));
-              rb.advance();
+              if (last_slab) umma::mma_commit(empty_b(rb.stage));
             }
-            umma::mma_commit(empty_a(ra.stage));
-            ra.advance();
+            __syncwarp();
+            first = 1;
+            if (last_slab) { sb = 0; rb.advance(); } else ++sb;
           }
+          if (umma::elect_one()) umma::mma_commit(empty_a(ra.stage));
+          __syncwarp();
+          ra.advance();
         }
-        umma::mma_commit(tmem_full(buf));
       }
-      if (!ok) atomicExch(p.error_flag, 3);
+      if (umma::elect_one()) umma::mma_commit(tmem_full(buf));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
+    // TMEM -> registers (one pixel per lane) -> bias / LeakyReLU -> 32-channel slice staged in shared memory ->
+    // copy-out in which 8 consecutive lanes write one pixel's 128 contiguous bytes (full lines), with the
+    // LeakyReLU' mask, the hi/lo split and the upsample / (un-)rotate scatter applied on the way out.
     const ConvDst& d = p.dst;
     const Geom& sg = p.src;
     const int ew = warp - 4;
+    float* stage = reinterpret_cast<float*>(smem + p.epi_off) + ew * 32 * kStagePitch;
+    __shared__ int s_dst[4][32][4];
+    __shared__ int s_meta[4][32];       // bits 0..2: number of destinations, bit 3: write zeros, bits 8..: channel shift
+    __shared__ int s_src[4][32];        // source flat pixel (activation lookup with EP_ACT_AT_SRC)
+    __shared__ float s_bias[400];
+    if (d.flags & EP_BIAS)
+      for (int i = threadIdx.x - 128; i < d.cvalid && i < 400; i += 128) s_bias[i] = __ldg(d.bias + i);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     int it = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
       const int buf = it & 1;
       const int um = u / p.n_tiles_n, nt = u % p.n_tiles_n;
-      if (!umma::mbar_wait(tmem_full(buf), (it >> 1) & 1)) { ok = false; }
-      ok = __all_sync(0xffffffffu, ok);
-      if (!ok) { if (lane == 0) atomicExch(p.error_flag, 4); break; }
+      umma::mbar_wait(tmem_full(buf), (it >> 1) & 1, abort_addr, p.error_flag, 4);
       umma::tc_fence_after();
-      for (int tile = 0; tile < p.T; ++tile) {
-        const long long j = (long long)um * 128 * p.T + tile * 128 + ew * 32 + lane;
+      for (int tile = 0; tile < T; ++tile) {
+        const long long j = (long long)um * 128 * T + tile * 128 + ew * 32 + lane;
         const int b = (int)(j / sg.S);
         const int rem = (int)(j - (long long)b * sg.S);
         const int rr = rem / sg.P;
         const int x = rem - rr * sg.P, y = rr - sg.row0;
         const bool valid = (b < sg.B) && (y >= 0) && (x < sg.W);
-        // destination pixel(s)
-        long long dflat[4]; int ndst = 0; bool zero = false; int cshift = 0;
-        if (valid) {
-          const Geom& dg = d.g;
-          if (d.map == MAP_IDENT) {
-            dflat[0] = (long long)b * dg.S + (y + dg.row0) * dg.P + x; ndst = 1;
-          } else if (d.map == MAP_UP2) {
-            const long long o = (long long)b * dg.S + (2 * y + dg.row0) * dg.P + 2 * x;
-            dflat[0] = o; dflat[1] = o + 1; dflat[2] = o + dg.P; dflat[3] = o + dg.P + 1; ndst = 4;
-          } else if (d.map == MAP_UNROT) {
-            const int br = b / d.nimg, n = b - br * d.nimg, H = sg.H, W = sg.W;
-            const int pp = (y + 1 == H) ? 0 : y + 1, q = x;
-            zero = (y + 1 == H);
-            int i, jj;
-            if (br == 0) { i = pp; jj = q; } else if (br == 1) { i = q; jj = H - 1 - pp; }
-            else if (br == 2) { i = H - 1 - pp; jj = W - 1 - q; } else { i = W - 1 - q; jj = pp; }
-            dflat[0] = (long long)n * dg.S + (i + dg.row0) * dg.P + jj; ndst = 1; cshift = br * d.cvalid;
-          } else if (d.map == MAP_UNROT_INV) {
-            const int br = nt, H = sg.H, W = sg.W;
-            int pp, q;
-            if (br == 0) { pp = y; q = x; } else if (br == 1) { pp = H - 1 - x; q = y; }
-            else if (br == 2) { pp = H - 1 - y; q = W - 1 - x; } else { pp = x; q = W - 1 - y; }
-            if (pp > 0) { dflat[0] = (long long)(br * d.nimg + b) * dg.S + (pp - 1 + dg.row0) * dg.P + q; ndst = 1; }
-          } else {
-            ndst = 1;
-          }
-        }
-        const uint32_t trow = tmem + (uint32_t(ew * 32) << 16) + (buf * p.T + tile) * p.N;
-        for (int c0 = 0; c0 < p.N; c0 += 16) {
-          uint32_t r[16];
-          umma::tmem_ld16(trow + c0, r);
-          umma::tmem_ld_wait();
-          if (ndst == 0) continue;
-          const int cg = (d.map == MAP_UNROT_INV ? 0 : nt * p.N) + c0;   // channel within this conv's outputs
-          if (cg >= d.cvalid) continue;
-          float val[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = __uint_as_float(r[i]);
-            if ((d.flags & EP_BIAS) && cg + i < d.cvalid) a += __ldg(d.bias + cg + i);
-            if (d.flags & EP_LRELU) a = lrelu(a);
-            val[i] = a;
-          }
-          if (d.map == MAP_NCHW) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (cg + i < d.cvalid)
-                d.v[(((long long)b * d.cvalid + cg + i) * sg.H + y) * sg.W + x] = val[i];
-          } else {
-            for (int k = 0; k < ndst; ++k) {
-              // forward activation for the LeakyReLU' mask: at the destination pixel, or (EP_ACT_AT_SRC) at the
-              // source pixel with the GEMM's true output channel (head input holds the un-rotated branch outputs)
-              const long long ai = (d.flags & EP_ACT_AT_SRC) ? j * d.act_cpitch + d.act_coff + nt * p.N + c0
-                                                             : dflat[k] * d.act_cpitch + d.act_coff + cg;
-              store_pixel(d, dflat[k], d.coff + cshift, cg, ai, val, zero);
+        if (d.map != MAP_NCHW) {
+          int nd = 0, zero = 0, cshift = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+          if (valid) {
+            const Geom& dg = d.g;
+            if (d.map == MAP_IDENT) {
+              d0 = b * dg.S + (y + dg.row0) * dg.P + x; nd = 1;
+            } else if (d.map == MAP_UP2) {
+              d0 = b * dg.S + (2 * y + dg.row0) * dg.P + 2 * x; d1 = d0 + 1; d2 = d0 + dg.P; d3 = d2 + 1; nd = 4;
+            } else if (d.map == MAP_UNROT) {
+              const int br = b / d.nimg, n = b - br * d.nimg, H = sg.H, W = sg.W;
+              const int pp = (y + 1 == H) ? 0 : y + 1, q = x;
+              zero = (y + 1 == H);
+              int i, jj;
+              if (br == 0) { i = pp; jj = q; } else if (br == 1) { i = q; jj = H - 1 - pp; }
+              else if (br == 2) { i = H - 1 - pp; jj = W - 1 - q; } else { i = W - 1 - q; jj = pp; }
+              d0 = n * dg.S + (i + dg.row0) * dg.P + jj; nd = 1; cshift = br * d.cvalid;
+            } else {   // MAP_UNROT_INV
+              const int br = nt, H = sg.H, W = sg.W;
+              int pp, q;
+              if (br == 0) { pp = y; q = x; } else if (br == 1) { pp = H - 1 - x; q = y; }
+              else if (br == 2) { pp = H - 1 - y; q = W - 1 - x; } else { pp = x; q = W - 1 - y; }
+              if (pp > 0) { d0 = (br * d.nimg + b) * dg.S + (pp - 1 + dg.row0) * dg.P + q; nd = 1; }
             }
           }
+          s_dst[ew][lane][0] = d0; s_dst[ew][lane][1] = d1; s_dst[ew][lane][2] = d2; s_dst[ew][lane][3] = d3;
+          s_meta[ew][lane] = nd | (zero << 3) | (cshift << 8);
+          s_src[ew][lane] = (int)j;
+        }
+        const uint32_t trow = tmem + (uint32_t(ew * 32) << 16) + (buf * T + tile) * p.N;
+        for (int c0 = 0; c0 < p.N; c0 += 32) {
+          const int cw = min(32, p.N - c0);                           // 32 or 16 channels in this slice
+          const int cg0 = (d.map == MAP_UNROT_INV ? 0 : nt * p.N) + c0; // first channel of the slice among this conv's outputs
+          uint32_t r[32];
+          umma::tmem_ld16(trow + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+          if (cw == 32) umma::tmem_ld16(trow + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+          umma::tmem_ld_wait();
+          if (cg0 >= d.cvalid) continue;
+          if (d.flags & (EP_BIAS | EP_LRELU)) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < cw) {
+                float a = __uint_as_float(r[i]);
+                if ((d.flags & EP_BIAS) && cg0 + i < d.cvalid) a += s_bias[cg0 + i];
+                if (d.flags & EP_LRELU) a = lrelu(a);
+                r[i] = __float_as_uint(a);
+              }
+            }
+          }
+          if (d.map == MAP_NCHW) {
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < cw && cg0 + i < d.cvalid)
+                  d.v[(((long long)b * d.cvalid + cg0 + i) * sg.H + y) * sg.W + x] = __uint_as_float(r[i]);
+            }
+            continue;
+          }
+          // stage this lane's pixel row
+          float* row = stage + lane * kStagePitch;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            if (i < cw) *reinterpret_cast<uint4*>(row + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+          __syncwarp();
+          // copy-out: L lanes per pixel, 32 / L pixels per pass
+          const int L = cw >> 2, sub = lane / L, f = lane - sub * L, ppi = 32 / L;
+          const int cg = cg0 + 4 * f;
+          if (cg < d.cvalid) {
+            for (int p0 = 0; p0 < 32; p0 += ppi) {
+              const int px = p0 + sub;
+              const int meta = s_meta[ew][px];
+              const int nd = meta & 7;
+              if (nd == 0) continue;
+              float4 v = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 4 * f);
+              if (meta & 8) v = make_float4(0.f, 0.f, 0.f, 0.f);
+              const int coff = d.coff + (meta >> 8) + cg;
+              for (int k = 0; k < nd; ++k) {
+                const long long dpix = s_dst[ew][px][k];
+                float4 o = v;
+                if (d.flags & EP_ACT_GRAD) {
+                  const long long ai = (d.flags & EP_ACT_AT_SRC) ? (long long)s_src[ew][px] * d.act_cpitch + d.act_coff + nt * p.N + c0 + 4 * f
+                                                                 : dpix * d.act_cpitch + d.act_coff + cg;
+                  const float4 a = __ldg(reinterpret_cast<const float4*>(d.act + ai));
+                  o.x = a.x > 0.f ? o.x : SSDN_LRELU_SLOPE * o.x; o.y = a.y > 0.f ? o.y : SSDN_LRELU_SLOPE * o.y;
+                  o.z = a.z > 0.f ? o.z : SSDN_LRELU_SLOPE * o.z; o.w = a.w > 0.f ? o.w : SSDN_LRELU_SLOPE * o.w;
+                }
+                const long long oi = dpix * d.cpitch + coff;
+                if (d.flags & EP_WRITE_LO) {
+                  float4 h, l;
+                  tf32_split(o.x, h.x, l.x); tf32_split(o.y, h.y, l.y); tf32_split(o.z, h.z, l.z); tf32_split(o.w, h.w, l.w);
+                  *reinterpret_cast<float4*>(d.v + oi) = h;
+                  *reinterpret_cast<float4*>(d.lo + oi) = l;
+                } else {
+                  *reinterpret_cast<float4*>(d.v + oi) = o;
+                }
+              }
+            }
+          }
+          __syncwarp();
         }
       }
       umma::tc_fence_before();
@@ -315,6 +344,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_v, const __grid_cons
 
 // ------------------------------------------------------------------------------------------ host
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 struct ConvTaps { int n; int off[9]; };   // flat-pixel offsets of the taps, in weight-slab order
@@ -328,22 +358,26 @@ static inline void conv_chunks(int cin, int* n_chunks, int* ksteps_last) {
 
 // Fills plan->p (everything except tensor maps' base pointers) and the tensor maps.
 //   a_v/a_lo : source planes with `a_cpitch` channels per pixel, the conv reads channels [a_coff, a_coff+cin)
-//   w_v/w_lo : prepared weight slab [n_tiles_n][n_chunks][ntaps][N][16]
+//   w_slab   : prepared weight slab [n_tiles_n][n_chunks][ntaps][plane][N][16] (see pw::weight_prep_kernel)
 static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a_v, const float* a_lo, int a_cpitch,
-                                 int a_coff, int cin, const float* w_v, const float* w_lo, int cout_padded, int N,
+                                 int a_coff, int cin, const float* w_slab, int cout_padded, int N,
                                  const ConvTaps& taps, const ConvDst& dst, int* error_flag, int num_sms,
                                  size_t smem_limit = 200 * 1024) {
   ConvParams& p = plan->p;
   p = ConvParams{};
   p.src = src; p.N = N; p.dst = dst; p.error_flag = error_flag;
+  p.debug = getenv("SSDN_CONV_DEBUG") ? atoi(getenv("SSDN_CONV_DEBUG")) : 0;
   p.n_tiles_n = cout_padded / N;
   conv_chunks(cin, &p.n_chunks, &p.ksteps_last);
   p.ntaps_total = taps.n;
   p.T = (2 * 2 * N <= 512) ? 2 : 1;
   const long long total = src.total();
   p.n_units_m = (int)((total + 128LL * p.T - 1) / (128LL * p.T));
-  p.b_stages = 6;
-  p.b_plane_bytes = (uint32_t)((N * 64 + 1023) / 1024 * 1024);
+  // B stage = bg consecutive weight slabs (both planes) loaded by ONE TMA op: a TMA instruction costs ~450 clk of the
+  // SM's TMA unit whatever its size (profiles/r01_tma_rate.log), so operands must arrive in few, large boxes.
+  const int n_slabs = p.n_chunks * taps.n;
+  p.bg = (taps.n % 3 == 0) ? 3 : (n_slabs % 3 == 0 ? 3 : (n_slabs % 2 == 0 ? 2 : 1));
+  p.b_stage_bytes = (uint32_t)(p.bg * 2 * N * 64);
   // choose the tap grouping: all taps in one window if it fits in shared memory, else one window per
   // distinct row offset (dy), else one window per tap.
   const int rows_unit = 128 * p.T;
@@ -360,42 +394,50 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
       max_rows = std::max(max_rows, rows_unit + hi - lo);
     }
     int nbox = (max_rows + 255) / 256;
-    int box_rows = ((max_rows + nbox - 1) / nbox + 7) / 8 * 8;
-    uint32_t plane = (uint32_t)((nbox * box_rows * 64 + 1023) / 1024 * 1024);
+    int box_rows = ((max_rows + nbox - 1) / nbox + 15) / 16 * 16;      // multiple of 16 rows => planes/boxes stay 1024-byte aligned
+    if (box_rows > 256) { ++nbox; box_rows = ((max_rows + nbox - 1) / nbox + 15) / 16 * 16; }
+    uint32_t plane = (uint32_t)(nbox * box_rows * 64);
     int stages = (mode == 0) ? 2 : 3;
-    size_t need = (size_t)stages * 2 * plane + (size_t)p.b_stages * 2 * p.b_plane_bytes + 1024;
-    if (need > smem_limit) return false;
-    p.n_groups = (int)gs.size(); p.nbox = nbox; p.box_rows = box_rows; p.a_plane_bytes = plane; p.a_stages = stages;
-    for (size_t gi = 0; gi < gs.size(); ++gi) {
-      int lo = INT32_MAX;
-      for (int t : gs[gi]) lo = std::min(lo, taps.off[t]);
-      TapGroup& tg = p.groups[gi];
-      tg.row_off = lo; tg.ntaps = (int)gs[gi].size();
-      for (size_t k = 0; k < gs[gi].size(); ++k) { tg.tap_id[k] = gs[gi][k]; tg.tap_rel[k] = taps.off[gs[gi][k]] - lo; }
+    for (int bst = 4; bst >= 2; --bst) {
+      const size_t epi = 4 * 32 * convk::kStagePitch * sizeof(float);
+      size_t need = (size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes + epi + 2048;
+      if (need > smem_limit) continue;
+      p.n_groups = (int)gs.size(); p.nbox = nbox; p.box_rows = box_rows; p.a_plane_bytes = plane; p.a_stages = stages; p.b_stages = bst;
+      p.epi_off = (uint32_t)((size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes);
+      for (size_t gi = 0; gi < gs.size(); ++gi) {
+        int lo = INT32_MAX;
+        for (int t : gs[gi]) lo = std::min(lo, taps.off[t]);
+        TapGroup& tg = p.groups[gi];
+        tg.row_off = lo; tg.ntaps = (int)gs[gi].size();
+        for (size_t k = 0; k < gs[gi].size(); ++k) { tg.tap_id[k] = gs[gi][k]; tg.tap_rel[k] = taps.off[gs[gi][k]] - lo; }
+      }
+      plan->smem = need;
+      return true;
     }
-    plan->smem = need;
-    return true;
+    return false;
   };
   if (!try_group(0) && !try_group(1) && !try_group(2)) return -10;
   plan->grid = std::min(p.n_units_m * p.n_tiles_n, num_sms);
-  // tensor maps
-  uint64_t adims[2] = {(uint64_t)cin, (uint64_t)total};
-  uint64_t astr[1] = {(uint64_t)a_cpitch * 4};
-  uint32_t abox[2] = {16, (uint32_t)p.box_rows};
+  // tensor maps.  A: 3-D (channel, flat pixel, plane); the lo plane must follow the hi plane at a constant byte distance.
+  const long long plane_stride = (long long)((const char*)a_lo - (const char*)a_v);
+  if (plane_stride <= 0 || plane_stride % 16) return -11;
+  uint64_t adims[3] = {(uint64_t)cin, (uint64_t)total, 2};
+  uint64_t astr[2] = {(uint64_t)a_cpitch * 4, (uint64_t)plane_stride};
+  uint32_t abox[3] = {16, (uint32_t)p.box_rows, (uint32_t)(p.nbox == 1 ? 2 : 1)};
   int r;
-  if ((r = umma::encode_f32(&plan->a_v, (void*)(a_v + a_coff), 2, adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
-  if ((r = umma::encode_f32(&plan->a_lo, (void*)(a_lo + a_coff), 2, adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
-  uint64_t bdims[2] = {16, (uint64_t)p.n_tiles_n * p.n_chunks * taps.n * N};
-  uint64_t bstr[1] = {64};
-  uint32_t bbox[2] = {16, (uint32_t)N};
-  if ((r = umma::encode_f32(&plan->b_v, (void*)w_v, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
-  if ((r = umma::encode_f32(&plan->b_lo, (void*)w_lo, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+  if ((r = umma::encode_f32(&plan->a, (void*)(a_v + a_coff), 3, adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+  // B: slabs [n_tile][chunk][tap][plane][N][16] -> 3-D (16, N, slab x plane), box = bg slabs x 2 planes
+  uint64_t bdims[3] = {16, (uint64_t)N, (uint64_t)p.n_tiles_n * n_slabs * 2};
+  uint64_t bstr[2] = {64, (uint64_t)N * 64};
+  uint32_t bbox[3] = {16, (uint32_t)N, (uint32_t)(2 * p.bg)};
+  if ((r = umma::encode_f32(&plan->b, (void*)w_slab, 3, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
   return 0;
 }
 
+// floats of the combined (hi + lo) weight slab
 static inline size_t conv_weight_slab_floats(int cin, int cout_padded, int ntaps) {
   int nc, kl; conv_chunks(cin, &nc, &kl);
-  return (size_t)cout_padded * nc * ntaps * 16;
+  return (size_t)cout_padded * nc * ntaps * 16 * 2;
 }
 
 // Optional per-launch timing (bench.py roofline): when enabled every GEMM launch is bracketed by CUDA events.
@@ -411,12 +453,14 @@ inline LaunchProfiler& profiler() { static LaunchProfiler p; return p; }
 static inline cudaError_t conv_launch(const ConvPlan& plan, cudaStream_t stream, int kind = 0) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(convk::conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(convk::conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(convk::conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   if (profiler().on) profiler().begin(kind, plan.flops, stream);
-  convk::conv_igemm_kernel<<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a_v, plan.a_lo, plan.b_v, plan.b_lo, plan.p);
+  if (plan.p.T == 2) convk::conv_igemm_kernel<2><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, plan.p);
+  else convk::conv_igemm_kernel<1><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, plan.p);
   if (profiler().on) profiler().end(stream);
   return cudaGetLastError();
 }

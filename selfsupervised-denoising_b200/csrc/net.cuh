@@ -27,10 +27,10 @@ struct Layer {               // one convolution of the network
   int cin, cout, ksize;
   size_t w_off, b_off;       // offsets (floats) into the flat parameter / gradient buffers
   // forward
-  ConvPlan fwd; float* slab_f_v; float* slab_f_lo; int n_f; int coutp_f;
+  ConvPlan fwd; float* slab_f; int n_f; int coutp_f;
   // data gradient (has_dgrad == false for the first conv: nobody consumes d(input))
   bool has_dgrad = false;
-  ConvPlan dgrad; float* slab_d_v; float* slab_d_lo; int n_d; int cinp_d; int dgrad_nvalid;
+  ConvPlan dgrad; float* slab_d; int n_d; int cinp_d; int dgrad_nvalid;
   // weight gradient
   WgradPlan wgrad; int ksplit;
   const Buf* x; int x_coff;          // conv input (channel slice [x_coff, x_coff+cin))
@@ -132,14 +132,14 @@ class Net {
       l.coutp_f = round_up(l.cout, 16);
       l.n_f = (l.cout == 384) ? 96 : eng::pick_n(l.coutp_f);
       size_t f = conv_weight_slab_floats(l.cin, l.coutp_f, nt);
-      l.slab_f_v = a.take<float>(f); l.slab_f_lo = a.take<float>(f);
+      l.slab_f = a.take<float>(f);
       l.has_dgrad = (l.name != "encode_block_1.0");
       l.dgrad_nvalid = (l.name == "decode_block_1.0") ? 96 : l.cin;       // d(x) part of the last concat is never used
       l.cinp_d = round_up(l.dgrad_nvalid, 16);
       l.n_d = (l.cinp_d == 384) ? 96 : eng::pick_n(l.cinp_d);
       if (l.cinp_d == 144) l.n_d = 144;   // one N=144 tile (T = 1) instead of three smem-bound N=48 tiles
       size_t fd = conv_weight_slab_floats(l.cout, l.cinp_d, nt);
-      l.slab_d_v = a.take<float>(fd); l.slab_d_lo = a.take<float>(fd);
+      l.slab_d = a.take<float>(fd);
     }
     // wgrad partials: one buffer, sized for the largest layer
     partial_floats = 0;
@@ -257,7 +257,7 @@ class Net {
 
   int plan_fwd(Layer& l, Buf& src, int coff, ConvDst d) {
     ConvTaps taps = eng::make_taps(l.ksize, blind, false, src.g.P);
-    int r = conv_plan_init(&l.fwd, src.g, src.v, src.lo, src.cpitch, coff, l.cin, l.slab_f_v, l.slab_f_lo, l.coutp_f, l.n_f, taps, d,
+    int r = conv_plan_init(&l.fwd, src.g, src.v, src.lo, src.cpitch, coff, l.cin, l.slab_f, l.coutp_f, l.n_f, taps, d,
                            flag, sms);
     if (r) return eng::fail(r, "forward plan for %s failed (%d)", l.name.c_str(), r);
     l.fwd.flops = 2.0 * B0(src.g) * l.cin * l.cout * l.ksize * l.ksize;
@@ -265,7 +265,7 @@ class Net {
   }
   int plan_dgrad(Layer& l, Buf& src, ConvDst d) {
     ConvTaps taps = eng::make_taps(l.ksize, blind, true, src.g.P);
-    int r = conv_plan_init(&l.dgrad, src.g, src.v, src.lo, src.cpitch, 0, l.cout, l.slab_d_v, l.slab_d_lo, l.cinp_d, l.n_d, taps, d,
+    int r = conv_plan_init(&l.dgrad, src.g, src.v, src.lo, src.cpitch, 0, l.cout, l.slab_d, l.cinp_d, l.n_d, taps, d,
                            flag, sms);
     if (r) return eng::fail(r, "dgrad plan for %s failed (%d)", l.name.c_str(), r);
     l.dgrad.flops = 2.0 * B0(src.g) * l.dgrad_nvalid * l.cout * l.ksize * l.ksize;
@@ -277,13 +277,13 @@ class Net {
     for (auto& l : layers) {
       const int nt = l.ksize * l.ksize;
       int nc, kl; conv_chunks(l.cin, &nc, &kl);
-      long long n1 = (long long)conv_weight_slab_floats(l.cin, l.coutp_f, nt);
-      pw::weight_prep_kernel<<<pw::grid_for(n1), pw::kBlock, 0, st>>>(params + l.w_off, l.slab_f_v, l.slab_f_lo, l.cout, l.cin, nt, l.cout,
+      long long n1 = (long long)conv_weight_slab_floats(l.cin, l.coutp_f, nt) / 2;
+      pw::weight_prep_kernel<<<pw::grid_for(n1), pw::kBlock, 0, st>>>(params + l.w_off, l.slab_f, l.cout, l.cin, nt, l.cout,
                                                                       l.cin, l.coutp_f / l.n_f, nc, l.n_f, 0);
       if (with_dgrad && l.has_dgrad) {
         conv_chunks(l.cout, &nc, &kl);
-        long long n2 = (long long)conv_weight_slab_floats(l.cout, l.cinp_d, nt);
-        pw::weight_prep_kernel<<<pw::grid_for(n2), pw::kBlock, 0, st>>>(params + l.w_off, l.slab_d_v, l.slab_d_lo, l.cout, l.cin, nt,
+        long long n2 = (long long)conv_weight_slab_floats(l.cout, l.cinp_d, nt) / 2;
+        pw::weight_prep_kernel<<<pw::grid_for(n2), pw::kBlock, 0, st>>>(params + l.w_off, l.slab_d, l.cout, l.cin, nt,
                                                                         l.dgrad_nvalid, l.cout, l.cinp_d / l.n_d, nc, l.n_d, 1);
       }
     }

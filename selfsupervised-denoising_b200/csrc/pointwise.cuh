@@ -145,26 +145,26 @@ __global__ void up_bwd_kernel(const float* __restrict__ g, Geom gg, int g_cpitch
 }
 
 // ---------------------------------------------------------------------------- weights
-// Builds the K-major weight slab [n_tile][chunk][tap][N][16] (v and lo planes) from PyTorch-layout
-// weights W[cout][cin][taps].  transpose == 0 (forward):  slab[n][k] = W[n][k][tap]
-//                              transpose == 1 (data-grad): slab[n][k] = W[k][n][tap]   (n = cin, k = cout)
-__global__ void weight_prep_kernel(const float* __restrict__ w, float* __restrict__ sv, float* __restrict__ slo,
-                                   int cout, int cin, int ntaps, int n_valid, int k_valid, int n_tiles, int n_chunks,
-                                   int N, int transpose) {
+// Builds the K-major weight slab [n_tile][chunk][tap][plane][N][16] (plane 0 = hi, 1 = lo of the tf32 split) from
+// PyTorch-layout weights W[cout][cin][taps].  transpose == 0 (forward):  slab[n][k] = W[n][k][tap]
+//                                           transpose == 1 (data-grad): slab[n][k] = W[k][n][tap]   (n = cin, k = cout)
+__global__ void weight_prep_kernel(const float* __restrict__ w, float* __restrict__ slab, int cout, int cin, int ntaps,
+                                   int n_valid, int k_valid, int n_tiles, int n_chunks, int N, int transpose) {
   const long long total = (long long)n_tiles * n_chunks * ntaps * N * 16;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int kk = (int)(idx % 16); long long t = idx / 16;
-  const int n = (int)(t % N); t /= N;
-  const int tap = (int)(t % ntaps); t /= ntaps;
-  const int ch = (int)(t % n_chunks); const int nt = (int)(t / n_chunks);
+  const int n = (int)(t % N); t /= N;                       // t = slab index ((nt * n_chunks + ch) * ntaps + tap)
+  const int tap = (int)(t % ntaps); const long long tc = t / ntaps;
+  const int ch = (int)(tc % n_chunks); const int nt = (int)(tc / n_chunks);
   const int ng = nt * N + n, k = ch * 16 + kk;
   float val = 0.f;
   if (ng < n_valid && k < k_valid) {
     const long long wi = transpose ? ((long long)k * cin + ng) * ntaps + tap : ((long long)ng * cin + k) * ntaps + tap;
     val = __ldg(w + wi);
   }
-  tf32_split(val, sv[idx], slo[idx]);
+  const long long o = ((t * 2) * N + n) * 16 + kk;
+  tf32_split(val, slab[o], slab[o + (long long)N * 16]);
 }
 
 // ---------------------------------------------------------------------------- bias gradient

@@ -12,6 +12,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp.  Role loops run WARP-UNIFORMLY and only the single-thread instructions
+// (tcgen05.mma / commit, TMA, expect_tx) are predicated with this: operands then stay in uniform registers.
+// Running the whole loop under `if (lane == 0)` instead makes ptxas move every descriptor through R2UR inside an
+// elect "waterfall" loop - measured 184 clk per MMA instead of <= 48 (profiles/r01_umma_rate.log).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -40,16 +50,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a kernel bug must not hang the GPU box. Returns false on timeout.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded spin: a kernel bug must not hang the GPU box.  On expiry the CTA-wide abort word (shared memory) is set;
+// every later wait of the CTA then returns at once, so the kernel drains quickly (its results are garbage and the
+// host sees the error flag).  The return value is deliberately NOT used for control flow by the callers: loop
+// structure stays warp-uniform, which is what lets ptxas keep MMA / TMA operands in uniform registers.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t abort_addr, int* error_flag, int code) {
+  uint32_t aborted;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(aborted) : "r"(abort_addr) : "memory");
+  if (aborted) return;
 #ifdef UMMA_UNBOUNDED_WAIT
   while (!mbar_try_wait(bar, parity)) {}
-  return true;
 #else
+  for (uint32_t i = 0; i < (1u << 22); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(abort_addr), "r"(1u) : "memory");
+  atomicExch(error_flag, code);
+#endif
+}
+// Simple bounded wait for the probes (returns false on timeout).
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t i = 0; i < (1u << 22); ++i)
     if (mbar_try_wait(bar, parity)) return true;
   return false;
-#endif
 }
 
 // ---------------------------------------------------------------- TMA

@@ -35,7 +35,7 @@ struct WgradParams {
 struct WgradPlan {
   WgradParams p;
   double flops = 0;
-  CUtensorMap dz_v, dz_lo, x_v, x_lo;
+  CUtensorMap dz, x;   // 4-D maps (32 channels, flat pixel, channel block, plane): ONE TMA op per operand per stage
   int grid; size_t smem;
 };
 
@@ -45,12 +45,12 @@ constexpr int kThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TM
 constexpr int kMaxStages = 6;
 
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz_v, const __grid_constant__ CUtensorMap map_dz_lo,
-                   const __grid_constant__ CUtensorMap map_x_v, const __grid_constant__ CUtensorMap map_x_lo,
+wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x,
                    const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2];
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t abort_word;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = umma::smem_u32(smem);
   const uint32_t stage_bytes = 2 * (p.a_plane_bytes + p.b_plane_bytes);
@@ -60,6 +60,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz_v, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    abort_word = 0;
     for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full(s), 1); umma::mbar_init(empty(s), 1); }
     umma::mbar_init(acc_full, 1); umma::mbar_init(acc_empty, 128);
     umma::fence_mbar_init();
@@ -74,67 +75,69 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz_v, const __grid_co
   auto decode = [&](int u, int& ks, int& g, int& cb, int& ct) {
     ks = u % p.ksplit; u /= p.ksplit; g = u % p.n_groups; u /= p.n_groups; cb = u % p.n_ci_blocks; ct = u / p.n_ci_blocks;
   };
-  bool ok = true;
+  const uint32_t abort_addr = umma::smem_u32(&abort_word);
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x) {
-        int ks, g, cb, ct; decode(u, ks, g, cb, ct);
-        const int c0 = ks * p.chunks_per_split, c1 = min(p.n_kchunks, c0 + p.chunks_per_split);
-        const int nb = p.ci_nblk[cb];
-        const uint32_t a_blk = p.KC * 128, b_blk = p.b_rows * 128;
-        for (int c = c0; c < c1; ++c) {
-          if (!(ok = umma::mbar_wait(empty(stage), phase ^ 1))) break;
-          umma::mbar_expect_tx(full(stage), 2 * (4 * a_blk + nb * b_blk));
-          const uint32_t av = sbase + stage * stage_bytes, al = av + p.a_plane_bytes;
-          const uint32_t bv = al + p.a_plane_bytes, bl = bv + p.b_plane_bytes;
-          const int row = c * p.KC;
-          for (int k = 0; k < 4; ++k) {
-            umma::tma_load_2d(av + k * a_blk, &map_dz_v, full(stage), ct * 128 + k * 32, row);
-            umma::tma_load_2d(al + k * a_blk, &map_dz_lo, full(stage), ct * 128 + k * 32, row);
-          }
-          for (int k = 0; k < nb; ++k) {
-            umma::tma_load_2d(bv + k * b_blk, &map_x_v, full(stage), p.ci_start[cb] + k * 32, row + p.groups[g].row_off);
-            umma::tma_load_2d(bl + k * b_blk, &map_x_lo, full(stage), p.ci_start[cb] + k * 32, row + p.groups[g].row_off);
-          }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    // ------------------------------------------------------------ TMA producer (warp-uniform loop, elected issue)
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t a_blk = p.KC * 128, b_blk = p.b_rows * 128;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      int ks, g, cb, ct; decode(u, ks, g, cb, ct);
+      const int c0 = ks * p.chunks_per_split, c1 = min(p.n_kchunks, c0 + p.chunks_per_split);
+      for (int c = c0; c < c1; ++c) {
+        umma::mbar_wait(empty(stage), phase ^ 1, abort_addr, p.error_flag, 11);
+        const uint32_t av = sbase + stage * stage_bytes;
+        const uint32_t bv = av + 2 * p.a_plane_bytes;
+        const int row = c * p.KC, brow = row + p.groups[g].row_off;
+        if (umma::elect_one()) {
+          // two TMA ops per stage: [plane][4 co blocks][KC rows][128 B] and [plane][3 ci blocks][b_rows][128 B]
+          umma::mbar_expect_tx(full(stage), 2 * (4 * a_blk + 3 * b_blk));
+          umma::tma_load_4d(av, &map_dz, full(stage), 0, row, ct * 4, 0);
+          umma::tma_load_4d(bv, &map_x, full(stage), 0, brow, p.ci_start[cb] / 32, 0);
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (!ok) atomicExch(p.error_flag, 11);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int it = 0;
-      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x, ++it) {
-        int ks, g, cb, ct; decode(u, ks, g, cb, ct);
-        const int c0 = ks * p.chunks_per_split, c1 = min(p.n_kchunks, c0 + p.chunks_per_split);
-        const int N = p.ci_n[cb];
-        const uint64_t adesc = umma::make_desc_base(p.KC * 128, 512, 1);
-        const uint64_t bdesc = umma::make_desc_base(p.b_rows * 128, 512, 1);
-        const uint32_t idesc = umma::make_idesc_tf32(128, N, 1, 1);
-        if (!(ok = umma::mbar_wait(acc_empty, (it & 1) ^ 1))) break;
+    // ------------------------------------------------------------ MMA issuer: per (stage, tap) an unrolled block of KC/8 x 3 MMAs
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    const uint64_t adesc = umma::make_desc_base(p.KC * 128, 512, 1);
+    const uint64_t bdesc = umma::make_desc_base(p.b_rows * 128, 512, 1);
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+      int ks, g, cb, ct; decode(u, ks, g, cb, ct);
+      const int c0 = ks * p.chunks_per_split, c1 = min(p.n_kchunks, c0 + p.chunks_per_split);
+      const int N = p.ci_n[cb];
+      const uint32_t idesc = umma::make_idesc_tf32(128, N, 1, 1);
+      umma::mbar_wait(acc_empty, (it & 1) ^ 1, abort_addr, p.error_flag, 12);
+      umma::tc_fence_after();
+      uint32_t acc = 0;
+      for (int c = c0; c < c1; ++c) {
+        umma::mbar_wait(full(stage), phase, abort_addr, p.error_flag, 12);
         umma::tc_fence_after();
-        for (int c = c0; c < c1 && ok; ++c) {
-          if (!(ok = umma::mbar_wait(full(stage), phase))) break;
-          umma::tc_fence_after();
-          const uint32_t av = sbase + stage * stage_bytes, al = av + p.a_plane_bytes;
-          const uint32_t bv = al + p.a_plane_bytes, bl = bv + p.b_plane_bytes;
-          for (int t = 0; t < p.groups[g].ntaps; ++t) {
-            const uint32_t d = tmem + t * N;
-            for (int k = 0; k < p.KC / 8; ++k) {
-              const uint32_t ao = k * 8 * 128, bo = (p.groups[g].tap_rel[t] + k * 8) * 128;
-              umma::mma_tf32_ss(d, umma::desc_at(adesc, al + ao), umma::desc_at(bdesc, bv + bo), idesc, !(c == c0 && k == 0));
-              umma::mma_tf32_ss(d, umma::desc_at(adesc, av + ao), umma::desc_at(bdesc, bl + bo), idesc, 1);
-              umma::mma_tf32_ss(d, umma::desc_at(adesc, av + ao), umma::desc_at(bdesc, bv + bo), idesc, 1);
+        const uint32_t av = sbase + stage * stage_bytes, al = av + p.a_plane_bytes;
+        const uint32_t bv0 = al + p.a_plane_bytes;
+        for (int t = 0; t < p.groups[g].ntaps; ++t) {
+          const uint32_t d = tmem + t * N;
+          const uint32_t bv = bv0 + p.groups[g].tap_rel[t] * 128, bl = bv + p.b_plane_bytes;
+          if (umma::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {            // KC == 32: four k-steps of 8 pixels
+              const uint32_t o = k * 8 * 128;
+              umma::mma_tf32_ss(d, umma::desc_at(adesc, al + o), umma::desc_at(bdesc, bv + o), idesc, k == 0 ? acc : 1u);
+              umma::mma_tf32_ss(d, umma::desc_at(adesc, av + o), umma::desc_at(bdesc, bl + o), idesc, 1);
+              umma::mma_tf32_ss(d, umma::desc_at(adesc, av + o), umma::desc_at(bdesc, bv + o), idesc, 1);
             }
           }
-          umma::mma_commit(empty(stage));
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          __syncwarp();
         }
-        umma::mma_commit(acc_full);
+        acc = 1;
+        if (umma::elect_one()) umma::mma_commit(empty(stage));
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (!ok) atomicExch(p.error_flag, 12);
+      if (umma::elect_one()) umma::mma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     const int ew = warp & 3;   // TMEM sub-partition of this warp (warps 2,3,4,5 -> 2,3,0,1)
@@ -142,9 +145,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz_v, const __grid_co
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
       int ks, g, cb, ct; decode(u, ks, g, cb, ct);
       const int N = p.ci_n[cb];
-      if (!umma::mbar_wait(acc_full, it & 1)) ok = false;
-      ok = __all_sync(0xffffffffu, ok);
-      if (!ok) { if (lane == 0) atomicExch(p.error_flag, 13); break; }
+      umma::mbar_wait(acc_full, it & 1, abort_addr, p.error_flag, 13);
       umma::tc_fence_after();
       const int co = ct * 128 + ew * 32 + lane;
       for (int t = 0; t < p.groups[g].ntaps; ++t) {
@@ -235,31 +236,39 @@ static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const floa
   }
   p.b_rows = (p.KC + span + 7) / 8 * 8;
   p.a_plane_bytes = 4 * p.KC * 128;
-  p.b_plane_bytes = (uint32_t)((3 * p.b_rows * 128 + 1023) / 1024 * 1024);
+  p.b_plane_bytes = (uint32_t)(3 * p.b_rows * 128);      // b_rows is a multiple of 8 => 1024-byte multiple
   const uint32_t stage_bytes = 2 * (p.a_plane_bytes + p.b_plane_bytes);
   p.stages = std::min(4, (int)((200 * 1024) / stage_bytes));
   plan->smem = (size_t)p.stages * stage_bytes + 1024;
   p.partial = partial; p.error_flag = error_flag;
   plan->grid = std::min(p.n_co_tiles * p.n_ci_blocks * p.n_groups * p.ksplit, num_sms);
-  uint64_t d1[2] = {(uint64_t)cout, (uint64_t)k_total}; uint64_t s1[1] = {(uint64_t)dz_cpitch * 4}; uint32_t b1[2] = {32, (uint32_t)p.KC};
-  uint64_t d2[2] = {(uint64_t)cin, (uint64_t)k_total}; uint64_t s2[1] = {(uint64_t)x_cpitch * 4}; uint32_t b2[2] = {32, (uint32_t)p.b_rows};
+  // 4-D maps: (32 channels of a block, flat pixel, channel block [stride 128 B], plane).  The block dimension has a
+  // smaller stride than the pixel dimension; cuTensorMapEncodeTiled accepts that (profiles/r01_tma_map_test.log) and the
+  // box then lands in shared memory as [plane][block][pixel][32 ch], exactly the MN-major operand layout.
+  const long long dz_plane = (long long)((const char*)dz_lo - (const char*)dz_v), x_plane = (long long)((const char*)x_lo - (const char*)x_v);
+  if (dz_plane <= 0 || x_plane <= 0 || dz_plane % 16 || x_plane % 16) return -11;
+  if (p.b_plane_bytes != (uint32_t)(3 * p.b_rows * 128)) return -12;
+  uint64_t d1[4] = {32, (uint64_t)k_total, (uint64_t)((cout + 31) / 32), 2};
+  uint64_t s1[3] = {(uint64_t)dz_cpitch * 4, 128, (uint64_t)dz_plane};
+  uint32_t b1[4] = {32, (uint32_t)p.KC, 4, 2};
+  uint64_t d2[4] = {32, (uint64_t)k_total, (uint64_t)((cin + 31) / 32), 2};
+  uint64_t s2[3] = {(uint64_t)x_cpitch * 4, 128, (uint64_t)x_plane};
+  uint32_t b2[4] = {32, (uint32_t)p.b_rows, 3, 2};
   int r;
-  if ((r = umma::encode_f32(&plan->dz_v, (void*)(dz_v + dz_coff), 2, d1, s1, b1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
-  if ((r = umma::encode_f32(&plan->dz_lo, (void*)(dz_lo + dz_coff), 2, d1, s1, b1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
-  if ((r = umma::encode_f32(&plan->x_v, (void*)(x_v + x_coff), 2, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
-  if ((r = umma::encode_f32(&plan->x_lo, (void*)(x_lo + x_coff), 2, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
+  if ((r = umma::encode_f32(&plan->dz, (void*)(dz_v + dz_coff), 4, d1, s1, b1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
+  if ((r = umma::encode_f32(&plan->x, (void*)(x_v + x_coff), 4, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
   return 0;
 }
 
 static inline cudaError_t wgrad_launch(const WgradPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgradk::wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(wgradk::wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   if (profiler().on) profiler().begin(2, plan.flops, stream);
-  wgradk::wgrad_igemm_kernel<<<plan.grid, wgradk::kThreads, plan.smem, stream>>>(plan.dz_v, plan.dz_lo, plan.x_v, plan.x_lo, plan.p);
+  wgradk::wgrad_igemm_kernel<<<plan.grid, wgradk::kThreads, plan.smem, stream>>>(plan.dz, plan.x, plan.p);
   if (profiler().on) profiler().end(stream);
   return cudaGetLastError();
 }

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "ssdn_net_kernel_launches": (_I, [_P, _I]),
     "ssdn_profile_begin": (_I, []),
     "ssdn_profile_end": (_I, [ctypes.POINTER(c_double)]),
+    "ssdn_profile_records": (_I, [ctypes.POINTER(c_double), _I]),
     "ssdn_net_debug_write": (_I, [_P, ctypes.c_char_p, _I, _P, _P]),
     "ssdn_net_debug_read": (_I, [_P, ctypes.c_char_p, _I, _I, _P, ctypes.POINTER(c_int), _P]),
     "ssdn_rot4_stack": (_I, [_P, _P] + [_I] * 4 + [_P]),
@@ -308,3 +309,11 @@ def profile_end():
     buf = (c_double * 9)()
     check(lib().ssdn_profile_end(buf))
     return {k: (int(buf[3 * i]), buf[3 * i + 1], buf[3 * i + 2]) for i, k in enumerate(("conv_fwd", "conv_dgrad", "wgrad"))}
+
+
+def profile_records(max_records=512):
+    """[(kind, ms, algorithmic FLOPs)] per tensor-core launch of the last profiled region, in launch order."""
+    buf = (c_double * (3 * max_records))()
+    n = min(lib().ssdn_profile_records(buf, max_records), max_records)
+    kinds = ("conv_fwd", "conv_dgrad", "wgrad")
+    return [(kinds[int(buf[3 * i])], buf[3 * i + 1], buf[3 * i + 2]) for i in range(n)]
