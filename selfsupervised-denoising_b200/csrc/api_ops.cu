@@ -135,10 +135,7 @@ extern "C" int ssdn_conv2d_backward_weight(void* ws, size_t ws_bytes, const floa
   }
   if (db) {
     const long long rows = g.total();
-    const int rpb = (int)((rows + 1023) / 1024);
-    const int nblk = (int)((rows + rpb - 1) / rpb);
-    pw::colsum_stage1_kernel<<<nblk, 256, 8 * cout * sizeof(float), st>>>(yv, yl, rows, yp, 0, cout, colpart, rpb);
-    pw::colsum_stage2_kernel<<<(cout + 127) / 128, 128, 0, st>>>(colpart, nblk, cout, db, 0);
+    pw::colsum_launch(yv, yl, rows, yp, 0, cout, colpart, db, st);
   }
   int hflag = 0;
   SSDN_CUDA(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));

@@ -333,10 +333,7 @@ class Net {
     wgradk::wgrad_reduce_kernel<<<pw::grid_for((long long)l.cout * l.cin * nt), pw::kBlock, 0, st>>>(partial, l.wgrad.p.ksplit, nt, l.cout,
                                                                                                    l.cin, grads + l.w_off, 0);
     const long long rows = l.dz->g.total();
-    const int rpb = (int)((rows + 1023) / 1024);
-    const int nblk = (int)((rows + rpb - 1) / rpb);
-    pw::colsum_stage1_kernel<<<nblk, 256, 8 * l.cout * sizeof(float), st>>>(l.dz->v, l.dz->lo, rows, l.dz->cpitch, 0, l.cout, colpart, rpb);
-    pw::colsum_stage2_kernel<<<(l.cout + 127) / 128, 128, 0, st>>>(colpart, nblk, l.cout, grads + l.b_off, 0);
+    pw::colsum_launch(l.dz->v, l.dz->lo, rows, l.dz->cpitch, 0, l.cout, colpart, grads + l.b_off, st);
     return 0;
   }
   int run_dgrad(Layer& l, cudaStream_t st) { SSDN_CUDA(conv_launch(l.dgrad, st, 1)); return 0; }

@@ -168,13 +168,15 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, float* __restric
 }
 
 // ---------------------------------------------------------------------------- bias gradient
-// db[c] = sum over flat pixels of dZ[flat][c].  Two deterministic stages.
+// db[c] = sum over flat pixels of dZ[flat][c] (hi + lo planes).  Two deterministic stages: kColsumBlocks strips of rows,
+// then a fixed-order reduction of the strip partials.
+constexpr int kColsumBlocks = 296;
 __global__ void colsum_stage1_kernel(const float* __restrict__ dz, const float* __restrict__ dz_lo, long long rows, int cpitch, int coff, int C,
-                                     float* __restrict__ partial, int rows_per_block) {
+                                     float* __restrict__ partial) {
   extern __shared__ float sm[];   // [warps][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
   for (int c = lane; c < C; c += 32) {
     float acc = 0.f;
     for (long long r = r0 + warp; r < r1; r += nwarps) acc += __ldg(dz + r * cpitch + coff + c) + __ldg(dz_lo + r * cpitch + coff + c);
@@ -187,13 +189,64 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ dz, const float* 
     partial[(long long)blockIdx.x * C + c] = acc;
   }
 }
-__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out,
-                                     int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// Fast path of stage 1 for dense tensors (cpitch == C, C % 4 == 0): the planes are flat float4 arrays in which a thread
+// that advances by a multiple of C/4 float4s always stays in the same channel quad, so every access is coalesced and many
+// independent loads are in flight.  blockDim.x must be a multiple of C/4.
+__global__ void colsum_flat_kernel(const float4* __restrict__ hi, const float4* __restrict__ lo, long long total_f4, int C4,
+                                   float* __restrict__ partial) {
+  extern __shared__ float4 sm4[];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < total_f4; i += 4 * stride) {
+    float4 a0 = __ldg(hi + i), a1 = __ldg(hi + i + stride), a2 = __ldg(hi + i + 2 * stride), a3 = __ldg(hi + i + 3 * stride);
+    float4 b0 = __ldg(lo + i), b1 = __ldg(lo + i + stride), b2 = __ldg(lo + i + 2 * stride), b3 = __ldg(lo + i + 3 * stride);
+    acc.x += ((a0.x + b0.x) + (a1.x + b1.x)) + ((a2.x + b2.x) + (a3.x + b3.x));
+    acc.y += ((a0.y + b0.y) + (a1.y + b1.y)) + ((a2.y + b2.y) + (a3.y + b3.y));
+    acc.z += ((a0.z + b0.z) + (a1.z + b1.z)) + ((a2.z + b2.z) + (a3.z + b3.z));
+    acc.w += ((a0.w + b0.w) + (a1.w + b1.w)) + ((a2.w + b2.w) + (a3.w + b3.w));
+  }
+  for (; i < total_f4; i += stride) {
+    const float4 a = __ldg(hi + i), b = __ldg(lo + i);
+    acc.x += a.x + b.x; acc.y += a.y + b.y; acc.z += a.z + b.z; acc.w += a.w + b.w;
+  }
+  sm4[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < C4) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = threadIdx.x; k < blockDim.x; k += C4) { const float4 v = sm4[k]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    reinterpret_cast<float4*>(partial + (long long)blockIdx.x * C4 * 4)[threadIdx.x] = t;
+  }
+}
+// Launch helper: picks the flat fast path when the layout allows it.
+static inline void colsum_launch(const float* hi, const float* lo, long long rows, int cpitch, int coff, int C, float* partial, float* out,
+                                 cudaStream_t st);
+
+// grid = ceil(C / 32), block = (32, 8): thread (lane, w) sums partials w, w+8, ... of channel blockIdx.x*32 + lane
+__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out, int accumulate) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int b = 0; b < nblk; ++b) acc += partial[(long long)b * C + c];
-  out[c] = accumulate ? out[c] + acc : acc;
+  if (c < C) for (int b = threadIdx.y; b < nblk; b += 8) acc += partial[(long long)b * C + c];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+static inline void colsum_launch(const float* hi, const float* lo, long long rows, int cpitch, int coff, int C, float* partial, float* out,
+                                 cudaStream_t st) {
+  if (cpitch == C && coff == 0 && C % 4 == 0 && C / 4 <= 256) {
+    const int C4 = C / 4, block = 256 / C4 * C4;
+    colsum_flat_kernel<<<kColsumBlocks, block, block * sizeof(float4), st>>>(reinterpret_cast<const float4*>(hi), reinterpret_cast<const float4*>(lo),
+                                                                             rows * C4, C4, partial);
+  } else {
+    colsum_stage1_kernel<<<kColsumBlocks, 256, 8 * C * sizeof(float), st>>>(hi, lo, rows, cpitch, coff, C, partial);
+  }
+  colsum_stage2_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, kColsumBlocks, C, out, 0);
 }
 
 }  // namespace pw

@@ -23,11 +23,12 @@ struct WgradParams {
   long long k_total;
   int KC, n_kchunks, ksplit, chunks_per_split;
   int n_co_tiles, cout, cin;
-  int n_ci_blocks, ci_start[4], ci_n[4], ci_nblk[4];
+  int n_ci_blocks, ci_start[4], ci_n[4];
+  int nba, nbx;        // 32-channel blocks actually loaded per stage for dZ (<= 4) and X (<= 6)
   int n_groups, ntaps_total;
   WgradGroup groups[9];
   int b_rows, stages;
-  uint32_t a_plane_bytes, b_plane_bytes;
+  uint32_t a_plane_bytes, b_plane_bytes;   // a_plane_bytes = nba * KC * 128 (loaded part; the MMA may address up to 4 blocks)
   float* partial;     // [ksplit][ntaps][cout][cin]
   int* error_flag;
 };
@@ -90,8 +91,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
         const uint32_t bv = av + 2 * p.a_plane_bytes;
         const int row = c * p.KC, brow = row + p.groups[g].row_off;
         if (umma::elect_one()) {
-          // two TMA ops per stage: [plane][4 co blocks][KC rows][128 B] and [plane][3 ci blocks][b_rows][128 B]
-          umma::mbar_expect_tx(full(stage), 2 * (4 * a_blk + 3 * b_blk));
+          // two TMA ops per stage: [plane][nba co blocks][KC rows][128 B] and [plane][nbx ci blocks][b_rows][128 B]
+          umma::mbar_expect_tx(full(stage), 2 * (p.a_plane_bytes + p.b_plane_bytes));
           umma::tma_load_4d(av, &map_dz, full(stage), 0, row, ct * 4, 0);
           umma::tma_load_4d(bv, &map_x, full(stage), 0, brow, p.ci_start[cb] / 32, 0);
         }
@@ -190,6 +191,9 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int kspli
 // ------------------------------------------------------------------------------------------ host
 #include <algorithm>
 
+static inline int wgrad_ci_cap(int ntaps) { return ntaps == 9 ? 144 : 192; }   // widest ci block (MMA N) per unit
+static inline int wgrad_n_ci_blocks(int cin, int ntaps) { const int c16 = (cin + 15) / 16 * 16; return (c16 + wgrad_ci_cap(ntaps) - 1) / wgrad_ci_cap(ntaps); }
+
 static inline size_t wgrad_partial_floats(int ksplit, int ntaps, int cout, int cin) {
   return (size_t)ksplit * ntaps * cout * cin;
 }
@@ -197,7 +201,7 @@ static inline size_t wgrad_partial_floats(int ksplit, int ntaps, int cout, int c
 // Decides the K split for a layer (so that the grid fills the chip) without needing pointers.
 static inline int wgrad_pick_ksplit(long long k_total, int cout, int cin, int ntaps, int num_sms, int KC = 32) {
   const int n_kchunks = (int)((k_total + KC - 1) / KC);
-  const int n_co_tiles = (cout + 127) / 128, n_ci_blocks = (cin + 95) / 96, n_groups = ntaps == 9 ? 3 : ntaps;
+  const int n_co_tiles = (cout + 127) / 128, n_ci_blocks = wgrad_n_ci_blocks(cin, ntaps), n_groups = ntaps == 9 ? 3 : ntaps;
   const int others = n_co_tiles * n_ci_blocks * n_groups;
   int ks = std::max(1, (2 * num_sms + others - 1) / others);
   ks = std::min(ks, std::max(1, n_kchunks / 4));
@@ -215,12 +219,19 @@ static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const floa
   p.k_total = k_total; p.KC = 32; p.n_kchunks = (int)((k_total + p.KC - 1) / p.KC);
   p.ksplit = ksplit; p.chunks_per_split = (p.n_kchunks + ksplit - 1) / ksplit;
   p.cout = cout; p.cin = cin; p.n_co_tiles = (cout + 127) / 128;
+  // ci blocks: as wide as TMEM allows (3 taps x N <= 512 columns, N <= 256), so that dZ is streamed as few times as possible
+  const int cap = wgrad_ci_cap(taps.n);
   p.n_ci_blocks = 0;
-  for (int c = 0; c < cin; c += 96) {
-    const int rem = std::min(96, cin - c);
-    p.ci_start[p.n_ci_blocks] = c; p.ci_n[p.n_ci_blocks] = (rem + 15) / 16 * 16; p.ci_nblk[p.n_ci_blocks] = (rem + 31) / 32;
+  const int cin16 = (cin + 15) / 16 * 16;
+  const int nblocks = (cin16 + cap - 1) / cap;
+  const int per = ((cin16 + nblocks - 1) / nblocks + 31) / 32 * 32;      // block starts must be multiples of 32 channels
+  for (int c = 0; c < cin; c += per) {
+    const int rem = std::min(per, cin - c);
+    p.ci_start[p.n_ci_blocks] = c; p.ci_n[p.n_ci_blocks] = (rem + 15) / 16 * 16;
     ++p.n_ci_blocks;
   }
+  p.nbx = (p.ci_n[0] + 31) / 32;
+  p.nba = std::min(4, (cout + 31) / 32);
   p.ntaps_total = taps.n;
   int span = 0;
   if (taps.n == 9) {
@@ -235,11 +246,11 @@ static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const floa
     for (int g = 0; g < taps.n; ++g) { p.groups[g].row_off = taps.off[g]; p.groups[g].ntaps = 1; p.groups[g].tap_id[0] = g; p.groups[g].tap_rel[0] = 0; }
   }
   p.b_rows = (p.KC + span + 7) / 8 * 8;
-  p.a_plane_bytes = 4 * p.KC * 128;
-  p.b_plane_bytes = (uint32_t)(3 * p.b_rows * 128);      // b_rows is a multiple of 8 => 1024-byte multiple
+  p.a_plane_bytes = p.nba * p.KC * 128;                    // the MMA addresses 4 co blocks; blocks >= nba alias whatever follows (ignored lanes)
+  p.b_plane_bytes = (uint32_t)(p.nbx * p.b_rows * 128);    // b_rows is a multiple of 8 => 1024-byte multiple
   const uint32_t stage_bytes = 2 * (p.a_plane_bytes + p.b_plane_bytes);
-  p.stages = std::min(4, (int)((200 * 1024) / stage_bytes));
-  plan->smem = (size_t)p.stages * stage_bytes + 1024;
+  p.stages = std::max(2, std::min(4, (int)((200 * 1024) / stage_bytes)));
+  plan->smem = (size_t)p.stages * stage_bytes + 4 * p.KC * 128 + 1024;   // slack so that aliased co blocks stay inside the allocation
   p.partial = partial; p.error_flag = error_flag;
   plan->grid = std::min(p.n_co_tiles * p.n_ci_blocks * p.n_groups * p.ksplit, num_sms);
   // 4-D maps: (32 channels of a block, flat pixel, channel block [stride 128 B], plane).  The block dimension has a
@@ -247,13 +258,12 @@ static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const floa
   // box then lands in shared memory as [plane][block][pixel][32 ch], exactly the MN-major operand layout.
   const long long dz_plane = (long long)((const char*)dz_lo - (const char*)dz_v), x_plane = (long long)((const char*)x_lo - (const char*)x_v);
   if (dz_plane <= 0 || x_plane <= 0 || dz_plane % 16 || x_plane % 16) return -11;
-  if (p.b_plane_bytes != (uint32_t)(3 * p.b_rows * 128)) return -12;
   uint64_t d1[4] = {32, (uint64_t)k_total, (uint64_t)((cout + 31) / 32), 2};
   uint64_t s1[3] = {(uint64_t)dz_cpitch * 4, 128, (uint64_t)dz_plane};
-  uint32_t b1[4] = {32, (uint32_t)p.KC, 4, 2};
+  uint32_t b1[4] = {32, (uint32_t)p.KC, (uint32_t)p.nba, 2};
   uint64_t d2[4] = {32, (uint64_t)k_total, (uint64_t)((cin + 31) / 32), 2};
   uint64_t s2[3] = {(uint64_t)x_cpitch * 4, 128, (uint64_t)x_plane};
-  uint32_t b2[4] = {32, (uint32_t)p.b_rows, 3, 2};
+  uint32_t b2[4] = {32, (uint32_t)p.b_rows, (uint32_t)p.nbx, 2};
   int r;
   if ((r = umma::encode_f32(&plan->dz, (void*)(dz_v + dz_coff), 4, d1, s1, b1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
   if ((r = umma::encode_f32(&plan->x, (void*)(x_v + x_coff), 4, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;

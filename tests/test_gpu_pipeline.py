@@ -70,7 +70,7 @@ def test_training_trajectory_matches_reference(engine):
         # parameters whose gradient is ~0 move by +-lr depending on rounding noise, in any implementation
         assert rel(out[PipelineOutput.LOSS], gold["losses"][k]) < (TOL if k == 0 else 1e-2), k
     main = den.get_model(ssdn.Denoiser.MODEL, False)
-    final = {k: p.data for k, p in main.named_parameters()}
+    final = {k: p.data.cpu() for k, p in main.named_parameters()}
     assert rel_l2(C.grad_summary(final)[:, 1], gold["final_summary"][:, 1]) < 1e-3     # parameter norms after 3 steps
 
 

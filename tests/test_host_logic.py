@@ -104,6 +104,7 @@ def test_unsupported_pipeline_raises():
     den = ssdn.Denoiser.__new__(ssdn.Denoiser)
     torch.nn.Module.__init__(den)
     den.cfg = cfg
+    den.device = torch.device("cpu")
     with pytest.raises(NotImplementedError):
         den.run_pipeline([torch.zeros(1, 3, 32, 32)])
 
