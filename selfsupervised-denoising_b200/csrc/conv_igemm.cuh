@@ -62,6 +62,51 @@ struct Ring {
 
 constexpr int kStagePitch = 36;   // floats per staged pixel row (32 channels + 4 pad: conflict-free float4 access)
 
+// Copy-out of one staged slice (CW = 32 or 16 channels x 32 pixels of this warp).  CW/4 consecutive lanes write one
+// pixel's contiguous bytes.  All shared-memory reads and the (read-only) activation loads of the slice are issued
+// before the first store, so their latencies overlap instead of serialising pass after pass.
+template <int CW>
+__device__ __forceinline__ void copy_out_slice(const ConvDst& d, const float* stage, const int (*s_dst)[4], const int* s_meta,
+                                               const int* s_src, int lane, int cg0, int act_c0) {
+  constexpr int L = CW / 4, PPI = 32 / L, PASSES = 32 / PPI;
+  const int sub = lane / L, f = lane - sub * L;
+  const int cg = cg0 + 4 * f;
+  if (cg >= d.cvalid) return;
+  float4 v[PASSES]; float4 a[PASSES]; int meta[PASSES]; int dp0[PASSES];
+#pragma unroll
+  for (int q = 0; q < PASSES; ++q) {
+    const int px = q * PPI + sub;
+    meta[q] = s_meta[px];
+    dp0[q] = s_dst[px][0];
+    v[q] = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 4 * f);
+    if ((d.flags & EP_ACT_GRAD) && (meta[q] & 7)) {
+      const long long ai = (d.flags & EP_ACT_AT_SRC) ? (long long)s_src[px] * d.act_cpitch + d.act_coff + act_c0 + 4 * f
+                                                     : (long long)dp0[q] * d.act_cpitch + d.act_coff + cg;
+      a[q] = __ldg(reinterpret_cast<const float4*>(d.act + ai));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PASSES; ++q) {
+    const int nd = meta[q] & 7;
+    if (nd == 0) continue;
+    float4 o = v[q];
+    if (meta[q] & 8) o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d.flags & EP_ACT_GRAD) {
+      o.x = a[q].x > 0.f ? o.x : SSDN_LRELU_SLOPE * o.x; o.y = a[q].y > 0.f ? o.y : SSDN_LRELU_SLOPE * o.y;
+      o.z = a[q].z > 0.f ? o.z : SSDN_LRELU_SLOPE * o.z; o.w = a[q].w > 0.f ? o.w : SSDN_LRELU_SLOPE * o.w;
+    }
+    float4 h = o, l = o;
+    if (d.flags & EP_WRITE_LO) { tf32_split(o.x, h.x, l.x); tf32_split(o.y, h.y, l.y); tf32_split(o.z, h.z, l.z); tf32_split(o.w, h.w, l.w); }
+    const int coff = d.coff + (meta[q] >> 8) + cg;
+    const int px = q * PPI + sub;
+    for (int k = 0; k < nd; ++k) {
+      const long long oi = (long long)(k == 0 ? dp0[q] : s_dst[px][k]) * d.cpitch + coff;
+      *reinterpret_cast<float4*>(d.v + oi) = h;
+      if (d.flags & EP_WRITE_LO) *reinterpret_cast<float4*>(d.lo + oi) = l;
+    }
+  }
+}
+
 template <int T>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -294,40 +339,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           for (int i = 0; i < 32; i += 4)
             if (i < cw) *reinterpret_cast<uint4*>(row + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
           __syncwarp();
-          // copy-out: L lanes per pixel, 32 / L pixels per pass
-          const int L = cw >> 2, sub = lane / L, f = lane - sub * L, ppi = 32 / L;
-          const int cg = cg0 + 4 * f;
-          if (cg < d.cvalid) {
-            for (int p0 = 0; p0 < 32; p0 += ppi) {
-              const int px = p0 + sub;
-              const int meta = s_meta[ew][px];
-              const int nd = meta & 7;
-              if (nd == 0) continue;
-              float4 v = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 4 * f);
-              if (meta & 8) v = make_float4(0.f, 0.f, 0.f, 0.f);
-              const int coff = d.coff + (meta >> 8) + cg;
-              for (int k = 0; k < nd; ++k) {
-                const long long dpix = s_dst[ew][px][k];
-                float4 o = v;
-                if (d.flags & EP_ACT_GRAD) {
-                  const long long ai = (d.flags & EP_ACT_AT_SRC) ? (long long)s_src[ew][px] * d.act_cpitch + d.act_coff + nt * p.N + c0 + 4 * f
-                                                                 : dpix * d.act_cpitch + d.act_coff + cg;
-                  const float4 a = __ldg(reinterpret_cast<const float4*>(d.act + ai));
-                  o.x = a.x > 0.f ? o.x : SSDN_LRELU_SLOPE * o.x; o.y = a.y > 0.f ? o.y : SSDN_LRELU_SLOPE * o.y;
-                  o.z = a.z > 0.f ? o.z : SSDN_LRELU_SLOPE * o.z; o.w = a.w > 0.f ? o.w : SSDN_LRELU_SLOPE * o.w;
-                }
-                const long long oi = dpix * d.cpitch + coff;
-                if (d.flags & EP_WRITE_LO) {
-                  float4 h, l;
-                  tf32_split(o.x, h.x, l.x); tf32_split(o.y, h.y, l.y); tf32_split(o.z, h.z, l.z); tf32_split(o.w, h.w, l.w);
-                  *reinterpret_cast<float4*>(d.v + oi) = h;
-                  *reinterpret_cast<float4*>(d.lo + oi) = l;
-                } else {
-                  *reinterpret_cast<float4*>(d.v + oi) = o;
-                }
-              }
-            }
-          }
+          if (cw == 32) copy_out_slice<32>(d, stage, s_dst[ew], s_meta[ew], s_src[ew], lane, cg0, nt * p.N + c0);
+          else copy_out_slice<16>(d, stage, s_dst[ew], s_meta[ew], s_src[ew], lane, cg0, nt * p.N + c0);
           __syncwarp();
         }
       }
