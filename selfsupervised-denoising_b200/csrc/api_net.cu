@@ -64,6 +64,9 @@ extern "C" int ssdn_net_debug_write(void* handle, const char* name, int c, const
   if (c > b->cpitch) return fail(-1, "buffer '%s' has only %d channels", name, b->cpitch);
   const long long n = (long long)b->g.B * c * b->g.H * b->g.W;
   pw::pack_nchw_kernel<<<pw::grid_for(n), pw::kBlock, 0, (cudaStream_t)stream>>>(src, b->v, b->lo, b->g.B, c, b->g.H, b->g.W, b->g, b->cpitch, 0, 0);
+  if (b->mask)
+    pw::mask_from_planes_kernel<<<pw::grid_for(b->g.total() * b->mask_words), pw::kBlock, 0, (cudaStream_t)stream>>>(b->v, b->g.total(), b->cpitch,
+                                                                                                                  b->mask, b->mask_words);
   SSDN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -96,8 +99,10 @@ extern "C" int ssdn_profile_records(double* out, int max_records) {
 }
 extern "C" int ssdn_net_kernel_launches(void* handle, int training) {
   net::Net* nn = (net::Net*)handle;
-  int fwd = (int)nn->layers.size() /*conv*/ + 5 /*pool*/ + 1 /*pack*/ + (int)nn->layers.size() * (training ? 2 : 1) - (training ? 1 : 0);
-  int bwd = 1 + (int)nn->layers.size() * 4 /*wgrad, reduce, colsum x2*/ + ((int)nn->layers.size() - 1) /*dgrad*/ + 5 + 5;
+  int nfused = 0;
+  for (auto& l : nn->layers) nfused += l.bias_fused ? 1 : 0;
+  int fwd = (int)nn->layers.size() /*conv*/ + 5 /*pool*/ + 1 /*pack*/ + 1 /*weight slabs*/;
+  int bwd = 1 + (int)nn->layers.size() * 4 /*wgrad, reduce, colsum x2*/ - nfused /*fused column sums*/ + ((int)nn->layers.size() - 1) /*dgrad*/ + 5 + 5;
   return training ? fwd + bwd : fwd;
 }
 

@@ -60,11 +60,15 @@ enum : int {
 enum : int {
   EP_BIAS = 1,        // add bias[c]
   EP_LRELU = 2,       // LeakyReLU(0.1)
-  EP_ACT_GRAD = 4,    // multiply by LeakyReLU'(act) where act is the forward activation at the destination
+  EP_ACT_GRAD = 4,    // multiply by LeakyReLU'(act): the sign bits of the forward activation come from mask_in
   EP_WRITE_LO = 8,    // destination is a GEMM operand: write the (hi, lo) tf32 split instead of the plain value
-  EP_ACT_AT_SRC = 16  // EP_ACT_GRAD reads the activation at the SOURCE pixel / true GEMM channel
+  EP_ACT_AT_SRC = 16  // EP_ACT_GRAD indexes mask_in by the SOURCE pixel / true GEMM channel (instead of the destination's)
 };
 
+// LeakyReLU sign masks: one bit per (pixel, channel) of an activation tensor, word w of a pixel holds channels
+// [32w, 32w+32).  The forward epilogue that produces an activation writes them (mask_out); the data-gradient epilogue
+// whose output is multiplied by LeakyReLU'(that activation) reads them (mask_in) - 1/32 of the bytes of re-reading the
+// activation, fetched before the accumulator is ready.
 struct ConvDst {
   float* v; float* lo;           // destination planes: (hi, lo) when EP_WRITE_LO, else v = plain fp32
   int cpitch, coff;              // channels per destination pixel, channel offset of this conv's output
@@ -73,5 +77,8 @@ struct ConvDst {
   int cvalid;                    // number of real output channels (<= n_tiles * N)
   int nimg;                      // images per rotation group (MAP_UNROT / MAP_UNROT_INV)
   const float* bias;
-  const float* act; int act_cpitch, act_coff;   // forward activation for EP_ACT_GRAD (destination geometry)
+  uint32_t* mask_out; int mask_out_words;        // EP_LRELU: sign bits of the written activation, [destination pixel][words]
+  const uint32_t* mask_in; int mask_in_words;    // EP_ACT_GRAD: sign bits of the forward activation, [pixel][words]
+  float* colsum; int colsum_pitch;               // optional: per-(CTA, epilogue warp) column sums of the written values
+                                                 // [gridDim.x * 4][colsum_pitch] (bias gradient of the consuming layer)
 };

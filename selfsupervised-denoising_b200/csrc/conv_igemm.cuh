@@ -35,11 +35,13 @@ struct ConvParams {
   int nbox, box_rows; // every group window is loaded as nbox TMA boxes of box_rows rows (one op for both planes if nbox == 1)
   int a_stages, b_stages;
   int bg;             // weight slabs ((chunk, tap) pairs, in consumption order) per B stage: ONE TMA op loads bg x 2 planes
+  int row3;           // 1: every B stage holds the 3 taps of one stencil row of one group, tap_rel advancing by tap_step
+  int tap_step;       //    (+1 forward, -1 data-gradient): the MMA warp then issues 3 x T x 6 MMAs per barrier wait
   uint32_t a_plane_bytes, b_stage_bytes;   // smem bytes of one A plane of one stage / of one B stage
-  uint32_t epi_off;   // byte offset of the epilogue staging area (4 warps x 32 pixels x 36 floats) in dynamic smem
   ConvDst dst;
   int* error_flag;
   int debug;          // experiments only: 2 = skip MMA issue
+  unsigned long long* stats;   // developer instrumentation (SSDN_CONV_STATS=1): per-CTA clocks spent in each role's waits
 };
 
 struct ConvPlan {
@@ -60,50 +62,59 @@ struct Ring {
   __device__ void advance() { if (++stage == n) { stage = 0; phase ^= 1; } }
 };
 
-constexpr int kStagePitch = 36;   // floats per staged pixel row (32 channels + 4 pad: conflict-free float4 access)
+constexpr int kMaxSlices = 5;     // 32-channel slices of one N tile (N <= 144 + padding)
 
-// Copy-out of one staged slice (CW = 32 or 16 channels x 32 pixels of this warp).  CW/4 consecutive lanes write one
-// pixel's contiguous bytes.  All shared-memory reads and the (read-only) activation loads of the slice are issued
-// before the first store, so their latencies overlap instead of serialising pass after pass.
-template <int CW>
-__device__ __forceinline__ void copy_out_slice(const ConvDst& d, const float* stage, const int (*s_dst)[4], const int* s_meta,
-                                               const int* s_src, int lane, int cg0, int act_c0) {
-  constexpr int L = CW / 4, PPI = 32 / L, PASSES = 32 / PPI;
-  const int sub = lane / L, f = lane - sub * L;
-  const int cg = cg0 + 4 * f;
-  if (cg >= d.cvalid) return;
-  float4 v[PASSES]; float4 a[PASSES]; int meta[PASSES]; int dp0[PASSES];
-#pragma unroll
-  for (int q = 0; q < PASSES; ++q) {
-    const int px = q * PPI + sub;
-    meta[q] = s_meta[px];
-    dp0[q] = s_dst[px][0];
-    v[q] = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 4 * f);
-    if ((d.flags & EP_ACT_GRAD) && (meta[q] & 7)) {
-      const long long ai = (d.flags & EP_ACT_AT_SRC) ? (long long)s_src[px] * d.act_cpitch + d.act_coff + act_c0 + 4 * f
-                                                     : (long long)dp0[q] * d.act_cpitch + d.act_coff + cg;
-      a[q] = __ldg(reinterpret_cast<const float4*>(d.act + ai));
-    }
+// What the epilogue needs to know about one lane's pixel of one 128-pixel tile.  Computed one tile ahead so that the
+// LeakyReLU sign-mask words (the only global LOADS of the epilogue) are in flight while the previous tile is written.
+struct LanePixel {
+  int d0;            // destination flat pixel (first of 1 or 4), or source flat pixel for MAP_NCHW bookkeeping
+  int nd;            // number of destinations (0 = halo / out of range: nothing is written)
+  int zero;          // write zeros (row shifted in by Shift2d)
+  int cshift;        // channel shift of the destination (rotation branch block)
+  int b, y, x;       // image / row / column of the source pixel (MAP_NCHW)
+  uint32_t mw[kMaxSlices];   // sign-mask words of the slices (EP_ACT_GRAD)
+};
+
+__device__ __forceinline__ void lane_pixel(const ConvParams& p, int um, int nt, int tile, int T, int ew, int lane, LanePixel& o) {
+  const ConvDst& d = p.dst;
+  const Geom& sg = p.src;
+  const long long j = (long long)um * 128 * T + tile * 128 + ew * 32 + lane;
+  const int b = (int)(j / sg.S);
+  const int rem = (int)(j - (long long)b * sg.S);
+  const int rr = rem / sg.P;
+  const int x = rem - rr * sg.P, y = rr - sg.row0;
+  const bool valid = (b < sg.B) && (y >= 0) && (x < sg.W);
+  o.b = b; o.y = y; o.x = x; o.nd = 0; o.zero = 0; o.cshift = 0; o.d0 = 0;
+  if (valid) {
+    const Geom& dg = d.g;
+    if (d.map == MAP_IDENT) { o.d0 = b * dg.S + (y + dg.row0) * dg.P + x; o.nd = 1; }
+    else if (d.map == MAP_UP2) { o.d0 = b * dg.S + (2 * y + dg.row0) * dg.P + 2 * x; o.nd = 4; }
+    else if (d.map == MAP_UNROT) {
+      const int br = b / d.nimg, n = b - br * d.nimg, H = sg.H, W = sg.W;
+      const int pp = (y + 1 == H) ? 0 : y + 1, q = x;
+      o.zero = (y + 1 == H);
+      int i, jj;
+      if (br == 0) { i = pp; jj = q; } else if (br == 1) { i = q; jj = H - 1 - pp; }
+      else if (br == 2) { i = H - 1 - pp; jj = W - 1 - q; } else { i = W - 1 - q; jj = pp; }
+      o.d0 = n * dg.S + (i + dg.row0) * dg.P + jj; o.nd = 1; o.cshift = br * d.cvalid;
+    } else if (d.map == MAP_UNROT_INV) {
+      const int br = nt, H = sg.H, W = sg.W;
+      int pp, q;
+      if (br == 0) { pp = y; q = x; } else if (br == 1) { pp = H - 1 - x; q = y; }
+      else if (br == 2) { pp = H - 1 - y; q = W - 1 - x; } else { pp = x; q = W - 1 - y; }
+      if (pp > 0) { o.d0 = (br * d.nimg + b) * dg.S + (pp - 1 + dg.row0) * dg.P + q; o.nd = 1; }
+    } else { o.nd = 1; }   // MAP_NCHW
   }
 #pragma unroll
-  for (int q = 0; q < PASSES; ++q) {
-    const int nd = meta[q] & 7;
-    if (nd == 0) continue;
-    float4 o = v[q];
-    if (meta[q] & 8) o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (d.flags & EP_ACT_GRAD) {
-      o.x = a[q].x > 0.f ? o.x : SSDN_LRELU_SLOPE * o.x; o.y = a[q].y > 0.f ? o.y : SSDN_LRELU_SLOPE * o.y;
-      o.z = a[q].z > 0.f ? o.z : SSDN_LRELU_SLOPE * o.z; o.w = a[q].w > 0.f ? o.w : SSDN_LRELU_SLOPE * o.w;
-    }
-    float4 h = o, l = o;
-    if (d.flags & EP_WRITE_LO) { tf32_split(o.x, h.x, l.x); tf32_split(o.y, h.y, l.y); tf32_split(o.z, h.z, l.z); tf32_split(o.w, h.w, l.w); }
-    const int coff = d.coff + (meta[q] >> 8) + cg;
-    const int px = q * PPI + sub;
-    for (int k = 0; k < nd; ++k) {
-      const long long oi = (long long)(k == 0 ? dp0[q] : s_dst[px][k]) * d.cpitch + coff;
-      *reinterpret_cast<float4*>(d.v + oi) = h;
-      if (d.flags & EP_WRITE_LO) *reinterpret_cast<float4*>(d.lo + oi) = l;
-    }
+  for (int s = 0; s < kMaxSlices; ++s) o.mw[s] = 0xffffffffu;
+  if ((d.flags & EP_ACT_GRAD) && o.nd) {
+    // word of slice s: channel (first channel of the slice) / 32, in the mask row of the destination (or source) pixel
+    const long long row = (d.flags & EP_ACT_AT_SRC) ? j : (long long)o.d0;
+    const int c_first = ((d.flags & EP_ACT_AT_SRC) || d.map != MAP_UNROT_INV) ? nt * p.N : 0;
+    const uint32_t* mrow = d.mask_in + row * d.mask_in_words + (c_first >> 5);
+#pragma unroll
+    for (int s = 0; s < kMaxSlices; ++s)
+      if (32 * s < p.N && c_first + 32 * s < d.mask_in_words * 32) o.mw[s] = __ldg(mrow + s);
   }
 }
 
@@ -153,12 +164,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // ------------------------------------------------------------ A producer (warp-uniform loop, elected issue)
     Ring ra(p.a_stages);
     const uint32_t box_bytes = p.box_rows * 64;
+    long long w_empty = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int um = u / p.n_tiles_n;
       const int j0 = um * 128 * T;
       for (int ch = 0; ch < p.n_chunks; ++ch)
         for (int g = 0; g < p.n_groups; ++g) {
-          umma::mbar_wait(empty_a(ra.stage), ra.phase ^ 1, abort_addr, p.error_flag, 1);
+          SSDN_TIMED(w_empty, umma::mbar_wait(empty_a(ra.stage), ra.phase ^ 1, abort_addr, p.error_flag, 1));
           const uint32_t dst = a_base + ra.stage * a_stage_bytes;
           const int row = j0 + p.groups[g].row_off;
           if (umma::elect_one()) {
@@ -176,14 +188,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           ra.advance();
         }
     }
+    if (p.stats && lane == 0) p.stats[blockIdx.x * 16 + 0] = w_empty;
   } else if (warp == 1) {
     // ------------------------------------------------------------ B producer: one TMA per stage = bg slabs x 2 planes
     Ring rb(p.b_stages);
     const int n_slabs = p.n_chunks * p.ntaps_total, n_bstages = n_slabs / p.bg;
+    long long w_empty = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int nt = u % p.n_tiles_n;
       for (int i = 0; i < n_bstages; ++i) {
-        umma::mbar_wait(empty_b(rb.stage), rb.phase ^ 1, abort_addr, p.error_flag, 2);
+        SSDN_TIMED(w_empty, umma::mbar_wait(empty_b(rb.stage), rb.phase ^ 1, abort_addr, p.error_flag, 2));
         if (umma::elect_one()) {
           umma::mbar_expect_tx(full_b(rb.stage), b_stage_bytes);
           umma::tma_load_3d(b_base + rb.stage * b_stage_bytes, &map_b, full_b(rb.stage), 0, 0, 2 * (nt * n_slabs + i * p.bg));
@@ -192,6 +206,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         rb.advance();
       }
     }
+    if (p.stats && lane == 0) p.stats[blockIdx.x * 16 + 1] = w_empty;
   } else if (warp == 2) {
     // ------------------------------------------------------------ MMA issuer: uniform loops, one elected lane issues a fully
     // unrolled block of T x 2 x 3 MMAs per (chunk, tap) whose descriptors are base + compile-time offsets
@@ -199,9 +214,69 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     constexpr uint64_t desc = umma::make_desc_base(16, 512, umma::LAYOUT_SW64);
     const uint32_t idesc = umma::make_idesc_tf32(128, p.N, 0, 0);
     int it = 0;
+    long long w_tmem = 0, w_a = 0, w_b = 0;
+    const long long t_start = clock64();
+    if (p.row3) {
+      // 3x3 stencils: one barrier wait and one block of 3 taps x T tiles x (2 k-steps x 3 products) MMAs per B stage.
+      // Descriptors are base + multiples of uniform strides in 16-byte units, so the elected thread has almost nothing
+      // to do between two tcgen05.mma: the tensor core's short queue never drains (profiles/r01_role_waits.log).
+      const uint32_t desc_hi = (uint32_t)(desc >> 32);
+      const uint32_t lbo_bits = (uint32_t)(desc & 0xffff0000u);
+      const uint32_t a_pl = p.a_plane_bytes >> 4, b_pl = (uint32_t)(p.N * 64) >> 4, slab = 2 * b_pl;
+      const int step = p.tap_step * 4;                       // one pixel row of the A window = 64 bytes
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+        const int buf = it & 1;
+        SSDN_TIMED(w_tmem, umma::mbar_wait(tmem_empty(buf), ((it >> 1) & 1) ^ 1, abort_addr, p.error_flag, 3));
+        umma::tc_fence_after();
+        const uint32_t d0 = tmem + buf * T * p.N;
+        uint32_t first = 0;
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          const bool two = (ch != p.n_chunks - 1) || (p.ksteps_last == 2);
+          for (int g = 0; g < p.n_groups; ++g) {
+            SSDN_TIMED(w_a, umma::mbar_wait(full_a(ra.stage), ra.phase, abort_addr, p.error_flag, 3));
+            const uint32_t a_stage = a_base + ra.stage * a_stage_bytes;
+            const int nrows = p.groups[g].ntaps / 3;
+            for (int r = 0; r < nrows; ++r) {
+              SSDN_TIMED(w_b, umma::mbar_wait(full_b(rb.stage), rb.phase, abort_addr, p.error_flag, 3));
+              umma::tc_fence_after();
+              const uint32_t a0 = (((a_stage + p.groups[g].tap_rel[3 * r] * 64) >> 4) & 0x3fffu) | lbo_bits;
+              const uint32_t b0 = (((b_base + rb.stage * b_stage_bytes) >> 4) & 0x3fffu) | lbo_bits;
+              if (umma::elect_one()) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                  const uint32_t aj = a0 + j * step, bj = b0 + j * slab;
+#pragma unroll
+                  for (int tile = 0; tile < T; ++tile) {
+                    const uint32_t d = d0 + tile * p.N;
+                    const uint32_t av = aj + tile * 512, al = av + a_pl, bv = bj, bl = bj + b_pl;
+                    umma::mma_tf32_lo(d, al, bv, desc_hi, idesc, (j == 0) ? first : 1u);
+                    umma::mma_tf32_lo(d, av, bl, desc_hi, idesc, 1);
+                    umma::mma_tf32_lo(d, av, bv, desc_hi, idesc, 1);
+                    if (two) {
+                      umma::mma_tf32_lo(d, al + 2, bv + 2, desc_hi, idesc, 1);
+                      umma::mma_tf32_lo(d, av + 2, bl + 2, desc_hi, idesc, 1);
+                      umma::mma_tf32_lo(d, av + 2, bv + 2, desc_hi, idesc, 1);
+                    }
+                  }
+                }
+                umma::mma_commit(empty_b(rb.stage));
+              }
+              __syncwarp();
+              first = 1;
+              rb.advance();
+            }
+            if (umma::elect_one()) umma::mma_commit(empty_a(ra.stage));
+            __syncwarp();
+            ra.advance();
+          }
+        }
+        if (umma::elect_one()) umma::mma_commit(tmem_full(buf));
+        __syncwarp();
+      }
+    } else
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
       const int buf = it & 1;
-      umma::mbar_wait(tmem_empty(buf), ((it >> 1) & 1) ^ 1, abort_addr, p.error_flag, 3);
+      SSDN_TIMED(w_tmem, umma::mbar_wait(tmem_empty(buf), ((it >> 1) & 1) ^ 1, abort_addr, p.error_flag, 3));
       umma::tc_fence_after();
       const uint32_t d0 = tmem + buf * T * p.N;
       uint32_t first = 0;       // becomes 1 after the first tap: accumulate flag of the very first MMA of each tile
@@ -210,10 +285,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int ch = 0; ch < p.n_chunks; ++ch) {
         const bool two = (ch != p.n_chunks - 1) || (p.ksteps_last == 2);
         for (int g = 0; g < p.n_groups; ++g) {
-          umma::mbar_wait(full_a(ra.stage), ra.phase, abort_addr, p.error_flag, 3);
+          SSDN_TIMED(w_a, umma::mbar_wait(full_a(ra.stage), ra.phase, abort_addr, p.error_flag, 3));
           const uint32_t av0 = a_base + ra.stage * a_stage_bytes;
           for (int t = 0; t < p.groups[g].ntaps; ++t) {
-            if (sb == 0) umma::mbar_wait(full_b(rb.stage), rb.phase, abort_addr, p.error_flag, 3);
+            if (sb == 0) SSDN_TIMED(w_b, umma::mbar_wait(full_b(rb.stage), rb.phase, abort_addr, p.error_flag, 3));
             umma::tc_fence_after();
             const uint32_t av = av0 + p.groups[g].tap_rel[t] * 64, al = av + p.a_plane_bytes;
             const uint32_t bv = b_base + rb.stage * b_stage_bytes + sb * slab_bytes, bl = bv + p.N * 64;
@@ -247,106 +322,166 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (umma::elect_one()) umma::mma_commit(tmem_full(buf));
       __syncwarp();
     }
+    if (p.stats && lane == 0) {
+      unsigned long long* s = p.stats + blockIdx.x * 16;
+      s[2] = w_tmem; s[3] = w_a; s[4] = w_b; s[5] = clock64() - t_start;
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
-    // TMEM -> registers (one pixel per lane) -> bias / LeakyReLU -> 32-channel slice staged in shared memory ->
-    // copy-out in which 8 consecutive lanes write one pixel's 128 contiguous bytes (full lines), with the
-    // LeakyReLU' mask, the hi/lo split and the upsample / (un-)rotate scatter applied on the way out.
+    // TMEM -> registers (one pixel per lane, 32 channels per slice) -> bias / LeakyReLU (+ sign-mask word out) or
+    // LeakyReLU' from the sign-mask word -> optional column sums -> hi/lo split -> global memory straight from registers:
+    // every lane writes its pixel's 128 contiguous bytes of the slice as 8 float4 stores per plane, with the upsample /
+    // (un-)rotate scatter in the address.  No shared-memory staging: the tensor core needs all of the shared-memory
+    // bandwidth for its operands (profiles/r01_role_waits.log), and L2 merges the 16-byte pieces into full lines.
     const ConvDst& d = p.dst;
     const Geom& sg = p.src;
     const int ew = warp - 4;
-    float* stage = reinterpret_cast<float*>(smem + p.epi_off) + ew * 32 * kStagePitch;
-    __shared__ int s_dst[4][32][4];
-    __shared__ int s_meta[4][32];       // bits 0..2: number of destinations, bit 3: write zeros, bits 8..: channel shift
-    __shared__ int s_src[4][32];        // source flat pixel (activation lookup with EP_ACT_AT_SRC)
-    __shared__ float s_bias[400];
+    __shared__ __align__(16) float s_bias[400];
     if (d.flags & EP_BIAS)
-      for (int i = threadIdx.x - 128; i < d.cvalid && i < 400; i += 128) s_bias[i] = __ldg(d.bias + i);
+      for (int i = threadIdx.x - 128; i < 400; i += 128) s_bias[i] = i < d.cvalid ? __ldg(d.bias + i) : 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    float csum[kMaxSlices];
+#pragma unroll
+    for (int s = 0; s < kMaxSlices; ++s) csum[s] = 0.f;
     int it = 0;
+    long long w_full = 0;
+    const long long t_start = clock64();
+    LanePixel nxt;
+    if (blockIdx.x < n_units) lane_pixel(p, blockIdx.x / p.n_tiles_n, blockIdx.x % p.n_tiles_n, 0, T, ew, lane, nxt);
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
       const int buf = it & 1;
       const int um = u / p.n_tiles_n, nt = u % p.n_tiles_n;
-      umma::mbar_wait(tmem_full(buf), (it >> 1) & 1, abort_addr, p.error_flag, 4);
+      SSDN_TIMED(w_full, umma::mbar_wait(tmem_full(buf), (it >> 1) & 1, abort_addr, p.error_flag, 4));
       umma::tc_fence_after();
       for (int tile = 0; tile < T; ++tile) {
-        const long long j = (long long)um * 128 * T + tile * 128 + ew * 32 + lane;
-        const int b = (int)(j / sg.S);
-        const int rem = (int)(j - (long long)b * sg.S);
-        const int rr = rem / sg.P;
-        const int x = rem - rr * sg.P, y = rr - sg.row0;
-        const bool valid = (b < sg.B) && (y >= 0) && (x < sg.W);
-        if (d.map != MAP_NCHW) {
-          int nd = 0, zero = 0, cshift = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-          if (valid) {
-            const Geom& dg = d.g;
-            if (d.map == MAP_IDENT) {
-              d0 = b * dg.S + (y + dg.row0) * dg.P + x; nd = 1;
-            } else if (d.map == MAP_UP2) {
-              d0 = b * dg.S + (2 * y + dg.row0) * dg.P + 2 * x; d1 = d0 + 1; d2 = d0 + dg.P; d3 = d2 + 1; nd = 4;
-            } else if (d.map == MAP_UNROT) {
-              const int br = b / d.nimg, n = b - br * d.nimg, H = sg.H, W = sg.W;
-              const int pp = (y + 1 == H) ? 0 : y + 1, q = x;
-              zero = (y + 1 == H);
-              int i, jj;
-              if (br == 0) { i = pp; jj = q; } else if (br == 1) { i = q; jj = H - 1 - pp; }
-              else if (br == 2) { i = H - 1 - pp; jj = W - 1 - q; } else { i = W - 1 - q; jj = pp; }
-              d0 = n * dg.S + (i + dg.row0) * dg.P + jj; nd = 1; cshift = br * d.cvalid;
-            } else {   // MAP_UNROT_INV
-              const int br = nt, H = sg.H, W = sg.W;
-              int pp, q;
-              if (br == 0) { pp = y; q = x; } else if (br == 1) { pp = H - 1 - x; q = y; }
-              else if (br == 2) { pp = H - 1 - y; q = W - 1 - x; } else { pp = x; q = W - 1 - y; }
-              if (pp > 0) { d0 = (br * d.nimg + b) * dg.S + (pp - 1 + dg.row0) * dg.P + q; nd = 1; }
-            }
-          }
-          s_dst[ew][lane][0] = d0; s_dst[ew][lane][1] = d1; s_dst[ew][lane][2] = d2; s_dst[ew][lane][3] = d3;
-          s_meta[ew][lane] = nd | (zero << 3) | (cshift << 8);
-          s_src[ew][lane] = (int)j;
+        const LanePixel cur = nxt;
+        {   // mapping + mask words of the next tile of this CTA (loads stay in flight while this tile is written)
+          int nu = u, ntile = tile + 1;
+          if (ntile == T) { ntile = 0; nu = u + gridDim.x; }
+          if (nu < n_units) lane_pixel(p, nu / p.n_tiles_n, nu % p.n_tiles_n, ntile, T, ew, lane, nxt);
         }
         const uint32_t trow = tmem + (uint32_t(ew * 32) << 16) + (buf * T + tile) * p.N;
-        for (int c0 = 0; c0 < p.N; c0 += 32) {
-          const int cw = min(32, p.N - c0);                           // 32 or 16 channels in this slice
-          const int cg0 = (d.map == MAP_UNROT_INV ? 0 : nt * p.N) + c0; // first channel of the slice among this conv's outputs
-          uint32_t r[32];
-          umma::tmem_ld16(trow + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-          if (cw == 32) umma::tmem_ld16(trow + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-          umma::tmem_ld_wait();
-          if (cg0 >= d.cvalid) continue;
-          if (d.flags & (EP_BIAS | EP_LRELU)) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (i < cw) {
-                float a = __uint_as_float(r[i]);
-                if ((d.flags & EP_BIAS) && cg0 + i < d.cvalid) a += s_bias[cg0 + i];
-                if (d.flags & EP_LRELU) a = lrelu(a);
-                r[i] = __float_as_uint(a);
+        for (int s = 0; s < kMaxSlices; ++s) {
+          const int c0 = 32 * s;
+          if (c0 < p.N) {
+            const int cw = min(32, p.N - c0);                              // 32 or 16 channels in this slice
+            const int cg0 = (d.map == MAP_UNROT_INV ? 0 : nt * p.N) + c0;  // first channel of the slice among this conv's outputs
+            uint32_t r[32];
+            umma::tmem_ld16(trow + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+            if (cw == 32) umma::tmem_ld16(trow + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+            umma::tmem_ld_wait();
+            if (cg0 < d.cvalid) {
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = (i < cw) ? __uint_as_float(r[i]) : 0.f;
+              if (d.flags & EP_BIAS) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  if (i < cw) {
+                    const float4 bq = *reinterpret_cast<const float4*>(&s_bias[cg0 + i]);
+                    f[i] += bq.x; f[i + 1] += bq.y; f[i + 2] += bq.z; f[i + 3] += bq.w;
+                  }
+                }
+              }
+              if (d.flags & EP_LRELU) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { word |= (f[i] > 0.f ? 1u : 0u) << i; f[i] = lrelu(f[i]); }
+                if (d.mask_out && cur.nd == 1)
+                  d.mask_out[(long long)cur.d0 * d.mask_out_words + ((cur.cshift + cg0) >> 5)] = cur.zero ? 0u : word;
+              }
+              if (d.flags & EP_ACT_GRAD) {
+                const uint32_t word = cur.mw[s];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = ((word >> i) & 1u) ? f[i] : SSDN_LRELU_SLOPE * f[i];
+              }
+              if (cur.zero || cur.nd == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = 0.f;
+              }
+              if (d.colsum) {
+                // transpose-reduce over the 32 pixels of the warp: after 5 exchange steps lane c holds the sum of channel c
+                float t16[16], t8[8], t4[4], t2[2];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const bool up = lane & 16;
+                  const float send = up ? f[i] : f[i + 16], keep = up ? f[i + 16] : f[i];
+                  t16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const bool up = lane & 8;
+                  const float send = up ? t16[i] : t16[i + 8], keep = up ? t16[i + 8] : t16[i];
+                  t8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const bool up = lane & 4;
+                  const float send = up ? t8[i] : t8[i + 4], keep = up ? t8[i + 4] : t8[i];
+                  t4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const bool up = lane & 2;
+                  const float send = up ? t4[i] : t4[i + 2], keep = up ? t4[i + 2] : t4[i];
+                  t2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                }
+                {
+                  const bool up = lane & 1;
+                  const float send = up ? t2[0] : t2[1], keep = up ? t2[1] : t2[0];
+                  csum[s] += keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                }
+              }
+              if (d.map == MAP_NCHW) {
+                if (cur.nd) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (i < cw && cg0 + i < d.cvalid)
+                      d.v[(((long long)cur.b * d.cvalid + cg0 + i) * sg.H + cur.y) * sg.W + cur.x] = f[i];
+                }
+              } else if (cur.nd) {
+                const long long cbase = d.coff + cur.cshift + cg0;
+                for (int k = 0; k < cur.nd; ++k) {
+                  const long long oi = (long long)(cur.d0 + (k & 1) + (k >> 1) * d.g.P) * d.cpitch + cbase;
+                  float4* ov = reinterpret_cast<float4*>(d.v + oi);
+                  if (d.flags & EP_WRITE_LO) {
+                    float4* ol = reinterpret_cast<float4*>(d.lo + oi);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                      if (i < cw && cg0 + i < d.cvalid) {
+                        float4 h, l;
+                        tf32_split(f[i], h.x, l.x); tf32_split(f[i + 1], h.y, l.y); tf32_split(f[i + 2], h.z, l.z); tf32_split(f[i + 3], h.w, l.w);
+                        ov[i >> 2] = h; ol[i >> 2] = l;
+                      }
+                    }
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                      if (i < cw && cg0 + i < d.cvalid) ov[i >> 2] = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                  }
+                }
               }
             }
           }
-          if (d.map == MAP_NCHW) {
-            if (valid) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < cw && cg0 + i < d.cvalid)
-                  d.v[(((long long)b * d.cvalid + cg0 + i) * sg.H + y) * sg.W + x] = __uint_as_float(r[i]);
-            }
-            continue;
-          }
-          // stage this lane's pixel row
-          float* row = stage + lane * kStagePitch;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            if (i < cw) *reinterpret_cast<uint4*>(row + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
-          __syncwarp();
-          if (cw == 32) copy_out_slice<32>(d, stage, s_dst[ew], s_meta[ew], s_src[ew], lane, cg0, nt * p.N + c0);
-          else copy_out_slice<16>(d, stage, s_dst[ew], s_meta[ew], s_src[ew], lane, cg0, nt * p.N + c0);
-          __syncwarp();
         }
       }
       umma::tc_fence_before();
       umma::mbar_arrive(tmem_empty(buf));
     }
+    if (d.colsum) {
+      // this CTA only ever sees one N tile when gridDim.x is a multiple of n_tiles_n (the host guarantees it)
+      const int nt = blockIdx.x % p.n_tiles_n;
+      const int c_first = (d.map == MAP_UNROT_INV) ? 0 : nt * p.N;
+      float* row = d.colsum + (long long)(blockIdx.x * 4 + ew) * d.colsum_pitch;
+      for (int c = lane; c < d.colsum_pitch; c += 32) row[c] = 0.f;
+      __syncwarp();
+      // lane -> channel of the transpose-reduce: bit k of the lane selected the upper half at step k, i.e. channel == lane
+#pragma unroll
+      for (int s = 0; s < kMaxSlices; ++s)
+        if (32 * s < p.N && c_first + 32 * s + lane < d.colsum_pitch && (blockIdx.x < n_units)) row[c_first + 32 * s + lane] = csum[s];
+    }
+    if (p.stats && threadIdx.x == 128) { p.stats[blockIdx.x * 16 + 6] = w_full; p.stats[blockIdx.x * 16 + 7] = clock64() - t_start; }
   }
   umma::tc_fence_before();
   __syncthreads();
@@ -375,7 +510,7 @@ static inline void conv_chunks(int cin, int* n_chunks, int* ksteps_last) {
 static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a_v, const float* a_lo, int a_cpitch,
                                  int a_coff, int cin, const float* w_slab, int cout_padded, int N,
                                  const ConvTaps& taps, const ConvDst& dst, int* error_flag, int num_sms,
-                                 size_t smem_limit = 200 * 1024) {
+                                 size_t smem_limit = 222 * 1024) {
   ConvParams& p = plan->p;
   p = ConvParams{};
   p.src = src; p.N = N; p.dst = dst; p.error_flag = error_flag;
@@ -385,6 +520,12 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
   p.ntaps_total = taps.n;
   p.T = (2 * 2 * N <= 512) ? 2 : 1;
   const long long total = src.total();
+  if (p.T == 2) {
+    // two tiles per unit halve the weight traffic, but on the small pyramid levels they leave SMs idle: compare waves x work
+    const long long tiles = (total + 127) / 128;
+    const long long cost2 = (((tiles + 1) / 2 * p.n_tiles_n + num_sms - 1) / num_sms) * 2, cost1 = (tiles * p.n_tiles_n + num_sms - 1) / num_sms;
+    if (cost1 * 5 <= cost2 * 4) p.T = 1;
+  }
   p.n_units_m = (int)((total + 128LL * p.T - 1) / (128LL * p.T));
   // B stage = bg consecutive weight slabs (both planes) loaded by ONE TMA op: a TMA instruction costs ~450 clk of the
   // SM's TMA unit whatever its size (profiles/r01_tma_rate.log), so operands must arrive in few, large boxes.
@@ -412,11 +553,9 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     uint32_t plane = (uint32_t)(nbox * box_rows * 64);
     int stages = (mode == 0) ? 2 : 3;
     for (int bst = 4; bst >= 2; --bst) {
-      const size_t epi = 4 * 32 * convk::kStagePitch * sizeof(float);
-      size_t need = (size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes + epi + 2048;
+      size_t need = (size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes + 2048;
       if (need > smem_limit) continue;
       p.n_groups = (int)gs.size(); p.nbox = nbox; p.box_rows = box_rows; p.a_plane_bytes = plane; p.a_stages = stages; p.b_stages = bst;
-      p.epi_off = (uint32_t)((size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes);
       for (size_t gi = 0; gi < gs.size(); ++gi) {
         int lo = INT32_MAX;
         for (int t : gs[gi]) lo = std::min(lo, taps.off[t]);
@@ -430,7 +569,26 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     return false;
   };
   if (!try_group(0) && !try_group(1) && !try_group(2)) return -10;
+  // fast issue path: every B stage = the three taps of one stencil row, with a constant step between their A offsets
+  p.row3 = 0; p.tap_step = 0;
+  if (taps.n == 9 && p.bg == 3) {
+    bool ok = true; int step = 0;
+    for (int g = 0; g < p.n_groups && ok; ++g) {
+      if (p.groups[g].ntaps % 3) { ok = false; break; }
+      for (int r = 0; r < p.groups[g].ntaps / 3; ++r) {
+        const int s1 = p.groups[g].tap_rel[3 * r + 1] - p.groups[g].tap_rel[3 * r], s2 = p.groups[g].tap_rel[3 * r + 2] - p.groups[g].tap_rel[3 * r + 1];
+        if (s1 != s2 || (s1 != 1 && s1 != -1) || (step && s1 != step)) ok = false;
+        step = s1;
+      }
+    }
+    if (ok) { p.row3 = 1; p.tap_step = step; }
+  }
   plan->grid = std::min(p.n_units_m * p.n_tiles_n, num_sms);
+  if (dst.colsum) {                                  // column sums: every CTA must stay on one N tile (see the epilogue)
+    plan->grid -= plan->grid % p.n_tiles_n;
+    if (plan->grid < p.n_tiles_n) return -12;
+  }
+  if (dst.map != MAP_NCHW && (dst.cvalid % 4 || dst.cpitch % 4 || dst.coff % 4)) return -13;   // float4 stores
   // tensor maps.  A: 3-D (channel, flat pixel, plane); the lo plane must follow the hi plane at a constant byte distance.
   const long long plane_stride = (long long)((const char*)a_lo - (const char*)a_v);
   if (plane_stride <= 0 || plane_stride % 16) return -11;
@@ -463,14 +621,38 @@ struct LaunchProfiler {
 };
 inline LaunchProfiler& profiler() { static LaunchProfiler p; return p; }
 
+// Developer instrumentation: one synchronous launch with the per-role wait clocks collected and printed to stderr.
+static inline cudaError_t conv_launch_with_stats(const ConvPlan& plan, cudaStream_t stream, int kind) {
+  static unsigned long long* dev = nullptr;
+  if (!dev) cudaMalloc(&dev, 1024 * 16 * sizeof(unsigned long long));
+  cudaMemsetAsync(dev, 0, 1024 * 16 * sizeof(unsigned long long), stream);
+  ConvParams p = plan.p; p.stats = dev;
+  profiler().begin(kind, plan.flops, stream);
+  if (p.T == 2) convk::conv_igemm_kernel<2><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, p);
+  else convk::conv_igemm_kernel<1><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, p);
+  profiler().end(stream);
+  std::vector<unsigned long long> h((size_t)plan.grid * 16);
+  cudaMemcpyAsync(h.data(), dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+  cudaError_t e = cudaStreamSynchronize(stream);
+  double s[8] = {0};
+  for (int b = 0; b < plan.grid; ++b) for (int k = 0; k < 8; ++k) s[k] += (double)h[(size_t)b * 16 + k] / plan.grid;
+  fprintf(stderr, "[conv stats] kind %d grid %d T %d N %d ntiles_n %d chunks %d groups %d taps %d a_st %d b_st %d bg %d | mma loop %.0f clk: wait tmem_empty %.1f%% "
+          "full_a %.1f%% full_b %.1f%% | prodA wait empty %.1f%% prodB wait empty %.1f%% | epi loop %.0f clk: wait tmem_full %.1f%%\n",
+          kind, plan.grid, p.T, p.N, p.n_tiles_n, p.n_chunks, p.n_groups, p.ntaps_total, p.a_stages, p.b_stages, p.bg, s[5], 100 * s[2] / s[5], 100 * s[3] / s[5],
+          100 * s[4] / s[5], 100 * s[0] / s[5], 100 * s[1] / s[5], s[7], 100 * s[6] / s[7]);
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 static inline cudaError_t conv_launch(const ConvPlan& plan, cudaStream_t stream, int kind = 0) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(convk::conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(convk::conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(convk::conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(convk::conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  static const bool want_stats = getenv("SSDN_CONV_STATS") != nullptr;
+  if (want_stats && profiler().on) return conv_launch_with_stats(plan, stream, kind);
   if (profiler().on) profiler().begin(kind, plan.flops, stream);
   if (plan.p.T == 2) convk::conv_igemm_kernel<2><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, plan.p);
   else convk::conv_igemm_kernel<1><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, plan.p);

@@ -19,6 +19,7 @@ using eng::round_up;
 struct Buf {                 // one padded-flat tensor (two planes when lo != nullptr)
   float* v = nullptr; float* lo = nullptr;
   Geom g{}; int cpitch = 0;
+  uint32_t* mask = nullptr; int mask_words = 0;   // LeakyReLU sign bits [flat pixel][words] (buffers whose derivative a dgrad epilogue applies)
   size_t floats() const { return (size_t)g.total() * cpitch; }
 };
 
@@ -31,6 +32,7 @@ struct Layer {               // one convolution of the network
   // data gradient (has_dgrad == false for the first conv: nobody consumes d(input))
   bool has_dgrad = false;
   ConvPlan dgrad; float* slab_d; int n_d; int cinp_d; int dgrad_nvalid;
+  bool bias_fused = false; int bias_nblk = 0;   // bias gradient = column sums written by the dgrad epilogue that produced this layer's dZ
   // weight gradient
   WgradPlan wgrad; int ksplit;
   const Buf* x; int x_coff;          // conv input (channel slice [x_coff, x_coff+cin))
@@ -51,7 +53,7 @@ class Net {
   // buffers
   Buf cat[6], e[6], e1a, p5, d_a[6], head_in, h1, h2;
   Buf g_out, dz_h2, dz_h1, dz_db[6], dz_da[6], gcat[6], dz_e[7], dz_e1a, g_p[6];
-  float* partial = nullptr; float* colpart = nullptr; int* flag = nullptr;
+  float* partial = nullptr; float* colpart = nullptr; float* colpart2 = nullptr; int* flag = nullptr;
   size_t partial_floats = 0;
   size_t ws_bytes = 0; void* ws = nullptr;
   std::vector<PoolOp> pools; std::vector<PoolBwdOp> pool_bwds; std::vector<UpBwdOp> up_bwds;
@@ -108,6 +110,7 @@ class Net {
       b.v = a.take<float>(b.floats()); b.lo = lo ? a.take<float>(b.floats()) : nullptr;
       if (!lo) b.lo = nullptr;
     };
+    auto mkmask = [&](Buf& b) { b.mask_words = (b.cpitch + 31) / 32; b.mask = a.take<uint32_t>((size_t)b.g.total() * b.mask_words); };
     const int c1 = round_up(96 + Cin, 4);
     mk(cat[1], g[0], c1, true); mk(e1a, g[0], 48, true); mk(e[1], g[0], 48, true);
     mk(cat[2], g[1], 144, true); mk(e[2], g[1], 48, true);
@@ -117,6 +120,8 @@ class Net {
     mk(p5, g[5], 48, true);
     for (int l = 1; l <= 5; ++l) mk(d_a[l], g[l - 1], 96, true);        // dec{l}a output lives at level l-1
     mk(head_in, gh, nin, true); mk(h1, gh, nin, true); mk(h2, gh, 96, true);
+    for (int l = 1; l <= 5; ++l) mkmask(d_a[l]);
+    mkmask(e1a); mkmask(head_in); mkmask(h1); mkmask(h2);
     // backward
     mk(g_out, gh, round_up(Cout, 4), true); mk(dz_h2, gh, 96, true); mk(dz_h1, gh, nin, true);
     for (int l = 1; l <= 5; ++l) { mk(dz_db[l], g[l - 1], 96, true); mk(dz_da[l], g[l - 1], 96, true); }
@@ -147,9 +152,12 @@ class Net {
       const Geom& gg = (l.ksize == 1) ? gh : g[level_of(l.name)];
       l.ksplit = wgrad_pick_ksplit(gg.total(), l.cout, l.cin, l.ksize * l.ksize, sms);
       partial_floats = std::max(partial_floats, wgrad_partial_floats(l.ksplit, l.ksize * l.ksize, l.cout, l.cin));
+      if (wgradk::wgrad_small_cin_ok(l.cin, l.cout, l.ksize * l.ksize))
+        partial_floats = std::max(partial_floats, wgradk::wgrad_small_cin_partial_floats(l.cin, l.cout));
     }
     partial = a.take<float>(partial_floats);
     colpart = a.take<float>((size_t)1024 * 384);
+    colpart2 = a.take<float>((size_t)1024 * 384);
     flag = a.take<int>(64);
     return a.off;
   }
@@ -197,13 +205,19 @@ class Net {
 
     // ---- backward: data gradients
     const int gact = EP_ACT_GRAD | EP_WRITE_LO;
-    if ((r = plan_dgrad(L("output_conv"), g_out, dst_act(dz_h2, MAP_IDENT, gact, 96, h2, 0)))) return r;
-    if ((r = plan_dgrad(L("output_block.2"), dz_h2, dst_act(dz_h1, MAP_IDENT, gact, nin, h1, 0)))) return r;
-    { ConvDst d = dst_act(dz_db[1], blind ? MAP_UNROT_INV : MAP_IDENT, gact | EP_ACT_AT_SRC, 96, head_in, 0);
+    // every dst_act below also yields the bias gradient of the layer that owns the produced dZ (fused column sums)
+    auto fused = [&](const char* producer, const char* owner) { Layer& o = L(owner); o.bias_fused = true; o.bias_nblk = L(producer).dgrad.grid * 4; };
+    if ((r = plan_dgrad(L("output_conv"), g_out, dst_act(dz_h2, MAP_IDENT, gact, 96, h2, true)))) return r;
+    fused("output_conv", "output_block.2");
+    if ((r = plan_dgrad(L("output_block.2"), dz_h2, dst_act(dz_h1, MAP_IDENT, gact, nin, h1, true)))) return r;
+    fused("output_block.2", "output_block.0");
+    { ConvDst d = dst_act(dz_db[1], blind ? MAP_UNROT_INV : MAP_IDENT, gact | EP_ACT_AT_SRC, 96, head_in, true);
       if ((r = plan_dgrad(L("output_block.0"), dz_h1, d))) return r; }
+    fused("output_block.0", "decode_block_1.2");
     for (int i = 1; i <= 5; ++i) {
       const std::string a_nm = "decode_block_" + std::to_string(i) + ".0", b_nm = "decode_block_" + std::to_string(i) + ".2";
-      if ((r = plan_dgrad(L(b_nm), dz_db[i], dst_act(dz_da[i], MAP_IDENT, gact, 96, d_a[i], 0)))) return r;
+      if ((r = plan_dgrad(L(b_nm), dz_db[i], dst_act(dz_da[i], MAP_IDENT, gact, 96, d_a[i], true)))) return r;
+      fused(b_nm.c_str(), a_nm.c_str());
       if ((r = plan_dgrad(L(a_nm), dz_da[i], dst(gcat[i], 0, MAP_IDENT, 0, L(a_nm).dgrad_nvalid)))) return r;
       if (i < 5) up_bwds.push_back({&gcat[i], &cat[i], &dz_db[i + 1], 96});
     }
@@ -215,7 +229,8 @@ class Net {
       if ((r = plan_dgrad(L("encode_block_" + std::to_string(i) + ".0"), dz_e[i], dst(g_p[i - 1], 0, MAP_IDENT, 0, 48)))) return r;
     }
     pool_bwds.push_back({&e[1], &g_p[1], &gcat[2], 96, &dz_e[1], g[1]});
-    if ((r = plan_dgrad(L("encode_block_1.2"), dz_e[1], dst_act(dz_e1a, MAP_IDENT, gact, 48, e1a, 0)))) return r;
+    if ((r = plan_dgrad(L("encode_block_1.2"), dz_e[1], dst_act(dz_e1a, MAP_IDENT, gact, 48, e1a, true)))) return r;
+    fused("encode_block_1.2", "encode_block_1.0");
 
     // ---- backward: weight gradients
     struct WG { const char* nm; const Buf* x; int xoff; const Buf* dz; };
@@ -248,11 +263,16 @@ class Net {
   ConvDst dst(Buf& b, int coff, int map, int flags, int cvalid) {
     ConvDst d{}; d.v = b.v; d.lo = b.lo; d.cpitch = b.cpitch; d.coff = coff; d.g = b.g; d.map = map; d.flags = flags;
     if (!b.lo) d.flags &= ~EP_WRITE_LO;
-    d.cvalid = cvalid; d.nimg = N; d.bias = nullptr; d.act = nullptr; d.act_cpitch = 0; d.act_coff = 0;
+    d.cvalid = cvalid; d.nimg = N; d.bias = nullptr;
+    if (b.mask && (flags & EP_LRELU) && (map == MAP_IDENT || map == MAP_UNROT)) { d.mask_out = b.mask; d.mask_out_words = b.mask_words; }
     return d;
   }
-  ConvDst dst_act(Buf& b, int map, int flags, int cvalid, Buf& act, int act_coff) {
-    ConvDst d = dst(b, 0, map, flags, cvalid); d.act = act.v; d.act_cpitch = act.cpitch; d.act_coff = act_coff; return d;
+  // data-gradient destination whose values are multiplied by LeakyReLU'(act) (sign masks of `act`); with_colsum also
+  // collects the column sums of what is written (= the bias gradient of the layer whose dZ this is)
+  ConvDst dst_act(Buf& b, int map, int flags, int cvalid, Buf& act, bool with_colsum) {
+    ConvDst d = dst(b, 0, map, flags, cvalid); d.mask_in = act.mask; d.mask_in_words = act.mask_words;
+    if (with_colsum) { d.colsum = colpart2; d.colsum_pitch = (map == MAP_UNROT_INV) ? 96 : cvalid; }
+    return d;
   }
 
   int plan_fwd(Layer& l, Buf& src, int coff, ConvDst d) {
@@ -274,19 +294,18 @@ class Net {
 
   // ------------------------------------------------------------------ execution
   int prep_weights(const float* params, cudaStream_t st, bool with_dgrad) {
+    pw::WeightPrepJobs jobs{};
+    int nj = 0;
     for (auto& l : layers) {
       const int nt = l.ksize * l.ksize;
       int nc, kl; conv_chunks(l.cin, &nc, &kl);
-      long long n1 = (long long)conv_weight_slab_floats(l.cin, l.coutp_f, nt) / 2;
-      pw::weight_prep_kernel<<<pw::grid_for(n1), pw::kBlock, 0, st>>>(params + l.w_off, l.slab_f, l.cout, l.cin, nt, l.cout,
-                                                                      l.cin, l.coutp_f / l.n_f, nc, l.n_f, 0);
+      jobs.j[nj++] = {params + l.w_off, l.slab_f, l.cout, l.cin, nt, l.cout, l.cin, l.coutp_f / l.n_f, nc, l.n_f, 0};
       if (with_dgrad && l.has_dgrad) {
         conv_chunks(l.cout, &nc, &kl);
-        long long n2 = (long long)conv_weight_slab_floats(l.cout, l.cinp_d, nt) / 2;
-        pw::weight_prep_kernel<<<pw::grid_for(n2), pw::kBlock, 0, st>>>(params + l.w_off, l.slab_d, l.cout, l.cin, nt,
-                                                                        l.dgrad_nvalid, l.cout, l.cinp_d / l.n_d, nc, l.n_d, 1);
+        jobs.j[nj++] = {params + l.w_off, l.slab_d, l.cout, l.cin, nt, l.dgrad_nvalid, l.cout, l.cinp_d / l.n_d, nc, l.n_d, 1};
       }
     }
+    pw::weight_prep_batched_kernel<<<dim3(64, nj), pw::kBlock, 0, st>>>(jobs);
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }
@@ -329,11 +348,23 @@ class Net {
 
   int run_wgrad(Layer& l, float* grads, cudaStream_t st) {
     const int nt = l.ksize * l.ksize;
-    SSDN_CUDA(wgrad_launch(l.wgrad, st));
-    wgradk::wgrad_reduce_kernel<<<pw::grid_for((long long)l.cout * l.cin * nt), pw::kBlock, 0, st>>>(partial, l.wgrad.p.ksplit, nt, l.cout,
-                                                                                                   l.cin, grads + l.w_off, 0);
-    const long long rows = l.dz->g.total();
-    pw::colsum_launch(l.dz->v, l.dz->lo, rows, l.dz->cpitch, 0, l.cout, colpart, grads + l.b_off, st);
+    if (wgradk::wgrad_small_cin_ok(l.cin, l.cout, nt)) {        // first conv: CUDA-core kernel (see wgrad_igemm.cuh)
+      ConvTaps taps = eng::make_taps(l.ksize, blind, false, l.x->g.P);
+      if (profiler().on) profiler().begin(2, l.wgrad.flops, st);
+      cudaError_t ce = wgradk::wgrad_small_cin_launch(l.dz->v, l.dz->lo, l.dz->cpitch, l.cout, l.x->v, l.x->lo, l.x->cpitch, l.x_coff, l.cin,
+                                                      l.x->g.total(), taps.off, partial, grads + l.w_off, st);
+      if (profiler().on) profiler().end(st);
+      SSDN_CUDA(ce);
+    } else {
+      SSDN_CUDA(wgrad_launch(l.wgrad, st));
+      wgradk::wgrad_reduce_launch(partial, l.wgrad.p.ksplit, nt, l.cout, l.cin, grads + l.w_off, 0, st);
+    }
+    if (l.bias_fused) {
+      pw::colsum_stage2_kernel<<<(l.cout + 31) / 32, dim3(32, 8), 0, st>>>(colpart2, l.bias_nblk, l.cout, grads + l.b_off, 0);
+    } else {
+      const long long rows = l.dz->g.total();
+      pw::colsum_launch(l.dz->v, l.dz->lo, rows, l.dz->cpitch, 0, l.cout, colpart, grads + l.b_off, st);
+    }
     return 0;
   }
   int run_dgrad(Layer& l, cudaStream_t st) { SSDN_CUDA(conv_launch(l.dgrad, st, 1)); return 0; }

@@ -43,6 +43,16 @@ __global__ void unpack_nchw_kernel(const float* __restrict__ v, const float* __r
   y[idx] = lo ? v[o] + lo[o] : v[o];
 }
 
+// LeakyReLU sign masks of a two-plane tensor (test hook: after an activation buffer was overwritten from outside).
+__global__ void mask_from_planes_kernel(const float* __restrict__ v, long long pixels, int cpitch, uint32_t* __restrict__ mask, int words) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= pixels * words) return;
+  const long long px = idx / words; const int w = (int)(idx - px * words);
+  uint32_t m = 0;
+  for (int i = 0; i < 32 && 32 * w + i < cpitch; ++i) m |= (v[px * cpitch + 32 * w + i] > 0.f ? 1u : 0u) << i;
+  mask[idx] = m;
+}
+
 // ---------------------------------------------------------------------------- max-pool 2x2
 // blind != 0: Shift2d((1,0)) then MaxPool2d(2)  (models/noise_network.py:64-67): window rows (2i-1, 2i),
 // row -1 is the zero halo row of the padded layout.  One thread = one output pixel x 4 channels.
@@ -165,6 +175,29 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, float* __restric
   }
   const long long o = ((t * 2) * N + n) * 16 + kk;
   tf32_split(val, slab[o], slab[o + (long long)N * 16]);
+}
+
+// All weight slabs of a network in ONE launch: blockIdx.y selects the job, blockIdx.x strides over its elements.
+struct WeightPrepJob { const float* w; float* slab; int cout, cin, ntaps, n_valid, k_valid, n_tiles, n_chunks, N, transpose; };
+constexpr int kMaxPrepJobs = 48;
+struct WeightPrepJobs { WeightPrepJob j[kMaxPrepJobs]; };
+__global__ void weight_prep_batched_kernel(const __grid_constant__ WeightPrepJobs jobs) {
+  const WeightPrepJob& q = jobs.j[blockIdx.y];
+  const long long total = (long long)q.n_tiles * q.n_chunks * q.ntaps * q.N * 16;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % 16); long long t = idx / 16;
+    const int n = (int)(t % q.N); t /= q.N;
+    const int tap = (int)(t % q.ntaps); const long long tc = t / q.ntaps;
+    const int ch = (int)(tc % q.n_chunks); const int nt = (int)(tc / q.n_chunks);
+    const int ng = nt * q.N + n, k = ch * 16 + kk;
+    float val = 0.f;
+    if (ng < q.n_valid && k < q.k_valid) {
+      const long long wi = q.transpose ? ((long long)k * q.cin + ng) * q.ntaps + tap : ((long long)ng * q.cin + k) * q.ntaps + tap;
+      val = __ldg(q.w + wi);
+    }
+    const long long o = ((t * 2) * q.N + n) * 16 + kk;
+    tf32_split(val, q.slab[o], q.slab[o + (long long)q.N * 16]);
+  }
 }
 
 // ---------------------------------------------------------------------------- bias gradient

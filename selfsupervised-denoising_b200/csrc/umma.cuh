@@ -6,6 +6,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// developer instrumentation: accumulate the clocks a call (an mbarrier wait) takes
+#define SSDN_TIMED(acc, call) do { const long long t0_ = clock64(); call; acc += clock64() - t0_; } while (0)
+
 namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -131,6 +134,20 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uin
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same, with the descriptors given as their LOW words (start address >> 4 | LBO << 16, see make_desc_base) and one shared
+// HIGH word: issue loops then advance a descriptor with ONE uniform add of a value in 16-byte units instead of
+// re-encoding (shift, mask, or) the address for every instruction.
+__device__ __forceinline__ void mma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.

@@ -31,6 +31,7 @@ struct WgradParams {
   uint32_t a_plane_bytes, b_plane_bytes;   // a_plane_bytes = nba * KC * 128 (loaded part; the MMA may address up to 4 blocks)
   float* partial;     // [ksplit][ntaps][cout][cin]
   int* error_flag;
+  unsigned long long* stats;   // developer instrumentation (SSDN_CONV_STATS=1)
 };
 
 struct WgradPlan {
@@ -81,12 +82,12 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, elected issue)
     int stage = 0; uint32_t phase = 0;
-    const uint32_t a_blk = p.KC * 128, b_blk = p.b_rows * 128;
+    long long w_empty = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       int ks, g, cb, ct; decode(u, ks, g, cb, ct);
       const int c0 = ks * p.chunks_per_split, c1 = min(p.n_kchunks, c0 + p.chunks_per_split);
       for (int c = c0; c < c1; ++c) {
-        umma::mbar_wait(empty(stage), phase ^ 1, abort_addr, p.error_flag, 11);
+        SSDN_TIMED(w_empty, umma::mbar_wait(empty(stage), phase ^ 1, abort_addr, p.error_flag, 11));
         const uint32_t av = sbase + stage * stage_bytes;
         const uint32_t bv = av + 2 * p.a_plane_bytes;
         const int row = c * p.KC, brow = row + p.groups[g].row_off;
@@ -100,53 +101,89 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
+    if (p.stats && lane == 0) p.stats[blockIdx.x * 16 + 0] = w_empty;
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: per (stage, tap) an unrolled block of KC/8 x 3 MMAs
     int stage = 0; uint32_t phase = 0; int it = 0;
     const uint64_t adesc = umma::make_desc_base(p.KC * 128, 512, 1);
     const uint64_t bdesc = umma::make_desc_base(p.b_rows * 128, 512, 1);
+    long long w_acc = 0, w_full = 0;
+    const long long t_start = clock64();
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
       int ks, g, cb, ct; decode(u, ks, g, cb, ct);
       const int c0 = ks * p.chunks_per_split, c1 = min(p.n_kchunks, c0 + p.chunks_per_split);
       const int N = p.ci_n[cb];
       const uint32_t idesc = umma::make_idesc_tf32(128, N, 1, 1);
-      umma::mbar_wait(acc_empty, (it & 1) ^ 1, abort_addr, p.error_flag, 12);
+      SSDN_TIMED(w_acc, umma::mbar_wait(acc_empty, (it & 1) ^ 1, abort_addr, p.error_flag, 12));
       umma::tc_fence_after();
       uint32_t acc = 0;
+      // one elected block of (taps x 4 k-steps x 3 products) MMAs per stage; descriptors advance by uniform adds in
+      // 16-byte units (low words), so the tensor core's queue does not drain between instructions
+      const uint32_t desc_hi = (uint32_t)(adesc >> 32);
+      const uint32_t a_lbo = (uint32_t)(adesc & 0xffff0000u), b_lbo = (uint32_t)(bdesc & 0xffff0000u);
+      const uint32_t a_pl = p.a_plane_bytes >> 4, b_pl = p.b_plane_bytes >> 4;
+      const int ntaps = p.groups[g].ntaps;
+      const bool unit_step = (ntaps == 3) && p.groups[g].tap_rel[1] == p.groups[g].tap_rel[0] + 1 && p.groups[g].tap_rel[2] == p.groups[g].tap_rel[0] + 2;
       for (int c = c0; c < c1; ++c) {
-        umma::mbar_wait(full(stage), phase, abort_addr, p.error_flag, 12);
+        SSDN_TIMED(w_full, umma::mbar_wait(full(stage), phase, abort_addr, p.error_flag, 12));
         umma::tc_fence_after();
-        const uint32_t av = sbase + stage * stage_bytes, al = av + p.a_plane_bytes;
-        const uint32_t bv0 = al + p.a_plane_bytes;
-        for (int t = 0; t < p.groups[g].ntaps; ++t) {
-          const uint32_t d = tmem + t * N;
-          const uint32_t bv = bv0 + p.groups[g].tap_rel[t] * 128, bl = bv + p.b_plane_bytes;
+        const uint32_t av = sbase + stage * stage_bytes;
+        const uint32_t bv0 = av + 2 * p.a_plane_bytes;
+        const uint32_t a0 = ((av >> 4) & 0x3fffu) | a_lbo;
+        if (unit_step || ntaps == 1) {
+          const uint32_t b0 = (((bv0 + p.groups[g].tap_rel[0] * 128) >> 4) & 0x3fffu) | b_lbo;
           if (umma::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {            // KC == 32: four k-steps of 8 pixels
-              const uint32_t o = k * 8 * 128;
-              umma::mma_tf32_ss(d, umma::desc_at(adesc, al + o), umma::desc_at(bdesc, bv + o), idesc, k == 0 ? acc : 1u);
-              umma::mma_tf32_ss(d, umma::desc_at(adesc, av + o), umma::desc_at(bdesc, bl + o), idesc, 1);
-              umma::mma_tf32_ss(d, umma::desc_at(adesc, av + o), umma::desc_at(bdesc, bv + o), idesc, 1);
+            for (int t = 0; t < 3; ++t) {
+              if (t < ntaps) {
+                const uint32_t d = tmem + t * N;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {          // KC == 32: four k-steps of 8 pixels (1024 bytes = 64 units)
+                  const uint32_t ah = a0 + k * 64, al = ah + a_pl, bh = b0 + t * 8 + k * 64, bl = bh + b_pl;
+                  umma::mma_tf32_lo(d, al, bh, desc_hi, idesc, k == 0 ? acc : 1u);
+                  umma::mma_tf32_lo(d, ah, bl, desc_hi, idesc, 1);
+                  umma::mma_tf32_lo(d, ah, bh, desc_hi, idesc, 1);
+                }
+              }
             }
+            umma::mma_commit(empty(stage));
           }
+          __syncwarp();
+        } else {
+          const uint32_t al = av + p.a_plane_bytes;
+          for (int t = 0; t < ntaps; ++t) {
+            const uint32_t d = tmem + t * N;
+            const uint32_t bv = bv0 + p.groups[g].tap_rel[t] * 128, bl = bv + p.b_plane_bytes;
+            if (umma::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t o = k * 8 * 128;
+                umma::mma_tf32_ss(d, umma::desc_at(adesc, al + o), umma::desc_at(bdesc, bv + o), idesc, k == 0 ? acc : 1u);
+                umma::mma_tf32_ss(d, umma::desc_at(adesc, av + o), umma::desc_at(bdesc, bl + o), idesc, 1);
+                umma::mma_tf32_ss(d, umma::desc_at(adesc, av + o), umma::desc_at(bdesc, bv + o), idesc, 1);
+              }
+            }
+            __syncwarp();
+          }
+          if (umma::elect_one()) umma::mma_commit(empty(stage));
           __syncwarp();
         }
         acc = 1;
-        if (umma::elect_one()) umma::mma_commit(empty(stage));
-        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       if (umma::elect_one()) umma::mma_commit(acc_full);
       __syncwarp();
     }
+    if (p.stats && lane == 0) { p.stats[blockIdx.x * 16 + 1] = w_acc; p.stats[blockIdx.x * 16 + 2] = w_full; p.stats[blockIdx.x * 16 + 3] = clock64() - t_start; }
   } else {
     const int ew = warp & 3;   // TMEM sub-partition of this warp (warps 2,3,4,5 -> 2,3,0,1)
     int it = 0;
+    long long w_accf = 0;
+    const long long t_start = clock64();
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
       int ks, g, cb, ct; decode(u, ks, g, cb, ct);
       const int N = p.ci_n[cb];
-      umma::mbar_wait(acc_full, it & 1, abort_addr, p.error_flag, 13);
+      SSDN_TIMED(w_accf, umma::mbar_wait(acc_full, it & 1, abort_addr, p.error_flag, 13));
       umma::tc_fence_after();
       const int co = ct * 128 + ew * 32 + lane;
       for (int t = 0; t < p.groups[g].ntaps; ++t) {
@@ -166,6 +203,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
       umma::tc_fence_before();
       umma::mbar_arrive(acc_empty);
     }
+    if (p.stats && threadIdx.x == 64) { p.stats[blockIdx.x * 16 + 4] = w_accf; p.stats[blockIdx.x * 16 + 5] = clock64() - t_start; }
   }
   umma::tc_fence_before();
   __syncthreads();
@@ -173,17 +211,104 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
 }
 
 // dW[co][ci][tap] (PyTorch layout) = (accumulate ? dW : 0) + sum_ks partial[ks][tap][co][ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int ksplit, int ntaps, int cout, int cin,
-                                    float* __restrict__ dw, int accumulate) {
+// block = (32 outputs, 16 K-split lanes): thread (x, y) sums splits y, y+16, ... of output blockIdx.x*32 + x with four
+// independent accumulators (coalesced 128-byte rows, many loads in flight), then the 16 lanes are combined in a fixed
+// order through shared memory - deterministic, and ~10x faster than one thread walking all splits serially.
+__global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restrict__ partial, int ksplit, int ntaps, int cout, int cin,
+                                                           float* __restrict__ dw, int accumulate) {
+  __shared__ float sm[16][33];
   const long long n = (long long)cout * cin * ntaps;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // over [tap][co][ci] (coalesced reads)
-  if (idx >= n) return;
-  const int ci = (int)(idx % cin); long long t = idx / cin;
-  const int co = (int)(t % cout); const int tap = (int)(t / cout);
-  float acc = 0.f;
-  for (int k = 0; k < ksplit; ++k) acc += partial[(long long)k * n + idx];
-  const long long o = ((long long)co * cin + ci) * ntaps + tap;
-  dw[o] = accumulate ? dw[o] + acc : acc;
+  const long long idx = blockIdx.x * 32LL + threadIdx.x;   // over [tap][co][ci]
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (idx < n) {
+    int k = threadIdx.y;
+    for (; k + 48 < ksplit; k += 64) {
+      a0 += __ldg(partial + (long long)k * n + idx); a1 += __ldg(partial + (long long)(k + 16) * n + idx);
+      a2 += __ldg(partial + (long long)(k + 32) * n + idx); a3 += __ldg(partial + (long long)(k + 48) * n + idx);
+    }
+    for (; k < ksplit; k += 16) a0 += __ldg(partial + (long long)k * n + idx);
+  }
+  sm[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (threadIdx.y == 0 && idx < n) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) acc += sm[w][threadIdx.x];
+    const int ci = (int)(idx % cin); long long t = idx / cin;
+    const int co = (int)(t % cout); const int tap = (int)(t / cout);
+    const long long o = ((long long)co * cin + ci) * ntaps + tap;
+    dw[o] = accumulate ? dw[o] + acc : acc;
+  }
+}
+static inline void wgrad_reduce_launch(const float* partial, int ksplit, int ntaps, int cout, int cin, float* dw, int accumulate, cudaStream_t st) {
+  const long long n = (long long)cout * cin * ntaps;
+  wgrad_reduce_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 16), 0, st>>>(partial, ksplit, ntaps, cout, cin, dw, accumulate);
+}
+
+// Weight gradient of the FIRST convolution (1..4 input channels, e.g. RGB): a [cout] x [cin x taps] problem is far too thin
+// for a 128 x N tensor-core tile (3 useful columns of 16), so it runs on the CUDA cores.  Thread (tap, co) keeps dW[tap][co][0..3]
+// in registers; dZ (hi + lo) and the X window (hi + lo, padded to float4) of 128 flat pixels are staged in shared memory;
+// every read in the pixel loop is either a broadcast or 32 consecutive words.  Partials [CTA][tap][co][ci] go through the
+// same fixed-order reduction as the tensor-core path.
+struct SmallCinTaps { int rel[9]; int lo; int span; };
+constexpr int kSmallCinTile = 128;
+__global__ void __launch_bounds__(1024) wgrad_small_cin_kernel(const float* __restrict__ dz_v, const float* __restrict__ dz_lo, int dz_cpitch,
+                                                               int cout, const float* __restrict__ x_v, const float* __restrict__ x_lo,
+                                                               int x_cpitch, int x_coff, int cin, long long total, SmallCinTaps taps,
+                                                               float* __restrict__ partial) {
+  extern __shared__ __align__(16) float sm_small[];
+  float* dz_s = sm_small;                                             // [128][cout]
+  float4* x_s = reinterpret_cast<float4*>(sm_small + kSmallCinTile * cout);   // [128 + span]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tap = tid / cout, co = tid - tap * cout;
+  const int rows = kSmallCinTile + taps.span;
+  const int rel = taps.rel[tap];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const long long ntiles = (total + kSmallCinTile - 1) / kSmallCinTile;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long base = tile * kSmallCinTile;
+    __syncthreads();
+    for (int i = tid; i < kSmallCinTile * cout; i += nthr) {
+      const int px = i / cout, c = i - px * cout;
+      const long long g = base + px;
+      dz_s[i] = g < total ? __ldg(dz_v + g * dz_cpitch + c) + __ldg(dz_lo + g * dz_cpitch + c) : 0.f;
+    }
+    for (int r = tid; r < rows; r += nthr) {
+      const long long g = base + taps.lo + r;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (g >= 0 && g < total)
+        for (int c = 0; c < cin; ++c) v[c] = __ldg(x_v + g * x_cpitch + x_coff + c) + __ldg(x_lo + g * x_cpitch + x_coff + c);
+      x_s[r] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int px = 0; px < kSmallCinTile; ++px) {
+      const float d = dz_s[px * cout + co];
+      const float4 xv = x_s[px + rel];
+      a0 = fmaf(d, xv.x, a0); a1 = fmaf(d, xv.y, a1); a2 = fmaf(d, xv.z, a2); a3 = fmaf(d, xv.w, a3);
+    }
+  }
+  float* dst = partial + ((long long)blockIdx.x * 9 + tap) * cout * cin + (long long)co * cin;
+  const float acc[4] = {a0, a1, a2, a3};
+  for (int c = 0; c < cin; ++c) dst[c] = acc[c];
+}
+constexpr int kSmallCinGrid = 296;
+static inline bool wgrad_small_cin_ok(int cin, int cout, int ntaps) { return cin <= 4 && ntaps == 9 && cout * ntaps <= 1024; }
+static inline size_t wgrad_small_cin_partial_floats(int cin, int cout) { return (size_t)kSmallCinGrid * 9 * cout * cin; }
+// taps: forward flat-pixel offsets of X relative to dZ (9 of them)
+static inline cudaError_t wgrad_small_cin_launch(const float* dz_v, const float* dz_lo, int dz_cpitch, int cout, const float* x_v, const float* x_lo,
+                                                 int x_cpitch, int x_coff, int cin, long long total, const int* tap_off, float* partial, float* dw,
+                                                 cudaStream_t st) {
+  SmallCinTaps t; t.lo = tap_off[0]; int hi = tap_off[0];
+  for (int i = 1; i < 9; ++i) { t.lo = tap_off[i] < t.lo ? tap_off[i] : t.lo; hi = tap_off[i] > hi ? tap_off[i] : hi; }
+  t.span = hi - t.lo;
+  for (int i = 0; i < 9; ++i) t.rel[i] = tap_off[i] - t.lo;
+  const size_t smem = (size_t)kSmallCinTile * cout * 4 + (size_t)(kSmallCinTile + t.span) * 16;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(wgrad_small_cin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+  wgrad_small_cin_kernel<<<kSmallCinGrid, cout * 9, smem, st>>>(dz_v, dz_lo, dz_cpitch, cout, x_v, x_lo, x_cpitch, x_coff, cin, total, t, partial);
+  wgrad_reduce_launch(partial, kSmallCinGrid, 9, cout, cin, dw, 0, st);
+  return cudaGetLastError();
 }
 
 }  // namespace wgradk
@@ -276,6 +401,25 @@ static inline cudaError_t wgrad_launch(const WgradPlan& plan, cudaStream_t strea
     cudaError_t e = cudaFuncSetAttribute(wgradk::wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
+  }
+  static const bool want_stats = getenv("SSDN_CONV_STATS") != nullptr;
+  if (want_stats && profiler().on) {
+    static unsigned long long* dev = nullptr;
+    if (!dev) cudaMalloc(&dev, 1024 * 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(dev, 0, 1024 * 16 * sizeof(unsigned long long), stream);
+    WgradParams p = plan.p; p.stats = dev;
+    profiler().begin(2, plan.flops, stream);
+    wgradk::wgrad_igemm_kernel<<<plan.grid, wgradk::kThreads, plan.smem, stream>>>(plan.dz, plan.x, p);
+    profiler().end(stream);
+    std::vector<unsigned long long> h((size_t)plan.grid * 16);
+    cudaMemcpyAsync(h.data(), dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    double s[8] = {0};
+    for (int b = 0; b < plan.grid; ++b) for (int k = 0; k < 8; ++k) s[k] += (double)h[(size_t)b * 16 + k] / plan.grid;
+    fprintf(stderr, "[wgrad stats] grid %d cout %d cin %d ci_blocks %d groups %d ksplit %d chunks/split %d stages %d nba %d nbx %d b_rows %d | mma loop %.0f clk: wait acc_empty %.1f%% "
+            "full %.1f%% | producer wait empty %.1f%% | epi loop %.0f clk: wait acc_full %.1f%%\n", plan.grid, p.cout, p.cin, p.n_ci_blocks, p.n_groups, p.ksplit,
+            p.chunks_per_split, p.stages, p.nba, p.nbx, p.b_rows, s[3], 100 * s[1] / s[3], 100 * s[2] / s[3], 100 * s[0] / s[3], s[5], 100 * s[4] / s[5]);
+    return e != cudaSuccess ? e : cudaGetLastError();
   }
   if (profiler().on) profiler().begin(2, plan.flops, stream);
   wgradk::wgrad_igemm_kernel<<<plan.grid, wgradk::kThreads, plan.smem, stream>>>(plan.dz, plan.x, plan.p);
