@@ -99,10 +99,9 @@ extern "C" int ssdn_profile_records(double* out, int max_records) {
 }
 extern "C" int ssdn_net_kernel_launches(void* handle, int training) {
   net::Net* nn = (net::Net*)handle;
-  int nfused = 0;
-  for (auto& l : nn->layers) nfused += l.bias_fused ? 1 : 0;
-  int fwd = (int)nn->layers.size() /*conv*/ + 5 /*pool*/ + 1 /*pack*/ + 1 /*weight slabs*/;
-  int bwd = 1 + (int)nn->layers.size() * 4 /*wgrad, reduce, colsum x2*/ - nfused /*fused column sums*/ + ((int)nn->layers.size() - 1) /*dgrad*/ + 5 + 5;
+  const int nl = (int)nn->layers.size();
+  int fwd = nl /*conv*/ + 5 /*pool*/ + 1 /*pack*/ + 1 /*weight slabs*/;
+  int bwd = 2 /*pack, loss-gradient column sums*/ + nl * 3 /*wgrad, split-K reduce, bias reduce*/ + (nl - 1) /*dgrad*/ + 5 + 5 /*pool, upsample*/;
   return training ? fwd + bwd : fwd;
 }
 

@@ -38,6 +38,7 @@ struct ConvParams {
   int row3;           // 1: every B stage holds the 3 taps of one stencil row of one group, tap_rel advancing by tap_step
   int tap_step;       //    (+1 forward, -1 data-gradient): the MMA warp then issues 3 x T x 6 MMAs per barrier wait
   uint32_t a_plane_bytes, b_stage_bytes;   // smem bytes of one A plane of one stage / of one B stage
+  uint32_t epi_off;   // MAP_UP2 only: byte offset of the epilogue staging area (4 warps x 32 pixels x 36 floats) in dynamic smem
   ConvDst dst;
   int* error_flag;
   int debug;          // experiments only: 2 = skip MMA issue
@@ -62,6 +63,7 @@ struct Ring {
   __device__ void advance() { if (++stage == n) { stage = 0; phase ^= 1; } }
 };
 
+constexpr int kStagePitch = 36;   // floats per staged pixel row (32 channels + 4 pad: conflict-free float4 access)
 constexpr int kMaxSlices = 5;     // 32-channel slices of one N tile (N <= 144 + padding)
 
 // What the epilogue needs to know about one lane's pixel of one 128-pixel tile.  Computed one tile ahead so that the
@@ -440,6 +442,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (i < cw && cg0 + i < d.cvalid)
                       d.v[(((long long)cur.b * d.cvalid + cg0 + i) * sg.H + cur.y) * sg.W + cur.x] = f[i];
                 }
+              } else if (d.map == MAP_UP2) {
+                // 4 destinations per pixel: transposing the slice through shared memory lets 8 consecutive lanes write one
+                // pixel's 128 contiguous bytes (4 full lines per store instruction instead of 32 line fragments) - with four
+                // times the store volume the load/store unit, not the tensor core's operand traffic, is what would bind
+                float* stage = reinterpret_cast<float*>(smem + p.epi_off) + ew * 32 * kStagePitch;
+                float* row = stage + lane * kStagePitch;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(row + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                __syncwarp();
+                const int L = cw >> 2, PPI = 32 / L, sub = lane / L, q4 = lane - sub * L;   // L lanes per pixel, PPI pixels per pass
+                const bool chan_ok = cg0 + 4 * q4 < d.cvalid;
+                for (int q = 0; q < 32; q += PPI) {
+                  const int px = q + sub;
+                  const int pd0 = __shfl_sync(0xffffffffu, cur.d0, px), pnd = __shfl_sync(0xffffffffu, cur.nd, px);
+                  if (chan_ok) {
+                    const float4 o = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 4 * q4);
+                    float4 h = o, l = o;
+                    if (d.flags & EP_WRITE_LO) { tf32_split(o.x, h.x, l.x); tf32_split(o.y, h.y, l.y); tf32_split(o.z, h.z, l.z); tf32_split(o.w, h.w, l.w); }
+                    for (int k = 0; k < pnd; ++k) {
+                      const long long oi = (long long)(pd0 + (k & 1) + (k >> 1) * d.g.P) * d.cpitch + d.coff + cg0 + 4 * q4;
+                      *reinterpret_cast<float4*>(d.v + oi) = h;
+                      if (d.flags & EP_WRITE_LO) *reinterpret_cast<float4*>(d.lo + oi) = l;
+                    }
+                  }
+                }
+                __syncwarp();
               } else if (cur.nd) {
                 const long long cbase = d.coff + cur.cshift + cg0;
                 for (int k = 0; k < cur.nd; ++k) {
@@ -553,8 +581,10 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     uint32_t plane = (uint32_t)(nbox * box_rows * 64);
     int stages = (mode == 0) ? 2 : 3;
     for (int bst = 4; bst >= 2; --bst) {
-      size_t need = (size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes + 2048;
+      const size_t epi = dst.map == MAP_UP2 ? 4 * 32 * convk::kStagePitch * sizeof(float) : 0;
+      size_t need = (size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes + epi + 2048;
       if (need > smem_limit) continue;
+      p.epi_off = (uint32_t)((size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes);
       p.n_groups = (int)gs.size(); p.nbox = nbox; p.box_rows = box_rows; p.a_plane_bytes = plane; p.a_stages = stages; p.b_stages = bst;
       for (size_t gi = 0; gi < gs.size(); ++gi) {
         int lo = INT32_MAX;

@@ -32,7 +32,8 @@ struct Layer {               // one convolution of the network
   // data gradient (has_dgrad == false for the first conv: nobody consumes d(input))
   bool has_dgrad = false;
   ConvPlan dgrad; float* slab_d; int n_d; int cinp_d; int dgrad_nvalid;
-  bool bias_fused = false; int bias_nblk = 0;   // bias gradient = column sums written by the dgrad epilogue that produced this layer's dZ
+  bool bias_fused = false; int bias_nblk = 0;   // bias gradient = column sums written by the kernel that produced this layer's dZ
+  const float* bias_partial = nullptr;          //   partial[bias_nblk][cout]
   // weight gradient
   WgradPlan wgrad; int ksplit;
   const Buf* x; int x_coff;          // conv input (channel slice [x_coff, x_coff+cin))
@@ -42,6 +43,7 @@ struct Layer {               // one convolution of the network
 struct PoolOp { const Buf* src; const Buf* dst; int dst_coff; };
 struct PoolBwdOp { const Buf* act; const Buf* g1; const Buf* g2; int g2_coff; const Buf* dz; Geom gp; };
 struct UpBwdOp { const Buf* g; const Buf* act_up; const Buf* dz; int C; };
+// pool_bwd / up_bwd / the loss-gradient pack also produce a dZ: their fused column sums go to colpart3
 
 class Net {
  public:
@@ -53,7 +55,7 @@ class Net {
   // buffers
   Buf cat[6], e[6], e1a, p5, d_a[6], head_in, h1, h2;
   Buf g_out, dz_h2, dz_h1, dz_db[6], dz_da[6], gcat[6], dz_e[7], dz_e1a, g_p[6];
-  float* partial = nullptr; float* colpart = nullptr; float* colpart2 = nullptr; int* flag = nullptr;
+  float* partial = nullptr; float* colpart = nullptr; float* colpart2 = nullptr; float* colpart3 = nullptr; int* flag = nullptr;
   size_t partial_floats = 0;
   size_t ws_bytes = 0; void* ws = nullptr;
   std::vector<PoolOp> pools; std::vector<PoolBwdOp> pool_bwds; std::vector<UpBwdOp> up_bwds;
@@ -158,6 +160,7 @@ class Net {
     partial = a.take<float>(partial_floats);
     colpart = a.take<float>((size_t)1024 * 384);
     colpart2 = a.take<float>((size_t)1024 * 384);
+    colpart3 = a.take<float>((size_t)1024 * 96);
     flag = a.take<int>(64);
     return a.off;
   }
@@ -206,7 +209,15 @@ class Net {
     // ---- backward: data gradients
     const int gact = EP_ACT_GRAD | EP_WRITE_LO;
     // every dst_act below also yields the bias gradient of the layer that owns the produced dZ (fused column sums)
-    auto fused = [&](const char* producer, const char* owner) { Layer& o = L(owner); o.bias_fused = true; o.bias_nblk = L(producer).dgrad.grid * 4; };
+    auto fused = [&](const char* producer, const char* owner) {
+      Layer& o = L(owner); o.bias_fused = true; o.bias_nblk = L(producer).dgrad.grid * 4; o.bias_partial = colpart2;
+    };
+    auto fused_pw = [&](const std::string& owner, int nblk) { Layer& o = L(owner); o.bias_fused = true; o.bias_nblk = nblk; o.bias_partial = colpart3; };
+    fused_pw("output_conv", N);                                              // nchw_colsum_kernel over d(loss)/d(out)
+    for (int i = 2; i <= 5; ++i) fused_pw("decode_block_" + std::to_string(i) + ".2", pw::kFusedColsumGrid);   // up_bwd
+    fused_pw("encode_block_6.0", pw::kFusedColsumGrid);                      // up_bwd
+    fused_pw("encode_block_1.2", pw::kFusedColsumGrid);                      // pool_bwd
+    for (int i = 2; i <= 5; ++i) fused_pw("encode_block_" + std::to_string(i) + ".0", pw::kFusedColsumGrid);   // pool_bwd
     if ((r = plan_dgrad(L("output_conv"), g_out, dst_act(dz_h2, MAP_IDENT, gact, 96, h2, true)))) return r;
     fused("output_conv", "output_block.2");
     if ((r = plan_dgrad(L("output_block.2"), dz_h2, dst_act(dz_h1, MAP_IDENT, gact, nin, h1, true)))) return r;
@@ -321,7 +332,7 @@ class Net {
     if (!ws) return eng::fail(-5, "network workspace not bound");
     int r;
     if ((r = prep_weights(params, st, training))) return r;
-    pw::pack_nchw_kernel<<<pw::grid_for((long long)B * Cin * H * W), pw::kBlock, 0, st>>>(x, cat[1].v, cat[1].lo, N, Cin, H, W, g[0],
+    pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)B * H * W), pw::kBlock, 0, st>>>(x, cat[1].v, cat[1].lo, N, Cin, H, W, g[0],
                                                                                           cat[1].cpitch, 96, blind ? 1 : 0);
     size_t pi = 0;
     auto pool = [&]() {
@@ -360,7 +371,7 @@ class Net {
       wgradk::wgrad_reduce_launch(partial, l.wgrad.p.ksplit, nt, l.cout, l.cin, grads + l.w_off, 0, st);
     }
     if (l.bias_fused) {
-      pw::colsum_stage2_kernel<<<(l.cout + 31) / 32, dim3(32, 8), 0, st>>>(colpart2, l.bias_nblk, l.cout, grads + l.b_off, 0);
+      pw::colsum_stage2_launch(l.bias_partial, l.bias_nblk, l.cout, grads + l.b_off, st);
     } else {
       const long long rows = l.dz->g.total();
       pw::colsum_launch(l.dz->v, l.dz->lo, rows, l.dz->cpitch, 0, l.cout, colpart, grads + l.b_off, st);
@@ -373,8 +384,9 @@ class Net {
   int backward(const float* params, const float* dout, float* grads, cudaStream_t st) {
     if (!ws) return eng::fail(-5, "network workspace not bound");
     int r;
-    pw::pack_nchw_kernel<<<pw::grid_for((long long)N * Cout * H * W), pw::kBlock, 0, st>>>(dout, g_out.v, g_out.lo, N, Cout, H, W, gh,
-                                                                                           g_out.cpitch, 0, 0);
+    pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)N * H * W), pw::kBlock, 0, st>>>(dout, g_out.v, g_out.lo, N, Cout, H, W, gh,
+                                                                                          g_out.cpitch, 0, 0);
+    pw::nchw_colsum_kernel<<<dim3(Cout, N), 256, 0, st>>>(dout, Cout, H * W, colpart3);
     auto both = [&](const std::string& nm, bool dgrad) -> int {
       Layer& l = L(nm);
       int rr = run_wgrad(l, grads, st);
@@ -389,15 +401,19 @@ class Net {
       const UpBwdOp& u = up_bwds[ui++];
       const Geom& gl = u.dz->g;
       const long long n = (long long)gl.B * gl.H * gl.W * (u.C / 4);
-      pw::up_bwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(u.g->v, u.g->g, u.g->cpitch, 0, u.act_up->v, u.act_up->cpitch, 0, gl, u.dz->v,
-                                                                u.dz->lo, u.dz->cpitch, 0, u.C);
+      const int grid = (int)std::min<long long>(pw::kFusedColsumGrid, (n + pw::kFusedColsumBlock - 1) / pw::kFusedColsumBlock);
+      if (grid < pw::kFusedColsumGrid) cudaMemsetAsync(colpart3, 0, (size_t)pw::kFusedColsumGrid * u.C * sizeof(float), st);
+      pw::up_bwd_kernel<<<grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * sizeof(float4), st>>>(
+          u.g->v, u.g->g, u.g->cpitch, 0, u.act_up->v, u.act_up->cpitch, 0, gl, u.dz->v, u.dz->lo, u.dz->cpitch, 0, u.C, colpart3);
     };
     auto pool_bwd = [&]() {
       const PoolBwdOp& q = pool_bwds[qi++];
       const long long n = (long long)q.gp.B * q.gp.H * q.gp.W * 48;
-      pw::pool_bwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(q.act->v, q.act->lo, q.act->g, q.act->cpitch, 0, q.g1->v, q.g1->cpitch, 0,
-                                                                  q.g2 ? q.g2->v : nullptr, q.g2 ? q.g2->cpitch : 0, q.g2_coff, q.gp, q.dz->v,
-                                                                  q.dz->lo, q.dz->cpitch, 0, 48, blind ? 1 : 0);
+      const int grid = (int)std::min<long long>(pw::kFusedColsumGrid, (n + pw::kFusedColsumBlock - 1) / pw::kFusedColsumBlock);
+      if (grid < pw::kFusedColsumGrid) cudaMemsetAsync(colpart3, 0, (size_t)pw::kFusedColsumGrid * 48 * sizeof(float), st);
+      pw::pool_bwd_kernel<<<grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * sizeof(float), st>>>(
+          q.act->v, q.act->lo, q.act->g, q.act->cpitch, 0, q.g1->v, q.g1->cpitch, 0, q.g2 ? q.g2->v : nullptr, q.g2 ? q.g2->cpitch : 0, q.g2_coff, q.gp,
+          q.dz->v, q.dz->lo, q.dz->cpitch, 0, 48, blind ? 1 : 0, colpart3);
     };
     for (int i = 1; i <= 5; ++i) {
       if ((r = both("decode_block_" + std::to_string(i) + ".2", true))) return r;

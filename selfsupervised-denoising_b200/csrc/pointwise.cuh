@@ -30,6 +30,28 @@ __global__ void pack_nchw_kernel(const float* __restrict__ x, float* __restrict_
   else v[o] = val;
 }
 
+// Same mapping, one thread per output PIXEL writing all C (<= 16) channels: the stores of a thread are contiguous and
+// the index arithmetic is done once per pixel (the network input and the loss gradient have 3..12 channels).
+__global__ void pack_nchw_pixel_kernel(const float* __restrict__ x, float* __restrict__ v, float* __restrict__ lo,
+                                       int B, int C, int H, int W, Geom g, int cpitch, int coff, int rot4) {
+  const long long n = (long long)(rot4 ? 4 : 1) * B * H * W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int j = (int)(idx % W); long long t = idx / W;
+  const int i = (int)(t % H); const int bo = (int)(t / H);
+  const int r = rot4 ? bo / B : 0, b = rot4 ? bo % B : bo;
+  int si = i, sj = j;
+  if (r == 1) { si = j; sj = W - 1 - i; } else if (r == 2) { si = H - 1 - i; sj = W - 1 - j; }
+  else if (r == 3) { si = H - 1 - j; sj = i; }
+  const float* src = x + ((long long)b * C * H + si) * W + sj;
+  const long long o = ((long long)bo * g.S + (i + g.row0) * g.P + j) * cpitch + coff;
+  for (int c = 0; c < C; ++c) {
+    const float val = __ldg(src + (long long)c * H * W);
+    if (lo) { float h, l; tf32_split(val, h, l); v[o + c] = h; lo[o + c] = l; }
+    else v[o + c] = val;
+  }
+}
+
 // padded flat -> dense NCHW (tests / gradients w.r.t. the input)
 __global__ void unpack_nchw_kernel(const float* __restrict__ v, const float* __restrict__ lo, float* __restrict__ y, int B, int C,
                                    int H, int W, Geom g, int cpitch, int coff) {
@@ -96,33 +118,47 @@ __global__ void pool_bwd_kernel(const float* __restrict__ act, const float* __re
                                 const float* __restrict__ g1, int g1_cpitch, int g1_coff,
                                 const float* __restrict__ g2, int g2_cpitch, int g2_coff, Geom gp,
                                 float* __restrict__ dv, float* __restrict__ dlo, int d_cpitch, int d_coff,
-                                int C, int blind) {
+                                int C, int blind, float* __restrict__ colsum_partial) {
+  // grid-stride with blockDim.x a multiple of C: a thread keeps its channel, so the column sums of dZ (the bias gradient of
+  // the conv in front of the pool) accumulate in a register; partial [gridDim.x][C], fixed-order second stage.
+  extern __shared__ float sm_pool[];
   const long long n = (long long)gp.B * gp.H * gp.W * C;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  const int c = (int)(idx % C); long long t = idx / C;
-  const int xo = (int)(t % gp.W); t /= gp.W;
-  const int yo = (int)(t % gp.H); const int b = (int)(t / gp.H);
-  const long long pflat = (long long)b * gp.S + (yo + gp.row0) * gp.P + xo;
-  float g = __ldg(g1 + pflat * g1_cpitch + g1_coff + c);
-  if (g2) g += __ldg(g2 + pflat * g2_cpitch + g2_coff + c);
-  const int y0 = 2 * yo - (blind ? 1 : 0);
-  const long long f0 = (long long)b * ga_.S + (y0 + ga_.row0) * ga_.P + 2 * xo;
-  const long long fl[4] = {f0, f0 + 1, f0 + ga_.P, f0 + ga_.P + 1};
-  float best = -INFINITY; int arg = 0;
+  float csum = 0.f;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C); long long t = idx / C;
+    const int xo = (int)(t % gp.W); t /= gp.W;
+    const int yo = (int)(t % gp.H); const int b = (int)(t / gp.H);
+    const long long pflat = (long long)b * gp.S + (yo + gp.row0) * gp.P + xo;
+    float g = __ldg(g1 + pflat * g1_cpitch + g1_coff + c);
+    if (g2) g += __ldg(g2 + pflat * g2_cpitch + g2_coff + c);
+    const int y0 = 2 * yo - (blind ? 1 : 0);
+    const long long f0 = (long long)b * ga_.S + (y0 + ga_.row0) * ga_.P + 2 * xo;
+    const long long fl[4] = {f0, f0 + 1, f0 + ga_.P, f0 + ga_.P + 1};
+    float best = -INFINITY; int arg = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float a = __ldg(act + fl[k] * a_cpitch + a_coff + c) + __ldg(act_lo + fl[k] * a_cpitch + a_coff + c);
-    if (a > best || a != a) { best = a; arg = k; }
+    for (int k = 0; k < 4; ++k) {
+      const float a = __ldg(act + fl[k] * a_cpitch + a_coff + c) + __ldg(act_lo + fl[k] * a_cpitch + a_coff + c);
+      if (a > best || a != a) { best = a; arg = k; }
+    }
+    const bool halo_row = blind && yo == 0;   // window rows (-1, 0): elements 0,1 are padding
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (halo_row && k < 2) continue;        // never write the halo
+      float o = 0.f;
+      if (k == arg) o = best > 0.f ? g : SSDN_LRELU_SLOPE * g;
+      csum += o;
+      const long long di = fl[k] * d_cpitch + d_coff + c;
+      tf32_split(o, dv[di], dlo[di]);
+    }
   }
-  const bool halo_row = blind && yo == 0;   // window rows (-1, 0): elements 0,1 are padding
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (halo_row && k < 2) continue;        // never write the halo
-    float o = 0.f;
-    if (k == arg) o = best > 0.f ? g : SSDN_LRELU_SLOPE * g;
-    const long long di = fl[k] * d_cpitch + d_coff + c;
-    tf32_split(o, dv[di], dlo[di]);
+  if (colsum_partial) {
+    sm_pool[threadIdx.x] = csum;
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float t = 0.f;
+      for (int k = threadIdx.x; k < blockDim.x; k += C) t += sm_pool[k];
+      colsum_partial[(long long)blockIdx.x * C + threadIdx.x] = t;
+    }
   }
 }
 
@@ -130,28 +166,61 @@ __global__ void pool_bwd_kernel(const float* __restrict__ act, const float* __re
 // The forward activation is read from its upsampled copy (geometry gg, pixel (2y, 2x)).
 __global__ void up_bwd_kernel(const float* __restrict__ g, Geom gg, int g_cpitch, int g_coff,
                               const float* __restrict__ act, int a_cpitch, int a_coff, Geom gl,
-                              float* __restrict__ dv, float* __restrict__ dlo, int d_cpitch, int d_coff, int C) {
+                              float* __restrict__ dv, float* __restrict__ dlo, int d_cpitch, int d_coff, int C,
+                              float* __restrict__ colsum_partial) {
+  // grid-stride with blockDim.x a multiple of C/4 (see pool_bwd_kernel): fused column sums of the produced dZ
+  extern __shared__ float4 sm_up[];
   const int c4n = C / 4;
   const long long n = (long long)gl.B * gl.H * gl.W * c4n;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  const int c = (int)(idx % c4n) * 4; long long t = idx / c4n;
-  const int x = (int)(t % gl.W); t /= gl.W;
-  const int y = (int)(t % gl.H); const int b = (int)(t / gl.H);
-  const long long s0 = ((long long)b * gg.S + (2 * y + gg.row0) * gg.P + 2 * x) * g_cpitch + g_coff + c;
-  const float4 a = *reinterpret_cast<const float4*>(g + s0);
-  const float4 bq = *reinterpret_cast<const float4*>(g + s0 + g_cpitch);
-  const float4 cq = *reinterpret_cast<const float4*>(g + s0 + (long long)gg.P * g_cpitch);
-  const float4 dq = *reinterpret_cast<const float4*>(g + s0 + (long long)(gg.P + 1) * g_cpitch);
-  const long long lf = (long long)b * gl.S + (y + gl.row0) * gl.P + x;
-  const float4 av = *reinterpret_cast<const float4*>(
-      act + ((long long)b * gg.S + (2 * y + gg.row0) * gg.P + 2 * x) * a_cpitch + a_coff + c);
-  float4 s;
-  s.x = (a.x + bq.x) + (cq.x + dq.x); s.y = (a.y + bq.y) + (cq.y + dq.y);
-  s.z = (a.z + bq.z) + (cq.z + dq.z); s.w = (a.w + bq.w) + (cq.w + dq.w);
-  s.x = av.x > 0.f ? s.x : SSDN_LRELU_SLOPE * s.x; s.y = av.y > 0.f ? s.y : SSDN_LRELU_SLOPE * s.y;
-  s.z = av.z > 0.f ? s.z : SSDN_LRELU_SLOPE * s.z; s.w = av.w > 0.f ? s.w : SSDN_LRELU_SLOPE * s.w;
-  st2(dv, dlo, lf * d_cpitch + d_coff + c, s);
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) * 4; long long t = idx / c4n;
+    const int x = (int)(t % gl.W); t /= gl.W;
+    const int y = (int)(t % gl.H); const int b = (int)(t / gl.H);
+    const long long s0 = ((long long)b * gg.S + (2 * y + gg.row0) * gg.P + 2 * x) * g_cpitch + g_coff + c;
+    const float4 a = *reinterpret_cast<const float4*>(g + s0);
+    const float4 bq = *reinterpret_cast<const float4*>(g + s0 + g_cpitch);
+    const float4 cq = *reinterpret_cast<const float4*>(g + s0 + (long long)gg.P * g_cpitch);
+    const float4 dq = *reinterpret_cast<const float4*>(g + s0 + (long long)(gg.P + 1) * g_cpitch);
+    const long long lf = (long long)b * gl.S + (y + gl.row0) * gl.P + x;
+    const float4 av = *reinterpret_cast<const float4*>(
+        act + ((long long)b * gg.S + (2 * y + gg.row0) * gg.P + 2 * x) * a_cpitch + a_coff + c);
+    float4 s;
+    s.x = (a.x + bq.x) + (cq.x + dq.x); s.y = (a.y + bq.y) + (cq.y + dq.y);
+    s.z = (a.z + bq.z) + (cq.z + dq.z); s.w = (a.w + bq.w) + (cq.w + dq.w);
+    s.x = av.x > 0.f ? s.x : SSDN_LRELU_SLOPE * s.x; s.y = av.y > 0.f ? s.y : SSDN_LRELU_SLOPE * s.y;
+    s.z = av.z > 0.f ? s.z : SSDN_LRELU_SLOPE * s.z; s.w = av.w > 0.f ? s.w : SSDN_LRELU_SLOPE * s.w;
+    csum.x += s.x; csum.y += s.y; csum.z += s.z; csum.w += s.w;
+    st2(dv, dlo, lf * d_cpitch + d_coff + c, s);
+  }
+  if (colsum_partial) {
+    sm_up[threadIdx.x] = csum;
+    __syncthreads();
+    if (threadIdx.x < c4n) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = threadIdx.x; k < blockDim.x; k += c4n) { const float4 v = sm_up[k]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+      reinterpret_cast<float4*>(colsum_partial + (long long)blockIdx.x * C)[threadIdx.x] = t;
+    }
+  }
+}
+constexpr int kFusedColsumBlock = 240;    // multiple of 48 (pool channels), 24 and 12 (upsample channel quads)
+constexpr int kFusedColsumGrid = 592;
+
+// column sums of a dense NCHW tensor: partial[n][c] = sum over h, w (the bias gradient of the last conv is the sum of
+// d(loss)/d(output) itself); grid = (C, N)
+__global__ void nchw_colsum_kernel(const float* __restrict__ x, int C, int HW, float* __restrict__ partial) {
+  __shared__ float sm[32];
+  const float* row = x + ((long long)blockIdx.y * C + blockIdx.x) * HW;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) acc += __ldg(row + i);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+    partial[(long long)blockIdx.y * C + blockIdx.x] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------- weights
@@ -255,19 +324,27 @@ __global__ void colsum_flat_kernel(const float4* __restrict__ hi, const float4* 
 static inline void colsum_launch(const float* hi, const float* lo, long long rows, int cpitch, int coff, int C, float* partial, float* out,
                                  cudaStream_t st);
 
-// grid = ceil(C / 32), block = (32, 8): thread (lane, w) sums partials w, w+8, ... of channel blockIdx.x*32 + lane
+// grid = ceil(C / 32), block = (32, 32): thread (lane, w) sums partials w, w+32, ... of channel blockIdx.x*32 + lane
 __global__ void colsum_stage2_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out, int accumulate) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
-  float acc = 0.f;
-  if (c < C) for (int b = threadIdx.y; b < nblk; b += 8) acc += partial[(long long)b * C + c];
-  sm[threadIdx.y][threadIdx.x] = acc;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    int b = threadIdx.y;
+    for (; b + 32 < nblk; b += 64) { a0 += partial[(long long)b * C + c]; a1 += partial[(long long)(b + 32) * C + c]; }
+    if (b < nblk) a0 += partial[(long long)b * C + c];
+  }
+  sm[threadIdx.y][threadIdx.x] = a0 + a1;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
     float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+#pragma unroll
+    for (int w = 0; w < 32; ++w) t += sm[w][threadIdx.x];
     out[c] = accumulate ? out[c] + t : t;
   }
+}
+static inline void colsum_stage2_launch(const float* partial, int nblk, int C, float* out, cudaStream_t st) {
+  colsum_stage2_kernel<<<(C + 31) / 32, dim3(32, 32), 0, st>>>(partial, nblk, C, out, 0);
 }
 
 static inline void colsum_launch(const float* hi, const float* lo, long long rows, int cpitch, int coff, int C, float* partial, float* out,
@@ -279,7 +356,7 @@ static inline void colsum_launch(const float* hi, const float* lo, long long row
   } else {
     colsum_stage1_kernel<<<kColsumBlocks, 256, 8 * C * sizeof(float), st>>>(hi, lo, rows, cpitch, coff, C, partial);
   }
-  colsum_stage2_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, kColsumBlocks, C, out, 0);
+  colsum_stage2_launch(partial, kColsumBlocks, C, out, st);
 }
 
 }  // namespace pw

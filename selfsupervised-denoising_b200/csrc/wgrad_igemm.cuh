@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(1024) wgrad_small_cin_kernel(const float* __re
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long base = tile * kSmallCinTile;
     __syncthreads();
+#pragma unroll 4
     for (int i = tid; i < kSmallCinTile * cout; i += nthr) {
       const int px = i / cout, c = i - px * cout;
       const long long g = base + px;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(1024) wgrad_small_cin_kernel(const float* __re
   const float acc[4] = {a0, a1, a2, a3};
   for (int c = 0; c < cin; ++c) dst[c] = acc[c];
 }
-constexpr int kSmallCinGrid = 296;
+constexpr int kSmallCinGrid = 592;
 static inline bool wgrad_small_cin_ok(int cin, int cout, int ntaps) { return cin <= 4 && ntaps == 9 && cout * ntaps <= 1024; }
 static inline size_t wgrad_small_cin_partial_floats(int cin, int cout) { return (size_t)kSmallCinGrid * 9 * cout * cin; }
 // taps: forward flat-pixel offsets of X relative to dZ (9 of them)
