@@ -60,6 +60,10 @@ class Net {
   size_t ws_bytes = 0; void* ws = nullptr;
   std::vector<PoolOp> pools; std::vector<PoolBwdOp> pool_bwds; std::vector<UpBwdOp> up_bwds;
   int nin;                                         // head width (384 blind, 96 plain)
+  // Weight gradients are off the critical path of the backward pass (nothing downstream reads them before the optimiser):
+  // they run on a second stream, forked after the dZ they consume is ready and joined at the end of backward(), so that
+  // they fill the SMs the small pyramid levels leave idle and hide each other's launch / drain latency.
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool use_side = true;
 
   Net(int n, int cin, int cout, int h, int w, bool blind_, int sms_) : N(n), Cin(cin), Cout(cout), H(h), W(w), blind(blind_), sms(sms_) {
     B = blind ? 4 * N : N;
@@ -68,7 +72,15 @@ class Net {
     gh = make_geom(N, H, W, false);
     build_layers();
     ws_bytes = carve(nullptr, 0);
+    use_side = !(getenv("SSDN_WGRAD_STREAM") && atoi(getenv("SSDN_WGRAD_STREAM")) == 0);
   }
+  ~Net() {
+    if (side) cudaStreamDestroy(side);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+  }
+  Net(const Net&) = delete;
+  Net& operator=(const Net&) = delete;
 
   const Buf* find_buf(const std::string& nm) const {
     auto idx = [&](const char* pre) -> int { return (nm.rfind(pre, 0) == 0 && nm.size() == strlen(pre) + 1) ? nm.back() - '0' : -1; };
@@ -359,23 +371,39 @@ class Net {
 
   int run_wgrad(Layer& l, float* grads, cudaStream_t st) {
     const int nt = l.ksize * l.ksize;
-    if (wgradk::wgrad_small_cin_ok(l.cin, l.cout, nt)) {        // first conv: CUDA-core kernel (see wgrad_igemm.cuh)
-      ConvTaps taps = eng::make_taps(l.ksize, blind, false, l.x->g.P);
-      if (profiler().on) profiler().begin(2, l.wgrad.flops, st);
-      cudaError_t ce = wgradk::wgrad_small_cin_launch(l.dz->v, l.dz->lo, l.dz->cpitch, l.cout, l.x->v, l.x->lo, l.x->cpitch, l.x_coff, l.cin,
-                                                      l.x->g.total(), taps.off, partial, grads + l.w_off, st);
-      if (profiler().on) profiler().end(st);
-      SSDN_CUDA(ce);
-    } else {
-      SSDN_CUDA(wgrad_launch(l.wgrad, st));
-      wgradk::wgrad_reduce_launch(partial, l.wgrad.p.ksplit, nt, l.cout, l.cin, grads + l.w_off, 0, st);
-    }
+    // bias gradient: reduce the column-sum partials its dZ producer left behind (main stream: the next producer reuses them)
     if (l.bias_fused) {
       pw::colsum_stage2_launch(l.bias_partial, l.bias_nblk, l.cout, grads + l.b_off, st);
     } else {
       const long long rows = l.dz->g.total();
       pw::colsum_launch(l.dz->v, l.dz->lo, rows, l.dz->cpitch, 0, l.cout, colpart, grads + l.b_off, st);
     }
+    cudaStream_t ws_ = st;
+    if (use_side && !(profiler().on && getenv("SSDN_CONV_STATS"))) {
+      if (!side) {
+        SSDN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        SSDN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        SSDN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      }
+      SSDN_CUDA(cudaEventRecord(ev_fork, st));          // this layer's dZ (and everything before it) is complete
+      SSDN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      ws_ = side;
+    }
+    if (wgradk::wgrad_small_cin_ok(l.cin, l.cout, nt)) {        // first conv: CUDA-core kernel (see wgrad_igemm.cuh)
+      ConvTaps taps = eng::make_taps(l.ksize, blind, false, l.x->g.P);
+      if (profiler().on) profiler().begin(2, l.wgrad.flops, ws_);
+      cudaError_t ce = wgradk::wgrad_small_cin_launch(l.dz->v, l.dz->lo, l.dz->cpitch, l.cout, l.x->v, l.x->lo, l.x->cpitch, l.x_coff, l.cin,
+                                                      l.x->g.total(), taps.off, partial, grads + l.w_off, ws_);
+      if (profiler().on) profiler().end(ws_);
+      SSDN_CUDA(ce);
+    } else {
+      SSDN_CUDA(wgrad_launch(l.wgrad, ws_));
+      wgradk::wgrad_reduce_launch(partial, l.wgrad.p.ksplit, nt, l.cout, l.cin, grads + l.w_off, 0, ws_);
+    }
+    return 0;
+  }
+  int join_side(cudaStream_t st) {
+    if (side) { SSDN_CUDA(cudaEventRecord(ev_join, side)); SSDN_CUDA(cudaStreamWaitEvent(st, ev_join, 0)); }
     return 0;
   }
   int run_dgrad(Layer& l, cudaStream_t st) { SSDN_CUDA(conv_launch(l.dgrad, st, 1)); return 0; }
@@ -428,6 +456,7 @@ class Net {
     pool_bwd();
     if ((r = both("encode_block_1.2", true))) return r;
     if ((r = both("encode_block_1.0", false))) return r;
+    if ((r = join_side(st))) return r;
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }
