@@ -379,7 +379,7 @@ class Net {
       pw::colsum_launch(l.dz->v, l.dz->lo, rows, l.dz->cpitch, 0, l.cout, colpart, grads + l.b_off, st);
     }
     cudaStream_t ws_ = st;
-    if (use_side && !(profiler().on && getenv("SSDN_CONV_STATS"))) {
+    if (use_side && !profiler().on) {   // per-launch profiling serialises everything on one stream
       if (!side) {
         SSDN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
         SSDN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));

@@ -329,7 +329,7 @@ static inline int wgrad_pick_ksplit(long long k_total, int cout, int cin, int nt
   const int n_kchunks = (int)((k_total + KC - 1) / KC);
   const int n_co_tiles = (cout + 127) / 128, n_ci_blocks = wgrad_n_ci_blocks(cin, ntaps), n_groups = ntaps == 9 ? 3 : ntaps;
   const int others = n_co_tiles * n_ci_blocks * n_groups;
-  int ks = std::max(1, (2 * num_sms + others - 1) / others);
+  int ks = std::max(1, (2 * num_sms) / others);   // at most two units per SM: one unit more would cost a whole extra wave
   ks = std::min(ks, std::max(1, n_kchunks / 4));
   ks = std::max(1, std::min(ks, n_kchunks));
   const int cps = (n_kchunks + ks - 1) / ks;      // no K split may be empty: its accumulator would be undefined
