@@ -44,11 +44,12 @@ int run_conv(void* ws, size_t ws_bytes, const float* x, const float* w, const fl
   SSDN_CUDA(cudaMemsetAsync(flag, 0, 4, st));
   const long long ne = (long long)n * cin * h * wd;
   pw::pack_nchw_kernel<<<pw::grid_for(ne), pw::kBlock, 0, st>>>(x, av, al, n, cin, h, wd, L.g, L.cin_pitch, 0, 0);
-  int nc, kl; conv_chunks(cin, &nc, &kl);
+  const bool wide = conv_is_wide(cin, L.taps.n);
+  int nc, kl; conv_chunks(cin, &nc, &kl, wide);
   const int n_tiles = L.cout_padded / L.N;
   const long long ns = (long long)L.slab_floats / 2;
   pw::weight_prep_kernel<<<pw::grid_for(ns), pw::kBlock, 0, st>>>(w, slab, w_cout, w_cin, L.taps.n, cout, cin, n_tiles, nc,
-                                                                  L.N, dgrad ? 1 : 0);
+                                                                  L.N, dgrad ? 1 : 0, wide ? 32 : 16);
   ConvDst d{};
   d.v = y; d.lo = nullptr; d.cpitch = 0; d.coff = 0; d.g = L.g; d.map = MAP_NCHW;
   d.flags = (bias ? EP_BIAS : 0) | (lrelu_act ? EP_LRELU : 0); d.cvalid = cout; d.nimg = n; d.bias = bias;

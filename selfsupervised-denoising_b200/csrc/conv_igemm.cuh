@@ -35,10 +35,14 @@ struct ConvParams {
   int nbox, box_rows; // every group window is loaded as nbox TMA boxes of box_rows rows (one op for both planes if nbox == 1)
   int a_stages, b_stages;
   int bg;             // weight slabs ((chunk, tap) pairs, in consumption order) per B stage: ONE TMA op loads bg x 2 planes
+  int wide;           // 1x1 convolutions with cin % 32 == 0: chunks of 32 channels (128-byte rows, SWIZZLE_128B, 4 k-steps), one
+                      //    weight slab per B stage; A is not reused by other taps there, so its TMA rate (rows/clk) is what binds
   int row3;           // 1: every B stage holds the 3 taps of one stencil row of one group, tap_rel advancing by tap_step
   int tap_step;       //    (+1 forward, -1 data-gradient): the MMA warp then issues 3 x T x 6 MMAs per barrier wait
   uint32_t a_plane_bytes, b_stage_bytes;   // smem bytes of one A plane of one stage / of one B stage
-  uint32_t epi_off;   // MAP_UP2 only: byte offset of the epilogue staging area (4 warps x 32 pixels x 36 floats) in dynamic smem
+  uint32_t epi_off;   // staged epilogue: byte offset of the staging area (4 warps x 32 pixels x 36 floats) in dynamic smem
+  int epi_staged;     // 1: slices are transposed through shared memory so that 8 lanes write one pixel's 128 contiguous bytes
+                      //    (store-bound epilogues: upsampling, 1x1 and few-channel convolutions); 0: straight from registers
   ConvDst dst;
   int* error_flag;
   int debug;          // experiments only: 2 = skip MMA issue
@@ -64,7 +68,7 @@ struct Ring {
 };
 
 constexpr int kStagePitch = 36;   // floats per staged pixel row (32 channels + 4 pad: conflict-free float4 access)
-constexpr int kMaxSlices = 5;     // 32-channel slices of one N tile (N <= 144 + padding)
+constexpr int kMaxSlices = 6;     // 32-channel slices of one N tile (N <= 192)
 
 // What the epilogue needs to know about one lane's pixel of one 128-pixel tile.  Computed one tile ahead so that the
 // LeakyReLU sign-mask words (the only global LOADS of the epilogue) are in flight while the previous tile is written.
@@ -165,7 +169,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------ A producer (warp-uniform loop, elected issue)
     Ring ra(p.a_stages);
-    const uint32_t box_bytes = p.box_rows * 64;
+    const int cw_ch = p.wide ? 32 : 16;                       // channels per chunk
+    const uint32_t box_bytes = p.box_rows * cw_ch * 4;
     long long w_empty = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int um = u / p.n_tiles_n;
@@ -178,11 +183,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (umma::elect_one()) {
             umma::mbar_expect_tx(full_a(ra.stage), 2 * p.nbox * box_bytes);
             if (p.nbox == 1) {      // one op brings both planes: box (16 ch, rows, 2 planes)
-              umma::tma_load_3d(dst, &map_a, full_a(ra.stage), ch * 16, row, 0);
+              umma::tma_load_3d(dst, &map_a, full_a(ra.stage), ch * cw_ch, row, 0);
             } else {
               for (int bx = 0; bx < p.nbox; ++bx) {
-                umma::tma_load_3d(dst + bx * box_bytes, &map_a, full_a(ra.stage), ch * 16, row + bx * p.box_rows, 0);
-                umma::tma_load_3d(dst + p.a_plane_bytes + bx * box_bytes, &map_a, full_a(ra.stage), ch * 16, row + bx * p.box_rows, 1);
+                umma::tma_load_3d(dst + bx * box_bytes, &map_a, full_a(ra.stage), ch * cw_ch, row + bx * p.box_rows, 0);
+                umma::tma_load_3d(dst + p.a_plane_bytes + bx * box_bytes, &map_a, full_a(ra.stage), ch * cw_ch, row + bx * p.box_rows, 1);
               }
             }
           }
@@ -218,7 +223,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     int it = 0;
     long long w_tmem = 0, w_a = 0, w_b = 0;
     const long long t_start = clock64();
-    if (p.row3) {
+    if (p.wide) {
+      // 1x1 convolutions: per 32-channel chunk one A stage and one B stage, T tiles x (4 k-steps x 3 products) MMAs
+      constexpr uint64_t wdesc = umma::make_desc_base(16, 1024, umma::LAYOUT_SW128);
+      const uint32_t desc_hi = (uint32_t)(wdesc >> 32);
+      const uint32_t lbo_bits = (uint32_t)(wdesc & 0xffff0000u);
+      const uint32_t a_pl = p.a_plane_bytes >> 4, b_pl = (uint32_t)(p.N * 128) >> 4;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+        const int buf = it & 1;
+        SSDN_TIMED(w_tmem, umma::mbar_wait(tmem_empty(buf), ((it >> 1) & 1) ^ 1, abort_addr, p.error_flag, 3));
+        umma::tc_fence_after();
+        const uint32_t d0 = tmem + buf * T * p.N;
+        uint32_t first = 0;
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          SSDN_TIMED(w_a, umma::mbar_wait(full_a(ra.stage), ra.phase, abort_addr, p.error_flag, 3));
+          SSDN_TIMED(w_b, umma::mbar_wait(full_b(rb.stage), rb.phase, abort_addr, p.error_flag, 3));
+          umma::tc_fence_after();
+          const uint32_t a0 = (((a_base + ra.stage * a_stage_bytes) >> 4) & 0x3fffu) | lbo_bits;
+          const uint32_t b0 = (((b_base + rb.stage * b_stage_bytes) >> 4) & 0x3fffu) | lbo_bits;
+          if (umma::elect_one()) {
+#pragma unroll
+            for (int tile = 0; tile < T; ++tile) {
+              const uint32_t d = d0 + tile * p.N;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t av = a0 + tile * 1024 + 2 * k, al = av + a_pl, bv = b0 + 2 * k, bl = bv + b_pl;
+                umma::mma_tf32_lo(d, al, bv, desc_hi, idesc, k == 0 ? first : 1u);
+                umma::mma_tf32_lo(d, av, bl, desc_hi, idesc, 1);
+                umma::mma_tf32_lo(d, av, bv, desc_hi, idesc, 1);
+              }
+            }
+            umma::mma_commit(empty_b(rb.stage));
+            umma::mma_commit(empty_a(ra.stage));
+          }
+          __syncwarp();
+          first = 1;
+          rb.advance(); ra.advance();
+        }
+        if (umma::elect_one()) umma::mma_commit(tmem_full(buf));
+        __syncwarp();
+      }
+    } else if (p.row3) {
       // 3x3 stencils: one barrier wait and one block of 3 taps x T tiles x (2 k-steps x 3 products) MMAs per B stage.
       // Descriptors are base + multiples of uniform strides in 16-byte units, so the elected thread has almost nothing
       // to do between two tcgen05.mma: the tensor core's short queue never drains (profiles/r01_role_waits.log).
@@ -442,10 +487,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (i < cw && cg0 + i < d.cvalid)
                       d.v[(((long long)cur.b * d.cvalid + cg0 + i) * sg.H + cur.y) * sg.W + cur.x] = f[i];
                 }
-              } else if (d.map == MAP_UP2) {
-                // 4 destinations per pixel: transposing the slice through shared memory lets 8 consecutive lanes write one
-                // pixel's 128 contiguous bytes (4 full lines per store instruction instead of 32 line fragments) - with four
-                // times the store volume the load/store unit, not the tensor core's operand traffic, is what would bind
+              } else if (p.epi_staged) {
+                // Store-bound epilogues (4 destinations per pixel when upsampling; little MMA work per output for 1x1 and
+                // few-channel convolutions): transposing the slice through shared memory lets 8 consecutive lanes write one
+                // pixel's 128 contiguous bytes - 4 full lines per store instruction instead of 32 line fragments, which is
+                // what the load/store unit can sustain.
                 float* stage = reinterpret_cast<float*>(smem + p.epi_off) + ew * 32 * kStagePitch;
                 float* row = stage + lane * kStagePitch;
 #pragma unroll
@@ -456,12 +502,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 for (int q = 0; q < 32; q += PPI) {
                   const int px = q + sub;
                   const int pd0 = __shfl_sync(0xffffffffu, cur.d0, px), pnd = __shfl_sync(0xffffffffu, cur.nd, px);
+                  const int pcs = __shfl_sync(0xffffffffu, cur.cshift, px);
                   if (chan_ok) {
                     const float4 o = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 4 * q4);
                     float4 h = o, l = o;
                     if (d.flags & EP_WRITE_LO) { tf32_split(o.x, h.x, l.x); tf32_split(o.y, h.y, l.y); tf32_split(o.z, h.z, l.z); tf32_split(o.w, h.w, l.w); }
                     for (int k = 0; k < pnd; ++k) {
-                      const long long oi = (long long)(pd0 + (k & 1) + (k >> 1) * d.g.P) * d.cpitch + d.coff + cg0 + 4 * q4;
+                      const long long oi = (long long)(pd0 + (k & 1) + (k >> 1) * d.g.P) * d.cpitch + d.coff + pcs + cg0 + 4 * q4;
                       *reinterpret_cast<float4*>(d.v + oi) = h;
                       if (d.flags & EP_WRITE_LO) *reinterpret_cast<float4*>(d.lo + oi) = l;
                     }
@@ -525,8 +572,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
 struct ConvTaps { int n; int off[9]; };   // flat-pixel offsets of the taps, in weight-slab order
 
-// Number of 16-channel chunks and k-steps of the last chunk for `cin` input channels.
-static inline void conv_chunks(int cin, int* n_chunks, int* ksteps_last) {
+// 1x1 convolutions whose input channels come in whole 32-channel groups use the wide chunk (see ConvParams::wide).
+static inline bool conv_is_wide(int cin, int ntaps) { return ntaps == 1 && cin % 32 == 0; }
+// Number of channel chunks (16 wide, or 32 in wide mode) and k-steps of the last chunk for `cin` input channels.
+static inline void conv_chunks(int cin, int* n_chunks, int* ksteps_last, bool wide = false) {
+  if (wide) { *n_chunks = cin / 32; *ksteps_last = 4; return; }
   *n_chunks = (cin + 15) / 16;
   const int rem = cin - (*n_chunks - 1) * 16;
   *ksteps_last = rem > 8 ? 2 : 1;
@@ -544,7 +594,9 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
   p.src = src; p.N = N; p.dst = dst; p.error_flag = error_flag;
   p.debug = getenv("SSDN_CONV_DEBUG") ? atoi(getenv("SSDN_CONV_DEBUG")) : 0;
   p.n_tiles_n = cout_padded / N;
-  conv_chunks(cin, &p.n_chunks, &p.ksteps_last);
+  p.wide = conv_is_wide(cin, taps.n) ? 1 : 0;
+  conv_chunks(cin, &p.n_chunks, &p.ksteps_last, p.wide);
+  const int cw_ch = p.wide ? 32 : 16;
   p.ntaps_total = taps.n;
   p.T = (2 * 2 * N <= 512) ? 2 : 1;
   const long long total = src.total();
@@ -558,8 +610,16 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
   // B stage = bg consecutive weight slabs (both planes) loaded by ONE TMA op: a TMA instruction costs ~450 clk of the
   // SM's TMA unit whatever its size (profiles/r01_tma_rate.log), so operands must arrive in few, large boxes.
   const int n_slabs = p.n_chunks * taps.n;
-  p.bg = (taps.n % 3 == 0) ? 3 : (n_slabs % 3 == 0 ? 3 : (n_slabs % 2 == 0 ? 2 : 1));
-  p.b_stage_bytes = (uint32_t)(p.bg * 2 * N * 64);
+  p.bg = p.wide ? 1 : ((taps.n % 3 == 0) ? 3 : (n_slabs % 3 == 0 ? 3 : (n_slabs % 2 == 0 ? 2 : 1)));
+  p.b_stage_bytes = (uint32_t)(p.bg * 2 * N * cw_ch * 4);
+  // epilogue mode: straight-from-register stores cost the load/store unit ~2800 clk per 32-channel slice of a tile
+  // (32 line fragments per instruction); stage through shared memory when the tile's MMA time cannot hide that
+  {
+    const double mma_clk = (double)n_slabs * (p.wide ? 12 : 6) * std::max(N / 2.0, (4096.0 + 32.0 * N) / 128.0);
+    const double direct_clk = 2800.0 * ((N + 31) / 32);
+    p.epi_staged = (dst.map != MAP_NCHW) && (dst.map == MAP_UP2 || mma_clk < 1.5 * direct_clk);
+    if (const char* e = getenv("SSDN_EPI_STAGED")) { const int v = atoi(e); if (v == 0) p.epi_staged = (dst.map == MAP_UP2); if (v == 1) p.epi_staged = (dst.map != MAP_NCHW); }
+  }
   // choose the tap grouping: all taps in one window if it fits in shared memory, else one window per
   // distinct row offset (dy), else one window per tap.
   const int rows_unit = 128 * p.T;
@@ -578,10 +638,10 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     int nbox = (max_rows + 255) / 256;
     int box_rows = ((max_rows + nbox - 1) / nbox + 15) / 16 * 16;      // multiple of 16 rows => planes/boxes stay 1024-byte aligned
     if (box_rows > 256) { ++nbox; box_rows = ((max_rows + nbox - 1) / nbox + 15) / 16 * 16; }
-    uint32_t plane = (uint32_t)(nbox * box_rows * 64);
-    int stages = (mode == 0) ? 2 : 3;
+    uint32_t plane = (uint32_t)(nbox * box_rows * cw_ch * 4);
+    for (int stages = (mode == 0 && !p.wide) ? 2 : 3; stages >= 2; --stages)
     for (int bst = 4; bst >= 2; --bst) {
-      const size_t epi = dst.map == MAP_UP2 ? 4 * 32 * convk::kStagePitch * sizeof(float) : 0;
+      const size_t epi = p.epi_staged ? 4 * 32 * convk::kStagePitch * sizeof(float) : 0;
       size_t need = (size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes + epi + 2048;
       if (need > smem_limit) continue;
       p.epi_off = (uint32_t)((size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes);
@@ -624,21 +684,23 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
   if (plane_stride <= 0 || plane_stride % 16) return -11;
   uint64_t adims[3] = {(uint64_t)cin, (uint64_t)total, 2};
   uint64_t astr[2] = {(uint64_t)a_cpitch * 4, (uint64_t)plane_stride};
-  uint32_t abox[3] = {16, (uint32_t)p.box_rows, (uint32_t)(p.nbox == 1 ? 2 : 1)};
+  uint32_t abox[3] = {(uint32_t)cw_ch, (uint32_t)p.box_rows, (uint32_t)(p.nbox == 1 ? 2 : 1)};
+  const CUtensorMapSwizzle swz = p.wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   int r;
-  if ((r = umma::encode_f32(&plan->a, (void*)(a_v + a_coff), 3, adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+  if ((r = umma::encode_f32(&plan->a, (void*)(a_v + a_coff), 3, adims, astr, abox, swz))) return r;
   // B: slabs [n_tile][chunk][tap][plane][N][16] -> 3-D (16, N, slab x plane), box = bg slabs x 2 planes
-  uint64_t bdims[3] = {16, (uint64_t)N, (uint64_t)p.n_tiles_n * n_slabs * 2};
-  uint64_t bstr[2] = {64, (uint64_t)N * 64};
-  uint32_t bbox[3] = {16, (uint32_t)N, (uint32_t)(2 * p.bg)};
-  if ((r = umma::encode_f32(&plan->b, (void*)w_slab, 3, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+  uint64_t bdims[3] = {(uint64_t)cw_ch, (uint64_t)N, (uint64_t)p.n_tiles_n * n_slabs * 2};
+  uint64_t bstr[2] = {(uint64_t)cw_ch * 4, (uint64_t)N * cw_ch * 4};
+  uint32_t bbox[3] = {(uint32_t)cw_ch, (uint32_t)N, (uint32_t)(2 * p.bg)};
+  if ((r = umma::encode_f32(&plan->b, (void*)w_slab, 3, bdims, bstr, bbox, swz))) return r;
   return 0;
 }
 
 // floats of the combined (hi + lo) weight slab
 static inline size_t conv_weight_slab_floats(int cin, int cout_padded, int ntaps) {
-  int nc, kl; conv_chunks(cin, &nc, &kl);
-  return (size_t)cout_padded * nc * ntaps * 16 * 2;
+  const bool wide = conv_is_wide(cin, ntaps);
+  int nc, kl; conv_chunks(cin, &nc, &kl, wide);
+  return (size_t)cout_padded * nc * ntaps * (wide ? 32 : 16) * 2;
 }
 
 // Optional per-launch timing (bench.py roofline): when enabled every GEMM launch is bracketed by CUDA events.

@@ -149,13 +149,14 @@ class Net {
     for (auto& l : layers) {
       const int nt = l.ksize * l.ksize;
       l.coutp_f = round_up(l.cout, 16);
-      l.n_f = (l.cout == 384) ? 96 : eng::pick_n(l.coutp_f);
+      l.n_f = (l.cout == 384) ? (l.ksize == 1 ? 192 : 96) : eng::pick_n(l.coutp_f);   // 1x1: N = 192 halves the re-reads of A
       size_t f = conv_weight_slab_floats(l.cin, l.coutp_f, nt);
       l.slab_f = a.take<float>(f);
       l.has_dgrad = (l.name != "encode_block_1.0");
       l.dgrad_nvalid = (l.name == "decode_block_1.0") ? 96 : l.cin;       // d(x) part of the last concat is never used
       l.cinp_d = round_up(l.dgrad_nvalid, 16);
-      l.n_d = (l.cinp_d == 384) ? 96 : eng::pick_n(l.cinp_d);
+      // data-gradient N tiles: the un-rotating head conv needs one tile per rotation branch (96 channels)
+      l.n_d = (l.cinp_d == 384) ? ((l.name == "output_block.0" || l.ksize != 1) ? 96 : 192) : eng::pick_n(l.cinp_d);
       if (l.cinp_d == 144) l.n_d = 144;   // one N=144 tile (T = 1) instead of three smem-bound N=48 tiles
       size_t fd = conv_weight_slab_floats(l.cout, l.cinp_d, nt);
       l.slab_d = a.take<float>(fd);
@@ -321,11 +322,13 @@ class Net {
     int nj = 0;
     for (auto& l : layers) {
       const int nt = l.ksize * l.ksize;
-      int nc, kl; conv_chunks(l.cin, &nc, &kl);
-      jobs.j[nj++] = {params + l.w_off, l.slab_f, l.cout, l.cin, nt, l.cout, l.cin, l.coutp_f / l.n_f, nc, l.n_f, 0};
+      bool wide = conv_is_wide(l.cin, nt);
+      int nc, kl; conv_chunks(l.cin, &nc, &kl, wide);
+      jobs.j[nj++] = {params + l.w_off, l.slab_f, l.cout, l.cin, nt, l.cout, l.cin, l.coutp_f / l.n_f, nc, l.n_f, 0, wide ? 32 : 16};
       if (with_dgrad && l.has_dgrad) {
-        conv_chunks(l.cout, &nc, &kl);
-        jobs.j[nj++] = {params + l.w_off, l.slab_d, l.cout, l.cin, nt, l.dgrad_nvalid, l.cout, l.cinp_d / l.n_d, nc, l.n_d, 1};
+        wide = conv_is_wide(l.cout, nt);
+        conv_chunks(l.cout, &nc, &kl, wide);
+        jobs.j[nj++] = {params + l.w_off, l.slab_d, l.cout, l.cin, nt, l.dgrad_nvalid, l.cout, l.cinp_d / l.n_d, nc, l.n_d, 1, wide ? 32 : 16};
       }
     }
     pw::weight_prep_batched_kernel<<<dim3(64, nj), pw::kBlock, 0, st>>>(jobs);

@@ -228,44 +228,45 @@ __global__ void nchw_colsum_kernel(const float* __restrict__ x, int C, int HW, f
 // PyTorch-layout weights W[cout][cin][taps].  transpose == 0 (forward):  slab[n][k] = W[n][k][tap]
 //                                           transpose == 1 (data-grad): slab[n][k] = W[k][n][tap]   (n = cin, k = cout)
 __global__ void weight_prep_kernel(const float* __restrict__ w, float* __restrict__ slab, int cout, int cin, int ntaps,
-                                   int n_valid, int k_valid, int n_tiles, int n_chunks, int N, int transpose) {
-  const long long total = (long long)n_tiles * n_chunks * ntaps * N * 16;
+                                   int n_valid, int k_valid, int n_tiles, int n_chunks, int N, int transpose, int CW) {
+  const long long total = (long long)n_tiles * n_chunks * ntaps * N * CW;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int kk = (int)(idx % 16); long long t = idx / 16;
+  const int kk = (int)(idx % CW); long long t = idx / CW;
   const int n = (int)(t % N); t /= N;                       // t = slab index ((nt * n_chunks + ch) * ntaps + tap)
   const int tap = (int)(t % ntaps); const long long tc = t / ntaps;
   const int ch = (int)(tc % n_chunks); const int nt = (int)(tc / n_chunks);
-  const int ng = nt * N + n, k = ch * 16 + kk;
+  const int ng = nt * N + n, k = ch * CW + kk;
   float val = 0.f;
   if (ng < n_valid && k < k_valid) {
     const long long wi = transpose ? ((long long)k * cin + ng) * ntaps + tap : ((long long)ng * cin + k) * ntaps + tap;
     val = __ldg(w + wi);
   }
-  const long long o = ((t * 2) * N + n) * 16 + kk;
-  tf32_split(val, slab[o], slab[o + (long long)N * 16]);
+  const long long o = ((t * 2) * N + n) * CW + kk;
+  tf32_split(val, slab[o], slab[o + (long long)N * CW]);
 }
 
 // All weight slabs of a network in ONE launch: blockIdx.y selects the job, blockIdx.x strides over its elements.
-struct WeightPrepJob { const float* w; float* slab; int cout, cin, ntaps, n_valid, k_valid, n_tiles, n_chunks, N, transpose; };
+struct WeightPrepJob { const float* w; float* slab; int cout, cin, ntaps, n_valid, k_valid, n_tiles, n_chunks, N, transpose, CW; };
 constexpr int kMaxPrepJobs = 48;
 struct WeightPrepJobs { WeightPrepJob j[kMaxPrepJobs]; };
 __global__ void weight_prep_batched_kernel(const __grid_constant__ WeightPrepJobs jobs) {
   const WeightPrepJob& q = jobs.j[blockIdx.y];
-  const long long total = (long long)q.n_tiles * q.n_chunks * q.ntaps * q.N * 16;
+  const int CW = q.CW;
+  const long long total = (long long)q.n_tiles * q.n_chunks * q.ntaps * q.N * CW;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int kk = (int)(idx % 16); long long t = idx / 16;
+    const int kk = (int)(idx % CW); long long t = idx / CW;
     const int n = (int)(t % q.N); t /= q.N;
     const int tap = (int)(t % q.ntaps); const long long tc = t / q.ntaps;
     const int ch = (int)(tc % q.n_chunks); const int nt = (int)(tc / q.n_chunks);
-    const int ng = nt * q.N + n, k = ch * 16 + kk;
+    const int ng = nt * q.N + n, k = ch * CW + kk;
     float val = 0.f;
     if (ng < q.n_valid && k < q.k_valid) {
       const long long wi = q.transpose ? ((long long)k * q.cin + ng) * q.ntaps + tap : ((long long)ng * q.cin + k) * q.ntaps + tap;
       val = __ldg(q.w + wi);
     }
-    const long long o = ((t * 2) * q.N + n) * 16 + kk;
-    tf32_split(val, q.slab[o], q.slab[o + (long long)q.N * 16]);
+    const long long o = ((t * 2) * q.N + n) * CW + kk;
+    tf32_split(val, q.slab[o], q.slab[o + (long long)q.N * CW]);
   }
 }
 
