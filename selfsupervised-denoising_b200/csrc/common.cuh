@@ -80,5 +80,5 @@ struct ConvDst {
   uint32_t* mask_out; int mask_out_words;        // EP_LRELU: sign bits of the written activation, [destination pixel][words]
   const uint32_t* mask_in; int mask_in_words;    // EP_ACT_GRAD: sign bits of the forward activation, [pixel][words]
   float* colsum; int colsum_pitch;               // optional: per-(CTA, epilogue warp) column sums of the written values
-                                                 // [gridDim.x * 4][colsum_pitch] (bias gradient of the consuming layer)
+                                                 // [gridDim.x * 8][colsum_pitch] (bias gradient of the consuming layer)
 };

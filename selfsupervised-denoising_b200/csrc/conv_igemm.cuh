@@ -41,6 +41,9 @@ struct ConvParams {
   int tap_step;       //    (+1 forward, -1 data-gradient): the MMA warp then issues 3 x T x 6 MMAs per barrier wait
   uint32_t a_plane_bytes, b_stage_bytes;   // smem bytes of one A plane of one stage / of one B stage
   uint32_t epi_off;   // staged epilogue: byte offset of the staging area (4 warps x 32 pixels x 36 floats) in dynamic smem
+  int epi_split;      // 1: both epilogue warps of a TMEM lane quadrant work (alternate slices) - epilogue-bound layers; 0: one warp
+                      //    per quadrant, the other four exit at once (they would only take issue slots and shared-memory
+                      //    bandwidth from an MMA-bound layer)
   int epi_staged;     // 1: slices are transposed through shared memory so that 8 lanes write one pixel's 128 contiguous bytes
                       //    (store-bound epilogues: upsampling, 1x1 and few-channel convolutions); 0: straight from registers
   ConvDst dst;
@@ -58,7 +61,8 @@ struct ConvPlan {
 
 namespace convk {
 
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;      // two epilogue warps per TMEM lane quadrant: they take alternate 32-channel slices of a tile
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 
 struct Ring {
@@ -152,7 +156,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     abort_word = 0;
     for (int s = 0; s < p.a_stages; ++s) { umma::mbar_init(full_a(s), 1); umma::mbar_init(empty_a(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { umma::mbar_init(full_b(s), 1); umma::mbar_init(empty_b(s), 1); }
-    for (int b = 0; b < 2; ++b) { umma::mbar_init(tmem_full(b), 1); umma::mbar_init(tmem_empty(b), 128); }
+    for (int b = 0; b < 2; ++b) { umma::mbar_init(tmem_full(b), 1); umma::mbar_init(tmem_empty(b), p.epi_split ? 32 * kEpiWarps : 128); }
     umma::fence_mbar_init();
   }
   if (warp == 3) {
@@ -373,7 +377,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       unsigned long long* s = p.stats + blockIdx.x * 16;
       s[2] = w_tmem; s[3] = w_a; s[4] = w_b; s[5] = clock64() - t_start;
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (p.epi_split || warp < 8)) {
     // ------------------------------------------------------------ epilogue
     // TMEM -> registers (one pixel per lane, 32 channels per slice) -> bias / LeakyReLU (+ sign-mask word out) or
     // LeakyReLU' from the sign-mask word -> optional column sums -> hi/lo split -> global memory straight from registers:
@@ -382,11 +386,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // bandwidth for its operands (profiles/r01_role_waits.log), and L2 merges the 16-byte pieces into full lines.
     const ConvDst& d = p.dst;
     const Geom& sg = p.src;
-    const int ew = warp - 4;
+    const int ew = (warp - 4) & 3;        // TMEM lane quadrant (a warp may only read lanes 32 * (warp % 4) ...)
+    const int half = (warp - 4) >> 2;     // which of the quadrant's two warps: slices with s % 2 == half are its own
+    const int n_epi_warps = p.epi_split ? kEpiWarps : 4;
     __shared__ __align__(16) float s_bias[400];
     if (d.flags & EP_BIAS)
-      for (int i = threadIdx.x - 128; i < 400; i += 128) s_bias[i] = i < d.cvalid ? __ldg(d.bias + i) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 128; i < 400; i += 32 * n_epi_warps) s_bias[i] = i < d.cvalid ? __ldg(d.bias + i) : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * n_epi_warps) : "memory");
     float csum[kMaxSlices];
 #pragma unroll
     for (int s = 0; s < kMaxSlices; ++s) csum[s] = 0.f;
@@ -411,7 +417,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
         for (int s = 0; s < kMaxSlices; ++s) {
           const int c0 = 32 * s;
-          if (c0 < p.N) {
+          if (c0 < p.N && (!p.epi_split || (s & 1) == half)) {
             const int cw = min(32, p.N - c0);                              // 32 or 16 channels in this slice
             const int cg0 = (d.map == MAP_UNROT_INV ? 0 : nt * p.N) + c0;  // first channel of the slice among this conv's outputs
             uint32_t r[32];
@@ -492,7 +498,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 // few-channel convolutions): transposing the slice through shared memory lets 8 consecutive lanes write one
                 // pixel's 128 contiguous bytes - 4 full lines per store instruction instead of 32 line fragments, which is
                 // what the load/store unit can sustain.
-                float* stage = reinterpret_cast<float*>(smem + p.epi_off) + ew * 32 * kStagePitch;
+                float* stage = reinterpret_cast<float*>(smem + p.epi_off) + (warp - 4) * 32 * kStagePitch;
                 float* row = stage + lane * kStagePitch;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(row + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
@@ -548,13 +554,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // this CTA only ever sees one N tile when gridDim.x is a multiple of n_tiles_n (the host guarantees it)
       const int nt = blockIdx.x % p.n_tiles_n;
       const int c_first = (d.map == MAP_UNROT_INV) ? 0 : nt * p.N;
-      float* row = d.colsum + (long long)(blockIdx.x * 4 + ew) * d.colsum_pitch;
+      float* row = d.colsum + (long long)(blockIdx.x * n_epi_warps + (warp - 4)) * d.colsum_pitch;
       for (int c = lane; c < d.colsum_pitch; c += 32) row[c] = 0.f;
       __syncwarp();
       // lane -> channel of the transpose-reduce: bit k of the lane selected the upper half at step k, i.e. channel == lane
 #pragma unroll
       for (int s = 0; s < kMaxSlices; ++s)
-        if (32 * s < p.N && c_first + 32 * s + lane < d.colsum_pitch && (blockIdx.x < n_units)) row[c_first + 32 * s + lane] = csum[s];
+        if (32 * s < p.N && (!p.epi_split || (s & 1) == half) && c_first + 32 * s + lane < d.colsum_pitch && (blockIdx.x < n_units)) row[c_first + 32 * s + lane] = csum[s];
     }
     if (p.stats && threadIdx.x == 128) { p.stats[blockIdx.x * 16 + 6] = w_full; p.stats[blockIdx.x * 16 + 7] = clock64() - t_start; }
   }
@@ -617,7 +623,11 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
   {
     const double mma_clk = (double)n_slabs * (p.wide ? 12 : 6) * std::max(N / 2.0, (4096.0 + 32.0 * N) / 128.0);
     const double direct_clk = 2800.0 * ((N + 31) / 32);
-    p.epi_staged = (dst.map != MAP_NCHW) && (dst.map == MAP_UP2 || mma_clk < 1.5 * direct_clk);
+    p.epi_staged = (dst.map != MAP_NCHW);   // measured: staging is never slower, even where the MMA time would hide direct stores
+    (void)direct_clk;
+    // one epilogue warp per quadrant needs ~4500 clk per slice of a tile: use both warps where the MMAs cannot hide that
+    p.epi_split = (dst.map != MAP_NCHW || N > 32) && mma_clk < 0.75 * 4500.0 * ((N + 31) / 32);
+    if (const char* e = getenv("SSDN_EPI_SPLIT")) p.epi_split = atoi(e) != 0;
     if (const char* e = getenv("SSDN_EPI_STAGED")) { const int v = atoi(e); if (v == 0) p.epi_staged = (dst.map == MAP_UP2); if (v == 1) p.epi_staged = (dst.map != MAP_NCHW); }
   }
   // choose the tap grouping: all taps in one window if it fits in shared memory, else one window per
@@ -641,7 +651,7 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     uint32_t plane = (uint32_t)(nbox * box_rows * cw_ch * 4);
     for (int stages = (mode == 0 && !p.wide) ? 2 : 3; stages >= 2; --stages)
     for (int bst = 4; bst >= 2; --bst) {
-      const size_t epi = p.epi_staged ? 4 * 32 * convk::kStagePitch * sizeof(float) : 0;
+      const size_t epi = p.epi_staged ? convk::kEpiWarps * 32 * convk::kStagePitch * sizeof(float) : 0;
       size_t need = (size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes + epi + 2048;
       if (need > smem_limit) continue;
       p.epi_off = (uint32_t)((size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes);

@@ -172,7 +172,7 @@ class Net {
     }
     partial = a.take<float>(partial_floats);
     colpart = a.take<float>((size_t)1024 * 384);
-    colpart2 = a.take<float>((size_t)1024 * 384);
+    colpart2 = a.take<float>((size_t)148 * convk::kEpiWarps * 384 + 4096);
     colpart3 = a.take<float>((size_t)1024 * 96);
     flag = a.take<int>(64);
     return a.off;
@@ -223,7 +223,7 @@ class Net {
     const int gact = EP_ACT_GRAD | EP_WRITE_LO;
     // every dst_act below also yields the bias gradient of the layer that owns the produced dZ (fused column sums)
     auto fused = [&](const char* producer, const char* owner) {
-      Layer& o = L(owner); o.bias_fused = true; o.bias_nblk = L(producer).dgrad.grid * 4; o.bias_partial = colpart2;
+      Layer& o = L(owner); o.bias_fused = true; o.bias_nblk = L(producer).dgrad.grid * (L(producer).dgrad.p.epi_split ? convk::kEpiWarps : 4); o.bias_partial = colpart2;
     };
     auto fused_pw = [&](const std::string& owner, int nblk) { Layer& o = L(owner); o.bias_fused = true; o.bias_nblk = nblk; o.bias_partial = colpart3; };
     fused_pw("output_conv", N);                                              // nchw_colsum_kernel over d(loss)/d(out)
