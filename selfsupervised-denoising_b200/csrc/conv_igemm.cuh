@@ -29,6 +29,8 @@ struct ConvParams {
   Geom src;           // geometry of A == geometry in which output pixels are enumerated
   int T, N;           // tiles per unit, MMA N
   int n_units_m, n_tiles_n;
+  int pair;           // 1: CTA pairs (cta_group::2, M = 256); n_pairs = ceil(n_units_m / 2) * n_tiles_n pair-units
+  int n_pairs;
   int n_chunks, ksteps_last;
   int n_groups, ntaps_total;
   TapGroup groups[9];
@@ -128,7 +130,7 @@ __device__ __forceinline__ void lane_pixel(const ConvParams& p, int um, int nt, 
   }
 }
 
-template <int T>
+template <int T, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ ConvParams p) {
@@ -150,23 +152,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t abort_addr = umma::smem_u32(&abort_word);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_units = p.n_units_m * p.n_tiles_n;
+  // Work decomposition.  Single CTA: unit u = (M unit u / n_tiles_n, N tile u % n_tiles_n), CTAs stride over units.
+  // CTA pair: pair-unit q covers M units 2 * (q / n_tiles_n) + {0, 1} (rank 0 / 1) of N tile q % n_tiles_n, clusters
+  // stride over pair-units; both CTAs of a pair run the same loops in lockstep through the shared barriers.
+  const uint32_t rank = PAIR ? umma::cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int n_units = PAIR ? p.n_pairs : p.n_units_m * p.n_tiles_n;
+  const int u_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, u_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto unit_m = [&](int u) { return PAIR ? 2 * (u / p.n_tiles_n) + (int)rank : u / p.n_tiles_n; };
 
   if (threadIdx.x == 0) {
     abort_word = 0;
-    for (int s = 0; s < p.a_stages; ++s) { umma::mbar_init(full_a(s), 1); umma::mbar_init(empty_a(s), 1); }
-    for (int s = 0; s < p.b_stages; ++s) { umma::mbar_init(full_b(s), 1); umma::mbar_init(empty_b(s), 1); }
-    for (int b = 0; b < 2; ++b) { umma::mbar_init(tmem_full(b), 1); umma::mbar_init(tmem_empty(b), p.epi_split ? 32 * kEpiWarps : 128); }
+    const int nprod = PAIR ? 2 : 1;     // a pair's leader barrier collects one arrival (+ bytes) from each CTA's producer
+    for (int s = 0; s < p.a_stages; ++s) { umma::mbar_init(full_a(s), nprod); umma::mbar_init(empty_a(s), 1); }
+    for (int s = 0; s < p.b_stages; ++s) { umma::mbar_init(full_b(s), nprod); umma::mbar_init(empty_b(s), 1); }
+    for (int b = 0; b < 2; ++b) { umma::mbar_init(tmem_full(b), 1); umma::mbar_init(tmem_empty(b), nprod * (p.epi_split ? 32 * kEpiWarps : 128)); }
     umma::fence_mbar_init();
   }
   if (warp == 3) {
-    umma::tmem_alloc(umma::smem_u32(&tmem_slot), 512);
-    umma::tmem_relinquish();
+    if (PAIR) { umma::tmem_alloc_pair(umma::smem_u32(&tmem_slot), 512); umma::tmem_relinquish_pair(); }
+    else { umma::tmem_alloc(umma::smem_u32(&tmem_slot), 512); umma::tmem_relinquish(); }
   }
   if (warp == 0 && lane == 0) umma::tma_prefetch_desc(&map_a);
   if (warp == 1 && lane == 0) umma::tma_prefetch_desc(&map_b);
   umma::tc_fence_before();
   __syncthreads();
+  if (PAIR) umma::cluster_sync();       // the peer's barriers must be initialised before anything arrives on them
   umma::tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
@@ -176,8 +187,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int cw_ch = p.wide ? 32 : 16;                       // channels per chunk
     const uint32_t box_bytes = p.box_rows * cw_ch * 4;
     long long w_empty = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int um = u / p.n_tiles_n;
+    for (int u = u_first; u < n_units; u += u_stride) {
+      const int um = unit_m(u);
       const int j0 = um * 128 * T;
       for (int ch = 0; ch < p.n_chunks; ++ch)
         for (int g = 0; g < p.n_groups; ++g) {
@@ -185,13 +196,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const uint32_t dst = a_base + ra.stage * a_stage_bytes;
           const int row = j0 + p.groups[g].row_off;
           if (umma::elect_one()) {
-            umma::mbar_expect_tx(full_a(ra.stage), 2 * p.nbox * box_bytes);
-            if (p.nbox == 1) {      // one op brings both planes: box (16 ch, rows, 2 planes)
-              umma::tma_load_3d(dst, &map_a, full_a(ra.stage), ch * cw_ch, row, 0);
+            if (PAIR) {             // own rows into own shared memory, bytes signalled on the leader's barrier
+              const uint32_t lbar = umma::mapa(full_a(ra.stage), 0);
+              umma::mbar_expect_tx_cluster(lbar, 2 * p.nbox * box_bytes);
+              if (p.nbox == 1) {
+                umma::tma_load_3d_pair(dst, &map_a, lbar, ch * cw_ch, row, 0);
+              } else {
+                for (int bx = 0; bx < p.nbox; ++bx) {
+                  umma::tma_load_3d_pair(dst + bx * box_bytes, &map_a, lbar, ch * cw_ch, row + bx * p.box_rows, 0);
+                  umma::tma_load_3d_pair(dst + p.a_plane_bytes + bx * box_bytes, &map_a, lbar, ch * cw_ch, row + bx * p.box_rows, 1);
+                }
+              }
             } else {
-              for (int bx = 0; bx < p.nbox; ++bx) {
-                umma::tma_load_3d(dst + bx * box_bytes, &map_a, full_a(ra.stage), ch * cw_ch, row + bx * p.box_rows, 0);
-                umma::tma_load_3d(dst + p.a_plane_bytes + bx * box_bytes, &map_a, full_a(ra.stage), ch * cw_ch, row + bx * p.box_rows, 1);
+              umma::mbar_expect_tx(full_a(ra.stage), 2 * p.nbox * box_bytes);
+              if (p.nbox == 1) {      // one op brings both planes: box (16 ch, rows, 2 planes)
+                umma::tma_load_3d(dst, &map_a, full_a(ra.stage), ch * cw_ch, row, 0);
+              } else {
+                for (int bx = 0; bx < p.nbox; ++bx) {
+                  umma::tma_load_3d(dst + bx * box_bytes, &map_a, full_a(ra.stage), ch * cw_ch, row + bx * p.box_rows, 0);
+                  umma::tma_load_3d(dst + p.a_plane_bytes + bx * box_bytes, &map_a, full_a(ra.stage), ch * cw_ch, row + bx * p.box_rows, 1);
+                }
               }
             }
           }
@@ -205,25 +229,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     Ring rb(p.b_stages);
     const int n_slabs = p.n_chunks * p.ntaps_total, n_bstages = n_slabs / p.bg;
     long long w_empty = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    for (int u = u_first; u < n_units; u += u_stride) {
       const int nt = u % p.n_tiles_n;
       for (int i = 0; i < n_bstages; ++i) {
         SSDN_TIMED(w_empty, umma::mbar_wait(empty_b(rb.stage), rb.phase ^ 1, abort_addr, p.error_flag, 2));
         if (umma::elect_one()) {
-          umma::mbar_expect_tx(full_b(rb.stage), b_stage_bytes);
-          umma::tma_load_3d(b_base + rb.stage * b_stage_bytes, &map_b, full_b(rb.stage), 0, 0, 2 * (nt * n_slabs + i * p.bg));
+          if (PAIR) {               // this CTA's half of the N rows of every slab (b_stage_bytes is the per-CTA size)
+            const uint32_t lbar = umma::mapa(full_b(rb.stage), 0);
+            umma::mbar_expect_tx_cluster(lbar, b_stage_bytes);
+            umma::tma_load_3d_pair(b_base + rb.stage * b_stage_bytes, &map_b, lbar, 0, (int)rank * (p.N / 2), 2 * (nt * n_slabs + i * p.bg));
+          } else {
+            umma::mbar_expect_tx(full_b(rb.stage), b_stage_bytes);
+            umma::tma_load_3d(b_base + rb.stage * b_stage_bytes, &map_b, full_b(rb.stage), 0, 0, 2 * (nt * n_slabs + i * p.bg));
+          }
         }
         __syncwarp();
         rb.advance();
       }
     }
     if (p.stats && lane == 0) p.stats[blockIdx.x * 16 + 1] = w_empty;
-  } else if (warp == 2) {
+  } else if (warp == 2 && (!PAIR || leader)) {
     // ------------------------------------------------------------ MMA issuer: uniform loops, one elected lane issues a fully
     // unrolled block of T x 2 x 3 MMAs per (chunk, tap) whose descriptors are base + compile-time offsets
     Ring ra(p.a_stages), rb(p.b_stages);
     constexpr uint64_t desc = umma::make_desc_base(16, 512, umma::LAYOUT_SW64);
-    const uint32_t idesc = umma::make_idesc_tf32(128, p.N, 0, 0);
+    const uint32_t idesc = umma::make_idesc_tf32(PAIR ? 256 : 128, p.N, 0, 0);
+    // single CTA: tcgen05.mma.cta_group::1 and a local commit; pair leader: cta_group::2 and a commit multicast to both CTAs
+    auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t acc) {
+      if (PAIR) umma::mma_tf32_lo_pair(d, a_lo, b_lo, hi, idesc, acc); else umma::mma_tf32_lo(d, a_lo, b_lo, hi, idesc, acc);
+    };
+    auto commit = [&](uint32_t bar) { if (PAIR) umma::mma_commit_pair(bar); else umma::mma_commit(bar); };
     int it = 0;
     long long w_tmem = 0, w_a = 0, w_b = 0;
     const long long t_start = clock64();
@@ -233,7 +268,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t desc_hi = (uint32_t)(wdesc >> 32);
       const uint32_t lbo_bits = (uint32_t)(wdesc & 0xffff0000u);
       const uint32_t a_pl = p.a_plane_bytes >> 4, b_pl = (uint32_t)(p.N * 128) >> 4;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+      for (int u = u_first; u < n_units; u += u_stride, ++it) {
         const int buf = it & 1;
         SSDN_TIMED(w_tmem, umma::mbar_wait(tmem_empty(buf), ((it >> 1) & 1) ^ 1, abort_addr, p.error_flag, 3));
         umma::tc_fence_after();
@@ -252,19 +287,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint32_t av = a0 + tile * 1024 + 2 * k, al = av + a_pl, bv = b0 + 2 * k, bl = bv + b_pl;
-                umma::mma_tf32_lo(d, al, bv, desc_hi, idesc, k == 0 ? first : 1u);
-                umma::mma_tf32_lo(d, av, bl, desc_hi, idesc, 1);
-                umma::mma_tf32_lo(d, av, bv, desc_hi, idesc, 1);
+                mma(d, al, bv, desc_hi, k == 0 ? first : 1u);
+                mma(d, av, bl, desc_hi, 1);
+                mma(d, av, bv, desc_hi, 1);
               }
             }
-            umma::mma_commit(empty_b(rb.stage));
-            umma::mma_commit(empty_a(ra.stage));
+            commit(empty_b(rb.stage));
+            commit(empty_a(ra.stage));
           }
           __syncwarp();
           first = 1;
           rb.advance(); ra.advance();
         }
-        if (umma::elect_one()) umma::mma_commit(tmem_full(buf));
+        if (umma::elect_one()) commit(tmem_full(buf));
         __syncwarp();
       }
     } else if (p.row3) {
@@ -273,9 +308,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // to do between two tcgen05.mma: the tensor core's short queue never drains (profiles/r01_role_waits.log).
       const uint32_t desc_hi = (uint32_t)(desc >> 32);
       const uint32_t lbo_bits = (uint32_t)(desc & 0xffff0000u);
-      const uint32_t a_pl = p.a_plane_bytes >> 4, b_pl = (uint32_t)(p.N * 64) >> 4, slab = 2 * b_pl;
+      const uint32_t a_pl = p.a_plane_bytes >> 4, b_pl = (uint32_t)((PAIR ? p.N / 2 : p.N) * 64) >> 4, slab = 2 * b_pl;
       const int step = p.tap_step * 4;                       // one pixel row of the A window = 64 bytes
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+      for (int u = u_first; u < n_units; u += u_stride, ++it) {
         const int buf = it & 1;
         SSDN_TIMED(w_tmem, umma::mbar_wait(tmem_empty(buf), ((it >> 1) & 1) ^ 1, abort_addr, p.error_flag, 3));
         umma::tc_fence_after();
@@ -300,32 +335,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                   for (int tile = 0; tile < T; ++tile) {
                     const uint32_t d = d0 + tile * p.N;
                     const uint32_t av = aj + tile * 512, al = av + a_pl, bv = bj, bl = bj + b_pl;
-                    umma::mma_tf32_lo(d, al, bv, desc_hi, idesc, (j == 0) ? first : 1u);
-                    umma::mma_tf32_lo(d, av, bl, desc_hi, idesc, 1);
-                    umma::mma_tf32_lo(d, av, bv, desc_hi, idesc, 1);
+                    mma(d, al, bv, desc_hi, (j == 0) ? first : 1u);
+                    mma(d, av, bl, desc_hi, 1);
+                    mma(d, av, bv, desc_hi, 1);
                     if (two) {
-                      umma::mma_tf32_lo(d, al + 2, bv + 2, desc_hi, idesc, 1);
-                      umma::mma_tf32_lo(d, av + 2, bl + 2, desc_hi, idesc, 1);
-                      umma::mma_tf32_lo(d, av + 2, bv + 2, desc_hi, idesc, 1);
+                      mma(d, al + 2, bv + 2, desc_hi, 1);
+                      mma(d, av + 2, bl + 2, desc_hi, 1);
+                      mma(d, av + 2, bv + 2, desc_hi, 1);
                     }
                   }
                 }
-                umma::mma_commit(empty_b(rb.stage));
+                commit(empty_b(rb.stage));
               }
               __syncwarp();
               first = 1;
               rb.advance();
             }
-            if (umma::elect_one()) umma::mma_commit(empty_a(ra.stage));
+            if (umma::elect_one()) commit(empty_a(ra.stage));
             __syncwarp();
             ra.advance();
           }
         }
-        if (umma::elect_one()) umma::mma_commit(tmem_full(buf));
+        if (umma::elect_one()) commit(tmem_full(buf));
         __syncwarp();
       }
     } else
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+    for (int u = u_first; u < n_units; u += u_stride, ++it) {
       const int buf = it & 1;
       SSDN_TIMED(w_tmem, umma::mbar_wait(tmem_empty(buf), ((it >> 1) & 1) ^ 1, abort_addr, p.error_flag, 3));
       umma::tc_fence_after();
@@ -359,18 +394,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                   umma::mma_tf32_ss(d, umma::desc_at(desc, av + ao + 32), umma::desc_at(desc, bv + 32), idesc, 1);
                 }
               }
-              if (last_slab) umma::mma_commit(empty_b(rb.stage));
+              if (last_slab) commit(empty_b(rb.stage));
             }
             __syncwarp();
             first = 1;
             if (last_slab) { sb = 0; rb.advance(); } else ++sb;
           }
-          if (umma::elect_one()) umma::mma_commit(empty_a(ra.stage));
+          if (umma::elect_one()) commit(empty_a(ra.stage));
           __syncwarp();
           ra.advance();
         }
       }
-      if (umma::elect_one()) umma::mma_commit(tmem_full(buf));
+      if (umma::elect_one()) commit(tmem_full(buf));
       __syncwarp();
     }
     if (p.stats && lane == 0) {
@@ -400,18 +435,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     long long w_full = 0;
     const long long t_start = clock64();
     LanePixel nxt;
-    if (blockIdx.x < n_units) lane_pixel(p, blockIdx.x / p.n_tiles_n, blockIdx.x % p.n_tiles_n, 0, T, ew, lane, nxt);
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+    if (u_first < n_units) lane_pixel(p, unit_m(u_first), u_first % p.n_tiles_n, 0, T, ew, lane, nxt);
+    const uint32_t tmem_empty_lead0 = PAIR ? umma::mapa(tmem_empty(0), 0) : tmem_empty(0);   // the MMA issuer's barrier
+    for (int u = u_first; u < n_units; u += u_stride, ++it) {
       const int buf = it & 1;
-      const int um = u / p.n_tiles_n, nt = u % p.n_tiles_n;
+      const int um = unit_m(u), nt = u % p.n_tiles_n;
       SSDN_TIMED(w_full, umma::mbar_wait(tmem_full(buf), (it >> 1) & 1, abort_addr, p.error_flag, 4));
       umma::tc_fence_after();
       for (int tile = 0; tile < T; ++tile) {
         const LanePixel cur = nxt;
         {   // mapping + mask words of the next tile of this CTA (loads stay in flight while this tile is written)
           int nu = u, ntile = tile + 1;
-          if (ntile == T) { ntile = 0; nu = u + gridDim.x; }
-          if (nu < n_units) lane_pixel(p, nu / p.n_tiles_n, nu % p.n_tiles_n, ntile, T, ew, lane, nxt);
+          if (ntile == T) { ntile = 0; nu = u + u_stride; }
+          if (nu < n_units) lane_pixel(p, unit_m(nu), nu % p.n_tiles_n, ntile, T, ew, lane, nxt);
         }
         const uint32_t trow = tmem + (uint32_t(ew * 32) << 16) + (buf * T + tile) * p.N;
 #pragma unroll
@@ -548,11 +584,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
       }
       umma::tc_fence_before();
-      umma::mbar_arrive(tmem_empty(buf));
+      if (PAIR) umma::mbar_arrive_cluster(tmem_empty_lead0 + 8 * buf); else umma::mbar_arrive(tmem_empty(buf));
     }
     if (d.colsum) {
       // this CTA only ever sees one N tile when gridDim.x is a multiple of n_tiles_n (the host guarantees it)
-      const int nt = blockIdx.x % p.n_tiles_n;
+      const int nt = u_first % p.n_tiles_n;
       const int c_first = (d.map == MAP_UNROT_INV) ? 0 : nt * p.N;
       float* row = d.colsum + (long long)(blockIdx.x * n_epi_warps + (warp - 4)) * d.colsum_pitch;
       for (int c = lane; c < d.colsum_pitch; c += 32) row[c] = 0.f;
@@ -560,13 +596,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // lane -> channel of the transpose-reduce: bit k of the lane selected the upper half at step k, i.e. channel == lane
 #pragma unroll
       for (int s = 0; s < kMaxSlices; ++s)
-        if (32 * s < p.N && (!p.epi_split || (s & 1) == half) && c_first + 32 * s + lane < d.colsum_pitch && (blockIdx.x < n_units)) row[c_first + 32 * s + lane] = csum[s];
+        if (32 * s < p.N && (!p.epi_split || (s & 1) == half) && c_first + 32 * s + lane < d.colsum_pitch && (u_first < n_units)) row[c_first + 32 * s + lane] = csum[s];
     }
     if (p.stats && threadIdx.x == 128) { p.stats[blockIdx.x * 16 + 6] = w_full; p.stats[blockIdx.x * 16 + 7] = clock64() - t_start; }
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 3) umma::tmem_dealloc(tmem, 512);
+  if (PAIR) umma::cluster_sync();       // the peer may still be signalling this CTA's barriers / reading its shared memory
+  if (warp == 3) { if (PAIR) umma::tmem_dealloc_pair(tmem, 512); else umma::tmem_dealloc(tmem, 512); }
 }
 
 }  // namespace convk
@@ -617,7 +654,22 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
   // SM's TMA unit whatever its size (profiles/r01_tma_rate.log), so operands must arrive in few, large boxes.
   const int n_slabs = p.n_chunks * taps.n;
   p.bg = p.wide ? 1 : ((taps.n % 3 == 0) ? 3 : (n_slabs % 3 == 0 ? 3 : (n_slabs % 2 == 0 ? 2 : 1)));
-  p.b_stage_bytes = (uint32_t)(p.bg * 2 * N * cw_ch * 4);
+  // CTA pairs (cta_group::2): 3x3 stencils whose rows advance by +-1 pixel (the row3 issue path), N/2 a whole number of
+  // 8-row swizzle groups, and at least one pair-unit per cluster worth of work
+  {
+    bool rows_ok = taps.n == 9 && p.bg == 3;
+    for (int r = 0; r < 3 && rows_ok; ++r) {
+      const int s1 = taps.off[3 * r + 1] - taps.off[3 * r], s2 = taps.off[3 * r + 2] - taps.off[3 * r + 1];
+      rows_ok = s1 == s2 && (s1 == 1 || s1 == -1);
+    }
+    const char* e = getenv("SSDN_CONV_PAIR");
+    // ... and only where the tensor core, not the epilogue, is the bottleneck of a tile (see epi_split below)
+    const double mma_clk = (double)n_slabs * 6 * std::max(N / 2.0, (4096.0 + 32.0 * N) / 128.0);
+    const double epi_clk = 4500.0 * ((N + 31) / 32) * (dst.map == MAP_UP2 ? 2 : 1);
+    p.pair = rows_ok && (N % 16 == 0) && (num_sms % 2 == 0) && mma_clk >= epi_clk && !(e && atoi(e) == 0);
+    if (e && atoi(e) == 2) p.pair = rows_ok && (N % 16 == 0);
+  }
+  p.b_stage_bytes = (uint32_t)(p.bg * 2 * (p.pair ? N / 2 : N) * cw_ch * 4);   // per CTA
   // epilogue mode: straight-from-register stores cost the load/store unit ~2800 clk per 32-channel slice of a tile
   // (32 line fragments per instruction); stage through shared memory when the tile's MMA time cannot hide that
   {
@@ -683,10 +735,18 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     }
     if (ok) { p.row3 = 1; p.tap_step = step; }
   }
-  plan->grid = std::min(p.n_units_m * p.n_tiles_n, num_sms);
-  if (dst.colsum) {                                  // column sums: every CTA must stay on one N tile (see the epilogue)
-    plan->grid -= plan->grid % p.n_tiles_n;
-    if (plan->grid < p.n_tiles_n) return -12;
+  if (p.pair && !p.row3) return -14;                 // the pair kernel only implements the row3 issue path
+  if (p.pair) {
+    p.n_pairs = (p.n_units_m + 1) / 2 * p.n_tiles_n;
+    int clusters = std::min(p.n_pairs, num_sms / 2);
+    if (dst.colsum) { clusters -= clusters % p.n_tiles_n; if (clusters < p.n_tiles_n) return -12; }
+    plan->grid = 2 * clusters;
+  } else {
+    plan->grid = std::min(p.n_units_m * p.n_tiles_n, num_sms);
+    if (dst.colsum) {                                  // column sums: every CTA must stay on one N tile (see the epilogue)
+      plan->grid -= plan->grid % p.n_tiles_n;
+      if (plan->grid < p.n_tiles_n) return -12;
+    }
   }
   if (dst.map != MAP_NCHW && (dst.cvalid % 4 || dst.cpitch % 4 || dst.coff % 4)) return -13;   // float4 stores
   // tensor maps.  A: 3-D (channel, flat pixel, plane); the lo plane must follow the hi plane at a constant byte distance.
@@ -701,7 +761,7 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
   // B: slabs [n_tile][chunk][tap][plane][N][16] -> 3-D (16, N, slab x plane), box = bg slabs x 2 planes
   uint64_t bdims[3] = {(uint64_t)cw_ch, (uint64_t)N, (uint64_t)p.n_tiles_n * n_slabs * 2};
   uint64_t bstr[2] = {(uint64_t)cw_ch * 4, (uint64_t)N * cw_ch * 4};
-  uint32_t bbox[3] = {(uint32_t)cw_ch, (uint32_t)N, (uint32_t)(2 * p.bg)};
+  uint32_t bbox[3] = {(uint32_t)cw_ch, (uint32_t)(p.pair ? N / 2 : N), (uint32_t)(2 * p.bg)};
   if ((r = umma::encode_f32(&plan->b, (void*)w_slab, 3, bdims, bstr, bbox, swz))) return r;
   return 0;
 }
@@ -723,6 +783,7 @@ struct LaunchProfiler {
 };
 inline LaunchProfiler& profiler() { static LaunchProfiler p; return p; }
 
+static inline cudaError_t conv_launch_raw(const ConvPlan& plan, const ConvParams& p, cudaStream_t stream);
 // Developer instrumentation: one synchronous launch with the per-role wait clocks collected and printed to stderr.
 static inline cudaError_t conv_launch_with_stats(const ConvPlan& plan, cudaStream_t stream, int kind) {
   static unsigned long long* dev = nullptr;
@@ -730,34 +791,51 @@ static inline cudaError_t conv_launch_with_stats(const ConvPlan& plan, cudaStrea
   cudaMemsetAsync(dev, 0, 1024 * 16 * sizeof(unsigned long long), stream);
   ConvParams p = plan.p; p.stats = dev;
   profiler().begin(kind, plan.flops, stream);
-  if (p.T == 2) convk::conv_igemm_kernel<2><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, p);
-  else convk::conv_igemm_kernel<1><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, p);
+  conv_launch_raw(plan, p, stream);
   profiler().end(stream);
   std::vector<unsigned long long> h((size_t)plan.grid * 16);
   cudaMemcpyAsync(h.data(), dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
   cudaError_t e = cudaStreamSynchronize(stream);
   double s[8] = {0};
   for (int b = 0; b < plan.grid; ++b) for (int k = 0; k < 8; ++k) s[k] += (double)h[(size_t)b * 16 + k] / plan.grid;
-  fprintf(stderr, "[conv stats] kind %d grid %d T %d N %d ntiles_n %d chunks %d groups %d taps %d a_st %d b_st %d bg %d | mma loop %.0f clk: wait tmem_empty %.1f%% "
+  fprintf(stderr, "[conv stats] kind %d pair %d grid %d T %d N %d ntiles_n %d chunks %d groups %d taps %d a_st %d b_st %d bg %d | mma loop %.0f clk: wait tmem_empty %.1f%% "
           "full_a %.1f%% full_b %.1f%% | prodA wait empty %.1f%% prodB wait empty %.1f%% | epi loop %.0f clk: wait tmem_full %.1f%%\n",
-          kind, plan.grid, p.T, p.N, p.n_tiles_n, p.n_chunks, p.n_groups, p.ntaps_total, p.a_stages, p.b_stages, p.bg, s[5], 100 * s[2] / s[5], 100 * s[3] / s[5],
+          kind, p.pair, plan.grid, p.T, p.N, p.n_tiles_n, p.n_chunks, p.n_groups, p.ntaps_total, p.a_stages, p.b_stages, p.bg, s[5], 100 * s[2] / s[5], 100 * s[3] / s[5],
           100 * s[4] / s[5], 100 * s[0] / s[5], 100 * s[1] / s[5], s[7], 100 * s[6] / s[7]);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-static inline cudaError_t conv_launch(const ConvPlan& plan, cudaStream_t stream, int kind = 0) {
+// One launch of the right instantiation; pairs go out as clusters of two CTAs.
+static inline cudaError_t conv_launch_raw(const ConvPlan& plan, const ConvParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(convk::conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(convk::conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(convk::conv_igemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(convk::conv_igemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(convk::conv_igemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(convk::conv_igemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  if (!p.pair) {
+    if (p.T == 2) convk::conv_igemm_kernel<2, false><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, p);
+    else convk::conv_igemm_kernel<1, false><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(convk::kThreads); cfg.dynamicSmemBytes = plan.smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (p.T == 2) return cudaLaunchKernelEx(&cfg, convk::conv_igemm_kernel<2, true>, plan.a, plan.b, p);
+  return cudaLaunchKernelEx(&cfg, convk::conv_igemm_kernel<1, true>, plan.a, plan.b, p);
+}
+
+static inline cudaError_t conv_launch(const ConvPlan& plan, cudaStream_t stream, int kind = 0) {
   static const bool want_stats = getenv("SSDN_CONV_STATS") != nullptr;
   if (want_stats && profiler().on) return conv_launch_with_stats(plan, stream, kind);
   if (profiler().on) profiler().begin(kind, plan.flops, stream);
-  if (plan.p.T == 2) convk::conv_igemm_kernel<2><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, plan.p);
-  else convk::conv_igemm_kernel<1><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, plan.p);
+  cudaError_t e = conv_launch_raw(plan, plan.p, stream);
   if (profiler().on) profiler().end(stream);
-  return cudaGetLastError();
+  return e;
 }

@@ -171,6 +171,67 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster on the two SMs of a TPC execute ONE tcgen05.mma of M = 256: each CTA supplies its own 128 rows of
+// A and HALF of the N rows of B from its own shared memory (same offsets in both), and receives its 128 accumulator rows
+// in its own TMEM.  Per CTA an MMA then reads 4 KB (A) + N/2 x 32 B (B) instead of 4 KB + N x 32 B - which is what takes
+// N = 96 tiles off the shared-memory bandwidth limit.  Only the leader (rank 0) issues MMAs and commits.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive / expect_tx on a barrier given by a shared::cluster address (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are signalled on a barrier of the pair's leader
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_lo_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once all previously issued MMAs completed
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100 format, version 1).
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4

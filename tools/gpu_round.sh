@@ -20,4 +20,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv
    python tests/dev_layer_times.py > gpurun_out/${TAG}_ncu_conv.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad_igemm_kernel -s 3 -c 1 -f -o gpurun_out/${TAG}_wgrad \
    python tests/dev_layer_times.py > gpurun_out/${TAG}_ncu_wgrad.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:wgrad_small_cin -c 1 -f -o gpurun_out/${TAG}_smallcin \
+   python tests/dev_layer_times.py > gpurun_out/${TAG}_ncu_smallcin.log 2>&1
+SSDN_CONV_STATS=1 timeout 200 python tests/dev_layer_times.py > gpurun_out/${TAG}_role_waits.log 2>&1
 ls -la gpurun_out
