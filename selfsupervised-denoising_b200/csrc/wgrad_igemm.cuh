@@ -75,7 +75,10 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
 
   const int n_units = p.n_co_tiles * p.n_ci_blocks * p.n_groups * p.ksplit;
   auto decode = [&](int u, int& ks, int& g, int& cb, int& ct) {
-    ks = u % p.ksplit; u /= p.ksplit; g = u % p.n_groups; u /= p.n_groups; cb = u % p.n_ci_blocks; ct = u / p.n_ci_blocks;
+    // the tap groups / channel blocks / co tiles of ONE K range are neighbours in the unit order: CTAs that run at the same
+    // time then read the same dZ and X rows and L2 serves the repeats (the K-range-major order re-read both from HBM once
+    // per group: 1.7 GB of DRAM reads for 0.84 GB of operands, profiles/r01_ncu_summary.txt)
+    g = u % p.n_groups; u /= p.n_groups; cb = u % p.n_ci_blocks; u /= p.n_ci_blocks; ct = u % p.n_co_tiles; ks = u / p.n_co_tiles;
   };
   const uint32_t abort_addr = umma::smem_u32(&abort_word);
 
