@@ -9,9 +9,10 @@ exactly the sequence of ssdn/ssdn/train.py:197-202 of the reference.
 
 engine arm (default)  : `value` times K steps with the batch already resident in HBM (CUDA events, barrier + sync on
                         both sides, max over ranks); `e2e` times K steps through the public API (Denoiser.run_pipeline +
-                        FlatAdam) with the batch in pinned HOST memory, host->device copy and the device->host read of
-                        the per-sample losses inside the timed region.  One extra profiled step brackets every
-                        tensor-core launch with CUDA events for the roofline block; rank 0 also times the CPU oracle.
+                        FlatAdam) with the batch in pinned HOST memory, host->device copy and the (asynchronous, pinned)
+                        device->host read of the per-sample losses of every step inside the timed region.  One extra
+                        profiled step brackets every tensor-core launch with CUDA events for the roofline block; rank 0
+                        also times the CPU oracle.
 reference arm         : `--impl reference` times the reference's own algorithm on the host cores (the oracle port of
                         the reference's PyTorch CPU path, all threads) on the same metric.
 """
@@ -56,34 +57,59 @@ def synthetic(n, seed):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML every 5 ms; nvidia-smi fallback)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
+        self.index, self.stop_flag, self.sm, self.mx, self.reasons = index, False, [], [], set()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml:
+                    n = self.nvml
+                    self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                    self.mx.append(int(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)):
+                        if r & bit:
+                            self.reasons.add(name)
+                    time.sleep(0.005)
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        c = [t.strip() for t in out.split(",")]
+                        if c[0].isdigit():
+                            self.sm.append(int(c[0]))
+                        if c[1].isdigit():
+                            self.mx.append(int(c[1]))
+                        for i in range(4):
+                            if len(c) >= 6 and c[2 + i].lower().startswith("active"):
+                                self.reasons.add(self.NAMES[i])
+                    time.sleep(0.05)
             except Exception:
-                pass
-            time.sleep(0.1)
+                time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
         self.join(timeout=6)
-        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": int(statistics.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def timed(fn, steps, device, dist_on):
@@ -182,7 +208,9 @@ def run_engine(args):
 
     def step_e2e():
         out = train_step(den, opt, [host_noisy, torch.zeros(0), {M.INPUT_NOISE_VALUES: host_sigma}], world)
-        host_loss.copy_(out[PipelineOutput.LOSS].detach(), non_blocking=False)      # D2H read of the step's result
+        # D2H read of the step's result into pinned memory.  Asynchronous, like a trainer that logs without stalling the
+        # device: every copy is enqueued inside the timed region and completes before timed()'s final synchronize.
+        host_loss.copy_(out[PipelineOutput.LOSS].detach(), non_blocking=True)
 
     for _ in range(max(3, args.warmup)):
         step_resident()
@@ -217,6 +245,13 @@ def run_engine(args):
         gemm_flops = sum(v[2] for v in prof.values())
         top = max(prof, key=lambda k: prof[k][1])
         ach = prof[top][2] / (prof[top][1] * 1e-3) / 1e12 if prof[top][1] > 0 else 0.0
+        # DRAM traffic per launch of the dominant kernel: from the committed `ncu --set full` capture (profiles/), not live
+        traffic = None
+        try:
+            prof_json = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = prof_json.get(top, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         launches = sum(p.kernel_launches(True) for net in den._models.values() for p in net._plans.values()) + 5
         cpu_rate, cpu_step = (0.0, 0.0) if args.no_cpu_baseline else cpu_oracle_rate(args.config, BATCH, 3, 1)
         line = {
@@ -234,7 +269,7 @@ def run_engine(args):
             "gpu_launches": int(launches * args.steps),
             "roofline": {"bound": "tensor", "kernel": {"conv_fwd": "conv_igemm_kernel (forward)", "conv_dgrad": "conv_igemm_kernel (data-gradient)",
                                                        "wgrad": "wgrad_igemm_kernel"}[top],
-                         "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+                         "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
                          "peak_source": peak_src,
                          "note": "achieved = algorithmic fp32-equivalent FLOPs / CUDA-event time of the kernel's launches in one step; the kernel "
                                  "issues 3 tf32 MMAs per product (3xTF32), so tensor-pipe issue rate = 3 x achieved",
