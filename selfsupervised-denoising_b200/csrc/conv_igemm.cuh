@@ -663,11 +663,8 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
       rows_ok = s1 == s2 && (s1 == 1 || s1 == -1);
     }
     const char* e = getenv("SSDN_CONV_PAIR");
-    // ... and only where the tensor core, not the epilogue, is the bottleneck of a tile (see epi_split below)
-    const double mma_clk = (double)n_slabs * 6 * std::max(N / 2.0, (4096.0 + 32.0 * N) / 128.0);
-    const double epi_clk = 4500.0 * ((N + 31) / 32) * (dst.map == MAP_UP2 ? 2 : 1);
-    p.pair = rows_ok && (N % 16 == 0) && (num_sms % 2 == 0) && mma_clk >= epi_clk && !(e && atoi(e) == 0);
-    if (e && atoi(e) == 2) p.pair = rows_ok && (N % 16 == 0);
+    // measured (profiles/r01_pair_split_ablation.log): pairs never lose except on the one-chunk first convolution
+    p.pair = rows_ok && (N % 16 == 0) && (num_sms % 2 == 0) && p.n_chunks >= 2 && !(e && atoi(e) == 0);
   }
   p.b_stage_bytes = (uint32_t)(p.bg * 2 * (p.pair ? N / 2 : N) * cw_ch * 4);   // per CTA
   // epilogue mode: straight-from-register stores cost the load/store unit ~2800 clk per 32-channel slice of a tile
@@ -677,8 +674,10 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     const double direct_clk = 2800.0 * ((N + 31) / 32);
     p.epi_staged = (dst.map != MAP_NCHW);   // measured: staging is never slower, even where the MMA time would hide direct stores
     (void)direct_clk;
-    // one epilogue warp per quadrant needs ~4500 clk per slice of a tile: use both warps where the MMAs cannot hide that
-    p.epi_split = (dst.map != MAP_NCHW || N > 32) && mma_clk < 0.75 * 4500.0 * ((N + 31) / 32);
+    // both epilogue warps of a quadrant: measured never slower, except with the upsampling epilogue (4x the stores: the two
+    // warps then only fight over the load/store unit)
+    p.epi_split = dst.map != MAP_UP2 && dst.map != MAP_NCHW;
+    (void)mma_clk;
     if (const char* e = getenv("SSDN_EPI_SPLIT")) p.epi_split = atoi(e) != 0;
     if (const char* e = getenv("SSDN_EPI_STAGED")) { const int v = atoi(e); if (v == 0) p.epi_staged = (dst.map == MAP_UP2); if (v == 1) p.epi_staged = (dst.map != MAP_NCHW); }
   }
