@@ -267,7 +267,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       constexpr uint64_t wdesc = umma::make_desc_base(16, 1024, umma::LAYOUT_SW128);
       const uint32_t desc_hi = (uint32_t)(wdesc >> 32);
       const uint32_t lbo_bits = (uint32_t)(wdesc & 0xffff0000u);
-      const uint32_t a_pl = p.a_plane_bytes >> 4, b_pl = (uint32_t)(p.N * 128) >> 4;
+      const uint32_t a_pl = p.a_plane_bytes >> 4, b_pl = (uint32_t)((PAIR ? p.N / 2 : p.N) * 128) >> 4;
       for (int u = u_first; u < n_units; u += u_stride, ++it) {
         const int buf = it & 1;
         SSDN_TIMED(w_tmem, umma::mbar_wait(tmem_empty(buf), ((it >> 1) & 1) ^ 1, abort_addr, p.error_flag, 3));
@@ -664,7 +664,10 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     }
     const char* e = getenv("SSDN_CONV_PAIR");
     // measured (profiles/r01_pair_split_ablation.log): pairs never lose except on the one-chunk first convolution
-    p.pair = rows_ok && (N % 16 == 0) && (num_sms % 2 == 0) && p.n_chunks >= 2 && !(e && atoi(e) == 0);
+    // 1x1 layers: only the wide-N, deep-K head conv gains (its B stream is what saturates the TMA unit); measured
+    const bool wide_ok = p.wide && N >= 192 && p.n_chunks >= 8;
+    p.pair = (rows_ok || wide_ok) && (N % 16 == 0) && (num_sms % 2 == 0) && p.n_chunks >= 2 && !(e && atoi(e) == 0);
+    if (p.wide && e && atoi(e) == 3) p.pair = 0;   // ablation: pairs on the 3x3 layers only
   }
   p.b_stage_bytes = (uint32_t)(p.bg * 2 * (p.pair ? N / 2 : N) * cw_ch * 4);   // per CTA
   // epilogue mode: straight-from-register stores cost the load/store unit ~2800 clk per 32-channel slice of a tile
@@ -734,7 +737,7 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     }
     if (ok) { p.row3 = 1; p.tap_step = step; }
   }
-  if (p.pair && !p.row3) return -14;                 // the pair kernel only implements the row3 issue path
+  if (p.pair && !p.row3 && !p.wide) return -14;      // pairs are implemented for the row3 and the wide issue paths
   if (p.pair) {
     p.n_pairs = (p.n_units_m + 1) / 2 * p.n_tiles_n;
     int clusters = std::min(p.n_pairs, num_sms / 2);

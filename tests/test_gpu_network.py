@@ -136,3 +136,13 @@ def test_shape_validation(engine):
     x = torch.rand(1, 3, 64, 32)
     out = plan.forward(_flat(params, O.param_order(3, 3, False)), x.cuda(), training=False)
     assert rel(out, O.noise_network_forward(params, x, False)) < TOL
+
+
+def test_forward_at_patch_128(engine):
+    """BASELINE config 5 geometry (128 x 128 patches, 3-box halo windows): blind-spot forward vs the oracle."""
+    p = O.init_params(3, 9, True, generator=torch.Generator().manual_seed(3))
+    x = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(4))
+    plan = engine.NetPlan(1, 3, 9, 128, 128, True, "cuda")
+    out = plan.forward(_flat(p, O.param_order(3, 9, True)), x.cuda(), training=False)
+    plan.check()
+    assert rel(out, O.noise_network_forward(p, x, True)) < TOL
