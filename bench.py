@@ -274,7 +274,8 @@ def run_engine(args):
                          "note": "achieved = algorithmic fp32-equivalent FLOPs / CUDA-event time of the kernel's launches in one step; the kernel "
                                  "issues 3 tf32 MMAs per product (3xTF32), so tensor-pipe issue rate = 3 x achieved",
                          "pipe_frac": 3 * ach / tf32_peak,
-                         "per_kind": {k: {"launches": v[0], "ms": v[1], "algorithmic_tflops": (v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0)}
+                         "per_kind": {k: {"launches": v[0], "ms": v[1], "algorithmic_tflops": (v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0),
+                                          "pipe_frac": (3 * v[2] / (v[1] * 1e-3) / 1e12 / tf32_peak if v[1] > 0 else 0.0)}
                                       for k, v in prof.items()},
                          "gemm_share_of_step": gemm_ms / (t_res / args.steps * 1e3),
                          "step_algorithmic_tflops": TRAIN_GFLOP_PER_PATCH[args.config] * 1e9 * BATCH / (t_res / args.steps) / 1e12},

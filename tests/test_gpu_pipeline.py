@@ -115,3 +115,25 @@ def test_gradients_are_written_into_the_flat_buffer(engine):
         assert torch.equal(flat_g[off:off + p.numel()], p.grad.reshape(-1))
         off += p.numel()
     assert off == flat_g.numel() == 1269130
+
+
+def test_trained_checkpoint_psnr_parity(engine):
+    """PSNR parity at TRAINED weights: the engine, loaded with the reference checkpoint
+    final-ssdn-gauss25-sigma_known.wt, reproduces the reference's outputs to 1e-4 and its PSNRs to 1e-3 dB."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wt_ssdn_gauss25_sigma_known.npz"))
+    params = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p.")}
+    g = {k: torch.from_numpy(z[k]) for k in z.files if not k.startswith("p.")}
+    den = ssdn.Denoiser(make_cfg("ssdn", "known", 3), device="cuda")
+    den.get_model(ssdn.Denoiser.MODEL, False).load_state_dict(params, strict=False)
+    den.eval()
+    M = NoisyDataset.Metadata
+    with torch.no_grad():
+        out = den.run_pipeline([g["noisy"], torch.zeros(0), {M.INPUT_NOISE_VALUES: g["sigma"], M.CLEAN: g["clean"]}])
+    psnr = lambda a, b: -10.0 * torch.log10(((a - b) ** 2).mean(dim=(1, 2, 3)))  # noqa: E731
+    pme, mu = out[PipelineOutput.IMG_DENOISED].cpu(), out[PipelineOutput.IMG_MU].cpu()
+    assert rel(pme, g["pme"]) < TOL and rel(mu, g["mu"]) < TOL
+    assert rel(out[PipelineOutput.LOSS].view(-1), g["loss"]) < TOL
+    assert (psnr(pme, g["clean"]) - g["psnr_pme"]).abs().max().item() < 1e-3
+    assert (psnr(mu, g["clean"]) - g["psnr_mu"]).abs().max().item() < 1e-3

@@ -1,4 +1,6 @@
 """CPU: the oracle reproduces every golden fixture (= outputs of the unmodified reference, tests/golden/make_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -131,3 +133,26 @@ def test_training_trajectory_fixture():
     for k in range(3):
         out = tr.step(d["noisy"], d["noise_values"], lr=3e-4)
         assert rel(out["loss"], gold["losses"][k]) < 5e-5
+
+
+def _load_wt_golden():
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wt_ssdn_gauss25_sigma_known.npz"))
+    params = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p.")}
+    return params, {k: torch.from_numpy(z[k]) for k in z.files if not k.startswith("p.")}
+
+
+def _psnr(a, b):
+    return -10.0 * torch.log10(((a - b) ** 2).mean(dim=(1, 2, 3)))
+
+
+def test_oracle_reproduces_trained_checkpoint_outputs():
+    """Trained reference weights (models/final-ssdn-gauss25-sigma_known.wt, tests/golden/make_wt_golden.py): the oracle
+    reproduces the reference's posterior mean, network mean, loss and PSNRs (20.3 dB in -> 30.2 dB out)."""
+    params, g = _load_wt_golden()
+    out = O.ssdn_pipeline(params, g["noisy"], g["sigma"], "known")
+    for k in ("pme", "mu"):
+        assert ((out[k] - g[k]).abs().max() / g[k].abs().max()).item() < 1e-5, k
+    assert ((out["loss"].view(-1) - g["loss"]).abs().max() / g["loss"].abs().max()).item() < 1e-5
+    assert (_psnr(out["pme"], g["clean"]) - g["psnr_pme"]).abs().max().item() < 1e-3
+    assert (g["psnr_pme"] > g["psnr_in"] + 9.0).all()          # the checkpoint really denoises: ~ +10 dB
