@@ -392,7 +392,9 @@ class Net {
       SSDN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
       ws_ = side;
     }
-    if (wgradk::wgrad_small_cin_ok(l.cin, l.cout, nt)) {        // first conv: CUDA-core kernel (see wgrad_igemm.cuh)
+    const bool small_cin = wgradk::wgrad_small_cin_ok(l.cin, l.cout, nt) && l.dz->cpitch == l.cout &&
+                           wgradk::kSmallCinTile + 2 * l.x->g.P + 2 <= 12 * l.cout;   // X window rows <= 2 x threads
+    if (small_cin) {                                              // first conv: CUDA-core kernel (see wgrad_igemm.cuh)
       ConvTaps taps = eng::make_taps(l.ksize, blind, false, l.x->g.P);
       if (profiler().on) profiler().begin(2, l.wgrad.flops, ws_);
       cudaError_t ce = wgradk::wgrad_small_cin_launch(l.dz->v, l.dz->lo, l.dz->cpitch, l.cout, l.x->v, l.x->lo, l.x->cpitch, l.x_coff, l.cin,

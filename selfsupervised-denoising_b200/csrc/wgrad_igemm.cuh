@@ -249,57 +249,104 @@ static inline void wgrad_reduce_launch(const float* partial, int ksplit, int nta
 }
 
 // Weight gradient of the FIRST convolution (1..4 input channels, e.g. RGB): a [cout] x [cin x taps] problem is far too thin
-// for a 128 x N tensor-core tile (3 useful columns of 16), so it runs on the CUDA cores.  Thread (tap, co) keeps dW[tap][co][0..3]
-// in registers; dZ (hi + lo) and the X window (hi + lo, padded to float4) of 128 flat pixels are staged in shared memory;
-// every read in the pixel loop is either a broadcast or 32 consecutive words.  Partials [CTA][tap][co][ci] go through the
-// same fixed-order reduction as the tensor-core path.
+// for a 128 x N tensor-core tile (3 useful columns of 16), so it runs on the CUDA cores.  Thread (pixel half, stencil row r,
+// co) keeps dW[3r .. 3r+2][co][0..3] in 12 registers.  The dZ planes of 128 flat pixels are one contiguous 24 KB block
+// each: they arrive by 1-D bulk TMA (cp.async.bulk) into a double buffer, one tile ahead; the X window (3 of 100 channels
+// per pixel) is prefetched into registers during the previous tile.  The three taps of a row read consecutive pixels of X,
+// so the pixel loop slides a 3-pixel register window: two 4-byte and one 16-byte shared loads feed 12 FMAs per pixel.
+// Partials [CTA][tap][co][ci] go through the same fixed-order reduction as the tensor-core path.
 struct SmallCinTaps { int rel[9]; int lo; int span; };
 constexpr int kSmallCinTile = 128;
-__global__ void __launch_bounds__(1024) wgrad_small_cin_kernel(const float* __restrict__ dz_v, const float* __restrict__ dz_lo, int dz_cpitch,
-                                                               int cout, const float* __restrict__ x_v, const float* __restrict__ x_lo,
-                                                               int x_cpitch, int x_coff, int cin, long long total, SmallCinTaps taps,
-                                                               float* __restrict__ partial) {
-  extern __shared__ __align__(16) float sm_small[];
-  float* dz_s = sm_small;                                             // [128][cout]
-  float4* x_s = reinterpret_cast<float4*>(sm_small + kSmallCinTile * cout);   // [128 + span]
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int tap = tid / cout, co = tid - tap * cout;
+__global__ void __launch_bounds__(384) wgrad_small_cin_kernel(const float* __restrict__ dz_v, const float* __restrict__ dz_lo, int cout,
+                                                              const float* __restrict__ x_v, const float* __restrict__ x_lo,
+                                                              int x_cpitch, int x_coff, int cin, long long total, SmallCinTaps taps,
+                                                              float* __restrict__ partial) {
+  extern __shared__ __align__(128) float sm_small[];
+  __shared__ __align__(8) uint64_t bars[2];
+  const int tile_floats = kSmallCinTile * cout;
   const int rows = kSmallCinTile + taps.span;
-  const int rel = taps.rel[tap];
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float* dz_s = sm_small;                                                          // [buf][plane][128][cout]
+  float4* x_s = reinterpret_cast<float4*>(sm_small + 4 * tile_floats);             // [buf][rows]
+  const int tid = threadIdx.x, nthr = blockDim.x;                                  // blockDim.x == 2 * 3 * cout
+  const int half = tid / (3 * cout), t3 = tid - half * 3 * cout;
+  const int r = t3 / cout, co = t3 - r * cout;
+  const int rel = taps.rel[3 * r];                                                 // taps 3r, 3r+1, 3r+2 read pixels rel, rel+1, rel+2
+  const uint32_t bar0 = umma::smem_u32(&bars[0]);
+  if (tid == 0) { umma::mbar_init(bar0, 1); umma::mbar_init(bar0 + 8, 1); umma::fence_mbar_init(); }
+  __syncthreads();
   const long long ntiles = (total + kSmallCinTile - 1) / kSmallCinTile;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  auto issue_dz = [&](long long tile, int buf) {      // one thread: both planes of a tile by bulk copy
     const long long base = tile * kSmallCinTile;
-    __syncthreads();
+    const uint32_t bytes = (uint32_t)((total - base < kSmallCinTile ? total - base : kSmallCinTile) * cout * 4);
+    const uint32_t dst = umma::smem_u32(dz_s + (size_t)buf * 2 * tile_floats), bar = bar0 + 8 * buf;
+    umma::mbar_expect_tx(bar, 2 * bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(dz_v + base * cout), "r"(bytes), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + tile_floats * 4),
+                 "l"(dz_lo + base * cout), "r"(bytes), "r"(bar) : "memory");
+  };
+  auto load_x = [&](long long tile, int q, float (&v)[4]) {   // X window row q of a tile (hi + lo), zero outside the tensor
+    const long long g = tile * kSmallCinTile + taps.lo + q;
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (q < rows && g >= 0 && g < total)
+      for (int c = 0; c < cin; ++c) v[c] = __ldg(x_v + g * x_cpitch + x_coff + c) + __ldg(x_lo + g * x_cpitch + x_coff + c);
+  };
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+  long long tile = blockIdx.x;
+  if (tile < ntiles) {
+    if (tid == 0) issue_dz(tile, 0);
+    for (int q = tid; q < rows; q += nthr) { float v[4]; load_x(tile, q, v); x_s[q] = make_float4(v[0], v[1], v[2], v[3]); }
+  }
+  __syncthreads();
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const long long next = tile + gridDim.x;
+    float xn[2][4];                                    // next tile's X rows tid and tid + nthr (rows <= 2 * nthr)
+    if (next < ntiles) {
+      if (tid == 0) issue_dz(next, buf ^ 1);
+      load_x(next, tid, xn[0]); load_x(next, tid + nthr, xn[1]);
+    }
+    umma::mbar_wait(bar0 + 8 * buf, (it >> 1) & 1);
+    const float* dh = dz_s + (size_t)buf * 2 * tile_floats + co, * dl = dh + tile_floats;
+    const float4* xs = x_s + (size_t)buf * rows + rel;
+    const long long left = total - tile * kSmallCinTile;
+    const int p0 = half * (kSmallCinTile / 2), p1 = (int)(left < p0 + kSmallCinTile / 2 ? (left > p0 ? left : p0) : p0 + kSmallCinTile / 2);
+    float4 x0 = xs[p0], x1 = xs[p0 + 1];
 #pragma unroll 4
-    for (int i = tid; i < kSmallCinTile * cout; i += nthr) {
-      const int px = i / cout, c = i - px * cout;
-      const long long g = base + px;
-      dz_s[i] = g < total ? __ldg(dz_v + g * dz_cpitch + c) + __ldg(dz_lo + g * dz_cpitch + c) : 0.f;
+    for (int px = p0; px < p1; ++px) {
+      const float4 x2 = xs[px + 2];
+      const float d = dh[px * cout] + dl[px * cout];
+      a0.x = fmaf(d, x0.x, a0.x); a0.y = fmaf(d, x0.y, a0.y); a0.z = fmaf(d, x0.z, a0.z); a0.w = fmaf(d, x0.w, a0.w);
+      a1.x = fmaf(d, x1.x, a1.x); a1.y = fmaf(d, x1.y, a1.y); a1.z = fmaf(d, x1.z, a1.z); a1.w = fmaf(d, x1.w, a1.w);
+      a2.x = fmaf(d, x2.x, a2.x); a2.y = fmaf(d, x2.y, a2.y); a2.z = fmaf(d, x2.z, a2.z); a2.w = fmaf(d, x2.w, a2.w);
+      x0 = x1; x1 = x2;
     }
-    for (int r = tid; r < rows; r += nthr) {
-      const long long g = base + taps.lo + r;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (g >= 0 && g < total)
-        for (int c = 0; c < cin; ++c) v[c] = __ldg(x_v + g * x_cpitch + x_coff + c) + __ldg(x_lo + g * x_cpitch + x_coff + c);
-      x_s[r] = make_float4(v[0], v[1], v[2], v[3]);
+    if (next < ntiles) {
+      float4* xd = x_s + (size_t)(buf ^ 1) * rows;
+      if (tid < rows) xd[tid] = make_float4(xn[0][0], xn[0][1], xn[0][2], xn[0][3]);
+      if (tid + nthr < rows) xd[tid + nthr] = make_float4(xn[1][0], xn[1][1], xn[1][2], xn[1][3]);
     }
-    __syncthreads();
-#pragma unroll 8
-    for (int px = 0; px < kSmallCinTile; ++px) {
-      const float d = dz_s[px * cout + co];
-      const float4 xv = x_s[px + rel];
-      a0 = fmaf(d, xv.x, a0); a1 = fmaf(d, xv.y, a1); a2 = fmaf(d, xv.z, a2); a3 = fmaf(d, xv.w, a3);
+    __syncthreads();                                   // everyone is done with buf: the next iteration may refill it
+  }
+  // combine the two pixel halves (fixed order), then write the CTA's partial
+  float4* red = reinterpret_cast<float4*>(sm_small);
+  if (half == 1) { red[3 * t3] = a0; red[3 * t3 + 1] = a1; red[3 * t3 + 2] = a2; }
+  __syncthreads();
+  if (half == 0) {
+    const float4 b0 = red[3 * t3], b1 = red[3 * t3 + 1], b2 = red[3 * t3 + 2];
+    const float v[3][4] = {{a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w}, {a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w},
+                           {a2.x + b2.x, a2.y + b2.y, a2.z + b2.z, a2.w + b2.w}};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float* dst = partial + ((long long)blockIdx.x * 9 + 3 * r + j) * cout * cin + (long long)co * cin;
+      for (int c = 0; c < cin; ++c) dst[c] = v[j][c];
     }
   }
-  float* dst = partial + ((long long)blockIdx.x * 9 + tap) * cout * cin + (long long)co * cin;
-  const float acc[4] = {a0, a1, a2, a3};
-  for (int c = 0; c < cin; ++c) dst[c] = acc[c];
 }
-constexpr int kSmallCinGrid = 592;
-static inline bool wgrad_small_cin_ok(int cin, int cout, int ntaps) { return cin <= 4 && ntaps == 9 && cout * ntaps <= 1024; }
+constexpr int kSmallCinGrid = 296;      // 2 CTAs of 2 x 3 x cout threads per SM (2 x 54 KB of shared memory each at cout = 48)
+static inline bool wgrad_small_cin_ok(int cin, int cout, int ntaps) { return cin <= 4 && ntaps == 9 && cout * 6 <= 384 && cout % 4 == 0; }
 static inline size_t wgrad_small_cin_partial_floats(int cin, int cout) { return (size_t)kSmallCinGrid * 9 * cout * cin; }
-// taps: forward flat-pixel offsets of X relative to dZ (9 of them)
+// taps: forward flat-pixel offsets of X relative to dZ (9 of them).  dZ must be dense (channel pitch == cout).
 static inline cudaError_t wgrad_small_cin_launch(const float* dz_v, const float* dz_lo, int dz_cpitch, int cout, const float* x_v, const float* x_lo,
                                                  int x_cpitch, int x_coff, int cin, long long total, const int* tap_off, float* partial, float* dw,
                                                  cudaStream_t st) {
@@ -307,10 +354,14 @@ static inline cudaError_t wgrad_small_cin_launch(const float* dz_v, const float*
   for (int i = 1; i < 9; ++i) { t.lo = tap_off[i] < t.lo ? tap_off[i] : t.lo; hi = tap_off[i] > hi ? tap_off[i] : hi; }
   t.span = hi - t.lo;
   for (int i = 0; i < 9; ++i) t.rel[i] = tap_off[i] - t.lo;
-  const size_t smem = (size_t)kSmallCinTile * cout * 4 + (size_t)(kSmallCinTile + t.span) * 16;
+  for (int r = 0; r < 3; ++r)       // the sliding window needs the taps of a stencil row on consecutive pixels
+    if (t.rel[3 * r + 1] != t.rel[3 * r] + 1 || t.rel[3 * r + 2] != t.rel[3 * r] + 2) return cudaErrorInvalidValue;
+  const int nthr = 6 * cout, rows = kSmallCinTile + t.span;
+  if (dz_cpitch != cout || rows > 2 * nthr) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)4 * kSmallCinTile * cout * 4 + (size_t)2 * rows * 16;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(wgrad_small_cin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-  wgrad_small_cin_kernel<<<kSmallCinGrid, cout * 9, smem, st>>>(dz_v, dz_lo, dz_cpitch, cout, x_v, x_lo, x_cpitch, x_coff, cin, total, t, partial);
+  wgrad_small_cin_kernel<<<kSmallCinGrid, nthr, smem, st>>>(dz_v, dz_lo, cout, x_v, x_lo, x_cpitch, x_coff, cin, total, t, partial);
   wgrad_reduce_launch(partial, kSmallCinGrid, 9, cout, cin, dw, 0, st);
   return cudaGetLastError();
 }

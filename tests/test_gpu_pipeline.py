@@ -133,7 +133,12 @@ def test_trained_checkpoint_psnr_parity(engine):
         out = den.run_pipeline([g["noisy"], torch.zeros(0), {M.INPUT_NOISE_VALUES: g["sigma"], M.CLEAN: g["clean"]}])
     psnr = lambda a, b: -10.0 * torch.log10(((a - b) ** 2).mean(dim=(1, 2, 3)))  # noqa: E731
     pme, mu = out[PipelineOutput.IMG_DENOISED].cpu(), out[PipelineOutput.IMG_MU].cpu()
-    assert rel(pme, g["pme"]) < TOL and rel(mu, g["mu"]) < TOL
+    assert rel(mu, g["mu"]) < TOL
+    # the posterior mean inverts Sigma_x + 1e-6 I: the fp32 reference itself is only accurate to its own rounding there,
+    # so the engine (closed form in fp64 registers) is held to the exact (fp64 oracle) result within the reference's band
+    ref64 = O.ssdn_pipeline({k: v.double() for k, v in params.items()}, g["noisy"].double(), g["sigma"].double(), "known")
+    ok, errs = as_accurate_as_reference(pme, g["pme"], ref64["pme"])
+    assert ok, errs
     assert rel(out[PipelineOutput.LOSS].view(-1), g["loss"]) < TOL
     assert (psnr(pme, g["clean"]) - g["psnr_pme"]).abs().max().item() < 1e-3
     assert (psnr(mu, g["clean"]) - g["psnr_mu"]).abs().max().item() < 1e-3
