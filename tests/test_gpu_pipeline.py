@@ -142,3 +142,46 @@ def test_trained_checkpoint_psnr_parity(engine):
     assert rel(out[PipelineOutput.LOSS].view(-1), g["loss"]) < TOL
     assert (psnr(pme, g["clean"]) - g["psnr_pme"]).abs().max().item() < 1e-3
     assert (psnr(mu, g["clean"]) - g["psnr_mu"]).abs().max().item() < 1e-3
+
+
+def test_evaluator_on_padded_full_images(engine):
+    """Evaluation path (eval.py:19-127, train.py:243-259, 553-584): non-square images are
+    reflect-padded to a square multiple of 32, denoised with the trained checkpoint, cropped back and scored.  PSNRs on the
+    unpadded region must equal the oracle's to 1e-3 dB."""
+    import os
+    import numpy as np
+    from ssdn.eval import DenoiserEvaluator
+    from ssdn.params import NoiseAlgorithm
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wt_ssdn_gauss25_sigma_known.npz"))
+    params = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p.")}
+    state = {"cfg": make_cfg("ssdn", "known", 3)}
+    state.update({"models.denoiser_model.module." + k: v for k, v in params.items()})
+    ev = DenoiserEvaluator(state, device="cuda")
+    torch.manual_seed(77)
+    images = [O.synthetic_batch(1, 3, 96, seed=s)[0][0][:, :h, :w].contiguous() for s, (h, w) in ((1, (40, 56)), (2, (96, 70)), (3, (64, 64)))]
+    ds = NoisyDataset([(im,) for im in images], "gauss25", NoiseAlgorithm.SELFSUPERVISED_DENOISING, pad_multiple=32, square=True)
+    batches, expect = [], []
+    for i in range(len(ds)):
+        inp, ref, md = ds[i]
+        md = {k: (v[None] if torch.is_tensor(v) else v) for k, v in md.items()}
+        assert inp.shape[-1] == inp.shape[-2] and inp.shape[-1] % 32 == 0
+        batches.append([inp[None], ref, md])
+        sigma = md[NoisyDataset.Metadata.INPUT_NOISE_VALUES].reshape(1, -1, 1, 1)
+        out = O.ssdn_pipeline(params, inp[None], sigma, "known")
+        h, w = images[i].shape[1:]
+        expect.append(float(-10.0 * torch.log10(((out["pme"][0, :, :h, :w] - images[i]) ** 2).mean())))
+    got = ev.evaluate(batches)
+    assert abs(got["psnr_out"] - sum(expect) / len(expect)) < 1e-3, (got, expect)
+    assert got["psnr_out"] > 28.0
+
+
+def test_forward_at_256_uses_row_windows(engine):
+    """Full-size evaluation geometry: at 256 x 256 the 3x3 halo window no longer fits in shared memory as one box set and
+    the plan falls back to one window per stencil row; outputs must still match the oracle."""
+    p = O.init_params(3, 9, True, generator=torch.Generator().manual_seed(5))
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(6))
+    plan = engine.NetPlan(1, 3, 9, 256, 256, True, "cuda")
+    flat = torch.cat([p[k].reshape(-1) for k in O.param_order(3, 9, True)]).cuda()
+    out = plan.forward(flat, x.cuda(), training=False)
+    plan.check()
+    assert rel(out, O.noise_network_forward(p, x, True)) < TOL
