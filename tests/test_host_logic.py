@@ -1,4 +1,5 @@
 """CPU: host-side mirror of the reference interface (config, enums, module / state-dict schema, schedule, data plumbing)."""
+import os
 import pickle
 
 import pytest
@@ -192,3 +193,22 @@ def test_metric_accumulates_batch_means():
     m += torch.tensor([[9.0, 11.0]])
     assert m.n == 3 and abs(float(m.accumulated()) - 6.0) < 1e-6
     assert ssdn.utils.seconds_to_dhms(3661) == "01h01m01s"
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference checkpoints only exist in the build container")
+@pytest.mark.parametrize("name", ["final-ssdn-gauss25-sigma_known.wt", "final-ssdn-gauss25-sigma_var.wt", "final-ssdn-gauss25-sigma_const.wt",
+                                  "final-n2v-gauss25.wt", "final-n2c-gauss25.wt"])
+def test_reference_checkpoints_load_and_round_trip(name, tmp_path):
+    """Checkpoint wire format: the reference's shipped ``.wt`` files (pickled ConfigValue enums,
+    ``models.<id>.module.`` / ``_models.<id>.`` alias keys, learnable sigma) load into this package unchanged, every tensor
+    survives, and what we save has exactly the reference's key set."""
+    st = torch.load(os.path.join("/root/reference/models", name), map_location="cpu", weights_only=False)
+    den = ssdn.Denoiser.from_state_dict(st, device="cpu")
+    sd = den.state_dict()
+    assert set(sd) == set(st)
+    assert all(torch.equal(sd[k], v) for k, v in st.items() if torch.is_tensor(v))
+    assert sd["cfg"] == st["cfg"]
+    path = tmp_path / "again.wt"
+    torch.save(sd, path)
+    again = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(again) == set(st) and all(torch.equal(again[k], v) for k, v in st.items() if torch.is_tensor(v))
