@@ -132,7 +132,7 @@ extern "C" int ssdn_conv2d_backward_weight(void* ws, size_t ws_bytes, const floa
                             partial, flag, num_sms());
     if (r) return fail(r, "wgrad_plan_init failed (%d)", r);
     SSDN_CUDA(wgrad_launch(plan, st));
-    wgradk::wgrad_reduce_launch(partial, ks, ntaps, cout, cin, dw, 0, st);
+    wgradk::wgrad_reduce_launch(partial, ks, ntaps, cout, cin, plan.p.cin_pitch, dw, 0, st);
   }
   if (db) {
     const long long rows = g.total();

@@ -403,7 +403,7 @@ class Net {
       SSDN_CUDA(ce);
     } else {
       SSDN_CUDA(wgrad_launch(l.wgrad, ws_));
-      wgradk::wgrad_reduce_launch(partial, l.wgrad.p.ksplit, nt, l.cout, l.cin, grads + l.w_off, 0, ws_);
+      wgradk::wgrad_reduce_launch(partial, l.wgrad.p.ksplit, nt, l.cout, l.cin, l.wgrad.p.cin_pitch, grads + l.w_off, 0, ws_);
     }
     return 0;
   }

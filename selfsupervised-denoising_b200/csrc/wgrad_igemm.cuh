@@ -23,6 +23,7 @@ struct WgradParams {
   long long k_total;
   int KC, n_kchunks, ksplit, chunks_per_split;
   int n_co_tiles, cout, cin;
+  int cin_pitch;       // floats per (tap, co) row of the partial buffer: cin rounded up to 4 so that every row is 16-byte aligned
   int n_ci_blocks, ci_start[4], ci_n[4];
   int nba, nbx;        // 32-channel blocks actually loaded per stage for dZ (<= 4) and X (<= 6)
   int n_groups, ntaps_total;
@@ -191,15 +192,22 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
       const int co = ct * 128 + ew * 32 + lane;
       for (int t = 0; t < p.groups[g].ntaps; ++t) {
         const int tap = p.groups[g].tap_id[t];
-        float* dst = p.partial + (((long long)ks * p.ntaps_total + tap) * p.cout + co) * p.cin + p.ci_start[cb];
+        float* dst = p.partial + (((long long)ks * p.ntaps_total + tap) * p.cout + co) * p.cin_pitch + p.ci_start[cb];
         for (int n0 = 0; n0 < N; n0 += 16) {
           uint32_t r[16];
           umma::tmem_ld16(tmem + (uint32_t(ew * 32) << 16) + t * N + n0, r);
           umma::tmem_ld_wait();
           if (co < p.cout) {
+            if (p.ci_start[cb] + n0 + 16 <= p.cin_pitch) {      // a lane owns a contiguous, 16-byte aligned row (pad columns are ignored)
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (p.ci_start[cb] + n0 + i < p.cin) dst[n0 + i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(dst + n0 + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                                                                      __uint_as_float(r[i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (p.ci_start[cb] + n0 + i < p.cin) dst[n0 + i] = __uint_as_float(r[i]);
+            }
           }
         }
       }
@@ -218,10 +226,10 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
 // independent accumulators (coalesced 128-byte rows, many loads in flight), then the 16 lanes are combined in a fixed
 // order through shared memory - deterministic, and ~10x faster than one thread walking all splits serially.
 __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restrict__ partial, int ksplit, int ntaps, int cout, int cin,
-                                                           float* __restrict__ dw, int accumulate) {
+                                                           int pitch, float* __restrict__ dw, int accumulate) {
   __shared__ float sm[16][33];
-  const long long n = (long long)cout * cin * ntaps;
-  const long long idx = blockIdx.x * 32LL + threadIdx.x;   // over [tap][co][ci]
+  const long long n = (long long)cout * pitch * ntaps;
+  const long long idx = blockIdx.x * 32LL + threadIdx.x;   // over [tap][co][ci < pitch] (rows padded to `pitch` floats)
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (idx < n) {
     int k = threadIdx.y;
@@ -237,15 +245,19 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
     float acc = 0.f;
 #pragma unroll
     for (int w = 0; w < 16; ++w) acc += sm[w][threadIdx.x];
-    const int ci = (int)(idx % cin); long long t = idx / cin;
+    const int ci = (int)(idx % pitch); long long t = idx / pitch;
     const int co = (int)(t % cout); const int tap = (int)(t / cout);
-    const long long o = ((long long)co * cin + ci) * ntaps + tap;
-    dw[o] = accumulate ? dw[o] + acc : acc;
+    if (ci < cin) {
+      const long long o = ((long long)co * cin + ci) * ntaps + tap;
+      dw[o] = accumulate ? dw[o] + acc : acc;
+    }
   }
 }
-static inline void wgrad_reduce_launch(const float* partial, int ksplit, int ntaps, int cout, int cin, float* dw, int accumulate, cudaStream_t st) {
-  const long long n = (long long)cout * cin * ntaps;
-  wgrad_reduce_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 16), 0, st>>>(partial, ksplit, ntaps, cout, cin, dw, accumulate);
+static inline int wgrad_cin_pitch(int cin) { return (cin + 3) / 4 * 4; }
+static inline void wgrad_reduce_launch(const float* partial, int ksplit, int ntaps, int cout, int cin, int pitch, float* dw, int accumulate,
+                                       cudaStream_t st) {
+  const long long n = (long long)cout * pitch * ntaps;
+  wgrad_reduce_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 16), 0, st>>>(partial, ksplit, ntaps, cout, cin, pitch, dw, accumulate);
 }
 
 // Weight gradient of the FIRST convolution (1..4 input channels, e.g. RGB): a [cout] x [cin x taps] problem is far too thin
@@ -362,7 +374,7 @@ static inline cudaError_t wgrad_small_cin_launch(const float* dz_v, const float*
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(wgrad_small_cin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
   wgrad_small_cin_kernel<<<kSmallCinGrid, nthr, smem, st>>>(dz_v, dz_lo, cout, x_v, x_lo, x_cpitch, x_coff, cin, total, t, partial);
-  wgrad_reduce_launch(partial, kSmallCinGrid, 9, cout, cin, dw, 0, st);
+  wgrad_reduce_launch(partial, kSmallCinGrid, 9, cout, cin, cin, dw, 0, st);
   return cudaGetLastError();
 }
 
@@ -375,7 +387,7 @@ static inline int wgrad_ci_cap(int ntaps) { return ntaps == 9 ? 144 : 192; }   /
 static inline int wgrad_n_ci_blocks(int cin, int ntaps) { const int c16 = (cin + 15) / 16 * 16; return (c16 + wgrad_ci_cap(ntaps) - 1) / wgrad_ci_cap(ntaps); }
 
 static inline size_t wgrad_partial_floats(int ksplit, int ntaps, int cout, int cin) {
-  return (size_t)ksplit * ntaps * cout * cin;
+  return (size_t)ksplit * ntaps * cout * ((cin + 3) / 4 * 4);
 }
 
 // Decides the K split for a layer (so that the grid fills the chip) without needing pointers.
@@ -398,7 +410,7 @@ static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const floa
   p = WgradParams{};
   p.k_total = k_total; p.KC = 32; p.n_kchunks = (int)((k_total + p.KC - 1) / p.KC);
   p.ksplit = ksplit; p.chunks_per_split = (p.n_kchunks + ksplit - 1) / ksplit;
-  p.cout = cout; p.cin = cin; p.n_co_tiles = (cout + 127) / 128;
+  p.cout = cout; p.cin = cin; p.cin_pitch = (cin + 3) / 4 * 4; p.n_co_tiles = (cout + 127) / 128;
   // ci blocks: as wide as TMEM allows (3 taps x N <= 512 columns, N <= 256), so that dZ is streamed as few times as possible
   const int cap = wgrad_ci_cap(taps.n);
   p.n_ci_blocks = 0;
