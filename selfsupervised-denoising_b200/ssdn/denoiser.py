@@ -196,6 +196,20 @@ class Denoiser(nn.Module):
         if not style.startswith("gauss"):
             raise NotImplementedError("only Gaussian noise styles are implemented by the B200 engine")
         n = noisy.shape[0]
+        est_stream = None
+        if mode == NoiseValue.UNKNOWN_VARIABLE and noisy.is_cuda:
+            # The sigma estimator (a plain U-Net on N images, a quarter of the blind-spot net's pixels) and the main network
+            # are independent until the loss: run the estimator on a second stream so that it fills the SMs the main
+            # network's small layers leave idle.  autograd replays each backward node on the stream of its forward, so the
+            # two backward passes overlap the same way.
+            if getattr(self, "_est_stream", None) is None:
+                self._est_stream = torch.cuda.Stream(device=noisy.device)
+            est_stream = self._est_stream
+            est_stream.wait_stream(torch.cuda.current_stream(noisy.device))
+            with torch.cuda.stream(est_stream):
+                est = self.models[Denoiser.SIGMA_ESTIMATOR](noisy)
+                sigma_est = SpatialMeanFunction.apply(est).reshape(n, 1)
+            noisy.record_stream(est_stream)
         net_out = self.models[Denoiser.MODEL](noisy)
         if mode == NoiseValue.KNOWN:
             sigma_raw = md[NoisyDataset.Metadata.INPUT_NOISE_VALUES].to(self.device, non_blocking=True).float().reshape(n, -1)
@@ -204,8 +218,13 @@ class Denoiser(nn.Module):
             sigma_raw = self.l_params[Denoiser.ESTIMATED_SIGMA].reshape(1, 1).expand(n, 1)
             stat_shape = (1, 1, 1)
         elif mode == NoiseValue.UNKNOWN_VARIABLE:
-            est = self.models[Denoiser.SIGMA_ESTIMATOR](noisy)
-            sigma_raw = SpatialMeanFunction.apply(est).reshape(n, 1)
+            if est_stream is not None:
+                torch.cuda.current_stream(noisy.device).wait_stream(est_stream)
+                sigma_raw = sigma_est
+                sigma_raw.record_stream(torch.cuda.current_stream(noisy.device))
+            else:
+                est = self.models[Denoiser.SIGMA_ESTIMATOR](noisy)
+                sigma_raw = SpatialMeanFunction.apply(est).reshape(n, 1)
             stat_shape = (n, 1, 1)
         else:
             raise NotImplementedError("Unsupported noise value mode")
