@@ -450,46 +450,50 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (nu < n_units) lane_pixel(p, unit_m(nu), nu % p.n_tiles_n, ntile, T, ew, lane, nxt);
         }
         const uint32_t trow = tmem + (uint32_t(ew * 32) << 16) + (buf * T + tile) * p.N;
-#pragma unroll
+        // NOT unrolled: six copies of the slice body (~600 instructions each) do not fit the instruction cache, and an
+        // epilogue warp that streams its code from L2 for every tile is several times slower (ncu: stall_no_inst)
+#pragma unroll 1
         for (int s = 0; s < kMaxSlices; ++s) {
           const int c0 = 32 * s;
           if (c0 < p.N && (!p.epi_split || (s & 1) == half)) {
-            const int cw = min(32, p.N - c0);                              // 32 or 16 channels in this slice
+            // A slice is always handled as 32 columns: when N is not a multiple of 32 the last slice reads 16 columns that
+            // belong to nobody (all 512 TMEM columns are allocated) and channel validity is enforced where values leave
+            // the warp.  No per-element predication => less than half the instructions (the epilogue is issue-bound).
             const int cg0 = (d.map == MAP_UNROT_INV ? 0 : nt * p.N) + c0;  // first channel of the slice among this conv's outputs
             uint32_t r[32];
             umma::tmem_ld16(trow + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-            if (cw == 32) umma::tmem_ld16(trow + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+            umma::tmem_ld16(trow + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
             umma::tmem_ld_wait();
             if (cg0 < d.cvalid) {
               float f[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = (i < cw) ? __uint_as_float(r[i]) : 0.f;
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
               if (d.flags & EP_BIAS) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                  if (i < cw) {
-                    const float4 bq = *reinterpret_cast<const float4*>(&s_bias[cg0 + i]);
-                    f[i] += bq.x; f[i + 1] += bq.y; f[i + 2] += bq.z; f[i + 3] += bq.w;
-                  }
+                  const float4 bq = *reinterpret_cast<const float4*>(&s_bias[cg0 + i]);     // zero beyond cvalid
+                  f[i] += bq.x; f[i + 1] += bq.y; f[i + 2] += bq.z; f[i + 3] += bq.w;
                 }
               }
               if (d.flags & EP_LRELU) {
                 uint32_t word = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { word |= (f[i] > 0.f ? 1u : 0u) << i; f[i] = lrelu(f[i]); }
+                for (int i = 0; i < 32; ++i) { word |= (f[i] > 0.f ? 1u : 0u) << i; f[i] = fmaxf(f[i], SSDN_LRELU_SLOPE * f[i]); }
                 if (d.mask_out && cur.nd == 1)
                   d.mask_out[(long long)cur.d0 * d.mask_out_words + ((cur.cshift + cg0) >> 5)] = cur.zero ? 0u : word;
               }
               if (d.flags & EP_ACT_GRAD) {
-                const uint32_t word = cur.mw[s];
+                uint32_t word = cur.mw[0];          // register array: select instead of a dynamic (local-memory) index
+#pragma unroll
+                for (int k = 1; k < kMaxSlices; ++k) word = (k == s) ? cur.mw[k] : word;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = ((word >> i) & 1u) ? f[i] : SSDN_LRELU_SLOPE * f[i];
               }
-              if (cur.zero || cur.nd == 0) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = 0.f;
-              }
               if (d.colsum) {
+                if (cur.nd == 0) {                  // halo / out-of-range pixels hold garbage accumulators
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) f[i] = 0.f;
+                }
                 // transpose-reduce over the 32 pixels of the warp: after 5 exchange steps lane c holds the sum of channel c
                 float t16[16], t8[8], t4[4], t2[2];
 #pragma unroll
@@ -519,66 +523,51 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 {
                   const bool up = lane & 1;
                   const float send = up ? t2[0] : t2[1], keep = up ? t2[1] : t2[0];
-                  csum[s] += keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                  const float total = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+#pragma unroll
+                  for (int k = 0; k < kMaxSlices; ++k) csum[k] += (k == s) ? total : 0.f;
                 }
               }
+              // Every slice goes through shared memory (36-float rows: conflict-free float4 access).  NHWC destinations:
+              // 8 consecutive lanes then write one pixel's 128 contiguous bytes - 4 full lines per store instruction
+              // instead of 32 line fragments, which is what the load/store unit can sustain (upsampling writes each value
+              // 4 times).  NCHW destination (network output): a lane keeps its own pixel and walks the channels.
+              float* stage = reinterpret_cast<float*>(smem + p.epi_off) + (warp - 4) * 32 * kStagePitch;
+              float* row = stage + lane * kStagePitch;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(row + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+              __syncwarp();
               if (d.map == MAP_NCHW) {
                 if (cur.nd) {
-#pragma unroll
-                  for (int i = 0; i < 32; ++i)
-                    if (i < cw && cg0 + i < d.cvalid)
-                      d.v[(((long long)cur.b * d.cvalid + cg0 + i) * sg.H + cur.y) * sg.W + cur.x] = f[i];
+                  const long long hw = (long long)sg.H * sg.W;
+                  float* dst = d.v + ((long long)cur.b * d.cvalid + cg0) * hw + (long long)cur.y * sg.W + cur.x;
+                  const int nc = min(min(32, p.N - c0), d.cvalid - cg0);     // a slice may be cut by the N tile or by cvalid
+                  for (int c = 0; c < nc; ++c) dst[c * hw] = row[c];
                 }
-              } else if (p.epi_staged) {
-                // Store-bound epilogues (4 destinations per pixel when upsampling; little MMA work per output for 1x1 and
-                // few-channel convolutions): transposing the slice through shared memory lets 8 consecutive lanes write one
-                // pixel's 128 contiguous bytes - 4 full lines per store instruction instead of 32 line fragments, which is
-                // what the load/store unit can sustain.
-                float* stage = reinterpret_cast<float*>(smem + p.epi_off) + (warp - 4) * 32 * kStagePitch;
-                float* row = stage + lane * kStagePitch;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(row + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                __syncwarp();
-                const int L = cw >> 2, PPI = 32 / L, sub = lane / L, q4 = lane - sub * L;   // L lanes per pixel, PPI pixels per pass
-                const bool chan_ok = cg0 + 4 * q4 < d.cvalid;
-                for (int q = 0; q < 32; q += PPI) {
+              } else {
+                const int sub = lane >> 3, q4 = lane & 7;                  // 8 lanes per pixel, 4 pixels per pass
+                const bool chan_ok = (c0 + 4 * q4 < p.N) && (cg0 + 4 * q4 < d.cvalid);
+                const int meta = cur.nd | (cur.zero << 3);
+#pragma unroll 2
+                for (int q = 0; q < 32; q += 4) {
                   const int px = q + sub;
-                  const int pd0 = __shfl_sync(0xffffffffu, cur.d0, px), pnd = __shfl_sync(0xffffffffu, cur.nd, px);
+                  const int pd0 = __shfl_sync(0xffffffffu, cur.d0, px), pmeta = __shfl_sync(0xffffffffu, meta, px);
                   const int pcs = __shfl_sync(0xffffffffu, cur.cshift, px);
-                  if (chan_ok) {
-                    const float4 o = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 4 * q4);
+                  if (chan_ok && (pmeta & 7)) {
+                    float4 o = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 4 * q4);
+                    if (pmeta & 8) o = make_float4(0.f, 0.f, 0.f, 0.f);     // row shifted in by Shift2d
                     float4 h = o, l = o;
                     if (d.flags & EP_WRITE_LO) { tf32_split(o.x, h.x, l.x); tf32_split(o.y, h.y, l.y); tf32_split(o.z, h.z, l.z); tf32_split(o.w, h.w, l.w); }
-                    for (int k = 0; k < pnd; ++k) {
-                      const long long oi = (long long)(pd0 + (k & 1) + (k >> 1) * d.g.P) * d.cpitch + d.coff + pcs + cg0 + 4 * q4;
+                    const int cb = d.coff + pcs + cg0 + 4 * q4;
+                    for (int k = 0; k < (pmeta & 7); ++k) {
+                      const long long oi = (long long)(pd0 + (k & 1) + (k >> 1) * d.g.P) * d.cpitch + cb;
                       *reinterpret_cast<float4*>(d.v + oi) = h;
                       if (d.flags & EP_WRITE_LO) *reinterpret_cast<float4*>(d.lo + oi) = l;
                     }
                   }
                 }
-                __syncwarp();
-              } else if (cur.nd) {
-                const long long cbase = d.coff + cur.cshift + cg0;
-                for (int k = 0; k < cur.nd; ++k) {
-                  const long long oi = (long long)(cur.d0 + (k & 1) + (k >> 1) * d.g.P) * d.cpitch + cbase;
-                  float4* ov = reinterpret_cast<float4*>(d.v + oi);
-                  if (d.flags & EP_WRITE_LO) {
-                    float4* ol = reinterpret_cast<float4*>(d.lo + oi);
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                      if (i < cw && cg0 + i < d.cvalid) {
-                        float4 h, l;
-                        tf32_split(f[i], h.x, l.x); tf32_split(f[i + 1], h.y, l.y); tf32_split(f[i + 2], h.z, l.z); tf32_split(f[i + 3], h.w, l.w);
-                        ov[i >> 2] = h; ol[i >> 2] = l;
-                      }
-                    }
-                  } else {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                      if (i < cw && cg0 + i < d.cvalid) ov[i >> 2] = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                  }
-                }
               }
+              __syncwarp();
             }
           }
         }
@@ -596,7 +585,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // lane -> channel of the transpose-reduce: bit k of the lane selected the upper half at step k, i.e. channel == lane
 #pragma unroll
       for (int s = 0; s < kMaxSlices; ++s)
-        if (32 * s < p.N && (!p.epi_split || (s & 1) == half) && c_first + 32 * s + lane < d.colsum_pitch && (u_first < n_units)) row[c_first + 32 * s + lane] = csum[s];
+        if (32 * s + lane < p.N && (!p.epi_split || (s & 1) == half) && c_first + 32 * s + lane < d.colsum_pitch && (u_first < n_units)) row[c_first + 32 * s + lane] = csum[s];
     }
     if (p.stats && threadIdx.x == 128) { p.stats[blockIdx.x * 16 + 6] = w_full; p.stats[blockIdx.x * 16 + 7] = clock64() - t_start; }
   }
@@ -675,14 +664,14 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
   {
     const double mma_clk = (double)n_slabs * (p.wide ? 12 : 6) * std::max(N / 2.0, (4096.0 + 32.0 * N) / 128.0);
     const double direct_clk = 2800.0 * ((N + 31) / 32);
-    p.epi_staged = (dst.map != MAP_NCHW);   // measured: staging is never slower, even where the MMA time would hide direct stores
+    p.epi_staged = 1;   // measured: staging is never slower, even where the MMA time would hide register-direct stores
     (void)direct_clk;
     // both epilogue warps of a quadrant: measured never slower, except with the upsampling epilogue (4x the stores: the two
     // warps then only fight over the load/store unit)
     p.epi_split = dst.map != MAP_UP2 && dst.map != MAP_NCHW;
     (void)mma_clk;
     if (const char* e = getenv("SSDN_EPI_SPLIT")) p.epi_split = atoi(e) != 0;
-    if (const char* e = getenv("SSDN_EPI_STAGED")) { const int v = atoi(e); if (v == 0) p.epi_staged = (dst.map == MAP_UP2); if (v == 1) p.epi_staged = (dst.map != MAP_NCHW); }
+
   }
   // choose the tap grouping: all taps in one window if it fits in shared memory, else one window per
   // distinct row offset (dy), else one window per tap.
@@ -705,7 +694,7 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     uint32_t plane = (uint32_t)(nbox * box_rows * cw_ch * 4);
     for (int stages = (mode == 0 && !p.wide) ? 2 : 3; stages >= 2; --stages)
     for (int bst = 4; bst >= 2; --bst) {
-      const size_t epi = p.epi_staged ? convk::kEpiWarps * 32 * convk::kStagePitch * sizeof(float) : 0;
+      const size_t epi = convk::kEpiWarps * 32 * convk::kStagePitch * sizeof(float);   // epilogue staging (all destinations)
       size_t need = (size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes + epi + 2048;
       if (need > smem_limit) continue;
       p.epi_off = (uint32_t)((size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes);
@@ -751,6 +740,7 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     }
   }
   if (dst.map != MAP_NCHW && (dst.cvalid % 4 || dst.cpitch % 4 || dst.coff % 4)) return -13;   // float4 stores
+  if ((dst.mask_out || dst.mask_in) && p.n_tiles_n > 1 && N % 32) return -15;                  // mask words are per 32 channels
   // tensor maps.  A: 3-D (channel, flat pixel, plane); the lo plane must follow the hi plane at a constant byte distance.
   const long long plane_stride = (long long)((const char*)a_lo - (const char*)a_v);
   if (plane_stride <= 0 || plane_stride % 16) return -11;

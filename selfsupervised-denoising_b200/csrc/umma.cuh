@@ -64,6 +64,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
 #ifdef UMMA_UNBOUNDED_WAIT
   while (!mbar_try_wait(bar, parity)) {}
 #else
+#pragma unroll 1      // ptxas otherwise unrolls the spin 64x at every call site: the kernels are instruction-cache-bound enough
   for (uint32_t i = 0; i < (1u << 22); ++i)
     if (mbar_try_wait(bar, parity)) return;
   asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(abort_addr), "r"(1u) : "memory");
@@ -72,6 +73,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
 }
 // Simple bounded wait for the probes (returns false on timeout).
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t i = 0; i < (1u << 22); ++i)
     if (mbar_try_wait(bar, parity)) return true;
   return false;
