@@ -23,6 +23,8 @@ struct WgradParams {
   long long k_total;
   int KC, n_kchunks, ksplit, chunks_per_split;
   int n_co_tiles, cout, cin;
+  int m64;             // cout <= 64: MMAs of M = 64 read half the dZ bytes from shared memory (same tensor time, the kernel is
+                       // operand-bandwidth-bound); accumulator row m then lives in TMEM lane (m % 16) + 32 * (m / 16)
   int cin_pitch;       // floats per (tap, co) row of the partial buffer: cin rounded up to 4 so that every row is 16-byte aligned
   int n_ci_blocks, ci_start[4], ci_n[4];
   int nba, nbx;        // 32-channel blocks actually loaded per stage for dZ (<= 4) and X (<= 6)
@@ -117,7 +119,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
       int ks, g, cb, ct; decode(u, ks, g, cb, ct);
       const int c0 = ks * p.chunks_per_split, c1 = min(p.n_kchunks, c0 + p.chunks_per_split);
       const int N = p.ci_n[cb];
-      const uint32_t idesc = umma::make_idesc_tf32(128, N, 1, 1);
+      const uint32_t idesc = umma::make_idesc_tf32(p.m64 ? 64 : 128, N, 1, 1);
       SSDN_TIMED(w_acc, umma::mbar_wait(acc_empty, (it & 1) ^ 1, abort_addr, p.error_flag, 12));
       umma::tc_fence_after();
       uint32_t acc = 0;
@@ -189,7 +191,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
       const int N = p.ci_n[cb];
       SSDN_TIMED(w_accf, umma::mbar_wait(acc_full, it & 1, abort_addr, p.error_flag, 13));
       umma::tc_fence_after();
-      const int co = ct * 128 + ew * 32 + lane;
+      const int co = p.m64 ? (lane < 16 ? ew * 16 + lane : p.cout) : ct * 128 + ew * 32 + lane;
       for (int t = 0; t < p.groups[g].ntaps; ++t) {
         const int tap = p.groups[g].tap_id[t];
         float* dst = p.partial + (((long long)ks * p.ntaps_total + tap) * p.cout + co) * p.cin_pitch + p.ci_start[cb];
@@ -411,6 +413,7 @@ static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const floa
   p.k_total = k_total; p.KC = 32; p.n_kchunks = (int)((k_total + p.KC - 1) / p.KC);
   p.ksplit = ksplit; p.chunks_per_split = (p.n_kchunks + ksplit - 1) / ksplit;
   p.cout = cout; p.cin = cin; p.cin_pitch = (cin + 3) / 4 * 4; p.n_co_tiles = (cout + 127) / 128;
+  p.m64 = (cout <= 64 && !(getenv("SSDN_WGRAD_M64") && atoi(getenv("SSDN_WGRAD_M64")) == 0)) ? 1 : 0;
   // ci blocks: as wide as TMEM allows (3 taps x N <= 512 columns, N <= 256), so that dZ is streamed as few times as possible
   const int cap = wgrad_ci_cap(taps.n);
   p.n_ci_blocks = 0;
