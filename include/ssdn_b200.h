@@ -108,6 +108,18 @@ int ssdn_masked_mse_backward(const float* out, const float* ref, const long long
 int ssdn_adam_step(float* p, const float* g, float* m, float* v, long long count, double lr, double beta1, double beta2, double eps,
                    long long step, double grad_scale, void* stream);
 
+/* ---- on-GPU input pipeline — train.py:756-760 (RandomCrop), datasets/noise_wrapper.py:98-163, utils/noise.py:14-63 ---------
+ * images: DEVICE uint8 cache [n_images][c][h][w] (c <= 4).  Output sample i takes image order[i] (DEVICE int32 [n]) or, with
+ * order == NULL, image (step * n + i) mod n_images; a uniformly random patch x patch crop; clean = u8 / 255 (ToTensor);
+ * noisy = clean + N(0, sigma^2) with sigma = sigma_lo, or U(sigma_lo, sigma_hi) per sample AND channel when
+ * sigma_hi > sigma_lo (the range styles draw per leading axis of a CHW image: noise.py:55-56); clipped to [0, 1] if clip.
+ * Randomness is Philox4x32-10 keyed by seed and indexed by (step, stream_id, sample, pixel): reproducible; stream_id
+ * selects an independent noise realisation of the SAME crops (the Noise2Noise reference).  Outputs dense NCHW fp32:
+ * clean (may be NULL), noisy [n][c][patch][patch], sigma [n][c] (may be NULL).  Statistical parity with the CPU generator. */
+int ssdn_noisy_crops(const unsigned char* images, int n_images, int c, int h, int w, const int* order, int n, int patch,
+                     unsigned long long seed, unsigned long long step, int stream_id, float sigma_lo, float sigma_hi, int clip,
+                     float* clean, float* noisy, float* sigma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,6 @@
 // C-ABI: whole-network forward/backward, pipeline losses, index operators, flat Adam.
 // Everything here is asynchronous on `stream` unless noted.  See include/ssdn_b200.h.
+#include "input_pipeline.cuh"
 #include "loss.cuh"
 #include "net.cuh"
 #include "../../include/ssdn_b200.h"
@@ -237,6 +238,22 @@ extern "C" int ssdn_adam_step(float* p, const float* g, float* m, float* v, long
   const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   lossk::adam_kernel<<<pw::grid_for(count), pw::kBlock, 0, (cudaStream_t)stream>>>(p, g, m, v, count, (float)(lr / bc1), (float)beta1, (float)beta2,
                                                                                   (float)eps, (float)sqrt(bc2), (float)grad_scale);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ on-GPU input pipeline
+extern "C" int ssdn_noisy_crops(const unsigned char* images, int n_images, int c, int h, int w, const int* order, int n, int patch,
+                                unsigned long long seed, unsigned long long step, int stream_id, float sigma_lo, float sigma_hi, int clip,
+                                float* clean, float* noisy, float* sigma, void* stream) {
+  if (!images || !noisy) return fail(-1, "null image cache / output");
+  if (c < 1 || c > 4) return fail(-1, "1..4 image channels are supported");
+  if (n_images <= 0 || n <= 0 || patch <= 0 || patch > h || patch > w) return fail(-1, "patch %d does not fit %dx%d images", patch, h, w);
+  if (sigma_lo < 0.f || sigma_hi < 0.f) return fail(-1, "negative noise level");
+  const long long total = (long long)n * patch * patch;
+  inpk::noisy_crops_kernel<<<pw::grid_for(total), pw::kBlock, 0, (cudaStream_t)stream>>>(
+      images, n_images, c, h, w, order, n, patch, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+      (uint32_t)stream_id, sigma_lo, sigma_hi, clip, clean, noisy, sigma);
   SSDN_CUDA(cudaGetLastError());
   return 0;
 }

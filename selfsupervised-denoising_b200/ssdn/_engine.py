@@ -50,6 +50,8 @@ _SIGNATURES = {
     "ssdn_masked_mse_forward": (_I, [_P, _P, _P, _P] + [_I] * 5 + [_P, _P]),
     "ssdn_masked_mse_backward": (_I, [_P, _P, _P, _I, _P] + [_I] * 4 + [_P, _P]),
     "ssdn_adam_step": (_I, [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _LL, _D, _P]),
+    "ssdn_noisy_crops": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, ctypes.c_ulonglong, ctypes.c_ulonglong, _I, ctypes.c_float, ctypes.c_float, _I,
+                              _P, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
@@ -317,3 +319,22 @@ def profile_records(max_records=512):
     n = min(lib().ssdn_profile_records(buf, max_records), max_records)
     kinds = ("conv_fwd", "conv_dgrad", "wgrad")
     return [(kinds[int(buf[3 * i])], buf[3 * i + 1], buf[3 * i + 2]) for i in range(n)]
+
+
+def noisy_crops(images_u8, n, patch, seed, step, sigma_lo, sigma_hi=None, clip=True, order=None, stream_id=0, want_clean=True):
+    """Random crops of a uint8 image cache [n_images][C][H][W] on the device with synthetic Gaussian noise
+    (include/ssdn_b200.h: ssdn_noisy_crops).  Returns (clean or None, noisy, sigma [n][C])."""
+    if not images_u8.is_cuda or images_u8.dtype != torch.uint8 or images_u8.dim() != 4:
+        raise EngineError("the image cache must be a CUDA uint8 tensor [n_images][C][H][W] (no CPU fallback exists)")
+    images_u8 = images_u8.contiguous()
+    ni, c, h, w = images_u8.shape
+    dev = images_u8.device
+    clean = torch.empty(n, c, patch, patch, device=dev) if want_clean else None
+    noisy = torch.empty(n, c, patch, patch, device=dev)
+    sigma = torch.empty(n, c, device=dev)
+    if order is not None:
+        order = order.to(device=dev, dtype=torch.int32).contiguous()
+    hi = sigma_lo if sigma_hi is None else sigma_hi
+    check(lib().ssdn_noisy_crops(_ptr(images_u8), ni, c, h, w, _ptr(order), n, patch, int(seed), int(step), int(stream_id), float(sigma_lo),
+                                 float(hi), 1 if clip else 0, _ptr(clean), _ptr(noisy), _ptr(sigma), _stream()))
+    return clean, noisy, sigma

@@ -1,0 +1,79 @@
+"""On-GPU input pipeline: random crops of a uint8 image cache resident in HBM, converted to float and
+noised by one CUDA kernel per batch (``ssdn_noisy_crops``), in the ``(input, reference, metadata)`` layout that
+``Denoiser.run_pipeline`` consumes.
+
+Reference: ``train.py:756-760`` (RandomCrop), ``datasets/noise_wrapper.py:98-163`` (prepare_input),
+``utils/noise.py:14-63`` (add_gaussian).  The reference feeds the GPU from 4 PIL / h5py worker processes; at the engine's
+step rate (> 4000 patches/s per GPU) that loader is the bottleneck by orders of magnitude.  Randomness is Philox
+counter-based: batches are a pure function of ``(seed, step)`` - a resumed run only needs the step counter - and parity
+with the CPU generator is statistical, not bit-wise.  Gaussian styles only (``gauss25``, ``gauss5_50``, ``_nc``);
+Noise2Void masking stays on the CPU path."""
+from __future__ import annotations
+
+import re
+from typing import Dict, List
+
+import torch
+
+from ssdn import _engine as E
+from ssdn.datasets.noise_wrapper import NULL_IMAGE, NoisyDataset
+from ssdn.params import NoiseAlgorithm
+
+
+def parse_gaussian_style(style: str):
+    """'gauss25' -> (25/255, 25/255, clip); 'gauss5_50_nc' -> (5/255, 50/255, no clip).  Integers are 8-bit units."""
+    kind = re.findall(r"[a-zA-Z]+", style)[0]
+    if kind != "gauss":
+        raise NotImplementedError("the on-GPU input pipeline implements Gaussian noise styles only")
+    tokens = [t for t in style.replace(kind, "").split("_") if t != ""]
+    clip = "nc" not in tokens
+    tokens = [t for t in tokens if t != "nc"]
+    as_float = any("." in t for t in tokens)
+    vals = [float(t) if as_float else int(t) / 255.0 for t in tokens]
+    if len(vals) == 1:
+        return vals[0], vals[0], clip
+    if len(vals) == 2:
+        return vals[0], vals[1], clip
+    raise ValueError(f"cannot parse noise style '{style}'")
+
+
+class GpuNoisyPatches:
+    """``batch(step)`` -> ``[input, reference, metadata]`` of ``batch_size`` noisy ``patch`` x ``patch`` crops."""
+
+    def __init__(self, images_u8: torch.Tensor, noise_style: str, algorithm: NoiseAlgorithm, patch: int, batch_size: int, seed: int = 0):
+        if not images_u8.is_cuda or images_u8.dtype != torch.uint8 or images_u8.dim() != 4:
+            raise E.EngineError("image cache must be a CUDA uint8 tensor [n_images][C][H][W]")
+        if algorithm == NoiseAlgorithm.NOISE_TO_VOID:
+            raise NotImplementedError("Noise2Void masking is not part of the on-GPU input pipeline")
+        self.images, self.style, self.algorithm = images_u8.contiguous(), noise_style, algorithm
+        self.patch, self.batch_size, self.seed = patch, batch_size, seed
+        self.sigma_lo, self.sigma_hi, self.clip = parse_gaussian_style(noise_style)
+
+    def batch(self, step: int) -> List:
+        M = NoisyDataset.Metadata
+        n, c = self.batch_size, self.images.shape[1]
+        clean, noisy, sigma = E.noisy_crops(self.images, n, self.patch, self.seed, step, self.sigma_lo, self.sigma_hi, self.clip)
+        ranged = self.sigma_hi > self.sigma_lo
+        coeff = sigma.reshape(n, c, 1, 1) if ranged else sigma[:, :1].reshape(n, 1, 1, 1)
+        md: Dict = {M.CLEAN: clean, M.INPUT_NOISE_VALUES: coeff, M.IMAGE_SHAPE: torch.tensor([[c, self.patch, self.patch]] * n),
+                    M.INDEXES: torch.arange(n) + step * n}
+        if self.algorithm == NoiseAlgorithm.NOISE_TO_CLEAN:
+            ref = clean
+            md[M.REFERENCE_NOISE_VALUES] = torch.zeros(n, 1, 1, 1)
+        elif self.algorithm == NoiseAlgorithm.NOISE_TO_NOISE:
+            _, ref, rs = E.noisy_crops(self.images, n, self.patch, self.seed, step, self.sigma_lo, self.sigma_hi, self.clip, stream_id=1,
+                                       want_clean=False)
+            md[M.REFERENCE_NOISE_VALUES] = rs.reshape(n, c, 1, 1) if ranged else rs[:, :1].reshape(n, 1, 1, 1)
+        elif self.algorithm == NoiseAlgorithm.SELFSUPERVISED_DENOISING_MEAN_ONLY:
+            ref = noisy
+            md[M.REFERENCE_NOISE_VALUES] = coeff
+        else:
+            ref = NULL_IMAGE
+            md[M.REFERENCE_NOISE_VALUES] = torch.zeros(n, 1, 1, 1)
+        return [noisy, ref, md]
+
+    def __iter__(self):
+        step = 0
+        while True:
+            yield self.batch(step)
+            step += 1

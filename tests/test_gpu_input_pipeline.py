@@ -1,0 +1,84 @@
+"""GPU: on-GPU input pipeline (ssdn_noisy_crops) - crops are bit-exact copies of the image cache, noise has the reference's
+statistics (utils/noise.py:14-63), batches are a pure function of (seed, step)."""
+import math
+
+import pytest
+import torch
+
+import ssdn
+from ssdn.datasets import GpuNoisyPatches, NoisyDataset
+from ssdn.datasets.gpu_pipeline import parse_gaussian_style
+from ssdn.params import NoiseAlgorithm, PipelineOutput
+from util import make_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _cache(n=6, c=3, h=40, w=48, seed=0):
+    return torch.randint(0, 256, (n, c, h, w), dtype=torch.uint8, generator=torch.Generator().manual_seed(seed))
+
+
+def test_crops_are_exact_and_reproducible(engine):
+    imgs = _cache()
+    cl, no, sg = engine.noisy_crops(imgs.cuda(), 8, 32, seed=7, step=3, sigma_lo=25 / 255, clip=True)
+    cl2, no2, _ = engine.noisy_crops(imgs.cuda(), 8, 32, seed=7, step=3, sigma_lo=25 / 255, clip=True)
+    assert torch.equal(cl, cl2) and torch.equal(no, no2)                      # pure function of (seed, step)
+    _, no3, _ = engine.noisy_crops(imgs.cuda(), 8, 32, seed=7, step=4, sigma_lo=25 / 255, clip=True)
+    assert not torch.equal(no, no3)
+    ref = imgs.float() / 255.0                                                # torchvision ToTensor
+    offsets = set()
+    for i in range(8):
+        img = ref[(3 * 8 + i) % 6]
+        found = [(oy, ox) for oy in range(40 - 32 + 1) for ox in range(48 - 32 + 1) if torch.equal(img[:, oy:oy + 32, ox:ox + 32], cl[i].cpu())]
+        assert len(found) >= 1, i                                             # bit-exact crop of the right image
+        offsets.add(found[0])
+    assert len(offsets) > 3                                                   # crop origins vary between samples
+    assert float(no.min()) >= 0.0 and float(no.max()) <= 1.0                  # clipped
+    assert torch.allclose(sg, torch.full_like(sg, 25 / 255))
+
+
+def test_noise_statistics_match_add_gaussian(engine):
+    imgs = torch.full((2, 3, 96, 96), 128, dtype=torch.uint8)                 # mid-grey: clipping never triggers at sigma 25
+    cl, no, _ = engine.noisy_crops(imgs.cuda(), 64, 64, seed=1, step=0, sigma_lo=25 / 255, clip=False)
+    d = (no - cl).double().cpu()
+    n = d.numel()
+    sigma = 25 / 255
+    assert abs(d.mean().item()) < 5 * sigma / math.sqrt(n)
+    assert abs(d.std().item() / sigma - 1) < 5e-3
+    z = d / sigma
+    assert abs((z ** 4).mean().item() - 3.0) < 0.05 and abs((z ** 3).mean().item()) < 0.02      # Gaussian moments
+    # independent across pixels, channels and samples
+    assert abs((z[:, 0] * z[:, 1]).mean().item()) < 0.01 and abs((z[:, :, :, 1:] * z[:, :, :, :-1]).mean().item()) < 0.01
+    assert abs((z[0] * z[1]).mean().item()) < 0.02
+
+
+def test_range_style_draws_sigma_per_sample_and_channel(engine):
+    lo, hi, clip = parse_gaussian_style("gauss5_50_nc")
+    assert (lo, hi, clip) == (5 / 255, 50 / 255, False) and parse_gaussian_style("gauss25") == (25 / 255, 25 / 255, True)
+    imgs = torch.full((1, 3, 64, 64), 100, dtype=torch.uint8)
+    cl, no, sg = engine.noisy_crops(imgs.cuda(), 32, 64, seed=5, step=9, sigma_lo=lo, sigma_hi=hi, clip=clip)
+    assert float(sg.min()) >= lo and float(sg.max()) <= hi and sg.unique().numel() > 80          # [32][3] distinct levels
+    emp = (no - cl).reshape(32, 3, -1).std(dim=2)
+    assert ((emp / sg - 1).abs() < 0.05).all()                                                  # reported sigma is the one applied
+    assert 20 / 255 < float(sg.mean()) < 35 / 255                                               # U(5, 50) / 255 has mean 27.5 / 255
+
+
+def test_pipeline_batches_feed_the_denoiser(engine):
+    imgs = _cache(n=4, h=64, w=80, seed=3).cuda()
+    gen = GpuNoisyPatches(imgs, "gauss25", NoiseAlgorithm.SELFSUPERVISED_DENOISING, patch=32, batch_size=4, seed=11)
+    data = gen.batch(0)
+    M = NoisyDataset.Metadata
+    assert data[0].shape == (4, 3, 32, 32) and data[2][M.INPUT_NOISE_VALUES].shape == (4, 1, 1, 1) and data[1].numel() == 0
+    den = ssdn.Denoiser(make_cfg("ssdn", "known", 3), device="cuda")
+    out = den.run_pipeline(data)
+    assert torch.isfinite(out[PipelineOutput.LOSS]).all() and out[PipelineOutput.IMG_DENOISED].shape == (4, 3, 32, 32)
+    n2n = GpuNoisyPatches(imgs, "gauss25", NoiseAlgorithm.NOISE_TO_NOISE, patch=32, batch_size=4, seed=11).batch(0)
+    assert torch.equal(n2n[2][M.CLEAN], data[2][M.CLEAN])                     # same crops ...
+    a, b = (n2n[0] - n2n[2][M.CLEAN]), (n2n[1] - n2n[2][M.CLEAN])
+    assert abs(float((a * b).mean()) / float((a * a).mean())) < 0.05          # ... independent noise realisations
+    with pytest.raises(NotImplementedError):
+        GpuNoisyPatches(imgs, "gauss25", NoiseAlgorithm.NOISE_TO_VOID, 32, 4)
+    with pytest.raises(NotImplementedError):
+        GpuNoisyPatches(imgs, "poisson30", NoiseAlgorithm.SELFSUPERVISED_DENOISING, 32, 4)
+    with pytest.raises(ValueError):
+        engine.noisy_crops(imgs, 4, 128, 0, 0, 0.1)                           # patch larger than the images
