@@ -277,19 +277,28 @@ def ssdn_posterior(net_out: torch.Tensor, noisy: torch.Tensor, noise_std: torch.
 
 def ssdn_pipeline(params: Dict[str, torch.Tensor], noisy: torch.Tensor, noise_values: torch.Tensor,
                   sigma_mode: str, est_params: Optional[Dict[str, torch.Tensor]] = None,
-                  est_sigma: Optional[torch.Tensor] = None):
-    """denoiser.py:182-397, Gaussian styles.  sigma_mode in {"known", "const", "var"}."""
+                  est_sigma: Optional[torch.Tensor] = None, noise_style: str = "gauss"):
+    """denoiser.py:182-397.  sigma_mode in {"known", "const", "var"}; noise_style "gauss..." or "poisson..." (the
+    signal-dependent approximation of :285-297: sigma = sqrt(max(mu, 1e-3) / lambda) per pixel and channel when lambda is
+    known, sqrt(max(mu, 1e-3) * estimate) otherwise)."""
     c = noisy.shape[1]
     net_out = noise_network_forward(params, noisy, blindspot=True)
     if sigma_mode == "known":
-        noise_std = torch.max(noise_values, torch.tensor(1e-3, dtype=noise_values.dtype))
+        est = None
     elif sigma_mode == "const":
-        noise_std = softplus_sigma(est_sigma)
+        est = softplus_sigma(est_sigma)
     elif sigma_mode == "var":
         e = noise_network_forward(est_params, noisy, blindspot=False)
-        noise_std = softplus_sigma(torch.mean(e, dim=(2, 3), keepdim=True))
+        est = softplus_sigma(torch.mean(e, dim=(2, 3), keepdim=True))
     else:
         raise NotImplementedError(sigma_mode)
+    if noise_style.startswith("gauss"):
+        noise_std = torch.max(noise_values, torch.tensor(1e-3, dtype=noise_values.dtype)) if est is None else est
+    elif noise_style.startswith("poisson"):
+        base = torch.max(net_out[:, :c], torch.tensor(1e-3, dtype=net_out.dtype))
+        noise_std = (base / noise_values) ** 0.5 if est is None else (base * est) ** 0.5
+    else:
+        raise NotImplementedError(noise_style)
     out = ssdn_posterior(net_out, noisy, noise_std, sigma_known=(sigma_mode == "known"))
     out["net_out"] = net_out
     return out

@@ -33,6 +33,9 @@ PIPELINE_CASES = OrderedDict(
     ssdn_var_rgb_perchannel=("ssdn", "var", 3, 2, 32),
     ssdn_known_mono=("ssdn", "known", 1, 2, 32),
     ssdn_var_mono=("ssdn", "var", 1, 2, 32),
+    ssdn_known_rgb_poisson=("ssdn", "known", 3, 2, 32),
+    ssdn_const_rgb_poisson=("ssdn", "const", 3, 2, 32),
+    ssdn_const_mono_poisson=("ssdn", "const", 1, 2, 32),
     n2c_mono=("n2c", None, 1, 4, 32),
     n2v_rgb=("n2v", None, 3, 2, 32),
 )
@@ -67,7 +70,10 @@ def pipeline_inputs(name):
     d = dict(algorithm=algo, sigma_mode=mode, channels=c, clean=clean, noisy=noisy)
     if algo == "ssdn":
         d["params"] = make_params(c, c + c * (c + 1) // 2, True, seed)
-        if name.endswith("perchannel"):
+        if name.endswith("poisson"):
+            d["noise_style"] = "poisson30"
+            d["noise_values"] = torch.full((n, 1, 1, 1), 30.0) if mode == "known" else torch.full((n, 1, 1, 1), 25.0 / 255.0)
+        elif name.endswith("perchannel"):
             d["noise_values"] = (torch.rand(n, c, 1, 1, generator=g) * 45 + 5) / 255.0
         else:
             d["noise_values"] = torch.full((n, 1, 1, 1), 25.0 / 255.0)
