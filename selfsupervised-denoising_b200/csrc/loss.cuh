@@ -52,22 +52,33 @@ __device__ __forceinline__ float block_sum(float v, float* sm) {
 
 // ---------------------------------------------------------------- SSDN posterior / NLL, forward
 // grid = (blocks_per_sample, N).  partial[n][blk] = sum of per-pixel losses of that strip.
+// Noise model.  Gaussian (poisson == 0): sigma_c is a per-sample constant, sigma_map(raw).  Poisson (denoiser.py:285-297,
+// the signal-dependent approximation of Hasinoff 2012): sigma_c = sqrt(max(mu_c, 1e-3) * k_c) per pixel, with k_c = 1 / raw
+// (raw = the known lambda) or k_c = softplus(raw - 4) + 1e-3 (learned); the per-pixel noise level is then an OUTPUT of the
+// forward kernel (noise_std_px, [n][hw]) and the loss gradient reaches mu through sigma as well.
+__device__ __forceinline__ float noise_coeff(float raw, int known, int poisson) {
+  if (!poisson) return sigma_map(raw, known);
+  return known ? 1.0f / raw : sigma_map(raw, 0);
+}
+
 template <int C>
 __global__ void posterior_fwd_kernel(const float* __restrict__ net_out, const float* __restrict__ noisy,
-                                     const float* __restrict__ sigma_raw, int cs, int known, int HW,
-                                     float* __restrict__ pme, float* __restrict__ model_std, float* __restrict__ partial) {
+                                     const float* __restrict__ sigma_raw, int cs, int known, int poisson, int HW,
+                                     float* __restrict__ pme, float* __restrict__ model_std, float* __restrict__ noise_std_px,
+                                     float* __restrict__ partial) {
   __shared__ float sm[32];
   constexpr int CO = C + C * (C + 1) / 2;
   const int n = blockIdx.y;
   const float* no = net_out + (long long)n * CO * HW;
   const float* yy = noisy + (long long)n * C * HW;
-  float sg[3];
+  float sg[3], kc[3];
 #pragma unroll
-  for (int c = 0; c < C; ++c) sg[c] = sigma_map(sigma_raw[n * cs + (cs == 1 ? 0 : c)], known);
+  for (int c = 0; c < C; ++c) { kc[c] = noise_coeff(sigma_raw[n * cs + (cs == 1 ? 0 : c)], known, poisson); sg[c] = kc[c]; }
   float acc = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     if (C == 1) {
       const float mu = no[i], a = no[HW + i], y = yy[i];
+      if (poisson) { sg[0] = sqrtf(fmaxf(mu, 1e-3f) * kc[0]); if (noise_std_px) noise_std_px[(long long)n * HW + i] = sg[0]; }
       const float sx = a * a, sn = sg[0] * sg[0], sy = sx + sn, d = y - mu;
       float l = d * d / sy + logf(sy);
       if (!known) l -= 0.1f * sg[0];
@@ -78,6 +89,11 @@ __global__ void posterior_fwd_kernel(const float* __restrict__ net_out, const fl
       double mu[3], y[3], a[6];
 #pragma unroll
       for (int c = 0; c < 3; ++c) { mu[c] = no[c * HW + i]; y[c] = yy[c * HW + i]; }
+      if (poisson) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sg[c] = sqrtf(fmaxf((float)mu[c], 1e-3f) * kc[c]);
+        if (noise_std_px) noise_std_px[(long long)n * HW + i] = (float)pow((double)sg[0] * sg[0] * sg[1] * sg[1] * sg[2] * sg[2], 1.0 / 6.0);
+      }
 #pragma unroll
       for (int c = 0; c < 6; ++c) a[c] = no[(3 + c) * HW + i];
       // Sigma_x = U U^T with U = [[a0,a1,a2],[0,a3,a4],[0,0,a5]]   (denoiser.py:246-255)
@@ -116,6 +132,7 @@ __global__ void posterior_fwd_kernel(const float* __restrict__ net_out, const fl
 // loss[n] = sum(partial[n][:]) / HW ; noise_std_out[n] = (prod sigma_c^2)^(1/6) (RGB) or sigma (mono)
 __global__ void posterior_finalize_kernel(const float* __restrict__ partial, int nblk, int HW, const float* __restrict__ sigma_raw,
                                           int cs, int known, int C, int N, float* __restrict__ loss, float* __restrict__ noise_std) {
+  // noise_std == NULL for Poisson noise (per-pixel levels were written by the forward kernel)
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
@@ -135,8 +152,10 @@ __global__ void posterior_finalize_kernel(const float* __restrict__ partial, int
 // d(net_out) for  L = sum_n gloss[n] * loss[n];  dsig_partial[n][blk][c] = strip sums of dL/d(sigma_c)
 template <int C>
 __global__ void posterior_bwd_kernel(const float* __restrict__ net_out, const float* __restrict__ noisy,
-                                     const float* __restrict__ sigma_raw, int cs, int known, int HW,
+                                     const float* __restrict__ sigma_raw, int cs, int known, int poisson, int HW,
                                      const float* __restrict__ gloss, float* __restrict__ dnet, float* __restrict__ dsig_partial) {
+  // ds[c] accumulates d(loss)/d(sigma_c) (Gaussian; the -0.1 regulariser is added by the finalize kernel) or
+  // d(loss)/d(k_c) including the regulariser (Poisson: it depends on the pixel)
   __shared__ float sm[32];
   constexpr int CO = C + C * (C + 1) / 2;
   const int n = blockIdx.y;
@@ -144,22 +163,35 @@ __global__ void posterior_bwd_kernel(const float* __restrict__ net_out, const fl
   const float* yy = noisy + (long long)n * C * HW;
   float* dn = dnet + (long long)n * CO * HW;
   const float scale = gloss[n] / (float)HW;
-  float sg[3];
+  float sg[3], kc[3];
 #pragma unroll
-  for (int c = 0; c < C; ++c) sg[c] = sigma_map(sigma_raw[n * cs + (cs == 1 ? 0 : c)], known);
+  for (int c = 0; c < C; ++c) { kc[c] = noise_coeff(sigma_raw[n * cs + (cs == 1 ? 0 : c)], known, poisson); sg[c] = kc[c]; }
   float ds[3] = {0.f, 0.f, 0.f};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     if (C == 1) {
       const float mu = no[i], a = no[HW + i], y = yy[i];
+      const float base = fmaxf(mu, 1e-3f);
+      if (poisson) sg[0] = sqrtf(base * kc[0]);
       const float sy = a * a + sg[0] * sg[0], d = y - mu;
       const float dsy = -d * d / (sy * sy) + 1.f / sy;
-      dn[i] = scale * (-2.f * d / sy);
+      float dmu = -2.f * d / sy;
+      if (poisson) {
+        const float reg = known ? 0.f : 0.1f / (2.f * sg[0]);      // d(-0.1 sigma)/d(sigma^2)
+        if (mu > 1e-3f) dmu += (dsy - reg) * kc[0];
+        ds[0] += scale * (dsy - reg) * base;
+      } else {
+        ds[0] += scale * dsy * 2.f * sg[0];
+      }
+      dn[i] = scale * dmu;
       dn[HW + i] = scale * dsy * 2.f * a;
-      ds[0] += scale * dsy * 2.f * sg[0];
     } else {
       double mu[3], y[3], a[6];
 #pragma unroll
       for (int c = 0; c < 3; ++c) { mu[c] = no[c * HW + i]; y[c] = yy[c * HW + i]; }
+      if (poisson) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sg[c] = sqrtf(fmaxf((float)mu[c], 1e-3f) * kc[c]);
+      }
 #pragma unroll
       for (int c = 0; c < 6; ++c) a[c] = no[(3 + c) * HW + i];
       Sym3 sy;
@@ -174,7 +206,17 @@ __global__ void posterior_bwd_kernel(const float* __restrict__ net_out, const fl
       G.a00 = ld * syi.a00 - 0.5 * v0 * v0; G.a01 = ld * syi.a01 - 0.5 * v0 * v1; G.a02 = ld * syi.a02 - 0.5 * v0 * v2;
       G.a11 = ld * syi.a11 - 0.5 * v1 * v1; G.a12 = ld * syi.a12 - 0.5 * v1 * v2; G.a22 = ld * syi.a22 - 0.5 * v2 * v2;
       const double s = scale;
-      dn[i] = (float)(-s * v0); dn[HW + i] = (float)(-s * v1); dn[2 * HW + i] = (float)(-s * v2);
+      double dmu[3] = {-v0, -v1, -v2};
+      if (poisson) {
+        const double gd[3] = {G.a00, G.a11, G.a22};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double reg = known ? 0.0 : (0.1 / 3.0) / (2.0 * sg[c]);       // d(-0.1 mean_c sigma_c)/d(sigma_c^2)
+          if (mu[c] > 1e-3) dmu[c] += (gd[c] - reg) * kc[c];
+          ds[c] += (float)(s * (gd[c] - reg) * fmax(mu[c], 1e-3));
+        }
+      }
+      dn[i] = (float)(s * dmu[0]); dn[HW + i] = (float)(s * dmu[1]); dn[2 * HW + i] = (float)(s * dmu[2]);
       // dL/dU = 2 G U restricted to the upper triangle, U = [[a0,a1,a2],[0,a3,a4],[0,0,a5]]
       dn[3 * HW + i] = (float)(2.0 * s * (G.a00 * a[0]));
       dn[4 * HW + i] = (float)(2.0 * s * (G.a00 * a[1] + G.a01 * a[3]));
@@ -182,7 +224,7 @@ __global__ void posterior_bwd_kernel(const float* __restrict__ net_out, const fl
       dn[6 * HW + i] = (float)(2.0 * s * (G.a01 * a[1] + G.a11 * a[3]));
       dn[7 * HW + i] = (float)(2.0 * s * (G.a01 * a[2] + G.a11 * a[4] + G.a12 * a[5]));
       dn[8 * HW + i] = (float)(2.0 * s * (G.a02 * a[2] + G.a12 * a[4] + G.a22 * a[5]));
-      ds[0] += (float)(s * 2.0 * G.a00 * sg[0]); ds[1] += (float)(s * 2.0 * G.a11 * sg[1]); ds[2] += (float)(s * 2.0 * G.a22 * sg[2]);
+      if (!poisson) { ds[0] += (float)(s * 2.0 * G.a00 * sg[0]); ds[1] += (float)(s * 2.0 * G.a11 * sg[1]); ds[2] += (float)(s * 2.0 * G.a22 * sg[2]); }
     }
   }
   if (dsig_partial) {
@@ -196,13 +238,15 @@ __global__ void posterior_bwd_kernel(const float* __restrict__ net_out, const fl
 
 // d(sigma_raw)[n][c'] from the strip partials: adds the -0.1 regulariser and the softplus chain rule.
 __global__ void posterior_bwd_finalize_kernel(const float* __restrict__ dsig_partial, int nblk, const float* __restrict__ sigma_raw,
-                                              int cs, int C, int N, const float* __restrict__ gloss, float* __restrict__ dsigma_raw) {
+                                              int cs, int C, int N, int poisson, const float* __restrict__ gloss,
+                                              float* __restrict__ dsigma_raw) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * cs) return;
   const int n = idx / cs, c = idx % cs;
   float s = 0.f;
-  if (cs == 1) { for (int b = 0; b < nblk; ++b) for (int k = 0; k < C; ++k) s += dsig_partial[(n * nblk + b) * 3 + k]; s -= 0.1f * gloss[n]; }
-  else { for (int b = 0; b < nblk; ++b) s += dsig_partial[(n * nblk + b) * 3 + c]; s -= 0.1f * gloss[n] / (float)C; }
+  const float reg = poisson ? 0.f : 0.1f * gloss[n];      // Poisson: the regulariser is per pixel, already in the partials
+  if (cs == 1) { for (int b = 0; b < nblk; ++b) for (int k = 0; k < C; ++k) s += dsig_partial[(n * nblk + b) * 3 + k]; s -= reg; }
+  else { for (int b = 0; b < nblk; ++b) s += dsig_partial[(n * nblk + b) * 3 + c]; s -= reg / (float)C; }
   dsigma_raw[idx] = s * sigma_map_grad(sigma_raw[idx]);
 }
 

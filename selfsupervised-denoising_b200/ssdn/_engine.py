@@ -41,8 +41,8 @@ _SIGNATURES = {
     "ssdn_rot4_stack": (_I, [_P, _P] + [_I] * 4 + [_P]),
     "ssdn_shift_unrot_concat": (_I, [_P, _P] + [_I] * 4 + [_P]),
     "ssdn_loss_workspace_bytes": (_Z, [_I, _I]),
-    "ssdn_posterior_forward": (_I, [_P, _P, _P, _P] + [_I] * 6 + [_P, _P, _P, _P, _P]),
-    "ssdn_posterior_backward": (_I, [_P, _P, _P, _P, _P] + [_I] * 6 + [_P, _P, _P]),
+    "ssdn_posterior_forward": (_I, [_P, _P, _P, _P] + [_I] * 7 + [_P, _P, _P, _P, _P]),
+    "ssdn_posterior_backward": (_I, [_P, _P, _P, _P, _P] + [_I] * 7 + [_P, _P, _P]),
     "ssdn_spatial_mean_forward": (_I, [_P, _I, _I, _P, _P]),
     "ssdn_spatial_mean_backward": (_I, [_P, _I, _I, _P, _P]),
     "ssdn_mse_forward": (_I, [_P, _P, _P, _I, _I, _P, _P]),
@@ -225,28 +225,30 @@ def _loss_ws(n, c, device):
     return _workspace(lib().ssdn_loss_workspace_bytes(n, c), device)
 
 
-def posterior_forward(net_out, noisy, sigma_raw, sigma_known):
+def posterior_forward(net_out, noisy, sigma_raw, sigma_known, poisson=False):
+    """poisson: sigma_raw is the known lambda (sigma_known) or the raw estimate of the per-unit-signal variance; the noise
+    level is then per pixel and noise_std comes back as [n][h][w] instead of [n][1][1] (denoiser.py:285-297, :375-380)."""
     n, c, h, w = noisy.shape
     cs = sigma_raw.numel() // n
     dev = noisy.device
     pme = torch.empty_like(noisy)
     loss = torch.empty(n, 1, device=dev)
     model_std = torch.empty(n, h, w, device=dev)
-    noise_std = torch.empty(n, 1, 1, device=dev)
+    noise_std = torch.empty(n, h, w, device=dev) if poisson else torch.empty(n, 1, 1, device=dev)
     ws = _loss_ws(n, c, dev)
-    check(lib().ssdn_posterior_forward(_ptr(ws), _ptr(net_out), _ptr(noisy), _ptr(sigma_raw), n, c, h, w, cs, int(sigma_known),
+    check(lib().ssdn_posterior_forward(_ptr(ws), _ptr(net_out), _ptr(noisy), _ptr(sigma_raw), n, c, h, w, cs, int(sigma_known), int(poisson),
                                        _ptr(pme), _ptr(loss), _ptr(model_std), _ptr(noise_std), _stream()))
     return pme, loss, model_std, noise_std
 
 
-def posterior_backward(net_out, noisy, sigma_raw, gloss, sigma_known):
+def posterior_backward(net_out, noisy, sigma_raw, gloss, sigma_known, poisson=False):
     n, c, h, w = noisy.shape
     cs = sigma_raw.numel() // n
     dnet = torch.empty_like(net_out)
     dsig = None if sigma_known else torch.empty_like(sigma_raw)
     ws = _loss_ws(n, c, noisy.device)
     check(lib().ssdn_posterior_backward(_ptr(ws), _ptr(net_out), _ptr(noisy), _ptr(sigma_raw), _ptr(gloss), n, c, h, w, cs,
-                                        int(sigma_known), _ptr(dnet), _ptr(dsig), _stream()))
+                                        int(sigma_known), int(poisson), _ptr(dnet), _ptr(dsig), _stream()))
     return dnet, dsig
 
 

@@ -193,8 +193,9 @@ class Denoiser(nn.Module):
         assert c in [1, 3]
         if self.cfg[ConfigValue.DIAGONAL_COVARIANCE]:
             raise NotImplementedError("diagonal covariance is not implemented by the B200 engine")
-        if not style.startswith("gauss"):
-            raise NotImplementedError("only Gaussian noise styles are implemented by the B200 engine")
+        if not (style.startswith("gauss") or style.startswith("poisson")):
+            raise NotImplementedError("Noise type not supported")
+        poisson = style.startswith("poisson")
         n = noisy.shape[0]
         est_stream = None
         if mode == NoiseValue.UNKNOWN_VARIABLE and noisy.is_cuda:
@@ -228,13 +229,15 @@ class Denoiser(nn.Module):
             stat_shape = (n, 1, 1)
         else:
             raise NotImplementedError("Unsupported noise value mode")
-        pme, loss, model_std, noise_std = PosteriorFunction.apply(net_out, noisy, sigma_raw, mode == NoiseValue.KNOWN)
+        pme, loss, model_std, noise_std = PosteriorFunction.apply(net_out, noisy, sigma_raw, mode == NoiseValue.KNOWN, poisson)
+        if poisson:             # signal-dependent noise: the level is per pixel (denoiser.py:378-380 -> N x H x W)
+            stat_shape = tuple(noise_std.shape)
         return {
             PipelineOutput.INPUTS: data,
             PipelineOutput.IMG_MU: net_out[:, 0:c, ...],
             PipelineOutput.IMG_DENOISED: pme,
             PipelineOutput.LOSS: loss,
-            PipelineOutput.NOISE_STD_DEV: noise_std[: stat_shape[0]].reshape(stat_shape),
+            PipelineOutput.NOISE_STD_DEV: noise_std if poisson else noise_std[: stat_shape[0]].reshape(stat_shape),
             PipelineOutput.MODEL_STD_DEV: model_std,
         }
 

@@ -33,11 +33,12 @@ PIPELINE_CASES = OrderedDict(
     ssdn_var_rgb_perchannel=("ssdn", "var", 3, 2, 32),
     ssdn_known_mono=("ssdn", "known", 1, 2, 32),
     ssdn_var_mono=("ssdn", "var", 1, 2, 32),
+    n2c_mono=("n2c", None, 1, 4, 32),
+    n2v_rgb=("n2v", None, 3, 2, 32),
+    # appended (seeds are 200 + position): Poisson noise, denoiser.py:285-297
     ssdn_known_rgb_poisson=("ssdn", "known", 3, 2, 32),
     ssdn_const_rgb_poisson=("ssdn", "const", 3, 2, 32),
     ssdn_const_mono_poisson=("ssdn", "const", 1, 2, 32),
-    n2c_mono=("n2c", None, 1, 4, 32),
-    n2v_rgb=("n2v", None, 3, 2, 32),
 )
 
 

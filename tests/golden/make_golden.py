@@ -92,11 +92,11 @@ def networks():
 
 
 # ------------------------------------------------------------------ pipelines
-def make_cfg(algo, mode, channels):
+def make_cfg(algo, mode, channels, style="gauss25"):
     cfg = ssdn.cfg.base()
     cfg[ConfigValue.ALGORITHM] = {"ssdn": NoiseAlgorithm.SELFSUPERVISED_DENOISING, "n2c": NoiseAlgorithm.NOISE_TO_CLEAN,
                                   "n2n": NoiseAlgorithm.NOISE_TO_NOISE, "n2v": NoiseAlgorithm.NOISE_TO_VOID}[algo]
-    cfg[ConfigValue.NOISE_STYLE] = "gauss25"
+    cfg[ConfigValue.NOISE_STYLE] = style
     cfg[ConfigValue.NOISE_VALUE] = {"known": NoiseValue.KNOWN, "const": NoiseValue.UNKNOWN_CONSTANT,
                                     "var": NoiseValue.UNKNOWN_VARIABLE, None: NoiseValue.KNOWN}[mode]
     cfg[ConfigValue.IMAGE_CHANNELS] = channels
@@ -105,7 +105,7 @@ def make_cfg(algo, mode, channels):
 
 
 def ref_denoiser(d):
-    den = Denoiser(make_cfg(d["algorithm"], d["sigma_mode"], d["channels"]), device="cpu")
+    den = Denoiser(make_cfg(d["algorithm"], d["sigma_mode"], d["channels"], d.get("noise_style", "gauss25")), device="cpu")
     load_into(den.get_model(Denoiser.MODEL, parallelised=False), d["params"])
     if "est_params" in d:
         load_into(den.get_model(Denoiser.SIGMA_ESTIMATOR, parallelised=False), d["est_params"])
@@ -130,7 +130,7 @@ def oracle_run(d):
     ep = {k: v.clone().requires_grad_(True) for k, v in d["est_params"].items()} if "est_params" in d else None
     es = d["est_sigma"].clone().requires_grad_(True) if "est_sigma" in d else None
     if d["algorithm"] == "ssdn":
-        out = O.ssdn_pipeline(p, d["noisy"], d["noise_values"], d["sigma_mode"], ep, es)
+        out = O.ssdn_pipeline(p, d["noisy"], d["noise_values"], d["sigma_mode"], ep, es, noise_style=d.get("noise_style", "gauss"))
     elif d["algorithm"] == "n2v":
         out = O.mask_mse_pipeline(p, d["noisy"], d["ref"], d["coords"])
     else:
@@ -139,8 +139,10 @@ def oracle_run(d):
     return out, p, ep, es
 
 
-def pipelines():
+def pipelines(only=None):
     for name in C.PIPELINE_CASES:
+        if only and only not in name:
+            continue
         d = C.pipeline_inputs(name)
         den = ref_denoiser(d)
         den.train()
@@ -234,6 +236,9 @@ def training_trajectory():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--pipelines":      # regenerate only the pipeline cases whose name contains argv[2]
+        pipelines(sys.argv[2])
+        sys.exit(0)
     index_ops()
     optimiser()
     networks()

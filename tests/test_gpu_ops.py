@@ -93,6 +93,38 @@ def test_posterior_forward_backward(engine, c, cs, known):
         assert dsig is None
 
 
+@pytest.mark.parametrize("c,cs,known", [(3, 1, True), (3, 1, False), (3, 3, False), (1, 1, True), (1, 1, False)])
+def test_posterior_poisson_forward_backward(engine, c, cs, known):
+    """Poisson noise model (denoiser.py:285-297): sigma = sqrt(max(mu, 1e-3) / lambda) or sqrt(max(mu, 1e-3) * estimate) per
+    pixel; values, the per-pixel noise level and the gradients (through sigma into mu and into the estimate) vs autograd
+    of the oracle formulation in fp64.  mu straddles the 1e-3 clamp."""
+    gen = torch.Generator().manual_seed(40 + c + cs)
+    n, h = 3, 32
+    co = c + c * (c + 1) // 2
+    net_out = torch.randn(n, co, h, h, generator=gen) * 0.3
+    net_out[:, :c] = torch.rand(n, c, h, h, generator=gen) * 0.9 - 0.05      # means mostly in (0, 0.85), some below the clamp
+    net_out[:, c:] += 0.5
+    noisy = torch.rand(n, c, h, h, generator=gen)
+    raw = (torch.rand(n, cs, 1, 1, generator=gen) * 40 + 10) if known else (torch.rand(n, cs, 1, 1, generator=gen) * 2 + 1.0)
+    gloss = torch.rand(n, 1, generator=gen)
+    no = net_out.double().requires_grad_(True)
+    rw = raw.double().requires_grad_(True)
+    base = torch.max(no[:, :c], torch.tensor(1e-3, dtype=torch.float64))
+    sig = (base / rw) ** 0.5 if known else (base * O.softplus_sigma(rw)) ** 0.5
+    ref = O.ssdn_posterior(no, noisy.double(), sig, known)
+    (ref["loss"] * gloss.double()).sum().backward()
+    pme, loss, mstd, nstd = engine.posterior_forward(net_out.cuda(), noisy.cuda(), raw.reshape(n, cs).cuda(), known, poisson=True)
+    assert nstd.shape == (n, h, h)
+    assert rel(loss, ref["loss"]) < 1e-5 and rel(pme, ref["pme"]) < 1e-4 and rel(mstd, ref["model_std"]) < 1e-4
+    assert rel(nstd, ref["noise_std"]) < 1e-5
+    dnet, dsig = engine.posterior_backward(net_out.cuda(), noisy.cuda(), raw.reshape(n, cs).cuda(), gloss.reshape(-1).cuda(), known, poisson=True)
+    assert rel(dnet, no.grad) < 1e-4
+    if not known:
+        assert rel(dsig.reshape(-1), rw.grad.reshape(-1)) < 1e-4
+    else:
+        assert dsig is None
+
+
 def test_mse_and_masked_mse(engine):
     gen = torch.Generator().manual_seed(31)
     a, b = torch.rand(4, 3, 32, 32, generator=gen), torch.rand(4, 3, 32, 32, generator=gen)

@@ -28,7 +28,13 @@ def test_pipeline_outputs_and_gradients(engine, name):
     assert out[PipelineOutput.LOSS].shape == gold["loss"].shape
     if d["algorithm"] == "ssdn":
         assert rel(out[PipelineOutput.IMG_MU], gold["mu"]) < TOL
-        assert rel(out[PipelineOutput.NOISE_STD_DEV].reshape(-1), gold["noise_std"].reshape(-1)) < TOL
+        if d.get("noise_style", "gauss").startswith("poisson"):
+            # sigma = sqrt(max(mu, 1e-3) * k) per pixel: the 4e-5 forward error of mu is amplified by 1 / (2 mu) where the
+            # (untrained) mean is small - held to the exact result within the fp32 reference's own band, floor 5e-4
+            ok, errs = as_accurate_as_reference(out[PipelineOutput.NOISE_STD_DEV], o32["noise_std"], o64["noise_std"], slack=1.0, floor=5e-4)
+            assert ok, errs
+        else:
+            assert rel(out[PipelineOutput.NOISE_STD_DEV].reshape(-1), gold["noise_std"].reshape(-1)) < TOL
         assert out[PipelineOutput.NOISE_STD_DEV].shape == gold["noise_std"].shape
         assert out[PipelineOutput.MODEL_STD_DEV].shape == gold["model_std"].shape
         # posterior mean / model std invert or take the determinant of Sigma_x, near-singular for an untrained net:
@@ -47,14 +53,18 @@ def test_pipeline_outputs_and_gradients(engine, name):
     main = den.get_model(ssdn.Denoiser.MODEL, False)
     for k, p in main.named_parameters():
         assert rel_l2(p.grad, g32[k]) < 2e-2, k
-    assert rel(dict(main.named_parameters())["output_conv.weight"].grad, gold["g_out_w"]) < 2e-3
-    assert rel(dict(main.named_parameters())["output_conv.bias"].grad, gold["g_out_b"]) < 1e-3
+    # Poisson: d(sigma^2)/d(mu) = k * [mu > 1e-3] and the 1 / (2 sigma) regulariser term amplify the forward error of the
+    # small means of an untrained network (the kernels themselves match autograd to 1e-4 on identical inputs:
+    # test_posterior_poisson_forward_backward)
+    tol_w, tol_b = (1e-2, 1e-2) if d.get("noise_style", "gauss").startswith("poisson") else (2e-3, 1e-3)
+    assert rel(dict(main.named_parameters())["output_conv.weight"].grad, gold["g_out_w"]) < tol_w
+    assert rel(dict(main.named_parameters())["output_conv.bias"].grad, gold["g_out_b"]) < tol_b
     if ge64 is not None:
         est = den.get_model(ssdn.Denoiser.SIGMA_ESTIMATOR, False)
         for k, p in est.named_parameters():
             assert rel_l2(p.grad, ge32[k]) < 2e-2, ("estimator", k)
     if gs64 is not None:
-        assert rel(den.l_params[ssdn.Denoiser.ESTIMATED_SIGMA].grad, gold["g_est_sigma"]) < TOL
+        assert rel(den.l_params[ssdn.Denoiser.ESTIMATED_SIGMA].grad, gold["g_est_sigma"]) < (1e-3 if d.get("noise_style", "gauss").startswith("poisson") else TOL)
 
 
 def test_training_trajectory_matches_reference(engine):
