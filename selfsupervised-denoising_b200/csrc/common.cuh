@@ -25,6 +25,14 @@
 
 #define SSDN_LRELU_SLOPE 0.1f
 
+// The tensor core's fp32 accumulator TRUNCATES (rounds toward zero): every tcgen05.mma accumulate step shrinks the magnitude
+// of the running sum by about half an ulp, so a 3xTF32 result carries a BIAS of -1.5e-8 x (number of MMA instructions per
+// output) relative to its magnitude - measured, stable to +-5 % across layer shapes and zero-mean data
+// (tests/dev_conv_accuracy.py, profiles/r01_conv_accuracy.log): -4.9e-6 for a 96->96 3x3 layer, 1e-4 once compounded over
+// the 20 layers.  The epilogues multiply by 1 + SSDN_ACC_BETA * n_mma: the remaining error is the zero-mean part (half the
+// rms per layer, and it compounds as a square root instead of linearly).  SSDN_ACC_COMP=0 disables it (to re-measure).
+#define SSDN_ACC_BETA 1.525e-8f
+
 struct Geom {            // geometry of one padded-flat tensor
   int B, H, W;           // images, height, width
   int P, S;              // row pitch (W+1 or W), image stride in flat pixels

@@ -43,6 +43,7 @@ struct ConvParams {
   int tap_step;       //    (+1 forward, -1 data-gradient): the MMA warp then issues 3 x T x 6 MMAs per barrier wait
   uint32_t a_plane_bytes, b_stage_bytes;   // smem bytes of one A plane of one stage / of one B stage
   uint32_t epi_off;   // staged epilogue: byte offset of the staging area (4 warps x 32 pixels x 36 floats) in dynamic smem
+  float acc_comp;     // 1 + SSDN_ACC_BETA x (MMA instructions accumulated into one output): truncation-bias compensation
   int epi_split;      // 1: both epilogue warps of a TMEM lane quadrant work (alternate slices) - epilogue-bound layers; 0: one warp
                       //    per quadrant, the other four exit at once (they would only take issue slots and shared-memory
                       //    bandwidth from an MMA-bound layer)
@@ -467,7 +468,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (cg0 < d.cvalid) {
               float f[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) * p.acc_comp;
               if (d.flags & EP_BIAS) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -659,6 +660,11 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     if (p.wide && e && atoi(e) == 3) p.pair = 0;   // ablation: pairs on the 3x3 layers only
   }
   p.b_stage_bytes = (uint32_t)(p.bg * 2 * (p.pair ? N / 2 : N) * cw_ch * 4);   // per CTA
+  {
+    const int ksteps = p.wide ? 4 * p.n_chunks : 2 * (p.n_chunks - 1) + p.ksteps_last;
+    const bool on = !(getenv("SSDN_ACC_COMP") && atoi(getenv("SSDN_ACC_COMP")) == 0);
+    p.acc_comp = on ? 1.0f + SSDN_ACC_BETA * (float)(ksteps * taps.n * 3) : 1.0f;
+  }
   // epilogue mode: straight-from-register stores cost the load/store unit ~2800 clk per 32-channel slice of a tile
   // (32 line fragments per instruction); stage through shared memory when the tile's MMA time cannot hide that
   {

@@ -23,6 +23,7 @@ struct WgradParams {
   long long k_total;
   int KC, n_kchunks, ksplit, chunks_per_split;
   int n_co_tiles, cout, cin;
+  float acc_beta;      // SSDN_ACC_BETA or 0: truncation-bias compensation of the accumulators (common.cuh)
   int m64;             // cout <= 64: MMAs of M = 64 read half the dZ bytes from shared memory (same tensor time, the kernel is
                        // operand-bandwidth-bound); accumulator row m then lives in TMEM lane (m % 16) + 32 * (m / 16)
   int cin_pitch;       // floats per (tap, co) row of the partial buffer: cin rounded up to 4 so that every row is 16-byte aligned
@@ -192,6 +193,9 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
       SSDN_TIMED(w_accf, umma::mbar_wait(acc_full, it & 1, abort_addr, p.error_flag, 13));
       umma::tc_fence_after();
       const int co = p.m64 ? (lane < 16 ? ew * 16 + lane : p.cout) : ct * 128 + ew * 32 + lane;
+      // every accumulator of this unit took (K chunks of the split) x 4 k-steps x 3 products accumulate steps
+      const int kc0 = ks * p.chunks_per_split, kc1 = min(p.n_kchunks, kc0 + p.chunks_per_split);
+      const float comp = 1.0f + p.acc_beta * (float)((kc1 - kc0) * 12);
       for (int t = 0; t < p.groups[g].ntaps; ++t) {
         const int tap = p.groups[g].tap_id[t];
         float* dst = p.partial + (((long long)ks * p.ntaps_total + tap) * p.cout + co) * p.cin_pitch + p.ci_start[cb];
@@ -203,12 +207,12 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
             if (p.ci_start[cb] + n0 + 16 <= p.cin_pitch) {      // a lane owns a contiguous, 16-byte aligned row (pad columns are ignored)
 #pragma unroll
               for (int i = 0; i < 16; i += 4)
-                *reinterpret_cast<float4*>(dst + n0 + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
-                                                                      __uint_as_float(r[i + 3]));
+                *reinterpret_cast<float4*>(dst + n0 + i) = make_float4(comp * __uint_as_float(r[i]), comp * __uint_as_float(r[i + 1]),
+                                                                      comp * __uint_as_float(r[i + 2]), comp * __uint_as_float(r[i + 3]));
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                if (p.ci_start[cb] + n0 + i < p.cin) dst[n0 + i] = __uint_as_float(r[i]);
+                if (p.ci_start[cb] + n0 + i < p.cin) dst[n0 + i] = comp * __uint_as_float(r[i]);
             }
           }
         }
@@ -413,6 +417,7 @@ static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const floa
   p.k_total = k_total; p.KC = 32; p.n_kchunks = (int)((k_total + p.KC - 1) / p.KC);
   p.ksplit = ksplit; p.chunks_per_split = (p.n_kchunks + ksplit - 1) / ksplit;
   p.cout = cout; p.cin = cin; p.cin_pitch = (cin + 3) / 4 * 4; p.n_co_tiles = (cout + 127) / 128;
+  p.acc_beta = (getenv("SSDN_ACC_COMP") && atoi(getenv("SSDN_ACC_COMP")) == 0) ? 0.0f : SSDN_ACC_BETA;
   p.m64 = (cout <= 64 && !(getenv("SSDN_WGRAD_M64") && atoi(getenv("SSDN_WGRAD_M64")) == 0)) ? 1 : 0;
   // ci blocks: as wide as TMEM allows (3 taps x N <= 512 columns, N <= 256), so that dZ is streamed as few times as possible
   const int cap = wgrad_ci_cap(taps.n);

@@ -41,7 +41,9 @@ def test_pipeline_outputs_and_gradients(engine, name):
         # the fp32 reference is itself only accurate to e_ref there (LAPACK LU in fp32), the engine works in fp64 registers
         for key, okey in ((PipelineOutput.IMG_DENOISED, "pme"), (PipelineOutput.MODEL_STD_DEV, "model_std")):
             # floor 5e-4: with an estimated sigma the posterior mean amplifies the ~4e-5 forward error of both networks
-            ok, errs = as_accurate_as_reference(out[key], o32[okey], o64[okey], slack=1.0, floor=5e-4)
+            # (Poisson: sigma itself depends on the small means of the untrained network - one more amplification: slack 3)
+            slack = 3.0 if d.get("noise_style", "gauss").startswith("poisson") else 1.0
+            ok, errs = as_accurate_as_reference(out[key], o32[okey], o64[okey], slack=slack, floor=5e-4)
             assert ok, (key, errs)
     else:
         assert rel(out[PipelineOutput.IMG_DENOISED], gold["out"]) < TOL
