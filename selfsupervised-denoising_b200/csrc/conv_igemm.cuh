@@ -4,15 +4,20 @@
 //
 // A is a padded-flat NHWC activation (common.cuh); because zero padding is stored in the halo,
 // every tap is a constant row offset into A.  Work decomposition:
-//   unit   = T consecutive tiles of 128 flat pixels  x  one N-tile (<= 128 output channels)
-//   chunk  = 16 input channels (one SWIZZLE_64B K-major smem tile row = 64 bytes, 2 tf32 k-steps)
+//   unit   = T consecutive tiles of 128 flat pixels  x  one N-tile (<= 192 output channels)
+//   chunk  = 16 input channels (one SWIZZLE_64B K-major smem tile row = 64 bytes, 2 tf32 k-steps); 1x1 layers use
+//            32-channel chunks (SWIZZLE_128B, 4 k-steps): without tap reuse the TMA row rate is what binds there
 //   group  = a set of taps that share one staged window of A rows (halo reuse: the window is
 //            loaded ONCE by TMA and each tap is only a different UMMA start address)
-//   B tile = the [N][16] weight slab of one (chunk, tap), streamed through its own smem ring.
-// Warp roles: 0 = A producer (TMA), 1 = B producer (TMA), 2 = MMA issuer (one thread),
-// 3 = TMEM allocator, 4..7 = epilogue (TMEM -> registers -> bias/LeakyReLU/grad-mask -> HBM,
-// with the upsample / un-rotate / NCHW scatter fused into the store address).
+//   B tile = the [N][16] weight slab of one (chunk, tap), streamed through its own smem ring (3 slabs per stage).
+// Warp roles (12 warps): 0 = A producer (TMA), 1 = B producer (TMA), 2 = MMA issuer (one elected thread),
+// 3 = TMEM allocator, 4..11 = epilogue - two warps per TMEM lane quadrant taking alternate 32-channel slices:
+// TMEM -> registers -> accumulator-truncation compensation -> bias / LeakyReLU (+ sign-mask word out) or LeakyReLU' from
+// the sign-mask word -> optional column sums (bias gradient) -> transposed through shared memory -> hi/lo split ->
+// full-line stores with the upsample / un-rotate / NCHW scatter in the address.
 // Accumulators are double buffered in TMEM so the epilogue of unit i overlaps the MMAs of unit i+1.
+// PAIR = true: the kernel runs as clusters of two CTAs that issue cta_group::2 MMAs of M = 256 (umma.cuh): each CTA loads
+// its own pixel rows of A and half of the N rows of B, the leader issues, both epilogues drain their own TMEM.
 // Precision: 3xTF32 (see common.cuh) => fp32-grade results, 3 MMAs per (tile, k-step).
 #pragma once
 #include "common.cuh"
@@ -42,13 +47,11 @@ struct ConvParams {
   int row3;           // 1: every B stage holds the 3 taps of one stencil row of one group, tap_rel advancing by tap_step
   int tap_step;       //    (+1 forward, -1 data-gradient): the MMA warp then issues 3 x T x 6 MMAs per barrier wait
   uint32_t a_plane_bytes, b_stage_bytes;   // smem bytes of one A plane of one stage / of one B stage
-  uint32_t epi_off;   // staged epilogue: byte offset of the staging area (4 warps x 32 pixels x 36 floats) in dynamic smem
+  uint32_t epi_off;   // byte offset of the epilogue staging area (8 warps x 32 pixels x 36 floats) in dynamic smem
   float acc_comp;     // 1 + SSDN_ACC_BETA x (MMA instructions accumulated into one output): truncation-bias compensation
   int epi_split;      // 1: both epilogue warps of a TMEM lane quadrant work (alternate slices) - epilogue-bound layers; 0: one warp
                       //    per quadrant, the other four exit at once (they would only take issue slots and shared-memory
                       //    bandwidth from an MMA-bound layer)
-  int epi_staged;     // 1: slices are transposed through shared memory so that 8 lanes write one pixel's 128 contiguous bytes
-                      //    (store-bound epilogues: upsampling, 1x1 and few-channel convolutions); 0: straight from registers
   ConvDst dst;
   int* error_flag;
   int debug;          // experiments only: 2 = skip MMA issue
@@ -665,19 +668,11 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     const bool on = !(getenv("SSDN_ACC_COMP") && atoi(getenv("SSDN_ACC_COMP")) == 0);
     p.acc_comp = on ? 1.0f + SSDN_ACC_BETA * (float)(ksteps * taps.n * 3) : 1.0f;
   }
-  // epilogue mode: straight-from-register stores cost the load/store unit ~2800 clk per 32-channel slice of a tile
-  // (32 line fragments per instruction); stage through shared memory when the tile's MMA time cannot hide that
+  // epilogue: both warps of a TMEM lane quadrant - measured never slower (profiles/r01_pair_split_ablation.log), except
+  // with the upsampling epilogue (4x the stores: the two warps then only fight over the load/store unit)
   {
-    const double mma_clk = (double)n_slabs * (p.wide ? 12 : 6) * std::max(N / 2.0, (4096.0 + 32.0 * N) / 128.0);
-    const double direct_clk = 2800.0 * ((N + 31) / 32);
-    p.epi_staged = 1;   // measured: staging is never slower, even where the MMA time would hide register-direct stores
-    (void)direct_clk;
-    // both epilogue warps of a quadrant: measured never slower, except with the upsampling epilogue (4x the stores: the two
-    // warps then only fight over the load/store unit)
     p.epi_split = dst.map != MAP_UP2 && dst.map != MAP_NCHW;
-    (void)mma_clk;
     if (const char* e = getenv("SSDN_EPI_SPLIT")) p.epi_split = atoi(e) != 0;
-
   }
   // choose the tap grouping: all taps in one window if it fits in shared memory, else one window per
   // distinct row offset (dy), else one window per tap.

@@ -8,11 +8,15 @@
 // swizzle with a 32-byte atom (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B / UMMA layout type 1), verified
 // on hardware by csrc/probe/umma_probe.cu, including start addresses shifted by whole pixel rows -
 // which is how the taps of one stencil row share a single staged window of X.
-//   unit  = (128-wide co tile) x (ci block, N <= 96) x (tap group) x (K split)
-//   stage = KC flat pixels of dZ (4 blocks of 32 co) + KC+halo pixels of X (<= 3 blocks of 32 ci)
-// Accumulators [co lane][tap][ci] live in TMEM for the whole K range of the unit; partial results go
-// to a workspace and a second, fixed-order reduction kernel produces dW (deterministic, no atomics).
-// Precision: 3xTF32 as in the forward kernel.
+//   unit  = (128-wide co tile) x (ci block, N <= 144 / 192) x (tap group = stencil row) x (K split)
+//   stage = KC flat pixels of dZ (<= 4 blocks of 32 co) + KC+halo pixels of X (<= 6 blocks of 32 ci), two TMA ops
+// Accumulators [co lane][tap][ci] live in TMEM for the whole K range of the unit; partial results (float4 rows, padded
+// to 16 bytes) go to a workspace and a fixed-order parallel reduction produces dW (deterministic, no atomics).
+// Unit order: the tap groups / ci blocks / co tiles of one K range are adjacent, so concurrently running CTAs share
+// their dZ and X rows through L2; the K split gives at most two units per SM (no third wave).  Layers with <= 64 output
+// channels issue M = 64 MMAs (half the dZ operand bytes).  The first conv (<= 4 input channels) does not use this kernel
+// at all: wgrad_small_cin_kernel below runs on the CUDA cores.
+// Precision: 3xTF32 as in the forward kernel, with the same accumulator-truncation compensation per K split.
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
