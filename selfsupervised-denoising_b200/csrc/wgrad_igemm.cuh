@@ -13,7 +13,7 @@
 // Accumulators [co lane][tap][ci] live in TMEM for the whole K range of the unit; partial results (float4 rows, padded
 // to 16 bytes) go to a workspace and a fixed-order parallel reduction produces dW (deterministic, no atomics).
 // Unit order: the tap groups / ci blocks / co tiles of one K range are adjacent, so concurrently running CTAs share
-// their dZ and X rows through L2; the K split gives at most two units per SM (no third wave).  Layers with <= 64 output
+// their dZ and X rows through L2; the K split gives one unit per SM (a whole wave, and the fewest partials to reduce).  Layers with <= 64 output
 // channels issue M = 64 MMAs (half the dZ operand bytes).  The first conv (<= 4 input channels) does not use this kernel
 // at all: wgrad_small_cin_kernel below runs on the CUDA cores.
 // Precision: 3xTF32 as in the forward kernel, with the same accumulator-truncation compensation per K split.
@@ -405,7 +405,8 @@ static inline int wgrad_pick_ksplit(long long k_total, int cout, int cin, int nt
   const int n_kchunks = (int)((k_total + KC - 1) / KC);
   const int n_co_tiles = (cout + 127) / 128, n_ci_blocks = wgrad_n_ci_blocks(cin, ntaps), n_groups = ntaps == 9 ? 3 : ntaps;
   const int others = n_co_tiles * n_ci_blocks * n_groups;
-  int ks = std::max(1, (2 * num_sms) / others);   // at most two units per SM: one unit more would cost a whole extra wave
+  static const int units_per_sm = getenv("SSDN_WGRAD_UNITS_PER_SM") ? atoi(getenv("SSDN_WGRAD_UNITS_PER_SM")) : 1;   // measured: 1 > 2 > 3 (fewer partials to write and reduce)
+  int ks = std::max(1, (units_per_sm * num_sms) / others);   // whole waves only: one unit more would cost a whole extra wave
   ks = std::min(ks, std::max(1, n_kchunks / 4));
   ks = std::max(1, std::min(ks, n_kchunks));
   const int cps = (n_kchunks + ks - 1) / ks;      // no K split may be empty: its accumulator would be undefined
