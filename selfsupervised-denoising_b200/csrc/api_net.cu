@@ -102,7 +102,7 @@ extern "C" int ssdn_net_kernel_launches(void* handle, int training) {
   net::Net* nn = (net::Net*)handle;
   const int nl = (int)nn->layers.size();
   int fwd = nl /*conv*/ + 5 /*pool*/ + 1 /*pack*/ + 1 /*weight slabs*/;
-  int bwd = 2 /*pack, loss-gradient column sums*/ + nl * 3 /*wgrad, split-K reduce, bias reduce*/ + (nl - 1) /*dgrad*/ + 5 + 5 /*pool, upsample*/;
+  int bwd = 2 /*pack, loss-gradient column sums*/ + nl * 2 /*wgrad, split-K reduce*/ + 1 /*all bias reductions*/ + (nl - 1) /*dgrad*/ + 5 + 5 /*pool, upsample*/;
   return training ? fwd + bwd : fwd;
 }
 

@@ -34,6 +34,7 @@ struct Layer {               // one convolution of the network
   ConvPlan dgrad; float* slab_d; int n_d; int cinp_d; int dgrad_nvalid;
   bool bias_fused = false; int bias_nblk = 0;   // bias gradient = column sums written by the kernel that produced this layer's dZ
   const float* bias_partial = nullptr;          //   partial[bias_nblk][cout]
+  float* bias_buf = nullptr;                    //   this layer's own partial buffer (all bias reductions run as one kernel at the end)
   // weight gradient
   WgradPlan wgrad; int ksplit;
   const Buf* x; int x_coff;          // conv input (channel slice [x_coff, x_coff+cin))
@@ -41,9 +42,9 @@ struct Layer {               // one convolution of the network
 };
 
 struct PoolOp { const Buf* src; const Buf* dst; int dst_coff; };
-struct PoolBwdOp { const Buf* act; const Buf* g1; const Buf* g2; int g2_coff; const Buf* dz; Geom gp; };
-struct UpBwdOp { const Buf* g; const Buf* act_up; const Buf* dz; int C; };
-// pool_bwd / up_bwd / the loss-gradient pack also produce a dZ: their fused column sums go to colpart3
+struct PoolBwdOp { const Buf* act; const Buf* g1; const Buf* g2; int g2_coff; const Buf* dz; Geom gp; float* colsum; int grid; };
+struct UpBwdOp { const Buf* g; const Buf* act_up; const Buf* dz; int C; float* colsum; int grid; };
+// pool_bwd / up_bwd / the loss-gradient pack also produce a dZ: their fused column sums go to the owning layer's bias_buf
 
 class Net {
  public:
@@ -55,7 +56,7 @@ class Net {
   // buffers
   Buf cat[6], e[6], e1a, p5, d_a[6], head_in, h1, h2;
   Buf g_out, dz_h2, dz_h1, dz_db[6], dz_da[6], gcat[6], dz_e[7], dz_e1a, g_p[6];
-  float* partial = nullptr; float* colpart = nullptr; float* colpart2 = nullptr; float* colpart3 = nullptr; int* flag = nullptr;
+  float* partial = nullptr; float* colpart = nullptr; int* flag = nullptr;
   size_t partial_floats = 0;
   size_t ws_bytes = 0; void* ws = nullptr;
   std::vector<PoolOp> pools; std::vector<PoolBwdOp> pool_bwds; std::vector<UpBwdOp> up_bwds;
@@ -172,8 +173,7 @@ class Net {
     }
     partial = a.take<float>(partial_floats);
     colpart = a.take<float>((size_t)1024 * 384);
-    colpart2 = a.take<float>((size_t)148 * convk::kEpiWarps * 384 + 4096);
-    colpart3 = a.take<float>((size_t)1024 * 96);
+    for (auto& l : layers) l.bias_buf = a.take<float>((size_t)148 * convk::kEpiWarps * l.cout);
     flag = a.take<int>(64);
     return a.off;
   }
@@ -223,37 +223,45 @@ class Net {
     const int gact = EP_ACT_GRAD | EP_WRITE_LO;
     // every dst_act below also yields the bias gradient of the layer that owns the produced dZ (fused column sums)
     auto fused = [&](const char* producer, const char* owner) {
-      Layer& o = L(owner); o.bias_fused = true; o.bias_nblk = L(producer).dgrad.grid * (L(producer).dgrad.p.epi_split ? convk::kEpiWarps : 4); o.bias_partial = colpart2;
+      Layer& o = L(owner); o.bias_fused = true; o.bias_partial = o.bias_buf;
+      o.bias_nblk = L(producer).dgrad.grid * (L(producer).dgrad.p.epi_split ? convk::kEpiWarps : 4);
     };
-    auto fused_pw = [&](const std::string& owner, int nblk) { Layer& o = L(owner); o.bias_fused = true; o.bias_nblk = nblk; o.bias_partial = colpart3; };
+    // pointwise producers (grid-stride kernels with at most kFusedColsumGrid blocks of kFusedColsumBlock threads)
+    auto pw_grid = [&](long long n) { return (int)std::min<long long>(pw::kFusedColsumGrid, (n + pw::kFusedColsumBlock - 1) / pw::kFusedColsumBlock); };
+    auto fused_pw = [&](const std::string& owner, int nblk) -> float* {
+      Layer& o = L(owner); o.bias_fused = true; o.bias_nblk = nblk; o.bias_partial = o.bias_buf; return o.bias_buf;
+    };
     fused_pw("output_conv", N);                                              // nchw_colsum_kernel over d(loss)/d(out)
-    for (int i = 2; i <= 5; ++i) fused_pw("decode_block_" + std::to_string(i) + ".2", pw::kFusedColsumGrid);   // up_bwd
-    fused_pw("encode_block_6.0", pw::kFusedColsumGrid);                      // up_bwd
-    fused_pw("encode_block_1.2", pw::kFusedColsumGrid);                      // pool_bwd
-    for (int i = 2; i <= 5; ++i) fused_pw("encode_block_" + std::to_string(i) + ".0", pw::kFusedColsumGrid);   // pool_bwd
-    if ((r = plan_dgrad(L("output_conv"), g_out, dst_act(dz_h2, MAP_IDENT, gact, 96, h2, true)))) return r;
+    if ((r = plan_dgrad(L("output_conv"), g_out, dst_act(dz_h2, MAP_IDENT, gact, 96, h2, &L("output_block.2"))))) return r;
     fused("output_conv", "output_block.2");
-    if ((r = plan_dgrad(L("output_block.2"), dz_h2, dst_act(dz_h1, MAP_IDENT, gact, nin, h1, true)))) return r;
+    if ((r = plan_dgrad(L("output_block.2"), dz_h2, dst_act(dz_h1, MAP_IDENT, gact, nin, h1, &L("output_block.0"))))) return r;
     fused("output_block.2", "output_block.0");
-    { ConvDst d = dst_act(dz_db[1], blind ? MAP_UNROT_INV : MAP_IDENT, gact | EP_ACT_AT_SRC, 96, head_in, true);
+    { ConvDst d = dst_act(dz_db[1], blind ? MAP_UNROT_INV : MAP_IDENT, gact | EP_ACT_AT_SRC, 96, head_in, &L("decode_block_1.2"));
       if ((r = plan_dgrad(L("output_block.0"), dz_h1, d))) return r; }
     fused("output_block.0", "decode_block_1.2");
     for (int i = 1; i <= 5; ++i) {
       const std::string a_nm = "decode_block_" + std::to_string(i) + ".0", b_nm = "decode_block_" + std::to_string(i) + ".2";
-      if ((r = plan_dgrad(L(b_nm), dz_db[i], dst_act(dz_da[i], MAP_IDENT, gact, 96, d_a[i], true)))) return r;
+      if ((r = plan_dgrad(L(b_nm), dz_db[i], dst_act(dz_da[i], MAP_IDENT, gact, 96, d_a[i], &L(a_nm))))) return r;
       fused(b_nm.c_str(), a_nm.c_str());
       if ((r = plan_dgrad(L(a_nm), dz_da[i], dst(gcat[i], 0, MAP_IDENT, 0, L(a_nm).dgrad_nvalid)))) return r;
-      if (i < 5) up_bwds.push_back({&gcat[i], &cat[i], &dz_db[i + 1], 96});
+      if (i < 5) {
+        const int grid = pw_grid((long long)g[i].B * g[i].H * g[i].W * (96 / 4));
+        up_bwds.push_back({&gcat[i], &cat[i], &dz_db[i + 1], 96, fused_pw("decode_block_" + std::to_string(i + 1) + ".2", grid), grid});
+      }
     }
-    up_bwds.push_back({&gcat[5], &cat[5], &dz_e[6], 48});
+    { const int grid = pw_grid((long long)g[5].B * g[5].H * g[5].W * (48 / 4));
+      up_bwds.push_back({&gcat[5], &cat[5], &dz_e[6], 48, fused_pw("encode_block_6.0", grid), grid}); }
     if ((r = plan_dgrad(L("encode_block_6.0"), dz_e[6], dst(g_p[5], 0, MAP_IDENT, 0, 48)))) return r;
     for (int i = 5; i >= 2; --i) {
       // dZ of the conv feeding pool i: gradient from the next encoder conv (+ the skip path for i <= 4)
-      pool_bwds.push_back({&e[i], &g_p[i], i <= 4 ? &gcat[i + 1] : nullptr, i == 4 ? 48 : 96, &dz_e[i], g[i]});
+      { const int grid = pw_grid((long long)g[i].B * g[i].H * g[i].W * 48);
+        pool_bwds.push_back({&e[i], &g_p[i], i <= 4 ? &gcat[i + 1] : nullptr, i == 4 ? 48 : 96, &dz_e[i], g[i],
+                             fused_pw("encode_block_" + std::to_string(i) + ".0", grid), grid}); }
       if ((r = plan_dgrad(L("encode_block_" + std::to_string(i) + ".0"), dz_e[i], dst(g_p[i - 1], 0, MAP_IDENT, 0, 48)))) return r;
     }
-    pool_bwds.push_back({&e[1], &g_p[1], &gcat[2], 96, &dz_e[1], g[1]});
-    if ((r = plan_dgrad(L("encode_block_1.2"), dz_e[1], dst_act(dz_e1a, MAP_IDENT, gact, 48, e1a, true)))) return r;
+    { const int grid = pw_grid((long long)g[1].B * g[1].H * g[1].W * 48);
+      pool_bwds.push_back({&e[1], &g_p[1], &gcat[2], 96, &dz_e[1], g[1], fused_pw("encode_block_1.2", grid), grid}); }
+    if ((r = plan_dgrad(L("encode_block_1.2"), dz_e[1], dst_act(dz_e1a, MAP_IDENT, gact, 48, e1a, &L("encode_block_1.0"))))) return r;
     fused("encode_block_1.2", "encode_block_1.0");
 
     // ---- backward: weight gradients
@@ -293,9 +301,9 @@ class Net {
   }
   // data-gradient destination whose values are multiplied by LeakyReLU'(act) (sign masks of `act`); with_colsum also
   // collects the column sums of what is written (= the bias gradient of the layer whose dZ this is)
-  ConvDst dst_act(Buf& b, int map, int flags, int cvalid, Buf& act, bool with_colsum) {
+  ConvDst dst_act(Buf& b, int map, int flags, int cvalid, Buf& act, Layer* bias_owner) {
     ConvDst d = dst(b, 0, map, flags, cvalid); d.mask_in = act.mask; d.mask_in_words = act.mask_words;
-    if (with_colsum) { d.colsum = colpart2; d.colsum_pitch = (map == MAP_UNROT_INV) ? 96 : cvalid; }
+    if (bias_owner) { d.colsum = bias_owner->bias_buf; d.colsum_pitch = (map == MAP_UNROT_INV) ? 96 : cvalid; }
     return d;
   }
 
@@ -376,7 +384,7 @@ class Net {
     const int nt = l.ksize * l.ksize;
     // bias gradient: reduce the column-sum partials its dZ producer left behind (main stream: the next producer reuses them)
     if (l.bias_fused) {
-      pw::colsum_stage2_launch(l.bias_partial, l.bias_nblk, l.cout, grads + l.b_off, st);
+      // nothing here: backward() finishes all bias gradients with one batched reduction after the last producer
     } else {
       const long long rows = l.dz->g.total();
       pw::colsum_launch(l.dz->v, l.dz->lo, rows, l.dz->cpitch, 0, l.cout, colpart, grads + l.b_off, st);
@@ -419,7 +427,7 @@ class Net {
     int r;
     pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)N * H * W), pw::kBlock, 0, st>>>(dout, g_out.v, g_out.lo, N, Cout, H, W, gh,
                                                                                           g_out.cpitch, 0, 0);
-    pw::nchw_colsum_kernel<<<dim3(Cout, N), 256, 0, st>>>(dout, Cout, H * W, colpart3);
+    pw::nchw_colsum_kernel<<<dim3(Cout, N), 256, 0, st>>>(dout, Cout, H * W, L("output_conv").bias_buf);
     auto both = [&](const std::string& nm, bool dgrad) -> int {
       Layer& l = L(nm);
       int rr = run_wgrad(l, grads, st);
@@ -434,19 +442,15 @@ class Net {
       const UpBwdOp& u = up_bwds[ui++];
       const Geom& gl = u.dz->g;
       const long long n = (long long)gl.B * gl.H * gl.W * (u.C / 4);
-      const int grid = (int)std::min<long long>(pw::kFusedColsumGrid, (n + pw::kFusedColsumBlock - 1) / pw::kFusedColsumBlock);
-      if (grid < pw::kFusedColsumGrid) cudaMemsetAsync(colpart3, 0, (size_t)pw::kFusedColsumGrid * u.C * sizeof(float), st);
-      pw::up_bwd_kernel<<<grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * sizeof(float4), st>>>(
-          u.g->v, u.g->g, u.g->cpitch, 0, u.act_up->v, u.act_up->cpitch, 0, gl, u.dz->v, u.dz->lo, u.dz->cpitch, 0, u.C, colpart3);
+      (void)n;
+      pw::up_bwd_kernel<<<u.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * sizeof(float4), st>>>(
+          u.g->v, u.g->g, u.g->cpitch, 0, u.act_up->v, u.act_up->cpitch, 0, gl, u.dz->v, u.dz->lo, u.dz->cpitch, 0, u.C, u.colsum);
     };
     auto pool_bwd = [&]() {
       const PoolBwdOp& q = pool_bwds[qi++];
-      const long long n = (long long)q.gp.B * q.gp.H * q.gp.W * 48;
-      const int grid = (int)std::min<long long>(pw::kFusedColsumGrid, (n + pw::kFusedColsumBlock - 1) / pw::kFusedColsumBlock);
-      if (grid < pw::kFusedColsumGrid) cudaMemsetAsync(colpart3, 0, (size_t)pw::kFusedColsumGrid * 48 * sizeof(float), st);
-      pw::pool_bwd_kernel<<<grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * sizeof(float), st>>>(
+      pw::pool_bwd_kernel<<<q.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * sizeof(float), st>>>(
           q.act->v, q.act->lo, q.act->g, q.act->cpitch, 0, q.g1->v, q.g1->cpitch, 0, q.g2 ? q.g2->v : nullptr, q.g2 ? q.g2->cpitch : 0, q.g2_coff, q.gp,
-          q.dz->v, q.dz->lo, q.dz->cpitch, 0, 48, blind ? 1 : 0, colpart3);
+          q.dz->v, q.dz->lo, q.dz->cpitch, 0, 48, blind ? 1 : 0, q.colsum);
     };
     for (int i = 1; i <= 5; ++i) {
       if ((r = both("decode_block_" + std::to_string(i) + ".2", true))) return r;
@@ -461,6 +465,13 @@ class Net {
     pool_bwd();
     if ((r = both("encode_block_1.2", true))) return r;
     if ((r = both("encode_block_1.0", false))) return r;
+    {   // all bias gradients: one batched fixed-order reduction of the per-layer column-sum partials
+      pw::BiasJobs jobs{};
+      int nj = 0, maxc = 0;
+      for (auto& l : layers)
+        if (l.bias_fused) { jobs.j[nj++] = {l.bias_partial, grads + l.b_off, l.bias_nblk, l.cout}; maxc = std::max(maxc, l.cout); }
+      if (nj) pw::colsum_stage2_batched_kernel<<<dim3((maxc + 31) / 32, nj), dim3(32, 32), 0, st>>>(jobs);
+    }
     if ((r = join_side(st))) return r;
     SSDN_CUDA(cudaGetLastError());
     return 0;

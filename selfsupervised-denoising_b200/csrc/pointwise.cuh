@@ -344,6 +344,31 @@ __global__ void colsum_stage2_kernel(const float* __restrict__ partial, int nblk
     out[c] = accumulate ? out[c] + t : t;
   }
 }
+// All bias gradients of a network in ONE launch at the end of the backward pass (every layer has its own partial buffer):
+// blockIdx.y selects the job, blockIdx.x a group of 32 channels.
+struct BiasJob { const float* partial; float* out; int nblk, C; };
+constexpr int kMaxBiasJobs = 24;
+struct BiasJobs { BiasJob j[kMaxBiasJobs]; };
+__global__ void colsum_stage2_batched_kernel(const __grid_constant__ BiasJobs jobs) {
+  __shared__ float sm[32][33];
+  const BiasJob& q = jobs.j[blockIdx.y];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (blockIdx.x * 32 >= q.C) return;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < q.C) {
+    int b = threadIdx.y;
+    for (; b + 32 < q.nblk; b += 64) { a0 += q.partial[(long long)b * q.C + c]; a1 += q.partial[(long long)(b + 32) * q.C + c]; }
+    if (b < q.nblk) a0 += q.partial[(long long)b * q.C + c];
+  }
+  sm[threadIdx.y][threadIdx.x] = a0 + a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < q.C) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) t += sm[w][threadIdx.x];
+    q.out[c] = t;
+  }
+}
 static inline void colsum_stage2_launch(const float* partial, int nblk, int C, float* out, cudaStream_t st) {
   colsum_stage2_kernel<<<(C + 31) / 32, dim3(32, 32), 0, st>>>(partial, nblk, C, out, 0);
 }
