@@ -126,6 +126,13 @@ int ssdn_noisy_crops(const unsigned char* images, int n_images, int c, int h, in
                      unsigned long long seed, unsigned long long step, int stream_id, float sigma_lo, float sigma_hi, int clip,
                      float* clean, float* noisy, float* sigma, void* stream);
 
+/* Noise2Void "uniform pixel selection" — utils/n2v_ups.py:7-96 (manipulate, get_stratified_coords).  noisy / masked
+ * [n][c][h][w] DEVICE fp32 (h, w multiples of 8; masked may alias noisy only if a stale read of a masked pixel is acceptable -
+ * pass a separate buffer), coords DEVICE int64 [n][(h/8)*(w/8)][2] = (x, y) per 8x8 box in the reference's list order.
+ * The reference's index quirks (min for max, negative wrap) are kept; parity is statistical. */
+int ssdn_n2v_mask(const float* noisy, float* masked, long long* coords, int n, int c, int h, int w, int subpatch_size,
+                  unsigned long long seed, unsigned long long step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

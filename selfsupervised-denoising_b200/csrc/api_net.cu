@@ -260,3 +260,18 @@ extern "C" int ssdn_noisy_crops(const unsigned char* images, int n_images, int c
   SSDN_CUDA(cudaGetLastError());
   return 0;
 }
+
+extern "C" int ssdn_n2v_mask(const float* noisy, float* masked, long long* coords, int n, int c, int h, int w, int subpatch_size,
+                             unsigned long long seed, unsigned long long step, void* stream) {
+  if (!noisy || !masked || !coords) return fail(-1, "null pointer");
+  if (subpatch_size % 2 == 0) return fail(-1, "subpatch_size must be odd");
+  const int box = 8;                                  // round(sqrt(100 / 1.5)), utils/n2v_ups.py:72-73
+  if (h % box || w % box) return fail(-1, "the on-GPU Noise2Void mask needs height and width that are multiples of %d", box);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (masked != noisy) SSDN_CUDA(cudaMemcpyAsync(masked, noisy, (size_t)n * c * h * w * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const int total = n * (h / box) * (w / box);
+  inpk::n2v_mask_kernel<<<pw::grid_for(total), pw::kBlock, 0, st>>>(noisy, masked, coords, n, c, h, w, box, subpatch_size / 2, (uint32_t)seed,
+                                                                      (uint32_t)(seed >> 32), (uint32_t)step, (uint32_t)(step >> 32));
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -66,4 +66,38 @@ __global__ void noisy_crops_kernel(const unsigned char* __restrict__ images, int
   }
 }
 
+// Noise2Void masking (utils/n2v_ups.py:7-49, "uniform pixel selection"): one stratified coordinate per 8 x 8 box
+// (get_stratified_coords: box = round(sqrt(100 / 1.5)) = 8), each replaced by another pixel of the same image whose column is
+// drawn from [min(x - r, 0), min(x + r, W - 1)) \ {x} and row from [min(y - r, 0), min(y + r, H - 1)) \ {y} - the reference's
+// `min` where `max` was meant is kept, negative indices wrap like Python's.  One thread per (sample, box); replacements read
+// the UNMASKED image (the reference updates in place, so a source pixel that is itself an earlier mask position differs -
+// probability ~1.5 %): statistical, not bit, parity.  coords[n][box] = (x, y) as int64, the order of the reference's list.
+__global__ void n2v_mask_kernel(const float* __restrict__ noisy, float* __restrict__ masked, long long* __restrict__ coords, int n, int C,
+                                int H, int W, int box, int radius, uint32_t seed_lo, uint32_t seed_hi, uint32_t step_lo, uint32_t step_hi) {
+  const int by = H / box, bx = W / box, nb = by * bx;        // the reference's outer loop runs over the x axis (shape[0] = W)
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * nb) return;
+  const int s = idx / nb, b = idx - s * nb;
+  const int i = b / by, j = b - i * by;                       // i: box along x, j: box along y
+  Philox r = philox4x32_10(step_lo, step_hi, (uint32_t)s, 0x80000000u + (uint32_t)b, seed_lo, seed_hi);
+  const int x = i * box + (int)(((unsigned long long)r.x[0] * (unsigned)box) >> 32);
+  const int y = j * box + (int)(((unsigned long long)r.x[1] * (unsigned)box) >> 32);
+  auto draw = [&](int centre, int size, uint32_t salt) {
+    const int lo = min(centre - radius, 0), hi = min(centre + radius, size - 1);      // torch.randint(lo, hi): [lo, hi)
+    int v = centre;
+    for (uint32_t t = 0; v == centre && t < 64; ++t) {
+      const Philox q = philox4x32_10(step_lo ^ salt, step_hi + t, (uint32_t)s, 0xC0000000u + (uint32_t)b, seed_lo, seed_hi);
+      v = lo + (int)(((unsigned long long)q.x[0] * (unsigned)(hi - lo)) >> 32);
+    }
+    return v < 0 ? v + size : v;                                                      // Python-style negative index
+  };
+  const int rx = draw(x, W, 0x5bd1e995u), ry = draw(y, H, 0x1b873593u);
+  for (int c = 0; c < C; ++c) {
+    const long long base = ((long long)s * C + c) * H * W;
+    masked[base + (long long)y * W + x] = noisy[base + (long long)ry * W + rx];
+  }
+  coords[((long long)s * nb + b) * 2 + 0] = x;
+  coords[((long long)s * nb + b) * 2 + 1] = y;
+}
+
 }  // namespace inpk

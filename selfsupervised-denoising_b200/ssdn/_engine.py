@@ -50,6 +50,7 @@ _SIGNATURES = {
     "ssdn_masked_mse_forward": (_I, [_P, _P, _P, _P] + [_I] * 5 + [_P, _P]),
     "ssdn_masked_mse_backward": (_I, [_P, _P, _P, _I, _P] + [_I] * 4 + [_P, _P]),
     "ssdn_adam_step": (_I, [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _LL, _D, _P]),
+    "ssdn_n2v_mask": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, ctypes.c_ulonglong, ctypes.c_ulonglong, _P]),
     "ssdn_noisy_crops": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, ctypes.c_ulonglong, ctypes.c_ulonglong, _I, ctypes.c_float, ctypes.c_float, _I,
                               _P, _P, _P, _P]),
 }
@@ -340,3 +341,13 @@ def noisy_crops(images_u8, n, patch, seed, step, sigma_lo, sigma_hi=None, clip=T
     check(lib().ssdn_noisy_crops(_ptr(images_u8), ni, c, h, w, _ptr(order), n, patch, int(seed), int(step), int(stream_id), float(sigma_lo),
                                  float(hi), 1 if clip else 0, _ptr(clean), _ptr(noisy), _ptr(sigma), _stream()))
     return clean, noisy, sigma
+
+
+def n2v_mask(noisy, seed, step, subpatch_size=5):
+    """Noise2Void uniform pixel selection on the device (utils/n2v_ups.py:7-49).  Returns (masked copy, coords int64 [n][k][2])."""
+    noisy = _f32(noisy)
+    n, c, h, w = noisy.shape
+    masked = torch.empty_like(noisy)
+    coords = torch.empty(n, (h // 8) * (w // 8), 2, dtype=torch.int64, device=noisy.device)
+    check(lib().ssdn_n2v_mask(_ptr(noisy), _ptr(masked), _ptr(coords), n, c, h, w, int(subpatch_size), int(seed), int(step), _stream()))
+    return masked, coords

@@ -6,8 +6,8 @@ Reference: ``train.py:756-760`` (RandomCrop), ``datasets/noise_wrapper.py:98-163
 ``utils/noise.py:14-63`` (add_gaussian).  The reference feeds the GPU from 4 PIL / h5py worker processes; at the engine's
 step rate (> 4000 patches/s per GPU) that loader is the bottleneck by orders of magnitude.  Randomness is Philox
 counter-based: batches are a pure function of ``(seed, step)`` - a resumed run only needs the step counter - and parity
-with the CPU generator is statistical, not bit-wise.  Gaussian styles only (``gauss25``, ``gauss5_50``, ``_nc``);
-Noise2Void masking stays on the CPU path."""
+with the CPU generator is statistical, not bit-wise.  Gaussian styles only (``gauss25``, ``gauss5_50``, ``_nc``).
+Noise2Void batches are masked on the device too (``ssdn_n2v_mask``, the reference's ``manipulate`` with its index quirks)."""
 from __future__ import annotations
 
 import re
@@ -43,8 +43,6 @@ class GpuNoisyPatches:
     def __init__(self, images_u8: torch.Tensor, noise_style: str, algorithm: NoiseAlgorithm, patch: int, batch_size: int, seed: int = 0):
         if not images_u8.is_cuda or images_u8.dtype != torch.uint8 or images_u8.dim() != 4:
             raise E.EngineError("image cache must be a CUDA uint8 tensor [n_images][C][H][W]")
-        if algorithm == NoiseAlgorithm.NOISE_TO_VOID:
-            raise NotImplementedError("Noise2Void masking is not part of the on-GPU input pipeline")
         self.images, self.style, self.algorithm = images_u8.contiguous(), noise_style, algorithm
         self.patch, self.batch_size, self.seed = patch, batch_size, seed
         self.sigma_lo, self.sigma_hi, self.clip = parse_gaussian_style(noise_style)
@@ -60,7 +58,7 @@ class GpuNoisyPatches:
         if self.algorithm == NoiseAlgorithm.NOISE_TO_CLEAN:
             ref = clean
             md[M.REFERENCE_NOISE_VALUES] = torch.zeros(n, 1, 1, 1)
-        elif self.algorithm == NoiseAlgorithm.NOISE_TO_NOISE:
+        elif self.algorithm in (NoiseAlgorithm.NOISE_TO_NOISE, NoiseAlgorithm.NOISE_TO_VOID):
             _, ref, rs = E.noisy_crops(self.images, n, self.patch, self.seed, step, self.sigma_lo, self.sigma_hi, self.clip, stream_id=1,
                                        want_clean=False)
             md[M.REFERENCE_NOISE_VALUES] = rs.reshape(n, c, 1, 1) if ranged else rs[:, :1].reshape(n, 1, 1, 1)
@@ -70,6 +68,8 @@ class GpuNoisyPatches:
         else:
             ref = NULL_IMAGE
             md[M.REFERENCE_NOISE_VALUES] = torch.zeros(n, 1, 1, 1)
+        if self.algorithm == NoiseAlgorithm.NOISE_TO_VOID:      # noise_wrapper.py:107-111: mask the input, keep the coordinates
+            noisy, md[M.MASK_COORDS] = E.n2v_mask(noisy, self.seed, step, 5)
         return [noisy, ref, md]
 
     def __iter__(self):

@@ -77,8 +77,46 @@ def test_pipeline_batches_feed_the_denoiser(engine):
     a, b = (n2n[0] - n2n[2][M.CLEAN]), (n2n[1] - n2n[2][M.CLEAN])
     assert abs(float((a * b).mean()) / float((a * a).mean())) < 0.05          # ... independent noise realisations
     with pytest.raises(NotImplementedError):
-        GpuNoisyPatches(imgs, "gauss25", NoiseAlgorithm.NOISE_TO_VOID, 32, 4)
-    with pytest.raises(NotImplementedError):
         GpuNoisyPatches(imgs, "poisson30", NoiseAlgorithm.SELFSUPERVISED_DENOISING, 32, 4)
     with pytest.raises(ValueError):
         engine.noisy_crops(imgs, 4, 128, 0, 0, 0.1)                           # patch larger than the images
+
+
+def test_n2v_mask_follows_the_reference_selection_rule(engine):
+    """utils/n2v_ups.py:7-49: one coordinate per 8 x 8 box in the reference's list order; the masked pixel equals (in every
+    channel) a pixel of the same image whose column / row lie in the reference's (quirky) ranges
+    [min(x - 2, 0), min(x + 2, W - 1)) excluding x, with Python-style negative wrap; everything else is untouched."""
+    g = torch.Generator().manual_seed(9)
+    noisy = torch.rand(4, 3, 64, 64, generator=g)
+    masked, coords = engine.n2v_mask(noisy.cuda(), seed=3, step=17)
+    masked2, coords2 = engine.n2v_mask(noisy.cuda(), seed=3, step=17)
+    assert torch.equal(masked, masked2) and torch.equal(coords, coords2)
+    masked, coords = masked.cpu(), coords.cpu()
+    assert coords.shape == (4, 64, 2) and coords.dtype == torch.int64
+    changed = (masked != noisy).any(dim=1)
+    offs = []
+    for n in range(4):
+        keep = torch.ones(64, 64, dtype=torch.bool)
+        for b, (x, y) in enumerate(coords[n].tolist()):
+            i, j = b // 8, b % 8
+            assert 8 * i <= x < 8 * i + 8 and 8 * j <= y < 8 * j + 8          # stratified, x outer / y inner as in the reference
+            keep[y, x] = False
+            cols = [c % 64 for c in range(min(x - 2, 0), min(x + 2, 63)) if c != x]
+            rows = [r % 64 for r in range(min(y - 2, 0), min(y + 2, 63)) if r != y]
+            cand = [(r, c) for r in rows for c in cols if torch.equal(noisy[n, :, r, c], masked[n, :, y, x])]
+            assert cand, (n, x, y)                                                # copied from an allowed source, all channels alike
+            offs.append(cand[0][1] - x)
+        assert not changed[n][keep].any()                                         # nothing else was touched
+    assert len(set(offs)) > 20                                                    # sources spread over the whole allowed range
+
+
+def test_n2v_batches_feed_the_denoiser(engine):
+    imgs = _cache(n=4, h=80, w=80, seed=5).cuda()
+    gen = GpuNoisyPatches(imgs, "gauss25", NoiseAlgorithm.NOISE_TO_VOID, patch=64, batch_size=4, seed=2)
+    data = gen.batch(1)
+    M = NoisyDataset.Metadata
+    assert data[2][M.MASK_COORDS].shape == (4, 64, 2) and data[1].shape == data[0].shape
+    den = ssdn.Denoiser(make_cfg("n2v", None, 3), device="cuda")
+    out = den.run_pipeline(data)
+    out[PipelineOutput.LOSS].mean().backward()
+    assert torch.isfinite(out[PipelineOutput.LOSS]).all()
