@@ -49,3 +49,17 @@ def test_product_package_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):
                 assert "ssdn_oracle" not in open(os.path.join(dirpath, f)).read(), f
+
+
+def test_python_binding_arity_matches_header(engine):
+    """Every ctypes signature in ssdn/_engine.py has exactly as many arguments as the prototype in include/ssdn_b200.h
+    (a drifted prototype would corrupt the call silently: ctypes cannot check it)."""
+    text = open(os.path.join(ROOT, "include", "ssdn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(ssdn_\w+)\s*\(([^)]*)\)\s*;", text))
+    assert set(protos) == set(engine.EXPORTS)
+    from ssdn import _engine
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert n == len(_engine._SIGNATURES[name][1]), (name, n, len(_engine._SIGNATURES[name][1]))
