@@ -8,17 +8,14 @@ from ssdn.params import ConfigValue, DatasetType, NoiseAlgorithm, Pipeline
 
 DEFAULT_RUN_DIR = "runs"
 
-_DEFAULTS = (
-    (ConfigValue.TRAIN_ITERATIONS, 2000000), (ConfigValue.TRAIN_MINIBATCH_SIZE, 4), (ConfigValue.TEST_MINIBATCH_SIZE, 2),
-    (ConfigValue.IMAGE_CHANNELS, 3), (ConfigValue.TRAIN_PATCH_SIZE, 64), (ConfigValue.LEARNING_RATE, 3e-4),
-    # NB: train.py hands these two to compute_ramped_lrate in swapped positions (see ssdn.train.learning_rate);
-    # the stored numbers are kept identical to the reference so the EFFECTIVE schedule is identical too.
-    (ConfigValue.LR_RAMPDOWN_FRACTION, 0.1), (ConfigValue.LR_RAMPUP_FRACTION, 0.3),
-    (ConfigValue.EVAL_INTERVAL, 10000), (ConfigValue.PRINT_INTERVAL, 1000), (ConfigValue.SNAPSHOT_INTERVAL, 10000),
-    (ConfigValue.DATALOADER_WORKERS, 4), (ConfigValue.PIN_DATA_MEMORY, False), (ConfigValue.DIAGONAL_COVARIANCE, False),
-    (ConfigValue.TRAIN_DATA_PATH, None), (ConfigValue.TRAIN_DATASET_TYPE, None), (ConfigValue.TRAIN_DATASET_NAME, None),
-    (ConfigValue.TEST_DATA_PATH, None), (ConfigValue.TEST_DATASET_TYPE, None), (ConfigValue.TEST_DATASET_NAME, None),
-)
+# Defaults of the reference (cfg.py:10-38), keyed by ConfigValue member name.
+# NB: train.py hands the two ramp fractions to compute_ramped_lrate in swapped positions (see ssdn.train.learning_rate);
+# the stored numbers are kept identical to the reference so the EFFECTIVE schedule is identical too.
+_DEFAULTS = {getattr(ConfigValue, name): value for name, value in dict(
+    TRAIN_ITERATIONS=2000000, TRAIN_MINIBATCH_SIZE=4, TEST_MINIBATCH_SIZE=2, IMAGE_CHANNELS=3, TRAIN_PATCH_SIZE=64, LEARNING_RATE=3e-4,
+    LR_RAMPDOWN_FRACTION=0.1, LR_RAMPUP_FRACTION=0.3, EVAL_INTERVAL=10000, PRINT_INTERVAL=1000, SNAPSHOT_INTERVAL=10000,
+    DATALOADER_WORKERS=4, PIN_DATA_MEMORY=False, DIAGONAL_COVARIANCE=False, TRAIN_DATA_PATH=None, TRAIN_DATASET_TYPE=None,
+    TRAIN_DATASET_NAME=None, TEST_DATA_PATH=None, TEST_DATASET_TYPE=None, TEST_DATASET_NAME=None).items()}
 
 
 def base() -> Dict:
