@@ -6,7 +6,8 @@ Differences that are deliberate and documented in DESIGN.md:
   * networks are NOT wrapped in ``nn.DataParallel`` (one process per GPU with a single gradient
     all-reduce replaces it, see ssdn.train); a transparent wrapper keeps the ``models.<id>.module.*`` keys;
   * ``forward`` works (in the reference it raises IndexError for every pipeline);
-  * Poisson noise styles and the diagonal-covariance option are not implemented by the engine."""
+  * the diagonal-covariance option is not implemented by the engine (it is dead code in the reference: denoiser.py:240
+    raises TypeError)."""
 from __future__ import annotations
 
 from typing import Dict, List

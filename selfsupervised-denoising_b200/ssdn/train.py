@@ -10,6 +10,7 @@ from __future__ import annotations
 import glob
 import os
 import re
+from collections import defaultdict
 from typing import Callable, Dict, Iterable, List, Optional
 
 import torch
@@ -17,7 +18,7 @@ import torch.distributed as dist
 
 import ssdn
 from ssdn import _engine as E
-from ssdn.datasets import NoisyDataset
+from ssdn.datasets import FixedLengthSampler, NoisyDataset, SamplingOrder
 from ssdn.denoiser import Denoiser
 from ssdn.params import ConfigValue, HistoryValue, PipelineOutput, StateValue
 from ssdn.utils import Metric, MetricDict, TrackedTime, compute_ramped_lrate
@@ -53,14 +54,63 @@ class FlatAdam:
                     grad_scale)
 
     def state_dict(self) -> Dict:
-        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "param_groups": self.param_groups}
+        """Wire format of ``torch.optim.Adam.state_dict()`` - what the reference stores under ``"optimizer"`` in a
+        ``.training`` file (train.py:724): per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` keyed by the parameter's
+        position in ``denoiser.parameters()``, and one parameter group.  The per-parameter moments are views of the two
+        flat buffers, so the file holds each buffer once."""
+        params = list(self.denoiser.parameters())
+        state = {}
+        if self.step_count > 0 and self.exp_avg is not None:
+            off = 0
+            for i, p in enumerate(params):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.exp_avg[off:off + n].view(p.shape),
+                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape)}
+                off += n
+        g = self.param_groups[0]
+        group = {"lr": g["lr"], "betas": tuple(g["betas"]), "eps": g["eps"], "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, state: Dict):
-        self.step_count = state["step"]
-        self.param_groups = state["param_groups"]
+        """Accepts ``torch.optim.Adam`` state dictionaries (any torch version: integer or tensor ``step``) as written by
+        the reference trainer or by state_dict() above, and the flat layout early versions of this package wrote."""
         dev = self.denoiser.device
-        self.exp_avg = None if state["exp_avg"] is None else state["exp_avg"].to(dev)
-        self.exp_avg_sq = None if state["exp_avg_sq"] is None else state["exp_avg_sq"].to(dev)
+        if "state" not in state:                                   # flat layout
+            self.step_count = int(state["step"])
+            self.param_groups = [dict(g) for g in state["param_groups"]]
+            self.exp_avg = None if state["exp_avg"] is None else state["exp_avg"].to(dev)
+            self.exp_avg_sq = None if state["exp_avg_sq"] is None else state["exp_avg_sq"].to(dev)
+            return
+        groups = state["param_groups"]
+        if len(groups) != 1:
+            raise ValueError("expected one Adam parameter group, found {}".format(len(groups)))
+        g = groups[0]
+        if g.get("weight_decay", 0) != 0 or g.get("amsgrad", False) or g.get("maximize", False):
+            raise NotImplementedError("the engine's Adam step has no weight decay / amsgrad / maximize")
+        params = list(self.denoiser.parameters())
+        if len(g["params"]) != len(params):
+            raise ValueError("optimizer state holds {} parameters, the denoiser has {}".format(len(g["params"]), len(params)))
+        self.param_groups = [{"lr": g["lr"], "betas": tuple(g["betas"]), "eps": g["eps"]}]
+        per_param = state["state"]
+        self.step_count = max((int(float(s["step"])) for s in per_param.values()), default=0)
+        if not per_param:
+            self.exp_avg = self.exp_avg_sq = None
+            return
+        total = sum(p.numel() for p in params)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for key, p in zip(g["params"], params):
+            n = p.numel()
+            s = per_param.get(key)
+            if s is not None:
+                if s["exp_avg"].numel() != n:
+                    raise ValueError("optimizer state of parameter {} has {} elements, expected {}".format(key, s["exp_avg"].numel(), n))
+                self.exp_avg[off:off + n].copy_(s["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(s["exp_avg_sq"].reshape(-1))
+            off += n
 
 
 def train_step(denoiser: Denoiser, optimizer: FlatAdam, data: List, world_size: int = 1) -> Dict:
@@ -99,6 +149,8 @@ class DenoiserTrainer:
         self.state = state if state is not None else {}
         self._denoiser: Optional[Denoiser] = None
         self._optimizer: Optional[FlatAdam] = None
+        self._train_iter: Optional[SamplingOrder] = None       # restored sample order waiting for a sampler (train.py:743,795-797)
+        self.train_sampler: Optional[FixedLengthSampler] = None
         self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
     @property
@@ -120,8 +172,29 @@ class DenoiserTrainer:
     def init_state(self):
         self.state[StateValue.INITIALISED] = True
         self.state[StateValue.ITERATION] = 0
+        # same containers as train.py:114-125 - they are pickled inside .training files and the reference indexes
+        # TIMINGS with keys it has not created yet ("last_print", "eta")
         self.state[StateValue.HISTORY] = {HistoryValue.TRAIN: MetricDict(), HistoryValue.EVAL: MetricDict(),
-                                          HistoryValue.TIMINGS: {"total": TrackedTime()}}
+                                          HistoryValue.TIMINGS: defaultdict(TrackedTime)}
+        self.reset_metrics()
+
+    def reset_metrics(self, eval: bool = True, train: bool = True):
+        """Empty the metric accumulators; the sample counter "n" is a plain integer next to them (train.py:515-533)."""
+        chosen = ([HistoryValue.TRAIN] if train else []) + ([HistoryValue.EVAL] if eval else [])
+        for which in chosen:
+            metrics = self.state[StateValue.HISTORY][which]
+            metrics["n"] = 0
+            for m in metrics.values():
+                if isinstance(m, Metric):
+                    m.reset()
+
+    def attach_sampler(self, sampler: FixedLengthSampler):
+        """Register the sampler that orders the training data, so that snapshots record its order and position and a
+        resumed run continues the same order (train.py:721-723,795-797)."""
+        self.train_sampler = sampler
+        if self._train_iter is not None:
+            sampler.for_next_iter(self._train_iter)
+            self._train_iter = None
 
     @property
     def learning_rate(self) -> float:
@@ -145,7 +218,7 @@ class DenoiserTrainer:
             outputs = train_step(self.denoiser, self.optimizer, data, self.world_size)
             n = data[NoisyDataset.INPUT].shape[0]
             with torch.no_grad():
-                history["n"] += torch.full((n,), 1.0)
+                history["n"] += n
                 history["loss"] += outputs[PipelineOutput.LOSS]
                 clean = self._clean(data)
                 if clean is not None:
@@ -198,8 +271,14 @@ class DenoiserTrainer:
         return os.path.join(self.runs_dir, self._run_dir)
 
     def state_dict(self) -> Dict:
-        return {"denoiser": self.denoiser.state_dict(), "state": self.state, "optimizer": self._optimizer.state_dict(),
-                "rng": torch.get_rng_state()}
+        """The reference's ``.training`` layout (train.py:711-726): denoiser, trainer state, the sample order with its
+        cursor set to the images actually processed, ``torch.optim.Adam`` state, CPU RNG state.  Without an attached
+        sampler (the on-GPU input pipeline is a pure function of (seed, step) and needs none) the order is empty."""
+        order = self.train_sampler.last_iter() if self.train_sampler is not None else self._train_iter
+        order_state = dict(order.state_dict()) if order is not None else {"order": []}
+        order_state["index"] = self.state[StateValue.ITERATION]
+        return {"denoiser": self.denoiser.state_dict(), "state": self.state, "train_order_iter": order_state,
+                "optimizer": self._optimizer.state_dict(), "rng": torch.get_rng_state()}
 
     def load_state_dict(self, state_dict, device: str = None):
         if isinstance(state_dict, str):
@@ -207,6 +286,10 @@ class DenoiserTrainer:
         self.denoiser = Denoiser.from_state_dict(state_dict["denoiser"], device=device)
         self.cfg = self.denoiser.cfg
         self.state = state_dict["state"]
+        if "train_order_iter" in state_dict:
+            self._train_iter = SamplingOrder.from_state_dict(state_dict["train_order_iter"])
+            if self.train_sampler is not None:
+                self.attach_sampler(self.train_sampler)
         self._optimizer.load_state_dict(state_dict["optimizer"])
         torch.set_rng_state(state_dict["rng"])
 
@@ -234,4 +317,7 @@ def resume_run(run_dir: str, iteration: int = None, device: str = None) -> Denoi
     run_dir = os.path.abspath(run_dir)
     trainer = DenoiserTrainer(None, runs_dir=os.path.dirname(run_dir), run_dir=os.path.basename(run_dir))
     trainer.load_state_dict(snaps[it], device=device)
+    for timing in trainer.state[StateValue.HISTORY][HistoryValue.TIMINGS].values():     # stale absolute times
+        if isinstance(timing, TrackedTime):
+            timing.forget()
     return trainer

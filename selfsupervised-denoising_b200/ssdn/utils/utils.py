@@ -72,7 +72,8 @@ class Metric:
                 value = value.mean(dim=dims)
         if self.batched:
             value = value.sum(dim=0)
-        self.total = value if self.total is None else self.total + value
+        # a resumed history arrives on the CPU (map_location) while new values live on the training device
+        self.total = value if self.total is None else self.total.to(value.device) + value
         self.n += n
 
     def __add__(self, value):

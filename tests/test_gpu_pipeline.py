@@ -197,3 +197,51 @@ def test_forward_at_256_uses_row_windows(engine):
     out = plan.forward(flat, x.cuda(), training=False)
     plan.check()
     assert rel(out, O.noise_network_forward(p, x, True)) < TOL
+
+
+def test_trainer_snapshot_and_resume_continue_the_run(engine, tmp_path):
+    """SURVEY.md 8f rank 3 on the device: two steps, snapshot (reference ``.training`` layout, tests/test_training_wire.py),
+    ``resume_run``, one more step == three uninterrupted steps.  The Adam moments travel through the per-parameter
+    torch.optim.Adam layout and back into the flat buffers; the learning rate follows the restored image counter."""
+    from ssdn.params import ConfigValue, HistoryValue, StateValue
+    from ssdn.train import DenoiserTrainer, resume_run
+    M = NoisyDataset.Metadata
+    batches = []
+    for s in range(3):
+        clean, noisy = O.synthetic_batch(8, 3, 32, seed=900 + s)
+        batches.append([noisy, torch.zeros(0), {M.CLEAN: clean, M.INPUT_NOISE_VALUES: torch.full((8, 1, 1, 1), 25 / 255)}])
+
+    def fresh(run):
+        cfg = make_cfg("ssdn", "const")
+        cfg[ConfigValue.TRAIN_ITERATIONS] = 80          # LR: 0 at image 0, 3e-4 from image 8 on (ramp-up over the first 10 %)
+        torch.manual_seed(3)
+        t = DenoiserTrainer(cfg, runs_dir=str(tmp_path), run_dir=run)
+        t.new_target(device="cuda")
+        return t
+
+    losses = {}
+    straight = fresh("straight")
+    straight.train(batches, on_step=lambda it, out: losses.setdefault(("straight", it), out[PipelineOutput.LOSS].detach().mean().item()))
+    first = fresh("interrupted")
+    first.train(batches[:2])
+    assert first.state[StateValue.ITERATION] == 16 and first.learning_rate == pytest.approx(3e-4)
+    path = first.snapshot()
+    assert path.endswith("model_00000016.training")
+    del first
+    resumed = resume_run(str(tmp_path / "interrupted"), device="cuda")
+    assert resumed.state[StateValue.ITERATION] == 16 and resumed._optimizer.step_count == 2
+    assert resumed.learning_rate == pytest.approx(3e-4)
+    resumed.train(batches[2:], on_step=lambda it, out: losses.setdefault(("resumed", it), out[PipelineOutput.LOSS].detach().mean().item()))
+    torch.cuda.synchronize()
+    assert resumed.state[StateValue.ITERATION] == straight.state[StateValue.ITERATION] == 24
+    assert resumed._optimizer.step_count == straight._optimizer.step_count == 3
+    assert resumed.state[StateValue.HISTORY][HistoryValue.TRAIN]["n"] == 24
+    assert abs(losses[("resumed", 24)] - losses[("straight", 24)]) < 1e-5 * abs(losses[("straight", 24)]) + 1e-6
+    assert rel_l2(resumed._optimizer.exp_avg, straight._optimizer.exp_avg) < 1e-4
+    assert rel_l2(resumed._optimizer.exp_avg_sq, straight._optimizer.exp_avg_sq) < 1e-4
+    for (k, a), b in zip(resumed.denoiser.named_parameters(), straight.denoiser.parameters()):
+        if a.dim() > 1 and a.numel() > 1:
+            assert rel_l2(a, b) < 1e-4, k
+    a = float(resumed.state[StateValue.HISTORY][HistoryValue.TRAIN]["loss"].accumulated())
+    b = float(straight.state[StateValue.HISTORY][HistoryValue.TRAIN]["loss"].accumulated())
+    assert abs(a - b) < 1e-5 * abs(b) + 1e-6
