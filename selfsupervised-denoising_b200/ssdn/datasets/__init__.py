@@ -1,5 +1,6 @@
-from ssdn.datasets.noise_wrapper import NoisyDataset, NULL_IMAGE
-from ssdn.datasets.sampler import FixedLengthSampler, SamplingOrder
-from ssdn.datasets.gpu_pipeline import GpuNoisyPatches
+"""Batch sources: the reference's noisy-dataset wrapper and resumable sampler, plus the on-GPU patch pipeline."""
+from .gpu_pipeline import GpuNoisyPatches
+from .noise_wrapper import NULL_IMAGE, NoisyDataset
+from .sampler import FixedLengthSampler, SamplingOrder
 
-__all__ = ["NoisyDataset", "NULL_IMAGE", "FixedLengthSampler", "SamplingOrder", "GpuNoisyPatches"]
+__all__ = ["GpuNoisyPatches", "NULL_IMAGE", "NoisyDataset", "FixedLengthSampler", "SamplingOrder"]

@@ -1,4 +1,5 @@
-from ssdn.models.utility import Shift2d, Crop2d
-from ssdn.models.noise_network import NoiseNetwork, ShiftConv2d
+"""Network classes of the hot path (reference: ssdn/ssdn/models/)."""
+from .noise_network import NoiseNetwork, ShiftConv2d
+from .utility import Crop2d, Shift2d
 
-__all__ = ["Shift2d", "Crop2d", "NoiseNetwork", "ShiftConv2d"]
+__all__ = ["NoiseNetwork", "ShiftConv2d", "Crop2d", "Shift2d"]

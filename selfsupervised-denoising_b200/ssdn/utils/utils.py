@@ -44,14 +44,15 @@ class TrackedTime:
 
 
 def seconds_to_dhms(seconds: float, trim: bool = True) -> str:
-    parts = ((seconds // 86400, "d"), (seconds // 3600 % 24, "h"), (seconds // 60 % 60, "m"), (seconds % 60, "s"))
-    out = ""
-    for value, unit in parts:
-        if trim and value < 1:
-            continue
-        trim = False
-        out += "{:02}{}".format(int(value), unit)
-    return out
+    """'01d02h03m04s'; with trim, leading units that are zero are left out."""
+    minutes, secs = divmod(seconds, 60)
+    hours, minutes = divmod(minutes, 60)
+    days, hours = divmod(hours, 24)
+    fields = [(days, "d"), (hours, "h"), (minutes, "m"), (secs, "s")]
+    if trim:
+        while fields and fields[0][0] < 1:
+            fields.pop(0)
+    return "".join("{:02}{}".format(int(v), unit) for v, unit in fields)
 
 
 class Metric:
@@ -65,16 +66,17 @@ class Metric:
         self.total, self.n = None, 0
 
     def add(self, value: Tensor):
-        n = value.shape[0] if self.batched else 1
-        if self.collapse:
-            dims = list(range(1 if self.batched else 0, value.dim()))
-            if dims:
-                value = value.mean(dim=dims)
+        count = 1
+        lead = 0
+        if self.batched:
+            count, lead = value.shape[0], 1
+        if self.collapse and value.dim() > lead:
+            value = value.mean(dim=tuple(range(lead, value.dim())))
         if self.batched:
             value = value.sum(dim=0)
         # a resumed history arrives on the CPU (map_location) while new values live on the training device
         self.total = value if self.total is None else self.total.to(value.device) + value
-        self.n += n
+        self.n += count
 
     def __add__(self, value):
         self.add(value)

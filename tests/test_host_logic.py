@@ -193,6 +193,17 @@ def test_metric_accumulates_batch_means():
     m += torch.tensor([[9.0, 11.0]])
     assert m.n == 3 and abs(float(m.accumulated()) - 6.0) < 1e-6
     assert ssdn.utils.seconds_to_dhms(3661) == "01h01m01s"
+    assert ssdn.utils.seconds_to_dhms(0) == "" and ssdn.utils.seconds_to_dhms(59.9) == "59s"
+    assert ssdn.utils.seconds_to_dhms(90061.5) == "01d01h01m01s" and ssdn.utils.seconds_to_dhms(60, trim=False) == "00d00h01m00s"
+    whole = ssdn.utils.Metric(batched=False)
+    whole += torch.full((3, 2), 2.0)
+    assert whole.n == 1 and float(whole.accumulated()) == 2.0
+    keep = ssdn.utils.Metric(collapse=False)
+    keep += torch.ones(4, 3)
+    assert keep.accumulated(reset=True).tolist() == [1.0, 1.0, 1.0] and keep.empty() and keep.accumulated() is None
+    history = ssdn.utils.MetricDict()
+    history["psnr"] += torch.ones(2)
+    assert list(history) == ["psnr"] and history["psnr"].n == 2
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference checkpoints only exist in the build container")
