@@ -88,7 +88,7 @@ def study(name, x, w, dz, blind3x3):
 
     run("3xTF32 (today)", split_tf32, split_tf32, split_tf32)
     run("fp16x2, no scaling", lambda t: split_f16(t, 1.0), lambda t: split_f16(t, 1.0), lambda t: split_f16(t, 1.0))
-    for target in (14, 8, 0, -6, -10):
+    for target in (15, 14, 8, 6, 4, 0, -6, -10):
         s = lambda t, target=target: split_f16(t, pow2_scale(t, target))          # noqa: E731
         run(f"fp16x2, per-tensor 2^k scale, max -> 2^{target}", s, s, s)
     # one plane only (what a single-pass half-precision GEMM would give), for scale
