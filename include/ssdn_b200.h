@@ -126,6 +126,15 @@ int ssdn_noisy_crops(const unsigned char* images, int n_images, int c, int h, in
                      unsigned long long seed, unsigned long long step, int stream_id, float sigma_lo, float sigma_hi, int clip,
                      float* clean, float* noisy, float* sigma, void* stream);
 
+/* The same crops with the reference's Poisson styles ('poisson30', 'poisson5_50') — utils/noise.py:66-109 (add_poisson):
+ * noisy = (clean * lam + K) / lam with K ~ Poisson(1) per element (the reference's generator has the constant rate 1, kept),
+ * lam = lam_lo, or U(lam_lo, lam_hi) per sample AND channel when lam_hi > lam_lo; clipped to [0, 1] if clip.  lam [n][c]
+ * (may be NULL) is what the data loader reports as INPUT_NOISE_VALUES.  Same crop / image draws as ssdn_noisy_crops at equal
+ * (seed, step); other arguments as there. */
+int ssdn_poisson_crops(const unsigned char* images, int n_images, int c, int h, int w, const int* order, int n, int patch,
+                       unsigned long long seed, unsigned long long step, int stream_id, float lam_lo, float lam_hi, int clip,
+                       float* clean, float* noisy, float* lam, void* stream);
+
 /* Noise2Void "uniform pixel selection" — utils/n2v_ups.py:7-96 (manipulate, get_stratified_coords).  noisy / masked
  * [n][c][h][w] DEVICE fp32 (h, w multiples of 8; masked may alias noisy only if a stale read of a masked pixel is acceptable -
  * pass a separate buffer), coords DEVICE int64 [n][(h/8)*(w/8)][2] = (x, y) per 8x8 box in the reference's list order.

@@ -261,6 +261,21 @@ extern "C" int ssdn_noisy_crops(const unsigned char* images, int n_images, int c
   return 0;
 }
 
+extern "C" int ssdn_poisson_crops(const unsigned char* images, int n_images, int c, int h, int w, const int* order, int n, int patch,
+                                  unsigned long long seed, unsigned long long step, int stream_id, float lam_lo, float lam_hi, int clip,
+                                  float* clean, float* noisy, float* lam, void* stream) {
+  if (!images || !noisy) return fail(-1, "null image cache / output");
+  if (c < 1 || c > 4) return fail(-1, "1..4 image channels are supported");
+  if (n_images <= 0 || n <= 0 || patch <= 0 || patch > h || patch > w) return fail(-1, "patch %d does not fit %dx%d images", patch, h, w);
+  if (!(lam_lo > 0.f) || !(lam_hi > 0.f)) return fail(-1, "the Poisson scale must be positive");
+  const long long total = (long long)n * patch * patch;
+  inpk::poisson_crops_kernel<<<pw::grid_for(total), pw::kBlock, 0, (cudaStream_t)stream>>>(
+      images, n_images, c, h, w, order, n, patch, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+      (uint32_t)stream_id, lam_lo, lam_hi, clip, clean, noisy, lam);
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int ssdn_n2v_mask(const float* noisy, float* masked, long long* coords, int n, int c, int h, int w, int subpatch_size,
                              unsigned long long seed, unsigned long long step, void* stream) {
   if (!noisy || !masked || !coords) return fail(-1, "null pointer");

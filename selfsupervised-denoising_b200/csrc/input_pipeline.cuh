@@ -66,6 +66,50 @@ __global__ void noisy_crops_kernel(const unsigned char* __restrict__ images, int
   }
 }
 
+// Poisson(1) by inversion on one 32-bit uniform: k = #{i : x >= floor(CDF(i) * 2^32)}, CDF(i) = sum_{j<=i} e^-1 / j!.
+// The tail beyond k = 12 has probability 6e-11 < 2^-32 and is folded into k = 12.
+__device__ __forceinline__ int poisson1(uint32_t x) {
+  constexpr uint32_t T[12] = {0x5E2D58D8u, 0xBC5AB1B1u, 0xEB715E1Du, 0xFB239797u, 0xFF1025F5u, 0xFFD90F3Bu,
+                              0xFFFA8B71u, 0xFFFF540Cu, 0xFFFFED1Fu, 0xFFFFFE21u, 0xFFFFFFD4u, 0xFFFFFFFCu};
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) k += x >= T[i] ? 1 : 0;
+  return k;
+}
+
+// The reference's Poisson styles (utils/noise.py:66-109, 'poisson30', 'poisson5_50'): noisy = (clean * lam + K) / lam with
+// K ~ Poisson(1) drawn per element - the rate of the generator is the constant 1 in the reference, NOT clean * lam; kept as
+// is - and lam = lam_lo, or U(lam_lo, lam_hi) per sample AND channel for the range styles (leading axis of a CHW image).
+// Same thread mapping, crop and image draws as noisy_crops_kernel, so both kernels cut identical crops at a given
+// (seed, step, sample).
+__global__ void poisson_crops_kernel(const unsigned char* __restrict__ images, int n_images, int C, int H, int W, const int* __restrict__ order,
+                                     int n, int patch, uint32_t seed_lo, uint32_t seed_hi, uint32_t step_lo, uint32_t step_hi, uint32_t stream_id,
+                                     float lam_lo, float lam_hi, int clip, float* __restrict__ clean, float* __restrict__ noisy,
+                                     float* __restrict__ lam_out) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int pp = patch * patch;
+  if (idx >= (long long)n * pp) return;
+  const int s = (int)(idx / pp), pix = (int)(idx - (long long)s * pp);
+  const int y = pix / patch, x = pix - y * patch;
+  const Philox cs = philox4x32_10(step_lo, step_hi, (uint32_t)s, 0xFFFFFFFFu, seed_lo, seed_hi);
+  const int oy = (int)(((unsigned long long)cs.x[0] * (unsigned)(H - patch + 1)) >> 32);
+  const int ox = (int)(((unsigned long long)cs.x[1] * (unsigned)(W - patch + 1)) >> 32);
+  const Philox ss = philox4x32_10(step_lo, step_hi, (uint32_t)s, 0xFFFFFFFEu - stream_id, seed_lo, seed_hi);
+  const int img = order ? order[s] : (int)((step_lo * (unsigned)n + (unsigned)s) % (unsigned)n_images);
+  const Philox pn = philox4x32_10(step_lo, step_hi ^ (stream_id << 24), (uint32_t)s, (uint32_t)pix, seed_lo, seed_hi);
+  const unsigned char* src = images + ((long long)img * C * H + (oy + y)) * W + (ox + x);
+  for (int c = 0; c < C; ++c) {
+    const float lam = lam_hi > lam_lo ? lam_lo + (lam_hi - lam_lo) * u01(ss.x[c & 3]) : lam_lo;
+    const float v = (float)src[(long long)c * H * W] / 255.0f;
+    float nv = (v * lam + (float)poisson1(pn.x[c & 3])) / lam;          // mul_, add_, div_ of the reference, in that order
+    if (clip) nv = fminf(fmaxf(nv, 0.0f), 1.0f);
+    const long long o = ((long long)s * C + c) * pp + pix;
+    if (clean) clean[o] = v;
+    noisy[o] = nv;
+    if (lam_out && pix == 0) lam_out[s * C + c] = lam;
+  }
+}
+
 // Noise2Void masking (utils/n2v_ups.py:7-49, "uniform pixel selection"): one stratified coordinate per 8 x 8 box
 // (get_stratified_coords: box = round(sqrt(100 / 1.5)) = 8), each replaced by another pixel of the same image whose column is
 // drawn from [min(x - r, 0), min(x + r, W - 1)) \ {x} and row from [min(y - r, 0), min(y + r, H - 1)) \ {y} - the reference's

@@ -53,6 +53,8 @@ _SIGNATURES = {
     "ssdn_n2v_mask": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, ctypes.c_ulonglong, ctypes.c_ulonglong, _P]),
     "ssdn_noisy_crops": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, ctypes.c_ulonglong, ctypes.c_ulonglong, _I, ctypes.c_float, ctypes.c_float, _I,
                               _P, _P, _P, _P]),
+    "ssdn_poisson_crops": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, ctypes.c_ulonglong, ctypes.c_ulonglong, _I, ctypes.c_float, ctypes.c_float, _I,
+                                _P, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
@@ -341,6 +343,25 @@ def noisy_crops(images_u8, n, patch, seed, step, sigma_lo, sigma_hi=None, clip=T
     check(lib().ssdn_noisy_crops(_ptr(images_u8), ni, c, h, w, _ptr(order), n, patch, int(seed), int(step), int(stream_id), float(sigma_lo),
                                  float(hi), 1 if clip else 0, _ptr(clean), _ptr(noisy), _ptr(sigma), _stream()))
     return clean, noisy, sigma
+
+
+def poisson_crops(images_u8, n, patch, seed, step, lam_lo, lam_hi=None, clip=True, order=None, stream_id=0, want_clean=True):
+    """The same crops with the reference's Poisson styles (include/ssdn_b200.h: ssdn_poisson_crops; utils/noise.py:66-109).
+    Returns (clean or None, noisy, lam [n][C])."""
+    if not images_u8.is_cuda or images_u8.dtype != torch.uint8 or images_u8.dim() != 4:
+        raise EngineError("the image cache must be a CUDA uint8 tensor [n_images][C][H][W] (no CPU fallback exists)")
+    images_u8 = images_u8.contiguous()
+    ni, c, h, w = images_u8.shape
+    dev = images_u8.device
+    clean = torch.empty(n, c, patch, patch, device=dev) if want_clean else None
+    noisy = torch.empty(n, c, patch, patch, device=dev)
+    lam = torch.empty(n, c, device=dev)
+    if order is not None:
+        order = order.to(device=dev, dtype=torch.int32).contiguous()
+    hi = lam_lo if lam_hi is None else lam_hi
+    check(lib().ssdn_poisson_crops(_ptr(images_u8), ni, c, h, w, _ptr(order), n, patch, int(seed), int(step), int(stream_id), float(lam_lo),
+                                   float(hi), 1 if clip else 0, _ptr(clean), _ptr(noisy), _ptr(lam), _stream()))
+    return clean, noisy, lam
 
 
 def n2v_mask(noisy, seed, step, subpatch_size=5):

@@ -6,7 +6,8 @@ Reference: ``train.py:756-760`` (RandomCrop), ``datasets/noise_wrapper.py:98-163
 ``utils/noise.py:14-63`` (add_gaussian).  The reference feeds the GPU from 4 PIL / h5py worker processes; at the engine's
 step rate (> 4000 patches/s per GPU) that loader is the bottleneck by orders of magnitude.  Randomness is Philox
 counter-based: batches are a pure function of ``(seed, step)`` - a resumed run only needs the step counter - and parity
-with the CPU generator is statistical, not bit-wise.  Gaussian styles only (``gauss25``, ``gauss5_50``, ``_nc``).
+with the CPU generator is statistical, not bit-wise.  Gaussian (``gauss25``, ``gauss5_50``, ``_nc``) and the reference's
+Poisson styles (``poisson30``, ``poisson5_50``: ``ssdn_poisson_crops``).
 Noise2Void batches are masked on the device too (``ssdn_n2v_mask``, the reference's ``manipulate`` with its index quirks)."""
 from __future__ import annotations
 
@@ -20,21 +21,32 @@ from ssdn.datasets.noise_wrapper import NULL_IMAGE, NoisyDataset
 from ssdn.params import NoiseAlgorithm
 
 
-def parse_gaussian_style(style: str):
-    """'gauss25' -> (25/255, 25/255, clip); 'gauss5_50_nc' -> (5/255, 50/255, no clip).  Integers are 8-bit units."""
+def parse_style(style: str):
+    """'gauss25' -> ('gauss', 25/255, 25/255, clip); 'gauss5_50_nc' -> ('gauss', 5/255, 50/255, no clip); 'poisson30' ->
+    ('poisson', 30, 30, clip).  Integer parameters of the Gaussian styles are 8-bit units, Poisson parameters are taken
+    as written (utils/noise.py:57-58, 112-153)."""
     kind = re.findall(r"[a-zA-Z]+", style)[0]
-    if kind != "gauss":
-        raise NotImplementedError("the on-GPU input pipeline implements Gaussian noise styles only")
+    if kind not in ("gauss", "poisson"):
+        raise NotImplementedError("Noise type not supported")
     tokens = [t for t in style.replace(kind, "").split("_") if t != ""]
     clip = "nc" not in tokens
     tokens = [t for t in tokens if t != "nc"]
     as_float = any("." in t for t in tokens)
-    vals = [float(t) if as_float else int(t) / 255.0 for t in tokens]
+    unit = 255.0 if kind == "gauss" and not as_float else 1.0
+    vals = [float(t) / unit for t in tokens]
     if len(vals) == 1:
-        return vals[0], vals[0], clip
+        return kind, vals[0], vals[0], clip
     if len(vals) == 2:
-        return vals[0], vals[1], clip
+        return kind, vals[0], vals[1], clip
     raise ValueError(f"cannot parse noise style '{style}'")
+
+
+def parse_gaussian_style(style: str):
+    """(sigma_lo, sigma_hi, clip) of a Gaussian style string."""
+    kind, lo, hi, clip = parse_style(style)
+    if kind != "gauss":
+        raise NotImplementedError("not a Gaussian noise style: '{}'".format(style))
+    return lo, hi, clip
 
 
 class GpuNoisyPatches:
@@ -45,12 +57,13 @@ class GpuNoisyPatches:
             raise E.EngineError("image cache must be a CUDA uint8 tensor [n_images][C][H][W]")
         self.images, self.style, self.algorithm = images_u8.contiguous(), noise_style, algorithm
         self.patch, self.batch_size, self.seed = patch, batch_size, seed
-        self.sigma_lo, self.sigma_hi, self.clip = parse_gaussian_style(noise_style)
+        self.kind, self.sigma_lo, self.sigma_hi, self.clip = parse_style(noise_style)
+        self._crops = E.noisy_crops if self.kind == "gauss" else E.poisson_crops
 
     def batch(self, step: int) -> List:
         M = NoisyDataset.Metadata
         n, c = self.batch_size, self.images.shape[1]
-        clean, noisy, sigma = E.noisy_crops(self.images, n, self.patch, self.seed, step, self.sigma_lo, self.sigma_hi, self.clip)
+        clean, noisy, sigma = self._crops(self.images, n, self.patch, self.seed, step, self.sigma_lo, self.sigma_hi, self.clip)
         ranged = self.sigma_hi > self.sigma_lo
         coeff = sigma.reshape(n, c, 1, 1) if ranged else sigma[:, :1].reshape(n, 1, 1, 1)
         md: Dict = {M.CLEAN: clean, M.INPUT_NOISE_VALUES: coeff, M.IMAGE_SHAPE: torch.tensor([[c, self.patch, self.patch]] * n),
@@ -59,8 +72,8 @@ class GpuNoisyPatches:
             ref = clean
             md[M.REFERENCE_NOISE_VALUES] = torch.zeros(n, 1, 1, 1)
         elif self.algorithm in (NoiseAlgorithm.NOISE_TO_NOISE, NoiseAlgorithm.NOISE_TO_VOID):
-            _, ref, rs = E.noisy_crops(self.images, n, self.patch, self.seed, step, self.sigma_lo, self.sigma_hi, self.clip, stream_id=1,
-                                       want_clean=False)
+            _, ref, rs = self._crops(self.images, n, self.patch, self.seed, step, self.sigma_lo, self.sigma_hi, self.clip, stream_id=1,
+                                     want_clean=False)
             md[M.REFERENCE_NOISE_VALUES] = rs.reshape(n, c, 1, 1) if ranged else rs[:, :1].reshape(n, 1, 1, 1)
         elif self.algorithm == NoiseAlgorithm.SELFSUPERVISED_DENOISING_MEAN_ONLY:
             ref = noisy

@@ -77,7 +77,7 @@ def test_pipeline_batches_feed_the_denoiser(engine):
     a, b = (n2n[0] - n2n[2][M.CLEAN]), (n2n[1] - n2n[2][M.CLEAN])
     assert abs(float((a * b).mean()) / float((a * a).mean())) < 0.05          # ... independent noise realisations
     with pytest.raises(NotImplementedError):
-        GpuNoisyPatches(imgs, "poisson30", NoiseAlgorithm.SELFSUPERVISED_DENOISING, 32, 4)
+        GpuNoisyPatches(imgs, "speckle3", NoiseAlgorithm.SELFSUPERVISED_DENOISING, 32, 4)
     with pytest.raises(ValueError):
         engine.noisy_crops(imgs, 4, 128, 0, 0, 0.1)                           # patch larger than the images
 
