@@ -49,6 +49,17 @@ def parse_gaussian_style(style: str):
     return lo, hi, clip
 
 
+def image_cache_from_dataset(dataset, limit: int = None) -> torch.Tensor:
+    """uint8 [n][C][H][W] cache (CPU) from a dataset of clean float images in [0, 1], e.g. ``UnlabelledImageFolderDataset``;
+    8-bit sources survive exactly.  All images must have one size (crop or pad the data set first)."""
+    count = len(dataset) if limit is None else min(limit, len(dataset))
+    imgs = [dataset[i][0] for i in range(count)]
+    sizes = sorted({tuple(t.shape) for t in imgs})
+    if len(sizes) != 1:
+        raise ValueError("the image cache holds equal-size images, found {}".format(sizes[:4]))
+    return (torch.stack(imgs) * 255.0).round().clamp(0, 255).to(torch.uint8)
+
+
 class GpuNoisyPatches:
     """``batch(step)`` -> ``[input, reference, metadata]`` of ``batch_size`` noisy ``patch`` x ``patch`` crops."""
 
@@ -59,6 +70,11 @@ class GpuNoisyPatches:
         self.patch, self.batch_size, self.seed = patch, batch_size, seed
         self.kind, self.sigma_lo, self.sigma_hi, self.clip = parse_style(noise_style)
         self._crops = E.noisy_crops if self.kind == "gauss" else E.poisson_crops
+
+    @classmethod
+    def from_dataset(cls, dataset, noise_style: str, algorithm: NoiseAlgorithm, patch: int, batch_size: int, seed: int = 0,
+                     device: str = "cuda", limit: int = None) -> "GpuNoisyPatches":
+        return cls(image_cache_from_dataset(dataset, limit).to(device), noise_style, algorithm, patch, batch_size, seed)
 
     def batch(self, step: int) -> List:
         M = NoisyDataset.Metadata

@@ -4,8 +4,9 @@
 The evaluation path is the forward half of the hot path at image size: images are reflect-padded on the right / bottom
 to a square multiple of 32 (``NoisyDataset(pad_multiple=NoiseNetwork.input_wh_mul(), square=blindspot)``,
 noise_wrapper.py:183-232), denoised by ``Denoiser.run_pipeline`` on the CUDA engine, cropped back to the original
-top-left region and scored by PSNR against the clean image.  Image dumps, TensorBoard and the folder / HDF5 readers of the
-reference are outside the hot path; any iterable of ``NoisyDataset`` batches can be evaluated."""
+top-left region and scored by PSNR against the clean image.  ``set_test_data(path)`` + ``evaluate()`` reads a folder or HDF5
+test set as the reference does; any iterable of ``NoisyDataset`` batches can be evaluated too.  Image dumps and
+TensorBoard are outside the hot path."""
 from __future__ import annotations
 
 from typing import Callable, Dict, Iterable
@@ -30,6 +31,4 @@ class DenoiserEvaluator(DenoiserTrainer):
     def evaluate(self, batches: Iterable = None, output_callback: Callable[[int, Dict], None] = None) -> Dict:
         if self.denoiser is None:
             raise RuntimeError("Denoiser not initialised for evaluation")
-        if batches is None:
-            raise ValueError("pass an iterable of NoisyDataset batches (the dataset readers of the reference are out of scope)")
-        return super().evaluate(batches, output_callback)
+        return super().evaluate(batches, output_callback)      # batches None: the test set chosen with set_test_data(path)

@@ -18,9 +18,10 @@ import torch.distributed as dist
 
 import ssdn
 from ssdn import _engine as E
-from ssdn.datasets import FixedLengthSampler, NoisyDataset, SamplingOrder
+from ssdn.datasets import FixedLengthSampler, HDF5Dataset, NoisyDataset, SamplingOrder, UnlabelledImageFolderDataset
 from ssdn.denoiser import Denoiser
-from ssdn.params import ConfigValue, HistoryValue, PipelineOutput, StateValue
+from ssdn.models import NoiseNetwork
+from ssdn.params import ConfigValue, DatasetType, HistoryValue, PipelineOutput, StateValue
 from ssdn.utils import Metric, MetricDict, TrackedTime, compute_ramped_lrate
 
 DEFAULT_RUN_DIR = ssdn.cfg.DEFAULT_RUN_DIR
@@ -137,8 +138,7 @@ def learning_rate(cfg: Dict, iteration: int) -> float:
 class DenoiserTrainer:
     """Compact counterpart of the reference trainer: drives train_step over any iterable of NoisyDataset-style batches,
     keeps the iteration counter in IMAGES (train.py:221), accumulates the same metrics, snapshots and resumes.
-    TensorBoard, image dumps and the HDF5/folder dataset readers of the reference are outside the hot path and are
-    not reproduced (DESIGN.md)."""
+    TensorBoard and image dumps of the reference are outside the hot path and are not reproduced."""
 
     def __init__(self, cfg: Dict, state: Optional[Dict] = None, runs_dir: str = DEFAULT_RUN_DIR, run_dir: str = None):
         self.runs_dir = os.path.abspath(runs_dir)
@@ -206,10 +206,13 @@ class DenoiserTrainer:
             group["lr"] = self.learning_rate
         return self._optimizer
 
-    def train(self, batches: Iterable, on_step: Callable[[int, Dict], None] = None):
-        """Consume batches until TRAIN_ITERATIONS images have been seen."""
+    def train(self, batches: Iterable = None, on_step: Callable[[int, Dict], None] = None):
+        """Consume batches until TRAIN_ITERATIONS images have been seen.  Without ``batches`` the training set named by the
+        configuration is read through the reference's CPU loader (train_data); ``GpuNoisyPatches`` is the fast source."""
         if self.denoiser is None:
             self.new_target()
+        if batches is None:
+            batches, _, _ = self.train_data()
         history = self.state[StateValue.HISTORY][HistoryValue.TRAIN]
         self.denoiser.train()
         for data in batches:
@@ -238,8 +241,11 @@ class DenoiserTrainer:
             return md[NoisyDataset.Metadata.CLEAN].to(self.denoiser.device)
         return None
 
-    def evaluate(self, batches: Iterable, output_callback: Callable[[int, Dict], None] = None) -> Dict:
-        """Forward-only pass; returns mean PSNR of the denoised output (and of mu for SSDN) on the unpadded region."""
+    def evaluate(self, batches: Iterable = None, output_callback: Callable[[int, Dict], None] = None) -> Dict:
+        """Forward-only pass; returns mean PSNR of the denoised output (and of mu for SSDN) on the unpadded region.
+        Without ``batches`` the test set named by the configuration is used (test_data)."""
+        if batches is None:
+            batches, _, _ = self.test_data()
         self.denoiser.eval()
         metrics = MetricDict()
         idx = 0
@@ -260,6 +266,54 @@ class DenoiserTrainer:
                 idx += data[NoisyDataset.INPUT].shape[0]
         self.denoiser.train()
         return {k: float(v.accumulated()) for k, v in metrics.items()}
+
+    # ------------------------------------------------------------------ data sets named by the configuration (train.py:746-864)
+    def _clean_images(self, path: str, kind: DatasetType, transform=None):
+        if kind == DatasetType.FOLDER:
+            return UnlabelledImageFolderDataset(path, channels=self.cfg[ConfigValue.IMAGE_CHANNELS], transform=transform, recursive=True)
+        if kind == DatasetType.HDF5:
+            return HDF5Dataset(path, transform=transform, channels=self.cfg[ConfigValue.IMAGE_CHANNELS])
+        raise NotImplementedError("Dataset type not implemented")
+
+    def _loader(self, dataset: NoisyDataset, sampler: FixedLengthSampler, batch_size: int):
+        from torch.utils.data import DataLoader
+        return DataLoader(dataset, sampler=sampler, batch_size=batch_size, num_workers=self.cfg[ConfigValue.DATALOADER_WORKERS],
+                          pin_memory=self.cfg[ConfigValue.PIN_DATA_MEMORY])
+
+    def train_data(self):
+        """(DataLoader, NoisyDataset, FixedLengthSampler) over random TRAIN_PATCH_SIZE crops of the training images, in a
+        shuffled fixed-length order that snapshots record and resume."""
+        from torchvision.transforms import RandomCrop
+        cfg = self.cfg
+        crop = RandomCrop(cfg[ConfigValue.TRAIN_PATCH_SIZE], pad_if_needed=True, padding_mode="reflect")
+        images = self._clean_images(cfg[ConfigValue.TRAIN_DATA_PATH], cfg[ConfigValue.TRAIN_DATASET_TYPE], crop)
+        dataset = NoisyDataset(images, cfg[ConfigValue.NOISE_STYLE], cfg[ConfigValue.ALGORITHM], pad_uniform=False,
+                               pad_multiple=NoiseNetwork.input_wh_mul(), square=cfg[ConfigValue.BLINDSPOT], training_mode=True)
+        _ = dataset[0]
+        sampler = FixedLengthSampler(dataset, num_samples=cfg[ConfigValue.TRAIN_ITERATIONS], shuffled=True)
+        self.attach_sampler(sampler)
+        return self._loader(dataset, sampler, cfg[ConfigValue.TRAIN_MINIBATCH_SIZE]), dataset, sampler
+
+    def test_data(self):
+        """(DataLoader, NoisyDataset, FixedLengthSampler) over the whole test images, reflect-padded to one common size
+        that is a multiple of 32 (square for blind-spot networks); test_length(name) images, cycling if the set is smaller."""
+        cfg = self.cfg
+        images = self._clean_images(cfg[ConfigValue.TEST_DATA_PATH], cfg[ConfigValue.TEST_DATASET_TYPE])
+        dataset = NoisyDataset(images, cfg[ConfigValue.NOISE_STYLE], cfg[ConfigValue.ALGORITHM], pad_uniform=True,
+                               pad_multiple=NoiseNetwork.input_wh_mul(), square=cfg[ConfigValue.BLINDSPOT], training_mode=False)
+        _ = dataset[0]
+        sampler = FixedLengthSampler(dataset, num_samples=ssdn.cfg.test_length(cfg[ConfigValue.TEST_DATASET_NAME]), shuffled=False)
+        return self._loader(dataset, sampler, cfg[ConfigValue.TEST_MINIBATCH_SIZE]), dataset, sampler
+
+    def set_train_data(self, path: str):
+        self.cfg[ConfigValue.TRAIN_DATA_PATH] = path
+        self.cfg[ConfigValue.TRAIN_DATASET_TYPE] = self.cfg[ConfigValue.TRAIN_DATASET_NAME] = None
+        ssdn.cfg.infer_datasets(self.cfg)
+
+    def set_test_data(self, path: str):
+        self.cfg[ConfigValue.TEST_DATA_PATH] = path
+        self.cfg[ConfigValue.TEST_DATASET_TYPE] = self.cfg[ConfigValue.TEST_DATASET_NAME] = None
+        ssdn.cfg.infer_datasets(self.cfg)
 
     # ------------------------------------------------------------------ persistence (train.py:378-408, 711-745, 871-909)
     @property

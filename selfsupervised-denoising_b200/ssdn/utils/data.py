@@ -1,8 +1,12 @@
-"""Image tensor helpers (reference: ssdn/ssdn/utils/data.py): rotations, clipping, PSNR."""
+"""Image tensor helpers (reference: ssdn/ssdn/utils/data.py): rotations, clipping, PSNR, tensor <-> PIL image."""
+import numpy as np
 import torch
 from torch import Tensor
 
-__all__ = ["clip_img", "rotate", "mse2psnr", "calculate_psnr"]
+from ssdn.utils.data_format import batch, permute_tuple, unbatch
+
+__all__ = ["clip_img", "rotate", "mse2psnr", "calculate_psnr", "tensor2image", "show_tensor_image", "save_tensor_image",
+           "set_color_channels"]
 
 
 def _hw_dims(data_format: str):
@@ -48,3 +52,35 @@ def calculate_psnr(img: Tensor, ref: Tensor, data_format: str = "BCHW") -> Tenso
     else:
         mse = ((img - ref) ** 2).mean(dim=dims)
     return mse2psnr(mse, img.is_floating_point())
+
+
+def tensor2image(img: Tensor, data_format: str = "CHW"):
+    """Float image tensor in [0, 1] -> 8-bit PIL image (RGB or L).  A batch becomes one grid image."""
+    from PIL import Image
+    img = img.detach().cpu()
+    if img.dim() == 4:
+        import torchvision
+        grid = torchvision.utils.make_grid(img.permute(permute_tuple(batch(data_format), "BCHW")))
+        data_format = unbatch(data_format)
+        img = grid.permute(permute_tuple("CHW", data_format))
+    arr = np.clip(img.numpy(), 0, 1).transpose(*permute_tuple(data_format, "WHC"))
+    channels = arr.shape[-1]
+    if channels not in (1, 3):
+        raise NotImplementedError("Cannot convert image with {} channels to PIL image.".format(channels))
+    arr = np.uint8(arr * 255)
+    return Image.fromarray(arr, mode="RGB") if channels == 3 else Image.fromarray(np.squeeze(arr), mode="L")
+
+
+def show_tensor_image(img: Tensor, data_format: str = "CHW"):
+    tensor2image(img, data_format=data_format).show()
+
+
+def save_tensor_image(img: Tensor, path: str, data_format: str = "CHW"):
+    tensor2image(img, data_format=data_format).save(path)
+
+
+def set_color_channels(img, channels: int):
+    """PIL image with the requested number of channels: grey -> RGB replicates, RGB -> grey is PIL's weighted 'L'."""
+    if len(img.getbands()) != channels and channels in (1, 3):
+        return img.convert("L" if channels == 1 else "RGB")
+    return img

@@ -249,4 +249,94 @@ for alg, nv in ((NoiseAlgorithm.SELFSUPERVISED_DENOISING, NoiseValue.KNOWN), (No
         }
 OUT["pipeline.enum"] = [(p.name, p.value) for p in Pipeline]
 
+# ---------------------------------------------------------------- axis-order strings, PIL conversion
+from ssdn.utils import data_format as DF  # noqa: E402
+
+OUT["data_format"] = [[DF.permute_tuple(a, b) for a, b in (("CWH", "CHW"), ("BCHW", "BHWC"), ("HWC", "CHW"), ("CHW", "CHW"), ("BCWH", "BCHW"))],
+                      DF.batch("CHW"), DF.batch("BCHW"), DF.unbatch("BHWC"), DF.PIL_FORMAT, DF.PIL_BATCH_FORMAT,
+                      sorted(k for k in vars(DF.DataFormat) if k.isupper())]
+OUT["data_format.bad"] = attempt(lambda: DF.permute_tuple("CHW", "BCHW"))
+
+
+def pil_plain(im):
+    return {"size": list(im.size), "mode": im.mode, "sha256": hashlib.sha256(im.tobytes()).hexdigest()[:24]}
+
+
+gi = torch.Generator().manual_seed(8)
+OUT["tensor2image.rgb"] = pil_plain(ssdn.utils.tensor2image(torch.rand(3, 6, 9, generator=gi) * 1.2 - 0.1))
+OUT["tensor2image.grey"] = pil_plain(ssdn.utils.tensor2image(torch.rand(1, 6, 9, generator=gi)))
+OUT["tensor2image.hwc"] = pil_plain(ssdn.utils.tensor2image(torch.rand(6, 9, 3, generator=gi), "HWC"))
+OUT["tensor2image.batch"] = pil_plain(ssdn.utils.tensor2image(torch.rand(3, 3, 6, 9, generator=gi)))      # a batch becomes a grid
+OUT["tensor2image.two_channels"] = attempt(lambda: ssdn.utils.tensor2image(torch.rand(2, 6, 9)))
+
+# ---------------------------------------------------------------- folder data set and the loaders the trainer builds from a configuration
+import tempfile  # noqa: E402
+
+from PIL import Image  # noqa: E402
+
+from ssdn.datasets import UnlabelledImageFolderDataset  # noqa: E402
+
+if MODE == "reference":        # the header-only size reader the reference imports is absent here; give the stub the same contract
+    sys.modules["imagesize"].get = lambda path: Image.open(path).size
+root = tempfile.mkdtemp(prefix="battery_")
+kodak = os.path.join(root, "kodak_synth")
+os.makedirs(os.path.join(kodak, "more"))
+gi = torch.Generator().manual_seed(12)
+
+
+def write(path, size, mode):
+    w, h = size
+    bands = {"RGB": 3, "L": 1, "RGBA": 4}[mode]
+    arr = torch.randint(0, 256, (h, w, bands), generator=gi, dtype=torch.uint8).numpy()
+    Image.fromarray(arr.squeeze() if bands == 1 else arr, mode=mode).save(path)
+
+
+write(os.path.join(kodak, "b.png"), (56, 40), "RGB")
+write(os.path.join(kodak, "a.PNG"), (33, 64), "RGB")
+write(os.path.join(kodak, "c.bmp"), (32, 32), "L")
+write(os.path.join(kodak, "more", "d.png"), (24, 20), "RGBA")
+open(os.path.join(kodak, "notes.txt"), "w").write("not an image")
+for recursive in (False, True):
+    for channels in (3, 1):
+        fd = UnlabelledImageFolderDataset(kodak, recursive=recursive, channels=channels)
+        OUT["folder.{}.{}".format(recursive, channels)] = [len(fd), [os.path.relpath(f, kodak) for f in fd.files], [plain(fd[i]) for i in range(len(fd))],
+                                                          [plain(fd.image_size(i)) for i in range(len(fd))]]
+OUT["folder.empty"] = attempt(lambda: UnlabelledImageFolderDataset(os.path.join(kodak, "more"), extensions=[".jpg"]))
+OUT["set_color_channels"] = [pil_plain(ssdn.utils.set_color_channels(Image.open(os.path.join(kodak, f)), ch)) for f in ("b.png", "c.bmp") for ch in (1, 3)]
+from torchvision.transforms import RandomCrop  # noqa: E402
+
+torch.manual_seed(21)
+fd = UnlabelledImageFolderDataset(kodak, recursive=True, transform=RandomCrop(48, pad_if_needed=True, padding_mode="reflect"))
+OUT["folder.randomcrop"] = [[plain(fd[i]) for i in range(len(fd))], plain(fd.image_size(1)), plain(fd.image_size(1, ignore_transform=True))]
+torch.manual_seed(22)
+OUT["noise_transform"] = plain(ssdn.utils.transforms.NoiseTransform("gauss25")(torch.rand(2, 3, 8, 8)))
+
+from ssdn.train import DenoiserTrainer  # noqa: E402
+
+for alg, nv in ((NoiseAlgorithm.SELFSUPERVISED_DENOISING, NoiseValue.KNOWN), (NoiseAlgorithm.NOISE_TO_VOID, NoiseValue.KNOWN)):
+    def loaders():
+        cfg = ssdn.cfg.base()
+        cfg[ConfigValue.ALGORITHM], cfg[ConfigValue.NOISE_VALUE], cfg[ConfigValue.NOISE_STYLE] = alg, nv, "gauss25"
+        cfg[ConfigValue.TRAIN_DATA_PATH] = cfg[ConfigValue.TEST_DATA_PATH] = kodak
+        cfg[ConfigValue.DATALOADER_WORKERS] = 0
+        cfg[ConfigValue.TRAIN_ITERATIONS], cfg[ConfigValue.TRAIN_MINIBATCH_SIZE], cfg[ConfigValue.TEST_MINIBATCH_SIZE] = 10, 3, 2
+        trainer = DenoiserTrainer(cfg, state={}, runs_dir=root)
+        described = [plain({k.name: trainer.cfg[k] for k in (ConfigValue.TRAIN_DATASET_NAME, ConfigValue.TRAIN_DATASET_TYPE,
+                                                              ConfigValue.TEST_DATASET_NAME, ConfigValue.TEST_DATASET_TYPE)})]
+        torch.manual_seed(31)
+        loader, dataset, sampler = trainer.train_data()
+        described.append([len(loader), len(dataset), len(sampler), [plain(list(b)) for b in loader]])
+        torch.manual_seed(32)
+        loader, dataset, sampler = trainer.test_data()
+        it = iter(loader)
+        described.append([len(loader), len(dataset), len(sampler), plain(dataset.max_image_size), [plain(list(next(it))) for _ in range(3)]])
+        trainer.set_test_data(os.path.join(root, "kodak_synth", "more"))
+        described.append(plain({k.name: trainer.cfg[k] for k in (ConfigValue.TEST_DATASET_NAME, ConfigValue.TEST_DATASET_TYPE)}))
+        described.append(os.path.relpath(trainer.cfg[ConfigValue.TEST_DATA_PATH], root))
+        return described
+    OUT["trainer.loaders." + alg.name] = attempt(loaders)
+
+import shutil  # noqa: E402
+
+shutil.rmtree(root, ignore_errors=True)
 print("JSON " + json.dumps(OUT))

@@ -223,3 +223,27 @@ def test_reference_checkpoints_load_and_round_trip(name, tmp_path):
     torch.save(sd, path)
     again = torch.load(path, map_location="cpu", weights_only=False)
     assert set(again) == set(st) and all(torch.equal(again[k], v) for k, v in st.items() if torch.is_tensor(v))
+
+
+def test_image_cache_from_folder_dataset(tmp_path):
+    """Folder of 8-bit images -> the uint8 cache of the on-GPU input pipeline, bit-exact; unequal sizes are refused."""
+    import numpy as np
+    from PIL import Image
+    from ssdn.datasets import UnlabelledImageFolderDataset
+    from ssdn.datasets.gpu_pipeline import image_cache_from_dataset
+    rng = np.random.default_rng(0)
+    arrs = [rng.integers(0, 256, (24, 40, 3), dtype=np.uint8) for _ in range(3)]
+    for i, a in enumerate(arrs):
+        Image.fromarray(a, mode="RGB").save(tmp_path / "img{}.png".format(i))
+    ds = UnlabelledImageFolderDataset(str(tmp_path), output_format=None)        # to_tensor layout: C x H x W
+    cache = image_cache_from_dataset(ds)
+    assert cache.dtype == torch.uint8 and cache.shape == (3, 3, 24, 40)
+    assert all(np.array_equal(cache[i].permute(1, 2, 0).numpy(), a) for i, a in enumerate(arrs))
+    assert image_cache_from_dataset(ds, limit=2).shape[0] == 2
+    Image.fromarray(rng.integers(0, 256, (30, 40, 3), dtype=np.uint8), mode="RGB").save(tmp_path / "odd.png")
+    with pytest.raises(ValueError):
+        image_cache_from_dataset(UnlabelledImageFolderDataset(str(tmp_path), output_format=None))
+    import importlib.util
+    if importlib.util.find_spec("h5py") is None:                                 # not installed in this image: a clear error, not a crash
+        with pytest.raises(ImportError):
+            ssdn.datasets.HDF5Dataset(str(tmp_path / "missing.h5"))
