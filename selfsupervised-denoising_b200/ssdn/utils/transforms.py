@@ -1,16 +1,18 @@
-"""Dataset transforms (reference: ssdn/ssdn/utils/transforms.py)."""
-from typing import NewType
+"""Callable transforms for data sets (reference: ssdn/ssdn/utils/transforms.py).
 
-import ssdn
+``Transform`` only labels "anything a data set may call on a loaded image" in type hints.  ``NoiseTransform("gauss25")(x)``
+returns ``x`` with the named synthetic noise applied - the noisy half of ``ssdn.utils.noise.add_style``'s result, the noise
+parameters are dropped."""
+from typing import NewType
 
 Transform = NewType("Transform", object)
 
 
 class NoiseTransform:
-    """Callable that applies a noise style string ('gauss25', 'poisson30', ...) to a batch of images."""
-
     def __init__(self, style: str):
         self.style = style
 
     def __call__(self, imgs):
-        return ssdn.utils.noise.add_style(imgs, self.style)[0]
+        from ssdn.utils.noise import add_style
+        noisy, _params = add_style(imgs, self.style)
+        return noisy
