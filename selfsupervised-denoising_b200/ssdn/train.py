@@ -8,6 +8,7 @@ one NCCL all-reduce of that buffer per step (the mean over ranks is folded into 
 from __future__ import annotations
 
 import glob
+import logging
 import os
 import re
 from collections import defaultdict
@@ -25,6 +26,7 @@ from ssdn.params import ConfigValue, DatasetType, HistoryValue, PipelineOutput, 
 from ssdn.utils import Metric, MetricDict, TrackedTime, compute_ramped_lrate
 
 DEFAULT_RUN_DIR = ssdn.cfg.DEFAULT_RUN_DIR
+logger = logging.getLogger("ssdn.train")
 
 
 class FlatAdam:
@@ -152,6 +154,8 @@ class DenoiserTrainer:
         self._train_iter: Optional[SamplingOrder] = None       # restored sample order waiting for a sampler (train.py:743,795-797)
         self.train_sampler: Optional[FixedLengthSampler] = None
         self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world_size > 1 else 0
+        self.last_eval: Optional[Dict] = None
 
     @property
     def denoiser(self) -> Denoiser:
@@ -206,16 +210,26 @@ class DenoiserTrainer:
             group["lr"] = self.learning_rate
         return self._optimizer
 
-    def train(self, batches: Iterable = None, on_step: Callable[[int, Dict], None] = None):
+    def train(self, batches: Iterable = None, on_step: Callable[[int, Dict], None] = None, intervals: bool = None):
         """Consume batches until TRAIN_ITERATIONS images have been seen.  Without ``batches`` the training set named by the
-        configuration is read through the reference's CPU loader (train_data); ``GpuNoisyPatches`` is the fast source."""
+        configuration is read through the reference's CPU loader (train_data); ``GpuNoisyPatches`` is the fast source.
+        ``intervals`` (default: on when the trainer reads its own data) adds the reference's housekeeping at multiples of
+        EVAL_INTERVAL / PRINT_INTERVAL / SNAPSHOT_INTERVAL images and the final snapshot + ``final-<config>.wt``
+        (train.py:155-181, 223-231)."""
         if self.denoiser is None:
             self.new_target()
+        if intervals is None:
+            intervals = batches is None
         if batches is None:
             batches, _, _ = self.train_data()
+        test_batches = None
+        if intervals and self.cfg.get(ConfigValue.TEST_DATA_PATH):
+            test_batches, _, _ = self.test_data()
         history = self.state[StateValue.HISTORY][HistoryValue.TRAIN]
         self.denoiser.train()
         for data in batches:
+            if intervals:
+                self._housekeeping(test_batches)
             if self.state[StateValue.ITERATION] >= self.cfg[ConfigValue.TRAIN_ITERATIONS]:
                 break
             outputs = train_step(self.denoiser, self.optimizer, data, self.world_size)
@@ -234,6 +248,44 @@ class DenoiserTrainer:
             self.state[StateValue.ITERATION] += n * self.world_size
             if on_step:
                 on_step(self.state[StateValue.ITERATION], outputs)
+        if intervals and self.state[StateValue.ITERATION] >= self.cfg[ConfigValue.TRAIN_ITERATIONS]:
+            self._housekeeping(test_batches)
+            if self.rank == 0:
+                self.snapshot()
+                self.snapshot(output_name="final-{}.wt".format(self.denoiser.config_name()), subdir="", model_only=True)
+
+    def _housekeeping(self, test_batches: Iterable = None):
+        """What the reference does at the top of every iteration (train.py:155-181): evaluate, report and reset the metric
+        window, snapshot - each when the image counter is a multiple of its interval."""
+        iteration = self.state[StateValue.ITERATION]
+        history = self.state[StateValue.HISTORY]
+        if getattr(self, "_housekept", None) == iteration:       # once per value of the image counter
+            return
+        self._housekept = iteration
+        if test_batches is not None and iteration % self.cfg[ConfigValue.EVAL_INTERVAL] == 0:
+            self.last_eval = self.evaluate(test_batches)
+            self.denoiser.train()
+        if iteration % self.cfg[ConfigValue.PRINT_INTERVAL] == 0:
+            history[HistoryValue.TIMINGS]["total"].update()
+            if self.rank == 0:
+                logger.info(self.state_str())
+            self.reset_metrics()
+        if iteration % self.cfg[ConfigValue.SNAPSHOT_INTERVAL] == 0 and self.rank == 0:
+            self.snapshot()
+
+    def state_str(self) -> str:
+        """One line per metric window: image counter, learning rate, means of the accumulated training metrics and the last
+        evaluation result."""
+        train = self.state[StateValue.HISTORY][HistoryValue.TRAIN]
+        parts = ["n={}".format(train["n"]), "lr={:.3e}".format(self.learning_rate)]
+        for name, metric in train.items():
+            if isinstance(metric, Metric) and not metric.empty():
+                parts.append("{}={:.4f}".format(name, float(metric.accumulated().mean())))
+        line = "[{:08d}] TRAIN | {}".format(self.state[StateValue.ITERATION], ", ".join(parts))
+        if getattr(self, "last_eval", None):
+            line += " | VALID " + ", ".join("{}={:.4f}".format(k, v) for k, v in self.last_eval.items())
+        total = self.state[StateValue.HISTORY][HistoryValue.TIMINGS]["total"].total
+        return line + " | " + (ssdn.utils.seconds_to_dhms(total) or "0s")
 
     def _clean(self, data):
         md = data[NoisyDataset.METADATA] if len(data) > NoisyDataset.METADATA else None

@@ -198,3 +198,62 @@ def test_flat_adam_accepts_old_torch_and_flat_layouts(tmp_path):
     bad["param_groups"][0]["params"] = bad["param_groups"][0]["params"][:-1]
     with pytest.raises(ValueError):
         other.load_state_dict(bad)
+
+
+def test_trainer_housekeeping_intervals_on_its_own_data(tmp_path, monkeypatch, caplog):
+    """The reference-style run: the trainer reads a folder data set through its own loaders and, at multiples of the
+    configured intervals, evaluates, reports + resets the metric window and snapshots; it ends with a snapshot and
+    ``final-<config>.wt`` (train.py:155-181, 223-231).  The engine calls are replaced by stand-ins (no GPU here): what is
+    under test is the host-side sequencing around them."""
+    import logging
+    import numpy as np
+    from PIL import Image
+    from ssdn.params import PipelineOutput
+    data_dir = tmp_path / "kodak_tiny"
+    data_dir.mkdir()
+    rng = np.random.default_rng(1)
+    for i in range(3):
+        Image.fromarray(rng.integers(0, 256, (40, 48, 3), dtype=np.uint8), mode="RGB").save(data_dir / "im{}.png".format(i))
+    cfg = _cfg("known")
+    cfg[ConfigValue.IMAGE_CHANNELS] = 3
+    cfg[ConfigValue.TRAIN_DATA_PATH] = cfg[ConfigValue.TEST_DATA_PATH] = str(data_dir)
+    cfg[ConfigValue.DATALOADER_WORKERS] = 0
+    cfg[ConfigValue.TRAIN_ITERATIONS], cfg[ConfigValue.TRAIN_MINIBATCH_SIZE], cfg[ConfigValue.TRAIN_PATCH_SIZE] = 12, 2, 32
+    cfg[ConfigValue.EVAL_INTERVAL], cfg[ConfigValue.PRINT_INTERVAL], cfg[ConfigValue.SNAPSHOT_INTERVAL] = 8, 4, 6
+    trainer = DenoiserTrainer(cfg, runs_dir=str(tmp_path), run_dir="run")
+    trainer.new_target(device="cpu")
+    steps, evals = [], []
+
+    def fake_step(denoiser, optimizer, data, world_size):
+        steps.append((trainer.state[StateValue.ITERATION], optimizer.param_groups[0]["lr"], tuple(data[0].shape)))
+        return {PipelineOutput.LOSS: torch.full((data[0].shape[0], 1), 0.5), PipelineOutput.IMG_DENOISED: data[0]}
+
+    def fake_pipeline(data, **kwargs):
+        evals.append(tuple(data[0].shape))
+        return {PipelineOutput.IMG_DENOISED: data[0], PipelineOutput.INPUTS: data}
+
+    monkeypatch.setattr(ssdn.train, "train_step", fake_step)
+    monkeypatch.setattr(trainer.denoiser, "run_pipeline", fake_pipeline)
+    monkeypatch.setattr(ssdn.cfg, "test_length", lambda name: 4)                 # 240 passes over 'kodak' would only take time
+    with caplog.at_level(logging.INFO, logger="ssdn.train"):
+        trainer.train()
+    assert [s[0] for s in steps] == [0, 2, 4, 6, 8, 10] and all(s[2] == (2, 3, 32, 32) for s in steps)
+    assert steps[0][1] == 0.0 and steps[-1][1] < 3e-4                            # the ramps follow the image counter
+    assert len(evals) == 2 * 2 and all(e == (2, 3, 64, 64) for e in evals)      # at images 0 and 8: 4 padded test images, 2 per batch
+    assert set(trainer.last_eval) == {"psnr_out"} and 5.0 < trainer.last_eval["psnr_out"] < 40.0
+    lines = [r.getMessage() for r in caplog.records if r.name == "ssdn.train"]
+    assert [ln[:10] for ln in lines] == ["[00000000]", "[00000004]", "[00000008]", "[00000012]"]
+    assert "loss=0.5000" in lines[1] and "n=4" in lines[1] and "VALID psnr_out=" in lines[1]
+    run = tmp_path / "run"
+    assert sorted(p.name for p in (run / "training").iterdir()) == ["model_00000000.training", "model_00000006.training", "model_00000012.training"]
+    assert [p.name for p in run.glob("final-*.wt")] == ["final-ssdn-gauss25-sigma_known.wt"]
+    final = torch.load(run / "final-ssdn-gauss25-sigma_known.wt", map_location="cpu", weights_only=False)
+    assert "cfg" in final and "state" not in final
+    resumed = ssdn.train.resume_run(str(run), device="cpu")
+    assert resumed.state[StateValue.ITERATION] == 12 and len(resumed._train_iter.order) == 12 and resumed._train_iter.index == 12
+    # with caller-supplied batches nothing of this happens unless asked for
+    quiet = DenoiserTrainer(_cfg("known"), runs_dir=str(tmp_path), run_dir="quiet")
+    quiet.new_target(device="cpu")
+    batch = [torch.rand(2, 1, 32, 32), torch.zeros(0), {}]
+    quiet.train([batch, batch])
+    assert quiet.state[StateValue.ITERATION] == 4 and not (tmp_path / "quiet").exists()
