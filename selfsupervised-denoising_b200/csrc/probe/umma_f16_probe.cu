@@ -1,7 +1,7 @@
 // Hardware probe #3 (developer tool for the NEXT step of DESIGN.md section 8, item 1; not part of the product path and
 // NOT yet run on a GPU): tcgen05.mma kind::f16 with fp16 operand planes, as a two-term split of fp32 data.
 //   F1  K-major SWIZZLE_128B, 64 halves per row (4 MMAs of K = 16 per row, +32 B each)
-//   F2  K-major SWIZZLE_64B, 32-channel chunks (2 MMAs per chunk)          F3  K-major SWIZZLE_32B, 16-channel chunks
+//   F2  K-major SWIZZLE_64B, 32-channel chunks (2 MMAs per chunk; F2': half chunk by TMA zero fill)   F3  K-major SWIZZLE_32B, 16-channel chunks
 //   F4  row-shifted A start address for F2 / F3 layouts (the implicit-GEMM halo reuse), base_offset 0 vs (r & 7)
 //   F5  fp16x2 split of fp32 data with a power-of-two scale: hi*hi + lo*hi + hi*lo, against fp64 and against 3xTF32's error
 //   F6  MN-major A / B (the weight-gradient operands), SWIZZLE_128B with 64-half atoms, both LBO / SBO conventions
@@ -222,6 +222,24 @@ int main() {
       char nm[128]; snprintf(nm, 128, "F4 %.16s row shift r=%d base_offset=%d", kl.name + 3, r, bo ? r % 8 : 0);
       run(nm, mA2, mB, q, ref2, 40960);
     }
+  }
+
+  // ---------- F2': half chunk - 16 valid channels loaded through a 32-wide SW64 box (TMA zero-fills the rest), ONE MMA per row
+  {
+    const int N = 96, K = 16;
+    std::vector<float> A(M * K), B(N * K);
+    for (auto& v : A) v = __half2float(__float2half_rn(frand()));
+    for (auto& v : B) v = __half2float(__float2half_rn(frand()));
+    std::vector<double> ref = gemm_ref(A, B, M, N, K);
+    __half *dA = upload(to_half(A)), *dB = upload(to_half(B));
+    CUtensorMap mA = map_h(dA, K, M, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B), mB = map_h(dB, K, N, 32, 96, CU_TENSOR_MAP_SWIZZLE_64B);
+    ProbeParams p{}; p.f16 = 1; p.n_loads = 2; p.loads[0] = {0, 0, 0, 0, (uint32_t)M * 32 * 2}; p.loads[1] = {1, 16384, 0, 0, (uint32_t)N * 32 * 2};
+    p.n_mma = 1; p.mma[0] = {0, 16384};
+    p.a_desc = umma::make_desc_base(16, 512, umma::LAYOUT_SW64); p.b_desc = p.a_desc;
+    p.idesc = f16p::make_idesc_f16(128, N, 0, 0); p.N = N;
+    run("F2' half chunk: 16 of 32 channels valid, one MMA", mA, mB, p, ref, 32768);
+    p.n_mma = 2; p.mma[1] = {32, 16384 + 32};        // the second MMA must add exactly zero
+    run("F2' half chunk, both MMAs (second reads the zero fill)", mA, mB, p, ref, 32768);
   }
 
   // ---------- F5: two-term fp16 split of fp32 data (wide dynamic range), scaled by 2^k, vs 3xTF32 on the same data
