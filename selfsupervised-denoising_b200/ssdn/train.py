@@ -147,7 +147,8 @@ class DenoiserTrainer:
         self._run_dir = run_dir
         self.cfg = cfg
         if self.cfg:
-            ssdn.cfg.infer(self.cfg, model_only=self.cfg.get(ConfigValue.TRAIN_DATA_PATH) is None)
+            no_data = self.cfg.get(ConfigValue.TRAIN_DATA_PATH) is None and self.cfg.get(ConfigValue.TEST_DATA_PATH) is None
+            ssdn.cfg.infer(self.cfg, model_only=no_data)
         self.state = state if state is not None else {}
         self._denoiser: Optional[Denoiser] = None
         self._optimizer: Optional[FlatAdam] = None
