@@ -53,20 +53,30 @@ int ssdn_shift_unrot_concat(const float* x, float* y, int n, int c, int h, int w
  * ssdn_net_param_count.  h and w must be multiples of 32 (input_wh_mul, :228-238); blind-spot needs h == w.
  *   forward : NoiseNetwork.forward (:186-226); `training` != 0 also prepares what backward needs.
  *   backward: autograd of forward w.r.t. all parameters given dout = d(loss)/d(out); overwrites grads.
- *             Must follow the forward whose activations it differentiates (they live in the workspace). */
+ *             Must follow the forward whose activations it differentiates (they live in the workspace).
+ * Operand scales: the tensor-core kernels read every activation / gradient tensor as two fp16 planes scaled by a per-tensor
+ * power of two that is derived from the tensor's maximum in the PREVIOUS pass (weights and the loss gradient: from the
+ * current one).  A pass during which some maximum left the accurate band is "stale": its results must not be used and the
+ * pass must simply be repeated (the first passes of a new plan usually are).  backward() writes the step's verdict to
+ * `stale_out` (DEVICE float, may be NULL; 1.0f = forward or backward stale) so that the caller can append it to the
+ * gradient buffer it all-reduces and hand it to ssdn_adam_step as a skip flag; ssdn_net_scale_status synchronises and
+ * returns {forward stale, backward stale, stale passes since bind}. */
 int ssdn_net_create(int n, int cin, int cout, int h, int w, int blindspot, void** handle);
 void ssdn_net_destroy(void* handle);
 size_t ssdn_net_workspace_bytes(void* handle);
 size_t ssdn_net_param_count(void* handle);
 int ssdn_net_bind(void* handle, void* workspace, size_t workspace_bytes, void* stream);
 int ssdn_net_forward(void* handle, const float* params, const float* x, float* out, int training, void* stream);
-int ssdn_net_backward(void* handle, const float* params, const float* dout, float* grads, void* stream);
+int ssdn_net_backward(void* handle, const float* params, const float* dout, float* grads, float* stale_out, void* stream);
+int ssdn_net_scale_status(void* handle, int* status3, void* stream);
 /* Synchronises `stream` and reports device-side errors (a bounded mbarrier wait that expired). */
 int ssdn_net_check(void* handle, void* stream);
 /* Number of kernels one forward (+ backward when training != 0) launches. */
 int ssdn_net_kernel_launches(void* handle, int training);
-/* Test hooks: copy the first c channels of a named internal buffer (plane 0 = value, 1 = tf32 residual) to / from a
- * dense [B][c][H][W] tensor; with out == NULL only dims[4] = {B, c, H, W} is filled. */
+/* Test hooks: copy the first c channels of a named internal buffer (plane 0 = value, 1 / 2 = the fp16 lo / hi plane as
+ * stored) to / from a dense [B][c][H][W] tensor; with out == NULL only dims[4] = {B, c, H, W} is filled.
+ * ssdn_net_debug_scales: the 96 scale exponents in use and the bit patterns of the running maxima. */
+int ssdn_net_debug_scales(void* handle, int* k96, unsigned* amax96, void* stream);
 int ssdn_net_debug_read(void* handle, const char* name, int plane, int c, float* out, int* dims, void* stream);
 int ssdn_net_debug_write(void* handle, const char* name, int c, const float* src, void* stream);
 /* Per-launch CUDA-event timing of the tensor-core kernels; out9[kind*3 + {0,1,2}] = {launches, ms, algorithmic FLOPs}
@@ -110,9 +120,16 @@ int ssdn_masked_mse_backward(const float* out, const float* ref, const long long
 
 /* ---- optim.Adam(betas=[0.9, 0.99]) over a flat buffer — train.py:100-107, :202 ------------------------------------
  * In place on p/m/v; `step` is the 1-based step count; the gradient is multiplied by grad_scale first (1/world_size
- * after the data-parallel all-reduce). */
+ * after the data-parallel all-reduce).  skip: n_skip (<= 8) DEVICE floats or NULL - if any is non-zero the update is a no-op
+ * (the stale flags of ssdn_net_backward, summed over ranks by the same all-reduce as the gradients). */
 int ssdn_adam_step(float* p, const float* g, float* m, float* v, long long count, double lr, double beta1, double beta2, double eps,
-                   long long step, double grad_scale, void* stream);
+                   long long step, double grad_scale, const float* skip, int n_skip, void* stream);
+
+/* ---- measured tensor roofline (bench.py) ------------------------------------------------------------------------------
+ * Full-chip sustained tcgen05.mma rate, kind::f16 (f16 != 0) or kind::tf32: every SM issues back-to-back M = 128 / 256,
+ * N = 256 MMAs on shared-memory-resident operands for `seconds` per configuration.  Synchronous.
+ * out4 = {TFLOP/s, FLOP/clk/SM, SM clock in MHz seen by clock64, seconds timed}. */
+int ssdn_tensor_peak(int f16, double seconds, double* out4, void* stream);
 
 /* ---- on-GPU input pipeline — train.py:756-760 (RandomCrop), datasets/noise_wrapper.py:98-163, utils/noise.py:14-63 ---------
  * images: DEVICE uint8 cache [n_images][c][h][w] (c <= 4).  Output sample i takes image order[i] (DEVICE int32 [n]) or, with

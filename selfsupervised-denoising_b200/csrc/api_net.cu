@@ -26,8 +26,27 @@ extern "C" int ssdn_net_bind(void* handle, void* ws, size_t bytes, void* stream)
 extern "C" int ssdn_net_forward(void* handle, const float* params, const float* x, float* out, int training, void* stream) {
   return ((net::Net*)handle)->forward(params, x, out, (cudaStream_t)stream, training != 0);
 }
-extern "C" int ssdn_net_backward(void* handle, const float* params, const float* dout, float* grads, void* stream) {
-  return ((net::Net*)handle)->backward(params, dout, grads, (cudaStream_t)stream);
+extern "C" int ssdn_net_backward(void* handle, const float* params, const float* dout, float* grads, float* stale_out, void* stream) {
+  return ((net::Net*)handle)->backward(params, dout, grads, stale_out, (cudaStream_t)stream);
+}
+// Synchronises the stream and reports the operand-scale status of the last passes: status3 = {forward stale, backward stale,
+// stale passes since bind}.  A stale pass ran with fp16 operand scales outside their accurate band and must be repeated
+// (the scales it left behind are the right ones).
+extern "C" int ssdn_net_scale_status(void* handle, int* status3, void* stream) {
+  net::Net* nn = (net::Net*)handle;
+  if (!nn->ws) return fail(-5, "network workspace not bound");
+  SSDN_CUDA(cudaMemcpyAsync(status3, nn->scales.status, 3 * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  SSDN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+// Test hook: the scale exponent in use and the bit pattern of the running maximum of every slot (96 each).
+extern "C" int ssdn_net_debug_scales(void* handle, int* k96, unsigned* amax96, void* stream) {
+  net::Net* nn = (net::Net*)handle;
+  if (!nn->ws) return fail(-5, "network workspace not bound");
+  SSDN_CUDA(cudaMemcpyAsync(k96, nn->scales.k, net::kSlots * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  SSDN_CUDA(cudaMemcpyAsync(amax96, nn->scales.amax, net::kSlots * sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  SSDN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
 }
 // Synchronises the stream and reports device-side pipeline errors (bounded mbarrier waits that expired).
 extern "C" int ssdn_net_check(void* handle, void* stream) {
@@ -39,34 +58,38 @@ extern "C" int ssdn_net_check(void* handle, void* stream) {
   if (h) return fail(-4, "kernel pipeline timeout (role %d)", h);
   return 0;
 }
-// Debug/test helper: copies channels [0, c) of a named internal buffer (plane 0 = value = hi + lo, 1 = lo, 2 = hi) into a dense
-// NCHW tensor [B][c][H][W] of that buffer's own geometry.  Returns B*H*W*c through *count when out == NULL.
+// Debug/test helper: copies channels [0, c) of a named internal buffer (plane 0 = value = (hi + lo) * 2^-k, 1 = lo, 2 = hi as
+// stored) into a dense NCHW tensor [B][c][H][W] of that buffer's own geometry.  With out == NULL only dims is filled.
 extern "C" int ssdn_net_debug_read(void* handle, const char* name, int plane, int c, float* out, int* dims, void* stream) {
   net::Net* nn = (net::Net*)handle;
   const net::Buf* b = nn->find_buf(name);
   if (!b) return fail(-1, "unknown buffer '%s'", name);
-  if (plane == 1 && !b->lo) return fail(-1, "buffer '%s' has no lo plane", name);
+  if (plane != 0 && !b->hi) return fail(-1, "buffer '%s' is a single fp32 plane", name);
   if (c > b->cpitch) return fail(-1, "buffer '%s' has only %d channels", name, b->cpitch);
   if (dims) { dims[0] = b->g.B; dims[1] = c; dims[2] = b->g.H; dims[3] = b->g.W; }
   if (!out) return 0;
   const long long n = (long long)b->g.B * c * b->g.H * b->g.W;
-  const float* p0 = plane == 1 ? b->lo : b->v;
-  const float* p1 = plane == 0 ? b->lo : nullptr;
-  pw::unpack_nchw_kernel<<<pw::grid_for(n), pw::kBlock, 0, (cudaStream_t)stream>>>(p0, p1, out, b->g.B, c, b->g.H, b->g.W, b->g, b->cpitch, 0);
+  if (b->hi) pw::unpack_nchw_kernel<<<pw::grid_for(n), pw::kBlock, 0, (cudaStream_t)stream>>>(b->hi, b->lo, b->sc.k, plane, out, b->g.B, c, b->g.H, b->g.W, b->g, b->cpitch, 0);
+  else pw::unpack_nchw_f32_kernel<<<pw::grid_for(n), pw::kBlock, 0, (cudaStream_t)stream>>>(b->v, out, b->g.B, c, b->g.H, b->g.W, b->g, b->cpitch, 0);
   SSDN_CUDA(cudaGetLastError());
   return 0;
 }
-// Test helper: overwrites channels [0, c) of a named internal buffer (both planes) from a dense NCHW tensor
-// [B][c][H][W].  Used by the parity tests to run the backward pass on the oracle's forward activations.
+// Test helper: overwrites channels [0, c) of a named internal buffer (both planes, with the buffer's current scale) from a
+// dense NCHW tensor [B][c][H][W].  Used by the parity tests to run the backward pass on the oracle's forward activations.
 extern "C" int ssdn_net_debug_write(void* handle, const char* name, int c, const float* src, void* stream) {
   net::Net* nn = (net::Net*)handle;
   net::Buf* b = const_cast<net::Buf*>(nn->find_buf(name));
   if (!b) return fail(-1, "unknown buffer '%s'", name);
   if (c > b->cpitch) return fail(-1, "buffer '%s' has only %d channels", name, b->cpitch);
   const long long n = (long long)b->g.B * c * b->g.H * b->g.W;
-  pw::pack_nchw_kernel<<<pw::grid_for(n), pw::kBlock, 0, (cudaStream_t)stream>>>(src, b->v, b->lo, b->g.B, c, b->g.H, b->g.W, b->g, b->cpitch, 0, 0);
+  if (b->hi) {
+    ScaleRef sc = b->sc; sc.amax = nullptr;
+    pw::pack_nchw_kernel<<<pw::grid_for(n), pw::kBlock, 0, (cudaStream_t)stream>>>(src, b->hi, b->lo, b->g.B, c, b->g.H, b->g.W, b->g, b->cpitch, 0, 0, sc);
+  } else {
+    pw::pack_nchw_f32_kernel<<<pw::grid_for(n), pw::kBlock, 0, (cudaStream_t)stream>>>(src, b->v, b->g.B, c, b->g.H, b->g.W, b->g, b->cpitch, 0);
+  }
   if (b->mask)
-    pw::mask_from_planes_kernel<<<pw::grid_for(b->g.total() * b->mask_words), pw::kBlock, 0, (cudaStream_t)stream>>>(b->v, b->g.total(), b->cpitch,
+    pw::mask_from_planes_kernel<<<pw::grid_for(b->g.total() * b->mask_words), pw::kBlock, 0, (cudaStream_t)stream>>>(b->hi, b->g.total(), b->cpitch,
                                                                                                                   b->mask, b->mask_words);
   SSDN_CUDA(cudaGetLastError());
   return 0;
@@ -101,8 +124,9 @@ extern "C" int ssdn_profile_records(double* out, int max_records) {
 extern "C" int ssdn_net_kernel_launches(void* handle, int training) {
   net::Net* nn = (net::Net*)handle;
   const int nl = (int)nn->layers.size();
-  int fwd = nl /*conv*/ + 5 /*pool*/ + 1 /*pack*/ + 1 /*weight slabs*/;
-  int bwd = 2 /*pack, loss-gradient column sums*/ + nl * 2 /*wgrad, split-K reduce*/ + 1 /*all bias reductions*/ + (nl - 1) /*dgrad*/ + 5 + 5 /*pool, upsample*/;
+  int fwd = nl /*conv*/ + 5 /*pool*/ + 1 /*pack*/ + 2 /*weight scales, weight slabs*/ + 2 /*scale begin / finish*/;
+  int bwd = 3 /*loss-gradient scale, pack, column sums*/ + nl * 2 /*wgrad, split-K reduce*/ + 1 /*all bias reductions*/ + (nl - 1) /*dgrad*/ + 5 + 5 /*pool, upsample*/ +
+            2 /*scale begin / finish*/;
   return training ? fwd + bwd : fwd;
 }
 
@@ -236,11 +260,12 @@ extern "C" int ssdn_masked_mse_backward(const float* out, const float* ref, cons
 // ------------------------------------------------------------------------------------ optimiser
 #include <math.h>
 extern "C" int ssdn_adam_step(float* p, const float* g, float* m, float* v, long long count, double lr, double beta1, double beta2,
-                              double eps, long long step, double grad_scale, void* stream) {
+                              double eps, long long step, double grad_scale, const float* skip, int n_skip, void* stream) {
   if (step < 1) return fail(-1, "Adam step count starts at 1");
+  if (n_skip < 0 || n_skip > 8) return fail(-1, "at most 8 skip flags");
   const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   lossk::adam_kernel<<<pw::grid_for(count), pw::kBlock, 0, (cudaStream_t)stream>>>(p, g, m, v, count, (float)(lr / bc1), (float)beta1, (float)beta2,
-                                                                                  (float)eps, (float)sqrt(bc2), (float)grad_scale);
+                                                                                  (float)eps, (float)sqrt(bc2), (float)grad_scale, skip, skip ? n_skip : 0);
   SSDN_CUDA(cudaGetLastError());
   return 0;
 }

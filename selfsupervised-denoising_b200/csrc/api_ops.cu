@@ -13,19 +13,33 @@ namespace {
 
 struct ConvOpLayout {
   Geom g; int cin_pitch; int cout_padded, N; ConvTaps taps;
-  size_t act_floats, slab_floats;
+  size_t act_halves, slab_halves;
 };
 
 ConvOpLayout conv_layout(int n, int cin, int h, int w, int cout, int ksize, bool blind, bool dgrad) {
   ConvOpLayout L;
   L.g = make_geom(n, h, w, ksize == 3);
-  L.cin_pitch = round_up(cin, 4);
+  L.cin_pitch = round_up(cin, 8);
   L.cout_padded = round_up(cout, 16);
   L.N = pick_n(L.cout_padded);
   L.taps = make_taps(ksize, blind, dgrad, L.g.P);
-  L.act_floats = (size_t)L.g.total() * L.cin_pitch;
-  L.slab_floats = conv_weight_slab_floats(cin, L.cout_padded, L.taps.n);
+  L.act_halves = ((size_t)L.g.total() * L.cin_pitch + 127) / 128 * 128;
+  L.slab_halves = conv_weight_slab_halves(cin, L.cout_padded, L.taps.n);
   return L;
+}
+
+// scale slots of a single-operator call (both operands are leaves: exact scales, computed before packing)
+pw::ScaleState take_scales(Arena& a) {
+  pw::ScaleState st{};
+  st.k = a.take<int>(4); st.k_next = a.take<int>(4); st.amax = a.take<unsigned>(4); st.status = a.take<int>(8); st.counter = a.take<unsigned>(1);
+  return st;
+}
+cudaError_t zero_scales(const pw::ScaleState& st, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(st.k, 0, 16, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(st.k_next, 0, 16, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(st.amax, 0, 16, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(st.counter, 0, 4, s);
+  return e;
 }
 
 // y[n,cout,h,w] = act( conv(x[n,cin,h,w], slab) + bias ); the slab orientation decides fwd vs dgrad
@@ -34,27 +48,33 @@ int run_conv(void* ws, size_t ws_bytes, const float* x, const float* w, const fl
              cudaStream_t st) {
   ConvOpLayout L = conv_layout(n, cin, h, wd, cout, ksize, blind, dgrad);
   Arena a(ws, ws_bytes);
-  float* av = a.take<float>(L.act_floats); float* al = a.take<float>(L.act_floats);
-  float* slab = a.take<float>(L.slab_floats);
+  __half* planes = a.take<__half>(2 * L.act_halves + 256);
+  __half* slab = a.take<__half>(L.slab_halves);
+  pw::ScaleState sc = take_scales(a);
   int* flag = a.take<int>(1);
   if (!ws) return (int)0;
   if (!a.ok()) return fail(-3, "workspace too small: need %zu bytes, have %zu", a.off, ws_bytes);
-  SSDN_CUDA(cudaMemsetAsync(av, 0, L.act_floats * 4, st));
-  SSDN_CUDA(cudaMemsetAsync(al, 0, L.act_floats * 4, st));
+  __half* ah = planes; __half* al = planes + L.act_halves;
+  SSDN_CUDA(cudaMemsetAsync(planes, 0, (2 * L.act_halves + 256) * sizeof(__half), st));
   SSDN_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+  SSDN_CUDA(zero_scales(sc, st));
   const long long ne = (long long)n * cin * h * wd;
-  pw::pack_nchw_kernel<<<pw::grid_for(ne), pw::kBlock, 0, st>>>(x, av, al, n, cin, h, wd, L.g, L.cin_pitch, 0, 0);
+  pw::leaf_scale_kernel<<<64, 256, 0, st>>>(x, ne, sc, 0, 0, 0);
+  pw::WeightScaleJobs wj{}; wj.j[0] = {w, w_cout * w_cin * ksize * ksize, 1};
+  pw::weight_scale_kernel<<<1, 256, 0, st>>>(wj, sc);
+  ScaleRef xs{sc.k, nullptr};
+  pw::pack_nchw_kernel<<<pw::grid_for(ne), pw::kBlock, 0, st>>>(x, ah, al, n, cin, h, wd, L.g, L.cin_pitch, 0, 0, xs);
   const bool wide = conv_is_wide(cin, L.taps.n);
   int nc, kl; conv_chunks(cin, &nc, &kl, wide);
   const int n_tiles = L.cout_padded / L.N;
-  const long long ns = (long long)L.slab_floats / 2;
+  const long long ns = (long long)L.slab_halves / 2;
   pw::weight_prep_kernel<<<pw::grid_for(ns), pw::kBlock, 0, st>>>(w, slab, w_cout, w_cin, L.taps.n, cout, cin, n_tiles, nc,
-                                                                  L.N, dgrad ? 1 : 0, wide ? 32 : 16);
+                                                                  L.N, dgrad ? 1 : 0, wide ? 64 : 32, sc.k + 1);
   ConvDst d{};
-  d.v = y; d.lo = nullptr; d.cpitch = 0; d.coff = 0; d.g = L.g; d.map = MAP_NCHW;
+  d.v = y; d.hi = d.lo = nullptr; d.cpitch = 0; d.coff = 0; d.g = L.g; d.map = MAP_NCHW;
   d.flags = (bias ? EP_BIAS : 0) | (lrelu_act ? EP_LRELU : 0); d.cvalid = cout; d.nimg = n; d.bias = bias;
   ConvPlan plan;
-  int r = conv_plan_init(&plan, L.g, av, al, L.cin_pitch, 0, cin, slab, L.cout_padded, L.N, L.taps, d, flag, num_sms());
+  int r = conv_plan_init(&plan, L.g, ah, al, L.cin_pitch, 0, cin, slab, L.cout_padded, L.N, L.taps, d, flag, num_sms(), sc.k, sc.k + 1);
   if (r) return fail(r, "conv_plan_init failed (%d)", r);
   SSDN_CUDA(conv_launch(plan, st));
   int hflag = 0;
@@ -67,7 +87,8 @@ int run_conv(void* ws, size_t ws_bytes, const float* x, const float* w, const fl
 size_t conv_ws_bytes(int n, int cin, int h, int w, int cout, int ksize, bool blind, bool dgrad) {
   ConvOpLayout L = conv_layout(n, cin, h, w, cout, ksize, blind, dgrad);
   Arena a(nullptr, 0);
-  a.take<float>(L.act_floats); a.take<float>(L.act_floats); a.take<float>(L.slab_floats);
+  a.take<__half>(2 * L.act_halves + 256); a.take<__half>(L.slab_halves);
+  take_scales(a);
   a.take<int>(1);
   return a.off;
 }
@@ -96,13 +117,24 @@ extern "C" int ssdn_conv2d_backward_data(void* ws, size_t ws_bytes, const float*
                   (cudaStream_t)stream);
 }
 
+static size_t wgrad_op_layout(Arena& a, const Geom& g, int cin, int cout, int ntaps, int ks, __half** xp, size_t* xh, __half** yp, size_t* yh,
+                              float** partial, float** colpart, pw::ScaleState* sc, int** flag) {
+  *xh = ((size_t)g.total() * round_up(cin, 8) + 127) / 128 * 128;
+  *yh = ((size_t)g.total() * round_up(cout, 8) + 127) / 128 * 128;
+  *xp = a.take<__half>(2 * *xh + 256); *yp = a.take<__half>(2 * *yh + 256);
+  *partial = a.take<float>(wgrad_partial_floats(ks, ntaps, cout, cin));
+  *colpart = a.take<float>((size_t)1024 * round_up(cout, 8));
+  *sc = take_scales(a);
+  *flag = a.take<int>(1);
+  return a.off;
+}
+
 extern "C" size_t ssdn_conv2d_backward_weight_workspace_bytes(int n, int cin, int h, int w, int cout, int ksize) {
   Geom g = make_geom(n, h, w, ksize == 3);
   const int ks = wgrad_pick_ksplit(g.total(), cout, cin, ksize * ksize, 148);
   Arena a(nullptr, 0);
-  a.take<float>((size_t)g.total() * round_up(cin, 4) * 2); a.take<float>((size_t)g.total() * round_up(cout, 4) * 2);
-  a.take<float>(wgrad_partial_floats(ks, ksize * ksize, cout, cin)); a.take<float>((size_t)1024 * round_up(cout, 4)); a.take<int>(1);
-  return a.off + 4096;
+  __half *xp, *yp; size_t xh, yh; float *partial, *colpart; pw::ScaleState sc; int* flag;
+  return wgrad_op_layout(a, g, cin, cout, ksize * ksize, ks, &xp, &xh, &yp, &yh, &partial, &colpart, &sc, &flag) + 4096;
 }
 
 /* dw[cout][cin][k][k], db[cout] (either may be NULL) from x and dy = d(loss)/d(conv output). */
@@ -111,36 +143,54 @@ extern "C" int ssdn_conv2d_backward_weight(void* ws, size_t ws_bytes, const floa
   if (ksize != 1 && ksize != 3) return fail(-1, "ksize must be 1 or 3");
   cudaStream_t st = (cudaStream_t)stream;
   Geom g = make_geom(n, h, wd, ksize == 3);
-  const int xp = round_up(cin, 4), yp = round_up(cout, 4), ntaps = ksize * ksize;
-  const int ks = wgrad_pick_ksplit(g.total(), cout, cin, ntaps, num_sms());
+  const int xp = round_up(cin, 8), yp = round_up(cout, 8), ntaps = ksize * ksize;
+  const int ks = wgrad_pick_ksplit(g.total(), cout, cin, ntaps, 148);
   Arena a(ws, ws_bytes);
-  const size_t xf = (size_t)g.total() * xp, yf = (size_t)g.total() * yp;
-  float* xv = a.take<float>(xf * 2); float* xl = xv + xf;
-  float* yv = a.take<float>(yf * 2); float* yl = yv + yf;
-  float* partial = a.take<float>(wgrad_partial_floats(ks, ntaps, cout, cin));
-  float* colpart = a.take<float>((size_t)1024 * yp);
-  int* flag = a.take<int>(1);
+  __half *xpl, *ypl; size_t xh, yh; float *partial, *colpart; pw::ScaleState sc; int* flag;
+  wgrad_op_layout(a, g, cin, cout, ntaps, ks, &xpl, &xh, &ypl, &yh, &partial, &colpart, &sc, &flag);
   if (!a.ok()) return fail(-3, "workspace too small: need %zu bytes, have %zu", a.off, ws_bytes);
-  SSDN_CUDA(cudaMemsetAsync(xv, 0, xf * 8, st));
-  SSDN_CUDA(cudaMemsetAsync(yv, 0, yf * 8, st));
+  SSDN_CUDA(cudaMemsetAsync(xpl, 0, (2 * xh + 256) * sizeof(__half), st));
+  SSDN_CUDA(cudaMemsetAsync(ypl, 0, (2 * yh + 256) * sizeof(__half), st));
   SSDN_CUDA(cudaMemsetAsync(flag, 0, 4, st));
-  pw::pack_nchw_kernel<<<pw::grid_for((long long)n * cin * h * wd), pw::kBlock, 0, st>>>(x, xv, xl, n, cin, h, wd, g, xp, 0, 0);
-  pw::pack_nchw_kernel<<<pw::grid_for((long long)n * cout * h * wd), pw::kBlock, 0, st>>>(dy, yv, yl, n, cout, h, wd, g, yp, 0, 0);
+  SSDN_CUDA(zero_scales(sc, st));
+  const long long nx = (long long)n * cin * h * wd, ny = (long long)n * cout * h * wd;
+  pw::leaf_scale_kernel<<<64, 256, 0, st>>>(x, nx, sc, 0, 0, 0);
+  pw::leaf_scale_kernel<<<64, 256, 0, st>>>(dy, ny, sc, 1, 0, 0);
+  ScaleRef xs{sc.k, nullptr}, ys{sc.k + 1, nullptr};
+  pw::pack_nchw_kernel<<<pw::grid_for(nx), pw::kBlock, 0, st>>>(x, xpl, xpl + xh, n, cin, h, wd, g, xp, 0, 0, xs);
+  pw::pack_nchw_kernel<<<pw::grid_for(ny), pw::kBlock, 0, st>>>(dy, ypl, ypl + yh, n, cout, h, wd, g, yp, 0, 0, ys);
   if (dw) {
     WgradPlan plan;
-    int r = wgrad_plan_init(&plan, g.total(), yv, yl, yp, 0, cout, xv, xl, xp, 0, cin, make_taps(ksize, blind != 0, false, g.P), ks,
-                            partial, flag, num_sms());
+    int r = wgrad_plan_init(&plan, g.total(), ypl, ypl + yh, yp, 0, cout, xpl, xpl + xh, xp, 0, cin, make_taps(ksize, blind != 0, false, g.P), ks,
+                            partial, flag, num_sms(), sc.k + 1, sc.k);
     if (r) return fail(r, "wgrad_plan_init failed (%d)", r);
     SSDN_CUDA(wgrad_launch(plan, st));
     wgradk::wgrad_reduce_launch(partial, ks, ntaps, cout, cin, plan.p.cin_pitch, dw, 0, st);
   }
   if (db) {
     const long long rows = g.total();
-    pw::colsum_launch(yv, yl, rows, yp, 0, cout, colpart, db, st);
+    pw::colsum_launch(ypl, ypl + yh, sc.k + 1, rows, yp, 0, cout, colpart, db, st);
   }
   int hflag = 0;
   SSDN_CUDA(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
   SSDN_CUDA(cudaStreamSynchronize(st));
   if (hflag) return fail(-4, "wgrad kernel pipeline timeout (role %d)", hflag);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ measured tensor peak
+#include "peak_kernel.cuh"
+// Full-chip sustained tcgen05.mma rate (peak_kernel.cuh): kind f16 (f16 != 0) or tf32, the better of cta_group::1 / ::2,
+// measured for `seconds` per configuration on `stream`'s device.  out4 = {TFLOP/s, FLOP/clk/SM, SM MHz (from clock64), seconds}.
+extern "C" int ssdn_tensor_peak(int f16, double seconds, double* out4, void* stream) {
+  if (!out4 || !(seconds > 0) || seconds > 30) return fail(-1, "bad arguments");
+  peakk::PeakResult best{}; best.tflops = 0;
+  for (int pair = 0; pair <= 1; ++pair) {
+    peakk::PeakResult r{};
+    int rc = peakk::measure(f16 ? 1 : 0, pair, num_sms(), seconds, (cudaStream_t)stream, &r);
+    if (rc) return fail(-2, "tensor peak measurement failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+    if (r.tflops > best.tflops) best = r;
+  }
+  out4[0] = best.tflops; out4[1] = best.flop_per_clk_sm; out4[2] = best.sm_mhz; out4[3] = best.seconds;
   return 0;
 }

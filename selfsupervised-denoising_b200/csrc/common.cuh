@@ -12,21 +12,32 @@
 //   in the halo.  Kernels never write halo pixels, so they stay zero for the life of the buffer.
 //   1x1 convolutions (the output head) use the same code with H+0 rows / pitch W ("dense" geometry).
 //
-//   Each GEMM operand tensor has two planes:  hi = round_tf32(v)  and  lo = round_tf32(v - hi)  (round to nearest).
-//   hi + lo reproduces the fp32 value v to 2^-24 relative, and
-//       a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b          (dropped lo*lo term <= 2^-24)
-//   gives fp32-grade products from three tf32 tensor-core MMAs ("3xTF32"); both planes are exactly representable in
-//   tf32, so the tensor core's own fp32->tf32 truncation (measured: profiles/r01_umma_probe_full.log) is a no-op.
-//   Kernels that need the value itself (pooling, reductions) read hi + lo; sign tests read hi alone.
+//   Each GEMM operand tensor has two fp16 planes of the value scaled by a per-tensor power of two 2^k:
+//       hi = rn_f16(v * 2^k),  lo = rn_f16(v * 2^k - hi)        (round to nearest, saturating)
+//   hi + lo reproduces v * 2^k to 2^-23 relative as long as |v| * 2^k stays inside fp16's range with room below it for
+//   the lo term (profiles/r01_split_numerics.txt, profiles/r02_f16_probe.log), and
+//       a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b          (dropped lo*lo term <= 2^-22)
+//   gives fp32-grade products from three kind::f16 tensor-core MMAs of K = 16 with fp32 accumulation in TMEM - half the
+//   instructions and half the operand bytes of the 3xTF32 scheme this replaces.  The consumer's epilogue multiplies the
+//   accumulator by 2^-(k_a + k_b).
+//   SCALES (ScaleRef below): every operand tensor owns a slot {k, k_next, amax} in device memory.  Whoever writes the planes
+//   reads k and folds max|v| of what it wrote into amax (one atomicMax per warp at the end of the kernel).  Leaves (weights,
+//   the loss gradient) get their exact scale from a reduction that runs before they are packed; every other tensor uses
+//   the scale derived from its maximum in the PREVIOUS pass ("delayed scaling", net.cuh: scale_finish / scale_begin), aimed
+//   at 2^11: five binades of headroom before fp16 saturates and thirteen before accuracy is lost.  A pass whose maxima
+//   left that band reports itself stale; the host re-runs it (first use of a plan) and the optimiser step is predicated on
+//   the flag, so a stale gradient never reaches the weights.
+//   Kernels that need the value itself (pooling, reductions) read (hi + lo) * 2^-k; sign tests read hi alone.
 //   Tensors that are only consumed by pointwise kernels ("raw" gradients) have a single plain fp32 plane.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #define SSDN_LRELU_SLOPE 0.1f
 
 // The tensor core's fp32 accumulator TRUNCATES (rounds toward zero): every tcgen05.mma accumulate step shrinks the magnitude
-// of the running sum by about half an ulp, so a 3xTF32 result carries a BIAS of -1.5e-8 x (number of MMA instructions per
+// of the running sum by about half an ulp, so a split-operand result carries a BIAS of -1.5e-8 x (number of MMA instructions per
 // output) relative to its magnitude - measured, stable to +-5 % across layer shapes and zero-mean data
 // (tests/dev_conv_accuracy.py, profiles/r01_conv_accuracy.log): -4.9e-6 for a 96->96 3x3 layer, 1e-4 once compounded over
 // the 20 layers.  The epilogues multiply by 1 + SSDN_ACC_BETA * n_mma: the remaining error is the zero-mean part (half the
@@ -46,15 +57,59 @@ static inline Geom make_geom(int B, int H, int W, bool padded) {
   return g;
 }
 
-__device__ __forceinline__ float tf32_rn(float v) {
-  uint32_t o;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(v));
-  return __uint_as_float(o);
+// ---------------------------------------------------------------- operand scales
+constexpr int kScaleTarget = 11;      // a tensor's maximum is aimed at [2^11, 2^12) in its fp16 planes
+constexpr int kScaleHiLimit = 16;     // floor(log2(max)) + k >= 16: values beyond fp16's largest finite number were saturated
+constexpr int kScaleLoLimit = 2;      // floor(log2(max)) + k <  2: the lo plane has lost bits (graceful, but re-run)
+struct ScaleRef {                     // one operand tensor's scale slot (device pointers; null = unscaled test tensor)
+  const int* k;                       // exponent in use: planes hold v * 2^k
+  unsigned* amax;                     // bit pattern of max|v| written during the current pass (atomicMax target)
+};
+__device__ __forceinline__ float exp2_int(int k) {          // 2^k as a float, k clamped to the normal range
+  k = k < -126 ? -126 : (k > 127 ? 127 : k);
+  return __int_as_float((127 + k) << 23);
 }
-__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
-  hi = tf32_rn(v);
-  lo = tf32_rn(v - hi);
+__device__ __forceinline__ int floor_log2_bits(unsigned bits) { return (int)(bits >> 23) - 127; }   // of a positive normal float
+// scale exponent that puts a maximum with bit pattern `bits` into [2^target, 2^(target+1)); 0 when the tensor is all zero
+__device__ __forceinline__ int scale_for_amax(unsigned bits) { return bits ? kScaleTarget - floor_log2_bits(bits) : 0; }
+__device__ __forceinline__ void amax_commit(unsigned* amax, float m) {   // whole warp: one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && amax && m > 0.f) atomicMax(amax, __float_as_uint(m));
 }
+
+// ---------------------------------------------------------------- fp16 two-term split
+// packs (a -> low half, b -> high half), round to nearest, saturating to +-65504 instead of infinity
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 f16x2_to_float2(uint32_t r) { return __half22float2(*reinterpret_cast<const __half2*>(&r)); }
+// (a, b) already multiplied by the tensor's scale -> packed hi pair and packed lo pair
+__device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_f16x2_sat(a, b);
+  const float2 h = f16x2_to_float2(hi);
+  lo = cvt_f16x2_sat(a - h.x, b - h.y);
+}
+__device__ __forceinline__ void f16_split1(float a, __half& hi, __half& lo) {
+  uint32_t h, l; f16_split2(a, 0.f, h, l);
+  hi = __ushort_as_half((unsigned short)(h & 0xffffu)); lo = __ushort_as_half((unsigned short)(l & 0xffffu));
+}
+// 8 consecutive channels: scaled floats -> one 16-byte vector per plane
+__device__ __forceinline__ void f16_split8(const float (&f)[8], uint4& hi, uint4& lo) {
+  f16_split2(f[0], f[1], hi.x, lo.x); f16_split2(f[2], f[3], hi.y, lo.y);
+  f16_split2(f[4], f[5], hi.z, lo.z); f16_split2(f[6], f[7], hi.w, lo.w);
+}
+// 8 consecutive channels of both planes -> hi + lo as floats (still carrying the tensor's scale)
+__device__ __forceinline__ void f16_join8(const uint4& hi, const uint4& lo, float (&f)[8]) {
+  const uint32_t* h = reinterpret_cast<const uint32_t*>(&hi); const uint32_t* l = reinterpret_cast<const uint32_t*>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = f16x2_to_float2(h[i]), b = f16x2_to_float2(l[i]);
+    f[2 * i] = a.x + b.x; f[2 * i + 1] = a.y + b.y;
+  }
+}
+__device__ __forceinline__ float f16_join1(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : SSDN_LRELU_SLOPE * v; }
 
 // Destination mapping modes of the conv epilogue
@@ -69,7 +124,7 @@ enum : int {
   EP_BIAS = 1,        // add bias[c]
   EP_LRELU = 2,       // LeakyReLU(0.1)
   EP_ACT_GRAD = 4,    // multiply by LeakyReLU'(act): the sign bits of the forward activation come from mask_in
-  EP_WRITE_LO = 8,    // destination is a GEMM operand: write the (hi, lo) tf32 split instead of the plain value
+  EP_WRITE_LO = 8,    // destination is a GEMM operand: write the scaled (hi, lo) fp16 split instead of the plain value
   EP_ACT_AT_SRC = 16  // EP_ACT_GRAD indexes mask_in by the SOURCE pixel / true GEMM channel (instead of the destination's)
 };
 
@@ -78,7 +133,9 @@ enum : int {
 // whose output is multiplied by LeakyReLU'(that activation) reads them (mask_in) - 1/32 of the bytes of re-reading the
 // activation, fetched before the accumulator is ready.
 struct ConvDst {
-  float* v; float* lo;           // destination planes: (hi, lo) when EP_WRITE_LO, else v = plain fp32
+  float* v;                      // plain fp32 destination (raw gradients, NCHW output) when not EP_WRITE_LO
+  __half* hi; __half* lo;        // EP_WRITE_LO: the two fp16 planes of a GEMM operand, values scaled by 2^(*scale.k)
+  ScaleRef scale;                //    scale slot of the destination tensor
   int cpitch, coff;              // channels per destination pixel, channel offset of this conv's output
   Geom g;                        // destination geometry
   int map, flags;

@@ -5,20 +5,24 @@
 // A is a padded-flat NHWC activation (common.cuh); because zero padding is stored in the halo,
 // every tap is a constant row offset into A.  Work decomposition:
 //   unit   = T consecutive tiles of 128 flat pixels  x  one N-tile (<= 192 output channels)
-//   chunk  = 16 input channels (one SWIZZLE_64B K-major smem tile row = 64 bytes, 2 tf32 k-steps); 1x1 layers use
-//            32-channel chunks (SWIZZLE_128B, 4 k-steps): without tap reuse the TMA row rate is what binds there
+//   chunk  = 32 input channels (one SWIZZLE_64B K-major smem tile row = 64 bytes of fp16, 2 k-steps of K = 16); 1x1 layers
+//            use 64-channel chunks (SWIZZLE_128B, 4 k-steps): without tap reuse the TMA row rate is what binds there.
+//            A channel count that is not a multiple of 32 ends in a partial chunk: TMA zero-fills the missing channels
+//            and a chunk with <= 16 real channels issues only the first of its two k-steps
 //   group  = a set of taps that share one staged window of A rows (halo reuse: the window is
 //            loaded ONCE by TMA and each tap is only a different UMMA start address)
-//   B tile = the [N][16] weight slab of one (chunk, tap), streamed through its own smem ring (3 slabs per stage).
+//   B tile = the [N][32] weight slab of one (chunk, tap), streamed through its own smem ring (3 slabs per stage).
 // Warp roles (12 warps): 0 = A producer (TMA), 1 = B producer (TMA), 2 = MMA issuer (one elected thread),
 // 3 = TMEM allocator, 4..11 = epilogue - two warps per TMEM lane quadrant taking alternate 32-channel slices:
-// TMEM -> registers -> accumulator-truncation compensation -> bias / LeakyReLU (+ sign-mask word out) or LeakyReLU' from
-// the sign-mask word -> optional column sums (bias gradient) -> transposed through shared memory -> hi/lo split ->
-// full-line stores with the upsample / un-rotate / NCHW scatter in the address.
+// TMEM -> registers -> operand scales 2^-(k_a + k_b) and accumulator-truncation compensation -> bias / LeakyReLU (+ sign-mask
+// word out) or LeakyReLU' from the sign-mask word -> optional column sums (bias gradient) -> transposed through shared
+// memory -> scaled fp16 hi/lo split (+ running max|v| for the destination's next scale) -> 16-byte stores with the
+// upsample / un-rotate / NCHW scatter in the address.
 // Accumulators are double buffered in TMEM so the epilogue of unit i overlaps the MMAs of unit i+1.
 // PAIR = true: the kernel runs as clusters of two CTAs that issue cta_group::2 MMAs of M = 256 (umma.cuh): each CTA loads
 // its own pixel rows of A and half of the N rows of B, the leader issues, both epilogues drain their own TMEM.
-// Precision: 3xTF32 (see common.cuh) => fp32-grade results, 3 MMAs per (tile, k-step).
+// Precision: two-term fp16 split with per-tensor power-of-two scales (see common.cuh) => fp32-grade results, 3 MMAs of
+// kind::f16 per (tile, k-step of 16 channels).
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -42,13 +46,14 @@ struct ConvParams {
   int nbox, box_rows; // every group window is loaded as nbox TMA boxes of box_rows rows (one op for both planes if nbox == 1)
   int a_stages, b_stages;
   int bg;             // weight slabs ((chunk, tap) pairs, in consumption order) per B stage: ONE TMA op loads bg x 2 planes
-  int wide;           // 1x1 convolutions with cin % 32 == 0: chunks of 32 channels (128-byte rows, SWIZZLE_128B, 4 k-steps), one
+  int wide;           // 1x1 convolutions with cin % 64 == 0: chunks of 64 channels (128-byte rows, SWIZZLE_128B, 4 k-steps), one
                       //    weight slab per B stage; A is not reused by other taps there, so its TMA rate (rows/clk) is what binds
   int row3;           // 1: every B stage holds the 3 taps of one stencil row of one group, tap_rel advancing by tap_step
   int tap_step;       //    (+1 forward, -1 data-gradient): the MMA warp then issues 3 x T x 6 MMAs per barrier wait
   uint32_t a_plane_bytes, b_stage_bytes;   // smem bytes of one A plane of one stage / of one B stage
   uint32_t epi_off;   // byte offset of the epilogue staging area (8 warps x 32 pixels x 36 floats) in dynamic smem
   float acc_comp;     // 1 + SSDN_ACC_BETA x (MMA instructions accumulated into one output): truncation-bias compensation
+  const int* k_a; const int* k_b;   // scale exponents of the A tensor and of the weight slab (device; null = 0)
   int epi_split;      // 1: both epilogue warps of a TMEM lane quadrant work (alternate slices) - epilogue-bound layers; 0: one warp
                       //    per quadrant, the other four exit at once (they would only take issue slots and shared-memory
                       //    bandwidth from an MMA-bound layer)
@@ -61,7 +66,7 @@ struct ConvParams {
 struct ConvPlan {
   ConvParams p;
   double flops = 0;   // algorithmic 2*MAC of this launch (valid pixels, real channels); filled by the owner
-  CUtensorMap a, b;   // a: [plane][flat pixel][channel] (3-D), b: weight slabs [slab x plane][N][16] (3-D)
+  CUtensorMap a, b;   // a: [plane][flat pixel][channel] (3-D), b: weight slabs [slab x plane][N][32] (3-D), fp16
   int grid; size_t smem;
 };
 
@@ -188,8 +193,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------ A producer (warp-uniform loop, elected issue)
     Ring ra(p.a_stages);
-    const int cw_ch = p.wide ? 32 : 16;                       // channels per chunk
-    const uint32_t box_bytes = p.box_rows * cw_ch * 4;
+    const int cw_ch = p.wide ? 64 : 32;                       // channels per chunk
+    const uint32_t box_bytes = p.box_rows * cw_ch * 2;
     long long w_empty = 0;
     for (int u = u_first; u < n_units; u += u_stride) {
       const int um = unit_m(u);
@@ -213,7 +218,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               }
             } else {
               umma::mbar_expect_tx(full_a(ra.stage), 2 * p.nbox * box_bytes);
-              if (p.nbox == 1) {      // one op brings both planes: box (16 ch, rows, 2 planes)
+              if (p.nbox == 1) {      // one op brings both planes: box (32 ch, rows, 2 planes)
                 umma::tma_load_3d(dst, &map_a, full_a(ra.stage), ch * cw_ch, row, 0);
               } else {
                 for (int bx = 0; bx < p.nbox; ++bx) {
@@ -257,17 +262,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // unrolled block of T x 2 x 3 MMAs per (chunk, tap) whose descriptors are base + compile-time offsets
     Ring ra(p.a_stages), rb(p.b_stages);
     constexpr uint64_t desc = umma::make_desc_base(16, 512, umma::LAYOUT_SW64);
-    const uint32_t idesc = umma::make_idesc_tf32(PAIR ? 256 : 128, p.N, 0, 0);
+    const uint32_t idesc = umma::make_idesc_f16(PAIR ? 256 : 128, p.N, 0, 0);
     // single CTA: tcgen05.mma.cta_group::1 and a local commit; pair leader: cta_group::2 and a commit multicast to both CTAs
     auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t acc) {
-      if (PAIR) umma::mma_tf32_lo_pair(d, a_lo, b_lo, hi, idesc, acc); else umma::mma_tf32_lo(d, a_lo, b_lo, hi, idesc, acc);
+      if (PAIR) umma::mma_f16_lo_pair(d, a_lo, b_lo, hi, idesc, acc); else umma::mma_f16_lo(d, a_lo, b_lo, hi, idesc, acc);
     };
     auto commit = [&](uint32_t bar) { if (PAIR) umma::mma_commit_pair(bar); else umma::mma_commit(bar); };
     int it = 0;
     long long w_tmem = 0, w_a = 0, w_b = 0;
     const long long t_start = clock64();
     if (p.wide) {
-      // 1x1 convolutions: per 32-channel chunk one A stage and one B stage, T tiles x (4 k-steps x 3 products) MMAs
+      // 1x1 convolutions: per 64-channel chunk one A stage and one B stage, T tiles x (4 k-steps x 3 products) MMAs
       constexpr uint64_t wdesc = umma::make_desc_base(16, 1024, umma::LAYOUT_SW128);
       const uint32_t desc_hi = (uint32_t)(wdesc >> 32);
       const uint32_t lbo_bits = (uint32_t)(wdesc & 0xffff0000u);
@@ -389,13 +394,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               for (int tile = 0; tile < T; ++tile) {
                 const uint32_t d = d0 + tile * p.N;
                 const uint32_t ao = tile * (128 * 64);
-                umma::mma_tf32_ss(d, umma::desc_at(desc, al + ao), umma::desc_at(desc, bv), idesc, first);
-                umma::mma_tf32_ss(d, umma::desc_at(desc, av + ao), umma::desc_at(desc, bl), idesc, 1);
-                umma::mma_tf32_ss(d, umma::desc_at(desc, av + ao), umma::desc_at(desc, bv), idesc, 1);
+                umma::mma_f16_ss(d, umma::desc_at(desc, al + ao), umma::desc_at(desc, bv), idesc, first);
+                umma::mma_f16_ss(d, umma::desc_at(desc, av + ao), umma::desc_at(desc, bl), idesc, 1);
+                umma::mma_f16_ss(d, umma::desc_at(desc, av + ao), umma::desc_at(desc, bv), idesc, 1);
                 if (two) {
-                  umma::mma_tf32_ss(d, umma::desc_at(desc, al + ao + 32), umma::desc_at(desc, bv + 32), idesc, 1);
-                  umma::mma_tf32_ss(d, umma::desc_at(desc, av + ao + 32), umma::desc_at(desc, bl + 32), idesc, 1);
-                  umma::mma_tf32_ss(d, umma::desc_at(desc, av + ao + 32), umma::desc_at(desc, bv + 32), idesc, 1);
+                  umma::mma_f16_ss(d, umma::desc_at(desc, al + ao + 32), umma::desc_at(desc, bv + 32), idesc, 1);
+                  umma::mma_f16_ss(d, umma::desc_at(desc, av + ao + 32), umma::desc_at(desc, bl + 32), idesc, 1);
+                  umma::mma_f16_ss(d, umma::desc_at(desc, av + ao + 32), umma::desc_at(desc, bv + 32), idesc, 1);
                 }
               }
               if (last_slab) commit(empty_b(rb.stage));
@@ -418,11 +423,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else if (warp >= 4 && (p.epi_split || warp < 8)) {
     // ------------------------------------------------------------ epilogue
-    // TMEM -> registers (one pixel per lane, 32 channels per slice) -> bias / LeakyReLU (+ sign-mask word out) or
-    // LeakyReLU' from the sign-mask word -> optional column sums -> hi/lo split -> global memory straight from registers:
-    // every lane writes its pixel's 128 contiguous bytes of the slice as 8 float4 stores per plane, with the upsample /
-    // (un-)rotate scatter in the address.  No shared-memory staging: the tensor core needs all of the shared-memory
-    // bandwidth for its operands (profiles/r01_role_waits.log), and L2 merges the 16-byte pieces into full lines.
+    // TMEM -> registers (one pixel per lane, 32 channels per slice) -> scales / bias / LeakyReLU (+ sign-mask word out) or
+    // LeakyReLU' from the sign-mask word -> optional column sums -> staged through shared memory -> fp16 hi/lo split ->
+    // global memory with the upsample / (un-)rotate scatter in the address.
     const ConvDst& d = p.dst;
     const Geom& sg = p.src;
     const int ew = (warp - 4) & 3;        // TMEM lane quadrant (a warp may only read lanes 32 * (warp % 4) ...)
@@ -435,6 +438,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     float csum[kMaxSlices];
 #pragma unroll
     for (int s = 0; s < kMaxSlices; ++s) csum[s] = 0.f;
+    // accumulators carry 2^(k_a + k_b); operand destinations are written with their own scale 2^k_dst
+    const float out_scale = p.acc_comp * exp2_int(-((p.k_a ? __ldg(p.k_a) : 0) + (p.k_b ? __ldg(p.k_b) : 0)));
+    const float dst_scale = ((d.flags & EP_WRITE_LO) && d.scale.k) ? exp2_int(__ldg(d.scale.k)) : 1.0f;
+    float amax_l = 0.f;        // running max|v| of what this lane wrote (next scale of the destination tensor)
     int it = 0;
     long long w_full = 0;
     const long long t_start = clock64();
@@ -471,7 +478,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (cg0 < d.cvalid) {
               float f[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) * p.acc_comp;
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) * out_scale;
               if (d.flags & EP_BIAS) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -533,9 +540,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
               }
               // Every slice goes through shared memory (36-float rows: conflict-free float4 access).  NHWC destinations:
-              // 8 consecutive lanes then write one pixel's 128 contiguous bytes - 4 full lines per store instruction
-              // instead of 32 line fragments, which is what the load/store unit can sustain (upsampling writes each value
-              // 4 times).  NCHW destination (network output): a lane keeps its own pixel and walks the channels.
+              // consecutive lanes then write one pixel's contiguous bytes (fp16 planes: 4 lanes x 16 bytes per plane, fp32:
+              // 8 lanes x 16 bytes) - whole sectors per store instruction instead of 32 fragments, which is what the load/store
+              // unit can sustain (upsampling writes each value 4 times).  NCHW destination (network output): a lane keeps its
+              // own pixel and walks the channels.
               float* stage = reinterpret_cast<float*>(smem + p.epi_off) + (warp - 4) * 32 * kStagePitch;
               float* row = stage + lane * kStagePitch;
 #pragma unroll
@@ -547,6 +555,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                   float* dst = d.v + ((long long)cur.b * d.cvalid + cg0) * hw + (long long)cur.y * sg.W + cur.x;
                   const int nc = min(min(32, p.N - c0), d.cvalid - cg0);     // a slice may be cut by the N tile or by cvalid
                   for (int c = 0; c < nc; ++c) dst[c * hw] = row[c];
+                }
+              } else if (d.flags & EP_WRITE_LO) {
+                // fp16 operand planes: 4 lanes per pixel (8 channels = 16 bytes per plane each), 8 pixels per pass
+                const int sub = lane >> 2, q8 = lane & 3;
+                const bool chan_ok = (c0 + 8 * q8 < p.N) && (cg0 + 8 * q8 < d.cvalid);
+                const int meta = cur.nd | (cur.zero << 3);
+#pragma unroll 2
+                for (int q = 0; q < 32; q += 8) {
+                  const int px = q + sub;
+                  const int pd0 = __shfl_sync(0xffffffffu, cur.d0, px), pmeta = __shfl_sync(0xffffffffu, meta, px);
+                  const int pcs = __shfl_sync(0xffffffffu, cur.cshift, px);
+                  if (chan_ok && (pmeta & 7)) {
+                    const float4 o0 = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 8 * q8);
+                    const float4 o1 = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 8 * q8 + 4);
+                    float f8[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+                    if (pmeta & 8) {                      // row shifted in by Shift2d
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) f8[i] = 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { amax_l = fmaxf(amax_l, fabsf(f8[i])); f8[i] *= dst_scale; }
+                    uint4 h, l;
+                    f16_split8(f8, h, l);
+                    const int cb = d.coff + pcs + cg0 + 8 * q8;
+                    for (int k = 0; k < (pmeta & 7); ++k) {
+                      const long long oi = (long long)(pd0 + (k & 1) + (k >> 1) * d.g.P) * d.cpitch + cb;
+                      *reinterpret_cast<uint4*>(d.hi + oi) = h;
+                      *reinterpret_cast<uint4*>(d.lo + oi) = l;
+                    }
+                  }
                 }
               } else {
                 const int sub = lane >> 3, q4 = lane & 7;                  // 8 lanes per pixel, 4 pixels per pass
@@ -560,13 +598,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                   if (chan_ok && (pmeta & 7)) {
                     float4 o = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 4 * q4);
                     if (pmeta & 8) o = make_float4(0.f, 0.f, 0.f, 0.f);     // row shifted in by Shift2d
-                    float4 h = o, l = o;
-                    if (d.flags & EP_WRITE_LO) { tf32_split(o.x, h.x, l.x); tf32_split(o.y, h.y, l.y); tf32_split(o.z, h.z, l.z); tf32_split(o.w, h.w, l.w); }
                     const int cb = d.coff + pcs + cg0 + 4 * q4;
                     for (int k = 0; k < (pmeta & 7); ++k) {
                       const long long oi = (long long)(pd0 + (k & 1) + (k >> 1) * d.g.P) * d.cpitch + cb;
-                      *reinterpret_cast<float4*>(d.v + oi) = h;
-                      if (d.flags & EP_WRITE_LO) *reinterpret_cast<float4*>(d.lo + oi) = l;
+                      *reinterpret_cast<float4*>(d.v + oi) = o;
                     }
                   }
                 }
@@ -579,6 +614,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       umma::tc_fence_before();
       if (PAIR) umma::mbar_arrive_cluster(tmem_empty_lead0 + 8 * buf); else umma::mbar_arrive(tmem_empty(buf));
     }
+    if (d.flags & EP_WRITE_LO) amax_commit(d.scale.amax, amax_l);
     if (d.colsum) {
       // this CTA only ever sees one N tile when gridDim.x is a multiple of n_tiles_n (the host guarantees it)
       const int nt = u_first % p.n_tiles_n;
@@ -608,31 +644,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
 struct ConvTaps { int n; int off[9]; };   // flat-pixel offsets of the taps, in weight-slab order
 
-// 1x1 convolutions whose input channels come in whole 32-channel groups use the wide chunk (see ConvParams::wide).
-static inline bool conv_is_wide(int cin, int ntaps) { return ntaps == 1 && cin % 32 == 0; }
-// Number of channel chunks (16 wide, or 32 in wide mode) and k-steps of the last chunk for `cin` input channels.
+// 1x1 convolutions whose input channels come in whole 64-channel groups use the wide chunk (see ConvParams::wide).
+static inline bool conv_is_wide(int cin, int ntaps) { return ntaps == 1 && cin % 64 == 0; }
+// Number of channel chunks (32 wide, or 64 in wide mode) and k-steps (of 16 channels) of the last chunk for `cin` input channels.
 static inline void conv_chunks(int cin, int* n_chunks, int* ksteps_last, bool wide = false) {
-  if (wide) { *n_chunks = cin / 32; *ksteps_last = 4; return; }
-  *n_chunks = (cin + 15) / 16;
-  const int rem = cin - (*n_chunks - 1) * 16;
-  *ksteps_last = rem > 8 ? 2 : 1;
+  if (wide) { *n_chunks = cin / 64; *ksteps_last = 4; return; }
+  *n_chunks = (cin + 31) / 32;
+  const int rem = cin - (*n_chunks - 1) * 32;
+  *ksteps_last = rem > 16 ? 2 : 1;
 }
 
 // Fills plan->p (everything except tensor maps' base pointers) and the tensor maps.
-//   a_v/a_lo : source planes with `a_cpitch` channels per pixel, the conv reads channels [a_coff, a_coff+cin)
-//   w_slab   : prepared weight slab [n_tiles_n][n_chunks][ntaps][plane][N][16] (see pw::weight_prep_kernel)
-static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a_v, const float* a_lo, int a_cpitch,
-                                 int a_coff, int cin, const float* w_slab, int cout_padded, int N,
+//   a_hi/a_lo : source planes (fp16) with `a_cpitch` channels per pixel, the conv reads channels [a_coff, a_coff+cin)
+//   w_slab    : prepared weight slab [n_tiles_n][n_chunks][ntaps][plane][N][32] (see pw::weight_prep_kernel)
+//   k_a / k_b : device pointers to the scale exponents of the A tensor and of the weights
+static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const __half* a_hi, const __half* a_lo, int a_cpitch,
+                                 int a_coff, int cin, const __half* w_slab, int cout_padded, int N,
                                  const ConvTaps& taps, const ConvDst& dst, int* error_flag, int num_sms,
-                                 size_t smem_limit = 222 * 1024) {
+                                 const int* k_a, const int* k_b, size_t smem_limit = 222 * 1024) {
   ConvParams& p = plan->p;
   p = ConvParams{};
-  p.src = src; p.N = N; p.dst = dst; p.error_flag = error_flag;
+  p.src = src; p.N = N; p.dst = dst; p.error_flag = error_flag; p.k_a = k_a; p.k_b = k_b;
   p.debug = getenv("SSDN_CONV_DEBUG") ? atoi(getenv("SSDN_CONV_DEBUG")) : 0;
   p.n_tiles_n = cout_padded / N;
   p.wide = conv_is_wide(cin, taps.n) ? 1 : 0;
   conv_chunks(cin, &p.n_chunks, &p.ksteps_last, p.wide);
-  const int cw_ch = p.wide ? 32 : 16;
+  const int cw_ch = p.wide ? 64 : 32;
   p.ntaps_total = taps.n;
   p.T = (2 * 2 * N <= 512) ? 2 : 1;
   const long long total = src.total();
@@ -658,11 +695,11 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     const char* e = getenv("SSDN_CONV_PAIR");
     // measured (profiles/r01_pair_split_ablation.log): pairs never lose except on the one-chunk first convolution
     // 1x1 layers: only the wide-N, deep-K head conv gains (its B stream is what saturates the TMA unit); measured
-    const bool wide_ok = p.wide && N >= 192 && p.n_chunks >= 8;
+    const bool wide_ok = p.wide && N >= 192 && p.n_chunks >= 4;
     p.pair = (rows_ok || wide_ok) && (N % 16 == 0) && (num_sms % 2 == 0) && p.n_chunks >= 2 && !(e && atoi(e) == 0);
     if (p.wide && e && atoi(e) == 3) p.pair = 0;   // ablation: pairs on the 3x3 layers only
   }
-  p.b_stage_bytes = (uint32_t)(p.bg * 2 * (p.pair ? N / 2 : N) * cw_ch * 4);   // per CTA
+  p.b_stage_bytes = (uint32_t)(p.bg * 2 * (p.pair ? N / 2 : N) * cw_ch * 2);   // per CTA
   {
     const int ksteps = p.wide ? 4 * p.n_chunks : 2 * (p.n_chunks - 1) + p.ksteps_last;
     const bool on = !(getenv("SSDN_ACC_COMP") && atoi(getenv("SSDN_ACC_COMP")) == 0);
@@ -692,7 +729,7 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     int nbox = (max_rows + 255) / 256;
     int box_rows = ((max_rows + nbox - 1) / nbox + 15) / 16 * 16;      // multiple of 16 rows => planes/boxes stay 1024-byte aligned
     if (box_rows > 256) { ++nbox; box_rows = ((max_rows + nbox - 1) / nbox + 15) / 16 * 16; }
-    uint32_t plane = (uint32_t)(nbox * box_rows * cw_ch * 4);
+    uint32_t plane = (uint32_t)(nbox * box_rows * cw_ch * 2);
     for (int stages = (mode == 0 && !p.wide) ? 2 : 3; stages >= 2; --stages)
     for (int bst = 4; bst >= 2; --bst) {
       const size_t epi = convk::kEpiWarps * 32 * convk::kStagePitch * sizeof(float);   // epilogue staging (all destinations)
@@ -741,29 +778,31 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const float* a
     }
   }
   if (dst.map != MAP_NCHW && (dst.cvalid % 4 || dst.cpitch % 4 || dst.coff % 4)) return -13;   // float4 stores
+  if ((dst.flags & EP_WRITE_LO) && (dst.cvalid % 8 || dst.cpitch % 8 || dst.coff % 8 || !dst.hi || !dst.lo)) return -13;   // 8 halves per store
+  if (a_cpitch % 8 || a_coff % 8) return -16;                                                  // TMA: 16-byte strides and base
   if ((dst.mask_out || dst.mask_in) && p.n_tiles_n > 1 && N % 32) return -15;                  // mask words are per 32 channels
   // tensor maps.  A: 3-D (channel, flat pixel, plane); the lo plane must follow the hi plane at a constant byte distance.
-  const long long plane_stride = (long long)((const char*)a_lo - (const char*)a_v);
+  const long long plane_stride = (long long)((const char*)a_lo - (const char*)a_hi);
   if (plane_stride <= 0 || plane_stride % 16) return -11;
   uint64_t adims[3] = {(uint64_t)cin, (uint64_t)total, 2};
-  uint64_t astr[2] = {(uint64_t)a_cpitch * 4, (uint64_t)plane_stride};
+  uint64_t astr[2] = {(uint64_t)a_cpitch * 2, (uint64_t)plane_stride};
   uint32_t abox[3] = {(uint32_t)cw_ch, (uint32_t)p.box_rows, (uint32_t)(p.nbox == 1 ? 2 : 1)};
   const CUtensorMapSwizzle swz = p.wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   int r;
-  if ((r = umma::encode_f32(&plan->a, (void*)(a_v + a_coff), 3, adims, astr, abox, swz))) return r;
-  // B: slabs [n_tile][chunk][tap][plane][N][16] -> 3-D (16, N, slab x plane), box = bg slabs x 2 planes
+  if ((r = umma::encode_f16(&plan->a, (void*)(a_hi + a_coff), 3, adims, astr, abox, swz))) return r;
+  // B: slabs [n_tile][chunk][tap][plane][N][32] -> 3-D (32, N, slab x plane), box = bg slabs x 2 planes
   uint64_t bdims[3] = {(uint64_t)cw_ch, (uint64_t)N, (uint64_t)p.n_tiles_n * n_slabs * 2};
-  uint64_t bstr[2] = {(uint64_t)cw_ch * 4, (uint64_t)N * cw_ch * 4};
+  uint64_t bstr[2] = {(uint64_t)cw_ch * 2, (uint64_t)N * cw_ch * 2};
   uint32_t bbox[3] = {(uint32_t)cw_ch, (uint32_t)(p.pair ? N / 2 : N), (uint32_t)(2 * p.bg)};
-  if ((r = umma::encode_f32(&plan->b, (void*)w_slab, 3, bdims, bstr, bbox, swz))) return r;
+  if ((r = umma::encode_f16(&plan->b, (void*)w_slab, 3, bdims, bstr, bbox, swz))) return r;
   return 0;
 }
 
-// floats of the combined (hi + lo) weight slab
-static inline size_t conv_weight_slab_floats(int cin, int cout_padded, int ntaps) {
+// halves of the combined (hi + lo) weight slab
+static inline size_t conv_weight_slab_halves(int cin, int cout_padded, int ntaps) {
   const bool wide = conv_is_wide(cin, ntaps);
   int nc, kl; conv_chunks(cin, &nc, &kl, wide);
-  return (size_t)cout_padded * nc * ntaps * (wide ? 32 : 16) * 2;
+  return (size_t)cout_padded * nc * ntaps * (wide ? 64 : 32) * 2;
 }
 
 // Optional per-launch timing (bench.py roofline): when enabled every GEMM launch is bracketed by CUDA events.

@@ -319,7 +319,11 @@ __global__ void masked_mse_bwd_kernel(const float* __restrict__ out, const float
 // torch.optim.Adam(betas=(0.9, 0.99), eps=1e-8) as used by train.py:100-107; grad_scale folds the 1/world_size of the
 // data-parallel all-reduce.  bc1 = 1 - beta1^t, bc2_sqrt = sqrt(1 - beta2^t) are computed on the host in fp64.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float step_size, float beta1, float beta2, float eps, float bc2_sqrt, float grad_scale) {
+                            long long n, float step_size, float beta1, float beta2, float eps, float bc2_sqrt, float grad_scale,
+                            const float* __restrict__ skip, int n_skip) {
+  // skip[0 .. n_skip): "this step's gradients are stale" flags left behind by the networks' backward passes (summed over ranks
+  // by the gradient all-reduce): any non-zero flag turns the whole update into a no-op
+  for (int j = 0; j < n_skip; ++j) if (__ldg(skip + j) != 0.f) return;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gr = g[i] * grad_scale;

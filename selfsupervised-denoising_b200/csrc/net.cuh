@@ -16,22 +16,32 @@ namespace net {
 using eng::Arena;
 using eng::round_up;
 
-struct Buf {                 // one padded-flat tensor (two planes when lo != nullptr)
-  float* v = nullptr; float* lo = nullptr;
+struct Buf {                 // one padded-flat tensor: a GEMM operand (two scaled fp16 planes + a scale slot) or a raw fp32 plane
+  __half* hi = nullptr; __half* lo = nullptr;     // operand planes
+  float* v = nullptr;                             // raw fp32 plane (gradients that only feed pointwise kernels)
+  ScaleRef sc{}; int sid = -1;                    // scale slot of an operand tensor
   Geom g{}; int cpitch = 0;
   uint32_t* mask = nullptr; int mask_words = 0;   // LeakyReLU sign bits [flat pixel][words] (buffers whose derivative a dgrad epilogue applies)
-  size_t floats() const { return (size_t)g.total() * cpitch; }
+  size_t elems() const { return (size_t)g.total() * cpitch; }
 };
+
+// Scale slots of a network (common.cuh): activations, gradients, weights.  Each range is begun / finished by its own pass.
+constexpr int kSlotA = 0, kSlotG = 32, kSlotW = 64, kSlots = 96;
+constexpr int kInitActScale = 8;                  // first forward pass of a plan: activations are assumed to peak near 2^3
+__global__ void scale_init_kernel(pw::ScaleState st, int first, int count, int value) {
+  const int i = first + threadIdx.x;
+  if (threadIdx.x < count) { st.k[i] = value; st.k_next[i] = value; }
+}
 
 struct Layer {               // one convolution of the network
   std::string name;
   int cin, cout, ksize;
   size_t w_off, b_off;       // offsets (floats) into the flat parameter / gradient buffers
   // forward
-  ConvPlan fwd; float* slab_f; int n_f; int coutp_f;
+  ConvPlan fwd; __half* slab_f; int n_f; int coutp_f;
   // data gradient (has_dgrad == false for the first conv: nobody consumes d(input))
   bool has_dgrad = false;
-  ConvPlan dgrad; float* slab_d; int n_d; int cinp_d; int dgrad_nvalid;
+  ConvPlan dgrad; __half* slab_d; int n_d; int cinp_d; int dgrad_nvalid;
   bool bias_fused = false; int bias_nblk = 0;   // bias gradient = column sums written by the kernel that produced this layer's dZ
   const float* bias_partial = nullptr;          //   partial[bias_nblk][cout]
   float* bias_buf = nullptr;                    //   this layer's own partial buffer (all bias reductions run as one kernel at the end)
@@ -57,6 +67,8 @@ class Net {
   Buf cat[6], e[6], e1a, p5, d_a[6], head_in, h1, h2;
   Buf g_out, dz_h2, dz_h1, dz_db[6], dz_da[6], gcat[6], dz_e[7], dz_e1a, g_p[6];
   float* partial = nullptr; float* colpart = nullptr; int* flag = nullptr;
+  pw::ScaleState scales{}; int n_slot_a = 0, n_slot_g = 0;   // operand-scale state (device) and the number of slots per range
+  int fwd_runs = 0, bwd_runs = 0;                            // passes launched so far (the first ones seed the scales)
   size_t partial_floats = 0;
   size_t ws_bytes = 0; void* ws = nullptr;
   std::vector<PoolOp> pools; std::vector<PoolBwdOp> pool_bwds; std::vector<UpBwdOp> up_bwds;
@@ -120,47 +132,57 @@ class Net {
   // Lays every buffer out in the workspace; with base == nullptr only measures.
   size_t carve(void* base, size_t cap) {
     Arena a(base, cap);
-    auto mk = [&](Buf& b, const Geom& gg, int cp, bool lo) {
-      b.g = gg; b.cpitch = cp;
-      b.v = a.take<float>(b.floats()); b.lo = lo ? a.take<float>(b.floats()) : nullptr;
-      if (!lo) b.lo = nullptr;
+    // scale state first: its addresses go into every operand buffer
+    scales.k = a.take<int>(kSlots); scales.k_next = a.take<int>(kSlots); scales.amax = a.take<unsigned>(kSlots);
+    scales.status = a.take<int>(8); scales.counter = a.take<unsigned>(1);
+    n_slot_a = 0; n_slot_g = 0;
+    auto slot = [&](Buf& b, int sid) { b.sid = sid; b.sc.k = scales.k ? scales.k + sid : nullptr; b.sc.amax = scales.amax ? scales.amax + sid : nullptr; };
+    // kind: 0 raw fp32 plane, 1 activation operand, 2 gradient operand.  Plane pairs are one allocation (+ slack: the weight
+    // gradient's 64-channel TMA blocks may run past the last pixel's channels)
+    auto mk = [&](Buf& b, const Geom& gg, int cp, int kind) {
+      b.g = gg; b.cpitch = cp; b.hi = b.lo = nullptr; b.v = nullptr;
+      if (kind == 0) { b.v = a.take<float>(b.elems()); return; }
+      const size_t n = (b.elems() + 127) / 128 * 128;
+      __half* p = a.take<__half>(2 * n + 256);
+      b.hi = p; b.lo = p ? p + n : nullptr;
+      slot(b, kind == 1 ? kSlotA + n_slot_a++ : kSlotG + n_slot_g++);
     };
     auto mkmask = [&](Buf& b) { b.mask_words = (b.cpitch + 31) / 32; b.mask = a.take<uint32_t>((size_t)b.g.total() * b.mask_words); };
-    const int c1 = round_up(96 + Cin, 4);
-    mk(cat[1], g[0], c1, true); mk(e1a, g[0], 48, true); mk(e[1], g[0], 48, true);
-    mk(cat[2], g[1], 144, true); mk(e[2], g[1], 48, true);
-    mk(cat[3], g[2], 144, true); mk(e[3], g[2], 48, true);
-    mk(cat[4], g[3], 144, true); mk(e[4], g[3], 48, true);
-    mk(cat[5], g[4], 96, true); mk(e[5], g[4], 48, true);
-    mk(p5, g[5], 48, true);
-    for (int l = 1; l <= 5; ++l) mk(d_a[l], g[l - 1], 96, true);        // dec{l}a output lives at level l-1
-    mk(head_in, gh, nin, true); mk(h1, gh, nin, true); mk(h2, gh, 96, true);
+    const int c1 = round_up(96 + Cin, 8);
+    mk(cat[1], g[0], c1, 1); mk(e1a, g[0], 48, 1); mk(e[1], g[0], 48, 1);
+    mk(cat[2], g[1], 144, 1); mk(e[2], g[1], 48, 1);
+    mk(cat[3], g[2], 144, 1); mk(e[3], g[2], 48, 1);
+    mk(cat[4], g[3], 144, 1); mk(e[4], g[3], 48, 1);
+    mk(cat[5], g[4], 96, 1); mk(e[5], g[4], 48, 1);
+    mk(p5, g[5], 48, 1);
+    for (int l = 1; l <= 5; ++l) mk(d_a[l], g[l - 1], 96, 1);        // dec{l}a output lives at level l-1
+    mk(head_in, gh, nin, 1); mk(h1, gh, nin, 1); mk(h2, gh, 96, 1);
     for (int l = 1; l <= 5; ++l) mkmask(d_a[l]);
     mkmask(e1a); mkmask(head_in); mkmask(h1); mkmask(h2);
     // backward
-    mk(g_out, gh, round_up(Cout, 4), true); mk(dz_h2, gh, 96, true); mk(dz_h1, gh, nin, true);
-    for (int l = 1; l <= 5; ++l) { mk(dz_db[l], g[l - 1], 96, true); mk(dz_da[l], g[l - 1], 96, true); }
-    mk(gcat[1], g[0], 96, false);
-    for (int l = 2; l <= 4; ++l) mk(gcat[l], g[l - 1], 144, false);
-    mk(gcat[5], g[4], 96, false);
-    for (int l = 1; l <= 5; ++l) mk(dz_e[l], g[l - 1], 48, true);       // dZ of the conv that feeds pool l
-    mk(dz_e[6], g[5], 48, true); mk(dz_e1a, g[0], 48, true);
-    for (int l = 1; l <= 5; ++l) mk(g_p[l], g[l], 48, false);           // d(pool l) coming from the next encoder conv
+    mk(g_out, gh, round_up(Cout, 8), 2); mk(dz_h2, gh, 96, 2); mk(dz_h1, gh, nin, 2);
+    for (int l = 1; l <= 5; ++l) { mk(dz_db[l], g[l - 1], 96, 2); mk(dz_da[l], g[l - 1], 96, 2); }
+    mk(gcat[1], g[0], 96, 0);
+    for (int l = 2; l <= 4; ++l) mk(gcat[l], g[l - 1], 144, 0);
+    mk(gcat[5], g[4], 96, 0);
+    for (int l = 1; l <= 5; ++l) mk(dz_e[l], g[l - 1], 48, 2);       // dZ of the conv that feeds pool l
+    mk(dz_e[6], g[5], 48, 2); mk(dz_e1a, g[0], 48, 2);
+    for (int l = 1; l <= 5; ++l) mk(g_p[l], g[l], 48, 0);           // d(pool l) coming from the next encoder conv
     // weight slabs
     for (auto& l : layers) {
       const int nt = l.ksize * l.ksize;
       l.coutp_f = round_up(l.cout, 16);
       l.n_f = (l.cout == 384) ? (l.ksize == 1 ? 192 : 96) : eng::pick_n(l.coutp_f);   // 1x1: N = 192 halves the re-reads of A
-      size_t f = conv_weight_slab_floats(l.cin, l.coutp_f, nt);
-      l.slab_f = a.take<float>(f);
+      size_t f = conv_weight_slab_halves(l.cin, l.coutp_f, nt);
+      l.slab_f = a.take<__half>(f);
       l.has_dgrad = (l.name != "encode_block_1.0");
       l.dgrad_nvalid = (l.name == "decode_block_1.0") ? 96 : l.cin;       // d(x) part of the last concat is never used
       l.cinp_d = round_up(l.dgrad_nvalid, 16);
       // data-gradient N tiles: the un-rotating head conv needs one tile per rotation branch (96 channels)
       l.n_d = (l.cinp_d == 384) ? ((l.name == "output_block.0" || l.ksize != 1) ? 96 : 192) : eng::pick_n(l.cinp_d);
       if (l.cinp_d == 144) l.n_d = 144;   // one N=144 tile (T = 1) instead of three smem-bound N=48 tiles
-      size_t fd = conv_weight_slab_floats(l.cout, l.cinp_d, nt);
-      l.slab_d = a.take<float>(fd);
+      size_t fd = conv_weight_slab_halves(l.cout, l.cinp_d, nt);
+      l.slab_d = a.take<__half>(fd);
     }
     // wgrad partials: one buffer, sized for the largest layer
     partial_floats = 0;
@@ -168,12 +190,10 @@ class Net {
       const Geom& gg = (l.ksize == 1) ? gh : g[level_of(l.name)];
       l.ksplit = wgrad_pick_ksplit(gg.total(), l.cout, l.cin, l.ksize * l.ksize, sms);
       partial_floats = std::max(partial_floats, wgrad_partial_floats(l.ksplit, l.ksize * l.ksize, l.cout, l.cin));
-      if (wgradk::wgrad_small_cin_ok(l.cin, l.cout, l.ksize * l.ksize))
-        partial_floats = std::max(partial_floats, wgradk::wgrad_small_cin_partial_floats(l.cin, l.cout));
     }
     partial = a.take<float>(partial_floats);
     colpart = a.take<float>((size_t)1024 * 384);
-    for (auto& l : layers) l.bias_buf = a.take<float>((size_t)148 * convk::kEpiWarps * l.cout);
+    for (auto& l : layers) l.bias_buf = a.take<float>((size_t)std::max(sms * convk::kEpiWarps, pw::kFusedColsumGrid) * l.cout);
     flag = a.take<int>(64);
     return a.off;
   }
@@ -192,6 +212,8 @@ class Net {
     cudaError_t ce = cudaMemsetAsync(workspace, 0, ws_bytes, st);   // zero halos (never written afterwards)
     if (ce != cudaSuccess) return eng::fail(-2, "memset failed: %s", cudaGetErrorString(ce));
     pools.clear(); pool_bwds.clear(); up_bwds.clear();
+    scale_init_kernel<<<1, 32, 0, st>>>(scales, kSlotA, n_slot_a, kInitActScale);
+    fwd_runs = bwd_runs = 0;
     int r;
     const int act = EP_BIAS | EP_LRELU | EP_WRITE_LO;
     // ---- encoder
@@ -216,7 +238,7 @@ class Net {
     // ---- head
     if ((r = plan_fwd(L("output_block.0"), head_in, 0, dst(h1, 0, MAP_IDENT, act, nin)))) return r;
     if ((r = plan_fwd(L("output_block.2"), h1, 0, dst(h2, 0, MAP_IDENT, act, 96)))) return r;
-    { ConvDst d = dst(h2, 0, MAP_NCHW, EP_BIAS, Cout); d.v = nullptr; d.lo = nullptr; d.g = gh;
+    { ConvDst d = dst(h2, 0, MAP_NCHW, EP_BIAS, Cout); d.v = nullptr; d.hi = d.lo = nullptr; d.g = gh;
       if ((r = plan_fwd(L("output_conv"), h2, 0, d))) return r; }
 
     // ---- backward: data gradients
@@ -225,6 +247,7 @@ class Net {
     auto fused = [&](const char* producer, const char* owner) {
       Layer& o = L(owner); o.bias_fused = true; o.bias_partial = o.bias_buf;
       o.bias_nblk = L(producer).dgrad.grid * (L(producer).dgrad.p.epi_split ? convk::kEpiWarps : 4);
+      if ((size_t)o.bias_nblk > (size_t)std::max(sms * convk::kEpiWarps, pw::kFusedColsumGrid)) o.bias_nblk = -1;   // checked below
     };
     // pointwise producers (grid-stride kernels with at most kFusedColsumGrid blocks of kFusedColsumBlock threads)
     auto pw_grid = [&](long long n) { return (int)std::min<long long>(pw::kFusedColsumGrid, (n + pw::kFusedColsumBlock - 1) / pw::kFusedColsumBlock); };
@@ -245,21 +268,21 @@ class Net {
       fused(b_nm.c_str(), a_nm.c_str());
       if ((r = plan_dgrad(L(a_nm), dz_da[i], dst(gcat[i], 0, MAP_IDENT, 0, L(a_nm).dgrad_nvalid)))) return r;
       if (i < 5) {
-        const int grid = pw_grid((long long)g[i].B * g[i].H * g[i].W * (96 / 4));
+        const int grid = pw_grid((long long)g[i].B * g[i].H * g[i].W * (96 / 8));
         up_bwds.push_back({&gcat[i], &cat[i], &dz_db[i + 1], 96, fused_pw("decode_block_" + std::to_string(i + 1) + ".2", grid), grid});
       }
     }
-    { const int grid = pw_grid((long long)g[5].B * g[5].H * g[5].W * (48 / 4));
+    { const int grid = pw_grid((long long)g[5].B * g[5].H * g[5].W * (48 / 8));
       up_bwds.push_back({&gcat[5], &cat[5], &dz_e[6], 48, fused_pw("encode_block_6.0", grid), grid}); }
     if ((r = plan_dgrad(L("encode_block_6.0"), dz_e[6], dst(g_p[5], 0, MAP_IDENT, 0, 48)))) return r;
     for (int i = 5; i >= 2; --i) {
       // dZ of the conv feeding pool i: gradient from the next encoder conv (+ the skip path for i <= 4)
-      { const int grid = pw_grid((long long)g[i].B * g[i].H * g[i].W * 48);
+      { const int grid = pw_grid((long long)g[i].B * g[i].H * g[i].W * (48 / 8));
         pool_bwds.push_back({&e[i], &g_p[i], i <= 4 ? &gcat[i + 1] : nullptr, i == 4 ? 48 : 96, &dz_e[i], g[i],
                              fused_pw("encode_block_" + std::to_string(i) + ".0", grid), grid}); }
       if ((r = plan_dgrad(L("encode_block_" + std::to_string(i) + ".0"), dz_e[i], dst(g_p[i - 1], 0, MAP_IDENT, 0, 48)))) return r;
     }
-    { const int grid = pw_grid((long long)g[1].B * g[1].H * g[1].W * 48);
+    { const int grid = pw_grid((long long)g[1].B * g[1].H * g[1].W * (48 / 8));
       pool_bwds.push_back({&e[1], &g_p[1], &gcat[2], 96, &dz_e[1], g[1], fused_pw("encode_block_1.2", grid), grid}); }
     if ((r = plan_dgrad(L("encode_block_1.2"), dz_e[1], dst_act(dz_e1a, MAP_IDENT, gact, 48, e1a, &L("encode_block_1.0"))))) return r;
     fused("encode_block_1.2", "encode_block_1.0");
@@ -282,19 +305,20 @@ class Net {
       l.x = w.x; l.x_coff = w.xoff; l.dz = w.dz;
       const Geom& gg = w.x->g;
       ConvTaps taps = eng::make_taps(l.ksize, blind, false, gg.P);
-      if ((r = wgrad_plan_init(&l.wgrad, gg.total(), w.dz->v, w.dz->lo, w.dz->cpitch, 0, l.cout, w.x->v, w.x->lo, w.x->cpitch,
-                               w.xoff, l.cin, taps, l.ksplit, partial, flag, sms)))
+      if ((r = wgrad_plan_init(&l.wgrad, gg.total(), w.dz->hi, w.dz->lo, w.dz->cpitch, 0, l.cout, w.x->hi, w.x->lo, w.x->cpitch,
+                               w.xoff, l.cin, taps, l.ksplit, partial, flag, sms, w.dz->sc.k, w.x->sc.k)))
         return eng::fail(r, "wgrad plan for %s failed (%d)", w.nm, r);
       l.wgrad.flops = 2.0 * B0(gg) * l.cin * l.cout * l.ksize * l.ksize;
     }
+    for (auto& l : layers) if (l.bias_fused && l.bias_nblk < 0) return eng::fail(-6, "bias partial buffer of %s too small", l.name.c_str());
     return 0;
   }
 
   static double B0(const Geom& gg) { return (double)gg.B * gg.H * gg.W; }   // valid pixels of a geometry
 
   ConvDst dst(Buf& b, int coff, int map, int flags, int cvalid) {
-    ConvDst d{}; d.v = b.v; d.lo = b.lo; d.cpitch = b.cpitch; d.coff = coff; d.g = b.g; d.map = map; d.flags = flags;
-    if (!b.lo) d.flags &= ~EP_WRITE_LO;
+    ConvDst d{}; d.v = b.v; d.hi = b.hi; d.lo = b.lo; d.scale = b.sc; d.cpitch = b.cpitch; d.coff = coff; d.g = b.g; d.map = map; d.flags = flags;
+    if (!b.hi) d.flags &= ~EP_WRITE_LO;
     d.cvalid = cvalid; d.nimg = N; d.bias = nullptr;
     if (b.mask && (flags & EP_LRELU) && (map == MAP_IDENT || map == MAP_UNROT)) { d.mask_out = b.mask; d.mask_out_words = b.mask_words; }
     return d;
@@ -307,18 +331,21 @@ class Net {
     return d;
   }
 
+  int layer_index(const Layer& l) const { return (int)(&l - layers.data()); }
+  const int* k_w(const Layer& l) const { return scales.k ? scales.k + kSlotW + layer_index(l) : nullptr; }
+
   int plan_fwd(Layer& l, Buf& src, int coff, ConvDst d) {
     ConvTaps taps = eng::make_taps(l.ksize, blind, false, src.g.P);
-    int r = conv_plan_init(&l.fwd, src.g, src.v, src.lo, src.cpitch, coff, l.cin, l.slab_f, l.coutp_f, l.n_f, taps, d,
-                           flag, sms);
+    int r = conv_plan_init(&l.fwd, src.g, src.hi, src.lo, src.cpitch, coff, l.cin, l.slab_f, l.coutp_f, l.n_f, taps, d,
+                           flag, sms, src.sc.k, k_w(l));
     if (r) return eng::fail(r, "forward plan for %s failed (%d)", l.name.c_str(), r);
     l.fwd.flops = 2.0 * B0(src.g) * l.cin * l.cout * l.ksize * l.ksize;
     return 0;
   }
   int plan_dgrad(Layer& l, Buf& src, ConvDst d) {
     ConvTaps taps = eng::make_taps(l.ksize, blind, true, src.g.P);
-    int r = conv_plan_init(&l.dgrad, src.g, src.v, src.lo, src.cpitch, 0, l.cout, l.slab_d, l.cinp_d, l.n_d, taps, d,
-                           flag, sms);
+    int r = conv_plan_init(&l.dgrad, src.g, src.hi, src.lo, src.cpitch, 0, l.cout, l.slab_d, l.cinp_d, l.n_d, taps, d,
+                           flag, sms, src.sc.k, k_w(l));
     if (r) return eng::fail(r, "dgrad plan for %s failed (%d)", l.name.c_str(), r);
     l.dgrad.flops = 2.0 * B0(src.g) * l.dgrad_nvalid * l.cout * l.ksize * l.ksize;
     return 0;
@@ -326,17 +353,22 @@ class Net {
 
   // ------------------------------------------------------------------ execution
   int prep_weights(const float* params, cudaStream_t st, bool with_dgrad) {
+    // exact per-layer scales first (weights are leaves), then all slabs in one launch
+    pw::WeightScaleJobs sj{};
+    int ns = 0;
+    for (auto& l : layers) sj.j[ns++] = {params + l.w_off, l.cout * l.cin * l.ksize * l.ksize, kSlotW + layer_index(l)};
+    pw::weight_scale_kernel<<<ns, 256, 0, st>>>(sj, scales);
     pw::WeightPrepJobs jobs{};
     int nj = 0;
     for (auto& l : layers) {
       const int nt = l.ksize * l.ksize;
       bool wide = conv_is_wide(l.cin, nt);
       int nc, kl; conv_chunks(l.cin, &nc, &kl, wide);
-      jobs.j[nj++] = {params + l.w_off, l.slab_f, l.cout, l.cin, nt, l.cout, l.cin, l.coutp_f / l.n_f, nc, l.n_f, 0, wide ? 32 : 16};
+      jobs.j[nj++] = {params + l.w_off, l.slab_f, l.cout, l.cin, nt, l.cout, l.cin, l.coutp_f / l.n_f, nc, l.n_f, 0, wide ? 64 : 32, k_w(l)};
       if (with_dgrad && l.has_dgrad) {
         wide = conv_is_wide(l.cout, nt);
         conv_chunks(l.cout, &nc, &kl, wide);
-        jobs.j[nj++] = {params + l.w_off, l.slab_d, l.cout, l.cin, nt, l.dgrad_nvalid, l.cout, l.cinp_d / l.n_d, nc, l.n_d, 1, wide ? 32 : 16};
+        jobs.j[nj++] = {params + l.w_off, l.slab_d, l.cout, l.cin, nt, l.dgrad_nvalid, l.cout, l.cinp_d / l.n_d, nc, l.n_d, 1, wide ? 64 : 32, k_w(l)};
       }
     }
     pw::weight_prep_batched_kernel<<<dim3(64, nj), pw::kBlock, 0, st>>>(jobs);
@@ -354,15 +386,17 @@ class Net {
   int forward(const float* params, const float* x, float* out, cudaStream_t st, bool training) {
     if (!ws) return eng::fail(-5, "network workspace not bound");
     int r;
+    pw::scale_begin_kernel<<<1, 32, 0, st>>>(scales, kSlotA, n_slot_a);
+    ++fwd_runs;
     if ((r = prep_weights(params, st, training))) return r;
-    pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)B * H * W), pw::kBlock, 0, st>>>(x, cat[1].v, cat[1].lo, N, Cin, H, W, g[0],
-                                                                                          cat[1].cpitch, 96, blind ? 1 : 0);
+    pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)B * H * W), pw::kBlock, 0, st>>>(x, cat[1].hi, cat[1].lo, N, Cin, H, W, g[0],
+                                                                                          cat[1].cpitch, 96, blind ? 1 : 0, cat[1].sc);
     size_t pi = 0;
     auto pool = [&]() {
       const PoolOp& p = pools[pi++];
-      const long long n = (long long)p.dst->g.B * p.dst->g.H * p.dst->g.W * 12;
-      pw::pool_fwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(p.src->v, p.src->lo, p.src->g, p.src->cpitch, 0, p.dst->v, p.dst->lo, p.dst->g,
-                                                                  p.dst->cpitch, p.dst_coff, 48, blind ? 1 : 0);
+      const long long n = (long long)p.dst->g.B * p.dst->g.H * p.dst->g.W * 6;
+      pw::pool_fwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(p.src->hi, p.src->lo, p.src->g, p.src->cpitch, 0, p.src->sc, p.dst->hi, p.dst->lo,
+                                                                  p.dst->g, p.dst->cpitch, p.dst_coff, p.dst->sc, 48, blind ? 1 : 0);
     };
     if ((r = run_fwd(L("encode_block_1.0"), params, st))) return r;
     if ((r = run_fwd(L("encode_block_1.2"), params, st))) return r;
@@ -376,6 +410,7 @@ class Net {
     if ((r = run_fwd(L("output_block.0"), params, st))) return r;
     if ((r = run_fwd(L("output_block.2"), params, st))) return r;
     if ((r = run_fwd(L("output_conv"), params, st, out))) return r;
+    pw::scale_finish_kernel<<<1, 32, 0, st>>>(scales, kSlotA, n_slot_a, 0, nullptr);
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }
@@ -383,12 +418,10 @@ class Net {
   int run_wgrad(Layer& l, float* grads, cudaStream_t st) {
     const int nt = l.ksize * l.ksize;
     // bias gradient: reduce the column-sum partials its dZ producer left behind (main stream: the next producer reuses them)
-    if (l.bias_fused) {
-      // nothing here: backward() finishes all bias gradients with one batched reduction after the last producer
-    } else {
+    if (!l.bias_fused) {
       const long long rows = l.dz->g.total();
-      pw::colsum_launch(l.dz->v, l.dz->lo, rows, l.dz->cpitch, 0, l.cout, colpart, grads + l.b_off, st);
-    }
+      pw::colsum_launch(l.dz->hi, l.dz->lo, l.dz->sc.k, rows, l.dz->cpitch, 0, l.cout, colpart, grads + l.b_off, st);
+    }   // else: backward() finishes all bias gradients with one batched reduction after the last producer
     cudaStream_t ws_ = st;
     if (use_side && !profiler().on) {   // per-launch profiling serialises everything on one stream
       if (!side) {
@@ -400,19 +433,8 @@ class Net {
       SSDN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
       ws_ = side;
     }
-    const bool small_cin = wgradk::wgrad_small_cin_ok(l.cin, l.cout, nt) && l.dz->cpitch == l.cout &&
-                           wgradk::kSmallCinTile + 2 * l.x->g.P + 2 <= 12 * l.cout;   // X window rows <= 2 x threads
-    if (small_cin) {                                              // first conv: CUDA-core kernel (see wgrad_igemm.cuh)
-      ConvTaps taps = eng::make_taps(l.ksize, blind, false, l.x->g.P);
-      if (profiler().on) profiler().begin(2, l.wgrad.flops, ws_);
-      cudaError_t ce = wgradk::wgrad_small_cin_launch(l.dz->v, l.dz->lo, l.dz->cpitch, l.cout, l.x->v, l.x->lo, l.x->cpitch, l.x_coff, l.cin,
-                                                      l.x->g.total(), taps.off, partial, grads + l.w_off, ws_);
-      if (profiler().on) profiler().end(ws_);
-      SSDN_CUDA(ce);
-    } else {
-      SSDN_CUDA(wgrad_launch(l.wgrad, ws_));
-      wgradk::wgrad_reduce_launch(partial, l.wgrad.p.ksplit, nt, l.cout, l.cin, l.wgrad.p.cin_pitch, grads + l.w_off, 0, ws_);
-    }
+    SSDN_CUDA(wgrad_launch(l.wgrad, ws_));
+    wgradk::wgrad_reduce_launch(partial, l.wgrad.p.ksplit, nt, l.cout, l.cin, l.wgrad.p.cin_pitch, grads + l.w_off, 0, ws_);
     return 0;
   }
   int join_side(cudaStream_t st) {
@@ -421,12 +443,18 @@ class Net {
   }
   int run_dgrad(Layer& l, cudaStream_t st) { SSDN_CUDA(conv_launch(l.dgrad, st, 1)); return 0; }
 
-  // grads: flat buffer with the layout of params; every element is overwritten.
-  int backward(const float* params, const float* dout, float* grads, cudaStream_t st) {
+  // grads: flat buffer with the layout of params; every element is overwritten.  stale_out (optional, device): receives 1.0f
+  // when this step's forward or backward pass ran with operand scales outside their band (see common.cuh), else 0.0f.
+  int backward(const float* params, const float* dout, float* grads, float* stale_out, cudaStream_t st) {
     if (!ws) return eng::fail(-5, "network workspace not bound");
     int r;
-    pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)N * H * W), pw::kBlock, 0, st>>>(dout, g_out.v, g_out.lo, N, Cout, H, W, gh,
-                                                                                          g_out.cpitch, 0, 0);
+    pw::scale_begin_kernel<<<1, 32, 0, st>>>(scales, kSlotG, n_slot_g);
+    // the loss gradient is a leaf: exact scale now; the very first backward pass seeds every gradient slot with it
+    pw::leaf_scale_kernel<<<64, 256, 0, st>>>(dout, (long long)N * Cout * H * W, scales, g_out.sid, kSlotG, bwd_runs == 0 ? n_slot_g : 0);
+    ++bwd_runs;
+    ScaleRef no_amax = g_out.sc; no_amax.amax = nullptr;
+    pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)N * H * W), pw::kBlock, 0, st>>>(dout, g_out.hi, g_out.lo, N, Cout, H, W, gh,
+                                                                                          g_out.cpitch, 0, 0, no_amax);
     pw::nchw_colsum_kernel<<<dim3(Cout, N), 256, 0, st>>>(dout, Cout, H * W, L("output_conv").bias_buf);
     auto both = [&](const std::string& nm, bool dgrad) -> int {
       Layer& l = L(nm);
@@ -443,14 +471,14 @@ class Net {
       const Geom& gl = u.dz->g;
       const long long n = (long long)gl.B * gl.H * gl.W * (u.C / 4);
       (void)n;
-      pw::up_bwd_kernel<<<u.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * sizeof(float4), st>>>(
-          u.g->v, u.g->g, u.g->cpitch, 0, u.act_up->v, u.act_up->cpitch, 0, gl, u.dz->v, u.dz->lo, u.dz->cpitch, 0, u.C, u.colsum);
+      pw::up_bwd_kernel<<<u.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * 8 * sizeof(float), st>>>(
+          u.g->v, u.g->g, u.g->cpitch, 0, u.act_up->hi, u.act_up->cpitch, 0, gl, u.dz->hi, u.dz->lo, u.dz->cpitch, 0, u.dz->sc, u.C, u.colsum);
     };
     auto pool_bwd = [&]() {
       const PoolBwdOp& q = pool_bwds[qi++];
-      pw::pool_bwd_kernel<<<q.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * sizeof(float), st>>>(
-          q.act->v, q.act->lo, q.act->g, q.act->cpitch, 0, q.g1->v, q.g1->cpitch, 0, q.g2 ? q.g2->v : nullptr, q.g2 ? q.g2->cpitch : 0, q.g2_coff, q.gp,
-          q.dz->v, q.dz->lo, q.dz->cpitch, 0, 48, blind ? 1 : 0, q.colsum);
+      pw::pool_bwd_kernel<<<q.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * 8 * sizeof(float), st>>>(
+          q.act->hi, q.act->lo, q.act->g, q.act->cpitch, 0, q.g1->v, q.g1->cpitch, 0, q.g2 ? q.g2->v : nullptr, q.g2 ? q.g2->cpitch : 0, q.g2_coff, q.gp,
+          q.dz->hi, q.dz->lo, q.dz->cpitch, 0, q.dz->sc, 48, blind ? 1 : 0, q.colsum);
     };
     for (int i = 1; i <= 5; ++i) {
       if ((r = both("decode_block_" + std::to_string(i) + ".2", true))) return r;
@@ -473,6 +501,7 @@ class Net {
       if (nj) pw::colsum_stage2_batched_kernel<<<dim3((maxc + 31) / 32, nj), dim3(32, 32), 0, st>>>(jobs);
     }
     if ((r = join_side(st))) return r;
+    pw::scale_finish_kernel<<<1, 32, 0, st>>>(scales, kSlotG, n_slot_g, 1, stale_out);
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }

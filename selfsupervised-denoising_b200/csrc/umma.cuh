@@ -1,5 +1,5 @@
 // sm_100a primitives used by the implicit-GEMM kernels: mbarrier, TMA (cp.async.bulk.tensor),
-// TMEM allocation, tcgen05.mma (kind::tf32), tcgen05.ld, and the shared-memory / instruction
+// TMEM allocation, tcgen05.mma (kind::f16; kind::tf32 kept for the probes), tcgen05.ld, and the shared-memory / instruction
 // descriptor encoders. Everything here is inline PTX; no CUTLASS dependency.
 #pragma once
 #include <cuda.h>
@@ -152,6 +152,27 @@ __device__ __forceinline__ void mma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (fp16 operands, K = 16 per instruction, fp32 accumulate): the product path.  Same descriptor conventions as
+// kind::tf32 (profiles/r02_f16_probe.log), twice the K per instruction at the same issue rate.
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -227,6 +248,17 @@ __device__ __forceinline__ void mma_tf32_lo_pair(uint32_t tmem_d, uint32_t a_lo,
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mma_f16_lo_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once all previously issued MMAs completed
 __device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -256,6 +288,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N, u
                                                        uint32_t b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major & 1u) << 15) | ((b_mn_major & 1u) << 16) |
          ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// Instruction descriptor for kind::f16 with fp16 A / B (format 0) and fp32 accumulate: the field positions of make_idesc_tf32.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
+  return (1u << 4) | ((a_mn_major & 1u) << 15) | ((b_mn_major & 1u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 }  // namespace umma
@@ -288,6 +325,21 @@ inline int encode_f32(CUtensorMap* m, void* base, int rank, const uint64_t* dims
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, base, d, s, b, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+// fp16 tensor, rank<=5. dims/strides innermost first; strides in BYTES for dims 1..rank-1.  Out-of-bounds elements read as zero.
+inline int encode_f16(CUtensorMap* m, void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw) {
+  auto fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint64_t d[5], s[5];
+  cuuint32_t b[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, d, s, b, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;

@@ -4,19 +4,18 @@
 //
 // Both operands are padded-flat NHWC tensors (common.cuh), so the reduction (K) dimension is the
 // flat pixel index and both operands are "MN-major" for the tensor core: a smem row is one pixel,
-// 32 channels (128 bytes) wide.  For tf32 the only MN-major shared-memory layout is the 128-byte
-// swizzle with a 32-byte atom (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B / UMMA layout type 1), verified
-// on hardware by csrc/probe/umma_probe.cu, including start addresses shifted by whole pixel rows -
+// 64 fp16 channels (128 bytes) wide, SWIZZLE_128B atoms of 8 pixel rows (LBO = distance between 64-channel blocks,
+// SBO = 1024; verified by csrc/probe/umma_f16_probe.cu F6), with start addresses shifted by whole pixel rows -
 // which is how the taps of one stencil row share a single staged window of X.
 //   unit  = (128-wide co tile) x (ci block, N <= 144 / 192) x (tap group = stencil row) x (K split)
-//   stage = KC flat pixels of dZ (<= 4 blocks of 32 co) + KC+halo pixels of X (<= 6 blocks of 32 ci), two TMA ops
+//   stage = KC flat pixels of dZ (<= 2 blocks of 64 co) + KC+halo pixels of X (<= 3 blocks of 64 ci), two TMA ops
 // Accumulators [co lane][tap][ci] live in TMEM for the whole K range of the unit; partial results (float4 rows, padded
 // to 16 bytes) go to a workspace and a fixed-order parallel reduction produces dW (deterministic, no atomics).
 // Unit order: the tap groups / ci blocks / co tiles of one K range are adjacent, so concurrently running CTAs share
 // their dZ and X rows through L2; the K split gives one unit per SM (a whole wave, and the fewest partials to reduce).  Layers with <= 64 output
-// channels issue M = 64 MMAs (half the dZ operand bytes).  The first conv (<= 4 input channels) does not use this kernel
-// at all: wgrad_small_cin_kernel below runs on the CUDA cores.
-// Precision: 3xTF32 as in the forward kernel, with the same accumulator-truncation compensation per K split.
+// channels issue M = 64 MMAs (half the dZ operand bytes).  The first conv (3 input channels) runs here too, as an N = 16 tile.
+// Precision: two-term fp16 split as in the forward kernel (K = 16 pixels per MMA), the accumulator scaled back by
+// 2^-(k_dz + k_x), with the same accumulator-truncation compensation per K split.
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -32,11 +31,12 @@ struct WgradParams {
                        // operand-bandwidth-bound); accumulator row m then lives in TMEM lane (m % 16) + 32 * (m / 16)
   int cin_pitch;       // floats per (tap, co) row of the partial buffer: cin rounded up to 4 so that every row is 16-byte aligned
   int n_ci_blocks, ci_start[4], ci_n[4];
-  int nba, nbx;        // 32-channel blocks actually loaded per stage for dZ (<= 4) and X (<= 6)
+  int nba, nbx;        // 64-channel blocks actually loaded per stage for dZ (<= 2) and X (<= 3)
+  const int* k_dz; const int* k_x;   // scale exponents of the two operand tensors (device; null = 0)
   int n_groups, ntaps_total;
   WgradGroup groups[9];
   int b_rows, stages;
-  uint32_t a_plane_bytes, b_plane_bytes;   // a_plane_bytes = nba * KC * 128 (loaded part; the MMA may address up to 4 blocks)
+  uint32_t a_plane_bytes, b_plane_bytes;   // a_plane_bytes = nba * KC * 128 (loaded part; the MMA may address up to 2 blocks)
   float* partial;     // [ksplit][ntaps][cout][cin]
   int* error_flag;
   unsigned long long* stats;   // developer instrumentation (SSDN_CONV_STATS=1)
@@ -45,7 +45,7 @@ struct WgradParams {
 struct WgradPlan {
   WgradParams p;
   double flops = 0;
-  CUtensorMap dz, x;   // 4-D maps (32 channels, flat pixel, channel block, plane): ONE TMA op per operand per stage
+  CUtensorMap dz, x;   // 4-D fp16 maps (64 channels, flat pixel, channel block, plane): ONE TMA op per operand per stage
   int grid; size_t smem;
 };
 
@@ -105,8 +105,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
         if (umma::elect_one()) {
           // two TMA ops per stage: [plane][nba co blocks][KC rows][128 B] and [plane][nbx ci blocks][b_rows][128 B]
           umma::mbar_expect_tx(full(stage), 2 * (p.a_plane_bytes + p.b_plane_bytes));
-          umma::tma_load_4d(av, &map_dz, full(stage), 0, row, ct * 4, 0);
-          umma::tma_load_4d(bv, &map_x, full(stage), 0, brow, p.ci_start[cb] / 32, 0);
+          umma::tma_load_4d(av, &map_dz, full(stage), 0, row, ct * 2, 0);
+          umma::tma_load_4d(bv, &map_x, full(stage), 0, brow, p.ci_start[cb] / 64, 0);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -114,21 +114,22 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
     }
     if (p.stats && lane == 0) p.stats[blockIdx.x * 16 + 0] = w_empty;
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer: per (stage, tap) an unrolled block of KC/8 x 3 MMAs
+    // ------------------------------------------------------------ MMA issuer: per (stage, tap) an unrolled block of KC/16 x 3 MMAs
     int stage = 0; uint32_t phase = 0; int it = 0;
-    const uint64_t adesc = umma::make_desc_base(p.KC * 128, 512, 1);
-    const uint64_t bdesc = umma::make_desc_base(p.b_rows * 128, 512, 1);
+    const uint64_t adesc = umma::make_desc_base(p.KC * 128, 1024, umma::LAYOUT_SW128);
+    const uint64_t bdesc = umma::make_desc_base(p.b_rows * 128, 1024, umma::LAYOUT_SW128);
+    const int nk = p.KC / 16;                       // k-steps per stage (16 pixel rows = 2048 bytes = 128 descriptor units each)
     long long w_acc = 0, w_full = 0;
     const long long t_start = clock64();
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
       int ks, g, cb, ct; decode(u, ks, g, cb, ct);
       const int c0 = ks * p.chunks_per_split, c1 = min(p.n_kchunks, c0 + p.chunks_per_split);
       const int N = p.ci_n[cb];
-      const uint32_t idesc = umma::make_idesc_tf32(p.m64 ? 64 : 128, N, 1, 1);
+      const uint32_t idesc = umma::make_idesc_f16(p.m64 ? 64 : 128, N, 1, 1);
       SSDN_TIMED(w_acc, umma::mbar_wait(acc_empty, (it & 1) ^ 1, abort_addr, p.error_flag, 12));
       umma::tc_fence_after();
       uint32_t acc = 0;
-      // one elected block of (taps x 4 k-steps x 3 products) MMAs per stage; descriptors advance by uniform adds in
+      // one elected block of (taps x KC/16 k-steps x 3 products) MMAs per stage; descriptors advance by uniform adds in
       // 16-byte units (low words), so the tensor core's queue does not drain between instructions
       const uint32_t desc_hi = (uint32_t)(adesc >> 32);
       const uint32_t a_lbo = (uint32_t)(adesc & 0xffff0000u), b_lbo = (uint32_t)(bdesc & 0xffff0000u);
@@ -149,11 +150,13 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
               if (t < ntaps) {
                 const uint32_t d = tmem + t * N;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {          // KC == 32: four k-steps of 8 pixels (1024 bytes = 64 units)
-                  const uint32_t ah = a0 + k * 64, al = ah + a_pl, bh = b0 + t * 8 + k * 64, bl = bh + b_pl;
-                  umma::mma_tf32_lo(d, al, bh, desc_hi, idesc, k == 0 ? acc : 1u);
-                  umma::mma_tf32_lo(d, ah, bl, desc_hi, idesc, 1);
-                  umma::mma_tf32_lo(d, ah, bh, desc_hi, idesc, 1);
+                for (int k = 0; k < 4; ++k) {          // k-steps of 16 pixels (2048 bytes = 128 units); a tap shifts X by one row (8 units)
+                  if (k < nk) {
+                    const uint32_t ah = a0 + k * 128, al = ah + a_pl, bh = b0 + t * 8 + k * 128, bl = bh + b_pl;
+                    umma::mma_f16_lo(d, al, bh, desc_hi, idesc, k == 0 ? acc : 1u);
+                    umma::mma_f16_lo(d, ah, bl, desc_hi, idesc, 1);
+                    umma::mma_f16_lo(d, ah, bh, desc_hi, idesc, 1);
+                  }
                 }
               }
             }
@@ -168,10 +171,12 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
             if (umma::elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t o = k * 8 * 128;
-                umma::mma_tf32_ss(d, umma::desc_at(adesc, al + o), umma::desc_at(bdesc, bv + o), idesc, k == 0 ? acc : 1u);
-                umma::mma_tf32_ss(d, umma::desc_at(adesc, av + o), umma::desc_at(bdesc, bl + o), idesc, 1);
-                umma::mma_tf32_ss(d, umma::desc_at(adesc, av + o), umma::desc_at(bdesc, bv + o), idesc, 1);
+                if (k < nk) {
+                  const uint32_t o = k * 16 * 128;
+                  umma::mma_f16_ss(d, umma::desc_at(adesc, al + o), umma::desc_at(bdesc, bv + o), idesc, k == 0 ? acc : 1u);
+                  umma::mma_f16_ss(d, umma::desc_at(adesc, av + o), umma::desc_at(bdesc, bl + o), idesc, 1);
+                  umma::mma_f16_ss(d, umma::desc_at(adesc, av + o), umma::desc_at(bdesc, bv + o), idesc, 1);
+                }
               }
             }
             __syncwarp();
@@ -197,9 +202,10 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
       SSDN_TIMED(w_accf, umma::mbar_wait(acc_full, it & 1, abort_addr, p.error_flag, 13));
       umma::tc_fence_after();
       const int co = p.m64 ? (lane < 16 ? ew * 16 + lane : p.cout) : ct * 128 + ew * 32 + lane;
-      // every accumulator of this unit took (K chunks of the split) x 4 k-steps x 3 products accumulate steps
+      // every accumulator of this unit took (K chunks of the split) x KC/16 k-steps x 3 products accumulate steps
       const int kc0 = ks * p.chunks_per_split, kc1 = min(p.n_kchunks, kc0 + p.chunks_per_split);
-      const float comp = 1.0f + p.acc_beta * (float)((kc1 - kc0) * 12);
+      const float comp = (1.0f + p.acc_beta * (float)((kc1 - kc0) * (p.KC / 16) * 3)) *
+                         exp2_int(-((p.k_dz ? __ldg(p.k_dz) : 0) + (p.k_x ? __ldg(p.k_x) : 0)));
       for (int t = 0; t < p.groups[g].ntaps; ++t) {
         const int tap = p.groups[g].tap_id[t];
         float* dst = p.partial + (((long long)ks * p.ntaps_total + tap) * p.cout + co) * p.cin_pitch + p.ci_start[cb];
@@ -270,124 +276,6 @@ static inline void wgrad_reduce_launch(const float* partial, int ksplit, int nta
   wgrad_reduce_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 16), 0, st>>>(partial, ksplit, ntaps, cout, cin, pitch, dw, accumulate);
 }
 
-// Weight gradient of the FIRST convolution (1..4 input channels, e.g. RGB): a [cout] x [cin x taps] problem is far too thin
-// for a 128 x N tensor-core tile (3 useful columns of 16), so it runs on the CUDA cores.  Thread (pixel half, stencil row r,
-// co) keeps dW[3r .. 3r+2][co][0..3] in 12 registers.  The dZ planes of 128 flat pixels are one contiguous 24 KB block
-// each: they arrive by 1-D bulk TMA (cp.async.bulk) into a double buffer, one tile ahead; the X window (3 of 100 channels
-// per pixel) is prefetched into registers during the previous tile.  The three taps of a row read consecutive pixels of X,
-// so the pixel loop slides a 3-pixel register window: two 4-byte and one 16-byte shared loads feed 12 FMAs per pixel.
-// Partials [CTA][tap][co][ci] go through the same fixed-order reduction as the tensor-core path.
-struct SmallCinTaps { int rel[9]; int lo; int span; };
-constexpr int kSmallCinTile = 128;
-__global__ void __launch_bounds__(384) wgrad_small_cin_kernel(const float* __restrict__ dz_v, const float* __restrict__ dz_lo, int cout,
-                                                              const float* __restrict__ x_v, const float* __restrict__ x_lo,
-                                                              int x_cpitch, int x_coff, int cin, long long total, SmallCinTaps taps,
-                                                              float* __restrict__ partial) {
-  extern __shared__ __align__(128) float sm_small[];
-  __shared__ __align__(8) uint64_t bars[2];
-  const int tile_floats = kSmallCinTile * cout;
-  const int rows = kSmallCinTile + taps.span;
-  float* dz_s = sm_small;                                                          // [buf][plane][128][cout]
-  float4* x_s = reinterpret_cast<float4*>(sm_small + 4 * tile_floats);             // [buf][rows]
-  const int tid = threadIdx.x, nthr = blockDim.x;                                  // blockDim.x == 2 * 3 * cout
-  const int half = tid / (3 * cout), t3 = tid - half * 3 * cout;
-  const int r = t3 / cout, co = t3 - r * cout;
-  const int rel = taps.rel[3 * r];                                                 // taps 3r, 3r+1, 3r+2 read pixels rel, rel+1, rel+2
-  const uint32_t bar0 = umma::smem_u32(&bars[0]);
-  if (tid == 0) { umma::mbar_init(bar0, 1); umma::mbar_init(bar0 + 8, 1); umma::fence_mbar_init(); }
-  __syncthreads();
-  const long long ntiles = (total + kSmallCinTile - 1) / kSmallCinTile;
-  auto issue_dz = [&](long long tile, int buf) {      // one thread: both planes of a tile by bulk copy
-    const long long base = tile * kSmallCinTile;
-    const uint32_t bytes = (uint32_t)((total - base < kSmallCinTile ? total - base : kSmallCinTile) * cout * 4);
-    const uint32_t dst = umma::smem_u32(dz_s + (size_t)buf * 2 * tile_floats), bar = bar0 + 8 * buf;
-    umma::mbar_expect_tx(bar, 2 * bytes);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(dz_v + base * cout), "r"(bytes), "r"(bar) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + tile_floats * 4),
-                 "l"(dz_lo + base * cout), "r"(bytes), "r"(bar) : "memory");
-  };
-  auto load_x = [&](long long tile, int q, float (&v)[4]) {   // X window row q of a tile (hi + lo), zero outside the tensor
-    const long long g = tile * kSmallCinTile + taps.lo + q;
-    v[0] = v[1] = v[2] = v[3] = 0.f;
-    if (q < rows && g >= 0 && g < total)
-      for (int c = 0; c < cin; ++c) v[c] = __ldg(x_v + g * x_cpitch + x_coff + c) + __ldg(x_lo + g * x_cpitch + x_coff + c);
-  };
-  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
-  long long tile = blockIdx.x;
-  if (tile < ntiles) {
-    if (tid == 0) issue_dz(tile, 0);
-    for (int q = tid; q < rows; q += nthr) { float v[4]; load_x(tile, q, v); x_s[q] = make_float4(v[0], v[1], v[2], v[3]); }
-  }
-  __syncthreads();
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const long long next = tile + gridDim.x;
-    float xn[2][4];                                    // next tile's X rows tid and tid + nthr (rows <= 2 * nthr)
-    if (next < ntiles) {
-      if (tid == 0) issue_dz(next, buf ^ 1);
-      load_x(next, tid, xn[0]); load_x(next, tid + nthr, xn[1]);
-    }
-    umma::mbar_wait(bar0 + 8 * buf, (it >> 1) & 1);
-    const float* dh = dz_s + (size_t)buf * 2 * tile_floats + co, * dl = dh + tile_floats;
-    const float4* xs = x_s + (size_t)buf * rows + rel;
-    const long long left = total - tile * kSmallCinTile;
-    const int p0 = half * (kSmallCinTile / 2), p1 = (int)(left < p0 + kSmallCinTile / 2 ? (left > p0 ? left : p0) : p0 + kSmallCinTile / 2);
-    float4 x0 = xs[p0], x1 = xs[p0 + 1];
-#pragma unroll 4
-    for (int px = p0; px < p1; ++px) {
-      const float4 x2 = xs[px + 2];
-      const float d = dh[px * cout] + dl[px * cout];
-      a0.x = fmaf(d, x0.x, a0.x); a0.y = fmaf(d, x0.y, a0.y); a0.z = fmaf(d, x0.z, a0.z); a0.w = fmaf(d, x0.w, a0.w);
-      a1.x = fmaf(d, x1.x, a1.x); a1.y = fmaf(d, x1.y, a1.y); a1.z = fmaf(d, x1.z, a1.z); a1.w = fmaf(d, x1.w, a1.w);
-      a2.x = fmaf(d, x2.x, a2.x); a2.y = fmaf(d, x2.y, a2.y); a2.z = fmaf(d, x2.z, a2.z); a2.w = fmaf(d, x2.w, a2.w);
-      x0 = x1; x1 = x2;
-    }
-    if (next < ntiles) {
-      float4* xd = x_s + (size_t)(buf ^ 1) * rows;
-      if (tid < rows) xd[tid] = make_float4(xn[0][0], xn[0][1], xn[0][2], xn[0][3]);
-      if (tid + nthr < rows) xd[tid + nthr] = make_float4(xn[1][0], xn[1][1], xn[1][2], xn[1][3]);
-    }
-    __syncthreads();                                   // everyone is done with buf: the next iteration may refill it
-  }
-  // combine the two pixel halves (fixed order), then write the CTA's partial
-  float4* red = reinterpret_cast<float4*>(sm_small);
-  if (half == 1) { red[3 * t3] = a0; red[3 * t3 + 1] = a1; red[3 * t3 + 2] = a2; }
-  __syncthreads();
-  if (half == 0) {
-    const float4 b0 = red[3 * t3], b1 = red[3 * t3 + 1], b2 = red[3 * t3 + 2];
-    const float v[3][4] = {{a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w}, {a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w},
-                           {a2.x + b2.x, a2.y + b2.y, a2.z + b2.z, a2.w + b2.w}};
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      float* dst = partial + ((long long)blockIdx.x * 9 + 3 * r + j) * cout * cin + (long long)co * cin;
-      for (int c = 0; c < cin; ++c) dst[c] = v[j][c];
-    }
-  }
-}
-constexpr int kSmallCinGrid = 296;      // 2 CTAs of 2 x 3 x cout threads per SM (2 x 54 KB of shared memory each at cout = 48)
-static inline bool wgrad_small_cin_ok(int cin, int cout, int ntaps) { return cin <= 4 && ntaps == 9 && cout * 6 <= 384 && cout % 4 == 0; }
-static inline size_t wgrad_small_cin_partial_floats(int cin, int cout) { return (size_t)kSmallCinGrid * 9 * cout * cin; }
-// taps: forward flat-pixel offsets of X relative to dZ (9 of them).  dZ must be dense (channel pitch == cout).
-static inline cudaError_t wgrad_small_cin_launch(const float* dz_v, const float* dz_lo, int dz_cpitch, int cout, const float* x_v, const float* x_lo,
-                                                 int x_cpitch, int x_coff, int cin, long long total, const int* tap_off, float* partial, float* dw,
-                                                 cudaStream_t st) {
-  SmallCinTaps t; t.lo = tap_off[0]; int hi = tap_off[0];
-  for (int i = 1; i < 9; ++i) { t.lo = tap_off[i] < t.lo ? tap_off[i] : t.lo; hi = tap_off[i] > hi ? tap_off[i] : hi; }
-  t.span = hi - t.lo;
-  for (int i = 0; i < 9; ++i) t.rel[i] = tap_off[i] - t.lo;
-  for (int r = 0; r < 3; ++r)       // the sliding window needs the taps of a stencil row on consecutive pixels
-    if (t.rel[3 * r + 1] != t.rel[3 * r] + 1 || t.rel[3 * r + 2] != t.rel[3 * r] + 2) return cudaErrorInvalidValue;
-  const int nthr = 6 * cout, rows = kSmallCinTile + t.span;
-  if (dz_cpitch != cout || rows > 2 * nthr) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)4 * kSmallCinTile * cout * 4 + (size_t)2 * rows * 16;
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(wgrad_small_cin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-  wgrad_small_cin_kernel<<<kSmallCinGrid, nthr, smem, st>>>(dz_v, dz_lo, cout, x_v, x_lo, x_cpitch, x_coff, cin, total, t, partial);
-  wgrad_reduce_launch(partial, kSmallCinGrid, 9, cout, cin, cin, dw, 0, st);
-  return cudaGetLastError();
-}
-
 }  // namespace wgradk
 
 // ------------------------------------------------------------------------------------------ host
@@ -399,9 +287,11 @@ static inline int wgrad_n_ci_blocks(int cin, int ntaps) { const int c16 = (cin +
 static inline size_t wgrad_partial_floats(int ksplit, int ntaps, int cout, int cin) {
   return (size_t)ksplit * ntaps * cout * ((cin + 3) / 4 * 4);
 }
+static inline int wgrad_kc() { static const int kc = getenv("SSDN_WGRAD_KC") ? atoi(getenv("SSDN_WGRAD_KC")) : 32; return kc == 64 ? 64 : 32; }
 
 // Decides the K split for a layer (so that the grid fills the chip) without needing pointers.
-static inline int wgrad_pick_ksplit(long long k_total, int cout, int cin, int ntaps, int num_sms, int KC = 32) {
+static inline int wgrad_pick_ksplit(long long k_total, int cout, int cin, int ntaps, int num_sms) {
+  const int KC = wgrad_kc();
   const int n_kchunks = (int)((k_total + KC - 1) / KC);
   const int n_co_tiles = (cout + 127) / 128, n_ci_blocks = wgrad_n_ci_blocks(cin, ntaps), n_groups = ntaps == 9 ? 3 : ntaps;
   const int others = n_co_tiles * n_ci_blocks * n_groups;
@@ -414,29 +304,33 @@ static inline int wgrad_pick_ksplit(long long k_total, int cout, int cin, int nt
 }
 
 // taps: flat offsets of X relative to dZ for each weight tap (the FORWARD offsets of the conv).
-static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const float* dz_v, const float* dz_lo, int dz_cpitch,
-                                  int dz_coff, int cout, const float* x_v, const float* x_lo, int x_cpitch, int x_coff,
-                                  int cin, const ConvTaps& taps, int ksplit, float* partial, int* error_flag, int num_sms) {
+// dz / x: fp16 plane pairs; k_dz / k_x: device pointers to their scale exponents (null = unscaled).
+static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const __half* dz_hi, const __half* dz_lo, int dz_cpitch,
+                                  int dz_coff, int cout, const __half* x_hi, const __half* x_lo, int x_cpitch, int x_coff,
+                                  int cin, const ConvTaps& taps, int ksplit, float* partial, int* error_flag, int num_sms,
+                                  const int* k_dz, const int* k_x) {
   WgradParams& p = plan->p;
   p = WgradParams{};
-  p.k_total = k_total; p.KC = 32; p.n_kchunks = (int)((k_total + p.KC - 1) / p.KC);
+  p.k_total = k_total; p.KC = wgrad_kc(); p.n_kchunks = (int)((k_total + p.KC - 1) / p.KC);
   p.ksplit = ksplit; p.chunks_per_split = (p.n_kchunks + ksplit - 1) / ksplit;
   p.cout = cout; p.cin = cin; p.cin_pitch = (cin + 3) / 4 * 4; p.n_co_tiles = (cout + 127) / 128;
+  p.k_dz = k_dz; p.k_x = k_x;
   p.acc_beta = (getenv("SSDN_ACC_COMP") && atoi(getenv("SSDN_ACC_COMP")) == 0) ? 0.0f : SSDN_ACC_BETA;
   p.m64 = (cout <= 64 && !(getenv("SSDN_WGRAD_M64") && atoi(getenv("SSDN_WGRAD_M64")) == 0)) ? 1 : 0;
+  if (dz_cpitch % 8 || dz_coff % 8 || x_cpitch % 8 || x_coff % 8) return -16;     // TMA: 16-byte strides and bases
   // ci blocks: as wide as TMEM allows (3 taps x N <= 512 columns, N <= 256), so that dZ is streamed as few times as possible
   const int cap = wgrad_ci_cap(taps.n);
   p.n_ci_blocks = 0;
   const int cin16 = (cin + 15) / 16 * 16;
   const int nblocks = (cin16 + cap - 1) / cap;
-  const int per = ((cin16 + nblocks - 1) / nblocks + 31) / 32 * 32;      // block starts must be multiples of 32 channels
+  const int per = ((cin16 + nblocks - 1) / nblocks + 63) / 64 * 64;      // block starts must be multiples of 64 channels
   for (int c = 0; c < cin; c += per) {
     const int rem = std::min(per, cin - c);
     p.ci_start[p.n_ci_blocks] = c; p.ci_n[p.n_ci_blocks] = (rem + 15) / 16 * 16;
     ++p.n_ci_blocks;
   }
-  p.nbx = (p.ci_n[0] + 31) / 32;
-  p.nba = std::min(4, (cout + 31) / 32);
+  p.nbx = (p.ci_n[0] + 63) / 64;
+  p.nba = std::min(2, (cout + 63) / 64);
   p.ntaps_total = taps.n;
   int span = 0;
   if (taps.n == 9) {
@@ -451,27 +345,28 @@ static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const floa
     for (int g = 0; g < taps.n; ++g) { p.groups[g].row_off = taps.off[g]; p.groups[g].ntaps = 1; p.groups[g].tap_id[0] = g; p.groups[g].tap_rel[0] = 0; }
   }
   p.b_rows = (p.KC + span + 7) / 8 * 8;
-  p.a_plane_bytes = p.nba * p.KC * 128;                    // the MMA addresses 4 co blocks; blocks >= nba alias whatever follows (ignored lanes)
+  p.a_plane_bytes = p.nba * p.KC * 128;                    // an M = 128 MMA addresses 2 co blocks; a missing one aliases whatever follows (ignored lanes)
   p.b_plane_bytes = (uint32_t)(p.nbx * p.b_rows * 128);    // b_rows is a multiple of 8 => 1024-byte multiple
   const uint32_t stage_bytes = 2 * (p.a_plane_bytes + p.b_plane_bytes);
-  p.stages = std::max(2, std::min(4, (int)((200 * 1024) / stage_bytes)));
-  plan->smem = (size_t)p.stages * stage_bytes + 4 * p.KC * 128 + 1024;   // slack so that aliased co blocks stay inside the allocation
+  p.stages = std::max(2, std::min(wgradk::kMaxStages, (int)((200 * 1024) / stage_bytes)));
+  plan->smem = (size_t)p.stages * stage_bytes + 2 * p.KC * 128 + 1024;   // slack so that aliased co blocks stay inside the allocation
   p.partial = partial; p.error_flag = error_flag;
   plan->grid = std::min(p.n_co_tiles * p.n_ci_blocks * p.n_groups * p.ksplit, num_sms);
-  // 4-D maps: (32 channels of a block, flat pixel, channel block [stride 128 B], plane).  The block dimension has a
+  // 4-D maps: (64 channels of a block, flat pixel, channel block [stride 128 B], plane).  The block dimension has a
   // smaller stride than the pixel dimension; cuTensorMapEncodeTiled accepts that (profiles/r01_tma_map_test.log) and the
-  // box then lands in shared memory as [plane][block][pixel][32 ch], exactly the MN-major operand layout.
-  const long long dz_plane = (long long)((const char*)dz_lo - (const char*)dz_v), x_plane = (long long)((const char*)x_lo - (const char*)x_v);
+  // box then lands in shared memory as [plane][block][pixel][64 ch], exactly the MN-major operand layout.  A block that
+  // runs past the tensor's channels reads the next pixel's first channels: those rows / columns of the MMA are never used.
+  const long long dz_plane = (long long)((const char*)dz_lo - (const char*)dz_hi), x_plane = (long long)((const char*)x_lo - (const char*)x_hi);
   if (dz_plane <= 0 || x_plane <= 0 || dz_plane % 16 || x_plane % 16) return -11;
-  uint64_t d1[4] = {32, (uint64_t)k_total, (uint64_t)((cout + 31) / 32), 2};
-  uint64_t s1[3] = {(uint64_t)dz_cpitch * 4, 128, (uint64_t)dz_plane};
-  uint32_t b1[4] = {32, (uint32_t)p.KC, (uint32_t)p.nba, 2};
-  uint64_t d2[4] = {32, (uint64_t)k_total, (uint64_t)((cin + 31) / 32), 2};
-  uint64_t s2[3] = {(uint64_t)x_cpitch * 4, 128, (uint64_t)x_plane};
-  uint32_t b2[4] = {32, (uint32_t)p.b_rows, (uint32_t)p.nbx, 2};
+  uint64_t d1[4] = {64, (uint64_t)k_total, (uint64_t)((cout + 63) / 64), 2};
+  uint64_t s1[3] = {(uint64_t)dz_cpitch * 2, 128, (uint64_t)dz_plane};
+  uint32_t b1[4] = {64, (uint32_t)p.KC, (uint32_t)p.nba, 2};
+  uint64_t d2[4] = {64, (uint64_t)k_total, (uint64_t)((cin + 63) / 64), 2};
+  uint64_t s2[3] = {(uint64_t)x_cpitch * 2, 128, (uint64_t)x_plane};
+  uint32_t b2[4] = {64, (uint32_t)p.b_rows, (uint32_t)p.nbx, 2};
   int r;
-  if ((r = umma::encode_f32(&plan->dz, (void*)(dz_v + dz_coff), 4, d1, s1, b1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
-  if ((r = umma::encode_f32(&plan->x, (void*)(x_v + x_coff), 4, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
+  if ((r = umma::encode_f16(&plan->dz, (void*)(dz_hi + dz_coff), 4, d1, s1, b1, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+  if ((r = umma::encode_f16(&plan->x, (void*)(x_hi + x_coff), 4, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
   return 0;
 }
 

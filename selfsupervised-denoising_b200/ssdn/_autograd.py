@@ -26,7 +26,7 @@ class NetFunction(torch.autograd.Function):
             raise RuntimeError("NoiseNetwork: backward() called after another forward() reused the same plan; the "
                                "engine keeps one set of activations per (batch, size) plan")
         target = owner.grad_buffer()
-        grads = plan.backward(owner.flat_parameters(), dout.contiguous().float(), target)
+        grads = plan.backward(owner.flat_parameters(), dout.contiguous().float(), target, owner.stale_slot())
         outs, off = [], 0
         for shp in ctx.shapes:
             n = 1

@@ -30,7 +30,9 @@ _SIGNATURES = {
     "ssdn_net_param_count": (_Z, [_P]),
     "ssdn_net_bind": (_I, [_P, _P, _Z, _P]),
     "ssdn_net_forward": (_I, [_P, _P, _P, _P, _I, _P]),
-    "ssdn_net_backward": (_I, [_P, _P, _P, _P, _P]),
+    "ssdn_net_backward": (_I, [_P, _P, _P, _P, _P, _P]),
+    "ssdn_net_scale_status": (_I, [_P, ctypes.POINTER(c_int), _P]),
+    "ssdn_net_debug_scales": (_I, [_P, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_uint), _P]),
     "ssdn_net_check": (_I, [_P, _P]),
     "ssdn_net_kernel_launches": (_I, [_P, _I]),
     "ssdn_profile_begin": (_I, []),
@@ -49,7 +51,8 @@ _SIGNATURES = {
     "ssdn_mse_backward": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "ssdn_masked_mse_forward": (_I, [_P, _P, _P, _P] + [_I] * 5 + [_P, _P]),
     "ssdn_masked_mse_backward": (_I, [_P, _P, _P, _I, _P] + [_I] * 4 + [_P, _P]),
-    "ssdn_adam_step": (_I, [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _LL, _D, _P]),
+    "ssdn_adam_step": (_I, [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _LL, _D, _P, _I, _P]),
+    "ssdn_tensor_peak": (_I, [_I, _D, ctypes.POINTER(c_double), _P]),
     "ssdn_n2v_mask": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, ctypes.c_ulonglong, ctypes.c_ulonglong, _P]),
     "ssdn_noisy_crops": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, ctypes.c_ulonglong, ctypes.c_ulonglong, _I, ctypes.c_float, ctypes.c_float, _I,
                               _P, _P, _P, _P]),
@@ -182,6 +185,8 @@ class NetPlan:
             self.ws = _workspace(lib().ssdn_net_workspace_bytes(handle), self.device)
             check(lib().ssdn_net_bind(handle, _ptr(self.ws), self.ws.numel(), _stream()))
         self.out_shape = (n, cout, h, w)
+        self.fwd_settled = False
+        self.bwd_settled = False
 
     def __del__(self):
         try:
@@ -191,17 +196,51 @@ class NetPlan:
         except Exception:
             pass
 
-    def forward(self, flat_params, x, training=True):
+    # Operand scales (include/ssdn_b200.h, csrc/common.cuh): the engine reads activations and gradients as fp16 plane pairs
+    # scaled by per-tensor powers of two taken from the previous pass.  A pass whose maxima left the accurate band is stale
+    # and is simply run again with the scales it left behind.  The first passes of a plan are checked (one stream
+    # synchronisation each) until one is clean; inference passes are always checked, their result is read back anyway.
+    # Unchecked training passes are covered by the stale flag that backward() leaves for the optimiser step.
+    MAX_SCALE_PASSES = 8
+
+    def scale_status(self):
+        """(forward stale, backward stale, stale passes since bind); synchronises the current stream."""
+        buf = (c_int * 3)()
+        check(lib().ssdn_net_scale_status(self.handle, buf, _stream()))
+        return int(buf[0]), int(buf[1]), int(buf[2])
+
+    def debug_scales(self):
+        k, a = (c_int * 96)(), (ctypes.c_uint * 96)()
+        check(lib().ssdn_net_debug_scales(self.handle, k, a, _stream()))
+        return list(k), list(a)
+
+    def forward(self, flat_params, x, training=True, verify=None):
         assert flat_params.numel() == self.n_params and flat_params.dtype == torch.float32
         out = torch.empty(self.out_shape, device=self.device, dtype=torch.float32)
-        check(lib().ssdn_net_forward(self.handle, _ptr(flat_params), _ptr(x), _ptr(out), int(training), _stream()))
-        return out
+        if verify is None:
+            verify = (not training) or not self.fwd_settled
+        for _ in range(self.MAX_SCALE_PASSES):
+            check(lib().ssdn_net_forward(self.handle, _ptr(flat_params), _ptr(x), _ptr(out), int(training), _stream()))
+            if not verify:
+                return out
+            if not self.scale_status()[0]:
+                self.fwd_settled = True
+                return out
+        raise EngineError("operand scales of the forward pass did not settle (non-finite activations?)")
 
-    def backward(self, flat_params, dout, grads=None):
+    def backward(self, flat_params, dout, grads=None, stale_out=None, verify=None):
         if grads is None:
             grads = torch.empty(self.n_params, device=self.device, dtype=torch.float32)
-        check(lib().ssdn_net_backward(self.handle, _ptr(flat_params), _ptr(dout), _ptr(grads), _stream()))
-        return grads
+        if verify is None:
+            verify = not self.bwd_settled
+        for _ in range(self.MAX_SCALE_PASSES):
+            check(lib().ssdn_net_backward(self.handle, _ptr(flat_params), _ptr(dout), _ptr(grads), _ptr(stale_out), _stream()))
+            if not verify:
+                return grads
+            if not self.scale_status()[1]:
+                self.bwd_settled = True
+                return grads
+        raise EngineError("operand scales of the backward pass did not settle (non-finite gradients?)")
 
     def check(self):
         check(lib().ssdn_net_check(self.handle, _stream()))
@@ -301,10 +340,18 @@ def masked_mse_backward(out, ref, coords, gloss):
     return dout
 
 
-def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.99, eps=1e-8, grad_scale=1.0):
-    """In-place torch.optim.Adam update of the flat fp32 buffer p (train.py:100-107 hyper-parameters)."""
+def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.99, eps=1e-8, grad_scale=1.0, skip=None):
+    """In-place torch.optim.Adam update of the flat fp32 buffer p (train.py:100-107 hyper-parameters).
+    skip: optional CUDA float tensor (<= 8 values); the update is a no-op when any of them is non-zero (stale-gradient flags)."""
     check(lib().ssdn_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), beta1, beta2, eps, int(step),
-                               float(grad_scale), _stream()))
+                               float(grad_scale), _ptr(skip), 0 if skip is None else skip.numel(), _stream()))
+
+
+def tensor_peak(f16=True, seconds=1.0):
+    """Measured full-chip tcgen05.mma rate of the current device: {tflops, flop_per_clk_sm, sm_mhz, seconds}."""
+    buf = (c_double * 4)()
+    check(lib().ssdn_tensor_peak(int(f16), float(seconds), buf, _stream()))
+    return {"tflops": buf[0], "flop_per_clk_sm": buf[1], "sm_mhz": buf[2], "seconds": buf[3]}
 
 
 def profile_begin():

@@ -95,14 +95,29 @@ class Denoiser(nn.Module):
                 off += p.numel()
         if not ok:
             flat = flatten_parameters(params)
-            self._flat, self._flat_grad = flat, torch.zeros_like(flat)
+            # gradient buffer = the parameters' layout + N_FLAGS trailing floats: every network's backward pass leaves its
+            # stale-scale flag there, so the flags ride along in the one gradient all-reduce and gate the Adam kernel
+            self._flat_grad_all = torch.zeros(flat.numel() + self.N_FLAGS, dtype=torch.float32, device=flat.device)
+            self._flat, self._flat_grad = flat, self._flat_grad_all[:flat.numel()]
             off = 0
-            for net in self._models.values():
+            for i, net in enumerate(self._models.values()):
                 n = sum(p.numel() for p in net.parameters())
                 net.adopt_flat(flat[off:off + n])
-                net.set_grad_buffer(self._flat_grad[off:off + n])
+                net.set_grad_buffer(self._flat_grad[off:off + n], self._flat_grad_all[flat.numel() + i:flat.numel() + i + 1])
                 off += n
         return self._flat
+
+    N_FLAGS = 8
+
+    def flat_gradients_with_flags(self) -> Tensor:
+        """flat_gradients() followed by the stale-scale flags: the buffer the data-parallel all-reduce sums."""
+        self.flat_gradients()
+        return self._flat_grad_all
+
+    def stale_flags(self) -> Tensor:
+        """The N_FLAGS trailing floats of the gradient buffer (non-zero: this step's gradients must not be applied)."""
+        self.flat_parameters()
+        return self._flat_grad_all[self._flat.numel():]
 
     def flat_gradients(self) -> Tensor:
         """Flat gradient buffer matching flat_parameters().  The engine writes each network's gradients straight into

@@ -84,6 +84,7 @@ class NoiseNetwork(nn.Module):
         self._plans: "OrderedDict[tuple, E.NetPlan]" = OrderedDict()
         self._flat = None
         self._grad_buffer = None
+        self._stale_slot = None
 
     @property
     def blindspot(self) -> bool:
@@ -132,9 +133,14 @@ class NoiseNetwork(nn.Module):
     def grad_buffer(self):
         return self._grad_buffer
 
-    def set_grad_buffer(self, buf):
-        """Optional flat buffer the engine writes parameter gradients into (p.grad become views of it)."""
+    def set_grad_buffer(self, buf, stale_slot=None):
+        """Optional flat buffer the engine writes parameter gradients into (p.grad become views of it) and an optional
+        one-float CUDA tensor that receives the step's stale-scale flag (see _engine.NetPlan)."""
         self._grad_buffer = buf
+        self._stale_slot = stale_slot
+
+    def stale_slot(self):
+        return self._stale_slot
 
     def _plan(self, x: Tensor) -> E.NetPlan:
         n, c, h, w = x.shape

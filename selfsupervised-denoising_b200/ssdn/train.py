@@ -54,7 +54,7 @@ class FlatAdam:
         self.step_count += 1
         g = self.param_groups[0]
         E.adam_step(flat, grads, self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count, g["betas"][0], g["betas"][1], g["eps"],
-                    grad_scale)
+                    grad_scale, skip=self.denoiser.stale_flags())
 
     def state_dict(self) -> Dict:
         """Wire format of ``torch.optim.Adam.state_dict()`` - what the reference stores under ``"optimizer"`` in a
@@ -124,7 +124,7 @@ def train_step(denoiser: Denoiser, optimizer: FlatAdam, data: List, world_size: 
     outputs = denoiser.run_pipeline(data)
     torch.mean(outputs[PipelineOutput.LOSS]).backward()
     if world_size > 1:
-        dist.all_reduce(denoiser.flat_gradients(), op=dist.ReduceOp.SUM)
+        dist.all_reduce(denoiser.flat_gradients_with_flags(), op=dist.ReduceOp.SUM)
     optimizer.step(grad_scale=1.0 / world_size)
     return outputs
 
