@@ -1,18 +1,24 @@
 #!/usr/bin/env python
 """Headline benchmark: 64x64 patches/sec of one SSDN training step (BASELINE.json configs[1]).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--config known|var]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--config known|var|n2v|var128]
+                  [--scaling weak|strong] [--no-extras] [--no-cpu-baseline]
 
 A step = rotate/stack -> blind-spot U-Net forward -> Gaussian posterior + NLL loss -> backward -> (one gradient
-all-reduce when N > 1) -> Adam, on a batch of 32 synthetic gauss25-noised 64x64 RGB patches PER GPU (weak scaling),
-exactly the sequence of ssdn/ssdn/train.py:197-202 of the reference.
+all-reduce when N > 1) -> Adam, exactly the sequence of ssdn/ssdn/train.py:197-202 of the reference.  The headline
+(`--config known`) is a batch of 32 synthetic gauss25-noised 64x64 RGB patches PER GPU (weak scaling); `--scaling strong`
+splits ONE global batch of 32 over the ranks instead (the reference's nn.DataParallel semantics, denoiser.py:102-110).
+The other BASELINE.json configurations: var (sigma estimated per image by a second U-Net), n2v (Noise2Void: plain U-Net,
+masked loss), var128 (gauss5_50, per-channel sigma, 128x128 patches, batch 16).
 
 engine arm (default)  : `value` times K steps with the batch already resident in HBM (CUDA events, barrier + sync on
                         both sides, max over ranks); `e2e` times K steps through the public API (Denoiser.run_pipeline +
                         FlatAdam) with the batch in pinned HOST memory, host->device copy and the (asynchronous, pinned)
                         device->host read of the per-sample losses of every step inside the timed region.  One extra
-                        profiled step brackets every tensor-core launch with CUDA events for the roofline block; rank 0
-                        also times the CPU oracle.
+                        profiled step brackets EVERY kernel launch with CUDA events (roofline block: tensor kernels against
+                        the tcgen05 peak measured live by ssdn_tensor_peak, HBM-bound kernels against MEASURED_PEAKS.json).
+                        Unless --no-extras: short runs of the other configurations and of strong scaling ride along as
+                        `configs` / `strong` fields of the same JSON line.  At N = 1 rank 0 also times the CPU oracle.
 reference arm         : `--impl reference` times the reference's own algorithm on the host cores (the oracle port of
                         the reference's PyTorch CPU path, all threads) on the same metric.
 """
@@ -28,32 +34,62 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "selfsupervised-denoising_b200"))
 
-BATCH, PATCH, CHANNELS = 32, 64, 3
-TRAIN_GFLOP_PER_PATCH = {"known": 30.6678, "var": 37.652}      # BASELINE.md section 2 (algorithmic, fwd+dgrad+wgrad)
+CHANNELS = 3
+# name -> (algorithm, sigma mode, noise style, patch, global batch, train GFLOP per patch, BASELINE.json row)
+CONFIGS = {
+    "known": ("ssdn", "known", "gauss25", 64, 32, 30.6678, "ssdn gauss25 sigma_known RGB, patch 64, batch 32"),
+    "var": ("ssdn", "var", "gauss25", 64, 32, 37.652, "ssdn gauss25 sigma_var RGB, patch 64, batch 32"),
+    "n2v": ("n2v", "known", "gauss25", 64, 32, 7.000, "n2v gauss25 RGB, patch 64, batch 32 (random-mask blind-spot path)"),
+    "var128": ("ssdn", "var", "gauss5_50", 128, 16, 150.609, "ssdn gauss5_50 sigma_var RGB, patch 128, batch 16"),
+}
+BATCH, PATCH = 32, 64
+TRAIN_GFLOP_PER_PATCH = {k: v[5] for k, v in CONFIGS.items()}
 
 
-def make_cfg(sigma_mode):
+def make_cfg(config):
     import ssdn
     from ssdn.params import ConfigValue, NoiseAlgorithm, NoiseValue
+    algo, mode, style, patch, batch, _, _ = CONFIGS[config]
     cfg = ssdn.cfg.base()
-    cfg[ConfigValue.ALGORITHM] = NoiseAlgorithm.SELFSUPERVISED_DENOISING
-    cfg[ConfigValue.NOISE_STYLE] = "gauss25"
-    cfg[ConfigValue.NOISE_VALUE] = {"known": NoiseValue.KNOWN, "var": NoiseValue.UNKNOWN_VARIABLE}[sigma_mode]
+    cfg[ConfigValue.ALGORITHM] = {"ssdn": NoiseAlgorithm.SELFSUPERVISED_DENOISING, "n2v": NoiseAlgorithm.NOISE_TO_VOID}[algo]
+    cfg[ConfigValue.NOISE_STYLE] = style
+    cfg[ConfigValue.NOISE_VALUE] = {"known": NoiseValue.KNOWN, "var": NoiseValue.UNKNOWN_VARIABLE}[mode]
     cfg[ConfigValue.IMAGE_CHANNELS] = CHANNELS
-    cfg[ConfigValue.TRAIN_MINIBATCH_SIZE] = BATCH
-    cfg[ConfigValue.TRAIN_PATCH_SIZE] = PATCH
+    cfg[ConfigValue.TRAIN_MINIBATCH_SIZE] = batch
+    cfg[ConfigValue.TRAIN_PATCH_SIZE] = patch
     ssdn.cfg.infer(cfg, model_only=True)
     return cfg
 
 
-def synthetic(n, seed):
-    """Smooth random clean images + clipped Gaussian noise sigma=25/255, CPU tensors."""
+def synthetic(n, seed, patch=PATCH, style="gauss25"):
+    """Smooth random clean images + clipped Gaussian noise, CPU tensors: sigma = 25/255, or U(5, 50)/255 per sample
+    and channel for gauss5_50 (utils/noise.py:55-61).  Returns (clean, noisy, sigma)."""
     import torch
     import torch.nn.functional as F
     g = torch.Generator().manual_seed(seed)
-    clean = F.interpolate(torch.rand(n, CHANNELS, 8, 8, generator=g), size=(PATCH, PATCH), mode="bilinear", align_corners=False)
-    noisy = (clean + torch.randn(n, CHANNELS, PATCH, PATCH, generator=g) * (25.0 / 255.0)).clamp(0, 1)
-    return clean, noisy
+    clean = F.interpolate(torch.rand(n, CHANNELS, 8, 8, generator=g), size=(patch, patch), mode="bilinear", align_corners=False)
+    if style == "gauss5_50":
+        sigma = (torch.rand(n, CHANNELS, 1, 1, generator=g) * 45.0 + 5.0) / 255.0
+    else:
+        sigma = torch.full((n, 1, 1, 1), 25.0 / 255.0)
+    noisy = (clean + torch.randn(n, CHANNELS, patch, patch, generator=g) * sigma).clamp(0, 1)
+    return clean, noisy, sigma
+
+
+def make_batch(config, n, seed):
+    """[input, reference, metadata] (CPU tensors) of one step of `config` with n samples."""
+    import torch
+    from ssdn.datasets import NoisyDataset
+    M = NoisyDataset.Metadata
+    algo, mode, style, patch, _, _, _ = CONFIGS[config]
+    clean, noisy, sigma = synthetic(n, seed, patch, style)
+    md = {M.INPUT_NOISE_VALUES: sigma}
+    ref = torch.zeros(0)
+    if algo == "n2v":       # second noise realisation as the reference, 64 masked coordinates per sample (one per 8x8 box)
+        g = torch.Generator().manual_seed(seed + 7)
+        ref = (clean + torch.randn(clean.shape, generator=g) * sigma).clamp(0, 1)
+        md[M.MASK_COORDS] = torch.randint(0, patch, (n, (patch // 8) ** 2, 2), generator=g)
+    return [noisy, ref, md]
 
 
 class ClockSampler(threading.Thread):
@@ -133,21 +169,23 @@ def timed(fn, steps, device, dist_on):
     return float(t.item())
 
 
-def cpu_oracle_rate(sigma_mode, batch, steps, warmup, threads=None):
+def cpu_oracle_rate(config, batch, steps, warmup, threads=None):
     """patches/s of the reference algorithm on the host cores (oracle port, autograd + Adam as train.py:197-202)."""
     import torch
+    from ssdn.datasets import NoisyDataset
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ssdn_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
-    tr = O.CpuTrainer("ssdn", sigma_mode, CHANNELS, seed=0)
-    _, noisy = synthetic(batch, 1234)
-    sigma = torch.full((batch, 1, 1, 1), 25.0 / 255.0)
+    torch.set_num_threads(threads or os.cpu_count())       # torchrun exports OMP_NUM_THREADS=1: ask for the host's cores explicitly
+    algo, mode, style, patch, _, _, _ = CONFIGS[config]
+    tr = O.CpuTrainer(algo, mode, CHANNELS, seed=0)
+    noisy, ref, md = make_batch(config, batch, 1234)
+    M = NoisyDataset.Metadata
+    args = (noisy, md[M.INPUT_NOISE_VALUES]) if algo == "ssdn" else (noisy, None, ref, md[M.MASK_COORDS])
     for _ in range(warmup):
-        tr.step(noisy, sigma)
+        tr.step(*args)
     t0 = time.perf_counter()
     for _ in range(steps):
-        tr.step(noisy, sigma)
+        tr.step(*args)
     dt = time.perf_counter() - t0
     return batch * steps / dt, dt / steps
 
@@ -159,29 +197,113 @@ def run_reference(args):
         return
     cores = os.cpu_count()
     torch.set_num_threads(cores)
+    gbatch = CONFIGS[args.config][4]
     probe_rate, _ = cpu_oracle_rate(args.config, 4, 1, 1)
     budget = 150.0                                        # seconds for the whole (K + W) run
     per_step = max(1, int(probe_rate * budget / max(1, args.steps + args.warmup)))
-    batch = max(b for b in (1, 2, 4, 8, 16, 32) if b <= max(1, per_step))
+    batch = max(b for b in (1, 2, 4, 8, 16, 32) if b <= max(1, min(per_step, gbatch)))
     rate, step_s = cpu_oracle_rate(args.config, batch, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "64x64 patches/sec (ssdn gauss25, bs32)", "value": rate, "unit": "patches/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"ssdn gauss25 sigma_{args.config} RGB, patch 64, batch 32, train step on the host CPU"},
+            "config": {"workload": workload_name(args.config, args.scaling), "arm": "train step on the host CPU"},
             "cpu_baseline": {"value": rate, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{args.steps} steps of {batch} patches (oracle port of the reference's PyTorch CPU path)"},
             "e2e": {"value": rate, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def workload_name(config, scaling):
+    per = "per GPU" if scaling == "weak" else "global (split over the GPUs)"
+    return f"{CONFIGS[config][6]} {per}, full train step (fwd + loss + bwd + Adam)"
+
+
+class Case:
+    """One configuration on this rank: Denoiser + optimiser + a resident batch + a pinned host copy of it."""
+
+    def __init__(self, config, n_local, device, rank, world):
+        import torch
+        import ssdn
+        from ssdn.datasets import NoisyDataset
+        from ssdn.train import FlatAdam
+        self.config, self.n, self.world, self.device = config, n_local, world, device
+        torch.manual_seed(0)                               # identical initial weights on every rank
+        self.den = ssdn.Denoiser(make_cfg(config), device=device)
+        self.opt = FlatAdam(self.den)
+        self.opt.param_groups[0]["lr"] = 3e-4
+        noisy, ref, md = make_batch(config, n_local, 1234 + rank)
+        self.M = NoisyDataset.Metadata
+        self.dev_data = [noisy.to(device), ref.to(device) if ref.numel() else ref, {k: v.to(device) for k, v in md.items()}]
+        self.host = [noisy.pin_memory(), ref.pin_memory() if ref.numel() else ref, {k: v.pin_memory() for k, v in md.items()}]
+        self.host_loss = torch.empty(n_local, 1).pin_memory()
+        self.h2d = int(sum(t.numel() * t.element_size() for t in [noisy, ref] + list(md.values())))
+
+    def step_resident(self):
+        from ssdn.train import train_step
+        train_step(self.den, self.opt, self.dev_data, self.world)
+
+    def step_e2e(self):
+        from ssdn.params import PipelineOutput
+        from ssdn.train import train_step
+        out = train_step(self.den, self.opt, [self.host[0], self.host[1], dict(self.host[2])], self.world)
+        # D2H read of the step's result into pinned memory.  Asynchronous, like a trainer that logs without stalling the
+        # device: every copy is enqueued inside the timed region and completes before timed()'s final synchronize.
+        self.host_loss.copy_(out[PipelineOutput.LOSS].detach(), non_blocking=True)
+
+    def plans(self):
+        return [p for net in self.den._models.values() for p in net._plans.values()]
+
+    def check(self):
+        """Device-side error flags and the number of passes that ran with stale operand scales."""
+        stale = 0
+        for p in self.plans():
+            p.check()
+            stale += p.scale_status()[2]
+        return stale
+
+    def launches_per_step(self):
+        return sum(p.kernel_launches(True) for p in self.plans()) + 5
+
+    def param_spread(self, dist_on):
+        """max over ranks of max |p - p_rank0| after the timed steps: data-parallel replicas must stay identical."""
+        import torch
+        import torch.distributed as dist
+        if not dist_on:
+            return 0.0
+        flat = self.den.flat_parameters()
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        d = (flat - ref).abs().max().reshape(1)
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        return float(d.item())
+
+
+def short_run(config, scaling, device, rank, world, dist_on, steps=8, warmup=4):
+    """A short measurement of another configuration / scaling mode (rides along in the main JSON line)."""
+    gbatch = CONFIGS[config][4]
+    n_local = gbatch if scaling == "weak" else max(1, gbatch // world)
+    case = Case(config, n_local, device, rank, world)
+    for _ in range(warmup):
+        case.step_resident()
+    stale0 = case.check()
+    t = timed(case.step_resident, steps, device, dist_on)
+    for _ in range(2):
+        case.step_e2e()
+    te = timed(case.step_e2e, steps, device, dist_on)
+    stale = case.check() - stale0
+    total = n_local * world
+    gf = TRAIN_GFLOP_PER_PATCH[config]
+    return {"workload": workload_name(config, scaling), "per_gpu_batch": n_local, "global_batch": total, "steps": steps,
+            "value": total * steps / t, "unit": "patches/s", "ms_per_step": t / steps * 1e3,
+            "e2e": {"value": total * steps / te, "ms_per_step": te / steps * 1e3, "h2d_bytes_per_step": case.h2d, "d2h_bytes_per_step": n_local * 4},
+            "step_algorithmic_tflops_per_gpu": gf * 1e9 * n_local / (t / steps) / 1e12, "stale_scale_passes": stale,
+            "rank_param_max_diff": case.param_spread(dist_on)}
+
+
 def run_engine(args):
     import torch
     import torch.distributed as dist
-    import ssdn
     from ssdn import _engine as E
-    from ssdn.datasets import NoisyDataset
-    from ssdn.params import PipelineOutput
-    from ssdn.train import FlatAdam, train_step
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -191,101 +313,120 @@ def run_engine(args):
     device = torch.device("cuda", local)
     if dist_on:
         dist.init_process_group("nccl", device_id=device)
-    torch.manual_seed(0)                                   # identical initial weights on every rank
-    den = ssdn.Denoiser(make_cfg(args.config), device=device)
-    opt = FlatAdam(den)
-    opt.param_groups[0]["lr"] = 3e-4
-    M = NoisyDataset.Metadata
-    clean, noisy = synthetic(BATCH, 1234 + rank)
-    sigma = torch.full((BATCH, 1, 1, 1), 25.0 / 255.0)
-    dev_data = [noisy.to(device), torch.zeros(0), {M.INPUT_NOISE_VALUES: sigma.to(device)}]
-    host_noisy, host_sigma = noisy.pin_memory(), sigma.pin_memory()
-    host_loss = torch.empty(BATCH, 1).pin_memory()
-    host_loss.requires_grad_(False)
-
-    def step_resident():
-        train_step(den, opt, dev_data, world)
-
-    def step_e2e():
-        out = train_step(den, opt, [host_noisy, torch.zeros(0), {M.INPUT_NOISE_VALUES: host_sigma}], world)
-        # D2H read of the step's result into pinned memory.  Asynchronous, like a trainer that logs without stalling the
-        # device: every copy is enqueued inside the timed region and completes before timed()'s final synchronize.
-        host_loss.copy_(out[PipelineOutput.LOSS].detach(), non_blocking=True)
-
+    gbatch = CONFIGS[args.config][4]
+    n_local = gbatch if args.scaling == "weak" else max(1, gbatch // world)
+    case = Case(args.config, n_local, device, rank, world)
     for _ in range(max(3, args.warmup)):
-        step_resident()
-    main = den.get_model(ssdn.Denoiser.MODEL, parallelised=False)
-    next(iter(main._plans.values())).check()
+        case.step_resident()
+    stale0 = case.check()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    t_res = timed(step_resident, args.steps, device, dist_on)
+    t_res = timed(case.step_resident, args.steps, device, dist_on)
     clocks = sampler.summary() if sampler else None
     for _ in range(2):
-        step_e2e()
-    t_e2e = timed(step_e2e, args.steps, device, dist_on)
-    # one profiled step: CUDA events around every tensor-core launch (same stream)
+        case.step_e2e()
+    t_e2e = timed(case.step_e2e, args.steps, device, dist_on)
+    stale = case.check() - stale0
+    spread = case.param_spread(dist_on)
+    # one profiled step: CUDA events around every kernel launch (everything on one stream)
     E.profile_begin()
-    step_resident()
+    case.step_resident()
     prof = E.profile_end()
-    next(iter(main._plans.values())).check()
-    loss_val = float(host_loss.detach().mean())
-
+    case.check()
+    loss_val = float(case.host_loss.detach().mean())
+    launches = case.launches_per_step()
+    total = n_local * world
+    extras = {}
+    if not args.no_extras:
+        del case
+        torch.cuda.empty_cache()
+        if dist_on and args.scaling == "weak":
+            extras["strong"] = short_run(args.config, "strong", device, rank, world, dist_on)
+        others = [c for c in ("var", "n2v", "var128") if c != args.config]
+        extras["configs"] = {c: short_run(c, "weak", device, rank, world, dist_on) for c in others}
+    peak = None
     if rank == 0:
-        peaks = {}
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 issues at half the bf16 rate)" if peaks else \
-            "fallback 1.4 PFLOP/s sustained bf16 / 2"
-        tf32_peak = bf16 / 2.0
-        gemm_ms = sum(v[1] for v in prof.values())
-        gemm_flops = sum(v[2] for v in prof.values())
-        top = max(prof, key=lambda k: prof[k][1])
-        ach = prof[top][2] / (prof[top][1] * 1e-3) / 1e12 if prof[top][1] > 0 else 0.0
-        # DRAM traffic per launch of the dominant kernel: from the committed `ncu --set full` capture (profiles/), not live
-        traffic = None
-        try:
-            prof_json = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            traffic = prof_json.get(top, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        launches = sum(p.kernel_launches(True) for net in den._models.values() for p in net._plans.values()) + 5
-        cpu_rate, cpu_step = (0.0, 0.0) if args.no_cpu_baseline else cpu_oracle_rate(args.config, BATCH, 3, 1)
-        line = {
-            "metric": "64x64 patches/sec (ssdn gauss25, bs32)", "value": BATCH * world * args.steps / t_res, "unit": "patches/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_res / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32-grade, fp32 accumulate)",
-            "data": "synthetic",
-            "config": {"workload": f"ssdn gauss25 sigma_{args.config} RGB, patch 64, batch 32 per GPU, full train step "
-                                   "(fwd + NLL/posterior + bwd + Adam)", "global_batch": BATCH * world, "parallelism": f"dp{world}",
-                       "l2": "per-step working set ~5 GB of activations >> 126 MB L2 (no explicit flush needed)",
-                       "train_gflop_per_patch": TRAIN_GFLOP_PER_PATCH[args.config], "final_loss": loss_val},
-            "clocks": clocks,
-            "e2e": {"value": BATCH * world * args.steps / t_e2e, "unit": "patches/s", "ms_per_step": t_e2e / args.steps * 1e3,
-                    "h2d_bytes_per_step": int(host_noisy.numel() * 4 + host_sigma.numel() * 4), "d2h_bytes_per_step": int(host_loss.numel() * 4)},
-            "gpu_launches": int(launches * args.steps),
-            "roofline": {"bound": "tensor", "kernel": {"conv_fwd": "conv_igemm_kernel (forward)", "conv_dgrad": "conv_igemm_kernel (data-gradient)",
-                                                       "wgrad": "wgrad_igemm_kernel"}[top],
-                         "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
-                         "peak_source": peak_src,
-                         "note": "achieved = algorithmic fp32-equivalent FLOPs / CUDA-event time of the kernel's launches in one step; the kernel "
-                                 "issues 3 tf32 MMAs per product (3xTF32), so tensor-pipe issue rate = 3 x achieved",
-                         "pipe_frac": 3 * ach / tf32_peak,
-                         "per_kind": {k: {"launches": v[0], "ms": v[1], "algorithmic_tflops": (v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0),
-                                          "pipe_frac": (3 * v[2] / (v[1] * 1e-3) / 1e12 / tf32_peak if v[1] > 0 else 0.0)}
-                                      for k, v in prof.items()},
-                         "gemm_share_of_step": gemm_ms / (t_res / args.steps * 1e3),
-                         "step_algorithmic_tflops": TRAIN_GFLOP_PER_PATCH[args.config] * 1e9 * BATCH / (t_res / args.steps) / 1e12},
-            "cpu_baseline": {"value": cpu_rate, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "3 steps of 32 patches after 1 warm-up (oracle port of the reference's PyTorch CPU path)"},
-        }
-        print(json.dumps(line), flush=True)
+            peak = E.tensor_peak(True, 1.0)             # measured now, on this GPU, in the same thermal / power state
+        except Exception as e:                          # noqa: BLE001
+            peak = {"error": str(e)}
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6.65 TB/s (of fallback)"
+    if peak and "tflops" in peak:
+        tpeak, tsrc = peak["tflops"], ("measured live: ssdn_tensor_peak (csrc/peak_kernel.cuh), every SM issuing back-to-back tcgen05.mma kind::f16 "
+                                       f"for {peak['seconds']:.1f} s: {peak['flop_per_clk_sm']:.0f} FLOP/clk/SM at {peak['sm_mhz']:.0f} MHz under the power cap")
+    else:
+        tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+        tsrc = "MEASURED_PEAKS.json bf16_tflops_sustained (live probe failed: %s)" % (peak or {}).get("error")
+    ms_step = t_res / args.steps * 1e3
+    by_symbol = {"conv_igemm_kernel": ("conv_fwd", "conv_dgrad"), "wgrad_igemm_kernel": ("wgrad",)}
+    sym_ms = {s: sum(prof[k][1] for k in ks if k in prof) for s, ks in by_symbol.items()}
+    sym_fl = {s: sum(prof[k][2] for k in ks if k in prof) for s, ks in by_symbol.items()}
+    top = max(sym_ms, key=sym_ms.get)                    # the dominant kernel SYMBOL by summed device time
+    ach = sym_fl[top] / (sym_ms[top] * 1e-3) / 1e12 if sym_ms[top] > 0 else 0.0
+    n_top = sum(prof[k][0] for k in by_symbol[top] if k in prof)
+    traffic = None
+    try:                                                 # DRAM bytes per launch of that kernel: committed `ncu --set full` capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    kernels = {}
+    for k, (n, ms, fl, by) in prof.items():
+        row = {"launches": n, "ms": ms}
+        if fl > 0:
+            row.update({"bound": "tensor", "algorithmic_tflops": fl / (ms * 1e-3) / 1e12, "frac_of_tensor_peak": fl / (ms * 1e-3) / 1e12 / tpeak,
+                        "issued_frac_of_tensor_peak": 3 * fl / (ms * 1e-3) / 1e12 / tpeak})
+        if by > 0:
+            row.update({"algorithmic_gb": by / 1e9, "gbs": by / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / hbm})
+            if fl == 0:
+                row["bound"] = "hbm"
+        kernels[k] = row
+    all_ms = sum(v[1] for v in prof.values())
+    cpu = {"value": None, "unit": "patches/s", "cores": None, "kind": "port", "sample": "measured at N = 1 only"}
+    if not args.no_cpu_baseline and world == 1:
+        cpu_batch = min(gbatch, 32)
+        cpu_rate, _ = cpu_oracle_rate(args.config, cpu_batch, 3, 1)
+        cpu = {"value": cpu_rate, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"3 steps of {cpu_batch} patches after 1 warm-up (oracle port of the reference's PyTorch CPU path, all host threads)"}
+    line = {
+        "metric": "64x64 patches/sec (ssdn gauss25, bs32)", "value": total * args.steps / t_res, "unit": "patches/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f16x2 split (two scaled fp16 planes per operand, 3 kind::f16 MMAs per product, fp32 accumulate: fp32-grade results)",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.config, args.scaling), "per_gpu_batch": n_local, "global_batch": total, "parallelism": f"dp{world}",
+                   "l2": "per-step working set ~2.7 GB of activations >> 126 MB L2 (no explicit flush needed)",
+                   "train_gflop_per_patch": TRAIN_GFLOP_PER_PATCH[args.config], "final_loss": loss_val},
+        "clocks": clocks,
+        "e2e": {"value": total * args.steps / t_e2e, "unit": "patches/s", "ms_per_step": t_e2e / args.steps * 1e3,
+                "h2d_bytes_per_step": None, "d2h_bytes_per_step": int(n_local * 4)},
+        "gpu_launches": int(launches * args.steps),
+        "stale_scale_passes": stale, "rank_param_max_diff": spread,
+        "roofline": {"bound": "tensor", "kernel": top, "launches_per_step": n_top,
+                     "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": traffic,
+                     "peak_source": tsrc, "hbm_peak_gbs": hbm, "hbm_peak_source": hbm_src,
+                     "note": "achieved = algorithmic fp32-equivalent FLOPs / summed CUDA-event time of the kernel symbol's launches in one profiled "
+                             "(stream-serialised) step; every product is 3 kind::f16 MMAs, so the tensor pipe executes issued_frac = 3 x frac",
+                     "issued_frac": 3 * ach / tpeak,
+                     "kernels": kernels, "profiled_step_ms": all_ms, "kernel_share_of_profiled_step": sym_ms[top] / all_ms if all_ms else None,
+                     "step_algorithmic_tflops": TRAIN_GFLOP_PER_PATCH[args.config] * 1e9 * n_local / (t_res / args.steps) / 1e12},
+        "cpu_baseline": cpu,
+    }
+    line["e2e"]["h2d_bytes_per_step"] = sum(t.numel() * t.element_size() for t in make_batch(args.config, n_local, 0)[:2]) + \
+        sum(t.numel() * t.element_size() for t in make_batch(args.config, n_local, 0)[2].values())
+    line.update(extras)
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -294,7 +435,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--config", default="known", choices=["known", "var"])
+    ap.add_argument("--config", default="known", choices=list(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other configurations / strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

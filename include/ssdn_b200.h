@@ -79,11 +79,14 @@ int ssdn_net_kernel_launches(void* handle, int training);
 int ssdn_net_debug_scales(void* handle, int* k96, unsigned* amax96, void* stream);
 int ssdn_net_debug_read(void* handle, const char* name, int plane, int c, float* out, int* dims, void* stream);
 int ssdn_net_debug_write(void* handle, const char* name, int c, const float* src, void* stream);
-/* Per-launch CUDA-event timing of the tensor-core kernels; out9[kind*3 + {0,1,2}] = {launches, ms, algorithmic FLOPs}
- * for kind 0 forward conv, 1 data-gradient conv, 2 weight-gradient. */
+/* Per-launch CUDA-event timing of every engine kernel (bench.py roofline).  Kinds, in order: conv_fwd, conv_dgrad, wgrad,
+ * wgrad_reduce, pool_fwd, pool_bwd, up_bwd, pack, weight_prep, bias, scale, posterior_fwd, posterior_bwd, adam, other
+ * (ssdn_profile_kinds() = 15).  profile_end: out[kind*4 + {0,1,2,3}] = {launches, ms, algorithmic FLOPs, algorithmic HBM bytes}.
+ * profile_records: per launch of the last profiled region, in launch order, out[4*i + {0,1,2,3}] = {kind, ms, FLOPs, bytes};
+ * returns the count. */
 int ssdn_profile_begin(void);
-int ssdn_profile_end(double* out9);
-/* Per-launch records of the last profiled region in launch order: out[3*i + {0,1,2}] = {kind, ms, FLOPs}; returns the count. */
+int ssdn_profile_kinds(void);
+int ssdn_profile_end(double* out);
 int ssdn_profile_records(double* out, int max_records);
 
 /* ---- Denoiser._ssdn_pipeline maths — denoiser.py:222-397 ------------------------------------------------------

@@ -94,39 +94,41 @@ extern "C" int ssdn_net_debug_write(void* handle, const char* name, int c, const
   SSDN_CUDA(cudaGetLastError());
   return 0;
 }
-// Per-launch timing of the tensor-core kernels (bench.py roofline).  profile_begin() switches CUDA-event bracketing of
-// every conv / wgrad launch on; profile_end() synchronises and returns, per kind (0 forward conv, 1 data-gradient conv,
-// 2 weight-gradient), the launch count, the summed device time in ms and the summed algorithmic FLOPs: out[kind*3 + {0,1,2}].
+// Per-launch timing of every engine kernel (bench.py roofline).  profile_begin() switches CUDA-event bracketing of every launch
+// on (everything then runs on one stream); profile_end() synchronises and returns, per kind (ProfKind, conv_igemm.cuh), the
+// launch count, the summed device time in ms, the summed algorithmic FLOPs and the summed algorithmic HBM bytes:
+// out[kind*4 + {0,1,2,3}] for K_COUNT = 15 kinds.
 extern "C" int ssdn_profile_begin(void) { profiler().recs.clear(); profiler().on = true; return 0; }
-static std::vector<double> g_last_records;   // (kind, ms, flops) per launch of the last profiled region
-extern "C" int ssdn_profile_end(double* out9) {
+static std::vector<double> g_last_records;   // (kind, ms, flops, bytes) per launch of the last profiled region
+extern "C" int ssdn_profile_kinds(void) { return K_COUNT; }
+extern "C" int ssdn_profile_end(double* out) {
   LaunchProfiler& pr = profiler();
   pr.on = false;
-  for (int i = 0; i < 9; ++i) out9[i] = 0;
+  for (int i = 0; i < 4 * K_COUNT; ++i) out[i] = 0;
   SSDN_CUDA(cudaDeviceSynchronize());
   g_last_records.clear();
   for (auto& r : pr.recs) {
     float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
-    out9[r.kind * 3 + 0] += 1; out9[r.kind * 3 + 1] += ms; out9[r.kind * 3 + 2] += r.flops;
-    g_last_records.push_back(r.kind); g_last_records.push_back(ms); g_last_records.push_back(r.flops);
+    out[r.kind * 4 + 0] += 1; out[r.kind * 4 + 1] += ms; out[r.kind * 4 + 2] += r.flops; out[r.kind * 4 + 3] += r.bytes;
+    g_last_records.push_back(r.kind); g_last_records.push_back(ms); g_last_records.push_back(r.flops); g_last_records.push_back(r.bytes);
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
   pr.recs.clear();
   return 0;
 }
-// Per-launch records of the last profiled region, in launch order: out[3*i + {0,1,2}] = {kind, ms, algorithmic FLOPs}.
+// Per-launch records of the last profiled region, in launch order: out[4*i + {0,1,2,3}] = {kind, ms, algorithmic FLOPs, bytes}.
 // Returns the number of records (copies at most max_records).
 extern "C" int ssdn_profile_records(double* out, int max_records) {
-  const int n = (int)(g_last_records.size() / 3);
-  for (int i = 0; i < n && i < max_records; ++i) for (int k = 0; k < 3; ++k) out[3 * i + k] = g_last_records[3 * i + k];
+  const int n = (int)(g_last_records.size() / 4);
+  for (int i = 0; i < n && i < max_records; ++i) for (int k = 0; k < 4; ++k) out[4 * i + k] = g_last_records[4 * i + k];
   return n;
 }
 extern "C" int ssdn_net_kernel_launches(void* handle, int training) {
   net::Net* nn = (net::Net*)handle;
   const int nl = (int)nn->layers.size();
-  int fwd = nl /*conv*/ + 5 /*pool*/ + 1 /*pack*/ + 2 /*weight scales, weight slabs*/ + 2 /*scale begin / finish*/;
-  int bwd = 3 /*loss-gradient scale, pack, column sums*/ + nl * 2 /*wgrad, split-K reduce*/ + 1 /*all bias reductions*/ + (nl - 1) /*dgrad*/ + 5 + 5 /*pool, upsample*/ +
-            2 /*scale begin / finish*/;
+  int fwd = nl /*conv*/ + 5 /*pool*/ + 1 /*pack*/ + 2 /*weight scales, weight slabs*/ + 1 /*scale finish*/;
+  int bwd = 3 /*loss-gradient scale, pack, column sums*/ + nl /*wgrad*/ + 1 /*all split-K reductions*/ + 1 /*all bias reductions*/ + (nl - 1) /*dgrad*/ +
+            5 + 5 /*pool, upsample*/ + 1 /*scale finish*/;
   return training ? fwd + bwd : fwd;
 }
 
@@ -187,8 +189,10 @@ extern "C" int ssdn_posterior_forward(void* ws, const float* net_out, const floa
   float* partial = (float*)ws;
   dim3 grid(nblk, n);
   float* ns_px = poisson ? noise_std : nullptr;     // Poisson: noise_std is [n][h][w]; Gaussian: [n]
-  if (c == 1) lossk::posterior_fwd_kernel<1><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, pme, model_std, ns_px, partial);
-  else lossk::posterior_fwd_kernel<3><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, pme, model_std, ns_px, partial);
+  // per pixel: net_out (c + c(c+1)/2) + noisy c in, pme c + model_std 1 out
+  const double fbytes = (double)n * hw * 4.0 * ((c + c * (c + 1) / 2) + c + c + 1);
+  if (c == 1) SSDN_PROF(K_POSTERIOR_FWD, 0, fbytes, st, (lossk::posterior_fwd_kernel<1><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, pme, model_std, ns_px, partial)));
+  else SSDN_PROF(K_POSTERIOR_FWD, 0, fbytes, st, (lossk::posterior_fwd_kernel<3><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, pme, model_std, ns_px, partial)));
   lossk::posterior_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, nblk, hw, sigma_raw, cs, sigma_known, c, n, loss,
                                                                      poisson ? nullptr : noise_std);
   SSDN_CUDA(cudaGetLastError());
@@ -204,8 +208,10 @@ extern "C" int ssdn_posterior_backward(void* ws, const float* net_out, const flo
   float* partial = (float*)ws;
   dim3 grid(nblk, n);
   float* dp = (dsigma_raw && !sigma_known) ? partial : nullptr;
-  if (c == 1) lossk::posterior_bwd_kernel<1><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, gloss, dnet, dp);
-  else lossk::posterior_bwd_kernel<3><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, gloss, dnet, dp);
+  // per pixel: net_out + noisy in, d(net_out) out
+  const double bbytes = (double)n * hw * 4.0 * (2 * (c + c * (c + 1) / 2) + c);
+  if (c == 1) SSDN_PROF(K_POSTERIOR_BWD, 0, bbytes, st, (lossk::posterior_bwd_kernel<1><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, gloss, dnet, dp)));
+  else SSDN_PROF(K_POSTERIOR_BWD, 0, bbytes, st, (lossk::posterior_bwd_kernel<3><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, gloss, dnet, dp)));
   if (dp) lossk::posterior_bwd_finalize_kernel<<<(n * cs + 127) / 128, 128, 0, st>>>(partial, nblk, sigma_raw, cs, c, n, poisson, gloss, dsigma_raw);
   SSDN_CUDA(cudaGetLastError());
   return 0;
@@ -264,8 +270,10 @@ extern "C" int ssdn_adam_step(float* p, const float* g, float* m, float* v, long
   if (step < 1) return fail(-1, "Adam step count starts at 1");
   if (n_skip < 0 || n_skip > 8) return fail(-1, "at most 8 skip flags");
   const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
-  lossk::adam_kernel<<<pw::grid_for(count), pw::kBlock, 0, (cudaStream_t)stream>>>(p, g, m, v, count, (float)(lr / bc1), (float)beta1, (float)beta2,
-                                                                                  (float)eps, (float)sqrt(bc2), (float)grad_scale, skip, skip ? n_skip : 0);
+  // 16 bytes read + 12 written per parameter
+  SSDN_PROF(K_ADAM, 0, 28.0 * count, (cudaStream_t)stream,
+            (lossk::adam_kernel<<<pw::grid_for(count), pw::kBlock, 0, (cudaStream_t)stream>>>(p, g, m, v, count, (float)(lr / bc1), (float)beta1, (float)beta2,
+                                                                                            (float)eps, (float)sqrt(bc2), (float)grad_scale, skip, skip ? n_skip : 0)));
   SSDN_CUDA(cudaGetLastError());
   return 0;
 }

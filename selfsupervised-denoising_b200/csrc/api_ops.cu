@@ -61,15 +61,15 @@ int run_conv(void* ws, size_t ws_bytes, const float* x, const float* w, const fl
   const long long ne = (long long)n * cin * h * wd;
   pw::leaf_scale_kernel<<<64, 256, 0, st>>>(x, ne, sc, 0, 0, 0);
   pw::WeightScaleJobs wj{}; wj.j[0] = {w, w_cout * w_cin * ksize * ksize, 1};
-  pw::weight_scale_kernel<<<1, 256, 0, st>>>(wj, sc);
+  pw::weight_scale_kernel<<<dim3(pw::kWeightScaleBlocks, 1), 256, 0, st>>>(wj, sc, 0, 0);
   ScaleRef xs{sc.k, nullptr};
   pw::pack_nchw_kernel<<<pw::grid_for(ne), pw::kBlock, 0, st>>>(x, ah, al, n, cin, h, wd, L.g, L.cin_pitch, 0, 0, xs);
   const bool wide = conv_is_wide(cin, L.taps.n);
   int nc, kl; conv_chunks(cin, &nc, &kl, wide);
   const int n_tiles = L.cout_padded / L.N;
-  const long long ns = (long long)L.slab_halves / 2;
+  const long long ns = (long long)L.slab_halves / 2 / 8;
   pw::weight_prep_kernel<<<pw::grid_for(ns), pw::kBlock, 0, st>>>(w, slab, w_cout, w_cin, L.taps.n, cout, cin, n_tiles, nc,
-                                                                  L.N, dgrad ? 1 : 0, wide ? 64 : 32, sc.k + 1);
+                                                                  L.N, dgrad ? 1 : 0, wide ? 64 : 32, sc, 1);
   ConvDst d{};
   d.v = y; d.hi = d.lo = nullptr; d.cpitch = 0; d.coff = 0; d.g = L.g; d.map = MAP_NCHW;
   d.flags = (bias ? EP_BIAS : 0) | (lrelu_act ? EP_LRELU : 0); d.cvalid = cout; d.nimg = n; d.bias = bias;

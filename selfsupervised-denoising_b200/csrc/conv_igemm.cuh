@@ -66,6 +66,7 @@ struct ConvParams {
 struct ConvPlan {
   ConvParams p;
   double flops = 0;   // algorithmic 2*MAC of this launch (valid pixels, real channels); filled by the owner
+  double bytes = 0;   // algorithmic HBM bytes of this launch (operand planes in, result out); filled by the owner
   CUtensorMap a, b;   // a: [plane][flat pixel][channel] (3-D), b: weight slabs [slab x plane][N][32] (3-D), fp16
   int grid; size_t smem;
 };
@@ -805,15 +806,22 @@ static inline size_t conv_weight_slab_halves(int cin, int cout_padded, int ntaps
   return (size_t)cout_padded * nc * ntaps * (wide ? 64 : 32) * 2;
 }
 
-// Optional per-launch timing (bench.py roofline): when enabled every GEMM launch is bracketed by CUDA events.
+// Optional per-launch timing (bench.py roofline): when enabled every kernel launch of the engine is bracketed by CUDA events
+// on the stream it is launched on, with its algorithmic FLOPs and HBM bytes.
+enum ProfKind : int { K_CONV_FWD = 0, K_CONV_DGRAD, K_WGRAD, K_WGRAD_REDUCE, K_POOL_FWD, K_POOL_BWD, K_UP_BWD, K_PACK, K_WEIGHT_PREP,
+                      K_BIAS, K_SCALE, K_POSTERIOR_FWD, K_POSTERIOR_BWD, K_ADAM, K_OTHER, K_COUNT };
 struct LaunchProfiler {
   bool on = false;
-  struct Rec { int kind; double flops; cudaEvent_t a, b; };
+  struct Rec { int kind; double flops, bytes; cudaEvent_t a, b; };
   std::vector<Rec> recs;
-  void begin(int kind, double flops, cudaStream_t st) { Rec r{kind, flops, nullptr, nullptr}; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, st); recs.push_back(r); }
+  void begin(int kind, double flops, double bytes, cudaStream_t st) {
+    Rec r{kind, flops, bytes, nullptr, nullptr}; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, st); recs.push_back(r);
+  }
   void end(cudaStream_t st) { cudaEventRecord(recs.back().b, st); }
 };
 inline LaunchProfiler& profiler() { static LaunchProfiler p; return p; }
+#define SSDN_PROF(kind, flops, bytes, st, launch) do { const bool on_ = profiler().on; if (on_) profiler().begin(kind, flops, bytes, st); launch; \
+                                                       if (on_) profiler().end(st); } while (0)
 
 static inline cudaError_t conv_launch_raw(const ConvPlan& plan, const ConvParams& p, cudaStream_t stream);
 // Developer instrumentation: one synchronous launch with the per-role wait clocks collected and printed to stderr.
@@ -822,7 +830,7 @@ static inline cudaError_t conv_launch_with_stats(const ConvPlan& plan, cudaStrea
   if (!dev) cudaMalloc(&dev, 1024 * 16 * sizeof(unsigned long long));
   cudaMemsetAsync(dev, 0, 1024 * 16 * sizeof(unsigned long long), stream);
   ConvParams p = plan.p; p.stats = dev;
-  profiler().begin(kind, plan.flops, stream);
+  profiler().begin(kind, plan.flops, plan.bytes, stream);
   conv_launch_raw(plan, p, stream);
   profiler().end(stream);
   std::vector<unsigned long long> h((size_t)plan.grid * 16);
@@ -866,7 +874,7 @@ static inline cudaError_t conv_launch_raw(const ConvPlan& plan, const ConvParams
 static inline cudaError_t conv_launch(const ConvPlan& plan, cudaStream_t stream, int kind = 0) {
   static const bool want_stats = getenv("SSDN_CONV_STATS") != nullptr;
   if (want_stats && profiler().on) return conv_launch_with_stats(plan, stream, kind);
-  if (profiler().on) profiler().begin(kind, plan.flops, stream);
+  if (profiler().on) profiler().begin(kind, plan.flops, plan.bytes, stream);
   cudaError_t e = conv_launch_raw(plan, plan.p, stream);
   if (profiler().on) profiler().end(stream);
   return e;

@@ -46,7 +46,7 @@ struct Layer {               // one convolution of the network
   const float* bias_partial = nullptr;          //   partial[bias_nblk][cout]
   float* bias_buf = nullptr;                    //   this layer's own partial buffer (all bias reductions run as one kernel at the end)
   // weight gradient
-  WgradPlan wgrad; int ksplit;
+  WgradPlan wgrad; int ksplit; float* partial = nullptr;   // this layer's own K-split partial buffer
   const Buf* x; int x_coff;          // conv input (channel slice [x_coff, x_coff+cin))
   const Buf* dz;                     // gradient w.r.t. this conv's pre-activation output
 };
@@ -184,14 +184,16 @@ class Net {
       size_t fd = conv_weight_slab_halves(l.cout, l.cinp_d, nt);
       l.slab_d = a.take<__half>(fd);
     }
-    // wgrad partials: one buffer, sized for the largest layer
+    // wgrad partials: one buffer per layer, so that a single batched reduction at the end of backward() finishes them all
     partial_floats = 0;
     for (auto& l : layers) {
       const Geom& gg = (l.ksize == 1) ? gh : g[level_of(l.name)];
       l.ksplit = wgrad_pick_ksplit(gg.total(), l.cout, l.cin, l.ksize * l.ksize, sms);
-      partial_floats = std::max(partial_floats, wgrad_partial_floats(l.ksplit, l.ksize * l.ksize, l.cout, l.cin));
+      const size_t pf = wgrad_partial_floats(l.ksplit, l.ksize * l.ksize, l.cout, l.cin);
+      l.partial = a.take<float>(pf);
+      partial_floats += pf;
     }
-    partial = a.take<float>(partial_floats);
+    partial = nullptr;
     colpart = a.take<float>((size_t)1024 * 384);
     for (auto& l : layers) l.bias_buf = a.take<float>((size_t)std::max(sms * convk::kEpiWarps, pw::kFusedColsumGrid) * l.cout);
     flag = a.take<int>(64);
@@ -306,9 +308,11 @@ class Net {
       const Geom& gg = w.x->g;
       ConvTaps taps = eng::make_taps(l.ksize, blind, false, gg.P);
       if ((r = wgrad_plan_init(&l.wgrad, gg.total(), w.dz->hi, w.dz->lo, w.dz->cpitch, 0, l.cout, w.x->hi, w.x->lo, w.x->cpitch,
-                               w.xoff, l.cin, taps, l.ksplit, partial, flag, sms, w.dz->sc.k, w.x->sc.k)))
+                               w.xoff, l.cin, taps, l.ksplit, l.partial, flag, sms, w.dz->sc.k, w.x->sc.k)))
         return eng::fail(r, "wgrad plan for %s failed (%d)", w.nm, r);
       l.wgrad.flops = 2.0 * B0(gg) * l.cin * l.cout * l.ksize * l.ksize;
+      // both operands' plane pairs once + the K-split partials
+      l.wgrad.bytes = (double)gg.total() * 4.0 * (l.cin + l.cout) + 4.0 * wgrad_partial_floats(l.ksplit, l.ksize * l.ksize, l.cout, l.cin);
     }
     for (auto& l : layers) if (l.bias_fused && l.bias_nblk < 0) return eng::fail(-6, "bias partial buffer of %s too small", l.name.c_str());
     return 0;
@@ -331,6 +335,17 @@ class Net {
     return d;
   }
 
+  // algorithmic HBM bytes of one conv launch: the source plane pair once (halo included) + what the epilogue writes
+  // (plane pairs or fp32, x4 when upsampling) + sign-mask words in / out
+  static double conv_bytes(const Geom& sg, int cin, const ConvDst& d, int cout) {
+    const double px = B0(sg);
+    double b = (double)sg.total() * cin * 4.0;
+    const double out_px = px * (d.map == MAP_UP2 ? 4.0 : 1.0);
+    b += out_px * cout * 4.0;                         // two fp16 planes or one fp32 plane: 4 bytes per element either way
+    if (d.mask_out) b += px * ((cout + 31) / 32) * 4.0;
+    if (d.mask_in) b += px * d.mask_in_words * 4.0;
+    return b;
+  }
   int layer_index(const Layer& l) const { return (int)(&l - layers.data()); }
   const int* k_w(const Layer& l) const { return scales.k ? scales.k + kSlotW + layer_index(l) : nullptr; }
 
@@ -340,6 +355,7 @@ class Net {
                            flag, sms, src.sc.k, k_w(l));
     if (r) return eng::fail(r, "forward plan for %s failed (%d)", l.name.c_str(), r);
     l.fwd.flops = 2.0 * B0(src.g) * l.cin * l.cout * l.ksize * l.ksize;
+    l.fwd.bytes = conv_bytes(src.g, l.cin, d, l.cout);
     return 0;
   }
   int plan_dgrad(Layer& l, Buf& src, ConvDst d) {
@@ -348,6 +364,7 @@ class Net {
                            flag, sms, src.sc.k, k_w(l));
     if (r) return eng::fail(r, "dgrad plan for %s failed (%d)", l.name.c_str(), r);
     l.dgrad.flops = 2.0 * B0(src.g) * l.dgrad_nvalid * l.cout * l.ksize * l.ksize;
+    l.dgrad.bytes = conv_bytes(src.g, l.cout, d, l.dgrad_nvalid);
     return 0;
   }
 
@@ -357,21 +374,25 @@ class Net {
     pw::WeightScaleJobs sj{};
     int ns = 0;
     for (auto& l : layers) sj.j[ns++] = {params + l.w_off, l.cout * l.cin * l.ksize * l.ksize, kSlotW + layer_index(l)};
-    pw::weight_scale_kernel<<<ns, 256, 0, st>>>(sj, scales);
+    SSDN_PROF(K_WEIGHT_PREP, 0, 4.0 * n_params, st,
+              (pw::weight_scale_kernel<<<dim3(pw::kWeightScaleBlocks, ns), 256, 0, st>>>(sj, scales, kSlotA, n_slot_a)));
     pw::WeightPrepJobs jobs{};
     int nj = 0;
     for (auto& l : layers) {
       const int nt = l.ksize * l.ksize;
       bool wide = conv_is_wide(l.cin, nt);
       int nc, kl; conv_chunks(l.cin, &nc, &kl, wide);
-      jobs.j[nj++] = {params + l.w_off, l.slab_f, l.cout, l.cin, nt, l.cout, l.cin, l.coutp_f / l.n_f, nc, l.n_f, 0, wide ? 64 : 32, k_w(l)};
+      jobs.j[nj++] = {params + l.w_off, l.slab_f, l.cout, l.cin, nt, l.cout, l.cin, l.coutp_f / l.n_f, nc, l.n_f, 0, wide ? 64 : 32, kSlotW + layer_index(l)};
       if (with_dgrad && l.has_dgrad) {
         wide = conv_is_wide(l.cout, nt);
         conv_chunks(l.cout, &nc, &kl, wide);
-        jobs.j[nj++] = {params + l.w_off, l.slab_d, l.cout, l.cin, nt, l.dgrad_nvalid, l.cout, l.cinp_d / l.n_d, nc, l.n_d, 1, wide ? 64 : 32, k_w(l)};
+        jobs.j[nj++] = {params + l.w_off, l.slab_d, l.cout, l.cin, nt, l.dgrad_nvalid, l.cout, l.cinp_d / l.n_d, nc, l.n_d, 1, wide ? 64 : 32, kSlotW + layer_index(l)};
       }
     }
-    pw::weight_prep_batched_kernel<<<dim3(64, nj), pw::kBlock, 0, st>>>(jobs);
+    double slab_bytes = 0;
+    for (int j = 0; j < nj; ++j) slab_bytes += 2.0 * 2.0 * jobs.j[j].n_tiles * jobs.j[j].n_chunks * jobs.j[j].ntaps * jobs.j[j].N * jobs.j[j].CW;
+    SSDN_PROF(K_WEIGHT_PREP, 0, slab_bytes + 4.0 * n_params * (with_dgrad ? 2 : 1), st,
+              (pw::weight_prep_batched_kernel<<<dim3(64, nj), pw::kBlock, 0, st>>>(jobs, scales)));
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }
@@ -379,24 +400,26 @@ class Net {
   int run_fwd(Layer& l, const float* params, cudaStream_t st, float* nchw_out = nullptr) {
     l.fwd.p.dst.bias = params + l.b_off;
     if (nchw_out) l.fwd.p.dst.v = nchw_out;
-    SSDN_CUDA(conv_launch(l.fwd, st));
+    SSDN_CUDA(conv_launch(l.fwd, st, K_CONV_FWD));
     return 0;
   }
 
   int forward(const float* params, const float* x, float* out, cudaStream_t st, bool training) {
     if (!ws) return eng::fail(-5, "network workspace not bound");
     int r;
-    pw::scale_begin_kernel<<<1, 32, 0, st>>>(scales, kSlotA, n_slot_a);
-    ++fwd_runs;
+    ++fwd_runs;                 // (the pass over the activation slots is begun by prep_weights' first kernel)
     if ((r = prep_weights(params, st, training))) return r;
-    pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)B * H * W), pw::kBlock, 0, st>>>(x, cat[1].hi, cat[1].lo, N, Cin, H, W, g[0],
-                                                                                          cat[1].cpitch, 96, blind ? 1 : 0, cat[1].sc);
+    SSDN_PROF(K_PACK, 0, (double)N * Cin * H * W * 4.0 + (double)B * H * W * Cin * 4.0, st,
+              (pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)B * H * W), pw::kBlock, 0, st>>>(x, cat[1].hi, cat[1].lo, N, Cin, H, W, g[0],
+                                                                                                    cat[1].cpitch, 96, blind ? 1 : 0, cat[1].sc)));
     size_t pi = 0;
     auto pool = [&]() {
       const PoolOp& p = pools[pi++];
       const long long n = (long long)p.dst->g.B * p.dst->g.H * p.dst->g.W * 6;
-      pw::pool_fwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(p.src->hi, p.src->lo, p.src->g, p.src->cpitch, 0, p.src->sc, p.dst->hi, p.dst->lo,
-                                                                  p.dst->g, p.dst->cpitch, p.dst_coff, p.dst->sc, 48, blind ? 1 : 0);
+      // reads the full-resolution plane pair once, writes the pooled one
+      SSDN_PROF(K_POOL_FWD, 0, B0(p.src->g) * 48 * 4.0 + B0(p.dst->g) * 48 * 4.0, st,
+                (pw::pool_fwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(p.src->hi, p.src->lo, p.src->g, p.src->cpitch, 0, p.src->sc, p.dst->hi, p.dst->lo,
+                                                                            p.dst->g, p.dst->cpitch, p.dst_coff, p.dst->sc, 48, blind ? 1 : 0)));
     };
     if ((r = run_fwd(L("encode_block_1.0"), params, st))) return r;
     if ((r = run_fwd(L("encode_block_1.2"), params, st))) return r;
@@ -410,7 +433,7 @@ class Net {
     if ((r = run_fwd(L("output_block.0"), params, st))) return r;
     if ((r = run_fwd(L("output_block.2"), params, st))) return r;
     if ((r = run_fwd(L("output_conv"), params, st, out))) return r;
-    pw::scale_finish_kernel<<<1, 32, 0, st>>>(scales, kSlotA, n_slot_a, 0, nullptr);
+    SSDN_PROF(K_SCALE, 0, 0, st, (pw::scale_finish_kernel<<<1, 32, 0, st>>>(scales, kSlotA, n_slot_a, 0, nullptr, 0, kSlotW, (int)layers.size())));
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }
@@ -433,29 +456,48 @@ class Net {
       SSDN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
       ws_ = side;
     }
-    SSDN_CUDA(wgrad_launch(l.wgrad, ws_));
-    wgradk::wgrad_reduce_launch(partial, l.wgrad.p.ksplit, nt, l.cout, l.cin, l.wgrad.p.cin_pitch, grads + l.w_off, 0, ws_);
+    (void)nt;
+    SSDN_CUDA(wgrad_launch(l.wgrad, ws_));     // its K-split partials are reduced by reduce_all_wgrads()
+    return 0;
+  }
+  // dW of every layer from its K-split partials: one launch on the stream the weight gradients ran on
+  int reduce_all_wgrads(float* grads, cudaStream_t st) {
+    wgradk::WgradReduceJobs jobs{};
+    int nj = 0, blocks = 0; double bytes = 0;
+    for (auto& l : layers) {
+      const int nt = l.ksize * l.ksize;
+      const long long n = (long long)l.cout * l.wgrad.p.cin_pitch * nt;
+      jobs.j[nj++] = {l.partial, grads + l.w_off, l.wgrad.p.ksplit, nt, l.cout, l.cin, l.wgrad.p.cin_pitch, blocks};
+      blocks += (int)((n + 31) / 32);
+      bytes += (double)n * 4 * (l.wgrad.p.ksplit + 1);
+    }
+    jobs.n_jobs = nj;
+    SSDN_PROF(K_WGRAD_REDUCE, 0, bytes, st, (wgradk::wgrad_reduce_batched_kernel<<<blocks, dim3(32, 16), 0, st>>>(jobs)));
+    SSDN_CUDA(cudaGetLastError());
     return 0;
   }
   int join_side(cudaStream_t st) {
     if (side) { SSDN_CUDA(cudaEventRecord(ev_join, side)); SSDN_CUDA(cudaStreamWaitEvent(st, ev_join, 0)); }
     return 0;
   }
-  int run_dgrad(Layer& l, cudaStream_t st) { SSDN_CUDA(conv_launch(l.dgrad, st, 1)); return 0; }
+  int run_dgrad(Layer& l, cudaStream_t st) { SSDN_CUDA(conv_launch(l.dgrad, st, K_CONV_DGRAD)); return 0; }
 
   // grads: flat buffer with the layout of params; every element is overwritten.  stale_out (optional, device): receives 1.0f
   // when this step's forward or backward pass ran with operand scales outside their band (see common.cuh), else 0.0f.
   int backward(const float* params, const float* dout, float* grads, float* stale_out, cudaStream_t st) {
     if (!ws) return eng::fail(-5, "network workspace not bound");
     int r;
-    pw::scale_begin_kernel<<<1, 32, 0, st>>>(scales, kSlotG, n_slot_g);
+    const double dout_bytes = (double)N * Cout * H * W * 4.0;
+    // (the gradient slots were begun by the previous backward pass's scale_finish_kernel, or by bind())
     // the loss gradient is a leaf: exact scale now; the very first backward pass seeds every gradient slot with it
-    pw::leaf_scale_kernel<<<64, 256, 0, st>>>(dout, (long long)N * Cout * H * W, scales, g_out.sid, kSlotG, bwd_runs == 0 ? n_slot_g : 0);
+    SSDN_PROF(K_SCALE, 0, dout_bytes, st,
+              (pw::leaf_scale_kernel<<<64, 256, 0, st>>>(dout, (long long)N * Cout * H * W, scales, g_out.sid, kSlotG, bwd_runs == 0 ? n_slot_g : 0)));
     ++bwd_runs;
     ScaleRef no_amax = g_out.sc; no_amax.amax = nullptr;
-    pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)N * H * W), pw::kBlock, 0, st>>>(dout, g_out.hi, g_out.lo, N, Cout, H, W, gh,
-                                                                                          g_out.cpitch, 0, 0, no_amax);
-    pw::nchw_colsum_kernel<<<dim3(Cout, N), 256, 0, st>>>(dout, Cout, H * W, L("output_conv").bias_buf);
+    SSDN_PROF(K_PACK, 0, 2 * dout_bytes, st,
+              (pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)N * H * W), pw::kBlock, 0, st>>>(dout, g_out.hi, g_out.lo, N, Cout, H, W, gh,
+                                                                                                    g_out.cpitch, 0, 0, no_amax)));
+    SSDN_PROF(K_BIAS, 0, dout_bytes, st, (pw::nchw_colsum_kernel<<<dim3(Cout, N), 256, 0, st>>>(dout, Cout, H * W, L("output_conv").bias_buf)));
     auto both = [&](const std::string& nm, bool dgrad) -> int {
       Layer& l = L(nm);
       int rr = run_wgrad(l, grads, st);
@@ -471,14 +513,18 @@ class Net {
       const Geom& gl = u.dz->g;
       const long long n = (long long)gl.B * gl.H * gl.W * (u.C / 4);
       (void)n;
-      pw::up_bwd_kernel<<<u.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * 8 * sizeof(float), st>>>(
-          u.g->v, u.g->g, u.g->cpitch, 0, u.act_up->hi, u.act_up->cpitch, 0, gl, u.dz->hi, u.dz->lo, u.dz->cpitch, 0, u.dz->sc, u.C, u.colsum);
+      // reads the fp32 gradient at the upsampled resolution (4 pixels per output) + one hi-plane sign per output, writes a plane pair
+      SSDN_PROF(K_UP_BWD, 0, B0(gl) * u.C * (4 * 4.0 + 2.0 + 4.0), st,
+                (pw::up_bwd_kernel<<<u.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * 8 * sizeof(float), st>>>(
+                    u.g->v, u.g->g, u.g->cpitch, 0, u.act_up->hi, u.act_up->cpitch, 0, gl, u.dz->hi, u.dz->lo, u.dz->cpitch, 0, u.dz->sc, u.C, u.colsum)));
     };
     auto pool_bwd = [&]() {
       const PoolBwdOp& q = pool_bwds[qi++];
-      pw::pool_bwd_kernel<<<q.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * 8 * sizeof(float), st>>>(
-          q.act->hi, q.act->lo, q.act->g, q.act->cpitch, 0, q.g1->v, q.g1->cpitch, 0, q.g2 ? q.g2->v : nullptr, q.g2 ? q.g2->cpitch : 0, q.g2_coff, q.gp,
-          q.dz->hi, q.dz->lo, q.dz->cpitch, 0, q.dz->sc, 48, blind ? 1 : 0, q.colsum);
+      // per pooled pixel and channel: 4 activations (plane pairs) in, 1 or 2 fp32 gradients in, 4 dZ values (plane pairs) out
+      SSDN_PROF(K_POOL_BWD, 0, B0(q.gp) * 48 * (4 * 4.0 + (q.g2 ? 8.0 : 4.0) + 4 * 4.0), st,
+                (pw::pool_bwd_kernel<<<q.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * 8 * sizeof(float), st>>>(
+                    q.act->hi, q.act->lo, q.act->g, q.act->cpitch, 0, q.g1->v, q.g1->cpitch, 0, q.g2 ? q.g2->v : nullptr, q.g2 ? q.g2->cpitch : 0, q.g2_coff, q.gp,
+                    q.dz->hi, q.dz->lo, q.dz->cpitch, 0, q.dz->sc, 48, blind ? 1 : 0, q.colsum)));
     };
     for (int i = 1; i <= 5; ++i) {
       if ((r = both("decode_block_" + std::to_string(i) + ".2", true))) return r;
@@ -498,10 +544,13 @@ class Net {
       int nj = 0, maxc = 0;
       for (auto& l : layers)
         if (l.bias_fused) { jobs.j[nj++] = {l.bias_partial, grads + l.b_off, l.bias_nblk, l.cout}; maxc = std::max(maxc, l.cout); }
-      if (nj) pw::colsum_stage2_batched_kernel<<<dim3((maxc + 31) / 32, nj), dim3(32, 32), 0, st>>>(jobs);
+      double pb = 0;
+      for (int j = 0; j < nj; ++j) pb += 4.0 * jobs.j[j].nblk * jobs.j[j].C;
+      if (nj) SSDN_PROF(K_BIAS, 0, pb, st, (pw::colsum_stage2_batched_kernel<<<dim3((maxc + 31) / 32, nj), dim3(32, 32), 0, st>>>(jobs)));
     }
+    if ((r = reduce_all_wgrads(grads, (side && use_side && !profiler().on) ? side : st))) return r;
     if ((r = join_side(st))) return r;
-    pw::scale_finish_kernel<<<1, 32, 0, st>>>(scales, kSlotG, n_slot_g, 1, stale_out);
+    SSDN_PROF(K_SCALE, 0, 0, st, (pw::scale_finish_kernel<<<1, 32, 0, st>>>(scales, kSlotG, n_slot_g, 1, stale_out, 1, 0, 0)));
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }

@@ -46,8 +46,9 @@ __global__ void pack_nchw_f32_kernel(const float* __restrict__ x, float* __restr
   v[((long long)b * g.S + (i + g.row0) * g.P + j) * cpitch + coff + c] = __ldg(x + idx);
 }
 
-// Same mapping, one thread per output PIXEL writing all C (<= 16) channels: the stores of a thread are contiguous and
-// the index arithmetic is done once per pixel (the network input and the loss gradient have 3..12 channels).
+// Same mapping, one thread per output PIXEL writing all C (<= 16) channels as 16-byte vectors of 8 channels per plane (the
+// destination's channel offset and pitch are multiples of 8; the pad channels of the last vector are written as zeros): the
+// index arithmetic is done once per pixel (the network input and the loss gradient have 3..12 channels).
 __global__ void pack_nchw_pixel_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
                                        int B, int C, int H, int W, Geom g, int cpitch, int coff, int rot4, ScaleRef sc) {
   const long long n = (long long)(rot4 ? 4 : 1) * B * H * W;
@@ -63,10 +64,17 @@ __global__ void pack_nchw_pixel_kernel(const float* __restrict__ x, __half* __re
     else if (r == 3) { si = H - 1 - j; sj = i; }
     const float* src = x + ((long long)b * C * H + si) * W + sj;
     const long long o = ((long long)bo * g.S + (i + g.row0) * g.P + j) * cpitch + coff;
-    for (int c = 0; c < C; ++c) {
-      const float val = __ldg(src + (long long)c * H * W);
-      f16_split1(val * s, hi[o + c], lo[o + c]);
-      m = fmaxf(m, fabsf(val));
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float val = (c0 + q < C) ? __ldg(src + (long long)(c0 + q) * H * W) : 0.f;
+        m = fmaxf(m, fabsf(val));
+        f[q] = val * s;
+      }
+      uint4 h, l;
+      f16_split8(f, h, l);
+      *reinterpret_cast<uint4*>(hi + o + c0) = h; *reinterpret_cast<uint4*>(lo + o + c0) = l;
     }
   }
   amax_commit(sc.amax, m);
@@ -319,9 +327,14 @@ __global__ void scale_begin_kernel(ScaleState st, int first, int count) {
 // pass stale (the host re-runs it / the optimiser skips it); every slot that saw data gets the scale that puts this pass's
 // maximum at 2^kScaleTarget.  which = 0 (forward) or 1 (backward); stale_out (optional, backward) receives
 // (forward stale | backward stale) as a float appended to the gradient buffer, so that it takes part in the all-reduce.
-__global__ void scale_finish_kernel(ScaleState st, int first, int count, int which, float* __restrict__ stale_out) {
+// apply != 0 (backward: nobody reads these slots any more): adopt the new scales and clear the maxima right away, so that
+// the next pass over these slots needs no scale_begin_kernel.
+// clear_count > 0: also clear the maxima of slots [clear_first, clear_first + clear_count) (the weight slots, whose readers are done).
+__global__ void scale_finish_kernel(ScaleState st, int first, int count, int which, float* __restrict__ stale_out, int apply,
+                                    int clear_first, int clear_count) {
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;
+  for (int i = threadIdx.x; i < clear_count; i += blockDim.x) st.amax[clear_first + i] = 0u;
   __syncthreads();
   for (int i = first + threadIdx.x; i < first + count; i += blockDim.x) {
     const unsigned a = st.amax[i];
@@ -330,6 +343,7 @@ __global__ void scale_finish_kernel(ScaleState st, int first, int count, int whi
       if (e >= kScaleHiLimit || e < kScaleLoLimit || a >= 0x7f800000u) atomicOr(&bad, 1);
       st.k_next[i] = scale_for_amax(a < 0x7f800000u ? a : 0x7f7fffffu);
     }
+    if (apply) { st.k[i] = st.k_next[i]; st.amax[i] = 0u; }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -362,63 +376,83 @@ __global__ void leaf_scale_kernel(const float* __restrict__ x, long long n, Scal
     }
   }
 }
-// Exact scales of all weight tensors of a network in one launch (block j handles job j).
+// Exact scales of all weight tensors of a network: grid (kWeightScaleBlocks, jobs) folds max|w| of every tensor into its
+// slot's amax (zero on entry: scale_finish_kernel clears the weight slots at the end of every forward pass); the weight-prep
+// kernel then turns the maximum into the exponent (weight_scale_from_amax) and records it for the conv kernels.
+// begin_count > 0: block (0, 0) also begins the pass over slots [begin_first, begin_first + begin_count) (scale_begin_kernel):
+// this is the first kernel of a forward pass.
 struct WeightScaleJob { const float* w; int n; int slot; };
 constexpr int kMaxScaleJobs = 24;
+constexpr int kWeightScaleBlocks = 16;
 struct WeightScaleJobs { WeightScaleJob j[kMaxScaleJobs]; };
-__global__ void weight_scale_kernel(const __grid_constant__ WeightScaleJobs jobs, ScaleState st) {
+__global__ void weight_scale_kernel(const __grid_constant__ WeightScaleJobs jobs, ScaleState st, int begin_first, int begin_count) {
   __shared__ float sm[32];
-  const WeightScaleJob& q = jobs.j[blockIdx.x];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < begin_count) { const int i = begin_first + threadIdx.x; st.k[i] = st.k_next[i]; st.amax[i] = 0u; }
+  const WeightScaleJob& q = jobs.j[blockIdx.y];
   float m = 0.f;
-  for (int i = threadIdx.x; i < q.n; i += blockDim.x) m = fmaxf(m, fabsf(__ldg(q.w + i)));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(__ldg(q.w + i)));
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sm[w]);
-    const unsigned a = __float_as_uint(m);
-    const int k = scale_for_amax(a < 0x7f800000u ? a : 0x7f7fffffu);
-    st.k[q.slot] = k; st.k_next[q.slot] = k; st.amax[q.slot] = a;
+    if (m > 0.f) atomicMax(&st.amax[q.slot], __float_as_uint(m));
   }
+}
+__device__ __forceinline__ int weight_scale_from_amax(const ScaleState& st, int slot) {
+  const unsigned a = st.amax[slot];
+  return scale_for_amax(a < 0x7f800000u ? a : 0x7f7fffffu);
 }
 
 // ---------------------------------------------------------------------------- weights
 // Builds the K-major weight slab [n_tile][chunk][tap][plane][N][CW] (plane 0 = hi, 1 = lo of the scaled fp16 split) from
 // PyTorch-layout weights W[cout][cin][taps].  transpose == 0 (forward):  slab[n][k] = W[n][k][tap]
 //                                           transpose == 1 (data-grad): slab[n][k] = W[k][n][tap]   (n = cin, k = cout)
-__device__ __forceinline__ void weight_prep_element(const float* __restrict__ w, __half* __restrict__ slab, int cin, int ntaps, int n_valid, int k_valid,
-                                                    int n_chunks, int N, int transpose, int CW, float s, long long idx) {
-  const int kk = (int)(idx % CW); long long t = idx / CW;
-  const int n = (int)(t % N); t /= N;                       // t = slab index ((nt * n_chunks + ch) * ntaps + tap)
-  const int tap = (int)(t % ntaps); const long long tc = t / ntaps;
-  const int ch = (int)(tc % n_chunks); const int nt = (int)(tc / n_chunks);
-  const int ng = nt * N + n, k = ch * CW + kk;
-  float val = 0.f;
-  if (ng < n_valid && k < k_valid) {
-    const long long wi = transpose ? ((long long)k * cin + ng) * ntaps + tap : ((long long)ng * cin + k) * ntaps + tap;
-    val = __ldg(w + wi);
+// One thread = 8 consecutive k of one slab row: one 16-byte store per plane, index arithmetic in 32 bits.
+__device__ __forceinline__ void weight_prep_vec8(const float* __restrict__ w, __half* __restrict__ slab, int cin, int ntaps, int n_valid, int k_valid,
+                                                 int n_chunks, int N, int transpose, int CW, float s, int idx) {
+  const int v8 = CW >> 3;
+  const int kk = (idx % v8) * 8; int t = idx / v8;
+  const int n = t % N; t /= N;                       // t = slab index ((nt * n_chunks + ch) * ntaps + tap)
+  const int tap = t % ntaps; const int tc = t / ntaps;
+  const int ch = tc % n_chunks; const int nt = tc / n_chunks;
+  const int ng = nt * N + n, k0 = ch * CW + kk;
+  float f[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int k = k0 + q;
+    float val = 0.f;
+    if (ng < n_valid && k < k_valid) val = __ldg(w + (transpose ? (k * cin + ng) * ntaps + tap : (ng * cin + k) * ntaps + tap));
+    f[q] = val * s;
   }
-  const long long o = ((t * 2) * N + n) * CW + kk;
-  f16_split1(val * s, slab[o], slab[o + (long long)N * CW]);
+  uint4 h, l;
+  f16_split8(f, h, l);
+  const long long o = ((long long)(t * 2) * N + n) * CW + kk;
+  *reinterpret_cast<uint4*>(slab + o) = h; *reinterpret_cast<uint4*>(slab + o + (long long)N * CW) = l;
 }
+// slot >= 0: the weights' scale exponent comes from st.amax[slot] (weight_scale_kernel ran before) and is recorded in st.k[slot]
 __global__ void weight_prep_kernel(const float* __restrict__ w, __half* __restrict__ slab, int cout, int cin, int ntaps,
-                                   int n_valid, int k_valid, int n_tiles, int n_chunks, int N, int transpose, int CW, const int* __restrict__ k_w) {
-  const long long total = (long long)n_tiles * n_chunks * ntaps * N * CW;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+                                   int n_valid, int k_valid, int n_tiles, int n_chunks, int N, int transpose, int CW, ScaleState st, int slot) {
+  const int total = n_tiles * n_chunks * ntaps * N * (CW >> 3);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = slot >= 0 ? weight_scale_from_amax(st, slot) : 0;
+  if (slot >= 0 && idx == 0) { st.k[slot] = k; st.k_next[slot] = k; }
   if (idx >= total) return;
-  weight_prep_element(w, slab, cin, ntaps, n_valid, k_valid, n_chunks, N, transpose, CW, k_w ? exp2_int(__ldg(k_w)) : 1.0f, idx);
+  weight_prep_vec8(w, slab, cin, ntaps, n_valid, k_valid, n_chunks, N, transpose, CW, exp2_int(k), idx);
 }
 
-// All weight slabs of a network in ONE launch: blockIdx.y selects the job, blockIdx.x strides over its elements.
-struct WeightPrepJob { const float* w; __half* slab; int cout, cin, ntaps, n_valid, k_valid, n_tiles, n_chunks, N, transpose, CW; const int* k_w; };
+// All weight slabs of a network in ONE launch: blockIdx.y selects the job, blockIdx.x strides over its 8-element vectors.
+struct WeightPrepJob { const float* w; __half* slab; int cout, cin, ntaps, n_valid, k_valid, n_tiles, n_chunks, N, transpose, CW; int slot; };
 constexpr int kMaxPrepJobs = 48;
 struct WeightPrepJobs { WeightPrepJob j[kMaxPrepJobs]; };
-__global__ void weight_prep_batched_kernel(const __grid_constant__ WeightPrepJobs jobs) {
+__global__ void weight_prep_batched_kernel(const __grid_constant__ WeightPrepJobs jobs, ScaleState st) {
   const WeightPrepJob& q = jobs.j[blockIdx.y];
-  const long long total = (long long)q.n_tiles * q.n_chunks * q.ntaps * q.N * q.CW;
-  const float s = q.k_w ? exp2_int(__ldg(q.k_w)) : 1.0f;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
-    weight_prep_element(q.w, q.slab, q.cin, q.ntaps, q.n_valid, q.k_valid, q.n_chunks, q.N, q.transpose, q.CW, s, idx);
+  const int total = q.n_tiles * q.n_chunks * q.ntaps * q.N * (q.CW >> 3);
+  const int k = weight_scale_from_amax(st, q.slot);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !q.transpose) { st.k[q.slot] = k; st.k_next[q.slot] = k; }    // the forward slab's job records it
+  const float s = exp2_int(k);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    weight_prep_vec8(q.w, q.slab, q.cin, q.ntaps, q.n_valid, q.k_valid, q.n_chunks, q.N, q.transpose, q.CW, s, idx);
 }
 
 // ---------------------------------------------------------------------------- bias gradient

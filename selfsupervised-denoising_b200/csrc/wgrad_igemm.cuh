@@ -44,7 +44,7 @@ struct WgradParams {
 
 struct WgradPlan {
   WgradParams p;
-  double flops = 0;
+  double flops = 0, bytes = 0;
   CUtensorMap dz, x;   // 4-D fp16 maps (64 channels, flat pixel, channel block, plane): ONE TMA op per operand per stage
   int grid; size_t smem;
 };
@@ -269,11 +269,44 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
     }
   }
 }
+// All weight gradients of a network in ONE launch at the end of the backward pass (every layer keeps its own partial
+// buffer): a block finds its job from the prefix sums of the jobs' block counts, then works like wgrad_reduce_kernel.
+struct WgradReduceJob { const float* partial; float* dw; int ksplit, ntaps, cout, cin, pitch, first_block; };
+constexpr int kMaxReduceJobs = 24;
+struct WgradReduceJobs { WgradReduceJob j[kMaxReduceJobs]; int n_jobs; };
+__global__ void __launch_bounds__(512) wgrad_reduce_batched_kernel(const __grid_constant__ WgradReduceJobs jobs) {
+  __shared__ float sm[16][33];
+  int ji = 0;
+  while (ji + 1 < jobs.n_jobs && (int)blockIdx.x >= jobs.j[ji + 1].first_block) ++ji;
+  const WgradReduceJob& q = jobs.j[ji];
+  const long long n = (long long)q.cout * q.pitch * q.ntaps;
+  const long long idx = ((long long)blockIdx.x - q.first_block) * 32LL + threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (idx < n) {
+    int k = threadIdx.y;
+    for (; k + 48 < q.ksplit; k += 64) {
+      a0 += __ldg(q.partial + (long long)k * n + idx); a1 += __ldg(q.partial + (long long)(k + 16) * n + idx);
+      a2 += __ldg(q.partial + (long long)(k + 32) * n + idx); a3 += __ldg(q.partial + (long long)(k + 48) * n + idx);
+    }
+    for (; k < q.ksplit; k += 16) a0 += __ldg(q.partial + (long long)k * n + idx);
+  }
+  sm[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (threadIdx.y == 0 && idx < n) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) acc += sm[w][threadIdx.x];
+    const int ci = (int)(idx % q.pitch); long long t = idx / q.pitch;
+    const int co = (int)(t % q.cout); const int tap = (int)(t / q.cout);
+    if (ci < q.cin) q.dw[((long long)co * q.cin + ci) * q.ntaps + tap] = acc;
+  }
+}
 static inline int wgrad_cin_pitch(int cin) { return (cin + 3) / 4 * 4; }
 static inline void wgrad_reduce_launch(const float* partial, int ksplit, int ntaps, int cout, int cin, int pitch, float* dw, int accumulate,
                                        cudaStream_t st) {
   const long long n = (long long)cout * pitch * ntaps;
-  wgrad_reduce_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 16), 0, st>>>(partial, ksplit, ntaps, cout, cin, pitch, dw, accumulate);
+  SSDN_PROF(K_WGRAD_REDUCE, 0, (double)n * 4 * (ksplit + 1), st,
+            (wgrad_reduce_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 16), 0, st>>>(partial, ksplit, ntaps, cout, cin, pitch, dw, accumulate)));
 }
 
 }  // namespace wgradk
@@ -383,7 +416,7 @@ static inline cudaError_t wgrad_launch(const WgradPlan& plan, cudaStream_t strea
     if (!dev) cudaMalloc(&dev, 1024 * 16 * sizeof(unsigned long long));
     cudaMemsetAsync(dev, 0, 1024 * 16 * sizeof(unsigned long long), stream);
     WgradParams p = plan.p; p.stats = dev;
-    profiler().begin(2, plan.flops, stream);
+    profiler().begin(K_WGRAD, plan.flops, plan.bytes, stream);
     wgradk::wgrad_igemm_kernel<<<plan.grid, wgradk::kThreads, plan.smem, stream>>>(plan.dz, plan.x, p);
     profiler().end(stream);
     std::vector<unsigned long long> h((size_t)plan.grid * 16);
@@ -396,7 +429,7 @@ static inline cudaError_t wgrad_launch(const WgradPlan& plan, cudaStream_t strea
             p.chunks_per_split, p.stages, p.nba, p.nbx, p.b_rows, s[3], 100 * s[1] / s[3], 100 * s[2] / s[3], 100 * s[0] / s[3], s[5], 100 * s[4] / s[5]);
     return e != cudaSuccess ? e : cudaGetLastError();
   }
-  if (profiler().on) profiler().begin(2, plan.flops, stream);
+  if (profiler().on) profiler().begin(K_WGRAD, plan.flops, plan.bytes, stream);
   wgradk::wgrad_igemm_kernel<<<plan.grid, wgradk::kThreads, plan.smem, stream>>>(plan.dz, plan.x, plan.p);
   if (profiler().on) profiler().end(stream);
   return cudaGetLastError();

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "ssdn_net_check": (_I, [_P, _P]),
     "ssdn_net_kernel_launches": (_I, [_P, _I]),
     "ssdn_profile_begin": (_I, []),
+    "ssdn_profile_kinds": (_I, []),
     "ssdn_profile_end": (_I, [ctypes.POINTER(c_double)]),
     "ssdn_profile_records": (_I, [ctypes.POINTER(c_double), _I]),
     "ssdn_net_debug_write": (_I, [_P, ctypes.c_char_p, _I, _P, _P]),
@@ -358,19 +359,24 @@ def profile_begin():
     check(lib().ssdn_profile_begin())
 
 
+PROFILE_KINDS = ("conv_fwd", "conv_dgrad", "wgrad", "wgrad_reduce", "pool_fwd", "pool_bwd", "up_bwd", "pack", "weight_prep", "bias", "scale",
+                 "posterior_fwd", "posterior_bwd", "adam", "other")
+
+
 def profile_end():
-    """-> {kind: (launches, device ms, algorithmic FLOPs)} for kinds conv_fwd / conv_dgrad / wgrad."""
-    buf = (c_double * 9)()
+    """-> {kind: (launches, device ms, algorithmic FLOPs, algorithmic HBM bytes)} for every kind that launched."""
+    nk = lib().ssdn_profile_kinds()
+    assert nk == len(PROFILE_KINDS)
+    buf = (c_double * (4 * nk))()
     check(lib().ssdn_profile_end(buf))
-    return {k: (int(buf[3 * i]), buf[3 * i + 1], buf[3 * i + 2]) for i, k in enumerate(("conv_fwd", "conv_dgrad", "wgrad"))}
+    return {k: (int(buf[4 * i]), buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]) for i, k in enumerate(PROFILE_KINDS) if buf[4 * i] > 0}
 
 
-def profile_records(max_records=512):
-    """[(kind, ms, algorithmic FLOPs)] per tensor-core launch of the last profiled region, in launch order."""
-    buf = (c_double * (3 * max_records))()
+def profile_records(max_records=1024):
+    """[(kind, ms, algorithmic FLOPs, algorithmic bytes)] per launch of the last profiled region, in launch order."""
+    buf = (c_double * (4 * max_records))()
     n = min(lib().ssdn_profile_records(buf, max_records), max_records)
-    kinds = ("conv_fwd", "conv_dgrad", "wgrad")
-    return [(kinds[int(buf[3 * i])], buf[3 * i + 1], buf[3 * i + 2]) for i in range(n)]
+    return [(PROFILE_KINDS[int(buf[4 * i])], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]) for i in range(n)]
 
 
 def noisy_crops(images_u8, n, patch, seed, step, sigma_lo, sigma_hi=None, clip=True, order=None, stream_id=0, want_clean=True):
