@@ -221,7 +221,7 @@ def workload_name(config, scaling):
 class Case:
     """One configuration on this rank: Denoiser + optimiser + a resident batch + a pinned host copy of it."""
 
-    def __init__(self, config, n_local, device, rank, world):
+    def __init__(self, config, n_local, device, rank, world, graph=True):
         import torch
         import ssdn
         from ssdn.datasets import NoisyDataset
@@ -237,15 +237,30 @@ class Case:
         self.host = [noisy.pin_memory(), ref.pin_memory() if ref.numel() else ref, {k: v.pin_memory() for k, v in md.items()}]
         self.host_loss = torch.empty(n_local, 1).pin_memory()
         self.h2d = int(sum(t.numel() * t.element_size() for t in [noisy, ref] + list(md.values())))
+        self.graph = graph
+        self.graphed = None
 
-    def step_resident(self):
+    def capture(self):
+        """After the eager warm-up steps: one CUDA graph of the whole step (ssdn.train.GraphedTrainStep)."""
+        from ssdn.train import GraphedTrainStep
+        if self.graph and self.graphed is None:
+            self.graphed = GraphedTrainStep(self.den, self.opt, self.dev_data, self.world, warmup=1)
+
+    def step_eager(self):
         from ssdn.train import train_step
         train_step(self.den, self.opt, self.dev_data, self.world)
+
+    def step_resident(self):
+        if self.graphed is not None:
+            self.graphed(self.dev_data)
+        else:
+            self.step_eager()
 
     def step_e2e(self):
         from ssdn.params import PipelineOutput
         from ssdn.train import train_step
-        out = train_step(self.den, self.opt, [self.host[0], self.host[1], dict(self.host[2])], self.world)
+        data = [self.host[0], self.host[1], dict(self.host[2])]
+        out = self.graphed(data) if self.graphed is not None else train_step(self.den, self.opt, data, self.world)
         # D2H read of the step's result into pinned memory.  Asynchronous, like a trainer that logs without stalling the
         # device: every copy is enqueued inside the timed region and completes before timed()'s final synchronize.
         self.host_loss.copy_(out[PipelineOutput.LOSS].detach(), non_blocking=True)
@@ -278,13 +293,14 @@ class Case:
         return float(d.item())
 
 
-def short_run(config, scaling, device, rank, world, dist_on, steps=8, warmup=4):
+def short_run(config, scaling, device, rank, world, dist_on, graph, steps=8, warmup=4):
     """A short measurement of another configuration / scaling mode (rides along in the main JSON line)."""
     gbatch = CONFIGS[config][4]
     n_local = gbatch if scaling == "weak" else max(1, gbatch // world)
-    case = Case(config, n_local, device, rank, world)
+    case = Case(config, n_local, device, rank, world, graph)
     for _ in range(warmup):
         case.step_resident()
+    case.capture()
     stale0 = case.check()
     t = timed(case.step_resident, steps, device, dist_on)
     for _ in range(2):
@@ -293,7 +309,7 @@ def short_run(config, scaling, device, rank, world, dist_on, steps=8, warmup=4):
     stale = case.check() - stale0
     total = n_local * world
     gf = TRAIN_GFLOP_PER_PATCH[config]
-    return {"workload": workload_name(config, scaling), "per_gpu_batch": n_local, "global_batch": total, "steps": steps,
+    return {"workload": workload_name(config, scaling), "per_gpu_batch": n_local, "global_batch": total, "steps": steps, "cuda_graph": bool(graph),
             "value": total * steps / t, "unit": "patches/s", "ms_per_step": t / steps * 1e3,
             "e2e": {"value": total * steps / te, "ms_per_step": te / steps * 1e3, "h2d_bytes_per_step": case.h2d, "d2h_bytes_per_step": n_local * 4},
             "step_algorithmic_tflops_per_gpu": gf * 1e9 * n_local / (t / steps) / 1e12, "stale_scale_passes": stale,
@@ -315,9 +331,11 @@ def run_engine(args):
         dist.init_process_group("nccl", device_id=device)
     gbatch = CONFIGS[args.config][4]
     n_local = gbatch if args.scaling == "weak" else max(1, gbatch // world)
-    case = Case(args.config, n_local, device, rank, world)
+    graph = not args.no_graph
+    case = Case(args.config, n_local, device, rank, world, graph)
     for _ in range(max(3, args.warmup)):
         case.step_resident()
+    case.capture()
     stale0 = case.check()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -331,7 +349,7 @@ def run_engine(args):
     spread = case.param_spread(dist_on)
     # one profiled step: CUDA events around every kernel launch (everything on one stream)
     E.profile_begin()
-    case.step_resident()
+    case.step_eager()
     prof = E.profile_end()
     case.check()
     loss_val = float(case.host_loss.detach().mean())
@@ -342,9 +360,9 @@ def run_engine(args):
         del case
         torch.cuda.empty_cache()
         if dist_on and args.scaling == "weak":
-            extras["strong"] = short_run(args.config, "strong", device, rank, world, dist_on)
+            extras["strong"] = short_run(args.config, "strong", device, rank, world, dist_on, graph)
         others = [c for c in ("var", "n2v", "var128") if c != args.config]
-        extras["configs"] = {c: short_run(c, "weak", device, rank, world, dist_on) for c in others}
+        extras["configs"] = {c: short_run(c, "weak", device, rank, world, dist_on, graph) for c in others}
     peak = None
     if rank == 0:
         try:
@@ -406,6 +424,7 @@ def run_engine(args):
         "dtype": "f16x2 split (two scaled fp16 planes per operand, 3 kind::f16 MMAs per product, fp32 accumulate: fp32-grade results)",
         "data": "synthetic",
         "config": {"workload": workload_name(args.config, args.scaling), "per_gpu_batch": n_local, "global_batch": total, "parallelism": f"dp{world}",
+                   "cuda_graph": bool(graph),
                    "l2": "per-step working set ~2.7 GB of activations >> 126 MB L2 (no explicit flush needed)",
                    "train_gflop_per_patch": TRAIN_GFLOP_PER_PATCH[args.config], "final_loss": loss_val},
         "clocks": clocks,
@@ -437,6 +456,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--config", default="known", choices=list(CONFIGS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step from Python instead of replaying one CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other configurations / strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiling runs)")
     args = ap.parse_args()

@@ -128,6 +128,11 @@ int ssdn_masked_mse_backward(const float* out, const float* ref, const long long
 int ssdn_adam_step(float* p, const float* g, float* m, float* v, long long count, double lr, double beta1, double beta2, double eps,
                    long long step, double grad_scale, const float* skip, int n_skip, void* stream);
 
+/* The same update with the step-dependent scalars in DEVICE memory: hyper6 = {lr / (1 - beta1^step), beta1, beta2, eps,
+ * sqrt(1 - beta2^step), grad_scale}.  A CUDA graph holding this launch can be replayed for every step (ssdn.train.GraphedTrainStep). */
+int ssdn_adam_step_dev(float* p, const float* g, float* m, float* v, long long count, const float* hyper6, const float* skip, int n_skip,
+                       void* stream);
+
 /* ---- measured tensor roofline (bench.py) ------------------------------------------------------------------------------
  * Full-chip sustained tcgen05.mma rate, kind::f16 (f16 != 0) or kind::tf32: every SM issues back-to-back M = 128 / 256,
  * N = 256 MMAs on shared-memory-resident operands for `seconds` per configuration.  Synchronous.

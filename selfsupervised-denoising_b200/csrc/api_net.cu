@@ -278,6 +278,16 @@ extern "C" int ssdn_adam_step(float* p, const float* g, float* m, float* v, long
   return 0;
 }
 
+extern "C" int ssdn_adam_step_dev(float* p, const float* g, float* m, float* v, long long count, const float* hyper6, const float* skip,
+                                  int n_skip, void* stream) {
+  if (!hyper6) return fail(-1, "null hyper-parameter buffer");
+  if (n_skip < 0 || n_skip > 8) return fail(-1, "at most 8 skip flags");
+  SSDN_PROF(K_ADAM, 0, 28.0 * count, (cudaStream_t)stream,
+            (lossk::adam_dev_kernel<<<pw::grid_for(count), pw::kBlock, 0, (cudaStream_t)stream>>>(p, g, m, v, count, hyper6, skip, skip ? n_skip : 0)));
+  SSDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ on-GPU input pipeline
 extern "C" int ssdn_noisy_crops(const unsigned char* images, int n_images, int c, int h, int w, const int* order, int n, int patch,
                                 unsigned long long seed, unsigned long long step, int stream_id, float sigma_lo, float sigma_hi, int clip,

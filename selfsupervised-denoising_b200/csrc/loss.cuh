@@ -318,20 +318,33 @@ __global__ void masked_mse_bwd_kernel(const float* __restrict__ out, const float
 // ---------------------------------------------------------------- Adam over a flat parameter buffer
 // torch.optim.Adam(betas=(0.9, 0.99), eps=1e-8) as used by train.py:100-107; grad_scale folds the 1/world_size of the
 // data-parallel all-reduce.  bc1 = 1 - beta1^t, bc2_sqrt = sqrt(1 - beta2^t) are computed on the host in fp64.
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float step_size, float beta1, float beta2, float eps, float bc2_sqrt, float grad_scale,
-                            const float* __restrict__ skip, int n_skip) {
-  // skip[0 .. n_skip): "this step's gradients are stale" flags left behind by the networks' backward passes (summed over ranks
-  // by the gradient all-reduce): any non-zero flag turns the whole update into a no-op
-  for (int j = 0; j < n_skip; ++j) if (__ldg(skip + j) != 0.f) return;
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void adam_update(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                            long long i, float step_size, float beta1, float beta2, float eps, float bc2_sqrt, float grad_scale) {
   const float gr = g[i] * grad_scale;
   const float mm = m[i] * beta1 + (1.f - beta1) * gr;       // exp_avg.mul_(b1).add_(g, alpha=1-b1)   [lerp form equals this to 1 ulp]
   const float vv = v[i] * beta2 + (1.f - beta2) * gr * gr;  // exp_avg_sq.mul_(b2).addcmul_(g, g, value=1-b2)
   m[i] = mm; v[i] = vv;
   const float denom = sqrtf(vv) / bc2_sqrt + eps;
   p[i] = p[i] - step_size * (mm / denom);
+}
+// skip[0 .. n_skip): "this step's gradients are stale" flags left behind by the networks' backward passes (summed over ranks
+// by the gradient all-reduce): any non-zero flag turns the whole update into a no-op
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float step_size, float beta1, float beta2, float eps, float bc2_sqrt, float grad_scale,
+                            const float* __restrict__ skip, int n_skip) {
+  for (int j = 0; j < n_skip; ++j) if (__ldg(skip + j) != 0.f) return;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  adam_update(p, g, m, v, i, step_size, beta1, beta2, eps, bc2_sqrt, grad_scale);
+}
+// The same update with the step-dependent scalars read from DEVICE memory (hyper = {lr / bias_correction1, beta1, beta2, eps,
+// sqrt(bias_correction2), grad_scale}): a CUDA graph that contains this launch can be replayed for every step.
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n, const float* __restrict__ hyper, const float* __restrict__ skip, int n_skip) {
+  for (int j = 0; j < n_skip; ++j) if (__ldg(skip + j) != 0.f) return;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  adam_update(p, g, m, v, i, __ldg(hyper), __ldg(hyper + 1), __ldg(hyper + 2), __ldg(hyper + 3), __ldg(hyper + 4), __ldg(hyper + 5));
 }
 
 }  // namespace lossk

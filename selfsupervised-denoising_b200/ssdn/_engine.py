@@ -53,6 +53,7 @@ _SIGNATURES = {
     "ssdn_masked_mse_forward": (_I, [_P, _P, _P, _P] + [_I] * 5 + [_P, _P]),
     "ssdn_masked_mse_backward": (_I, [_P, _P, _P, _I, _P] + [_I] * 4 + [_P, _P]),
     "ssdn_adam_step": (_I, [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _LL, _D, _P, _I, _P]),
+    "ssdn_adam_step_dev": (_I, [_P, _P, _P, _P, _LL, _P, _P, _I, _P]),
     "ssdn_tensor_peak": (_I, [_I, _D, ctypes.POINTER(c_double), _P]),
     "ssdn_n2v_mask": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, ctypes.c_ulonglong, ctypes.c_ulonglong, _P]),
     "ssdn_noisy_crops": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, ctypes.c_ulonglong, ctypes.c_ulonglong, _I, ctypes.c_float, ctypes.c_float, _I,
@@ -346,6 +347,12 @@ def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.99, eps=1e-8, grad_scale=
     skip: optional CUDA float tensor (<= 8 values); the update is a no-op when any of them is non-zero (stale-gradient flags)."""
     check(lib().ssdn_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), beta1, beta2, eps, int(step),
                                float(grad_scale), _ptr(skip), 0 if skip is None else skip.numel(), _stream()))
+
+
+def adam_step_dev(p, g, m, v, hyper, skip=None):
+    """adam_step with {lr / bias_correction1, beta1, beta2, eps, sqrt(bias_correction2), grad_scale} in the CUDA tensor `hyper`."""
+    check(lib().ssdn_adam_step_dev(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(hyper), _ptr(skip), 0 if skip is None else skip.numel(),
+                                   _stream()))
 
 
 def tensor_peak(f16=True, seconds=1.0):

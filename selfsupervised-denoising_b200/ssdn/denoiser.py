@@ -226,7 +226,8 @@ class Denoiser(nn.Module):
             with torch.cuda.stream(est_stream):
                 est = self.models[Denoiser.SIGMA_ESTIMATOR](noisy)
                 sigma_est = SpatialMeanFunction.apply(est).reshape(n, 1)
-            noisy.record_stream(est_stream)
+            if not torch.cuda.is_current_stream_capturing():
+                noisy.record_stream(est_stream)
         net_out = self.models[Denoiser.MODEL](noisy)
         if mode == NoiseValue.KNOWN:
             sigma_raw = md[NoisyDataset.Metadata.INPUT_NOISE_VALUES].to(self.device, non_blocking=True).float().reshape(n, -1)
@@ -238,7 +239,8 @@ class Denoiser(nn.Module):
             if est_stream is not None:
                 torch.cuda.current_stream(noisy.device).wait_stream(est_stream)
                 sigma_raw = sigma_est
-                sigma_raw.record_stream(torch.cuda.current_stream(noisy.device))
+                if not torch.cuda.is_current_stream_capturing():
+                    sigma_raw.record_stream(torch.cuda.current_stream(noisy.device))
             else:
                 est = self.models[Denoiser.SIGMA_ESTIMATOR](noisy)
                 sigma_raw = SpatialMeanFunction.apply(est).reshape(n, 1)

@@ -56,6 +56,20 @@ class FlatAdam:
         E.adam_step(flat, grads, self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count, g["betas"][0], g["betas"][1], g["eps"],
                     grad_scale, skip=self.denoiser.stale_flags())
 
+    # ---- the same step with its scalars in device memory (what a CUDA graph of the step launches)
+    def hyper_values(self, grad_scale: float = 1.0):
+        """{lr / bias_correction1, beta1, beta2, eps, sqrt(bias_correction2), grad_scale} of the CURRENT step_count."""
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        return [g["lr"] / (1.0 - b1 ** self.step_count), b1, b2, g["eps"], (1.0 - b2 ** self.step_count) ** 0.5, grad_scale]
+
+    def step_dev(self, hyper: torch.Tensor):
+        """Launch the update with scalars read from `hyper` (CUDA float[6]); the caller advances step_count and fills hyper."""
+        flat = self.denoiser.flat_parameters()
+        grads = self.denoiser.flat_gradients()
+        self._ensure_state(flat)
+        E.adam_step_dev(flat, grads, self.exp_avg, self.exp_avg_sq, hyper, skip=self.denoiser.stale_flags())
+
     def state_dict(self) -> Dict:
         """Wire format of ``torch.optim.Adam.state_dict()`` - what the reference stores under ``"optimizer"`` in a
         ``.training`` file (train.py:724): per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` keyed by the parameter's
@@ -127,6 +141,65 @@ def train_step(denoiser: Denoiser, optimizer: FlatAdam, data: List, world_size: 
         dist.all_reduce(denoiser.flat_gradients_with_flags(), op=dist.ReduceOp.SUM)
     optimizer.step(grad_scale=1.0 / world_size)
     return outputs
+
+
+class GraphedTrainStep:
+    """train_step for a FIXED batch shape as ONE CUDA-graph launch: zero_grad -> run_pipeline -> mean(loss).backward() ->
+    (gradient all-reduce) -> Adam are captured once (after eager warm-up steps that also settle the operand scales) and
+    replayed for every batch.  A step is ~110 kernel launches; on the small per-GPU batches of strong scaling their launch
+    cost, not the device work, is what bounds the eager step.  Inputs are copied into the graph's static buffers, the step's
+    scalars (learning rate, Adam bias corrections, 1 / world_size) live in a device buffer that is refreshed before each replay.
+    The returned outputs are the graph's static tensors: read (or copy) them before the next call."""
+
+    def __init__(self, denoiser: Denoiser, optimizer: FlatAdam, example: List, world_size: int = 1, warmup: int = 3):
+        self.denoiser, self.optimizer, self.world_size = denoiser, optimizer, world_size
+        dev = denoiser.device
+        to_dev = lambda t: t.to(dev).clone() if torch.is_tensor(t) and t.numel() else t     # noqa: E731
+        md = example[NoisyDataset.METADATA] if len(example) > NoisyDataset.METADATA else {}
+        self.static = [to_dev(example[0]), to_dev(example[1]) if len(example) > 1 else None,
+                       {k: to_dev(v) for k, v in md.items() if k != NoisyDataset.Metadata.CLEAN}]
+        self.hyper = torch.zeros(6, dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):            # eager steps: lazily created streams / attributes / settled operand scales
+                self._refresh_hyper()
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self._refresh_hyper()
+        with torch.cuda.graph(self.graph):
+            self.outputs = self._body()
+        # the captured launch itself did not execute: run it once so that step_count and the weights agree
+        self.graph.replay()
+
+    def _refresh_hyper(self):
+        self.optimizer.step_count += 1
+        # from pageable memory on purpose: the driver stages the six floats before the call returns, so the next refresh
+        # cannot overwrite them while an earlier replay is still queued
+        self.hyper.copy_(torch.tensor(self.optimizer.hyper_values(1.0 / self.world_size), dtype=torch.float32))
+
+    def _body(self):
+        self.optimizer.zero_grad()
+        outputs = self.denoiser.run_pipeline(self.static)
+        torch.mean(outputs[PipelineOutput.LOSS]).backward()
+        if self.world_size > 1:
+            dist.all_reduce(self.denoiser.flat_gradients_with_flags(), op=dist.ReduceOp.SUM)
+        self.optimizer.step_dev(self.hyper)
+        return outputs
+
+    def __call__(self, data: List) -> Dict:
+        self.static[0].copy_(data[0], non_blocking=True)
+        if self.static[1] is not None and torch.is_tensor(self.static[1]) and self.static[1].numel():
+            self.static[1].copy_(data[1], non_blocking=True)
+        md = data[NoisyDataset.METADATA] if len(data) > NoisyDataset.METADATA else {}
+        for k, v in self.static[2].items():
+            if torch.is_tensor(v) and k in md:
+                v.copy_(md[k], non_blocking=True)
+        self._refresh_hyper()
+        self.graph.replay()
+        return self.outputs
 
 
 def learning_rate(cfg: Dict, iteration: int) -> float:
