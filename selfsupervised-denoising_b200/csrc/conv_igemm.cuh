@@ -292,14 +292,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const uint32_t b0 = (((b_base + rb.stage * b_stage_bytes) >> 4) & 0x3fffu) | lbo_bits;
           if (umma::elect_one()) {
 #pragma unroll
-            for (int tile = 0; tile < T; ++tile) {
-              const uint32_t d = d0 + tile * p.N;
+            for (int k = 0; k < 4; ++k) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t av = a0 + tile * 1024 + 2 * k, al = av + a_pl, bv = b0 + 2 * k, bl = bv + b_pl;
-                mma(d, al, bv, desc_hi, k == 0 ? first : 1u);
-                mma(d, av, bl, desc_hi, 1);
-                mma(d, av, bv, desc_hi, 1);
+              for (int prod = 0; prod < 3; ++prod) {
+#pragma unroll
+                for (int tile = 0; tile < T; ++tile) {          // tiles innermost: consecutive MMAs alternate accumulators
+                  const uint32_t d = d0 + tile * p.N;
+                  const uint32_t av = a0 + tile * 1024 + 2 * k, al = av + a_pl, bv = b0 + 2 * k, bl = bv + b_pl;
+                  mma(d, prod == 0 ? al : av, prod == 1 ? bl : bv, desc_hi, (k == 0 && prod == 0) ? first : 1u);
+                }
               }
             }
             commit(empty_b(rb.stage));
@@ -338,20 +339,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               const uint32_t a0 = (((a_stage + p.groups[g].tap_rel[3 * r] * 64) >> 4) & 0x3fffu) | lbo_bits;
               const uint32_t b0 = (((b_base + rb.stage * b_stage_bytes) >> 4) & 0x3fffu) | lbo_bits;
               if (umma::elect_one()) {
+                // consecutive MMAs go to DIFFERENT accumulators (tiles alternate): back-to-back accumulation into one
+                // accumulator exposes the tensor pipe's accumulate latency (profiles/r02_f16_probe.log F7 vs r02_umma_peak.log)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                   const uint32_t aj = a0 + j * step, bj = b0 + j * slab;
 #pragma unroll
-                  for (int tile = 0; tile < T; ++tile) {
-                    const uint32_t d = d0 + tile * p.N;
-                    const uint32_t av = aj + tile * 512, al = av + a_pl, bv = bj, bl = bj + b_pl;
-                    mma(d, al, bv, desc_hi, (j == 0) ? first : 1u);
-                    mma(d, av, bl, desc_hi, 1);
-                    mma(d, av, bv, desc_hi, 1);
-                    if (two) {
-                      mma(d, al + 2, bv + 2, desc_hi, 1);
-                      mma(d, av + 2, bl + 2, desc_hi, 1);
-                      mma(d, av + 2, bv + 2, desc_hi, 1);
+                  for (int q = 0; q < 6; ++q) {           // q = k-step * 3 + product (lo*hi, hi*lo, hi*hi)
+                    if (q < 3 || two) {
+                      const uint32_t ko = (q >= 3) ? 2u : 0u, prod = q % 3;
+#pragma unroll
+                      for (int tile = 0; tile < T; ++tile) {
+                        const uint32_t d = d0 + tile * p.N;
+                        const uint32_t av = aj + tile * 512 + ko, al = av + a_pl, bv = bj + ko, bl = bv + b_pl;
+                        mma(d, prod == 0 ? al : av, prod == 1 ? bl : bv, desc_hi, (j == 0 && q == 0) ? first : 1u);
+                      }
                     }
                   }
                 }

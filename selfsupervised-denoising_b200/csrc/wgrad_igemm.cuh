@@ -145,17 +145,19 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
         if (unit_step || ntaps == 1) {
           const uint32_t b0 = (((bv0 + p.groups[g].tap_rel[0] * 128) >> 4) & 0x3fffu) | b_lbo;
           if (umma::elect_one()) {
+            // taps innermost: consecutive MMAs accumulate into DIFFERENT accumulators (see conv_igemm.cuh)
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-              if (t < ntaps) {
-                const uint32_t d = tmem + t * N;
+            for (int k = 0; k < 4; ++k) {              // k-steps of 16 pixels (2048 bytes = 128 units); a tap shifts X by one row (8 units)
+              if (k < nk) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {          // k-steps of 16 pixels (2048 bytes = 128 units); a tap shifts X by one row (8 units)
-                  if (k < nk) {
-                    const uint32_t ah = a0 + k * 128, al = ah + a_pl, bh = b0 + t * 8 + k * 128, bl = bh + b_pl;
-                    umma::mma_f16_lo(d, al, bh, desc_hi, idesc, k == 0 ? acc : 1u);
-                    umma::mma_f16_lo(d, ah, bl, desc_hi, idesc, 1);
-                    umma::mma_f16_lo(d, ah, bh, desc_hi, idesc, 1);
+                for (int prod = 0; prod < 3; ++prod) {
+#pragma unroll
+                  for (int t = 0; t < 3; ++t) {
+                    if (t < ntaps) {
+                      const uint32_t d = tmem + t * N;
+                      const uint32_t ah = a0 + k * 128, al = ah + a_pl, bh = b0 + t * 8 + k * 128, bl = bh + b_pl;
+                      umma::mma_f16_lo(d, prod == 0 ? al : ah, prod == 1 ? bl : bh, desc_hi, idesc, (k == 0 && prod == 0) ? acc : 1u);
+                    }
                   }
                 }
               }
@@ -320,7 +322,8 @@ static inline int wgrad_n_ci_blocks(int cin, int ntaps) { const int c16 = (cin +
 static inline size_t wgrad_partial_floats(int ksplit, int ntaps, int cout, int cin) {
   return (size_t)ksplit * ntaps * cout * ((cin + 3) / 4 * 4);
 }
-static inline int wgrad_kc() { static const int kc = getenv("SSDN_WGRAD_KC") ? atoi(getenv("SSDN_WGRAD_KC")) : 32; return kc == 64 ? 64 : 32; }
+// pixels per pipeline stage: 64 (4 k-steps per barrier round trip) measured 10 % faster over the step than 32 (profiles/r02_layer_times.log)
+static inline int wgrad_kc() { static const int kc = getenv("SSDN_WGRAD_KC") ? atoi(getenv("SSDN_WGRAD_KC")) : 64; return kc == 32 ? 32 : 64; }
 
 // Decides the K split for a layer (so that the grid fills the chip) without needing pointers.
 static inline int wgrad_pick_ksplit(long long k_total, int cout, int cin, int ntaps, int num_sms) {
