@@ -39,6 +39,15 @@ size_t ssdn_conv2d_backward_weight_workspace_bytes(int n, int cin, int h, int w,
 int ssdn_conv2d_backward_weight(void* ws, size_t ws_bytes, const float* x, const float* dy, float* dw, float* db,
                                 int n, int cin, int h, int wd, int cout, int ksize, int blind, void* stream);
 
+/* ---- shifted max-pool — models/noise_network.py:64-67 --------------------------------------------------------
+ * y = MaxPool2d(2)(Shift2d((1,0))(x)) (blind != 0) or MaxPool2d(2)(x): x [n][c][h][w] -> y [n][c][h/2][w/2], c % 8 == 0.
+ * With dy / dz non-NULL also the backward of [LeakyReLU(0.1) -> (shift) -> max-pool] as the network runs it: x is the
+ * ACTIVATION LeakyReLU(z); dz = d(loss)/dz given dy (first maximum wins ties as in ATen's max_pool2d; a winning padding
+ * zero swallows the gradient).  Synchronous. */
+size_t ssdn_maxpool2_workspace_bytes(int n, int c, int h, int w);
+int ssdn_maxpool2(void* ws, size_t ws_bytes, const float* x, float* y, const float* dy, float* dz, int n, int c, int h, int w, int blind,
+                  void* stream);
+
 /* ---- index operators ------------------------------------------------------------------------------------
  * ssdn.utils.rotate x4 + torch.cat(dim=0) — models/noise_network.py:187-189, utils/data.py:42-67.
  *   y[r*n + b] = rotate(x[b], 90*r), x [n][c][h][w] (h == w), y [4n][c][h][w].  Bit exact. */

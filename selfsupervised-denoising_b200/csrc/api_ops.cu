@@ -178,6 +178,56 @@ extern "C" int ssdn_conv2d_backward_weight(void* ws, size_t ws_bytes, const floa
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ shifted max-pool (operator level)
+// nn.Sequential(Shift2d((1, 0)), nn.MaxPool2d(2)) / nn.MaxPool2d(2) - models/noise_network.py:64-67 - through the network's own
+// pool kernels: x [n][c][h][w] -> y [n][c][h/2][w/2], c a multiple of 8.  Synchronous.
+extern "C" size_t ssdn_maxpool2_workspace_bytes(int n, int c, int h, int w) {
+  Geom gs = make_geom(n, h, w, true), gd = make_geom(n, h / 2, w / 2, true);
+  Arena a(nullptr, 0);
+  a.take<__half>(2 * (((size_t)gs.total() * c + 127) / 128 * 128) + 256); a.take<__half>(2 * (((size_t)gs.total() * c + 127) / 128 * 128) + 256);
+  a.take<__half>(2 * (((size_t)gd.total() * c + 127) / 128 * 128) + 256); a.take<float>((size_t)gd.total() * c);
+  take_scales(a);
+  return a.off + 4096;
+}
+// forward: y = maxpool(shift(x)).  backward (dy != NULL): also dz = d(loss)/dz for x = LeakyReLU(z) given dy = d(loss)/dy, i.e. the
+// backward of [LeakyReLU -> (shift) -> max-pool] as the network runs it (first maximum wins ties, a winning padding zero
+// swallows the gradient).  y or (dy, dz) may be NULL.
+extern "C" int ssdn_maxpool2(void* ws, size_t ws_bytes, const float* x, float* y, const float* dy, float* dz, int n, int c, int h, int w, int blind,
+                             void* stream) {
+  if (c % 8 || h % 2 || w % 2 || n <= 0 || c <= 0) return fail(-1, "maxpool2 needs c %% 8 == 0 and even h, w");
+  cudaStream_t st = (cudaStream_t)stream;
+  Geom gs = make_geom(n, h, w, true), gd = make_geom(n, h / 2, w / 2, true);
+  const size_t sh = ((size_t)gs.total() * c + 127) / 128 * 128, dh = ((size_t)gd.total() * c + 127) / 128 * 128;
+  Arena a(ws, ws_bytes);
+  __half* xs = a.take<__half>(2 * sh + 256); __half* zs = a.take<__half>(2 * sh + 256); __half* ys = a.take<__half>(2 * dh + 256);
+  float* g1 = a.take<float>((size_t)gd.total() * c);
+  pw::ScaleState sc = take_scales(a);
+  if (!a.ok()) return fail(-3, "workspace too small: need %zu bytes, have %zu", a.off, ws_bytes);
+  SSDN_CUDA(cudaMemsetAsync(xs, 0, (2 * sh + 256) * sizeof(__half), st));
+  SSDN_CUDA(cudaMemsetAsync(zs, 0, (2 * sh + 256) * sizeof(__half), st));
+  SSDN_CUDA(cudaMemsetAsync(ys, 0, (2 * dh + 256) * sizeof(__half), st));
+  SSDN_CUDA(zero_scales(sc, st));
+  const long long ne = (long long)n * c * h * w, no = ne / 4;
+  pw::leaf_scale_kernel<<<64, 256, 0, st>>>(x, ne, sc, 0, 0, 0);
+  ScaleRef xsc{sc.k, nullptr}, ysc{sc.k, nullptr}, zsc{sc.k + 1, nullptr};      // the pooled tensor shares x's scale (max <= max)
+  pw::pack_nchw_kernel<<<pw::grid_for(ne), pw::kBlock, 0, st>>>(x, xs, xs + sh, n, c, h, w, gs, c, 0, 0, xsc);
+  if (y) {
+    pw::pool_fwd_kernel<<<pw::grid_for(no / 8), pw::kBlock, 0, st>>>(xs, xs + sh, gs, c, 0, xsc, ys, ys + dh, gd, c, 0, ysc, c, blind);
+    pw::unpack_nchw_kernel<<<pw::grid_for(no), pw::kBlock, 0, st>>>(ys, ys + dh, sc.k, 0, y, n, c, h / 2, w / 2, gd, c, 0);
+  }
+  if (dy && dz) {
+    pw::leaf_scale_kernel<<<64, 256, 0, st>>>(dy, no, sc, 1, 0, 0);
+    pw::pack_nchw_f32_kernel<<<pw::grid_for(no), pw::kBlock, 0, st>>>(dy, g1, n, c, h / 2, w / 2, gd, c, 0);
+    const int grid = (int)std::min<long long>(pw::kFusedColsumGrid, (no / 8 + pw::kFusedColsumBlock - 1) / pw::kFusedColsumBlock);
+    pw::pool_bwd_kernel<<<grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * 8 * sizeof(float), st>>>(
+        xs, xs + sh, gs, c, 0, g1, c, 0, nullptr, 0, 0, gd, zs, zs + sh, c, 0, zsc, c, blind, nullptr);
+    pw::unpack_nchw_kernel<<<pw::grid_for(ne), pw::kBlock, 0, st>>>(zs, zs + sh, sc.k + 1, 0, dz, n, c, h, w, gs, c, 0);
+  }
+  SSDN_CUDA(cudaGetLastError());
+  SSDN_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ measured tensor peak
 #include "peak_kernel.cuh"
 // Full-chip sustained tcgen05.mma rate (peak_kernel.cuh): kind f16 (f16 != 0) or tf32, the better of cta_group::1 / ::2,

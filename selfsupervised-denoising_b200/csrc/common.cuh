@@ -37,12 +37,17 @@
 #define SSDN_LRELU_SLOPE 0.1f
 
 // The tensor core's fp32 accumulator TRUNCATES (rounds toward zero): every tcgen05.mma accumulate step shrinks the magnitude
-// of the running sum by about half an ulp, so a split-operand result carries a BIAS of -1.5e-8 x (number of MMA instructions per
-// output) relative to its magnitude - measured, stable to +-5 % across layer shapes and zero-mean data
-// (tests/dev_conv_accuracy.py, profiles/r01_conv_accuracy.log): -4.9e-6 for a 96->96 3x3 layer, 1e-4 once compounded over
-// the 20 layers.  The epilogues multiply by 1 + SSDN_ACC_BETA * n_mma: the remaining error is the zero-mean part (half the
-// rms per layer, and it compounds as a square root instead of linearly).  SSDN_ACC_COMP=0 disables it (to re-measure).
-#define SSDN_ACC_BETA 1.525e-8f
+// of the running sum by a fraction of an ulp, so a split-operand result carries a BIAS proportional to the number of MMA
+// instructions per output.  Its size depends on how the partial sums evolve, i.e. on the data: measured per MMA instruction
+// (kind::f16, tests/dev_conv_accuracy.py and tests/dev_trained_bias.py -> profiles/r02_conv_accuracy*.log, r02_trained_bias*.log)
+//   -1.4e-8 .. -1.6e-8  zero-mean synthetic activations and weights, every layer shape
+//   -0.35e-8 .. -1.3e-8 the 20 layers of the TRAINED checkpoint on their own activations (smallest on the 144-channel concat inputs)
+//   -3.8e-8             all-positive activations AND weights (no layer of the network looks like that).
+// The epilogues multiply by 1 + SSDN_ACC_BETA * n_mma with the midpoint of the first two ranges: the residual is then at most
+// 0.65e-8 per MMA either way - below 1.6e-6 for the deepest accumulation of the network (243 MMAs) and below 2e-5 if the
+// residuals of all 20 layers lined up - where the uncompensated bias is 4e-5 summed over the depth of the network.
+// tests/test_gpu_accuracy.py pins both numbers on the trained checkpoint.  SSDN_ACC_COMP=0 disables it (to re-measure).
+#define SSDN_ACC_BETA 0.95e-8f
 
 struct Geom {            // geometry of one padded-flat tensor
   int B, H, W;           // images, height, width

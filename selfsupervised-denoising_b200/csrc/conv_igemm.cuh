@@ -716,7 +716,7 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const __half* 
   }
   // choose the tap grouping: all taps in one window if it fits in shared memory, else one window per
   // distinct row offset (dy), else one window per tap.
-  const int rows_unit = 128 * p.T;
+  int rows_unit = 128 * p.T;
   auto try_group = [&](int mode) -> bool {
     // mode 0: single window, 1: group by rows of the 3x3 stencil (taps sorted in slab order, 3 per row), 2: per tap
     std::vector<std::vector<int>> gs;
@@ -752,7 +752,12 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const __half* 
     }
     return false;
   };
-  if (!try_group(0) && !try_group(1) && !try_group(2)) return -10;
+  if (!try_group(0) && !try_group(1) && !try_group(2)) {
+    if (p.T != 2) return -10;
+    p.T = 1; rows_unit = 128;                          // two tiles per unit do not fit in shared memory (wide 1x1 layers with N = 128)
+    p.n_units_m = (int)((total + 127) / 128);
+    if (!try_group(0) && !try_group(1) && !try_group(2)) return -10;
+  }
   // fast issue path: every B stage = the three taps of one stencil row, with a constant step between their A offsets
   p.row3 = 0; p.tap_step = 0;
   if (taps.n == 9 && p.bg == 3) {

@@ -24,6 +24,8 @@ _SIGNATURES = {
     "ssdn_conv2d_backward_data": (_I, [_P, _Z, _P, _P, _P] + [_I] * 7 + [_P]),
     "ssdn_conv2d_backward_weight_workspace_bytes": (_Z, [_I] * 6),
     "ssdn_conv2d_backward_weight": (_I, [_P, _Z, _P, _P, _P, _P] + [_I] * 7 + [_P]),
+    "ssdn_maxpool2_workspace_bytes": (_Z, [_I] * 4),
+    "ssdn_maxpool2": (_I, [_P, _Z, _P, _P, _P, _P] + [_I] * 5 + [_P]),
     "ssdn_net_create": (_I, [_I] * 6 + [ctypes.POINTER(c_void_p)]),
     "ssdn_net_destroy": (None, [_P]),
     "ssdn_net_workspace_bytes": (_Z, [_P]),
@@ -150,6 +152,19 @@ def conv2d_backward_weight(x, dy, ksize, blind=True):
     check(lib().ssdn_conv2d_backward_weight(_ptr(ws), ws.numel(), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), n, cin, h, wd, cout,
                                             ksize, int(blind), _stream()))
     return dw, db
+
+
+def maxpool2(x, blind=True, dy=None):
+    """Shift2d((1,0)) + MaxPool2d(2) (blind) or MaxPool2d(2) of x [N,C,H,W] (C % 8 == 0) through the network's pool kernels.
+    With dy: also returns dz for x = LeakyReLU(z) (the network's fused backward).  -> y or (y, dz)."""
+    x = _f32(x)
+    n, c, h, w = x.shape
+    y = torch.empty(n, c, h // 2, w // 2, device=x.device, dtype=torch.float32)
+    dz = torch.empty_like(x) if dy is not None else None
+    dy = _f32(dy)
+    ws = _workspace(lib().ssdn_maxpool2_workspace_bytes(n, c, h, w), x.device)
+    check(lib().ssdn_maxpool2(_ptr(ws), ws.numel(), _ptr(x), _ptr(y), _ptr(dy), _ptr(dz), n, c, h, w, int(blind), _stream()))
+    return y if dz is None else (y, dz)
 
 
 # ------------------------------------------------------------------------------------ index operators

@@ -53,6 +53,7 @@ class Denoiser(nn.Module):
         self.init_l_params()
         self._flat = None
         self._flat_grad = None
+        self.dp_world_size = 1           # set by ssdn.train.train_step: ranks that each hold a shard of one global batch
 
     # ------------------------------------------------------------------ construction
     def init_networks(self):
@@ -194,7 +195,15 @@ class Denoiser(nn.Module):
         md = data[NoisyDataset.METADATA] if len(data) > NoisyDataset.METADATA else None
         if self._has_reference(data) and md and NoisyDataset.Metadata.MASK_COORDS in md:
             ref = data[NoisyDataset.REFERENCE].to(self.device, non_blocking=True).float()
-            loss = ssdn.utils.n2v_loss.loss_mask_mse(md[NoisyDataset.Metadata.MASK_COORDS], cleaned, ref)
+            coords = md[NoisyDataset.Metadata.MASK_COORDS]
+            if cleaned.is_cuda and getattr(self, "dp_world_size", 1) > 1 and torch.is_grad_enabled():
+                # The reference applies the coordinate list of the batch's FIRST sample to every sample (utils/n2v_loss.py:12).
+                # One process per GPU holds a shard of that batch: rank 0's first sample is the global batch's first sample, so
+                # its list is broadcast (64 x 2 int64) and the sharded step stays equal to the reference's global-batch step.
+                first = coords[0:1].to(self.device).long().contiguous().clone()
+                torch.distributed.broadcast(first, 0)
+                coords = first
+            loss = ssdn.utils.n2v_loss.loss_mask_mse(coords, cleaned, ref)
             out[PipelineOutput.LOSS] = loss.reshape(loss.shape[0], -1).mean(1, keepdim=True)
         return out
 

@@ -135,6 +135,7 @@ def train_step(denoiser: Denoiser, optimizer: FlatAdam, data: List, world_size: 
     the local loss is the mean over the shard, and gradients are summed by ONE all-reduce then scaled by 1/world_size
     inside the Adam kernel - identical to the gradient of the mean over the global batch."""
     optimizer.zero_grad()
+    denoiser.dp_world_size = world_size
     outputs = denoiser.run_pipeline(data)
     torch.mean(outputs[PipelineOutput.LOSS]).backward()
     if world_size > 1:
@@ -149,7 +150,8 @@ class GraphedTrainStep:
     replayed for every batch.  A step is ~110 kernel launches; on the small per-GPU batches of strong scaling their launch
     cost, not the device work, is what bounds the eager step.  Inputs are copied into the graph's static buffers, the step's
     scalars (learning rate, Adam bias corrections, 1 / world_size) live in a device buffer that is refreshed before each replay.
-    The returned outputs are the graph's static tensors: read (or copy) them before the next call."""
+    The returned outputs are the graph's static tensors: read (or copy) them before the next call.  Outputs of earlier EAGER
+    steps must not be alive when the graph is captured (their autograd graph pins gradient accumulators to the default stream)."""
 
     def __init__(self, denoiser: Denoiser, optimizer: FlatAdam, example: List, world_size: int = 1, warmup: int = 3):
         self.denoiser, self.optimizer, self.world_size = denoiser, optimizer, world_size
@@ -159,6 +161,8 @@ class GraphedTrainStep:
         self.static = [to_dev(example[0]), to_dev(example[1]) if len(example) > 1 else None,
                        {k: to_dev(v) for k, v in md.items() if k != NoisyDataset.Metadata.CLEAN}]
         self.hyper = torch.zeros(6, dtype=torch.float32, device=dev)
+        import gc
+        gc.collect()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -182,6 +186,7 @@ class GraphedTrainStep:
 
     def _body(self):
         self.optimizer.zero_grad()
+        self.denoiser.dp_world_size = self.world_size
         outputs = self.denoiser.run_pipeline(self.static)
         torch.mean(outputs[PipelineOutput.LOSS]).backward()
         if self.world_size > 1:

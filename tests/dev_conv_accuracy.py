@@ -1,4 +1,4 @@
-"""Developer tool (GPU box): accuracy of one 3xTF32 convolution against fp64.  The tensor core's fp32 accumulator
+"""Developer tool (GPU box): accuracy of one split-operand (fp16 hi/lo planes, 3 MMAs per product) convolution against fp64.  The tensor core's fp32 accumulator
 TRUNCATES: every accumulate step shrinks the magnitude by about half an ulp, so the error is a bias proportional to the
 number of MMA instructions per output, not noise.  Prints the error before and after the first-order compensation
 y * (1 + beta * n_mma) for several input distributions (beta is fitted on the first case only)."""
@@ -17,8 +17,7 @@ def dist(name, shape):
     if name == "lrelu(normal)": return F.leaky_relu(torch.randn(shape), 0.1)
     if name == "sparse+": return torch.rand(shape) * (torch.rand(shape) < 0.2)
 for cin, cout, k in ((96, 96, 3), (384, 384, 1), (48, 48, 3), (144, 96, 3)):
-    wide = (k == 1 and cin % 32 == 0)
-    n_mma = (cin // 32 * 4 if wide else (cin + 15) // 16 * 2) * k * k * 3
+    n_mma = (cin + 15) // 16 * k * k * 3            # k-steps of 16 channels x taps x 3 products
     for xd, wd in (("uniform+", "normal"), ("normal", "normal"), ("lrelu(normal)", "normal"), ("sparse+", "normal"), ("uniform+", "uniform+")):
         x = dist(xd, (4, cin, 32, 32)); w = dist(wd, (cout, cin, k, k)) / (cin * k * k) ** 0.5
         y64 = F.conv2d(x.double(), w.double(), padding=k // 2)

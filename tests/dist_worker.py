@@ -1,0 +1,105 @@
+"""torchrun worker of tests/test_gpu_multirank.py (one process per GPU, NCCL).
+
+Every rank builds the same Denoiser (same seed), takes its shard of ONE global batch, and runs K optimiser steps through
+ssdn.train.train_step(world_size = W): mean loss over the shard, ONE all-reduce of the flat gradient buffer (+ stale
+flags), 1 / W folded into Adam.  Checks, printed as one JSON line by rank 0:
+  * replicas: max over ranks of max |p - p_rank0| after the steps must be exactly 0;
+  * equivalence: rank 0 repeats the K steps alone on the whole global batch; parameters must agree to 1e-4 (relative L2
+    per tensor) - the reference's nn.DataParallel semantics (denoiser.py:102-110: one batch split over the GPUs);
+  * Noise2Void: the masked loss uses the coordinate list of the GLOBAL batch's first sample for every sample
+    (utils/n2v_loss.py:12); under sharding rank 0's list is broadcast, so the sharded run still equals the global one."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in ("selfsupervised-denoising_b200", "oracle", "tests"):
+    sys.path.insert(0, os.path.join(ROOT, p))
+
+import torch
+import torch.distributed as dist
+
+import ssdn
+import ssdn_oracle as O
+from ssdn.datasets import NoisyDataset
+from ssdn.train import FlatAdam, GraphedTrainStep, train_step
+from util import make_cfg, rel_l2
+
+M = NoisyDataset.Metadata
+K = 3
+
+
+def global_batch(algo, n, size):
+    clean, noisy = O.synthetic_batch(n, 3, size, seed=77)
+    g = torch.Generator().manual_seed(5)
+    md = {M.INPUT_NOISE_VALUES: torch.full((n, 1, 1, 1), 25 / 255)}
+    ref = torch.zeros(0)
+    if algo == "n2v":
+        ref = (clean + torch.randn(clean.shape, generator=g) * 25 / 255).clamp(0, 1)
+        md[M.MASK_COORDS] = torch.randint(0, size, (n, 16, 2), generator=g)      # a different list per sample
+    return noisy, ref, md
+
+
+def shard(batch, r, w):
+    noisy, ref, md = batch
+    n = noisy.shape[0] // w
+    sl = slice(r * n, (r + 1) * n)
+    return [noisy[sl], ref[sl] if ref.numel() else ref, {k: v[sl] for k, v in md.items()}]
+
+
+def run(algo, mode, device, rank, world, graph):
+    n, size = 8, 32
+    torch.manual_seed(0)
+    den = ssdn.Denoiser(make_cfg(algo, mode, 3), device=device)
+    opt = FlatAdam(den)
+    opt.param_groups[0]["lr"] = 3e-4
+    batch = global_batch(algo, n, size)
+    data = shard(batch, rank, world)
+    data = [data[0].to(device), data[1].to(device) if data[1].numel() else data[1], {k: v.to(device) for k, v in data[2].items()}]
+    if graph:
+        step = GraphedTrainStep(den, opt, data, world, warmup=1)      # = 2 steps
+        for _ in range(K - 2):
+            step(data)
+    else:
+        for _ in range(K):
+            train_step(den, opt, data, world)
+    torch.cuda.synchronize(device)
+    flat = den.flat_parameters()
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    spread = (flat - ref).abs().max().reshape(1)
+    dist.all_reduce(spread, op=dist.ReduceOp.MAX)
+    result = {"spread": float(spread.item())}
+    if rank == 0:
+        torch.manual_seed(0)
+        solo = ssdn.Denoiser(make_cfg(algo, mode, 3), device=device)
+        sopt = FlatAdam(solo)
+        sopt.param_groups[0]["lr"] = 3e-4
+        for _ in range(K):
+            train_step(solo, sopt, [batch[0], batch[1], dict(batch[2])], 1)
+        torch.cuda.synchronize(device)
+        worst = 0.0
+        for (name, a), b in zip(den.named_parameters(), solo.parameters()):
+            if a.numel() > 1:
+                worst = max(worst, rel_l2(a, b))
+        result["vs_global_batch"] = worst
+    return result
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
+    out = {}
+    for name, algo, mode, graph in (("ssdn_known", "ssdn", "known", False), ("ssdn_var_graph", "ssdn", "var", True), ("n2v", "n2v", "known", False)):
+        out[name] = run(algo, mode, device, rank, world, graph)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        ok = all(v["spread"] == 0.0 and v["vs_global_batch"] < 1e-4 for v in out.values())
+        print("MULTIRANK " + json.dumps({"ok": ok, "world": world, "steps": K, "cases": out}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
