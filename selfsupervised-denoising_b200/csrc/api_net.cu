@@ -55,7 +55,10 @@ extern "C" int ssdn_net_check(void* handle, void* stream) {
   int h = 0;
   SSDN_CUDA(cudaMemcpyAsync(&h, nn->flag, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   SSDN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  if (h) return fail(-4, "kernel pipeline timeout (role %d)", h);
+  if (h) {
+    cudaMemsetAsync(nn->flag, 0, 4, (cudaStream_t)stream);       // report once: the next check sees only new trouble
+    return fail(-4, "kernel pipeline timeout (role %d)", h);
+  }
   return 0;
 }
 // Debug/test helper: copies channels [0, c) of a named internal buffer (plane 0 = value = (hi + lo) * 2^-k, 1 = lo, 2 = hi as

@@ -18,9 +18,10 @@ inline int fail(int code, const char* fmt, ...) {
 }
 #define SSDN_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng::fail(-2, "CUDA error '%s' at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
-inline int num_sms() {
-  static int n = 0;
-  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+inline int num_sms() {      // of the CURRENT device (a process may drive plans on several devices)
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   return n;
 }
 

@@ -26,6 +26,13 @@ class NetFunction(torch.autograd.Function):
             raise RuntimeError("NoiseNetwork: backward() called after another forward() reused the same plan; the "
                                "engine keeps one set of activations per (batch, size) plan")
         target = owner.grad_buffer()
+        if target is not None:
+            first = next(iter(owner.parameters())).grad
+            if first is not None and first.data_ptr() == target.data_ptr():
+                # p.grad already ARE views of the buffer the engine is about to overwrite: autograd would then add the new
+                # gradient to itself (2 x new instead of old + new)
+                raise RuntimeError("NoiseNetwork: gradients of an earlier backward() are still attached; the engine writes into one flat "
+                                   "gradient buffer and cannot accumulate - call zero_grad(set_to_none=True) before every backward pass")
         grads = plan.backward(owner.flat_parameters(), dout.contiguous().float(), target, owner.stale_slot())
         outs, off = [], 0
         for shp in ctx.shapes:

@@ -114,11 +114,27 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_tensor_device(fn):
+    """Run an operator with the device of its first tensor argument current: the engine launches on the CURRENT device's
+    current stream, so device pointers, stream and kernels then agree whatever device the caller had selected."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        t = next((a for a in args if torch.is_tensor(a)), None)
+        if t is None or not t.is_cuda:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 # ------------------------------------------------------------------------------------ conv operators
+@_on_tensor_device
 def conv2d_forward(x, w, bias=None, blind=True, lrelu=True):
     """ShiftConv2d / Conv2d (+LeakyReLU 0.1).  x [N,Cin,H,W], w [Cout,Cin,k,k]."""
     x, w, bias = _f32(x), _f32(w), _f32(bias)
@@ -131,6 +147,7 @@ def conv2d_forward(x, w, bias=None, blind=True, lrelu=True):
     return y
 
 
+@_on_tensor_device
 def conv2d_backward_data(dy, w, blind=True):
     dy, w = _f32(dy), _f32(w)
     n, cout, h, wd = dy.shape
@@ -142,6 +159,7 @@ def conv2d_backward_data(dy, w, blind=True):
     return dx
 
 
+@_on_tensor_device
 def conv2d_backward_weight(x, dy, ksize, blind=True):
     x, dy = _f32(x), _f32(dy)
     n, cin, h, wd = x.shape
@@ -154,6 +172,7 @@ def conv2d_backward_weight(x, dy, ksize, blind=True):
     return dw, db
 
 
+@_on_tensor_device
 def maxpool2(x, blind=True, dy=None):
     """Shift2d((1,0)) + MaxPool2d(2) (blind) or MaxPool2d(2) of x [N,C,H,W] (C % 8 == 0) through the network's pool kernels.
     With dy: also returns dz for x = LeakyReLU(z) (the network's fused backward).  -> y or (y, dz)."""
@@ -168,6 +187,7 @@ def maxpool2(x, blind=True, dy=None):
 
 
 # ------------------------------------------------------------------------------------ index operators
+@_on_tensor_device
 def rot4_stack(x):
     x = _f32(x)
     n, c, h, w = x.shape
@@ -176,6 +196,7 @@ def rot4_stack(x):
     return y
 
 
+@_on_tensor_device
 def shift_unrot_concat(x):
     x = _f32(x)
     b, c, h, w = x.shape
@@ -223,7 +244,8 @@ class NetPlan:
     def scale_status(self):
         """(forward stale, backward stale, stale passes since bind); synchronises the current stream."""
         buf = (c_int * 3)()
-        check(lib().ssdn_net_scale_status(self.handle, buf, _stream()))
+        with torch.cuda.device(self.device):
+            check(lib().ssdn_net_scale_status(self.handle, buf, _stream()))
         return int(buf[0]), int(buf[1]), int(buf[2])
 
     def debug_scales(self):
@@ -236,13 +258,16 @@ class NetPlan:
         out = torch.empty(self.out_shape, device=self.device, dtype=torch.float32)
         if verify is None:
             verify = (not training) or not self.fwd_settled
-        for _ in range(self.MAX_SCALE_PASSES):
-            check(lib().ssdn_net_forward(self.handle, _ptr(flat_params), _ptr(x), _ptr(out), int(training), _stream()))
-            if not verify:
-                return out
-            if not self.scale_status()[0]:
-                self.fwd_settled = True
-                return out
+        if x.device != self.device or flat_params.device != self.device:
+            raise EngineError(f"plan lives on {self.device}, got tensors on {x.device} / {flat_params.device}")
+        with torch.cuda.device(self.device):                       # kernels, streams and events belong to the plan's device
+            for _ in range(self.MAX_SCALE_PASSES):
+                check(lib().ssdn_net_forward(self.handle, _ptr(flat_params), _ptr(x), _ptr(out), int(training), _stream()))
+                if not verify:
+                    return out
+                if not self.scale_status()[0]:
+                    self.fwd_settled = True
+                    return out
         raise EngineError("operand scales of the forward pass did not settle (non-finite activations?)")
 
     def backward(self, flat_params, dout, grads=None, stale_out=None, verify=None):
@@ -250,17 +275,21 @@ class NetPlan:
             grads = torch.empty(self.n_params, device=self.device, dtype=torch.float32)
         if verify is None:
             verify = not self.bwd_settled
-        for _ in range(self.MAX_SCALE_PASSES):
-            check(lib().ssdn_net_backward(self.handle, _ptr(flat_params), _ptr(dout), _ptr(grads), _ptr(stale_out), _stream()))
-            if not verify:
-                return grads
-            if not self.scale_status()[1]:
-                self.bwd_settled = True
-                return grads
+        with torch.cuda.device(self.device):
+            for _ in range(self.MAX_SCALE_PASSES):
+                check(lib().ssdn_net_backward(self.handle, _ptr(flat_params), _ptr(dout), _ptr(grads), _ptr(stale_out), _stream()))
+                if not verify:
+                    return grads
+                if not self.scale_status()[1]:
+                    self.bwd_settled = True
+                    return grads
         raise EngineError("operand scales of the backward pass did not settle (non-finite gradients?)")
 
     def check(self):
-        check(lib().ssdn_net_check(self.handle, _stream()))
+        """Synchronises; raises EngineError if a kernel's bounded pipeline wait expired since the last check (the flag is
+        cleared by the check, so the next one reports only new trouble)."""
+        with torch.cuda.device(self.device):
+            check(lib().ssdn_net_check(self.handle, _stream()))
 
     def debug_read(self, name, channels, plane=0):
         """Internal activation / gradient buffer `name` (see net.cuh) as a dense [B, channels, H, W] tensor."""
@@ -284,6 +313,7 @@ def _loss_ws(n, c, device):
     return _workspace(lib().ssdn_loss_workspace_bytes(n, c), device)
 
 
+@_on_tensor_device
 def posterior_forward(net_out, noisy, sigma_raw, sigma_known, poisson=False):
     """poisson: sigma_raw is the known lambda (sigma_known) or the raw estimate of the per-unit-signal variance; the noise
     level is then per pixel and noise_std comes back as [n][h][w] instead of [n][1][1] (denoiser.py:285-297, :375-380)."""
@@ -300,6 +330,7 @@ def posterior_forward(net_out, noisy, sigma_raw, sigma_known, poisson=False):
     return pme, loss, model_std, noise_std
 
 
+@_on_tensor_device
 def posterior_backward(net_out, noisy, sigma_raw, gloss, sigma_known, poisson=False):
     n, c, h, w = noisy.shape
     cs = sigma_raw.numel() // n
@@ -311,6 +342,7 @@ def posterior_backward(net_out, noisy, sigma_raw, gloss, sigma_known, poisson=Fa
     return dnet, dsig
 
 
+@_on_tensor_device
 def spatial_mean_forward(x):
     n, c, h, w = x.shape
     out = torch.empty(n, c, 1, 1, device=x.device)
@@ -318,6 +350,7 @@ def spatial_mean_forward(x):
     return out
 
 
+@_on_tensor_device
 def spatial_mean_backward(g, shape):
     n, c, h, w = shape
     dx = torch.empty(shape, device=g.device)
@@ -325,6 +358,7 @@ def spatial_mean_backward(g, shape):
     return dx
 
 
+@_on_tensor_device
 def mse_forward(a, b):
     n = a.shape[0]
     loss = torch.empty(n, 1, device=a.device)
@@ -333,6 +367,7 @@ def mse_forward(a, b):
     return loss
 
 
+@_on_tensor_device
 def mse_backward(a, b, gloss):
     n = a.shape[0]
     da = torch.empty_like(a)
@@ -340,6 +375,7 @@ def mse_backward(a, b, gloss):
     return da
 
 
+@_on_tensor_device
 def masked_mse_forward(out, ref, coords):
     n, c, h, w = out.shape
     loss = torch.empty(n, 1, device=out.device)
@@ -349,6 +385,7 @@ def masked_mse_forward(out, ref, coords):
     return loss
 
 
+@_on_tensor_device
 def masked_mse_backward(out, ref, coords, gloss):
     n, c, h, w = out.shape
     dout = torch.empty_like(out)
@@ -357,6 +394,7 @@ def masked_mse_backward(out, ref, coords, gloss):
     return dout
 
 
+@_on_tensor_device
 def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.99, eps=1e-8, grad_scale=1.0, skip=None):
     """In-place torch.optim.Adam update of the flat fp32 buffer p (train.py:100-107 hyper-parameters).
     skip: optional CUDA float tensor (<= 8 values); the update is a no-op when any of them is non-zero (stale-gradient flags)."""
@@ -364,6 +402,7 @@ def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.99, eps=1e-8, grad_scale=
                                float(grad_scale), _ptr(skip), 0 if skip is None else skip.numel(), _stream()))
 
 
+@_on_tensor_device
 def adam_step_dev(p, g, m, v, hyper, skip=None):
     """adam_step with {lr / bias_correction1, beta1, beta2, eps, sqrt(bias_correction2), grad_scale} in the CUDA tensor `hyper`."""
     check(lib().ssdn_adam_step_dev(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(hyper), _ptr(skip), 0 if skip is None else skip.numel(),
@@ -401,6 +440,7 @@ def profile_records(max_records=1024):
     return [(PROFILE_KINDS[int(buf[4 * i])], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]) for i in range(n)]
 
 
+@_on_tensor_device
 def noisy_crops(images_u8, n, patch, seed, step, sigma_lo, sigma_hi=None, clip=True, order=None, stream_id=0, want_clean=True):
     """Random crops of a uint8 image cache [n_images][C][H][W] on the device with synthetic Gaussian noise
     (include/ssdn_b200.h: ssdn_noisy_crops).  Returns (clean or None, noisy, sigma [n][C])."""
@@ -420,6 +460,7 @@ def noisy_crops(images_u8, n, patch, seed, step, sigma_lo, sigma_hi=None, clip=T
     return clean, noisy, sigma
 
 
+@_on_tensor_device
 def poisson_crops(images_u8, n, patch, seed, step, lam_lo, lam_hi=None, clip=True, order=None, stream_id=0, want_clean=True):
     """The same crops with the reference's Poisson styles (include/ssdn_b200.h: ssdn_poisson_crops; utils/noise.py:66-109).
     Returns (clean or None, noisy, lam [n][C])."""
@@ -439,6 +480,7 @@ def poisson_crops(images_u8, n, patch, seed, step, lam_lo, lam_hi=None, clip=Tru
     return clean, noisy, lam
 
 
+@_on_tensor_device
 def n2v_mask(noisy, seed, step, subpatch_size=5):
     """Noise2Void uniform pixel selection on the device (utils/n2v_ups.py:7-49).  Returns (masked copy, coords int64 [n][k][2])."""
     noisy = _f32(noisy)

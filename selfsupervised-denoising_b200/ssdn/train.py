@@ -215,6 +215,33 @@ def learning_rate(cfg: Dict, iteration: int) -> float:
                                 cfg[ConfigValue.LR_RAMPUP_FRACTION], cfg[ConfigValue.LEARNING_RATE])
 
 
+class RankShardSampler(torch.utils.data.Sampler):
+    """Rank r of W reads positions cursor + r, cursor + r + W, ... of the wrapped sampler's global order.  The order itself is
+    rank 0's (broadcast), so ranks need not share a seed; the trainer keeps the global cursor (images seen by all ranks)."""
+
+    def __init__(self, base: FixedLengthSampler, rank: int, world: int):
+        self.base, self.rank, self.world = base, rank, world
+
+    def _order(self) -> SamplingOrder:
+        order = iter(self.base)
+        if self.world > 1 and dist.is_available() and dist.is_initialized():
+            box = [order.state_dict() if self.rank == 0 else None]
+            dist.broadcast_object_list(box, 0)
+            if self.rank != 0:
+                order = SamplingOrder.from_state_dict(box[0])
+                self.base.for_next_iter(order)
+        return order
+
+    def __iter__(self):
+        order = self._order()
+        return iter(order.order[order.index + self.rank::self.world])
+
+    def __len__(self) -> int:
+        order = self.base.last_iter()
+        start = order.index if order is not None else 0
+        return max(0, (len(self.base) - start - self.rank + self.world - 1) // self.world)
+
+
 class DenoiserTrainer:
     """Compact counterpart of the reference trainer: drives train_step over any iterable of NoisyDataset-style batches,
     keeps the iteration counter in IMAGES (train.py:221), accumulates the same metrics, snapshots and resumes.
@@ -251,6 +278,40 @@ class DenoiserTrainer:
     def new_target(self, device: str = None):
         self.denoiser = Denoiser(self.cfg, device=device)
         self.init_state()
+        self.sync_replicas()
+
+    def sync_replicas(self):
+        """Data-parallel runs (one process per GPU): every rank adopts rank 0's weights, Adam moments and step count, so that
+        replicas start identical whatever each process seeded or loaded; train_step keeps them identical from then on (all
+        ranks apply the same all-reduced gradient)."""
+        if self.world_size <= 1 or self.denoiser is None or self.denoiser.device.type != "cuda":
+            return
+        flat = self.denoiser.flat_parameters()
+        dist.broadcast(flat, 0)
+        opt = self._optimizer
+        meta = torch.tensor([opt.step_count, 0 if opt.exp_avg is None else 1], dtype=torch.int64, device=flat.device)
+        dist.broadcast(meta, 0)
+        opt.step_count = int(meta[0])
+        if int(meta[1]):
+            opt._ensure_state(flat)
+            dist.broadcast(opt.exp_avg, 0)
+            dist.broadcast(opt.exp_avg_sq, 0)
+
+    def check_engine(self) -> int:
+        """Device-side health of every live execution plan: raises EngineError if a kernel pipeline timed out (results since
+        the last check are then garbage and must not be saved); returns the number of passes that ran with stale operand
+        scales (their optimiser steps were skipped on the device)."""
+        stale = 0
+        if self.denoiser is None:
+            return 0
+        for net in self.denoiser._models.values():
+            for plan in getattr(net, "_plans", {}).values():
+                plan.check()
+                stale += plan.scale_status()[2]
+        if stale > getattr(self, "_stale_seen", 0):
+            logger.warning("%d forward/backward passes ran with stale operand scales so far (their updates were skipped or repeated)", stale)
+        self._stale_seen = stale
+        return stale
 
     def init_state(self):
         self.state[StateValue.INITIALISED] = True
@@ -345,6 +406,7 @@ class DenoiserTrainer:
             self.last_eval = self.evaluate(test_batches)
             self.denoiser.train()
         if iteration % self.cfg[ConfigValue.PRINT_INTERVAL] == 0:
+            self.check_engine()
             history[HistoryValue.TIMINGS]["total"].update()
             if self.rank == 0:
                 logger.info(self.state_str())
@@ -406,8 +468,14 @@ class DenoiserTrainer:
             return HDF5Dataset(path, transform=transform, channels=self.cfg[ConfigValue.IMAGE_CHANNELS])
         raise NotImplementedError("Dataset type not implemented")
 
-    def _loader(self, dataset: NoisyDataset, sampler: FixedLengthSampler, batch_size: int):
+    def _loader(self, dataset: NoisyDataset, sampler: FixedLengthSampler, batch_size: int, shard: bool = False):
+        """shard: data-parallel training - this rank reads positions rank, rank + W, ... of the ONE global order (drawn by rank
+        0) in batches of batch_size / W, so that the W ranks together consume exactly the reference's global mini-batches."""
         from torch.utils.data import DataLoader
+        if shard and self.world_size > 1:
+            if batch_size % self.world_size:
+                raise ValueError("TRAIN_MINIBATCH_SIZE {} is not divisible by the {} data-parallel ranks".format(batch_size, self.world_size))
+            sampler, batch_size = RankShardSampler(sampler, self.rank, self.world_size), batch_size // self.world_size
         return DataLoader(dataset, sampler=sampler, batch_size=batch_size, num_workers=self.cfg[ConfigValue.DATALOADER_WORKERS],
                           pin_memory=self.cfg[ConfigValue.PIN_DATA_MEMORY])
 
@@ -423,7 +491,7 @@ class DenoiserTrainer:
         _ = dataset[0]
         sampler = FixedLengthSampler(dataset, num_samples=cfg[ConfigValue.TRAIN_ITERATIONS], shuffled=True)
         self.attach_sampler(sampler)
-        return self._loader(dataset, sampler, cfg[ConfigValue.TRAIN_MINIBATCH_SIZE]), dataset, sampler
+        return self._loader(dataset, sampler, cfg[ConfigValue.TRAIN_MINIBATCH_SIZE], shard=True), dataset, sampler
 
     def test_data(self):
         """(DataLoader, NoisyDataset, FixedLengthSampler) over the whole test images, reflect-padded to one common size
@@ -477,8 +545,14 @@ class DenoiserTrainer:
                 self.attach_sampler(self.train_sampler)
         self._optimizer.load_state_dict(state_dict["optimizer"])
         torch.set_rng_state(state_dict["rng"])
+        self.sync_replicas()
 
-    def snapshot(self, output_name: str = None, subdir: str = "training", model_only: bool = False) -> str:
+    def snapshot(self, output_name: str = None, subdir: str = None, model_only: bool = False) -> str:
+        """``<run>/training/model_<images>.training`` or, model_only, ``<run>/models/model_<images>.wt`` (train.py:378-408).
+        Refuses to write (EngineError) when a device-side pipeline error was flagged since the last check."""
+        self.check_engine()
+        if subdir is None:
+            subdir = "models" if model_only else "training"
         if output_name is None:
             output_name = "model_{:08d}.{}".format(self.state[StateValue.ITERATION], "wt" if model_only else "training")
         path = os.path.join(self.run_dir_path, subdir, output_name)

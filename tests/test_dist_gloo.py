@@ -59,3 +59,48 @@ def test_sharded_gradient_equals_global_gradient():
     ref = torch.cat([t.grad.reshape(-1) for t in tr.leaves])
     assert torch.allclose(losses, out["loss"].detach(), rtol=1e-5, atol=1e-6)
     assert ((flat - ref).abs().max() / ref.abs().max()).item() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- trainer-side sharding
+def _shard_worker(rank, world, port, q):
+    sys.path.insert(0, os.path.join(ROOT, "selfsupervised-denoising_b200"))
+    from ssdn.datasets import FixedLengthSampler, SamplingOrder
+    from ssdn.train import RankShardSampler
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                       # ranks deliberately seeded DIFFERENTLY: the order must still be rank 0's
+    data = list(range(10))
+    base = FixedLengthSampler(data, num_samples=24, shuffled=True)
+    mine = list(RankShardSampler(base, rank, world))
+    order = base.last_iter().order
+    # resume: a restored global order with the cursor at 8 images seen (by all ranks together)
+    base2 = FixedLengthSampler(data, num_samples=24, shuffled=True)
+    base2.for_next_iter(SamplingOrder(list(order), 8))
+    resumed = list(RankShardSampler(base2, rank, world))
+    q.put((rank, mine, order, resumed))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank_shard_sampler_partitions_one_global_order():
+    """DenoiserTrainer.train_data under data parallelism: the ranks read disjoint, interleaved slices of ONE order (rank 0's),
+    together exactly the reference's sequence of global mini-batches; after a resume they continue from the global cursor."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(2):
+        rank, mine, order, resumed = q.get(timeout=300)
+        got[rank] = (mine, order, resumed)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    order = got[0][1]
+    assert got[1][1] == order and len(order) == 24                 # one order on both ranks although they seeded differently
+    assert got[0][0] == order[0::2] and got[1][0] == order[1::2]   # interleaved: global batch b = positions [b*B, (b+1)*B) split over ranks
+    assert got[0][2] == order[8::2] and got[1][2] == order[9::2]   # resumed from the global cursor
+    inter = [x for pair in zip(got[0][0], got[1][0]) for x in pair]
+    assert inter == order
