@@ -215,6 +215,8 @@ class NetPlan:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise EngineError("the ssdn_b200 network runs on CUDA devices only (no CPU fallback exists)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         handle = c_void_p()
         check(lib().ssdn_net_create(n, cin, cout, h, w, int(blindspot), ctypes.byref(handle)))
         self.handle = handle
