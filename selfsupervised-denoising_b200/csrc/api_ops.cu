@@ -131,7 +131,7 @@ static size_t wgrad_op_layout(Arena& a, const Geom& g, int cin, int cout, int nt
 
 extern "C" size_t ssdn_conv2d_backward_weight_workspace_bytes(int n, int cin, int h, int w, int cout, int ksize) {
   Geom g = make_geom(n, h, w, ksize == 3);
-  const int ks = wgrad_pick_ksplit(g.total(), cout, cin, ksize * ksize, 148);
+  const int ks = wgrad_pick_ksplit(g.total(), cout, cin, ksize * ksize, 148, g.P);
   Arena a(nullptr, 0);
   __half *xp, *yp; size_t xh, yh; float *partial, *colpart; pw::ScaleState sc; int* flag;
   return wgrad_op_layout(a, g, cin, cout, ksize * ksize, ks, &xp, &xh, &yp, &yh, &partial, &colpart, &sc, &flag) + 4096;
@@ -144,7 +144,7 @@ extern "C" int ssdn_conv2d_backward_weight(void* ws, size_t ws_bytes, const floa
   cudaStream_t st = (cudaStream_t)stream;
   Geom g = make_geom(n, h, wd, ksize == 3);
   const int xp = round_up(cin, 8), yp = round_up(cout, 8), ntaps = ksize * ksize;
-  const int ks = wgrad_pick_ksplit(g.total(), cout, cin, ntaps, 148);
+  const int ks = wgrad_pick_ksplit(g.total(), cout, cin, ntaps, 148, g.P);
   Arena a(ws, ws_bytes);
   __half *xpl, *ypl; size_t xh, yh; float *partial, *colpart; pw::ScaleState sc; int* flag;
   wgrad_op_layout(a, g, cin, cout, ntaps, ks, &xpl, &xh, &ypl, &yh, &partial, &colpart, &sc, &flag);

@@ -188,7 +188,7 @@ class Net {
     partial_floats = 0;
     for (auto& l : layers) {
       const Geom& gg = (l.ksize == 1) ? gh : g[level_of(l.name)];
-      l.ksplit = wgrad_pick_ksplit(gg.total(), l.cout, l.cin, l.ksize * l.ksize, sms);
+      l.ksplit = wgrad_pick_ksplit(gg.total(), l.cout, l.cin, l.ksize * l.ksize, sms, gg.P);
       const size_t pf = wgrad_partial_floats(l.ksplit, l.ksize * l.ksize, l.cout, l.cin);
       l.partial = a.take<float>(pf);
       partial_floats += pf;

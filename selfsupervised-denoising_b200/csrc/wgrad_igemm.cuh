@@ -34,6 +34,7 @@ struct WgradParams {
   int nba, nbx;        // 64-channel blocks actually loaded per stage for dZ (<= 2) and X (<= 3)
   const int* k_dz; const int* k_x;   // scale exponents of the two operand tensors (device; null = 0)
   int n_groups, ntaps_total;
+  int rows_per_group, row_stride;   // a group holds rows_per_group stencil rows of 3 taps (consecutive pixels) each, row_stride pixels apart
   WgradGroup groups[9];
   int b_rows, stages;
   uint32_t a_plane_bytes, b_plane_bytes;   // a_plane_bytes = nba * KC * 128 (loaded part; the MMA may address up to 2 blocks)
@@ -135,7 +136,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
       const uint32_t a_lbo = (uint32_t)(adesc & 0xffff0000u), b_lbo = (uint32_t)(bdesc & 0xffff0000u);
       const uint32_t a_pl = p.a_plane_bytes >> 4, b_pl = p.b_plane_bytes >> 4;
       const int ntaps = p.groups[g].ntaps;
-      const bool unit_step = (ntaps == 3) && p.groups[g].tap_rel[1] == p.groups[g].tap_rel[0] + 1 && p.groups[g].tap_rel[2] == p.groups[g].tap_rel[0] + 2;
+      const bool unit_step = (ntaps == 3 * p.rows_per_group) && p.groups[g].tap_rel[1] == p.groups[g].tap_rel[0] + 1 && p.groups[g].tap_rel[2] == p.groups[g].tap_rel[0] + 2;
+      const int rstep = p.row_stride * 8;            // descriptor units (16 bytes) between the X windows of two stencil rows
       for (int c = c0; c < c1; ++c) {
         SSDN_TIMED(w_full, umma::mbar_wait(full(stage), phase, abort_addr, p.error_flag, 12));
         umma::tc_fence_after();
@@ -145,18 +147,39 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
         if (unit_step || ntaps == 1) {
           const uint32_t b0 = (((bv0 + p.groups[g].tap_rel[0] * 128) >> 4) & 0x3fffu) | b_lbo;
           if (umma::elect_one()) {
-            // taps innermost: consecutive MMAs accumulate into DIFFERENT accumulators (see conv_igemm.cuh)
+            // taps innermost: consecutive MMAs accumulate into DIFFERENT accumulators (see conv_igemm.cuh).  Two fully
+            // unrolled variants - the elected thread must have next to nothing to do between two MMAs (the queue is short).
+            if (p.rows_per_group == 3) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {              // k-steps of 16 pixels (2048 bytes = 128 units); a tap shifts X by one row (8 units)
-              if (k < nk) {
+              for (int k = 0; k < 4; ++k) {            // k-steps of 16 pixels (2048 bytes = 128 units); a tap shifts X by one row (8 units)
+                if (k < nk) {
 #pragma unroll
-                for (int prod = 0; prod < 3; ++prod) {
+                  for (int prod = 0; prod < 3; ++prod) {
 #pragma unroll
-                  for (int t = 0; t < 3; ++t) {
-                    if (t < ntaps) {
-                      const uint32_t d = tmem + t * N;
-                      const uint32_t ah = a0 + k * 128, al = ah + a_pl, bh = b0 + t * 8 + k * 128, bl = bh + b_pl;
-                      umma::mma_f16_lo(d, prod == 0 ? al : ah, prod == 1 ? bl : bh, desc_hi, idesc, (k == 0 && prod == 0) ? acc : 1u);
+                    for (int r = 0; r < 3; ++r) {      // all three stencil rows of the 3x3 kernel: nine accumulators
+#pragma unroll
+                      for (int j = 0; j < 3; ++j) {
+                        const uint32_t d = tmem + (3 * r + j) * N;
+                        const uint32_t ah = a0 + k * 128, al = ah + a_pl, bh = b0 + r * rstep + j * 8 + k * 128, bl = bh + b_pl;
+                        umma::mma_f16_lo(d, prod == 0 ? al : ah, prod == 1 ? bl : bh, desc_hi, idesc, (k == 0 && prod == 0) ? acc : 1u);
+                      }
+                    }
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < nk) {
+#pragma unroll
+                  for (int prod = 0; prod < 3; ++prod) {
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                      if (t < ntaps) {
+                        const uint32_t d = tmem + t * N;
+                        const uint32_t ah = a0 + k * 128, al = ah + a_pl, bh = b0 + t * 8 + k * 128, bl = bh + b_pl;
+                        umma::mma_f16_lo(d, prod == 0 ? al : ah, prod == 1 ? bl : bh, desc_hi, idesc, (k == 0 && prod == 0) ? acc : 1u);
+                      }
                     }
                   }
                 }
@@ -325,11 +348,20 @@ static inline size_t wgrad_partial_floats(int ksplit, int ntaps, int cout, int c
 // pixels per pipeline stage: 64 (4 k-steps per barrier round trip) measured 10 % faster over the step than 32 (profiles/r02_layer_times.log)
 static inline int wgrad_kc() { static const int kc = getenv("SSDN_WGRAD_KC") ? atoi(getenv("SSDN_WGRAD_KC")) : 64; return kc == 32 ? 32 : 64; }
 
-// Decides the K split for a layer (so that the grid fills the chip) without needing pointers.
-static inline int wgrad_pick_ksplit(long long k_total, int cout, int cin, int ntaps, int num_sms) {
+// Narrow ci blocks (9 taps x N <= 512 TMEM columns, i.e. cin <= 48) keep ALL nine accumulators of a 3x3 stencil in one unit: dZ is
+// then streamed once instead of once per stencil row, and the K split has three times as many units to hand out.  Needs the X
+// window of three image rows (2 x pitch + 2 more pixels than the chunk) in one TMA box of <= 256 rows.
+static inline bool wgrad_all_taps_in_one_unit(int cin, int ntaps, int pitch) {
+  static const bool off = getenv("SSDN_WGRAD_NINE") && atoi(getenv("SSDN_WGRAD_NINE")) == 0;
+  const int n = (cin + 15) / 16 * 16;
+  return !off && ntaps == 9 && 9 * n <= 512 && (wgrad_kc() + 2 * pitch + 2 + 7) / 8 * 8 <= 256;
+}
+// Decides the K split for a layer (so that the grid fills the chip) without needing pointers.  pitch: row pitch of the geometry.
+static inline int wgrad_pick_ksplit(long long k_total, int cout, int cin, int ntaps, int num_sms, int pitch) {
   const int KC = wgrad_kc();
   const int n_kchunks = (int)((k_total + KC - 1) / KC);
-  const int n_co_tiles = (cout + 127) / 128, n_ci_blocks = wgrad_n_ci_blocks(cin, ntaps), n_groups = ntaps == 9 ? 3 : ntaps;
+  const int n_co_tiles = (cout + 127) / 128, n_ci_blocks = wgrad_n_ci_blocks(cin, ntaps);
+  const int n_groups = ntaps == 9 ? (wgrad_all_taps_in_one_unit(cin, ntaps, pitch) ? 1 : 3) : ntaps;
   const int others = n_co_tiles * n_ci_blocks * n_groups;
   static const int units_per_sm = getenv("SSDN_WGRAD_UNITS_PER_SM") ? atoi(getenv("SSDN_WGRAD_UNITS_PER_SM")) : 1;   // measured: 1 > 2 > 3 (fewer partials to write and reduce)
   int ks = std::max(1, (units_per_sm * num_sms) / others);   // whole waves only: one unit more would cost a whole extra wave
@@ -369,7 +401,15 @@ static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const __ha
   p.nba = std::min(2, (cout + 63) / 64);
   p.ntaps_total = taps.n;
   int span = 0;
-  if (taps.n == 9) {
+  p.rows_per_group = 1; p.row_stride = 0;
+  bool nine = taps.n == 9 && wgrad_all_taps_in_one_unit(cin, taps.n, taps.off[3] - taps.off[0]) && taps.off[6] - taps.off[3] == taps.off[3] - taps.off[0] &&
+              taps.off[3] - taps.off[0] > 0;
+  for (int r = 0; r < 3 && nine; ++r) nine = taps.off[3 * r + 1] == taps.off[3 * r] + 1 && taps.off[3 * r + 2] == taps.off[3 * r] + 2;
+  if (nine) {
+    p.n_groups = 1; p.rows_per_group = 3; p.row_stride = taps.off[3] - taps.off[0];
+    p.groups[0].row_off = taps.off[0]; p.groups[0].ntaps = 9;
+    for (int t = 0; t < 9; ++t) { p.groups[0].tap_id[t] = t; p.groups[0].tap_rel[t] = taps.off[t] - taps.off[0]; span = std::max(span, taps.off[t] - taps.off[0]); }
+  } else if (taps.n == 9) {
     p.n_groups = 3;
     for (int g = 0; g < 3; ++g) {
       int lo = std::min({taps.off[3 * g], taps.off[3 * g + 1], taps.off[3 * g + 2]});
@@ -384,8 +424,11 @@ static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const __ha
   p.a_plane_bytes = p.nba * p.KC * 128;                    // an M = 128 MMA addresses 2 co blocks; a missing one aliases whatever follows (ignored lanes)
   p.b_plane_bytes = (uint32_t)(p.nbx * p.b_rows * 128);    // b_rows is a multiple of 8 => 1024-byte multiple
   const uint32_t stage_bytes = 2 * (p.a_plane_bytes + p.b_plane_bytes);
-  p.stages = std::max(2, std::min(wgradk::kMaxStages, (int)((200 * 1024) / stage_bytes)));
-  plan->smem = (size_t)p.stages * stage_bytes + 2 * p.KC * 128 + 1024;   // slack so that aliased co blocks stay inside the allocation
+  const size_t slack = 2 * p.KC * 128 + 1024;              // so that aliased co blocks stay inside the allocation
+  static const int smem_kb = getenv("SSDN_WGRAD_SMEM_KB") ? atoi(getenv("SSDN_WGRAD_SMEM_KB")) : 224;
+  p.stages = std::max(2, std::min(wgradk::kMaxStages, (int)((smem_kb * 1024 - slack) / stage_bytes)));
+  plan->smem = (size_t)p.stages * stage_bytes + slack;
+  if (plan->smem > 226 * 1024) return -10;
   p.partial = partial; p.error_flag = error_flag;
   plan->grid = std::min(p.n_co_tiles * p.n_ci_blocks * p.n_groups * p.ksplit, num_sms);
   // 4-D maps: (64 channels of a block, flat pixel, channel block [stride 128 B], plane).  The block dimension has a
@@ -409,7 +452,7 @@ static inline int wgrad_plan_init(WgradPlan* plan, long long k_total, const __ha
 static inline cudaError_t wgrad_launch(const WgradPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgradk::wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(wgradk::wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
