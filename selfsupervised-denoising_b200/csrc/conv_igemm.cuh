@@ -73,7 +73,12 @@ struct ConvPlan {
 
 namespace convk {
 
-constexpr int kEpiWarps = 8;      // two epilogue warps per TMEM lane quadrant: they take alternate 32-channel slices of a tile
+#ifndef SSDN_EPI_WARPS_PER_QUADRANT
+#define SSDN_EPI_WARPS_PER_QUADRANT 3
+#endif
+constexpr int kEpiPerQuad = SSDN_EPI_WARPS_PER_QUADRANT;   // epilogue warps per TMEM lane quadrant: warp j of a quadrant takes the 32-channel
+constexpr int kEpiWarps = 4 * kEpiPerQuad;                 // slices s with s % kEpiPerQuad == j (N = 96: one slice per warp and tile).  The
+                                                           // epilogue is latency-bound per warp, so more warps = more slices in flight
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 
@@ -432,7 +437,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const ConvDst& d = p.dst;
     const Geom& sg = p.src;
     const int ew = (warp - 4) & 3;        // TMEM lane quadrant (a warp may only read lanes 32 * (warp % 4) ...)
-    const int half = (warp - 4) >> 2;     // which of the quadrant's two warps: slices with s % 2 == half are its own
+    const int half = (warp - 4) >> 2;     // which of the quadrant's warps: slices with s % kEpiPerQuad == half are its own
     const int n_epi_warps = p.epi_split ? kEpiWarps : 4;
     __shared__ __align__(16) float s_bias[400];
     if (d.flags & EP_BIAS)
@@ -469,7 +474,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll 1
         for (int s = 0; s < kMaxSlices; ++s) {
           const int c0 = 32 * s;
-          if (c0 < p.N && (!p.epi_split || (s & 1) == half)) {
+          if (c0 < p.N && (!p.epi_split || (s % kEpiPerQuad) == half)) {
             // A slice is always handled as 32 columns: when N is not a multiple of 32 the last slice reads 16 columns that
             // belong to nobody (all 512 TMEM columns are allocated) and channel validity is enforced where values leave
             // the warp.  No per-element predication => less than half the instructions (the epilogue is issue-bound).
@@ -628,7 +633,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // lane -> channel of the transpose-reduce: bit k of the lane selected the upper half at step k, i.e. channel == lane
 #pragma unroll
       for (int s = 0; s < kMaxSlices; ++s)
-        if (32 * s + lane < p.N && (!p.epi_split || (s & 1) == half) && c_first + 32 * s + lane < d.colsum_pitch && (u_first < n_units)) row[c_first + 32 * s + lane] = csum[s];
+        if (32 * s + lane < p.N && (!p.epi_split || (s % kEpiPerQuad) == half) && c_first + 32 * s + lane < d.colsum_pitch && (u_first < n_units)) row[c_first + 32 * s + lane] = csum[s];
     }
     if (p.stats && threadIdx.x == 128) { p.stats[blockIdx.x * 16 + 6] = w_full; p.stats[blockIdx.x * 16 + 7] = clock64() - t_start; }
   }
@@ -733,7 +738,8 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const __half* 
     int box_rows = ((max_rows + nbox - 1) / nbox + 15) / 16 * 16;      // multiple of 16 rows => planes/boxes stay 1024-byte aligned
     if (box_rows > 256) { ++nbox; box_rows = ((max_rows + nbox - 1) / nbox + 15) / 16 * 16; }
     uint32_t plane = (uint32_t)(nbox * box_rows * cw_ch * 2);
-    for (int stages = (mode == 0 && !p.wide) ? 2 : 3; stages >= 2; --stages)
+    static const int max_a_stages = getenv("SSDN_CONV_A_STAGES") ? atoi(getenv("SSDN_CONV_A_STAGES")) : 3;
+    for (int stages = std::max(2, std::min(3, max_a_stages)); stages >= 2; --stages)
     for (int bst = 4; bst >= 2; --bst) {
       const size_t epi = convk::kEpiWarps * 32 * convk::kStagePitch * sizeof(float);   // epilogue staging (all destinations)
       size_t need = (size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes + epi + 2048;
@@ -752,11 +758,20 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const __half* 
     }
     return false;
   };
-  if (!try_group(0) && !try_group(1) && !try_group(2)) {
-    if (p.T != 2) return -10;
-    p.T = 1; rows_unit = 128;                          // two tiles per unit do not fit in shared memory (wide 1x1 layers with N = 128)
-    p.n_units_m = (int)((total + 127) / 128);
-    if (!try_group(0) && !try_group(1) && !try_group(2)) return -10;
+  auto try_all = [&]() { return try_group(0) || try_group(1) || try_group(2); };
+  if (!try_all()) {
+    bool ok = false;
+    if (p.T == 2) {                                      // two tiles per unit do not fit in shared memory (wide 1x1 layers with N = 128)
+      p.T = 1; rows_unit = 128;
+      p.n_units_m = (int)((total + 127) / 128);
+      ok = try_all();
+    }
+    if (!ok && taps.n == 1 && p.bg > 1 && !p.pair) {     // 1x1 layers with wide N: one weight slab per B stage instead of three
+      p.bg = 1;
+      p.b_stage_bytes = (uint32_t)(p.bg * 2 * N * cw_ch * 2);
+      ok = try_all();
+    }
+    if (!ok) return -10;
   }
   // fast issue path: every B stage = the three taps of one stencil row, with a constant step between their A offsets
   p.row3 = 0; p.tap_step = 0;
