@@ -36,6 +36,14 @@
 
 #define SSDN_LRELU_SLOPE 0.1f
 
+// Programmatic dependent launch: every engine kernel is launched with programmaticStreamSerializationAllowed, so that it may
+// become resident (and run its prologue: barrier init, TMEM allocation, tensor-map prefetch) while the kernel before it on
+// the stream is still running on other SMs; pdl_wait() then blocks until that kernel has completed and its writes are visible.
+// It is the FIRST thing a kernel does before touching global memory, so stream-order semantics are unchanged.  On the small
+// pyramid levels (grids of 12 .. 90 CTAs, 15 - 25 us per kernel) this hides most of the launch latency and the prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // The tensor core's fp32 accumulator TRUNCATES (rounds toward zero): every tcgen05.mma accumulate step shrinks the magnitude
 // of the running sum by a fraction of an ulp, so a split-operand result carries a BIAS proportional to the number of MMA
 // instructions per output.  Its size depends on how the partial sums evolve, i.e. on the data: measured per MMA instruction
@@ -55,6 +63,20 @@ struct Geom {            // geometry of one padded-flat tensor
   int row0;              // halo rows above each image (2 or 0)
   __host__ __device__ long long total() const { return (long long)B * S; }
 };
+
+#include <cstdlib>
+#include <utility>
+static inline bool pdl_enabled() { static const bool on = !(getenv("SSDN_PDL") && atoi(getenv("SSDN_PDL")) == 0); return on; }
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute (see pdl_wait)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute a[1];
+  a[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; a[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = a; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 static inline Geom make_geom(int B, int H, int W, bool padded) {
   Geom g; g.B = B; g.H = H; g.W = W;

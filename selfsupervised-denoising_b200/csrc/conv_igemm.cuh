@@ -195,6 +195,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (PAIR) umma::cluster_sync();       // the peer's barriers must be initialised before anything arrives on them
   umma::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_launch_dependents();      // the next kernel on the stream may start its prologue on idle SMs ...
+  pdl_wait();                   // ... and this one touches global memory only after its predecessor has completed
 
   if (warp == 0) {
     // ------------------------------------------------------------ A producer (warp-uniform loop, elected issue)
@@ -879,16 +881,16 @@ static inline cudaError_t conv_launch_raw(const ConvPlan& plan, const ConvParams
     attr_set = true;
   }
   if (!p.pair) {
-    if (p.T == 2) convk::conv_igemm_kernel<2, false><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, p);
-    else convk::conv_igemm_kernel<1, false><<<plan.grid, convk::kThreads, plan.smem, stream>>>(plan.a, plan.b, p);
-    return cudaGetLastError();
+    if (p.T == 2) return launch_pdl(convk::conv_igemm_kernel<2, false>, dim3(plan.grid), dim3(convk::kThreads), plan.smem, stream, plan.a, plan.b, p);
+    return launch_pdl(convk::conv_igemm_kernel<1, false>, dim3(plan.grid), dim3(convk::kThreads), plan.smem, stream, plan.a, plan.b, p);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(convk::kThreads); cfg.dynamicSmemBytes = plan.smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   if (p.T == 2) return cudaLaunchKernelEx(&cfg, convk::conv_igemm_kernel<2, true>, plan.a, plan.b, p);
   return cudaLaunchKernelEx(&cfg, convk::conv_igemm_kernel<1, true>, plan.a, plan.b, p);
 }

@@ -66,6 +66,7 @@ __global__ void posterior_fwd_kernel(const float* __restrict__ net_out, const fl
                                      const float* __restrict__ sigma_raw, int cs, int known, int poisson, int HW,
                                      float* __restrict__ pme, float* __restrict__ model_std, float* __restrict__ noise_std_px,
                                      float* __restrict__ partial) {
+  pdl_wait();
   __shared__ float sm[32];
   constexpr int CO = C + C * (C + 1) / 2;
   const int n = blockIdx.y;
@@ -132,6 +133,7 @@ __global__ void posterior_fwd_kernel(const float* __restrict__ net_out, const fl
 // loss[n] = sum(partial[n][:]) / HW ; noise_std_out[n] = (prod sigma_c^2)^(1/6) (RGB) or sigma (mono)
 __global__ void posterior_finalize_kernel(const float* __restrict__ partial, int nblk, int HW, const float* __restrict__ sigma_raw,
                                           int cs, int known, int C, int N, float* __restrict__ loss, float* __restrict__ noise_std) {
+  pdl_wait();
   // noise_std == NULL for Poisson noise (per-pixel levels were written by the forward kernel)
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -154,6 +156,7 @@ template <int C>
 __global__ void posterior_bwd_kernel(const float* __restrict__ net_out, const float* __restrict__ noisy,
                                      const float* __restrict__ sigma_raw, int cs, int known, int poisson, int HW,
                                      const float* __restrict__ gloss, float* __restrict__ dnet, float* __restrict__ dsig_partial) {
+  pdl_wait();
   // ds[c] accumulates d(loss)/d(sigma_c) (Gaussian; the -0.1 regulariser is added by the finalize kernel) or
   // d(loss)/d(k_c) including the regulariser (Poisson: it depends on the pixel)
   __shared__ float sm[32];
@@ -240,6 +243,7 @@ __global__ void posterior_bwd_kernel(const float* __restrict__ net_out, const fl
 __global__ void posterior_bwd_finalize_kernel(const float* __restrict__ dsig_partial, int nblk, const float* __restrict__ sigma_raw,
                                               int cs, int C, int N, int poisson, const float* __restrict__ gloss,
                                               float* __restrict__ dsigma_raw) {
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * cs) return;
   const int n = idx / cs, c = idx % cs;
@@ -251,7 +255,8 @@ __global__ void posterior_bwd_finalize_kernel(const float* __restrict__ dsig_par
 }
 
 // ---------------------------------------------------------------- per-sample spatial mean (sigma estimator head)
-__global__ void spatial_mean_kernel(const float* __restrict__ x, int HW, float* __restrict__ out) {   // grid = N*C
+__global__ void spatial_mean_kernel(const float* __restrict__ x, int HW, float* __restrict__ out) {
+  pdl_wait();   // grid = N*C
   __shared__ float sm[32];
   const float* p = x + (long long)blockIdx.x * HW;
   float acc = 0.f;
@@ -260,12 +265,14 @@ __global__ void spatial_mean_kernel(const float* __restrict__ x, int HW, float* 
   if (threadIdx.x == 0) out[blockIdx.x] = t / (float)HW;
 }
 __global__ void spatial_mean_bwd_kernel(const float* __restrict__ g, int HW, long long total, float* __restrict__ dx) {
+  pdl_wait();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < total) dx[i] = g[i / HW] / (float)HW;
 }
 
 // ---------------------------------------------------------------- MSE per sample (denoiser.py:153-154) and its gradient
 __global__ void mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int CHW, float* __restrict__ partial) {
+  pdl_wait();
   __shared__ float sm[32];   // grid = (blocks_per_sample, N)
   const float* pa = a + (long long)blockIdx.y * CHW; const float* pb = b + (long long)blockIdx.y * CHW;
   float acc = 0.f;
@@ -274,6 +281,7 @@ __global__ void mse_fwd_kernel(const float* __restrict__ a, const float* __restr
   if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
 }
 __global__ void mean_finalize_kernel(const float* __restrict__ partial, int nblk, float denom, int N, float* __restrict__ out) {
+  pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
@@ -282,6 +290,7 @@ __global__ void mean_finalize_kernel(const float* __restrict__ partial, int nblk
 }
 __global__ void mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gloss, int CHW,
                                long long total, float* __restrict__ da) {
+  pdl_wait();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < total) da[i] = 2.f * (a[i] - b[i]) * gloss[i / CHW] / (float)CHW;
 }
@@ -291,6 +300,7 @@ __global__ void mse_bwd_kernel(const float* __restrict__ a, const float* __restr
 // One thread per (n, c): sequential over the K coordinates (duplicates accumulate deterministically).
 __global__ void masked_mse_fwd_kernel(const float* __restrict__ out, const float* __restrict__ ref, const long long* __restrict__ coords,
                                       int K, int NC, int H, int W, float* __restrict__ per_nc) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NC) return;
   const float* po = out + (long long)i * H * W; const float* pr = ref + (long long)i * H * W;
@@ -299,6 +309,7 @@ __global__ void masked_mse_fwd_kernel(const float* __restrict__ out, const float
   per_nc[i] = acc;
 }
 __global__ void masked_mse_reduce_kernel(const float* __restrict__ per_nc, int N, int C, float* __restrict__ loss) {
+  pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
@@ -307,6 +318,7 @@ __global__ void masked_mse_reduce_kernel(const float* __restrict__ per_nc, int N
 }
 __global__ void masked_mse_bwd_kernel(const float* __restrict__ out, const float* __restrict__ ref, const long long* __restrict__ coords,
                                       int K, int NC, int C, int H, int W, const float* __restrict__ gloss, float* __restrict__ dout) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // dout must be zero-filled beforehand
   if (i >= NC) return;
   const float* po = out + (long long)i * H * W; const float* pr = ref + (long long)i * H * W;
@@ -332,6 +344,7 @@ __device__ __forceinline__ void adam_update(float* __restrict__ p, const float* 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float step_size, float beta1, float beta2, float eps, float bc2_sqrt, float grad_scale,
                             const float* __restrict__ skip, int n_skip) {
+  pdl_wait();
   for (int j = 0; j < n_skip; ++j) if (__ldg(skip + j) != 0.f) return;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -341,6 +354,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // sqrt(bias_correction2), grad_scale}): a CUDA graph that contains this launch can be replayed for every step.
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                 long long n, const float* __restrict__ hyper, const float* __restrict__ skip, int n_skip) {
+  pdl_wait();
   for (int j = 0; j < n_skip; ++j) if (__ldg(skip + j) != 0.f) return;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;

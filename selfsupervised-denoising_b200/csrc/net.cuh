@@ -214,7 +214,7 @@ class Net {
     cudaError_t ce = cudaMemsetAsync(workspace, 0, ws_bytes, st);   // zero halos (never written afterwards)
     if (ce != cudaSuccess) return eng::fail(-2, "memset failed: %s", cudaGetErrorString(ce));
     pools.clear(); pool_bwds.clear(); up_bwds.clear();
-    scale_init_kernel<<<1, 32, 0, st>>>(scales, kSlotA, n_slot_a, kInitActScale);
+    launch_pdl(scale_init_kernel, dim3(1), dim3(32), 0, st, scales, kSlotA, n_slot_a, kInitActScale);
     fwd_runs = bwd_runs = 0;
     int r;
     const int act = EP_BIAS | EP_LRELU | EP_WRITE_LO;
@@ -375,7 +375,7 @@ class Net {
     int ns = 0;
     for (auto& l : layers) sj.j[ns++] = {params + l.w_off, l.cout * l.cin * l.ksize * l.ksize, kSlotW + layer_index(l)};
     SSDN_PROF(K_WEIGHT_PREP, 0, 4.0 * n_params, st,
-              (pw::weight_scale_kernel<<<dim3(pw::kWeightScaleBlocks, ns), 256, 0, st>>>(sj, scales, kSlotA, n_slot_a)));
+              (launch_pdl(pw::weight_scale_kernel, dim3(pw::kWeightScaleBlocks, ns), dim3(256), 0, st, sj, scales, kSlotA, n_slot_a)));
     pw::WeightPrepJobs jobs{};
     int nj = 0;
     for (auto& l : layers) {
@@ -392,7 +392,7 @@ class Net {
     double slab_bytes = 0;
     for (int j = 0; j < nj; ++j) slab_bytes += 2.0 * 2.0 * jobs.j[j].n_tiles * jobs.j[j].n_chunks * jobs.j[j].ntaps * jobs.j[j].N * jobs.j[j].CW;
     SSDN_PROF(K_WEIGHT_PREP, 0, slab_bytes + 4.0 * n_params * (with_dgrad ? 2 : 1), st,
-              (pw::weight_prep_batched_kernel<<<dim3(64, nj), pw::kBlock, 0, st>>>(jobs, scales)));
+              (launch_pdl(pw::weight_prep_batched_kernel, dim3(64, nj), dim3(pw::kBlock), 0, st, jobs, scales)));
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }
@@ -410,7 +410,7 @@ class Net {
     ++fwd_runs;                 // (the pass over the activation slots is begun by prep_weights' first kernel)
     if ((r = prep_weights(params, st, training))) return r;
     SSDN_PROF(K_PACK, 0, (double)N * Cin * H * W * 4.0 + (double)B * H * W * Cin * 4.0, st,
-              (pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)B * H * W), pw::kBlock, 0, st>>>(x, cat[1].hi, cat[1].lo, N, Cin, H, W, g[0],
+              (launch_pdl(pw::pack_nchw_pixel_kernel, dim3(pw::grid_for((long long)B * H * W)), dim3(pw::kBlock), 0, st, x, cat[1].hi, cat[1].lo, N, Cin, H, W, g[0],
                                                                                                     cat[1].cpitch, 96, blind ? 1 : 0, cat[1].sc)));
     size_t pi = 0;
     auto pool = [&]() {
@@ -418,7 +418,7 @@ class Net {
       const long long n = (long long)p.dst->g.B * p.dst->g.H * p.dst->g.W * 6;
       // reads the full-resolution plane pair once, writes the pooled one
       SSDN_PROF(K_POOL_FWD, 0, B0(p.src->g) * 48 * 4.0 + B0(p.dst->g) * 48 * 4.0, st,
-                (pw::pool_fwd_kernel<<<pw::grid_for(n), pw::kBlock, 0, st>>>(p.src->hi, p.src->lo, p.src->g, p.src->cpitch, 0, p.src->sc, p.dst->hi, p.dst->lo,
+                (launch_pdl(pw::pool_fwd_kernel, dim3(pw::grid_for(n)), dim3(pw::kBlock), 0, st, p.src->hi, p.src->lo, p.src->g, p.src->cpitch, 0, p.src->sc, p.dst->hi, p.dst->lo,
                                                                             p.dst->g, p.dst->cpitch, p.dst_coff, p.dst->sc, 48, blind ? 1 : 0)));
     };
     if ((r = run_fwd(L("encode_block_1.0"), params, st))) return r;
@@ -433,7 +433,7 @@ class Net {
     if ((r = run_fwd(L("output_block.0"), params, st))) return r;
     if ((r = run_fwd(L("output_block.2"), params, st))) return r;
     if ((r = run_fwd(L("output_conv"), params, st, out))) return r;
-    SSDN_PROF(K_SCALE, 0, 0, st, (pw::scale_finish_kernel<<<1, 32, 0, st>>>(scales, kSlotA, n_slot_a, 0, nullptr, 0, kSlotW, (int)layers.size())));
+    SSDN_PROF(K_SCALE, 0, 0, st, (launch_pdl(pw::scale_finish_kernel, dim3(1), dim3(32), 0, st, scales, kSlotA, n_slot_a, 0, nullptr, 0, kSlotW, (int)layers.size())));
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }
@@ -468,11 +468,11 @@ class Net {
       const int nt = l.ksize * l.ksize;
       const long long n = (long long)l.cout * l.wgrad.p.cin_pitch * nt;
       jobs.j[nj++] = {l.partial, grads + l.w_off, l.wgrad.p.ksplit, nt, l.cout, l.cin, l.wgrad.p.cin_pitch, blocks};
-      blocks += (int)((n + 31) / 32);
+      blocks += (int)((n / 4 + 31) / 32);
       bytes += (double)n * 4 * (l.wgrad.p.ksplit + 1);
     }
     jobs.n_jobs = nj;
-    SSDN_PROF(K_WGRAD_REDUCE, 0, bytes, st, (wgradk::wgrad_reduce_batched_kernel<<<blocks, dim3(32, 16), 0, st>>>(jobs)));
+    SSDN_PROF(K_WGRAD_REDUCE, 0, bytes, st, (launch_pdl(wgradk::wgrad_reduce_batched_kernel, dim3(blocks), dim3(32, 16), 0, st, jobs)));
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }
@@ -491,13 +491,13 @@ class Net {
     // (the gradient slots were begun by the previous backward pass's scale_finish_kernel, or by bind())
     // the loss gradient is a leaf: exact scale now; the very first backward pass seeds every gradient slot with it
     SSDN_PROF(K_SCALE, 0, dout_bytes, st,
-              (pw::leaf_scale_kernel<<<64, 256, 0, st>>>(dout, (long long)N * Cout * H * W, scales, g_out.sid, kSlotG, bwd_runs == 0 ? n_slot_g : 0)));
+              (launch_pdl(pw::leaf_scale_kernel, dim3(64), dim3(256), 0, st, dout, (long long)N * Cout * H * W, scales, g_out.sid, kSlotG, bwd_runs == 0 ? n_slot_g : 0)));
     ++bwd_runs;
     ScaleRef no_amax = g_out.sc; no_amax.amax = nullptr;
     SSDN_PROF(K_PACK, 0, 2 * dout_bytes, st,
-              (pw::pack_nchw_pixel_kernel<<<pw::grid_for((long long)N * H * W), pw::kBlock, 0, st>>>(dout, g_out.hi, g_out.lo, N, Cout, H, W, gh,
+              (launch_pdl(pw::pack_nchw_pixel_kernel, dim3(pw::grid_for((long long)N * H * W)), dim3(pw::kBlock), 0, st, dout, g_out.hi, g_out.lo, N, Cout, H, W, gh,
                                                                                                     g_out.cpitch, 0, 0, no_amax)));
-    SSDN_PROF(K_BIAS, 0, dout_bytes, st, (pw::nchw_colsum_kernel<<<dim3(Cout, N), 256, 0, st>>>(dout, Cout, H * W, L("output_conv").bias_buf)));
+    SSDN_PROF(K_BIAS, 0, dout_bytes, st, (launch_pdl(pw::nchw_colsum_kernel, dim3(Cout, N), dim3(256), 0, st, dout, Cout, H * W, L("output_conv").bias_buf)));
     auto both = [&](const std::string& nm, bool dgrad) -> int {
       Layer& l = L(nm);
       int rr = run_wgrad(l, grads, st);
@@ -515,14 +515,14 @@ class Net {
       (void)n;
       // reads the fp32 gradient at the upsampled resolution (4 pixels per output) + one hi-plane sign per output, writes a plane pair
       SSDN_PROF(K_UP_BWD, 0, B0(gl) * u.C * (4 * 4.0 + 2.0 + 4.0), st,
-                (pw::up_bwd_kernel<<<u.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * 8 * sizeof(float), st>>>(
+                (launch_pdl(pw::up_bwd_kernel, dim3(u.grid), dim3(pw::kFusedColsumBlock), pw::kFusedColsumBlock * 8 * sizeof(float), st, 
                     u.g->v, u.g->g, u.g->cpitch, 0, u.act_up->hi, u.act_up->cpitch, 0, gl, u.dz->hi, u.dz->lo, u.dz->cpitch, 0, u.dz->sc, u.C, u.colsum)));
     };
     auto pool_bwd = [&]() {
       const PoolBwdOp& q = pool_bwds[qi++];
       // per pooled pixel and channel: 4 activations (plane pairs) in, 1 or 2 fp32 gradients in, 4 dZ values (plane pairs) out
       SSDN_PROF(K_POOL_BWD, 0, B0(q.gp) * 48 * (4 * 4.0 + (q.g2 ? 8.0 : 4.0) + 4 * 4.0), st,
-                (pw::pool_bwd_kernel<<<q.grid, pw::kFusedColsumBlock, pw::kFusedColsumBlock * 8 * sizeof(float), st>>>(
+                (launch_pdl(pw::pool_bwd_kernel, dim3(q.grid), dim3(pw::kFusedColsumBlock), pw::kFusedColsumBlock * 8 * sizeof(float), st, 
                     q.act->hi, q.act->lo, q.act->g, q.act->cpitch, 0, q.g1->v, q.g1->cpitch, 0, q.g2 ? q.g2->v : nullptr, q.g2 ? q.g2->cpitch : 0, q.g2_coff, q.gp,
                     q.dz->hi, q.dz->lo, q.dz->cpitch, 0, q.dz->sc, 48, blind ? 1 : 0, q.colsum)));
     };
@@ -546,11 +546,11 @@ class Net {
         if (l.bias_fused) { jobs.j[nj++] = {l.bias_partial, grads + l.b_off, l.bias_nblk, l.cout}; maxc = std::max(maxc, l.cout); }
       double pb = 0;
       for (int j = 0; j < nj; ++j) pb += 4.0 * jobs.j[j].nblk * jobs.j[j].C;
-      if (nj) SSDN_PROF(K_BIAS, 0, pb, st, (pw::colsum_stage2_batched_kernel<<<dim3((maxc + 31) / 32, nj), dim3(32, 32), 0, st>>>(jobs)));
+      if (nj) SSDN_PROF(K_BIAS, 0, pb, st, (launch_pdl(pw::colsum_stage2_batched_kernel, dim3((maxc + 31) / 32, nj), dim3(32, 32), 0, st, jobs)));
     }
     if ((r = reduce_all_wgrads(grads, (side && use_side && !profiler().on) ? side : st))) return r;
     if ((r = join_side(st))) return r;
-    SSDN_PROF(K_SCALE, 0, 0, st, (pw::scale_finish_kernel<<<1, 32, 0, st>>>(scales, kSlotG, n_slot_g, 1, stale_out, 1, 0, 0)));
+    SSDN_PROF(K_SCALE, 0, 0, st, (launch_pdl(pw::scale_finish_kernel, dim3(1), dim3(32), 0, st, scales, kSlotG, n_slot_g, 1, stale_out, 1, 0, 0)));
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }

@@ -16,6 +16,7 @@ static inline int grid_for(long long n, int block = kBlock) { return (int)((n + 
 // One thread per element (tests, single-operator entry points).
 __global__ void pack_nchw_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
                                  int B, int C, int H, int W, Geom g, int cpitch, int coff, int rot4, ScaleRef sc) {
+  pdl_wait();
   const long long n = (long long)(rot4 ? 4 : 1) * B * C * H * W;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const float s = sc.k ? exp2_int(__ldg(sc.k)) : 1.0f;
@@ -37,6 +38,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ x, __half* __restrict
 }
 // the same mapping into a single fp32 plane (raw gradient buffers; test hook)
 __global__ void pack_nchw_f32_kernel(const float* __restrict__ x, float* __restrict__ v, int B, int C, int H, int W, Geom g, int cpitch, int coff) {
+  pdl_wait();
   const long long n = (long long)B * C * H * W;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= n) return;
@@ -51,6 +53,7 @@ __global__ void pack_nchw_f32_kernel(const float* __restrict__ x, float* __restr
 // index arithmetic is done once per pixel (the network input and the loss gradient have 3..12 channels).
 __global__ void pack_nchw_pixel_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
                                        int B, int C, int H, int W, Geom g, int cpitch, int coff, int rot4, ScaleRef sc) {
+  pdl_wait();
   const long long n = (long long)(rot4 ? 4 : 1) * B * H * W;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const float s = sc.k ? exp2_int(__ldg(sc.k)) : 1.0f;
@@ -83,6 +86,7 @@ __global__ void pack_nchw_pixel_kernel(const float* __restrict__ x, __half* __re
 // padded flat -> dense NCHW (tests / debugging): plane 0: value = (hi + lo) * 2^-k, 1: lo, 2: hi (as stored, scaled)
 __global__ void unpack_nchw_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, const int* __restrict__ k, int plane,
                                    float* __restrict__ y, int B, int C, int H, int W, Geom g, int cpitch, int coff) {
+  pdl_wait();
   const long long n = (long long)B * C * H * W;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= n) return;
@@ -94,6 +98,7 @@ __global__ void unpack_nchw_kernel(const __half* __restrict__ hi, const __half* 
   else y[idx] = __half2float(plane == 1 ? lo[o] : hi[o]);
 }
 __global__ void unpack_nchw_f32_kernel(const float* __restrict__ v, float* __restrict__ y, int B, int C, int H, int W, Geom g, int cpitch, int coff) {
+  pdl_wait();
   const long long n = (long long)B * C * H * W;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= n) return;
@@ -105,6 +110,7 @@ __global__ void unpack_nchw_f32_kernel(const float* __restrict__ v, float* __res
 
 // LeakyReLU sign masks of a two-plane tensor (test hook: after an activation buffer was overwritten from outside).
 __global__ void mask_from_planes_kernel(const __half* __restrict__ hi, long long pixels, int cpitch, uint32_t* __restrict__ mask, int words) {
+  pdl_wait();
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= pixels * words) return;
   const long long px = idx / words; const int w = (int)(idx - px * words);
@@ -130,6 +136,7 @@ __device__ __forceinline__ void st8(__half* __restrict__ hi, __half* __restrict_
 __global__ void pool_fwd_kernel(const __half* __restrict__ src, const __half* __restrict__ src_lo, Geom gs, int s_cpitch, int s_coff, ScaleRef ssc,
                                 __half* __restrict__ dv, __half* __restrict__ dlo, Geom gd, int d_cpitch, int d_coff, ScaleRef dsc,
                                 int C, int blind) {
+  pdl_wait();
   const int c8n = C / 8;
   const long long n = (long long)gd.B * gd.H * gd.W * c8n;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -172,6 +179,7 @@ pool_bwd_kernel(const __half* __restrict__ act, const __half* __restrict__ act_l
                 const float* __restrict__ g2, int g2_cpitch, int g2_coff, Geom gp,
                 __half* __restrict__ dv, __half* __restrict__ dlo, int d_cpitch, int d_coff, ScaleRef dsc,
                 int C, int blind, float* __restrict__ colsum_partial) {
+  pdl_wait();
   extern __shared__ float sm_pool[];      // [blockDim.x][8]
   const int c8n = C / 8;
   const long long n = (long long)gp.B * gp.H * gp.W * c8n;
@@ -243,6 +251,7 @@ up_bwd_kernel(const float* __restrict__ g, Geom gg, int g_cpitch, int g_coff,
               const __half* __restrict__ act_hi, int a_cpitch, int a_coff, Geom gl,
               __half* __restrict__ dv, __half* __restrict__ dlo, int d_cpitch, int d_coff, ScaleRef dsc, int C,
               float* __restrict__ colsum_partial) {
+  pdl_wait();
   extern __shared__ float sm_up[];        // [blockDim.x][8]
   const int c8n = C / 8;
   const long long n = (long long)gl.B * gl.H * gl.W * c8n;
@@ -297,6 +306,7 @@ up_bwd_kernel(const float* __restrict__ g, Geom gg, int g_cpitch, int g_coff,
 // column sums of a dense NCHW tensor: partial[n][c] = sum over h, w (the bias gradient of the last conv is the sum of
 // d(loss)/d(output) itself); grid = (C, N)
 __global__ void nchw_colsum_kernel(const float* __restrict__ x, int C, int HW, float* __restrict__ partial) {
+  pdl_wait();
   __shared__ float sm[32];
   const float* row = x + ((long long)blockIdx.y * C + blockIdx.x) * HW;
   float acc = 0.f;
@@ -320,6 +330,7 @@ struct ScaleState {
 };
 // Start of a pass over slots [first, first + count): adopt the scales derived from the previous pass, clear the maxima.
 __global__ void scale_begin_kernel(ScaleState st, int first, int count) {
+  pdl_wait();
   const int i = first + threadIdx.x + blockIdx.x * blockDim.x;
   if (i < first + count) { st.k[i] = st.k_next[i]; st.amax[i] = 0u; }
 }
@@ -332,6 +343,7 @@ __global__ void scale_begin_kernel(ScaleState st, int first, int count) {
 // clear_count > 0: also clear the maxima of slots [clear_first, clear_first + clear_count) (the weight slots, whose readers are done).
 __global__ void scale_finish_kernel(ScaleState st, int first, int count, int which, float* __restrict__ stale_out, int apply,
                                     int clear_first, int clear_count) {
+  pdl_wait();
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;
   for (int i = threadIdx.x; i < clear_count; i += blockDim.x) st.amax[clear_first + i] = 0u;
@@ -356,6 +368,7 @@ __global__ void scale_finish_kernel(ScaleState st, int first, int count, int whi
 // last block to finish sets k[slot] (and, when init_count > 0, seeds slots [init_first, init_first + init_count) with the
 // same exponent: the first backward pass of a plan has no previous maxima to go by).
 __global__ void leaf_scale_kernel(const float* __restrict__ x, long long n, ScaleState st, int slot, int init_first, int init_count) {
+  pdl_wait();
   __shared__ float sm[32];
   float m = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(__ldg(x + i)));
@@ -386,6 +399,7 @@ constexpr int kMaxScaleJobs = 24;
 constexpr int kWeightScaleBlocks = 16;
 struct WeightScaleJobs { WeightScaleJob j[kMaxScaleJobs]; };
 __global__ void weight_scale_kernel(const __grid_constant__ WeightScaleJobs jobs, ScaleState st, int begin_first, int begin_count) {
+  pdl_wait();
   __shared__ float sm[32];
   if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < begin_count) { const int i = begin_first + threadIdx.x; st.k[i] = st.k_next[i]; st.amax[i] = 0u; }
   const WeightScaleJob& q = jobs.j[blockIdx.y];
@@ -433,6 +447,7 @@ __device__ __forceinline__ void weight_prep_vec8(const float* __restrict__ w, __
 // slot >= 0: the weights' scale exponent comes from st.amax[slot] (weight_scale_kernel ran before) and is recorded in st.k[slot]
 __global__ void weight_prep_kernel(const float* __restrict__ w, __half* __restrict__ slab, int cout, int cin, int ntaps,
                                    int n_valid, int k_valid, int n_tiles, int n_chunks, int N, int transpose, int CW, ScaleState st, int slot) {
+  pdl_wait();
   const int total = n_tiles * n_chunks * ntaps * N * (CW >> 3);
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = slot >= 0 ? weight_scale_from_amax(st, slot) : 0;
@@ -446,6 +461,7 @@ struct WeightPrepJob { const float* w; __half* slab; int cout, cin, ntaps, n_val
 constexpr int kMaxPrepJobs = 48;
 struct WeightPrepJobs { WeightPrepJob j[kMaxPrepJobs]; };
 __global__ void weight_prep_batched_kernel(const __grid_constant__ WeightPrepJobs jobs, ScaleState st) {
+  pdl_wait();
   const WeightPrepJob& q = jobs.j[blockIdx.y];
   const int total = q.n_tiles * q.n_chunks * q.ntaps * q.N * (q.CW >> 3);
   const int k = weight_scale_from_amax(st, q.slot);
@@ -462,6 +478,7 @@ __global__ void weight_prep_batched_kernel(const __grid_constant__ WeightPrepJob
 constexpr int kColsumBlocks = 296;
 __global__ void colsum_stage1_kernel(const __half* __restrict__ dz, const __half* __restrict__ dz_lo, const int* __restrict__ k, long long rows, int cpitch,
                                      int coff, int C, float* __restrict__ partial) {
+  pdl_wait();
   extern __shared__ float sm[];   // [warps][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const long long per = (rows + gridDim.x - 1) / gridDim.x;
@@ -482,6 +499,7 @@ __global__ void colsum_stage1_kernel(const __half* __restrict__ dz, const __half
 
 // grid = ceil(C / 32), block = (32, 32): thread (lane, w) sums partials w, w+32, ... of channel blockIdx.x*32 + lane
 __global__ void colsum_stage2_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out, int accumulate) {
+  pdl_wait();
   __shared__ float sm[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float a0 = 0.f, a1 = 0.f;
@@ -505,6 +523,7 @@ struct BiasJob { const float* partial; float* out; int nblk, C; };
 constexpr int kMaxBiasJobs = 24;
 struct BiasJobs { BiasJob j[kMaxBiasJobs]; };
 __global__ void colsum_stage2_batched_kernel(const __grid_constant__ BiasJobs jobs) {
+  pdl_wait();
   __shared__ float sm[32][33];
   const BiasJob& q = jobs.j[blockIdx.y];
   const int c = blockIdx.x * 32 + threadIdx.x;

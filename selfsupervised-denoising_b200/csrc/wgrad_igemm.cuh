@@ -81,6 +81,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int n_units = p.n_co_tiles * p.n_ci_blocks * p.n_groups * p.ksplit;
   auto decode = [&](int u, int& ks, int& g, int& cb, int& ct) {
@@ -269,6 +271,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
 __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restrict__ partial, int ksplit, int ntaps, int cout, int cin,
                                                            int pitch, float* __restrict__ dw, int accumulate) {
   __shared__ float sm[16][33];
+  pdl_wait();
   const long long n = (long long)cout * pitch * ntaps;
   const long long idx = blockIdx.x * 32LL + threadIdx.x;   // over [tap][co][ci < pitch] (rows padded to `pitch` floats)
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -300,30 +303,38 @@ struct WgradReduceJob { const float* partial; float* dw; int ksplit, ntaps, cout
 constexpr int kMaxReduceJobs = 24;
 struct WgradReduceJobs { WgradReduceJob j[kMaxReduceJobs]; int n_jobs; };
 __global__ void __launch_bounds__(512) wgrad_reduce_batched_kernel(const __grid_constant__ WgradReduceJobs jobs) {
-  __shared__ float sm[16][33];
+  // block = (32 lanes x 4 outputs each, 16 K-split lanes): 16-byte loads of the float4-aligned partial rows
+  __shared__ float4 sm[16][33];
+  pdl_wait();
   int ji = 0;
   while (ji + 1 < jobs.n_jobs && (int)blockIdx.x >= jobs.j[ji + 1].first_block) ++ji;
   const WgradReduceJob& q = jobs.j[ji];
-  const long long n = (long long)q.cout * q.pitch * q.ntaps;
-  const long long idx = ((long long)blockIdx.x - q.first_block) * 32LL + threadIdx.x;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const long long n = (long long)q.cout * q.pitch * q.ntaps;              // a multiple of 4 (pitch is)
+  const long long idx = (((long long)blockIdx.x - q.first_block) * 32LL + threadIdx.x) * 4;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
   if (idx < n) {
     int k = threadIdx.y;
-    for (; k + 48 < q.ksplit; k += 64) {
-      a0 += __ldg(q.partial + (long long)k * n + idx); a1 += __ldg(q.partial + (long long)(k + 16) * n + idx);
-      a2 += __ldg(q.partial + (long long)(k + 32) * n + idx); a3 += __ldg(q.partial + (long long)(k + 48) * n + idx);
+    for (; k + 16 < q.ksplit; k += 32) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(q.partial + (long long)k * n + idx));
+      const float4 v = __ldg(reinterpret_cast<const float4*>(q.partial + (long long)(k + 16) * n + idx));
+      a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w; a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
     }
-    for (; k < q.ksplit; k += 16) a0 += __ldg(q.partial + (long long)k * n + idx);
+    for (; k < q.ksplit; k += 16) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(q.partial + (long long)k * n + idx));
+      a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+    }
   }
-  sm[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
+  sm[threadIdx.y][threadIdx.x] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
   __syncthreads();
   if (threadIdx.y == 0 && idx < n) {
-    float acc = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int w = 0; w < 16; ++w) acc += sm[w][threadIdx.x];
-    const int ci = (int)(idx % q.pitch); long long t = idx / q.pitch;
+    for (int w = 0; w < 16; ++w) { const float4 t = sm[w][threadIdx.x]; acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w; }
+    const int ci0 = (int)(idx % q.pitch); long long t = idx / q.pitch;       // the 4 outputs share (tap, co): pitch % 4 == 0
     const int co = (int)(t % q.cout); const int tap = (int)(t / q.cout);
-    if (ci < q.cin) q.dw[((long long)co * q.cin + ci) * q.ntaps + tap] = acc;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (ci0 + e < q.cin) q.dw[((long long)co * q.cin + ci0 + e) * q.ntaps + tap] = acc[e];
   }
 }
 static inline int wgrad_cin_pitch(int cin) { return (cin + 3) / 4 * 4; }
@@ -463,7 +474,7 @@ static inline cudaError_t wgrad_launch(const WgradPlan& plan, cudaStream_t strea
     cudaMemsetAsync(dev, 0, 1024 * 16 * sizeof(unsigned long long), stream);
     WgradParams p = plan.p; p.stats = dev;
     profiler().begin(K_WGRAD, plan.flops, plan.bytes, stream);
-    wgradk::wgrad_igemm_kernel<<<plan.grid, wgradk::kThreads, plan.smem, stream>>>(plan.dz, plan.x, p);
+    launch_pdl(wgradk::wgrad_igemm_kernel, dim3(plan.grid), dim3(wgradk::kThreads), plan.smem, stream, plan.dz, plan.x, p);
     profiler().end(stream);
     std::vector<unsigned long long> h((size_t)plan.grid * 16);
     cudaMemcpyAsync(h.data(), dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
@@ -476,7 +487,7 @@ static inline cudaError_t wgrad_launch(const WgradPlan& plan, cudaStream_t strea
     return e != cudaSuccess ? e : cudaGetLastError();
   }
   if (profiler().on) profiler().begin(K_WGRAD, plan.flops, plan.bytes, stream);
-  wgradk::wgrad_igemm_kernel<<<plan.grid, wgradk::kThreads, plan.smem, stream>>>(plan.dz, plan.x, plan.p);
+  cudaError_t e = launch_pdl(wgradk::wgrad_igemm_kernel, dim3(plan.grid), dim3(wgradk::kThreads), plan.smem, stream, plan.dz, plan.x, plan.p);
   if (profiler().on) profiler().end(stream);
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
