@@ -460,11 +460,15 @@ class Net {
     SSDN_CUDA(wgrad_launch(l.wgrad, ws_));     // its K-split partials are reduced by reduce_all_wgrads()
     return 0;
   }
-  // dW of every layer from its K-split partials: one launch on the stream the weight gradients ran on
-  int reduce_all_wgrads(float* grads, cudaStream_t st) {
+  // dW of the layers [first, last) of `order` (names in launch order) from their K-split partials: one launch on the stream
+  // the weight gradients ran on.  backward() calls it twice: for everything but the last two layers while the main stream
+  // still has work, and for those two at the very end (a short tail instead of an 80 us one).
+  int reduce_wgrads(float* grads, cudaStream_t st, bool last_two) {
     wgradk::WgradReduceJobs jobs{};
     int nj = 0, blocks = 0; double bytes = 0;
     for (auto& l : layers) {
+      const bool tail = (l.name == "encode_block_1.0" || l.name == "encode_block_1.2");
+      if (tail != last_two) continue;
       const int nt = l.ksize * l.ksize;
       const long long n = (long long)l.cout * l.wgrad.p.cin_pitch * nt;
       jobs.j[nj++] = {l.partial, grads + l.w_off, l.wgrad.p.ksplit, nt, l.cout, l.cin, l.wgrad.p.cin_pitch, blocks};
@@ -536,6 +540,7 @@ class Net {
       pool_bwd();
       if ((r = both("encode_block_" + std::to_string(i) + ".0", true))) return r;
     }
+    if ((r = reduce_wgrads(grads, (side && use_side && !profiler().on) ? side : st, false))) return r;   // all layers launched so far
     pool_bwd();
     if ((r = both("encode_block_1.2", true))) return r;
     if ((r = both("encode_block_1.0", false))) return r;
@@ -548,7 +553,7 @@ class Net {
       for (int j = 0; j < nj; ++j) pb += 4.0 * jobs.j[j].nblk * jobs.j[j].C;
       if (nj) SSDN_PROF(K_BIAS, 0, pb, st, (launch_pdl(pw::colsum_stage2_batched_kernel, dim3((maxc + 31) / 32, nj), dim3(32, 32), 0, st, jobs)));
     }
-    if ((r = reduce_all_wgrads(grads, (side && use_side && !profiler().on) ? side : st))) return r;
+    if ((r = reduce_wgrads(grads, (side && use_side && !profiler().on) ? side : st, true))) return r;
     if ((r = join_side(st))) return r;
     SSDN_PROF(K_SCALE, 0, 0, st, (launch_pdl(pw::scale_finish_kernel, dim3(1), dim3(32), 0, st, scales, kSlotG, n_slot_g, 1, stale_out, 1, 0, 0)));
     SSDN_CUDA(cudaGetLastError());
