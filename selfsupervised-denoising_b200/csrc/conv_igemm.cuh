@@ -54,6 +54,8 @@ struct ConvParams {
   uint32_t epi_off;   // byte offset of the epilogue staging area (8 warps x 32 pixels x 36 floats) in dynamic smem
   float acc_comp;     // 1 + SSDN_ACC_BETA x (MMA instructions accumulated into one output): truncation-bias compensation
   const int* k_a; const int* k_b;   // scale exponents of the A tensor and of the weight slab (device; null = 0)
+  uint64_t magic_s, magic_p;   // ceil(2^64 / src.S), ceil(2^64 / src.P): the epilogue's pixel -> (image, row, column) divisions
+  uint32_t wait_hint;          // suspend-time hint (ns) of the producers' / epilogue's mbarrier waits (0 = plain try_wait spin)
   int epi_split;      // 1: both epilogue warps of a TMEM lane quadrant work (alternate slices) - epilogue-bound layers; 0: one warp
                       //    per quadrant, the other four exit at once (they would only take issue slots and shared-memory
                       //    bandwidth from an MMA-bound layer)
@@ -91,57 +93,74 @@ struct Ring {
 constexpr int kStagePitch = 36;   // floats per staged pixel row (32 channels + 4 pad: conflict-free float4 access)
 constexpr int kMaxSlices = 6;     // 32-channel slices of one N tile (N <= 192)
 
-// What the epilogue needs to know about one lane's pixel of one 128-pixel tile.  Computed one tile ahead so that the
-// LeakyReLU sign-mask words (the only global LOADS of the epilogue) are in flight while the previous tile is written.
+// What the epilogue needs to know about one lane's pixel of one 128-pixel tile, for one work item (tile, 32-channel slice).
+// Computed one item ahead so that the LeakyReLU sign-mask word (the only global LOAD of the epilogue) is in flight while the
+// previous item is written.
 struct LanePixel {
-  int d0;            // destination flat pixel (first of 1 or 4), or source flat pixel for MAP_NCHW bookkeeping
-  int nd;            // number of destinations (0 = halo / out of range: nothing is written)
-  int zero;          // write zeros (row shifted in by Shift2d)
-  int cshift;        // channel shift of the destination (rotation branch block)
+  uint32_t pk;       // destination flat pixel (first of 1 or 4) in bits [0,26) | number of destinations (0 = halo / out of range:
+                     // nothing is written, 1, or 4) << 26 | write zeros (row shifted in by Shift2d) << 29 | rotation branch << 30
   int b, y, x;       // image / row / column of the source pixel (MAP_NCHW)
-  uint32_t mw[kMaxSlices];   // sign-mask words of the slices (EP_ACT_GRAD)
+  uint32_t mw;       // sign-mask word of the slice (EP_ACT_GRAD)
 };
+constexpr uint32_t kPkPixelMask = (1u << 26) - 1;
 
-__device__ __forceinline__ void lane_pixel(const ConvParams& p, int um, int nt, int tile, int T, int ew, int lane, LanePixel& o) {
+// n / d for n < 2^32 with m = ceil(2^64 / d) (host: div_magic_for): two wide multiplies instead of the ~70-instruction
+// 64-bit division subroutine the epilogue used to call twice per tile
+__device__ __forceinline__ uint32_t div_magic(uint32_t n, uint64_t m) { return (uint32_t)__umul64hi((uint64_t)n, m); }
+
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void lane_pixel(const ConvParams& p, int um, int nt, int tile, int s, int T, int ew, int lane, LanePixel& o) {
   const ConvDst& d = p.dst;
   const Geom& sg = p.src;
-  const long long j = (long long)um * 128 * T + tile * 128 + ew * 32 + lane;
-  const int b = (int)(j / sg.S);
-  const int rem = (int)(j - (long long)b * sg.S);
-  const int rr = rem / sg.P;
-  const int x = rem - rr * sg.P, y = rr - sg.row0;
-  const bool valid = (b < sg.B) && (y >= 0) && (x < sg.W);
-  o.b = b; o.y = y; o.x = x; o.nd = 0; o.zero = 0; o.cshift = 0; o.d0 = 0;
+  const uint32_t j = (uint32_t)um * (128u * T) + tile * 128 + ew * 32 + lane;
+  const uint32_t b = div_magic(j, p.magic_s);
+  const uint32_t rem = j - b * (uint32_t)sg.S;
+  const uint32_t rr = div_magic(rem, p.magic_p);
+  const int x = (int)(rem - rr * (uint32_t)sg.P), y = (int)rr - sg.row0;
+  const bool valid = ((int)b < sg.B) && (y >= 0) && (x < sg.W);
+  o.b = (int)b; o.y = y; o.x = x; o.mw = 0xffffffffu;
+  uint32_t d0 = 0, nd = 0, zero = 0, br = 0;
   if (valid) {
     const Geom& dg = d.g;
-    if (d.map == MAP_IDENT) { o.d0 = b * dg.S + (y + dg.row0) * dg.P + x; o.nd = 1; }
-    else if (d.map == MAP_UP2) { o.d0 = b * dg.S + (2 * y + dg.row0) * dg.P + 2 * x; o.nd = 4; }
+    if (d.map == MAP_IDENT) { d0 = b * dg.S + (y + dg.row0) * dg.P + x; nd = 1; }
+    else if (d.map == MAP_UP2) { d0 = b * dg.S + (2 * y + dg.row0) * dg.P + 2 * x; nd = 4; }
     else if (d.map == MAP_UNROT) {
-      const int br = b / d.nimg, n = b - br * d.nimg, H = sg.H, W = sg.W;
+      const int H = sg.H, W = sg.W;
+      br = ((int)b >= d.nimg) + ((int)b >= 2 * d.nimg) + ((int)b >= 3 * d.nimg);
+      const int n = (int)b - (int)br * d.nimg;
       const int pp = (y + 1 == H) ? 0 : y + 1, q = x;
-      o.zero = (y + 1 == H);
+      zero = (y + 1 == H);
       int i, jj;
       if (br == 0) { i = pp; jj = q; } else if (br == 1) { i = q; jj = H - 1 - pp; }
       else if (br == 2) { i = H - 1 - pp; jj = W - 1 - q; } else { i = W - 1 - q; jj = pp; }
-      o.d0 = n * dg.S + (i + dg.row0) * dg.P + jj; o.nd = 1; o.cshift = br * d.cvalid;
+      d0 = n * dg.S + (i + dg.row0) * dg.P + jj; nd = 1;
     } else if (d.map == MAP_UNROT_INV) {
-      const int br = nt, H = sg.H, W = sg.W;
+      const int brn = nt, H = sg.H, W = sg.W;
       int pp, q;
-      if (br == 0) { pp = y; q = x; } else if (br == 1) { pp = H - 1 - x; q = y; }
-      else if (br == 2) { pp = H - 1 - y; q = W - 1 - x; } else { pp = x; q = W - 1 - y; }
-      if (pp > 0) { o.d0 = (br * d.nimg + b) * dg.S + (pp - 1 + dg.row0) * dg.P + q; o.nd = 1; }
-    } else { o.nd = 1; }   // MAP_NCHW
+      if (brn == 0) { pp = y; q = x; } else if (brn == 1) { pp = H - 1 - x; q = y; }
+      else if (brn == 2) { pp = H - 1 - y; q = W - 1 - x; } else { pp = x; q = W - 1 - y; }
+      if (pp > 0) { d0 = (brn * d.nimg + b) * dg.S + (pp - 1 + dg.row0) * dg.P + q; nd = 1; }
+    } else { nd = 1; }   // MAP_NCHW
   }
-#pragma unroll
-  for (int s = 0; s < kMaxSlices; ++s) o.mw[s] = 0xffffffffu;
-  if ((d.flags & EP_ACT_GRAD) && o.nd) {
+  o.pk = d0 | (nd << 26) | (zero << 29) | (br << 30);
+  if ((d.flags & EP_ACT_GRAD) && nd) {
     // word of slice s: channel (first channel of the slice) / 32, in the mask row of the destination (or source) pixel
-    const long long row = (d.flags & EP_ACT_AT_SRC) ? j : (long long)o.d0;
+    const long long row = (d.flags & EP_ACT_AT_SRC) ? (long long)j : (long long)d0;
     const int c_first = ((d.flags & EP_ACT_AT_SRC) || d.map != MAP_UNROT_INV) ? nt * p.N : 0;
-    const uint32_t* mrow = d.mask_in + row * d.mask_in_words + (c_first >> 5);
-#pragma unroll
-    for (int s = 0; s < kMaxSlices; ++s)
-      if (32 * s < p.N && c_first + 32 * s < d.mask_in_words * 32) o.mw[s] = __ldg(mrow + s);
+    if (c_first + 32 * s < d.mask_in_words * 32) o.mw = __ldg(d.mask_in + row * d.mask_in_words + (c_first >> 5) + s);
   }
 }
 
@@ -209,7 +228,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int j0 = um * 128 * T;
       for (int ch = 0; ch < p.n_chunks; ++ch)
         for (int g = 0; g < p.n_groups; ++g) {
-          SSDN_TIMED(w_empty, umma::mbar_wait(empty_a(ra.stage), ra.phase ^ 1, abort_addr, p.error_flag, 1));
+          SSDN_TIMED(w_empty, umma::mbar_wait(empty_a(ra.stage), ra.phase ^ 1, abort_addr, p.error_flag, 1, p.wait_hint));
           const uint32_t dst = a_base + ra.stage * a_stage_bytes;
           const int row = j0 + p.groups[g].row_off;
           if (umma::elect_one()) {
@@ -249,7 +268,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int u = u_first; u < n_units; u += u_stride) {
       const int nt = u % p.n_tiles_n;
       for (int i = 0; i < n_bstages; ++i) {
-        SSDN_TIMED(w_empty, umma::mbar_wait(empty_b(rb.stage), rb.phase ^ 1, abort_addr, p.error_flag, 2));
+        SSDN_TIMED(w_empty, umma::mbar_wait(empty_b(rb.stage), rb.phase ^ 1, abort_addr, p.error_flag, 2, p.wait_hint));
         if (umma::elect_one()) {
           if (PAIR) {               // this CTA's half of the N rows of every slab (b_stage_bytes is the per-CTA size)
             const uint32_t lbar = umma::mapa(full_b(rb.stage), 0);
@@ -436,197 +455,212 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // TMEM -> registers (one pixel per lane, 32 channels per slice) -> scales / bias / LeakyReLU (+ sign-mask word out) or
     // LeakyReLU' from the sign-mask word -> optional column sums -> staged through shared memory -> fp16 hi/lo split ->
     // global memory with the upsample / (un-)rotate scatter in the address.
+    // WORK ITEMS: the (tile, slice) pairs of this CTA's units, numbered in consumption order w = unit * T * nsl + tile * nsl + s;
+    // warp j of a TMEM lane quadrant takes the items with w % kEpiPerQuad == j, so all three warps of a quadrant are busy
+    // whatever N is (N = 48: 4 items per unit over 3 warps; the old "slice s belongs to warp s % 3" left one warp idle and two
+    // with double work).  The epilogue is what binds the N = 48 / upsampling / 1x1 layers: the instruction count per item is
+    // what matters here (profiles/r02_epilogue_source_counters.txt).
     const ConvDst& d = p.dst;
     const Geom& sg = p.src;
     const int ew = (warp - 4) & 3;        // TMEM lane quadrant (a warp may only read lanes 32 * (warp % 4) ...)
-    const int half = (warp - 4) >> 2;     // which of the quadrant's warps: slices with s % kEpiPerQuad == half are its own
+    const int half = (warp - 4) >> 2;     // which of the quadrant's warps
     const int n_epi_warps = p.epi_split ? kEpiWarps : 4;
+    const int stride = p.epi_split ? kEpiPerQuad : 1;
+    const int nsl = (p.N + 31) >> 5, ipu = T * nsl;      // slices per tile, items per unit
     __shared__ __align__(16) float s_bias[400];
+    // accumulators carry 2^(k_a + k_b); operand destinations are written with their own scale 2^k_dst, which is folded into
+    // the accumulator scale and the bias (LeakyReLU commutes with a positive factor): one FFMA per element
+    const float dst_scale = ((d.flags & EP_WRITE_LO) && d.scale.k) ? exp2_int(__ldg(d.scale.k)) : 1.0f;
+    const float inv_dst_scale = 1.0f / dst_scale;          // exact: a power of two
+    const float out_scale = p.acc_comp * exp2_int(-((p.k_a ? __ldg(p.k_a) : 0) + (p.k_b ? __ldg(p.k_b) : 0))) * dst_scale;
     if (d.flags & EP_BIAS)
-      for (int i = threadIdx.x - 128; i < 400; i += 32 * n_epi_warps) s_bias[i] = i < d.cvalid ? __ldg(d.bias + i) : 0.f;
+      for (int i = threadIdx.x - 128; i < 400; i += 32 * n_epi_warps) s_bias[i] = i < d.cvalid ? __ldg(d.bias + i) * dst_scale : 0.f;
     asm volatile("bar.sync 1, %0;" ::"r"(32 * n_epi_warps) : "memory");
+    const uint32_t bias_s = umma::smem_u32(s_bias);
+    const uint32_t stage_s = sbase + p.epi_off + (uint32_t)(warp - 4) * (32 * kStagePitch * 4);     // this warp's staging area
+    const uint32_t row_s = stage_s + lane * (kStagePitch * 4);
     float csum[kMaxSlices];
 #pragma unroll
     for (int s = 0; s < kMaxSlices; ++s) csum[s] = 0.f;
-    // accumulators carry 2^(k_a + k_b); operand destinations are written with their own scale 2^k_dst
-    const float out_scale = p.acc_comp * exp2_int(-((p.k_a ? __ldg(p.k_a) : 0) + (p.k_b ? __ldg(p.k_b) : 0)));
-    const float dst_scale = ((d.flags & EP_WRITE_LO) && d.scale.k) ? exp2_int(__ldg(d.scale.k)) : 1.0f;
-    float amax_l = 0.f;        // running max|v| of what this lane wrote (next scale of the destination tensor)
-    int it = 0;
+    float amax_l = 0.f;        // running max|v| (in destination-scaled units) of what this lane wrote
     long long w_full = 0;
     const long long t_start = clock64();
-    LanePixel nxt;
-    if (u_first < n_units) lane_pixel(p, unit_m(u_first), u_first % p.n_tiles_n, 0, T, ew, lane, nxt);
+    const bool up2 = d.map == MAP_UP2;
     const uint32_t tmem_empty_lead0 = PAIR ? umma::mapa(tmem_empty(0), 0) : tmem_empty(0);   // the MMA issuer's barrier
+    // cursor over this warp's items: (c_it, c_u, c_i) = unit counter, unit, item inside the unit
+    int c_it = 0, c_u = u_first, c_i = half;
+    auto normalise = [&]() { while (c_i >= ipu && c_u < n_units) { c_i -= ipu; ++c_it; c_u += u_stride; } };
+    normalise();
+    LanePixel nxt;
+    if (c_u < n_units) { const int t0 = c_i >= nsl ? 1 : 0; lane_pixel(p, unit_m(c_u), c_u % p.n_tiles_n, t0, c_i - t0 * nsl, T, ew, lane, nxt); }
+    int it = 0;
     for (int u = u_first; u < n_units; u += u_stride, ++it) {
       const int buf = it & 1;
-      const int um = unit_m(u), nt = u % p.n_tiles_n;
-      SSDN_TIMED(w_full, umma::mbar_wait(tmem_full(buf), (it >> 1) & 1, abort_addr, p.error_flag, 4));
+      const int nt = u % p.n_tiles_n;
+      SSDN_TIMED(w_full, umma::mbar_wait(tmem_full(buf), (it >> 1) & 1, abort_addr, p.error_flag, 4, p.wait_hint));
       umma::tc_fence_after();
-      for (int tile = 0; tile < T; ++tile) {
-        const LanePixel cur = nxt;
-        {   // mapping + mask words of the next tile of this CTA (loads stay in flight while this tile is written)
-          int nu = u, ntile = tile + 1;
-          if (ntile == T) { ntile = 0; nu = u + u_stride; }
-          if (nu < n_units) lane_pixel(p, unit_m(nu), nu % p.n_tiles_n, ntile, T, ew, lane, nxt);
-        }
-        const uint32_t trow = tmem + (uint32_t(ew * 32) << 16) + (buf * T + tile) * p.N;
-        // NOT unrolled: six copies of the slice body (~600 instructions each) do not fit the instruction cache, and an
-        // epilogue warp that streams its code from L2 for every tile is several times slower (ncu: stall_no_inst)
 #pragma unroll 1
-        for (int s = 0; s < kMaxSlices; ++s) {
-          const int c0 = 32 * s;
-          if (c0 < p.N && (!p.epi_split || (s % kEpiPerQuad) == half)) {
-            // A slice is always handled as 32 columns: when N is not a multiple of 32 the last slice reads 16 columns that
-            // belong to nobody (all 512 TMEM columns are allocated) and channel validity is enforced where values leave
-            // the warp.  No per-element predication => less than half the instructions (the epilogue is issue-bound).
-            const int cg0 = (d.map == MAP_UNROT_INV ? 0 : nt * p.N) + c0;  // first channel of the slice among this conv's outputs
-            uint32_t r[32];
-            umma::tmem_ld16(trow + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-            umma::tmem_ld16(trow + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-            umma::tmem_ld_wait();
-            if (cg0 < d.cvalid) {
-              float f[32];
+      while (c_it == it && c_u < n_units) {
+        const int tile = c_i >= nsl ? 1 : 0, s = c_i - tile * nsl;
+        const LanePixel cur = nxt;
+        {   // next item of this warp: its pixel mapping + mask word (the load stays in flight while this item is written)
+          c_i += stride;
+          normalise();
+          if (c_u < n_units) { const int t1 = c_i >= nsl ? 1 : 0; lane_pixel(p, unit_m(c_u), c_u % p.n_tiles_n, t1, c_i - t1 * nsl, T, ew, lane, nxt); }
+        }
+        const int c0 = 32 * s;
+        // A slice is always handled as 32 columns: when N is not a multiple of 32 the last slice reads 16 columns that
+        // belong to nobody (all 512 TMEM columns are allocated) and channel validity is enforced where values leave
+        // the warp.  No per-element predication => less than half the instructions (the epilogue is issue-bound).
+        const int cg0 = (d.map == MAP_UNROT_INV ? 0 : nt * p.N) + c0;  // first channel of the slice among this conv's outputs
+        const uint32_t trow = tmem + (uint32_t(ew * 32) << 16) + (buf * T + tile) * p.N;
+        uint32_t r[32];
+        umma::tmem_ld16(trow + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        umma::tmem_ld16(trow + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        umma::tmem_ld_wait();
+        if (cg0 < d.cvalid) {
+          float f[32];
+          if (d.flags & EP_BIAS) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) * out_scale;
-              if (d.flags & EP_BIAS) {
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bq = lds128(bias_s + (cg0 + i) * 4);     // zero beyond cvalid
+              f[i] = fmaf(__uint_as_float(r[i]), out_scale, bq.x); f[i + 1] = fmaf(__uint_as_float(r[i + 1]), out_scale, bq.y);
+              f[i + 2] = fmaf(__uint_as_float(r[i + 2]), out_scale, bq.z); f[i + 3] = fmaf(__uint_as_float(r[i + 3]), out_scale, bq.w);
+            }
+          } else {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 bq = *reinterpret_cast<const float4*>(&s_bias[cg0 + i]);     // zero beyond cvalid
-                  f[i] += bq.x; f[i + 1] += bq.y; f[i + 2] += bq.z; f[i + 3] += bq.w;
-                }
-              }
-              if (d.flags & EP_LRELU) {
-                uint32_t word = 0;
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) * out_scale;
+          }
+          const uint32_t cur_nd = (cur.pk >> 26) & 7u;
+          if (d.flags & EP_LRELU) {
+            uint32_t word = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { word |= (f[i] > 0.f ? 1u : 0u) << i; f[i] = fmaxf(f[i], SSDN_LRELU_SLOPE * f[i]); }
-                if (d.mask_out && cur.nd == 1)
-                  d.mask_out[(long long)cur.d0 * d.mask_out_words + ((cur.cshift + cg0) >> 5)] = cur.zero ? 0u : word;
-              }
-              if (d.flags & EP_ACT_GRAD) {
-                uint32_t word = cur.mw[0];          // register array: select instead of a dynamic (local-memory) index
+            for (int i = 0; i < 32; ++i) { const bool pos = f[i] > 0.f; word |= (pos ? 1u : 0u) << i; f[i] = pos ? f[i] : SSDN_LRELU_SLOPE * f[i]; }
+            if (d.mask_out && cur_nd == 1)
+              d.mask_out[(long long)(cur.pk & kPkPixelMask) * d.mask_out_words + (((cur.pk >> 30) * d.cvalid + cg0) >> 5)] = (cur.pk & (1u << 29)) ? 0u : word;
+          }
+          if (d.flags & EP_ACT_GRAD) {
 #pragma unroll
-                for (int k = 1; k < kMaxSlices; ++k) word = (k == s) ? cur.mw[k] : word;
+            for (int i = 0; i < 32; ++i) f[i] = ((cur.mw >> i) & 1u) ? f[i] : SSDN_LRELU_SLOPE * f[i];
+          }
+          if (d.colsum) {
+            if (cur_nd == 0) {                  // halo / out-of-range pixels hold garbage accumulators
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = ((word >> i) & 1u) ? f[i] : SSDN_LRELU_SLOPE * f[i];
-              }
-              if (d.colsum) {
-                if (cur.nd == 0) {                  // halo / out-of-range pixels hold garbage accumulators
+              for (int i = 0; i < 32; ++i) f[i] = 0.f;
+            }
+            // transpose-reduce over the 32 pixels of the warp: after 5 exchange steps lane c holds the sum of channel c
+            float t16[16], t8[8], t4[4], t2[2];
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) f[i] = 0.f;
-                }
-                // transpose-reduce over the 32 pixels of the warp: after 5 exchange steps lane c holds the sum of channel c
-                float t16[16], t8[8], t4[4], t2[2];
+            for (int i = 0; i < 16; ++i) {
+              const bool up = lane & 16;
+              const float send = up ? f[i] : f[i + 16], keep = up ? f[i + 16] : f[i];
+              t16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const bool up = lane & 16;
-                  const float send = up ? f[i] : f[i + 16], keep = up ? f[i + 16] : f[i];
-                  t16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                }
+            for (int i = 0; i < 8; ++i) {
+              const bool up = lane & 8;
+              const float send = up ? t16[i] : t16[i + 8], keep = up ? t16[i + 8] : t16[i];
+              t8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const bool up = lane & 8;
-                  const float send = up ? t16[i] : t16[i + 8], keep = up ? t16[i + 8] : t16[i];
-                  t8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                }
+            for (int i = 0; i < 4; ++i) {
+              const bool up = lane & 4;
+              const float send = up ? t8[i] : t8[i + 4], keep = up ? t8[i + 4] : t8[i];
+              t4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const bool up = lane & 4;
-                  const float send = up ? t8[i] : t8[i + 4], keep = up ? t8[i + 4] : t8[i];
-                  t4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                }
+            for (int i = 0; i < 2; ++i) {
+              const bool up = lane & 2;
+              const float send = up ? t4[i] : t4[i + 2], keep = up ? t4[i + 2] : t4[i];
+              t2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            {
+              const bool up = lane & 1;
+              const float send = up ? t2[0] : t2[1], keep = up ? t2[1] : t2[0];
+              const float total = keep + __shfl_xor_sync(0xffffffffu, send, 1);
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                  const bool up = lane & 2;
-                  const float send = up ? t4[i] : t4[i + 2], keep = up ? t4[i + 2] : t4[i];
-                  t2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                }
-                {
-                  const bool up = lane & 1;
-                  const float send = up ? t2[0] : t2[1], keep = up ? t2[1] : t2[0];
-                  const float total = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-#pragma unroll
-                  for (int k = 0; k < kMaxSlices; ++k) csum[k] += (k == s) ? total : 0.f;
-                }
-              }
-              // Every slice goes through shared memory (36-float rows: conflict-free float4 access).  NHWC destinations:
-              // consecutive lanes then write one pixel's contiguous bytes (fp16 planes: 4 lanes x 16 bytes per plane, fp32:
-              // 8 lanes x 16 bytes) - whole sectors per store instruction instead of 32 fragments, which is what the load/store
-              // unit can sustain (upsampling writes each value 4 times).  NCHW destination (network output): a lane keeps its
-              // own pixel and walks the channels.
-              float* stage = reinterpret_cast<float*>(smem + p.epi_off) + (warp - 4) * 32 * kStagePitch;
-              float* row = stage + lane * kStagePitch;
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(row + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-              __syncwarp();
-              if (d.map == MAP_NCHW) {
-                if (cur.nd) {
-                  const long long hw = (long long)sg.H * sg.W;
-                  float* dst = d.v + ((long long)cur.b * d.cvalid + cg0) * hw + (long long)cur.y * sg.W + cur.x;
-                  const int nc = min(min(32, p.N - c0), d.cvalid - cg0);     // a slice may be cut by the N tile or by cvalid
-                  for (int c = 0; c < nc; ++c) dst[c * hw] = row[c];
-                }
-              } else if (d.flags & EP_WRITE_LO) {
-                // fp16 operand planes: 4 lanes per pixel (8 channels = 16 bytes per plane each), 8 pixels per pass
-                const int sub = lane >> 2, q8 = lane & 3;
-                const bool chan_ok = (c0 + 8 * q8 < p.N) && (cg0 + 8 * q8 < d.cvalid);
-                const int meta = cur.nd | (cur.zero << 3);
-#pragma unroll 2
-                for (int q = 0; q < 32; q += 8) {
-                  const int px = q + sub;
-                  const int pd0 = __shfl_sync(0xffffffffu, cur.d0, px), pmeta = __shfl_sync(0xffffffffu, meta, px);
-                  const int pcs = __shfl_sync(0xffffffffu, cur.cshift, px);
-                  if (chan_ok && (pmeta & 7)) {
-                    const float4 o0 = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 8 * q8);
-                    const float4 o1 = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 8 * q8 + 4);
-                    float f8[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-                    if (pmeta & 8) {                      // row shifted in by Shift2d
-#pragma unroll
-                      for (int i = 0; i < 8; ++i) f8[i] = 0.f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { amax_l = fmaxf(amax_l, fabsf(f8[i])); f8[i] *= dst_scale; }
-                    uint4 h, l;
-                    f16_split8(f8, h, l);
-                    const int cb = d.coff + pcs + cg0 + 8 * q8;
-                    for (int k = 0; k < (pmeta & 7); ++k) {
-                      const long long oi = (long long)(pd0 + (k & 1) + (k >> 1) * d.g.P) * d.cpitch + cb;
-                      *reinterpret_cast<uint4*>(d.hi + oi) = h;
-                      *reinterpret_cast<uint4*>(d.lo + oi) = l;
-                    }
-                  }
-                }
-              } else {
-                const int sub = lane >> 3, q4 = lane & 7;                  // 8 lanes per pixel, 4 pixels per pass
-                const bool chan_ok = (c0 + 4 * q4 < p.N) && (cg0 + 4 * q4 < d.cvalid);
-                const int meta = cur.nd | (cur.zero << 3);
-#pragma unroll 2
-                for (int q = 0; q < 32; q += 4) {
-                  const int px = q + sub;
-                  const int pd0 = __shfl_sync(0xffffffffu, cur.d0, px), pmeta = __shfl_sync(0xffffffffu, meta, px);
-                  const int pcs = __shfl_sync(0xffffffffu, cur.cshift, px);
-                  if (chan_ok && (pmeta & 7)) {
-                    float4 o = *reinterpret_cast<const float4*>(stage + px * kStagePitch + 4 * q4);
-                    if (pmeta & 8) o = make_float4(0.f, 0.f, 0.f, 0.f);     // row shifted in by Shift2d
-                    const int cb = d.coff + pcs + cg0 + 4 * q4;
-                    for (int k = 0; k < (pmeta & 7); ++k) {
-                      const long long oi = (long long)(pd0 + (k & 1) + (k >> 1) * d.g.P) * d.cpitch + cb;
-                      *reinterpret_cast<float4*>(d.v + oi) = o;
-                    }
-                  }
-                }
-              }
-              __syncwarp();
+              for (int k = 0; k < kMaxSlices; ++k) csum[k] += (k == s) ? total : 0.f;
             }
           }
+          // Every slice goes through shared memory (36-float rows: conflict-free float4 access).  NHWC destinations:
+          // consecutive lanes then write one pixel's contiguous bytes (fp16 planes: 4 lanes x 16 bytes per plane, fp32:
+          // 8 lanes x 16 bytes) - whole sectors per store instruction instead of 32 fragments, which is what the load/store
+          // unit can sustain (upsampling writes each value 4 times).  NCHW destination (network output): a lane keeps its
+          // own pixel and walks the channels.
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) sts128(row_s + i * 4, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
+          __syncwarp();
+          if (d.map == MAP_NCHW) {
+            if (cur_nd) {
+              const long long hw = (long long)sg.H * sg.W;
+              float* dst = d.v + ((long long)cur.b * d.cvalid + cg0) * hw + (long long)cur.y * sg.W + cur.x;
+              const int nc = min(min(32, p.N - c0), d.cvalid - cg0);     // a slice may be cut by the N tile or by cvalid
+              for (int c = 0; c < nc; ++c) dst[c * hw] = lds32(row_s + c * 4);
+            }
+          } else if (d.flags & EP_WRITE_LO) {
+            // fp16 operand planes: 4 lanes per pixel (8 channels = 16 bytes per plane each), 8 pixels per pass
+            const int sub = lane >> 2, q8 = lane & 3;
+            const bool chan_ok = (c0 + 8 * q8 < p.N) && (cg0 + 8 * q8 < d.cvalid);
+            const int cb0 = d.coff + cg0 + 8 * q8;
+#pragma unroll
+            for (int q = 0; q < 32; q += 8) {
+              const int px = q + sub;
+              const uint32_t ppk = __shfl_sync(0xffffffffu, cur.pk, px);
+              if (chan_ok && (ppk & (7u << 26))) {
+                const float4 o0 = lds128(stage_s + (px * kStagePitch + 8 * q8) * 4);
+                const float4 o1 = lds128(stage_s + (px * kStagePitch + 8 * q8 + 4) * 4);
+                float f8[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+                if (ppk & (1u << 29)) {                      // row shifted in by Shift2d
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f8[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) amax_l = fmaxf(amax_l, fabsf(f8[i]));
+                uint4 h, l;
+                f16_split8(f8, h, l);
+                const long long oi = (long long)(ppk & kPkPixelMask) * d.cpitch + (cb0 + (int)(ppk >> 30) * d.cvalid);
+                *reinterpret_cast<uint4*>(d.hi + oi) = h;
+                *reinterpret_cast<uint4*>(d.lo + oi) = l;
+                if (up2) {                                   // nearest-neighbour upsample: the 2 x 2 block
+                  const long long o1i = oi + d.cpitch, o2i = oi + (long long)d.g.P * d.cpitch, o3i = o2i + d.cpitch;
+                  *reinterpret_cast<uint4*>(d.hi + o1i) = h; *reinterpret_cast<uint4*>(d.lo + o1i) = l;
+                  *reinterpret_cast<uint4*>(d.hi + o2i) = h; *reinterpret_cast<uint4*>(d.lo + o2i) = l;
+                  *reinterpret_cast<uint4*>(d.hi + o3i) = h; *reinterpret_cast<uint4*>(d.lo + o3i) = l;
+                }
+              }
+            }
+          } else {
+            const int sub = lane >> 3, q4 = lane & 7;                  // 8 lanes per pixel, 4 pixels per pass
+            const bool chan_ok = (c0 + 4 * q4 < p.N) && (cg0 + 4 * q4 < d.cvalid);
+            const int cb0 = d.coff + cg0 + 4 * q4;
+#pragma unroll 4
+            for (int q = 0; q < 32; q += 4) {
+              const int px = q + sub;
+              const uint32_t ppk = __shfl_sync(0xffffffffu, cur.pk, px);
+              if (chan_ok && (ppk & (7u << 26))) {
+                float4 o = lds128(stage_s + (px * kStagePitch + 4 * q4) * 4);
+                if (ppk & (1u << 29)) o = make_float4(0.f, 0.f, 0.f, 0.f);     // row shifted in by Shift2d
+                const long long oi = (long long)(ppk & kPkPixelMask) * d.cpitch + (cb0 + (int)(ppk >> 30) * d.cvalid);
+                *reinterpret_cast<float4*>(d.v + oi) = o;
+                if (up2) {
+                  const long long o2i = oi + (long long)d.g.P * d.cpitch;
+                  *reinterpret_cast<float4*>(d.v + oi + d.cpitch) = o;
+                  *reinterpret_cast<float4*>(d.v + o2i) = o;
+                  *reinterpret_cast<float4*>(d.v + o2i + d.cpitch) = o;
+                }
+              }
+            }
+          }
+          __syncwarp();
         }
       }
       umma::tc_fence_before();
       if (PAIR) umma::mbar_arrive_cluster(tmem_empty_lead0 + 8 * buf); else umma::mbar_arrive(tmem_empty(buf));
     }
-    if (d.flags & EP_WRITE_LO) amax_commit(d.scale.amax, amax_l);
+    if (d.flags & EP_WRITE_LO) amax_commit(d.scale.amax, amax_l * inv_dst_scale);
     if (d.colsum) {
-      // this CTA only ever sees one N tile when gridDim.x is a multiple of n_tiles_n (the host guarantees it)
+      // this CTA only ever sees one N tile when gridDim.x is a multiple of n_tiles_n (the host guarantees it); a warp may have
+      // handled any slice of it.  Sums were taken in destination-scaled units.
       const int nt = u_first % p.n_tiles_n;
       const int c_first = (d.map == MAP_UNROT_INV) ? 0 : nt * p.N;
       float* row = d.colsum + (long long)(blockIdx.x * n_epi_warps + (warp - 4)) * d.colsum_pitch;
@@ -635,7 +669,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // lane -> channel of the transpose-reduce: bit k of the lane selected the upper half at step k, i.e. channel == lane
 #pragma unroll
       for (int s = 0; s < kMaxSlices; ++s)
-        if (32 * s + lane < p.N && (!p.epi_split || (s % kEpiPerQuad) == half) && c_first + 32 * s + lane < d.colsum_pitch && (u_first < n_units)) row[c_first + 32 * s + lane] = csum[s];
+        if (32 * s + lane < p.N && c_first + 32 * s + lane < d.colsum_pitch && (u_first < n_units)) row[c_first + 32 * s + lane] = csum[s] * inv_dst_scale;
     }
     if (p.stats && threadIdx.x == 128) { p.stats[blockIdx.x * 16 + 6] = w_full; p.stats[blockIdx.x * 16 + 7] = clock64() - t_start; }
   }
@@ -652,7 +686,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #include <cstdlib>
 #include <vector>
 
-struct ConvTaps { int n; int off[9]; };   // flat-pixel offsets of the taps, in weight-slab order
+struct ConvTaps { int n; int off[9]; };
+#ifndef SSDN_WAIT_HINT_DEFAULT
+#define SSDN_WAIT_HINT_DEFAULT 0
+#endif
+// ceil(2^64 / d) for d >= 2: umulhi64(n, m) == n / d for every n < 2^32 (convk::div_magic)
+static inline uint64_t div_magic_for(uint32_t d) { return ~0ULL / d + 1; }   // flat-pixel offsets of the taps, in weight-slab order
 
 // 1x1 convolutions whose input channels come in whole 64-channel groups use the wide chunk (see ConvParams::wide).
 static inline bool conv_is_wide(int cin, int ntaps) { return ntaps == 1 && cin % 64 == 0; }
@@ -676,6 +715,14 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const __half* 
   p = ConvParams{};
   p.src = src; p.N = N; p.dst = dst; p.error_flag = error_flag; p.k_a = k_a; p.k_b = k_b;
   p.debug = getenv("SSDN_CONV_DEBUG") ? atoi(getenv("SSDN_CONV_DEBUG")) : 0;
+  {
+    static const int hint = getenv("SSDN_WAIT_HINT") ? atoi(getenv("SSDN_WAIT_HINT")) : SSDN_WAIT_HINT_DEFAULT;
+    p.wait_hint = (uint32_t)hint;
+  }
+  // the epilogue's index arithmetic: 32-bit flat pixels, destination pixels packed into 26 bits (LanePixel::pk)
+  if (src.total() + 512 >= (1LL << 31) || src.S < 2 || src.P < 2) return -17;
+  if (dst.map != MAP_NCHW && dst.g.total() >= (1LL << 26)) return -17;
+  p.magic_s = div_magic_for((uint32_t)src.S); p.magic_p = div_magic_for((uint32_t)src.P);
   p.n_tiles_n = cout_padded / N;
   p.wide = conv_is_wide(cin, taps.n) ? 1 : 0;
   conv_chunks(cin, &p.n_chunks, &p.ksteps_last, p.wide);

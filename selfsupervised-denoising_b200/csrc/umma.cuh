@@ -53,17 +53,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the warp may sleep in hardware up to that long instead of spinning through the
+// issue slots of its scheduler (which the epilogue warps need)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded spin: a kernel bug must not hang the GPU box.  On expiry the CTA-wide abort word (shared memory) is set;
 // every later wait of the CTA then returns at once, so the kernel drains quickly (its results are garbage and the
 // host sees the error flag).  The return value is deliberately NOT used for control flow by the callers: loop
 // structure stays warp-uniform, which is what lets ptxas keep MMA / TMA operands in uniform registers.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t abort_addr, int* error_flag, int code) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t abort_addr, int* error_flag, int code, uint32_t hint_ns = 0) {
   uint32_t aborted;
   asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(aborted) : "r"(abort_addr) : "memory");
   if (aborted) return;
 #ifdef UMMA_UNBOUNDED_WAIT
   while (!mbar_try_wait(bar, parity)) {}
 #else
+  if (hint_ns) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 22); ++i)
+      if (mbar_try_wait_hint(bar, parity, hint_ns)) return;
+  } else
 #pragma unroll 1      // ptxas otherwise unrolls the spin 64x at every call site: the kernels are instruction-cache-bound enough
   for (uint32_t i = 0; i < (1u << 22); ++i)
     if (mbar_try_wait(bar, parity)) return;
@@ -214,8 +232,12 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // arrive / expect_tx on a barrier given by a shared::cluster address (possibly in the peer CTA)
+// RELAXED: the only thing this arrival orders is TMEM traffic, which tcgen05.fence::before_thread_sync (issued by the caller)
+// and the waiter's tcgen05.fence::after_thread_sync take care of.  The .release.cluster form compiles to MEMBAR.ALL.GPU +
+// ERRBAR, i.e. the epilogue warp stalls until every global store it has in flight is acknowledged - 10 % of the epilogue's
+// time in the CTA-pair kernels (profiles/r02_epilogue_source_counters.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
