@@ -35,7 +35,8 @@ __global__ void scale_init_kernel(pw::ScaleState st, int first, int count, int v
 
 struct Layer {               // one convolution of the network
   std::string name;
-  int cin, cout, ksize;
+  int cin, cout, ksize;       // GEMM view: the first conv is (9 * Cin, 48, 1) over the im2col'd input (same flat weight order)
+  bool im2col = false;
   size_t w_off, b_off;       // offsets (floats) into the flat parameter / gradient buffers
   // forward
   ConvPlan fwd; __half* slab_f; int n_f; int coutp_f;
@@ -64,7 +65,7 @@ class Net {
   std::vector<Layer> layers;                       // in PARAMETER order (noise_network.py registration order)
   size_t n_params = 0;
   // buffers
-  Buf cat[6], e[6], e1a, p5, d_a[6], head_in, h1, h2;
+  Buf cat[6], e[6], e1a, p5, d_a[6], head_in, h1, h2, xcol;
   Buf g_out, dz_h2, dz_h1, dz_db[6], dz_da[6], gcat[6], dz_e[7], dz_e1a, g_p[6];
   float* partial = nullptr; float* colpart = nullptr; int* flag = nullptr;
   pw::ScaleState scales{}; int n_slot_a = 0, n_slot_g = 0;   // operand-scale state (device) and the number of slots per range
@@ -98,7 +99,7 @@ class Net {
   const Buf* find_buf(const std::string& nm) const {
     auto idx = [&](const char* pre) -> int { return (nm.rfind(pre, 0) == 0 && nm.size() == strlen(pre) + 1) ? nm.back() - '0' : -1; };
     int i;
-    if (nm == "e1a") return &e1a; if (nm == "p5") return &p5; if (nm == "head_in") return &head_in;
+    if (nm == "e1a") return &e1a; if (nm == "xcol") return &xcol; if (nm == "p5") return &p5; if (nm == "head_in") return &head_in;
     if (nm == "h1") return &h1; if (nm == "h2") return &h2; if (nm == "g_out") return &g_out;
     if (nm == "dz_h2") return &dz_h2; if (nm == "dz_h1") return &dz_h1; if (nm == "dz_e1a") return &dz_e1a;
     if ((i = idx("cat")) >= 1 && i <= 5) return &cat[i];
@@ -121,7 +122,9 @@ class Net {
       l.b_off = n_params; n_params += co;
       layers.push_back(l);
     };
-    add("encode_block_1.0", Cin, 48, 3); add("encode_block_1.2", 48, 48, 3);
+    // the first conv as a 1x1 GEMM over xcol (pw::pack_im2col3x3_kernel): a [48][Cin][3][3] weight IS a [48][9 Cin] matrix
+    add("encode_block_1.0", 9 * Cin, 48, 1); layers.back().im2col = true;
+    add("encode_block_1.2", 48, 48, 3);
     for (int i = 2; i <= 6; ++i) add("encode_block_" + std::to_string(i) + ".0", 48, 48, 3);
     add("decode_block_5.0", 96, 96, 3); add("decode_block_5.2", 96, 96, 3);
     for (int i = 4; i >= 2; --i) { add("decode_block_" + std::to_string(i) + ".0", 144, 96, 3); add("decode_block_" + std::to_string(i) + ".2", 96, 96, 3); }
@@ -148,8 +151,11 @@ class Net {
       slot(b, kind == 1 ? kSlotA + n_slot_a++ : kSlotG + n_slot_g++);
     };
     auto mkmask = [&](Buf& b) { b.mask_words = (b.cpitch + 31) / 32; b.mask = a.take<uint32_t>((size_t)b.g.total() * b.mask_words); };
-    const int c1 = round_up(96 + Cin, 8);
+    // 16 channels = 32 bytes: every pixel of the largest concat buffer starts on a sector boundary, so the upsampling epilogue
+    // that fills it writes whole sectors (with a pitch of 104 channels it wrote 25 % more sectors, half of them partial)
+    const int c1 = round_up(96 + Cin, 16);
     mk(cat[1], g[0], c1, 1); mk(e1a, g[0], 48, 1); mk(e[1], g[0], 48, 1);
+    mk(xcol, g[0], round_up(9 * Cin, 8), 1);
     mk(cat[2], g[1], 144, 1); mk(e[2], g[1], 48, 1);
     mk(cat[3], g[2], 144, 1); mk(e[3], g[2], 48, 1);
     mk(cat[4], g[3], 144, 1); mk(e[4], g[3], 48, 1);
@@ -187,7 +193,7 @@ class Net {
     // wgrad partials: one buffer per layer, so that a single batched reduction at the end of backward() finishes them all
     partial_floats = 0;
     for (auto& l : layers) {
-      const Geom& gg = (l.ksize == 1) ? gh : g[level_of(l.name)];
+      const Geom& gg = l.im2col ? g[0] : (l.ksize == 1) ? gh : g[level_of(l.name)];
       l.ksplit = wgrad_pick_ksplit(gg.total(), l.cout, l.cin, l.ksize * l.ksize, sms, gg.P);
       const size_t pf = wgrad_partial_floats(l.ksplit, l.ksize * l.ksize, l.cout, l.cin);
       l.partial = a.take<float>(pf);
@@ -219,7 +225,7 @@ class Net {
     int r;
     const int act = EP_BIAS | EP_LRELU | EP_WRITE_LO;
     // ---- encoder
-    if ((r = plan_fwd(L("encode_block_1.0"), cat[1], 96, dst(e1a, 0, MAP_IDENT, act, 48)))) return r;
+    if ((r = plan_fwd(L("encode_block_1.0"), xcol, 0, dst(e1a, 0, MAP_IDENT, act, 48)))) return r;
     if ((r = plan_fwd(L("encode_block_1.2"), e1a, 0, dst(e[1], 0, MAP_IDENT, act, 48)))) return r;
     pools.push_back({&e[1], &cat[2], 96});
     for (int i = 2; i <= 4; ++i) {
@@ -292,7 +298,7 @@ class Net {
     // ---- backward: weight gradients
     struct WG { const char* nm; const Buf* x; int xoff; const Buf* dz; };
     const WG wg[] = {
-        {"encode_block_1.0", &cat[1], 96, &dz_e1a}, {"encode_block_1.2", &e1a, 0, &dz_e[1]},
+        {"encode_block_1.0", &xcol, 0, &dz_e1a}, {"encode_block_1.2", &e1a, 0, &dz_e[1]},
         {"encode_block_2.0", &cat[2], 96, &dz_e[2]}, {"encode_block_3.0", &cat[3], 96, &dz_e[3]},
         {"encode_block_4.0", &cat[4], 96, &dz_e[4]}, {"encode_block_5.0", &cat[5], 48, &dz_e[5]},
         {"encode_block_6.0", &p5, 0, &dz_e[6]},
@@ -412,6 +418,9 @@ class Net {
     SSDN_PROF(K_PACK, 0, (double)N * Cin * H * W * 4.0 + (double)B * H * W * Cin * 4.0, st,
               (launch_pdl(pw::pack_nchw_pixel_kernel, dim3(pw::grid_for((long long)B * H * W)), dim3(pw::kBlock), 0, st, x, cat[1].hi, cat[1].lo, N, Cin, H, W, g[0],
                                                                                                     cat[1].cpitch, 96, blind ? 1 : 0, cat[1].sc)));
+    SSDN_PROF(K_PACK, 0, (double)N * Cin * H * W * 4.0 + (double)B * H * W * xcol.cpitch * 4.0, st,
+              (launch_pdl(pw::pack_im2col3x3_kernel, dim3(pw::grid_for((long long)B * H * W * (xcol.cpitch / 8))), dim3(pw::kBlock), 0, st, x, xcol.hi, xcol.lo, N, Cin, H, W,
+                          g[0], xcol.cpitch, blind ? 2 : 1, blind ? 1 : 0, xcol.sc)));
     size_t pi = 0;
     auto pool = [&]() {
       const PoolOp& p = pools[pi++];

@@ -83,6 +83,50 @@ __global__ void pack_nchw_pixel_kernel(const float* __restrict__ x, __half* __re
   amax_commit(sc.amax, m);
 }
 
+// The FIRST convolution runs as a 1x1 GEMM over an im2col'd input (net.cuh): xcol[flat pixel][k], k = c * 9 + kh * 3 + kw (the
+// flat order of a PyTorch [co][ci][kh][kw] weight row), holds x(c, i + kh - sh, j + kw - 1) of the (rotated) image and zero
+// outside it (sh = 2: half-plane ShiftConv2d, 1: plain conv).  With 3 input channels a stencil tap is a K = 3 sliver of a
+// K = 16 MMA: nine taps cost nine MMAs per k-step and product where one N = 32 (weight gradient) / one chunk (forward) now do.
+// One thread = 8 consecutive k of one pixel (one 16-byte store per plane); the gathers hit L1 / L2 (the input is a few MB).
+__global__ void pack_im2col3x3_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                                      int B, int C, int H, int W, Geom g, int cpitch, int sh, int rot4, ScaleRef sc) {
+  pdl_wait();
+  const int groups = cpitch >> 3;
+  const long long n = (long long)(rot4 ? 4 : 1) * B * H * W * groups;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const float s = sc.k ? exp2_int(__ldg(sc.k)) : 1.0f;
+  float m = 0.f;
+  if (idx < n) {
+    const int q = (int)(idx % groups); long long t = idx / groups;
+    const int j = (int)(t % W); t /= W;
+    const int i = (int)(t % H); const int bo = (int)(t / H);
+    const int r = rot4 ? bo / B : 0, b = rot4 ? bo % B : bo;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = 8 * q + e;
+      float val = 0.f;
+      if (k < 9 * C) {
+        const int c = k / 9, tap = k - 9 * c, kh = tap / 3, kw = tap - 3 * kh;
+        const int ii = i + kh - sh, jj = j + kw - 1;
+        if (ii >= 0 && ii < H && jj >= 0 && jj < W) {
+          int si = ii, sj = jj;
+          if (r == 1) { si = jj; sj = W - 1 - ii; } else if (r == 2) { si = H - 1 - ii; sj = W - 1 - jj; }
+          else if (r == 3) { si = H - 1 - jj; sj = ii; }
+          val = __ldg(x + (((long long)b * C + c) * H + si) * W + sj);
+        }
+      }
+      m = fmaxf(m, fabsf(val));
+      f[e] = val * s;
+    }
+    uint4 h, l;
+    f16_split8(f, h, l);
+    const long long o = ((long long)bo * g.S + (i + g.row0) * g.P + j) * cpitch + 8 * q;
+    *reinterpret_cast<uint4*>(hi + o) = h; *reinterpret_cast<uint4*>(lo + o) = l;
+  }
+  amax_commit(sc.amax, m);
+}
+
 // padded flat -> dense NCHW (tests / debugging): plane 0: value = (hi + lo) * 2^-k, 1: lo, 2: hi (as stored, scaled)
 __global__ void unpack_nchw_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, const int* __restrict__ k, int plane,
                                    float* __restrict__ y, int B, int C, int H, int W, Geom g, int cpitch, int coff) {
