@@ -129,7 +129,7 @@ extern "C" int ssdn_profile_records(double* out, int max_records) {
 extern "C" int ssdn_net_kernel_launches(void* handle, int training) {
   net::Net* nn = (net::Net*)handle;
   const int nl = (int)nn->layers.size();
-  int fwd = nl /*conv*/ + 5 /*pool*/ + 2 /*pack, im2col of the first conv*/ + 2 /*weight scales, weight slabs*/ + 1 /*scale finish*/;
+  int fwd = nl /*conv*/ + 5 /*pool*/ + 1 /*pack: rotation stack + im2col of the first conv*/ + 2 /*weight scales, weight slabs*/ + 1 /*scale finish*/;
   int bwd = 3 /*loss-gradient scale, pack, column sums*/ + nl /*wgrad*/ + 2 /*split-K reductions*/ + 1 /*all bias reductions*/ + (nl - 1) /*dgrad*/ +
             5 + 5 /*pool, upsample*/ + 1 /*scale finish*/;
   return training ? fwd + bwd : fwd;

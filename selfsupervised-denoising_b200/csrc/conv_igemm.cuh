@@ -751,8 +751,9 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const __half* 
     }
     const char* e = getenv("SSDN_CONV_PAIR");
     // measured (profiles/r01_pair_split_ablation.log): pairs never lose except on the one-chunk first convolution
-    // 1x1 layers: only the wide-N, deep-K head conv gains (its B stream is what saturates the TMA unit); measured
-    const bool wide_ok = p.wide && N >= 192 && p.n_chunks >= 4;
+    // (1x1 layers are shared-memory-bound INCLUDING the TMA fill traffic - no tap reuses a staged byte - and a pair halves the
+    // B bytes per CTA: measured -12 % on the un-rotating head data-gradient (4 N tiles of 96), +8 % on the 96-wide head conv)
+    const bool wide_ok = p.wide && (cout_padded >= 192 || (e && atoi(e) == 2)) && p.n_chunks >= 4;   // SSDN_CONV_PAIR=2: every deep wide layer (ablation)
     p.pair = (rows_ok || wide_ok) && (N % 16 == 0) && (num_sms % 2 == 0) && p.n_chunks >= 2 && !(e && atoi(e) == 0);
     if (p.wide && e && atoi(e) == 3) p.pair = 0;   // ablation: pairs on the 3x3 layers only
   }

@@ -397,9 +397,28 @@ class Net {
     }
     double slab_bytes = 0;
     for (int j = 0; j < nj; ++j) slab_bytes += 2.0 * 2.0 * jobs.j[j].n_tiles * jobs.j[j].n_chunks * jobs.j[j].ntaps * jobs.j[j].N * jobs.j[j].CW;
-    SSDN_PROF(K_WEIGHT_PREP, 0, slab_bytes + 4.0 * n_params * (with_dgrad ? 2 : 1), st,
-              (launch_pdl(pw::weight_prep_batched_kernel, dim3(64, nj), dim3(pw::kBlock), 0, st, jobs, scales)));
+    // the slabs are independent of the input pack that follows: they are prepared on the side stream (forward() joins it before
+    // the first convolution), two latency-bound kernels side by side instead of one after the other
+    cudaStream_t ps = st;
+    prep_forked = false;
+    if (use_side && !profiler().on) {
+      int r = ensure_side(); if (r) return r;
+      SSDN_CUDA(cudaEventRecord(ev_fork, st));          // the weight scales (and the begun activation pass) are complete
+      SSDN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      ps = side; prep_forked = true;
+    }
+    SSDN_PROF(K_WEIGHT_PREP, 0, slab_bytes + 4.0 * n_params * (with_dgrad ? 2 : 1), ps,
+              (launch_pdl(pw::weight_prep_batched_kernel, dim3(64, nj), dim3(pw::kBlock), 0, ps, jobs, scales)));
     SSDN_CUDA(cudaGetLastError());
+    return 0;
+  }
+  bool prep_forked = false;
+  int ensure_side() {
+    if (!side) {
+      SSDN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+      SSDN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      SSDN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
     return 0;
   }
 
@@ -415,12 +434,15 @@ class Net {
     int r;
     ++fwd_runs;                 // (the pass over the activation slots is begun by prep_weights' first kernel)
     if ((r = prep_weights(params, st, training))) return r;
-    SSDN_PROF(K_PACK, 0, (double)N * Cin * H * W * 4.0 + (double)B * H * W * Cin * 4.0, st,
-              (launch_pdl(pw::pack_nchw_pixel_kernel, dim3(pw::grid_for((long long)B * H * W)), dim3(pw::kBlock), 0, st, x, cat[1].hi, cat[1].lo, N, Cin, H, W, g[0],
-                                                                                                    cat[1].cpitch, 96, blind ? 1 : 0, cat[1].sc)));
-    SSDN_PROF(K_PACK, 0, (double)N * Cin * H * W * 4.0 + (double)B * H * W * xcol.cpitch * 4.0, st,
-              (launch_pdl(pw::pack_im2col3x3_kernel, dim3(pw::grid_for((long long)B * H * W * (xcol.cpitch / 8))), dim3(pw::kBlock), 0, st, x, xcol.hi, xcol.lo, N, Cin, H, W,
-                          g[0], xcol.cpitch, blind ? 2 : 1, blind ? 1 : 0, xcol.sc)));
+    {   // the input: rotation stack -> its channel slot of the last concat buffer + the first conv's im2col operand, one kernel
+      const int tiles = ((H + pw::kPackTileH - 1) / pw::kPackTileH) * ((W + pw::kPackTileW - 1) / pw::kPackTileW);
+      const size_t smem = (size_t)Cin * pw::kPackRegH * pw::kPackRegPitch * sizeof(float);
+      if (smem > 48 * 1024) return eng::fail(-7, "input with %d channels does not fit the pack kernel's tile", Cin);
+      SSDN_PROF(K_PACK, 0, (double)N * Cin * H * W * 4.0 + (double)B * H * W * (round_up(Cin, 8) + xcol.cpitch) * 4.0, st,
+                (launch_pdl(pw::pack_input_kernel, dim3(B * tiles), dim3(256), smem, st, x, cat[1].hi, cat[1].lo, cat[1].cpitch, 96, cat[1].sc,
+                            xcol.hi, xcol.lo, xcol.cpitch, xcol.sc, N, Cin, H, W, g[0], blind ? 2 : 1, blind ? 1 : 0)));
+    }
+    if (prep_forked) { if ((r = join_side(st))) return r; }      // the weight slabs are ready
     size_t pi = 0;
     auto pool = [&]() {
       const PoolOp& p = pools[pi++];
@@ -456,11 +478,7 @@ class Net {
     }   // else: backward() finishes all bias gradients with one batched reduction after the last producer
     cudaStream_t ws_ = st;
     if (use_side && !profiler().on) {   // per-launch profiling serialises everything on one stream
-      if (!side) {
-        SSDN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-        SSDN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-        SSDN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-      }
+      { int rs = ensure_side(); if (rs) return rs; }
       SSDN_CUDA(cudaEventRecord(ev_fork, st));          // this layer's dZ (and everything before it) is complete
       SSDN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
       ws_ = side;
