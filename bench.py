@@ -260,9 +260,13 @@ class Case:
         from ssdn.params import PipelineOutput
         from ssdn.train import train_step
         data = [self.host[0], self.host[1], dict(self.host[2])]
-        out = self.graphed(data) if self.graphed is not None else train_step(self.den, self.opt, data, self.world)
-        # D2H read of the step's result into pinned memory.  Asynchronous, like a trainer that logs without stalling the
-        # device: every copy is enqueued inside the timed region and completes before timed()'s final synchronize.
+        if self.graphed is not None:
+            # host batch -> copy stream -> the slot's graph; the per-sample loss reaches pinned host memory through the graph's
+            # last node (GraphedTrainStep.loss_host()): every copy runs inside the timed region and completes before timed()'s
+            # final synchronize.  Asynchronous, like a trainer that logs without stalling the device.
+            self.graphed(data)
+            return
+        out = train_step(self.den, self.opt, data, self.world)
         self.host_loss.copy_(out[PipelineOutput.LOSS].detach(), non_blocking=True)
 
     def plans(self):

@@ -146,65 +146,134 @@ def train_step(denoiser: Denoiser, optimizer: FlatAdam, data: List, world_size: 
 
 class GraphedTrainStep:
     """train_step for a FIXED batch shape as ONE CUDA-graph launch: zero_grad -> run_pipeline -> mean(loss).backward() ->
-    (gradient all-reduce) -> Adam are captured once (after eager warm-up steps that also settle the operand scales) and
-    replayed for every batch.  A step is ~110 kernel launches; on the small per-GPU batches of strong scaling their launch
-    cost, not the device work, is what bounds the eager step.  Inputs are copied into the graph's static buffers, the step's
-    scalars (learning rate, Adam bias corrections, 1 / world_size) live in a device buffer that is refreshed before each replay.
-    The returned outputs are the graph's static tensors: read (or copy) them before the next call.  Outputs of earlier EAGER
-    steps must not be alive when the graph is captured (their autograd graph pins gradient accumulators to the default stream)."""
+    (gradient all-reduce) -> Adam -> loss to pinned host memory are captured once (after eager warm-up steps that also settle the
+    operand scales) and replayed for every batch.  A step is ~110 kernel launches; on the small per-GPU batches of strong
+    scaling their launch cost, not the device work, is what bounds the eager step.
+
+    Input pipeline: the graph is captured TWICE, over two sets of static input buffers ("slots").  Call i stages its batch and
+    the step's scalars (learning rate, Adam bias corrections, 1 / world_size: six floats in pinned memory) into slot i % 2 on a
+    COPY stream and replays that slot's graph on the current stream once the copies have landed - so the host-to-device copy
+    of batch i + 1 runs while step i computes, and nothing but graph launches (and two event operations) is ever queued on the
+    compute stream: stream operations between two graph launches each cost a 10 - 40 us bubble (tests/dev_e2e_breakdown.py).
+    Host batches should be pinned (torch's caching host allocator keeps a pinned block alive until the copy that reads it has
+    run); device batches work too (the copy then waits for whatever produced them on the current stream).
+
+    The returned outputs are the slot's static tensors: they stay valid until the call after the next one.  `loss_host()` is
+    the step's per-sample loss in pinned host memory, written by the graph's last node (valid after a synchronize / the
+    slot's `done` event).  Outputs of earlier EAGER steps must not be alive when the graph is captured (their autograd graph
+    pins gradient accumulators to the default stream)."""
+
+    N_SLOTS = 2
 
     def __init__(self, denoiser: Denoiser, optimizer: FlatAdam, example: List, world_size: int = 1, warmup: int = 3):
         self.denoiser, self.optimizer, self.world_size = denoiser, optimizer, world_size
         dev = denoiser.device
         to_dev = lambda t: t.to(dev).clone() if torch.is_tensor(t) and t.numel() else t     # noqa: E731
         md = example[NoisyDataset.METADATA] if len(example) > NoisyDataset.METADATA else {}
-        self.static = [to_dev(example[0]), to_dev(example[1]) if len(example) > 1 else None,
-                       {k: to_dev(v) for k, v in md.items() if k != NoisyDataset.Metadata.CLEAN}]
-        self.hyper = torch.zeros(6, dtype=torch.float32, device=dev)
+
+        def make_slot():
+            return [to_dev(example[0]), to_dev(example[1]) if len(example) > 1 else None,
+                    {k: to_dev(v) for k, v in md.items() if k != NoisyDataset.Metadata.CLEAN}]
+        self.slots = [make_slot() for _ in range(self.N_SLOTS)]
+        self.hyper = [torch.zeros(6, dtype=torch.float32, device=dev) for _ in range(self.N_SLOTS)]
+        self.hyper_host = [torch.zeros(6, dtype=torch.float32).pin_memory() for _ in range(self.N_SLOTS)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in range(self.N_SLOTS)]     # the slot's inputs have landed (copy stream)
+        self.done = [torch.cuda.Event() for _ in range(self.N_SLOTS)]      # the replay that read the slot has finished
+        self.calls = 0
+        self.last = 0
         import gc
         gc.collect()
+        cur = torch.cuda.current_stream(dev)
+        self._stage(0, None)
+        cur.wait_event(self.ready[0])
         side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
+        side.wait_stream(cur)
         with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):            # eager steps: lazily created streams / attributes / settled operand scales
-                self._refresh_hyper()
-                self._body()
-        torch.cuda.current_stream(dev).wait_stream(side)
+            for i in range(max(1, warmup)):            # eager steps: lazily created streams / attributes / settled operand scales
+                if i:
+                    self._stage(0, None)
+                    side.wait_event(self.ready[0])
+                out = self._body(0)
+                loss_shape, loss_dtype = out[PipelineOutput.LOSS].shape, out[PipelineOutput.LOSS].dtype
+                del out
+                self.done[0].record(side)
+        cur.wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        self._refresh_hyper()
-        with torch.cuda.graph(self.graph):
-            self.outputs = self._body()
-        # the captured launch itself did not execute: run it once so that step_count and the weights agree
-        self.graph.replay()
+        self.graphs, self._outputs = [], []
+        self._loss_host = [torch.empty(loss_shape, dtype=loss_dtype).pin_memory() for _ in range(self.N_SLOTS)]   # (not during capture)
+        for s in range(self.N_SLOTS):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._body(s)
+                # a memcpy node: the step's result reaches the host without a stream operation of its own
+                self._loss_host[s].copy_(out[PipelineOutput.LOSS].detach(), non_blocking=True)
+            self.graphs.append(g); self._outputs.append(out)
+        # the captured launches themselves did not execute: run slot 0's once so that step_count and the weights agree
+        self._stage(0, None)
+        cur.wait_event(self.ready[0])
+        self.graphs[0].replay()
+        self.done[0].record(cur)
+        self.calls = 1
 
-    def _refresh_hyper(self):
+    @property
+    def outputs(self) -> Dict:
+        """Outputs (static tensors) of the most recent step."""
+        return self._outputs[self.last]
+
+    @property
+    def static(self) -> List:
+        return self.slots[self.last]
+
+    def loss_host(self) -> torch.Tensor:
+        """Per-sample loss of the most recent step in pinned host memory (complete once that step has finished on the device)."""
+        return self._loss_host[self.last]
+
+    def _stage(self, s: int, data: Optional[List]):
+        """Queue the copies of `data` (None: keep the slot's contents) and of the step's scalars into slot s on the copy stream."""
         self.optimizer.step_count += 1
-        # from pageable memory on purpose: the driver stages the six floats before the call returns, so the next refresh
-        # cannot overwrite them while an earlier replay is still queued
-        self.hyper.copy_(torch.tensor(self.optimizer.hyper_values(1.0 / self.world_size), dtype=torch.float32))
+        self.ready[s].synchronize()                     # the previous copy out of this slot's pinned scalars has run (two calls ago)
+        self.hyper_host[s].copy_(torch.tensor(self.optimizer.hyper_values(1.0 / self.world_size), dtype=torch.float32))
+        cur = torch.cuda.current_stream(self.denoiser.device)
+        cs = self.copy_stream
+        cs.wait_event(self.done[s])                     # the replay that last read this slot has finished
+        slot = self.slots[s]
+        with torch.cuda.stream(cs):
+            if data is not None:
+                md = data[NoisyDataset.METADATA] if len(data) > NoisyDataset.METADATA else {}
+                pairs = [(slot[0], data[0])]
+                if slot[1] is not None and torch.is_tensor(slot[1]) and slot[1].numel():
+                    pairs.append((slot[1], data[1]))
+                pairs += [(v, md[k]) for k, v in slot[2].items() if torch.is_tensor(v) and k in md]
+                if any(src.is_cuda for _, src in pairs):
+                    cs.wait_stream(cur)                 # device batches: whatever produced them on the current stream comes first
+                for dst, src in pairs:
+                    dst.copy_(src, non_blocking=True)
+                    if src.is_cuda:
+                        src.record_stream(cs)
+            self.hyper[s].copy_(self.hyper_host[s], non_blocking=True)
+            self.ready[s].record(cs)
 
-    def _body(self):
+    def _body(self, s: int):
         self.optimizer.zero_grad()
         self.denoiser.dp_world_size = self.world_size
-        outputs = self.denoiser.run_pipeline(self.static)
+        outputs = self.denoiser.run_pipeline(self.slots[s])
         torch.mean(outputs[PipelineOutput.LOSS]).backward()
         if self.world_size > 1:
             dist.all_reduce(self.denoiser.flat_gradients_with_flags(), op=dist.ReduceOp.SUM)
-        self.optimizer.step_dev(self.hyper)
+        self.optimizer.step_dev(self.hyper[s])
         return outputs
 
     def __call__(self, data: List) -> Dict:
-        self.static[0].copy_(data[0], non_blocking=True)
-        if self.static[1] is not None and torch.is_tensor(self.static[1]) and self.static[1].numel():
-            self.static[1].copy_(data[1], non_blocking=True)
-        md = data[NoisyDataset.METADATA] if len(data) > NoisyDataset.METADATA else {}
-        for k, v in self.static[2].items():
-            if torch.is_tensor(v) and k in md:
-                v.copy_(md[k], non_blocking=True)
-        self._refresh_hyper()
-        self.graph.replay()
-        return self.outputs
+        s = self.calls % self.N_SLOTS
+        self.calls += 1
+        self._stage(s, data)
+        cur = torch.cuda.current_stream(self.denoiser.device)
+        cur.wait_event(self.ready[s])
+        self.graphs[s].replay()
+        self.done[s].record(cur)
+        self.last = s
+        return self._outputs[s]
 
 
 def learning_rate(cfg: Dict, iteration: int) -> float:
