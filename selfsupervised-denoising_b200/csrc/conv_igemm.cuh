@@ -294,6 +294,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t acc) {
       if (PAIR) umma::mma_f16_lo_pair(d, a_lo, b_lo, hi, idesc, acc); else umma::mma_f16_lo(d, a_lo, b_lo, hi, idesc, acc);
     };
+    auto mma_fill = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi) { umma::mma_f16_lo_cu<umma::CU_FILL, PAIR>(d, a_lo, b_lo, hi, idesc, 1u); };
+    auto mma_last = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi) { umma::mma_f16_lo_cu<umma::CU_LASTUSE, PAIR>(d, a_lo, b_lo, hi, idesc, 1u); };
     auto commit = [&](uint32_t bar) { if (PAIR) umma::mma_commit_pair(bar); else umma::mma_commit(bar); };
     int it = 0;
     long long w_tmem = 0, w_a = 0, w_b = 0;
@@ -320,13 +322,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
 #pragma unroll
-              for (int prod = 0; prod < 3; ++prod) {
-#pragma unroll
-                for (int tile = 0; tile < T; ++tile) {          // tiles innermost: consecutive MMAs alternate accumulators
-                  const uint32_t d = d0 + tile * p.N;
-                  const uint32_t av = a0 + tile * 1024 + 2 * k, al = av + a_pl, bv = b0 + 2 * k, bl = bv + b_pl;
-                  mma(d, prod == 0 ? al : av, prod == 1 ? bl : bv, desc_hi, (k == 0 && prod == 0) ? first : 1u);
-                }
+              for (int tile = 0; tile < T; ++tile) {
+                // the three products of one (tile, k-step) back to back: the hi*lo and hi*hi products share the A_hi tile,
+                // which the second one takes from the tensor core's collector instead of shared memory (umma::mma_f16_lo_cu)
+                const uint32_t d = d0 + tile * p.N;
+                const uint32_t av = a0 + tile * 1024 + 2 * k, al = av + a_pl, bv = b0 + 2 * k, bl = bv + b_pl;
+                mma(d, al, bv, desc_hi, k == 0 ? first : 1u);
+                mma_fill(d, av, bl, desc_hi);
+                mma_last(d, av, bv, desc_hi);
               }
             }
             commit(empty_b(rb.stage));
@@ -371,14 +374,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 for (int j = 0; j < 3; ++j) {
                   const uint32_t aj = a0 + j * step, bj = b0 + j * slab;
 #pragma unroll
-                  for (int q = 0; q < 6; ++q) {           // q = k-step * 3 + product (lo*hi, hi*lo, hi*hi)
-                    if (q < 3 || two) {
-                      const uint32_t ko = (q >= 3) ? 2u : 0u, prod = q % 3;
+                  for (int ks = 0; ks < 2; ++ks) {        // k-steps of the chunk; per (tile, k-step) the products lo*hi, hi*lo, hi*hi
+                    if (ks == 0 || two) {
+                      const uint32_t ko = ks ? 2u : 0u;
 #pragma unroll
                       for (int tile = 0; tile < T; ++tile) {
                         const uint32_t d = d0 + tile * p.N;
                         const uint32_t av = aj + tile * 512 + ko, al = av + a_pl, bv = bj + ko, bl = bv + b_pl;
-                        mma(d, prod == 0 ? al : av, prod == 1 ? bl : bv, desc_hi, (j == 0 && q == 0) ? first : 1u);
+                        mma(d, al, bv, desc_hi, (j == 0 && ks == 0) ? first : 1u);
+                        mma_fill(d, av, bl, desc_hi);      // A_hi: fetched once for the two products that use it
+                        mma_last(d, av, bv, desc_hi);
                       }
                     }
                   }

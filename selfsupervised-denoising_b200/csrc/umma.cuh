@@ -191,6 +191,32 @@ __device__ __forceinline__ void mma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint3
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same MMA with a COLLECTOR hint for the A operand: the tensor core keeps the A tile it fetched from shared memory in its
+// collector buffer (FILL), later MMAs with the SAME A descriptor read it from there instead of shared memory (USE), the last one
+// releases it (LASTUSE).  SS-mode MMAs are shared-memory-bandwidth-bound (A 4 KB + B 32 N bytes per instruction at 128 B/clk):
+// when consecutive instructions share A - the taps of a weight-gradient stencil, the hi*lo / hi*hi products of a tile - this
+// takes most of the A bytes off the shared-memory port.  SASS: UTCHMMA gdesc[..].A_KEEP / .A_REUSE.A_KEEP / .A_REUSE.
+enum : int { CU_NONE = 0, CU_FILL = 1, CU_USE = 2, CU_LASTUSE = 3 };
+template <int CU, bool PAIR>
+__device__ __forceinline__ void mma_f16_lo_cu(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+#define SSDN_MMA_CU(GROUP, SUFFIX)                                                                                      \
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t" \
+               "tcgen05.mma.cta_group::" GROUP ".kind::f16" SUFFIX " [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),        \
+               "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)                                          \
+               : "memory")
+#ifdef SSDN_NO_COLLECTOR          // ablation build: the same instruction stream without the hints
+  if (PAIR) SSDN_MMA_CU("2", ""); else SSDN_MMA_CU("1", "");
+#else
+  if (PAIR) {
+    if (CU == CU_FILL) SSDN_MMA_CU("2", ".collector::a::fill"); else if (CU == CU_USE) SSDN_MMA_CU("2", ".collector::a::use");
+    else if (CU == CU_LASTUSE) SSDN_MMA_CU("2", ".collector::a::lastuse"); else SSDN_MMA_CU("2", "");
+  } else {
+    if (CU == CU_FILL) SSDN_MMA_CU("1", ".collector::a::fill"); else if (CU == CU_USE) SSDN_MMA_CU("1", ".collector::a::use");
+    else if (CU == CU_LASTUSE) SSDN_MMA_CU("1", ".collector::a::lastuse"); else SSDN_MMA_CU("1", "");
+  }
+#endif
+#undef SSDN_MMA_CU
+}
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(

@@ -151,6 +151,9 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
           if (umma::elect_one()) {
             // taps innermost: consecutive MMAs accumulate into DIFFERENT accumulators (see conv_igemm.cuh).  Two fully
             // unrolled variants - the elected thread must have next to nothing to do between two MMAs (the queue is short).
+            // The A tile (dZ) of a k-step is the same for every tap: it is fetched from shared memory ONCE per plane use
+            // (collector FILL on the first tap, USE on the others, LASTUSE on the last - the dz_lo tile serves one product, the
+            // dz_hi tile the hi*lo and the hi*hi product back to back) instead of once per MMA.
             if (p.rows_per_group == 3) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {            // k-steps of 16 pixels (2048 bytes = 128 units); a tap shifts X by one row (8 units)
@@ -163,13 +166,17 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
                       for (int j = 0; j < 3; ++j) {
                         const uint32_t d = tmem + (3 * r + j) * N;
                         const uint32_t ah = a0 + k * 128, al = ah + a_pl, bh = b0 + r * rstep + j * 8 + k * 128, bl = bh + b_pl;
-                        umma::mma_f16_lo(d, prod == 0 ? al : ah, prod == 1 ? bl : bh, desc_hi, idesc, (k == 0 && prod == 0) ? acc : 1u);
+                        const uint32_t a_ = prod == 0 ? al : ah, b_ = prod == 1 ? bl : bh, acc_ = (k == 0 && prod == 0) ? acc : 1u;
+                        const bool first = (prod == 0 || prod == 1) && r == 0 && j == 0, last = (prod == 0 || prod == 2) && r == 2 && j == 2;
+                        if (first) umma::mma_f16_lo_cu<umma::CU_FILL, false>(d, a_, b_, desc_hi, idesc, acc_);
+                        else if (last) umma::mma_f16_lo_cu<umma::CU_LASTUSE, false>(d, a_, b_, desc_hi, idesc, acc_);
+                        else umma::mma_f16_lo_cu<umma::CU_USE, false>(d, a_, b_, desc_hi, idesc, acc_);
                       }
                     }
                   }
                 }
               }
-            } else {
+            } else if (ntaps == 3) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (k < nk) {
@@ -177,13 +184,25 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_cons
                   for (int prod = 0; prod < 3; ++prod) {
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
-                      if (t < ntaps) {
-                        const uint32_t d = tmem + t * N;
-                        const uint32_t ah = a0 + k * 128, al = ah + a_pl, bh = b0 + t * 8 + k * 128, bl = bh + b_pl;
-                        umma::mma_f16_lo(d, prod == 0 ? al : ah, prod == 1 ? bl : bh, desc_hi, idesc, (k == 0 && prod == 0) ? acc : 1u);
-                      }
+                      const uint32_t d = tmem + t * N;
+                      const uint32_t ah = a0 + k * 128, al = ah + a_pl, bh = b0 + t * 8 + k * 128, bl = bh + b_pl;
+                      const uint32_t a_ = prod == 0 ? al : ah, b_ = prod == 1 ? bl : bh, acc_ = (k == 0 && prod == 0) ? acc : 1u;
+                      const bool first = (prod == 0 || prod == 1) && t == 0, last = (prod == 0 || prod == 2) && t == 2;
+                      if (first) umma::mma_f16_lo_cu<umma::CU_FILL, false>(d, a_, b_, desc_hi, idesc, acc_);
+                      else if (last) umma::mma_f16_lo_cu<umma::CU_LASTUSE, false>(d, a_, b_, desc_hi, idesc, acc_);
+                      else umma::mma_f16_lo_cu<umma::CU_USE, false>(d, a_, b_, desc_hi, idesc, acc_);
                     }
                   }
+                }
+              }
+            } else {                                   // one tap (1x1 layers): the dz_hi tile still serves two products in a row
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < nk) {
+                  const uint32_t ah = a0 + k * 128, al = ah + a_pl, bh = b0 + k * 128, bl = bh + b_pl;
+                  umma::mma_f16_lo(tmem, al, bh, desc_hi, idesc, k == 0 ? acc : 1u);
+                  umma::mma_f16_lo_cu<umma::CU_FILL, false>(tmem, ah, bl, desc_hi, idesc, 1u);
+                  umma::mma_f16_lo_cu<umma::CU_LASTUSE, false>(tmem, ah, bh, desc_hi, idesc, 1u);
                 }
               }
             }

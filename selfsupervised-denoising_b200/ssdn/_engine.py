@@ -11,7 +11,8 @@ from ctypes import c_double, c_int, c_longlong, c_size_t, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libssdn_b200.so")
+# SSDN_B200_LIB: another build of the same engine (developer A/B runs); there is no other implementation to fall back to
+LIB_PATH = os.environ.get("SSDN_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libssdn_b200.so")
 _lib = None
 
 _P, _I, _Z, _LL, _D = c_void_p, c_int, c_size_t, c_longlong, c_double

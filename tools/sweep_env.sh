@@ -3,7 +3,7 @@
 # runs tests/dev_layer_times.py under each and prints the per-kind totals + the big layers
 mkdir -p gpurun_out
 for setting in "$@"; do
-  tag=$(echo "$setting" | tr ' =' '__')
+  tag=$(echo "$setting" | tr ' =/' '___')
   if [ "$setting" == "none" ]; then env python tests/dev_layer_times.py > gpurun_out/sweep_$tag.log 2>&1
   else env $setting python tests/dev_layer_times.py > gpurun_out/sweep_$tag.log 2>&1; fi
   echo "== $setting"
