@@ -40,7 +40,7 @@ if has ncu; then
      python tests/dev_layer_times.py > gpurun_out/${TAG}_ncu_conv.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad_igemm_kernel -s 3 -c 2 -f -o gpurun_out/${TAG}_wgrad \
      python tests/dev_layer_times.py > gpurun_out/${TAG}_ncu_wgrad.log 2>&1
-  timeout 600 ncu --set full --clock-control none -k regex:"pool_bwd|up_bwd|pool_fwd|wgrad_reduce_batched|pack_nchw_pixel|adam|posterior" -c 14 -f -o gpurun_out/${TAG}_pointwise \
+  timeout 600 ncu --set full --clock-control none -k regex:"pool_bwd|up_bwd|pool_fwd|wgrad_reduce_batched|pack_nchw_pixel|pack_input|adam|posterior" -c 16 -f -o gpurun_out/${TAG}_pointwise \
      python tests/dev_layer_times.py > gpurun_out/${TAG}_ncu_pointwise.log 2>&1
 fi
 if has sanitize; then
