@@ -67,14 +67,28 @@ struct Geom {            // geometry of one padded-flat tensor
 #include <cstdlib>
 #include <utility>
 static inline bool pdl_enabled() { static const bool on = !(getenv("SSDN_PDL") && atoi(getenv("SSDN_PDL")) == 0); return on; }
+// Launch priority of the kernels on the CRITICAL path (everything except the weight gradients, which run on the side stream and
+// only have to be done by the end of the backward pass): when CTAs of both are pending, the critical path's are placed first and
+// the weight gradients fill the SMs the small pyramid levels leave idle.  A launch attribute (captured into CUDA graphs), relative
+// to the device's range (0 = least urgent).  An experiment knob (SSDN_MAIN_PRIORITY=-2), see below.
+// MEASURED (tools/sweep_bench.sh, interleaved runs): priority -2 / -5 on the critical path makes the step 5 % SLOWER (3.92 vs 3.71 ms) -
+// the weight gradients are then pushed to the end of the backward pass, where nothing overlaps them - so the default is 0 (off).
+static inline int main_priority() { static const int p = getenv("SSDN_MAIN_PRIORITY") ? atoi(getenv("SSDN_MAIN_PRIORITY")) : 0; return p; }
+inline bool& launching_background() { static thread_local bool b = false; return b; }   // set around the side-stream launches
+static inline int launch_attrs(cudaLaunchAttribute* a, bool cluster2) {                   // fills a[0..], returns the count
+  int n = 0;
+  if (cluster2) { a[n].id = cudaLaunchAttributeClusterDimension; a[n].val.clusterDim.x = 2; a[n].val.clusterDim.y = 1; a[n].val.clusterDim.z = 1; ++n; }
+  if (pdl_enabled()) { a[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; a[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+  if (main_priority() != 0 && !launching_background()) { a[n].id = cudaLaunchAttributePriority; a[n].val.priority = main_priority(); ++n; }
+  return n;
+}
 // kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute (see pdl_wait)
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute a[1];
-  a[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; a[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = a; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchAttribute a[3];
+  cfg.attrs = a; cfg.numAttrs = launch_attrs(a, false);
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

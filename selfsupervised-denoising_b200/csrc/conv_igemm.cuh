@@ -548,44 +548,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = ((cur.mw >> i) & 1u) ? f[i] : SSDN_LRELU_SLOPE * f[i];
           }
-          if (d.colsum) {
-            if (cur_nd == 0) {                  // halo / out-of-range pixels hold garbage accumulators
+          if (d.colsum && cur_nd == 0) {        // halo / out-of-range pixels hold garbage accumulators: they must not reach the column sums
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = 0.f;
-            }
-            // transpose-reduce over the 32 pixels of the warp: after 5 exchange steps lane c holds the sum of channel c
-            float t16[16], t8[8], t4[4], t2[2];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const bool up = lane & 16;
-              const float send = up ? f[i] : f[i + 16], keep = up ? f[i + 16] : f[i];
-              t16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const bool up = lane & 8;
-              const float send = up ? t16[i] : t16[i + 8], keep = up ? t16[i + 8] : t16[i];
-              t8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const bool up = lane & 4;
-              const float send = up ? t8[i] : t8[i + 4], keep = up ? t8[i + 4] : t8[i];
-              t4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const bool up = lane & 2;
-              const float send = up ? t4[i] : t4[i + 2], keep = up ? t4[i + 2] : t4[i];
-              t2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-            {
-              const bool up = lane & 1;
-              const float send = up ? t2[0] : t2[1], keep = up ? t2[1] : t2[0];
-              const float total = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-#pragma unroll
-              for (int k = 0; k < kMaxSlices; ++k) csum[k] += (k == s) ? total : 0.f;
-            }
+            for (int i = 0; i < 32; ++i) f[i] = 0.f;
           }
           // Every slice goes through shared memory (36-float rows: conflict-free float4 access).  NHWC destinations:
           // consecutive lanes then write one pixel's contiguous bytes (fp16 planes: 4 lanes x 16 bytes per plane, fp32:
@@ -595,6 +560,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; i += 4) sts128(row_s + i * 4, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
           __syncwarp();
+          if (d.colsum) {
+            // column sums of the staged tile (bias gradient): lane c adds channel c of the 32 pixel rows - bank (4 px + c) % 32,
+            // conflict-free - in a fixed order; half the instructions of a shuffle transpose-reduce over the registers
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+            for (int px = 0; px < 32; px += 4) {
+              t0 += lds32(stage_s + ((px + 0) * kStagePitch + lane) * 4); t1 += lds32(stage_s + ((px + 1) * kStagePitch + lane) * 4);
+              t2 += lds32(stage_s + ((px + 2) * kStagePitch + lane) * 4); t3 += lds32(stage_s + ((px + 3) * kStagePitch + lane) * 4);
+            }
+            const float total = (t0 + t1) + (t2 + t3);
+#pragma unroll
+            for (int k = 0; k < kMaxSlices; ++k) csum[k] += (k == s) ? total : 0.f;
+          }
           if (d.map == MAP_NCHW) {
             if (cur_nd) {
               const long long hw = (long long)sg.H * sg.W;
@@ -671,7 +649,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       float* row = d.colsum + (long long)(blockIdx.x * n_epi_warps + (warp - 4)) * d.colsum_pitch;
       for (int c = lane; c < d.colsum_pitch; c += 32) row[c] = 0.f;
       __syncwarp();
-      // lane -> channel of the transpose-reduce: bit k of the lane selected the upper half at step k, i.e. channel == lane
+      // lane c holds the column sum of channel c of each slice
 #pragma unroll
       for (int s = 0; s < kMaxSlices; ++s)
         if (32 * s + lane < p.N && c_first + 32 * s + lane < d.colsum_pitch && (u_first < n_units)) row[c_first + 32 * s + lane] = csum[s] * inv_dst_scale;
@@ -939,11 +917,8 @@ static inline cudaError_t conv_launch_raw(const ConvPlan& plan, const ConvParams
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(convk::kThreads); cfg.dynamicSmemBytes = plan.smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaLaunchAttribute attr[3];
+  cfg.attrs = attr; cfg.numAttrs = launch_attrs(attr, true);
   if (p.T == 2) return cudaLaunchKernelEx(&cfg, convk::conv_igemm_kernel<2, true>, plan.a, plan.b, p);
   return cudaLaunchKernelEx(&cfg, convk::conv_igemm_kernel<1, true>, plan.a, plan.b, p);
 }

@@ -484,7 +484,10 @@ class Net {
       ws_ = side;
     }
     (void)nt;
-    SSDN_CUDA(wgrad_launch(l.wgrad, ws_));     // its K-split partials are reduced by reduce_all_wgrads()
+    launching_background() = (ws_ != st);      // off the critical path: default launch priority (common.cuh: main_priority)
+    cudaError_t we = wgrad_launch(l.wgrad, ws_);     // its K-split partials are reduced by reduce_all_wgrads()
+    launching_background() = false;
+    SSDN_CUDA(we);
     return 0;
   }
   // dW of the layers [first, last) of `order` (names in launch order) from their K-split partials: one launch on the stream
@@ -503,7 +506,9 @@ class Net {
       bytes += (double)n * 4 * (l.wgrad.p.ksplit + 1);
     }
     jobs.n_jobs = nj;
+    launching_background() = (st == side);
     SSDN_PROF(K_WGRAD_REDUCE, 0, bytes, st, (launch_pdl(wgradk::wgrad_reduce_batched_kernel, dim3(blocks), dim3(32, 16), 0, st, jobs)));
+    launching_background() = false;
     SSDN_CUDA(cudaGetLastError());
     return 0;
   }

@@ -395,7 +395,10 @@ static inline int wgrad_pick_ksplit(long long k_total, int cout, int cin, int nt
   const int others = n_co_tiles * n_ci_blocks * n_groups;
   static const int units_per_sm = getenv("SSDN_WGRAD_UNITS_PER_SM") ? atoi(getenv("SSDN_WGRAD_UNITS_PER_SM")) : 1;   // measured: 1 > 2 > 3 (fewer partials to write and reduce)
   int ks = std::max(1, (units_per_sm * num_sms) / others);   // whole waves only: one unit more would cost a whole extra wave
-  ks = std::min(ks, std::max(1, n_kchunks / 4));
+  // at least 4 chunks per unit on the large levels (fewer partials to write and reduce); on the small pyramid levels the serial MMA
+  // chain of a unit IS the kernel's duration (4 chunks x 108 MMAs = 8 us of a 15 us kernel): one or two chunks per unit there
+  const int min_chunks = n_kchunks <= 256 ? 1 : 4;
+  ks = std::min(ks, std::max(1, n_kchunks / min_chunks));
   ks = std::max(1, std::min(ks, n_kchunks));
   const int cps = (n_kchunks + ks - 1) / ks;      // no K split may be empty: its accumulator would be undefined
   return (n_kchunks + cps - 1) / cps;
