@@ -155,3 +155,30 @@ def test_forward_at_patch_128(engine):
     out = plan.forward(_flat(p, O.param_order(3, 9, True)), x.cuda(), training=False)
     plan.check()
     assert rel(out, O.noise_network_forward(p, x, True)) < TOL
+
+
+@pytest.mark.parametrize("blind", [True, False])
+def test_input_pack_im2col_operand(engine, blind):
+    """pack_input_kernel: the first convolution's im2col operand xcol[pixel][c * 9 + kh * 3 + kw] = x_rot(c, i + kh - sh, j + kw - 1)
+    (sh = 2: half-plane ShiftConv2d, models/noise_network.py:241-260; 1: plain conv), zero outside the image, for the rotation stack
+    of utils/data.py:42-67 - and the input's own channel slot of the last concat buffer.  The values are the inputs themselves
+    (two fp16 planes reproduce an fp32 to 2^-22), the padding is exactly zero."""
+    n, size = 2, 32
+    x = torch.rand(n, 3, size, size, generator=torch.Generator().manual_seed(5)) * 1.3 - 0.1
+    params = O.init_params(3, 9 if blind else 3, blind, generator=torch.Generator().manual_seed(1))
+    cout = 9 if blind else 3
+    plan = engine.NetPlan(n, 3, cout, size, size, blind, "cuda")
+    flat = _flat(params, O.param_order(3, cout, blind))
+    plan.forward(flat, x.cuda(), training=False)
+    plan.forward(flat, x.cuda(), training=False)                 # second pass: settled operand scales
+    xr = O.rot4_stack(x) if blind else x                          # [4n or n, 3, H, W]
+    sh = 2 if blind else 1
+    padded = torch.nn.functional.pad(xr, (1, 1, sh, 2 - sh))
+    cols = torch.stack([padded[:, :, kh:kh + size, kw:kw + size] for kh in range(3) for kw in range(3)], 2)   # [B, 3, 9, H, W]
+    want = cols.reshape(xr.shape[0], 27, size, size)
+    got = plan.debug_read("xcol", 32).cpu()
+    assert got.shape == (xr.shape[0], 32, size, size)
+    assert (got[:, :27] - want).abs().max() <= 1e-6 and torch.equal(got[:, 27:], torch.zeros_like(got[:, 27:]))
+    assert torch.equal(got[:, :27][want == 0], torch.zeros_like(got[:, :27][want == 0]))                  # padding: exact zeros
+    slot = plan.debug_read("cat1", 112).cpu()[:, 96:]
+    assert (slot[:, :3] - xr).abs().max() <= 1e-6 and torch.equal(slot[:, 3:], torch.zeros_like(slot[:, 3:]))

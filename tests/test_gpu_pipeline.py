@@ -248,3 +248,59 @@ def test_trainer_snapshot_and_resume_continue_the_run(engine, tmp_path):
     a = float(resumed.state[StateValue.HISTORY][HistoryValue.TRAIN]["loss"].accumulated())
     b = float(straight.state[StateValue.HISTORY][HistoryValue.TRAIN]["loss"].accumulated())
     assert abs(a - b) < 1e-5 * abs(b) + 1e-6
+
+
+def test_graphed_step_with_pinned_host_batches_equals_the_eager_step(engine):
+    """GraphedTrainStep: a different PINNED HOST batch every call (staged on the copy stream into alternating input slots
+    while the previous step computes) gives the losses and the weights of the eager train_step on the same sequence, and
+    loss_host() - written by the graph's own last node - is the step's per-sample loss."""
+    from ssdn.train import GraphedTrainStep
+    M = NoisyDataset.Metadata
+    n, size, steps = 4, 32, 7
+    sigma = torch.full((n, 1, 1, 1), 25 / 255)
+    batches = [O.synthetic_batch(n, 3, size, seed=300 + s)[1] for s in range(steps)]
+    cfg = make_cfg("ssdn", "known", 3)
+
+    def fresh():
+        torch.manual_seed(0)
+        den = ssdn.Denoiser(cfg, device="cuda")
+        opt = FlatAdam(den)
+        opt.param_groups[0]["lr"] = 3e-4
+        return den, opt
+
+    den_e, opt_e = fresh()
+    eager = []
+    for b in batches:
+        out = train_step(den_e, opt_e, [b.cuda(), torch.zeros(0), {M.INPUT_NOISE_VALUES: sigma.cuda()}])
+        eager.append(out[PipelineOutput.LOSS].detach().cpu().clone())
+        del out
+    den_g, opt_g = fresh()
+    host = lambda b: [b.pin_memory(), torch.zeros(0), {M.INPUT_NOISE_VALUES: sigma.pin_memory()}]     # noqa: E731
+    graphed, got = None, []
+    for s, b in enumerate(batches):
+        if s == 0:
+            out = train_step(den_g, opt_g, [b.cuda(), torch.zeros(0), {M.INPUT_NOISE_VALUES: sigma.cuda()}])     # step 1 (eager)
+            got.append(out[PipelineOutput.LOSS].detach().cpu().clone())
+            del out
+        elif graphed is None:
+            graphed = GraphedTrainStep(den_g, opt_g, host(b), warmup=1)     # runs this batch as steps 2 and 3 (warm-up + first replay)
+            got.append(None)
+        else:
+            out = graphed(host(b))
+            torch.cuda.synchronize()
+            assert torch.equal(graphed.loss_host(), out[PipelineOutput.LOSS].detach().cpu())
+            got.append(graphed.loss_host().clone())
+    # the eager reference took batch 1 once where the graphed run took it twice: replay that on the eager side for the weights
+    den_r, opt_r = fresh()
+    seq = [batches[0], batches[1], batches[1]] + batches[2:]
+    ref = []
+    for b in seq:
+        out = train_step(den_r, opt_r, [b.cuda(), torch.zeros(0), {M.INPUT_NOISE_VALUES: sigma.cuda()}])
+        ref.append(out[PipelineOutput.LOSS].detach().cpu().clone())
+        del out
+    torch.cuda.synchronize()
+    assert opt_g.step_count == opt_r.step_count == steps + 1
+    for s in range(2, steps):
+        assert rel(got[s], ref[s + 1]) < 1e-5, s                   # same data, same weights history: rounding only (operand scales)
+    assert rel_l2(den_g.flat_parameters(), den_r.flat_parameters()) < 1e-5
+    assert rel(eager[0], got[0]) < 1e-6
