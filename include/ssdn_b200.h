@@ -103,7 +103,10 @@ int ssdn_profile_records(double* out, int max_records);
  * sigma_raw [n][cs], cs in {1, c}.
  * Gaussian noise (poisson == 0): sigma_known != 0 -> sigma = max(raw, 1e-3) (:279-282), else
  *   sigma = softplus(raw - 4) + 1e-3 (:272-275) and the -0.1 sigma regulariser is applied (:333, :360-363).
- * Poisson noise (poisson != 0, :285-297): sigma = sqrt(max(mu, 1e-3) * k) per pixel and channel with k = 1 / raw
+ * noise_model: bit 0 = Poisson noise, bit 1 = diagonal covariance (cfg DIAGONAL_COVARIANCE, :213, :236-243: net_out then has
+ *   c + c channels - the mean and c diagonal factors d, Sigma_x = diag(d^2); the reference's own branch raises a TypeError at
+ *   :240 (`c00.shape()`), this is what it evidently means - see oracle/ssdn_oracle.py:ssdn_posterior).
+ * Poisson noise (noise_model & 1, :285-297): sigma = sqrt(max(mu, 1e-3) * k) per pixel and channel with k = 1 / raw
  *   (raw = the known lambda) or k = softplus(raw - 4) + 1e-3 (learned, regularised); the loss gradient then also
  *   reaches mu through sigma.
  * Outputs: pme [n][c][h][w] posterior mean (:328-330, :366-372), loss [n] per-sample mean NLL (:323-363, :388),
@@ -111,11 +114,11 @@ int ssdn_profile_records(double* out, int max_records);
  * Poisson noise. */
 size_t ssdn_loss_workspace_bytes(int n, int c);
 int ssdn_posterior_forward(void* ws, const float* net_out, const float* noisy, const float* sigma_raw, int n, int c, int h, int w,
-                           int cs, int sigma_known, int poisson, float* pme, float* loss, float* model_std, float* noise_std,
+                           int cs, int sigma_known, int noise_model, float* pme, float* loss, float* model_std, float* noise_std,
                            void* stream);
 /* Gradient of sum_n gloss[n] * loss[n]: dnet like net_out; dsigma_raw [n][cs] (NULL or sigma_known: not computed). */
 int ssdn_posterior_backward(void* ws, const float* net_out, const float* noisy, const float* sigma_raw, const float* gloss, int n,
-                            int c, int h, int w, int cs, int sigma_known, int poisson, float* dnet, float* dsigma_raw, void* stream);
+                            int c, int h, int w, int cs, int sigma_known, int noise_model, float* dnet, float* dsigma_raw, void* stream);
 /* torch.mean(x, dim=(2,3)) of the sigma-estimator output — denoiser.py:263-265.  x [rows][hw] -> out [rows]. */
 int ssdn_spatial_mean_forward(const float* x, int rows, int hw, float* out, void* stream);
 int ssdn_spatial_mean_backward(const float* g, int rows, int hw, float* dx, void* stream);

@@ -218,8 +218,13 @@ def _inv3(m: torch.Tensor) -> torch.Tensor:
     return torch.inverse(m)
 
 
-def ssdn_posterior(net_out: torch.Tensor, noisy: torch.Tensor, noise_std: torch.Tensor, sigma_known: bool):
+def ssdn_posterior(net_out: torch.Tensor, noisy: torch.Tensor, noise_std: torch.Tensor, sigma_known: bool, diagonal: bool = False):
     """denoiser.py:222-255 and :320-397 for Gaussian noise.
+
+    diagonal (cfg DIAGONAL_COVARIANCE, denoiser.py:213, :236-243): net_out is N x 2C x H x W and Sigma_x = diag(d0^2, d1^2, d2^2).
+    The reference's branch stops at :240 with a TypeError (`torch.zeros(c00.shape())`: torch.Size is not callable); this follows
+    its evident meaning, and tests/golden/make_golden.py runs the UNMODIFIED reference past that line (with a tensor subclass
+    whose .shape is callable) to pin it.
 
     net_out  N x (C + C(C+1)/2) x H x W   (mean, then the triangular factor A)
     noisy    N x C x H x W
@@ -242,7 +247,11 @@ def ssdn_posterior(net_out: torch.Tensor, noisy: torch.Tensor, noise_std: torch.
     else:
         assert c == 3
         a = a.permute(0, 2, 3, 1)
-        a0, a1, a2, a3, a4, a5 = [a[..., i] for i in range(6)]
+        if diagonal:
+            zero = torch.zeros_like(a[..., 0])
+            a0, a1, a2, a3, a4, a5 = a[..., 0], zero, zero, a[..., 1], zero, a[..., 2]
+        else:
+            a0, a1, a2, a3, a4, a5 = [a[..., i] for i in range(6)]
         c00 = a0 ** 2 + a1 ** 2 + a2 ** 2
         c01 = a1 * a3 + a2 * a4
         c02 = a2 * a5
@@ -277,7 +286,7 @@ def ssdn_posterior(net_out: torch.Tensor, noisy: torch.Tensor, noise_std: torch.
 
 def ssdn_pipeline(params: Dict[str, torch.Tensor], noisy: torch.Tensor, noise_values: torch.Tensor,
                   sigma_mode: str, est_params: Optional[Dict[str, torch.Tensor]] = None,
-                  est_sigma: Optional[torch.Tensor] = None, noise_style: str = "gauss"):
+                  est_sigma: Optional[torch.Tensor] = None, noise_style: str = "gauss", diagonal: bool = False):
     """denoiser.py:182-397.  sigma_mode in {"known", "const", "var"}; noise_style "gauss..." or "poisson..." (the
     signal-dependent approximation of :285-297: sigma = sqrt(max(mu, 1e-3) / lambda) per pixel and channel when lambda is
     known, sqrt(max(mu, 1e-3) * estimate) otherwise)."""
@@ -299,7 +308,7 @@ def ssdn_pipeline(params: Dict[str, torch.Tensor], noisy: torch.Tensor, noise_va
         noise_std = (base / noise_values) ** 0.5 if est is None else (base * est) ** 0.5
     else:
         raise NotImplementedError(noise_style)
-    out = ssdn_posterior(net_out, noisy, noise_std, sigma_known=(sigma_mode == "known"))
+    out = ssdn_posterior(net_out, noisy, noise_std, sigma_known=(sigma_mode == "known"), diagonal=diagonal and c == 3)
     out["net_out"] = net_out
     return out
 

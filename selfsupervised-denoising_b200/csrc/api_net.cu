@@ -183,19 +183,21 @@ static inline int loss_blocks(int hw) { int b = (hw + 511) / 512; return b < 1 ?
 extern "C" size_t ssdn_loss_workspace_bytes(int n, int c) { return (size_t)n * 64 * 4 * sizeof(float) + (size_t)n * c * sizeof(float) + 1024; }
 
 extern "C" int ssdn_posterior_forward(void* ws, const float* net_out, const float* noisy, const float* sigma_raw, int n, int c, int h,
-                                      int w, int cs, int sigma_known, int poisson, float* pme, float* loss, float* model_std,
+                                      int w, int cs, int sigma_known, int noise_model, float* pme, float* loss, float* model_std,
                                       float* noise_std, void* stream) {
   if (c != 1 && c != 3) return fail(-1, "num_channels must be 1 or 3");
   if (cs != 1 && cs != c) return fail(-1, "sigma must have 1 or C values per sample");
+  if (noise_model & ~3) return fail(-1, "noise_model: bit 0 = Poisson noise, bit 1 = diagonal covariance");
+  const int poisson = noise_model & 1, diag = (noise_model >> 1) & 1;
   cudaStream_t st = (cudaStream_t)stream;
   const int hw = h * w, nblk = loss_blocks(hw);
   float* partial = (float*)ws;
   dim3 grid(nblk, n);
   float* ns_px = poisson ? noise_std : nullptr;     // Poisson: noise_std is [n][h][w]; Gaussian: [n]
-  // per pixel: net_out (c + c(c+1)/2) + noisy c in, pme c + model_std 1 out
-  const double fbytes = (double)n * hw * 4.0 * ((c + c * (c + 1) / 2) + c + c + 1);
-  if (c == 1) SSDN_PROF(K_POSTERIOR_FWD, 0, fbytes, st, (lossk::posterior_fwd_kernel<1><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, pme, model_std, ns_px, partial)));
-  else SSDN_PROF(K_POSTERIOR_FWD, 0, fbytes, st, (lossk::posterior_fwd_kernel<3><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, pme, model_std, ns_px, partial)));
+  // per pixel: net_out (c + c(c+1)/2, or 2c with a diagonal covariance) + noisy c in, pme c + model_std 1 out
+  const double fbytes = (double)n * hw * 4.0 * ((diag ? 2 * c : c + c * (c + 1) / 2) + c + c + 1);
+  if (c == 1) SSDN_PROF(K_POSTERIOR_FWD, 0, fbytes, st, (lossk::posterior_fwd_kernel<1><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, diag, hw, pme, model_std, ns_px, partial)));
+  else SSDN_PROF(K_POSTERIOR_FWD, 0, fbytes, st, (lossk::posterior_fwd_kernel<3><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, diag, hw, pme, model_std, ns_px, partial)));
   lossk::posterior_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, nblk, hw, sigma_raw, cs, sigma_known, c, n, loss,
                                                                      poisson ? nullptr : noise_std);
   SSDN_CUDA(cudaGetLastError());
@@ -203,18 +205,20 @@ extern "C" int ssdn_posterior_forward(void* ws, const float* net_out, const floa
 }
 
 extern "C" int ssdn_posterior_backward(void* ws, const float* net_out, const float* noisy, const float* sigma_raw, const float* gloss,
-                                       int n, int c, int h, int w, int cs, int sigma_known, int poisson, float* dnet, float* dsigma_raw,
+                                       int n, int c, int h, int w, int cs, int sigma_known, int noise_model, float* dnet, float* dsigma_raw,
                                        void* stream) {
   if (c != 1 && c != 3) return fail(-1, "num_channels must be 1 or 3");
+  if (noise_model & ~3) return fail(-1, "noise_model: bit 0 = Poisson noise, bit 1 = diagonal covariance");
+  const int poisson = noise_model & 1, diag = (noise_model >> 1) & 1;
   cudaStream_t st = (cudaStream_t)stream;
   const int hw = h * w, nblk = loss_blocks(hw);
   float* partial = (float*)ws;
   dim3 grid(nblk, n);
   float* dp = (dsigma_raw && !sigma_known) ? partial : nullptr;
   // per pixel: net_out + noisy in, d(net_out) out
-  const double bbytes = (double)n * hw * 4.0 * (2 * (c + c * (c + 1) / 2) + c);
-  if (c == 1) SSDN_PROF(K_POSTERIOR_BWD, 0, bbytes, st, (lossk::posterior_bwd_kernel<1><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, gloss, dnet, dp)));
-  else SSDN_PROF(K_POSTERIOR_BWD, 0, bbytes, st, (lossk::posterior_bwd_kernel<3><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, hw, gloss, dnet, dp)));
+  const double bbytes = (double)n * hw * 4.0 * (2 * (diag ? 2 * c : c + c * (c + 1) / 2) + c);
+  if (c == 1) SSDN_PROF(K_POSTERIOR_BWD, 0, bbytes, st, (lossk::posterior_bwd_kernel<1><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, diag, hw, gloss, dnet, dp)));
+  else SSDN_PROF(K_POSTERIOR_BWD, 0, bbytes, st, (lossk::posterior_bwd_kernel<3><<<grid, lossk::kBlock, 0, st>>>(net_out, noisy, sigma_raw, cs, sigma_known, poisson, diag, hw, gloss, dnet, dp)));
   if (dp) lossk::posterior_bwd_finalize_kernel<<<(n * cs + 127) / 128, 128, 0, st>>>(partial, nblk, sigma_raw, cs, c, n, poisson, gloss, dsigma_raw);
   SSDN_CUDA(cudaGetLastError());
   return 0;

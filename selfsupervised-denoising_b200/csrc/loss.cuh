@@ -63,12 +63,13 @@ __device__ __forceinline__ float noise_coeff(float raw, int known, int poisson) 
 
 template <int C>
 __global__ void posterior_fwd_kernel(const float* __restrict__ net_out, const float* __restrict__ noisy,
-                                     const float* __restrict__ sigma_raw, int cs, int known, int poisson, int HW,
+                                     const float* __restrict__ sigma_raw, int cs, int known, int poisson, int diag, int HW,
                                      float* __restrict__ pme, float* __restrict__ model_std, float* __restrict__ noise_std_px,
                                      float* __restrict__ partial) {
   pdl_wait();
   __shared__ float sm[32];
-  constexpr int CO = C + C * (C + 1) / 2;
+  // diag (denoiser.py:236-243, cfg DIAGONAL_COVARIANCE): the network gives C diagonal factors instead of the triangular one
+  const int CO = diag ? 2 * C : C + C * (C + 1) / 2;
   const int n = blockIdx.y;
   const float* no = net_out + (long long)n * CO * HW;
   const float* yy = noisy + (long long)n * C * HW;
@@ -95,8 +96,12 @@ __global__ void posterior_fwd_kernel(const float* __restrict__ net_out, const fl
         for (int c = 0; c < 3; ++c) sg[c] = sqrtf(fmaxf((float)mu[c], 1e-3f) * kc[c]);
         if (noise_std_px) noise_std_px[(long long)n * HW + i] = (float)pow((double)sg[0] * sg[0] * sg[1] * sg[1] * sg[2] * sg[2], 1.0 / 6.0);
       }
+      if (diag) {          // Sigma_x = diag(d0^2, d1^2, d2^2): U with only its diagonal
+        a[0] = no[3 * HW + i]; a[3] = no[4 * HW + i]; a[5] = no[5 * HW + i]; a[1] = a[2] = a[4] = 0.0;
+      } else {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) a[c] = no[(3 + c) * HW + i];
+        for (int c = 0; c < 6; ++c) a[c] = no[(3 + c) * HW + i];
+      }
       // Sigma_x = U U^T with U = [[a0,a1,a2],[0,a3,a4],[0,0,a5]]   (denoiser.py:246-255)
       Sym3 sx;
       sx.a00 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; sx.a01 = a[1] * a[3] + a[2] * a[4]; sx.a02 = a[2] * a[5];
@@ -154,13 +159,13 @@ __global__ void posterior_finalize_kernel(const float* __restrict__ partial, int
 // d(net_out) for  L = sum_n gloss[n] * loss[n];  dsig_partial[n][blk][c] = strip sums of dL/d(sigma_c)
 template <int C>
 __global__ void posterior_bwd_kernel(const float* __restrict__ net_out, const float* __restrict__ noisy,
-                                     const float* __restrict__ sigma_raw, int cs, int known, int poisson, int HW,
+                                     const float* __restrict__ sigma_raw, int cs, int known, int poisson, int diag, int HW,
                                      const float* __restrict__ gloss, float* __restrict__ dnet, float* __restrict__ dsig_partial) {
   pdl_wait();
   // ds[c] accumulates d(loss)/d(sigma_c) (Gaussian; the -0.1 regulariser is added by the finalize kernel) or
   // d(loss)/d(k_c) including the regulariser (Poisson: it depends on the pixel)
   __shared__ float sm[32];
-  constexpr int CO = C + C * (C + 1) / 2;
+  const int CO = diag ? 2 * C : C + C * (C + 1) / 2;
   const int n = blockIdx.y;
   const float* no = net_out + (long long)n * CO * HW;
   const float* yy = noisy + (long long)n * C * HW;
@@ -195,8 +200,12 @@ __global__ void posterior_bwd_kernel(const float* __restrict__ net_out, const fl
 #pragma unroll
         for (int c = 0; c < 3; ++c) sg[c] = sqrtf(fmaxf((float)mu[c], 1e-3f) * kc[c]);
       }
+      if (diag) {
+        a[0] = no[3 * HW + i]; a[3] = no[4 * HW + i]; a[5] = no[5 * HW + i]; a[1] = a[2] = a[4] = 0.0;
+      } else {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) a[c] = no[(3 + c) * HW + i];
+        for (int c = 0; c < 6; ++c) a[c] = no[(3 + c) * HW + i];
+      }
       Sym3 sy;
       sy.a00 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + (double)sg[0] * sg[0]; sy.a01 = a[1] * a[3] + a[2] * a[4]; sy.a02 = a[2] * a[5];
       sy.a11 = a[3] * a[3] + a[4] * a[4] + (double)sg[1] * sg[1]; sy.a12 = a[4] * a[5]; sy.a22 = a[5] * a[5] + (double)sg[2] * sg[2];
@@ -221,12 +230,16 @@ __global__ void posterior_bwd_kernel(const float* __restrict__ net_out, const fl
       }
       dn[i] = (float)(s * dmu[0]); dn[HW + i] = (float)(s * dmu[1]); dn[2 * HW + i] = (float)(s * dmu[2]);
       // dL/dU = 2 G U restricted to the upper triangle, U = [[a0,a1,a2],[0,a3,a4],[0,0,a5]]
+      if (diag) {
+        dn[3 * HW + i] = (float)(2.0 * s * (G.a00 * a[0])); dn[4 * HW + i] = (float)(2.0 * s * (G.a11 * a[3])); dn[5 * HW + i] = (float)(2.0 * s * (G.a22 * a[5]));
+      } else {
       dn[3 * HW + i] = (float)(2.0 * s * (G.a00 * a[0]));
       dn[4 * HW + i] = (float)(2.0 * s * (G.a00 * a[1] + G.a01 * a[3]));
       dn[5 * HW + i] = (float)(2.0 * s * (G.a00 * a[2] + G.a01 * a[4] + G.a02 * a[5]));
       dn[6 * HW + i] = (float)(2.0 * s * (G.a01 * a[1] + G.a11 * a[3]));
       dn[7 * HW + i] = (float)(2.0 * s * (G.a01 * a[2] + G.a11 * a[4] + G.a12 * a[5]));
       dn[8 * HW + i] = (float)(2.0 * s * (G.a02 * a[2] + G.a12 * a[4] + G.a22 * a[5]));
+      }
       if (!poisson) { ds[0] += (float)(s * 2.0 * G.a00 * sg[0]); ds[1] += (float)(s * 2.0 * G.a11 * sg[1]); ds[2] += (float)(s * 2.0 * G.a22 * sg[2]); }
     }
   }

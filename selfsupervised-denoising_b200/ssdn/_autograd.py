@@ -48,19 +48,19 @@ class PosteriorFunction(torch.autograd.Function):
     """SSDN posterior mean + NLL for Gaussian or Poisson noise (denoiser.py:222-397).  Only `loss` is differentiable."""
 
     @staticmethod
-    def forward(ctx, net_out, noisy, sigma_raw, sigma_known, poisson=False):
+    def forward(ctx, net_out, noisy, sigma_raw, sigma_known, poisson=False, diagonal=False):
         net_out, noisy, sigma_raw = net_out.contiguous(), noisy.contiguous(), sigma_raw.contiguous().float()
-        pme, loss, model_std, noise_std = E.posterior_forward(net_out, noisy, sigma_raw, sigma_known, poisson)
+        pme, loss, model_std, noise_std = E.posterior_forward(net_out, noisy, sigma_raw, sigma_known, poisson, diagonal)
         ctx.save_for_backward(net_out, noisy, sigma_raw)
-        ctx.known, ctx.poisson = sigma_known, poisson
+        ctx.known, ctx.poisson, ctx.diagonal = sigma_known, poisson, diagonal
         ctx.mark_non_differentiable(pme, model_std, noise_std)
         return pme, loss, model_std, noise_std
 
     @staticmethod
     def backward(ctx, _gpme, gloss, _gms, _gns):
         net_out, noisy, sigma_raw = ctx.saved_tensors
-        dnet, dsig = E.posterior_backward(net_out, noisy, sigma_raw, gloss.contiguous().float().view(-1), ctx.known, ctx.poisson)
-        return dnet, None, dsig, None, None
+        dnet, dsig = E.posterior_backward(net_out, noisy, sigma_raw, gloss.contiguous().float().view(-1), ctx.known, ctx.poisson, ctx.diagonal)
+        return dnet, None, dsig, None, None, None
 
 
 class SpatialMeanFunction(torch.autograd.Function):

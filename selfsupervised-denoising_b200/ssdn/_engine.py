@@ -316,11 +316,20 @@ def _loss_ws(n, c, device):
     return _workspace(lib().ssdn_loss_workspace_bytes(n, c), device)
 
 
+def _posterior_channels(net_out, c, diagonal):
+    want = 2 * c if diagonal else c + c * (c + 1) // 2
+    if net_out.shape[1] != want:
+        raise ValueError("network output has {} channels, the posterior needs {} ({} covariance)".format(
+            net_out.shape[1], want, "diagonal" if diagonal else "full"))
+
+
 @_on_tensor_device
-def posterior_forward(net_out, noisy, sigma_raw, sigma_known, poisson=False):
+def posterior_forward(net_out, noisy, sigma_raw, sigma_known, poisson=False, diagonal=False):
     """poisson: sigma_raw is the known lambda (sigma_known) or the raw estimate of the per-unit-signal variance; the noise
-    level is then per pixel and noise_std comes back as [n][h][w] instead of [n][1][1] (denoiser.py:285-297, :375-380)."""
+    level is then per pixel and noise_std comes back as [n][h][w] instead of [n][1][1] (denoiser.py:285-297, :375-380).
+    diagonal: net_out carries c diagonal factors of Sigma_x instead of the triangular one (denoiser.py:213, :236-243)."""
     n, c, h, w = noisy.shape
+    _posterior_channels(net_out, c, diagonal)
     cs = sigma_raw.numel() // n
     dev = noisy.device
     pme = torch.empty_like(noisy)
@@ -328,20 +337,21 @@ def posterior_forward(net_out, noisy, sigma_raw, sigma_known, poisson=False):
     model_std = torch.empty(n, h, w, device=dev)
     noise_std = torch.empty(n, h, w, device=dev) if poisson else torch.empty(n, 1, 1, device=dev)
     ws = _loss_ws(n, c, dev)
-    check(lib().ssdn_posterior_forward(_ptr(ws), _ptr(net_out), _ptr(noisy), _ptr(sigma_raw), n, c, h, w, cs, int(sigma_known), int(poisson),
+    check(lib().ssdn_posterior_forward(_ptr(ws), _ptr(net_out), _ptr(noisy), _ptr(sigma_raw), n, c, h, w, cs, int(sigma_known), int(poisson) | (2 if diagonal else 0),
                                        _ptr(pme), _ptr(loss), _ptr(model_std), _ptr(noise_std), _stream()))
     return pme, loss, model_std, noise_std
 
 
 @_on_tensor_device
-def posterior_backward(net_out, noisy, sigma_raw, gloss, sigma_known, poisson=False):
+def posterior_backward(net_out, noisy, sigma_raw, gloss, sigma_known, poisson=False, diagonal=False):
     n, c, h, w = noisy.shape
+    _posterior_channels(net_out, c, diagonal)
     cs = sigma_raw.numel() // n
     dnet = torch.empty_like(net_out)
     dsig = None if sigma_known else torch.empty_like(sigma_raw)
     ws = _loss_ws(n, c, noisy.device)
     check(lib().ssdn_posterior_backward(_ptr(ws), _ptr(net_out), _ptr(noisy), _ptr(sigma_raw), _ptr(gloss), n, c, h, w, cs,
-                                        int(sigma_known), int(poisson), _ptr(dnet), _ptr(dsig), _stream()))
+                                        int(sigma_known), int(poisson) | (2 if diagonal else 0), _ptr(dnet), _ptr(dsig), _stream()))
     return dnet, dsig
 
 

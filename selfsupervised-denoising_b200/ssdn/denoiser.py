@@ -6,8 +6,8 @@ Differences that are deliberate and documented in DESIGN.md:
   * networks are NOT wrapped in ``nn.DataParallel`` (one process per GPU with a single gradient
     all-reduce replaces it, see ssdn.train); a transparent wrapper keeps the ``models.<id>.module.*`` keys;
   * ``forward`` works (in the reference it raises IndexError for every pipeline);
-  * the diagonal-covariance option is not implemented by the engine (it is dead code in the reference: denoiser.py:240
-    raises TypeError)."""
+  * the diagonal-covariance option works (the reference's branch raises TypeError at denoiser.py:240, `c00.shape()`; the
+    engine computes Sigma_x = diag(d^2) from the c diagonal factors, which is what that branch evidently means)."""
 from __future__ import annotations
 
 from typing import Dict, List
@@ -216,8 +216,10 @@ class Denoiser(nn.Module):
         mode = self.cfg[ConfigValue.NOISE_VALUE]
         c = self.cfg[ConfigValue.IMAGE_CHANNELS]
         assert c in [1, 3]
-        if self.cfg[ConfigValue.DIAGONAL_COVARIANCE]:
-            raise NotImplementedError("diagonal covariance is not implemented by the B200 engine")
+        # diagonal covariance (cfg DIAGONAL_COVARIANCE): c diagonal factors instead of the triangular one.  The reference's own
+        # branch stops with a TypeError (denoiser.py:240, `c00.shape()`); the engine computes what it evidently means.  With
+        # one channel the two parameterisations coincide.
+        diagonal = bool(self.cfg[ConfigValue.DIAGONAL_COVARIANCE]) and c == 3
         if not (style.startswith("gauss") or style.startswith("poisson")):
             raise NotImplementedError("Noise type not supported")
         poisson = style.startswith("poisson")
@@ -256,7 +258,7 @@ class Denoiser(nn.Module):
             stat_shape = (n, 1, 1)
         else:
             raise NotImplementedError("Unsupported noise value mode")
-        pme, loss, model_std, noise_std = PosteriorFunction.apply(net_out, noisy, sigma_raw, mode == NoiseValue.KNOWN, poisson)
+        pme, loss, model_std, noise_std = PosteriorFunction.apply(net_out, noisy, sigma_raw, mode == NoiseValue.KNOWN, poisson, diagonal)
         if poisson:             # signal-dependent noise: the level is per pixel (denoiser.py:378-380 -> N x H x W)
             stat_shape = tuple(noise_std.shape)
         return {

@@ -39,6 +39,9 @@ PIPELINE_CASES = OrderedDict(
     ssdn_known_rgb_poisson=("ssdn", "known", 3, 2, 32),
     ssdn_const_rgb_poisson=("ssdn", "const", 3, 2, 32),
     ssdn_const_mono_poisson=("ssdn", "const", 1, 2, 32),
+    # appended: diagonal covariance (cfg DIAGONAL_COVARIANCE, denoiser.py:213, :236-243), 3 + 3 network outputs
+    ssdn_known_rgb_diag=("ssdn", "known", 3, 2, 32),
+    ssdn_const_rgb_diag=("ssdn", "const", 3, 2, 32),
 )
 
 
@@ -70,7 +73,8 @@ def pipeline_inputs(name):
     clean, noisy = O.synthetic_batch(n, c, size, seed=seed)
     d = dict(algorithm=algo, sigma_mode=mode, channels=c, clean=clean, noisy=noisy)
     if algo == "ssdn":
-        d["params"] = make_params(c, c + c * (c + 1) // 2, True, seed)
+        d["diagonal"] = name.endswith("diag")
+        d["params"] = make_params(c, 2 * c if d["diagonal"] else c + c * (c + 1) // 2, True, seed)
         if name.endswith("poisson"):
             d["noise_style"] = "poisson30"
             d["noise_values"] = torch.full((n, 1, 1, 1), 30.0) if mode == "known" else torch.full((n, 1, 1, 1), 25.0 / 255.0)

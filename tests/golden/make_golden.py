@@ -92,8 +92,9 @@ def networks():
 
 
 # ------------------------------------------------------------------ pipelines
-def make_cfg(algo, mode, channels, style="gauss25"):
+def make_cfg(algo, mode, channels, style="gauss25", diagonal=False):
     cfg = ssdn.cfg.base()
+    cfg[ConfigValue.DIAGONAL_COVARIANCE] = diagonal
     cfg[ConfigValue.ALGORITHM] = {"ssdn": NoiseAlgorithm.SELFSUPERVISED_DENOISING, "n2c": NoiseAlgorithm.NOISE_TO_CLEAN,
                                   "n2n": NoiseAlgorithm.NOISE_TO_NOISE, "n2v": NoiseAlgorithm.NOISE_TO_VOID}[algo]
     cfg[ConfigValue.NOISE_STYLE] = style
@@ -104,9 +105,35 @@ def make_cfg(algo, mode, channels, style="gauss25"):
     return cfg
 
 
+class _CallableSize(tuple):
+    def __call__(self):
+        return torch.Size(self)
+
+
+class _ShapeCallableTensor(torch.Tensor):
+    """The reference's diagonal-covariance branch evaluates `torch.zeros(c00.shape())` (denoiser.py:240): torch.Size is not
+    callable, so the UNMODIFIED reference raises TypeError there.  A tensor whose .shape is a callable Size lets its own code
+    run past that line with the meaning it evidently has; everything else is the reference's arithmetic, untouched."""
+
+    @property
+    def shape(self):
+        return _CallableSize(torch.Tensor.shape.__get__(self))
+
+
+class _AsShapeCallable(torch.nn.Module):
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+
+    def forward(self, x):
+        return self.net(x).as_subclass(_ShapeCallableTensor)
+
+
 def ref_denoiser(d):
-    den = Denoiser(make_cfg(d["algorithm"], d["sigma_mode"], d["channels"], d.get("noise_style", "gauss25")), device="cpu")
+    den = Denoiser(make_cfg(d["algorithm"], d["sigma_mode"], d["channels"], d.get("noise_style", "gauss25"), d.get("diagonal", False)), device="cpu")
     load_into(den.get_model(Denoiser.MODEL, parallelised=False), d["params"])
+    if d.get("diagonal"):
+        den.models[Denoiser.MODEL] = _AsShapeCallable(den.models[Denoiser.MODEL])
     if "est_params" in d:
         load_into(den.get_model(Denoiser.SIGMA_ESTIMATOR, parallelised=False), d["est_params"])
     if "est_sigma" in d:
@@ -130,7 +157,8 @@ def oracle_run(d):
     ep = {k: v.clone().requires_grad_(True) for k, v in d["est_params"].items()} if "est_params" in d else None
     es = d["est_sigma"].clone().requires_grad_(True) if "est_sigma" in d else None
     if d["algorithm"] == "ssdn":
-        out = O.ssdn_pipeline(p, d["noisy"], d["noise_values"], d["sigma_mode"], ep, es, noise_style=d.get("noise_style", "gauss"))
+        out = O.ssdn_pipeline(p, d["noisy"], d["noise_values"], d["sigma_mode"], ep, es, noise_style=d.get("noise_style", "gauss"),
+                              diagonal=d.get("diagonal", False))
     elif d["algorithm"] == "n2v":
         out = O.mask_mse_pipeline(p, d["noisy"], d["ref"], d["coords"])
     else:
@@ -150,7 +178,7 @@ def pipelines(only=None):
         outs[PipelineOutput.LOSS].mean().backward()
         main = den.get_model(Denoiser.MODEL, parallelised=False)
         c = d["channels"]
-        names = O.param_order(c, c + c * (c + 1) // 2 if d["algorithm"] == "ssdn" else c, d["algorithm"] == "ssdn")
+        names = O.param_order(c, (2 * c if d.get("diagonal") else c + c * (c + 1) // 2) if d["algorithm"] == "ssdn" else c, d["algorithm"] == "ssdn")
         g_main = {k: dict(main.named_parameters())[k].grad for k in names}
         arrs = dict(loss=outs[PipelineOutput.LOSS], out=outs[PipelineOutput.IMG_DENOISED], grad_summary=C.grad_summary(g_main),
                     g_first_w=g_main["encode_block_1.0.weight"], g_out_w=g_main["output_conv.weight"], g_out_b=g_main["output_conv.bias"])

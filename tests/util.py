@@ -32,8 +32,9 @@ ALGO = {"ssdn": NoiseAlgorithm.SELFSUPERVISED_DENOISING, "n2c": NoiseAlgorithm.N
 MODE = {"known": NoiseValue.KNOWN, "const": NoiseValue.UNKNOWN_CONSTANT, "var": NoiseValue.UNKNOWN_VARIABLE, None: NoiseValue.KNOWN}
 
 
-def make_cfg(algorithm="ssdn", sigma_mode="known", channels=3, style="gauss25"):
+def make_cfg(algorithm="ssdn", sigma_mode="known", channels=3, style="gauss25", diagonal=False):
     cfg = ssdn.cfg.base()
+    cfg[ConfigValue.DIAGONAL_COVARIANCE] = diagonal
     cfg[ConfigValue.ALGORITHM] = ALGO[algorithm]
     cfg[ConfigValue.NOISE_STYLE] = style
     cfg[ConfigValue.NOISE_VALUE] = MODE[sigma_mode]
@@ -44,7 +45,7 @@ def make_cfg(algorithm="ssdn", sigma_mode="known", channels=3, style="gauss25"):
 
 def denoiser_for_case(d, device="cuda"):
     """Engine Denoiser loaded with the weights of a tests/golden pipeline case."""
-    den = ssdn.Denoiser(make_cfg(d["algorithm"], d["sigma_mode"], d["channels"], d.get("noise_style", "gauss25")), device=device)
+    den = ssdn.Denoiser(make_cfg(d["algorithm"], d["sigma_mode"], d["channels"], d.get("noise_style", "gauss25"), d.get("diagonal", False)), device=device)
     den.get_model(ssdn.Denoiser.MODEL, False).load_state_dict(d["params"], strict=False)
     if "est_params" in d:
         den.get_model(ssdn.Denoiser.SIGMA_ESTIMATOR, False).load_state_dict(d["est_params"], strict=False)
@@ -71,7 +72,8 @@ def oracle_case(d, dtype=torch.float32):
     ep = {k: cast(v).clone().requires_grad_(True) for k, v in d["est_params"].items()} if "est_params" in d else None
     es = cast(d["est_sigma"]).clone().requires_grad_(True) if "est_sigma" in d else None
     if d["algorithm"] == "ssdn":
-        out = O.ssdn_pipeline(p, cast(d["noisy"]), cast(d["noise_values"]), d["sigma_mode"], ep, es, noise_style=d.get("noise_style", "gauss"))
+        out = O.ssdn_pipeline(p, cast(d["noisy"]), cast(d["noise_values"]), d["sigma_mode"], ep, es, noise_style=d.get("noise_style", "gauss"),
+                              diagonal=d.get("diagonal", False))
     elif d["algorithm"] == "n2v":
         out = O.mask_mse_pipeline(p, cast(d["noisy"]), cast(d["ref"]), d["coords"])
     else:
