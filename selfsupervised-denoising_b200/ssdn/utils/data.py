@@ -50,6 +50,8 @@ def calculate_psnr(img: Tensor, ref: Tensor, data_format: str = "BCHW") -> Tenso
         from ssdn import _engine as E
         mse = E.mse_forward(img.contiguous(), ref.to(img.device).contiguous()).view(-1)
     else:
+        # host-side metric helper of the reference's API (uint8 / CPU images, other axis orders: data-set tools, the differential
+        # battery); the hot loop's PSNR (CUDA float BCHW, train.py:243-259) is the engine call above
         mse = ((img - ref) ** 2).mean(dim=dims)
     return mse2psnr(mse, img.is_floating_point())
 
