@@ -443,7 +443,14 @@ __global__ void nchw_colsum_kernel(const float* __restrict__ x, int C, int HW, f
   __shared__ float sm[32];
   const float* row = x + ((long long)blockIdx.y * C + blockIdx.x) * HW;
   float acc = 0.f;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) acc += __ldg(row + i);
+  if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {      // 16-byte loads, fixed order
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int i = threadIdx.x; i < (HW >> 2); i += blockDim.x) { const float4 v = __ldg(r4 + i); a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w; }
+    acc = (a0 + a1) + (a2 + a3);
+  } else {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) acc += __ldg(row + i);
+  }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -504,7 +511,14 @@ __global__ void leaf_scale_kernel(const float* __restrict__ x, long long n, Scal
   pdl_wait();
   __shared__ float sm[32];
   float m = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(__ldg(x + i)));
+  const long long stride = (long long)gridDim.x * blockDim.x;      // four independent loads in flight per thread (see weight_scale_kernel)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+    const float a = fabsf(__ldg(x + i));
+    const float b = i + stride < n ? fabsf(__ldg(x + i + stride)) : 0.f;
+    const float c = i + 2 * stride < n ? fabsf(__ldg(x + i + 2 * stride)) : 0.f;
+    const float d = i + 3 * stride < n ? fabsf(__ldg(x + i + 3 * stride)) : 0.f;
+    m = fmaxf(fmaxf(m, fmaxf(a, b)), fmaxf(c, d));
+  }
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -529,7 +543,7 @@ __global__ void leaf_scale_kernel(const float* __restrict__ x, long long n, Scal
 // this is the first kernel of a forward pass.
 struct WeightScaleJob { const float* w; int n; int slot; };
 constexpr int kMaxScaleJobs = 24;
-constexpr int kWeightScaleBlocks = 16;
+constexpr int kWeightScaleBlocks = 32;
 struct WeightScaleJobs { WeightScaleJob j[kMaxScaleJobs]; };
 __global__ void weight_scale_kernel(const __grid_constant__ WeightScaleJobs jobs, ScaleState st, int begin_first, int begin_count) {
   pdl_wait();
@@ -537,7 +551,16 @@ __global__ void weight_scale_kernel(const __grid_constant__ WeightScaleJobs jobs
   if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < begin_count) { const int i = begin_first + threadIdx.x; st.k[i] = st.k_next[i]; st.amax[i] = 0u; }
   const WeightScaleJob& q = jobs.j[blockIdx.y];
   float m = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(__ldg(q.w + i)));
+  // four independent loads in flight per thread: this kernel is the first of every step and nothing can start before it
+  // (a dependent-load loop of 36 iterations made it 18 us for 5 MB)
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += 4 * stride) {
+    const float a = fabsf(__ldg(q.w + i));
+    const float b = i + stride < q.n ? fabsf(__ldg(q.w + i + stride)) : 0.f;
+    const float c = i + 2 * stride < q.n ? fabsf(__ldg(q.w + i + 2 * stride)) : 0.f;
+    const float d = i + 3 * stride < q.n ? fabsf(__ldg(q.w + i + 3 * stride)) : 0.f;
+    m = fmaxf(fmaxf(m, fmaxf(a, b)), fmaxf(c, d));
+  }
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
   __syncthreads();
