@@ -190,6 +190,27 @@ def timed_region(fn, steps, device, dist_on, sampler=None):
     return t
 
 
+def eval_rate(device, sizes=(512, 768), reps=5):
+    """Forward-only SSDN pipeline (sigma known, eval mode: blind-spot network + posterior mean) on one full-size RGB image - the
+    evaluation path of SURVEY.md section 8(f)-1 (eval.py:19-127; BSD300 pads to 512 x 512, Kodak to 768 x 768).  Rank 0 only."""
+    import torch
+    import ssdn
+    from ssdn.datasets import NoisyDataset
+    den = ssdn.Denoiser(make_cfg("known"), device=device)
+    den.eval()
+    out = {}
+    M = NoisyDataset.Metadata
+    for s in sizes:
+        g = torch.Generator().manual_seed(s)
+        x = torch.rand(1, 3, s, s, generator=g).to(device)
+        data = [x, torch.zeros(0), {M.INPUT_NOISE_VALUES: torch.full((1, 1, 1, 1), 25 / 255, device=device)}]
+        with torch.no_grad():
+            fn = lambda: den.run_pipeline(data)       # noqa: E731
+            t = timed_region(fn, reps, device, False)
+        out[f"{s}x{s}"] = {"ms_per_image": t / reps * 1e3, "megapixels_per_s": s * s * reps / t / 1e6}
+    return out
+
+
 def cpu_oracle_rate(config, batch, steps, warmup, threads=None):
     """patches/s of the reference algorithm on the host cores (oracle port, autograd + Adam as train.py:197-202)."""
     import torch
@@ -387,6 +408,12 @@ def run_engine(args):
             extras["strong"] = short_run(args.config, "strong", device, rank, world, dist_on, graph)
         others = [c for c in ("var", "n2v", "var128") if c != args.config]
         extras["configs"] = {c: short_run(c, "weak", device, rank, world, dist_on, graph) for c in others}
+        if rank == 0 and not dist_on:
+            torch.cuda.empty_cache()
+            try:
+                extras["eval_forward"] = eval_rate(device)
+            except Exception as e:                      # noqa: BLE001  (a diagnostic extra must not cost the line)
+                extras["eval_forward"] = {"error": str(e)}
     peak = None
     if rank == 0:
         try:
