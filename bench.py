@@ -401,9 +401,14 @@ def run_engine(args):
     launches = case.launches_per_step()
     total = n_local * world
     extras = {}
+    # the captured graphs (they hold NCCL work at N > 1) go before anything else is set up or torn down: a process group must
+    # not be destroyed under live graphs
+    import gc
+    del case
+    gc.collect()
+    torch.cuda.synchronize(device)
+    torch.cuda.empty_cache()
     if not args.no_extras:
-        del case
-        torch.cuda.empty_cache()
         if dist_on and args.scaling == "weak":
             extras["strong"] = short_run(args.config, "strong", device, rank, world, dist_on, graph)
         others = [c for c in ("var", "n2v", "var128") if c != args.config]

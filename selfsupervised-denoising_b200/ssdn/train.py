@@ -274,7 +274,7 @@ class GraphedTrainStep:
         self.denoiser.dp_world_size = self.world_size
         outputs = self.denoiser.run_pipeline(self.slots[s])
         _backward_of_mean(outputs[PipelineOutput.LOSS], self._mean_grads)
-        if self.world_size > 1:
+        if self.world_size > 1 and not os.environ.get("SSDN_DEV_SKIP_ALLREDUCE"):    # (developer timing switch: NOT a valid training step)
             dist.all_reduce(self.denoiser.flat_gradients_with_flags(), op=dist.ReduceOp.SUM)
         self.optimizer.step_dev(self.hyper[s])
         return outputs
