@@ -12,17 +12,18 @@
 //   group  = a set of taps that share one staged window of A rows (halo reuse: the window is
 //            loaded ONCE by TMA and each tap is only a different UMMA start address)
 //   B tile = the [N][32] weight slab of one (chunk, tap), streamed through its own smem ring (3 slabs per stage).
-// Warp roles (12 warps): 0 = A producer (TMA), 1 = B producer (TMA), 2 = MMA issuer (one elected thread),
-// 3 = TMEM allocator, 4..11 = epilogue - two warps per TMEM lane quadrant taking alternate 32-channel slices:
-// TMEM -> registers -> operand scales 2^-(k_a + k_b) and accumulator-truncation compensation -> bias / LeakyReLU (+ sign-mask
-// word out) or LeakyReLU' from the sign-mask word -> optional column sums (bias gradient) -> transposed through shared
-// memory -> scaled fp16 hi/lo split (+ running max|v| for the destination's next scale) -> 16-byte stores with the
-// upsample / un-rotate / NCHW scatter in the address.
+// Warp roles (16 warps): 0 = A producer (TMA), 1 = B producer (TMA), 2 = MMA issuer (one elected thread),
+// 3 = TMEM allocator, 4..15 = epilogue - three warps per TMEM lane quadrant; the (tile, 32-channel slice) work items of a CTA's
+// units are dealt to them round-robin: TMEM -> registers -> one FFMA (accumulator scale 2^-(k_a + k_b), truncation compensation
+// and the destination's scale; bias) -> LeakyReLU (+ sign-mask word out) or LeakyReLU' from the sign-mask word -> transposed
+// through shared memory -> optional column sums of the staged tile (bias gradient) -> fp16 hi/lo split (+ running max|v| for
+// the destination's next scale) -> 16-byte stores with the upsample / un-rotate / NCHW scatter in the address.
 // Accumulators are double buffered in TMEM so the epilogue of unit i overlaps the MMAs of unit i+1.
 // PAIR = true: the kernel runs as clusters of two CTAs that issue cta_group::2 MMAs of M = 256 (umma.cuh): each CTA loads
 // its own pixel rows of A and half of the N rows of B, the leader issues, both epilogues drain their own TMEM.
 // Precision: two-term fp16 split with per-tensor power-of-two scales (see common.cuh) => fp32-grade results, 3 MMAs of
-// kind::f16 per (tile, k-step of 16 channels).
+// kind::f16 per (tile, k-step of 16 channels), issued back to back: lo*hi, then hi*lo and hi*hi, which share the A_hi tile
+// through the tensor core's operand collector (umma::mma_f16_lo_cu).
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
