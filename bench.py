@@ -323,7 +323,11 @@ class Case:
         return stale
 
     def launches_per_step(self):
-        return sum(p.kernel_launches(True) for p in self.plans()) + 5
+        """The engine's own kernel launches of one training step: every plan's (ssdn_net_kernel_launches) + the loss and the
+        optimiser - known sigma: posterior forward, its finalize, posterior backward, Adam; learned sigma: + the backward
+        finalize and the spatial mean forward / backward; Noise2Void: masked MSE forward, its reduction, backward, Adam."""
+        loss = {"known": 4, "var": 7, "n2v": 4, "var128": 7}.get(self.config, 4)
+        return sum(p.kernel_launches(True) for p in self.plans()) + loss
 
     def param_spread(self, dist_on):
         """max over ranks of max |p - p_rank0| after the timed steps: data-parallel replicas must stay identical."""
