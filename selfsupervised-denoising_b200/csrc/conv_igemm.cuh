@@ -62,7 +62,7 @@ struct ConvParams {
                       //    bandwidth from an MMA-bound layer)
   ConvDst dst;
   int* error_flag;
-  int debug;          // experiments only: 2 = skip MMA issue, 4 = one store per upsampled pixel, 8 = no operand-plane stores
+  int debug;          // experiments only: 2 = skip MMA issue (generic issue path)
   unsigned long long* stats;   // developer instrumentation (SSDN_CONV_STATS=1): per-CTA clocks spent in each role's waits
 };
 
@@ -491,7 +491,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     float amax_l = 0.f;        // running max|v| (in destination-scaled units) of what this lane wrote
     long long w_full = 0;
     const long long t_start = clock64();
-    const bool up2 = d.map == MAP_UP2 && !(p.debug & 4);      // debug 4: upsampling writes one of its four destinations, 8: no stores
+    const bool up2 = d.map == MAP_UP2;
     const uint32_t tmem_empty_lead0 = PAIR ? umma::mapa(tmem_empty(0), 0) : tmem_empty(0);   // the MMA issuer's barrier
     // cursor over this warp's items: (c_it, c_u, c_i) = unit counter, unit, item inside the unit
     int c_it = 0, c_u = u_first, c_i = half;
@@ -590,7 +590,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int q = 0; q < 32; q += 8) {
               const int px = q + sub;
               const uint32_t ppk = __shfl_sync(0xffffffffu, cur.pk, px);
-              if (chan_ok && (ppk & (7u << 26)) && !(p.debug & 8)) {
+              if (chan_ok && (ppk & (7u << 26))) {
                 const float4 o0 = lds128(stage_s + (px * kStagePitch + 8 * q8) * 4);
                 const float4 o1 = lds128(stage_s + (px * kStagePitch + 8 * q8 + 4) * 4);
                 float f8[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
