@@ -57,9 +57,9 @@ struct ConvParams {
   const int* k_a; const int* k_b;   // scale exponents of the A tensor and of the weight slab (device; null = 0)
   uint64_t magic_s, magic_p;   // ceil(2^64 / src.S), ceil(2^64 / src.P): the epilogue's pixel -> (image, row, column) divisions
   uint32_t wait_hint;          // suspend-time hint (ns) of the producers' / epilogue's mbarrier waits (0 = plain try_wait spin)
-  int epi_split;      // 1: both epilogue warps of a TMEM lane quadrant work (alternate slices) - epilogue-bound layers; 0: one warp
-                      //    per quadrant, the other four exit at once (they would only take issue slots and shared-memory
-                      //    bandwidth from an MMA-bound layer)
+  int epi_per_quad;   // epilogue warps per TMEM lane quadrant that work (1 .. kEpiPerQuad); the others exit at once.  3: epilogue-bound
+                      //    layers; 2: the MMA-bound 3x3 layers (their 18 KB of staging rows buy one more weight stage: the issuer
+                      //    waits less for weights); 1: upsampling / NCHW epilogues (more warps only fight over the load/store unit)
   ConvDst dst;
   int* error_flag;
   int debug;          // experiments only: 2 = skip MMA issue (generic issue path)
@@ -201,7 +201,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int nprod = PAIR ? 2 : 1;     // a pair's leader barrier collects one arrival (+ bytes) from each CTA's producer
     for (int s = 0; s < p.a_stages; ++s) { umma::mbar_init(full_a(s), nprod); umma::mbar_init(empty_a(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { umma::mbar_init(full_b(s), nprod); umma::mbar_init(empty_b(s), 1); }
-    for (int b = 0; b < 2; ++b) { umma::mbar_init(tmem_full(b), 1); umma::mbar_init(tmem_empty(b), nprod * (p.epi_split ? 32 * kEpiWarps : 128)); }
+    for (int b = 0; b < 2; ++b) { umma::mbar_init(tmem_full(b), 1); umma::mbar_init(tmem_empty(b), nprod * 128 * p.epi_per_quad); }
     umma::fence_mbar_init();
   }
   if (warp == 3) {
@@ -456,7 +456,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       unsigned long long* s = p.stats + blockIdx.x * 16;
       s[2] = w_tmem; s[3] = w_a; s[4] = w_b; s[5] = clock64() - t_start;
     }
-  } else if (warp >= 4 && (p.epi_split || warp < 8)) {
+  } else if (warp >= 4 && warp < 4 + 4 * p.epi_per_quad) {
     // ------------------------------------------------------------ epilogue
     // TMEM -> registers (one pixel per lane, 32 channels per slice) -> scales / bias / LeakyReLU (+ sign-mask word out) or
     // LeakyReLU' from the sign-mask word -> optional column sums -> staged through shared memory -> fp16 hi/lo split ->
@@ -470,8 +470,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const Geom& sg = p.src;
     const int ew = (warp - 4) & 3;        // TMEM lane quadrant (a warp may only read lanes 32 * (warp % 4) ...)
     const int half = (warp - 4) >> 2;     // which of the quadrant's warps
-    const int n_epi_warps = p.epi_split ? kEpiWarps : 4;
-    const int stride = p.epi_split ? kEpiPerQuad : 1;
+    const int n_epi_warps = 4 * p.epi_per_quad;
+    const int stride = p.epi_per_quad;
     const int nsl = (p.N + 31) >> 5, ipu = T * nsl;      // slices per tile, items per unit
     __shared__ __align__(16) float s_bias[400];
     // accumulators carry 2^(k_a + k_b); operand destinations are written with their own scale 2^k_dst, which is folded into
@@ -750,8 +750,9 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const __half* 
   // epilogue: both warps of a TMEM lane quadrant - measured never slower (profiles/r01_pair_split_ablation.log), except
   // with the upsampling epilogue (4x the stores: the two warps then only fight over the load/store unit)
   {
-    p.epi_split = dst.map != MAP_UP2 && dst.map != MAP_NCHW;
-    if (const char* e = getenv("SSDN_EPI_SPLIT")) p.epi_split = atoi(e) != 0;
+    p.epi_per_quad = (dst.map != MAP_UP2 && dst.map != MAP_NCHW) ? convk::kEpiPerQuad : 1;
+    if (const char* e = getenv("SSDN_EPI_SPLIT")) p.epi_per_quad = atoi(e) != 0 ? convk::kEpiPerQuad : 1;
+    if (const char* e = getenv("SSDN_EPI_PER_QUAD")) { const int v = atoi(e); if (v >= 1 && v <= convk::kEpiPerQuad && p.epi_per_quad > 1) p.epi_per_quad = v; }
   }
   // choose the tap grouping: all taps in one window if it fits in shared memory, else one window per
   // distinct row offset (dy), else one window per tap.
@@ -775,9 +776,10 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const __half* 
     static const int max_a_stages = getenv("SSDN_CONV_A_STAGES") ? atoi(getenv("SSDN_CONV_A_STAGES")) : 3;
     for (int stages = std::max(2, std::min(3, max_a_stages)); stages >= 2; --stages)
     for (int bst = 4; bst >= 2; --bst) {
-      const size_t epi = convk::kEpiWarps * 32 * convk::kStagePitch * sizeof(float);   // epilogue staging (all destinations)
+      const size_t epi = (size_t)4 * p.epi_per_quad * 32 * convk::kStagePitch * sizeof(float);   // epilogue staging rows of the working warps
       size_t need = (size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes + epi + 2048;
-      if (need > smem_limit) continue;
+      static const size_t limit_env = getenv("SSDN_CONV_SMEM_KB") ? (size_t)atoi(getenv("SSDN_CONV_SMEM_KB")) * 1024 : 0;   // ablation: fewer stages
+      if (need > (limit_env ? std::min(limit_env, smem_limit) : smem_limit)) continue;
       p.epi_off = (uint32_t)((size_t)stages * 2 * plane + (size_t)bst * p.b_stage_bytes);
       p.n_groups = (int)gs.size(); p.nbox = nbox; p.box_rows = box_rows; p.a_plane_bytes = plane; p.a_stages = stages; p.b_stages = bst;
       for (size_t gi = 0; gi < gs.size(); ++gi) {

@@ -254,7 +254,7 @@ class Net {
     // every dst_act below also yields the bias gradient of the layer that owns the produced dZ (fused column sums)
     auto fused = [&](const char* producer, const char* owner) {
       Layer& o = L(owner); o.bias_fused = true; o.bias_partial = o.bias_buf;
-      o.bias_nblk = L(producer).dgrad.grid * (L(producer).dgrad.p.epi_split ? convk::kEpiWarps : 4);
+      o.bias_nblk = L(producer).dgrad.grid * 4 * L(producer).dgrad.p.epi_per_quad;
       if ((size_t)o.bias_nblk > (size_t)std::max(sms * convk::kEpiWarps, pw::kFusedColsumGrid)) o.bias_nblk = -1;   // checked below
     };
     // pointwise producers (grid-stride kernels with at most kFusedColsumGrid blocks of kFusedColsumBlock threads)
