@@ -46,6 +46,7 @@ struct ConvParams {
   TapGroup groups[9];
   int nbox, box_rows; // every group window is loaded as nbox TMA boxes of box_rows rows (one op for both planes if nbox == 1)
   int a_stages, b_stages;
+  int lookahead;      // row3 issue path: poll the next operand stages while the first tap of a stencil row is queued (see the MMA issuer)
   int bg;             // weight slabs ((chunk, tap) pairs, in consumption order) per B stage: ONE TMA op loads bg x 2 planes
   int wide;           // 1x1 convolutions with cin % 64 == 0: chunks of 64 channels (128-byte rows, SWIZZLE_128B, 4 k-steps), one
                       //    weight slab per B stage; A is not reused by other taps there, so its TMA rate (rows/clk) is what binds
@@ -351,6 +352,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t lbo_bits = (uint32_t)(desc & 0xffff0000u);
       const uint32_t a_pl = p.a_plane_bytes >> 4, b_pl = (uint32_t)((PAIR ? p.N / 2 : p.N) * 64) >> 4, slab = 2 * b_pl;
       const int step = p.tap_step * 4;                       // one pixel row of the A window = 64 bytes
+      // The issuing thread's waits are NOT free: the tensor core's queue is a few instructions deep, so the ~200 clk an mbarrier
+      // wait + fence + elect costs - even on a barrier that completed long ago - idles the pipe (the loop ran 17 % above the
+      // tensor floor, the sum of its full_a / full_b wait shares).  Each stage is therefore LOOKED AT one stage ahead: after
+      // the first tap of a stencil row has been queued (12 MMAs, ~550 clk of tensor work) the warp polls the NEXT weight
+      // stage - and the next activation window when this is the last row of the current one - before it issues the other taps.
+      int n_my_units = 0;
+      for (int u = u_first; u < n_units; u += u_stride) ++n_my_units;
+      int rows_per_chunk = 0;
+      for (int g = 0; g < p.n_groups; ++g) rows_per_chunk += p.groups[g].ntaps / 3;
+      long long b_left = (long long)n_my_units * p.n_chunks * rows_per_chunk;      // weight stages still to be consumed
+      long long a_left = (long long)n_my_units * p.n_chunks * p.n_groups;          // activation windows still to be consumed
+      bool a_ready = false, b_ready = false;                                         // the current stage has already been waited for
       for (int u = u_first; u < n_units; u += u_stride, ++it) {
         const int buf = it & 1;
         SSDN_TIMED(w_tmem, umma::mbar_wait(tmem_empty(buf), ((it >> 1) & 1) ^ 1, abort_addr, p.error_flag, 3));
@@ -360,44 +373,65 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           const bool two = (ch != p.n_chunks - 1) || (p.ksteps_last == 2);
           for (int g = 0; g < p.n_groups; ++g) {
-            SSDN_TIMED(w_a, umma::mbar_wait(full_a(ra.stage), ra.phase, abort_addr, p.error_flag, 3));
+            if (!a_ready) SSDN_TIMED(w_a, umma::mbar_wait(full_a(ra.stage), ra.phase, abort_addr, p.error_flag, 3));
+            a_ready = false; --a_left;
             const uint32_t a_stage = a_base + ra.stage * a_stage_bytes;
+            const int a_cur = ra.stage;
+            ra.advance();                                     // (ra now names the NEXT window)
             const int nrows = p.groups[g].ntaps / 3;
             for (int r = 0; r < nrows; ++r) {
-              SSDN_TIMED(w_b, umma::mbar_wait(full_b(rb.stage), rb.phase, abort_addr, p.error_flag, 3));
+              if (!b_ready) SSDN_TIMED(w_b, umma::mbar_wait(full_b(rb.stage), rb.phase, abort_addr, p.error_flag, 3));
+              b_ready = false; --b_left;
               umma::tc_fence_after();
               const uint32_t a0 = (((a_stage + p.groups[g].tap_rel[3 * r] * 64) >> 4) & 0x3fffu) | lbo_bits;
               const uint32_t b0 = (((b_base + rb.stage * b_stage_bytes) >> 4) & 0x3fffu) | lbo_bits;
-              if (umma::elect_one()) {
-                // consecutive MMAs go to DIFFERENT accumulators (tiles alternate): back-to-back accumulation into one
-                // accumulator exposes the tensor pipe's accumulate latency (profiles/r02_f16_probe.log F7 vs r02_umma_peak.log)
+              const int b_cur = rb.stage;
+              rb.advance();                                   // (rb now names the NEXT weight stage)
+              // per (tile, k-step) the products lo*hi, hi*lo, hi*hi back to back (collector, see above)
+              auto issue_tap = [&](int j) {
+                const uint32_t aj = a0 + j * step, bj = b0 + j * slab;
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                  const uint32_t aj = a0 + j * step, bj = b0 + j * slab;
+                for (int ks = 0; ks < 2; ++ks) {
+                  if (ks == 0 || two) {
+                    const uint32_t ko = ks ? 2u : 0u;
 #pragma unroll
-                  for (int ks = 0; ks < 2; ++ks) {        // k-steps of the chunk; per (tile, k-step) the products lo*hi, hi*lo, hi*hi
-                    if (ks == 0 || two) {
-                      const uint32_t ko = ks ? 2u : 0u;
-#pragma unroll
-                      for (int tile = 0; tile < T; ++tile) {
-                        const uint32_t d = d0 + tile * p.N;
-                        const uint32_t av = aj + tile * 512 + ko, al = av + a_pl, bv = bj + ko, bl = bv + b_pl;
-                        mma(d, al, bv, desc_hi, (j == 0 && ks == 0) ? first : 1u);
-                        mma_fill(d, av, bl, desc_hi);      // A_hi: fetched once for the two products that use it
-                        mma_last(d, av, bv, desc_hi);
-                      }
+                    for (int tile = 0; tile < T; ++tile) {
+                      const uint32_t d = d0 + tile * p.N;
+                      const uint32_t av = aj + tile * 512 + ko, al = av + a_pl, bv = bj + ko, bl = bv + b_pl;
+                      mma(d, al, bv, desc_hi, (j == 0 && ks == 0) ? first : 1u);
+                      mma_fill(d, av, bl, desc_hi);      // A_hi: fetched once for the two products that use it
+                      mma_last(d, av, bv, desc_hi);
                     }
                   }
                 }
-                commit(empty_b(rb.stage));
+              };
+              if (!p.lookahead) {                             // short stages (N <= 48, one tile): the look-ahead is pure overhead there
+                if (umma::elect_one()) {
+                  issue_tap(0); issue_tap(1); issue_tap(2);
+                  commit(empty_b(b_cur));
+                  if (r == nrows - 1) commit(empty_a(a_cur));
+                }
+                __syncwarp();
+                first = 1;
+                continue;
+              }
+              if (umma::elect_one()) issue_tap(0);
+              __syncwarp();
+              // ONE non-blocking look at the next weight stage (and at the next activation window when this is the last row of
+              // the current one) while the first tap is in the queue: if it has landed, the blocking wait at the top of the next
+              // stage - whose fixed cost would idle the pipe - is skipped; if not, nothing is lost (blocking here instead made the
+              // N = 48 layers, whose short weight stages are latency-bound, 9 % slower)
+              if (b_left > 0) b_ready = __all_sync(0xffffffffu, umma::mbar_try_wait(full_b(rb.stage), rb.phase));
+              if (r == nrows - 1 && a_left > 0) a_ready = __all_sync(0xffffffffu, umma::mbar_try_wait(full_a(ra.stage), ra.phase));
+              if (umma::elect_one()) {
+                issue_tap(1);
+                issue_tap(2);
+                commit(empty_b(b_cur));
+                if (r == nrows - 1) commit(empty_a(a_cur));
               }
               __syncwarp();
               first = 1;
-              rb.advance();
             }
-            if (umma::elect_one()) commit(empty_a(ra.stage));
-            __syncwarp();
-            ra.advance();
           }
         }
         if (umma::elect_one()) commit(tmem_full(buf));
@@ -823,6 +857,10 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const __half* 
     }
     if (ok) { p.row3 = 1; p.tap_step = step; }
   }
+  // measured (interleaved A/B against the build without it): -5 % / -2.5 % on the two largest layers, -2 % on the data-gradients,
+  // +4 % on the 48-channel layers and +1-2 us on every one-tile layer if it were on everywhere
+  p.lookahead = (p.row3 && N >= 96 && !(getenv("SSDN_LOOKAHEAD") && atoi(getenv("SSDN_LOOKAHEAD")) == 0)) ? 1 : 0;
+  if (getenv("SSDN_LOOKAHEAD") && atoi(getenv("SSDN_LOOKAHEAD")) == 2) p.lookahead = p.row3;
   if (p.pair && !p.row3 && !p.wide) return -14;      // pairs are implemented for the row3 and the wide issue paths
   if (p.pair) {
     p.n_pairs = (p.n_units_m + 1) / 2 * p.n_tiles_n;
