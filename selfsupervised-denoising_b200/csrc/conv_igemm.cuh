@@ -58,9 +58,9 @@ struct ConvParams {
   const int* k_a; const int* k_b;   // scale exponents of the A tensor and of the weight slab (device; null = 0)
   uint64_t magic_s, magic_p;   // ceil(2^64 / src.S), ceil(2^64 / src.P): the epilogue's pixel -> (image, row, column) divisions
   uint32_t wait_hint;          // suspend-time hint (ns) of the producers' / epilogue's mbarrier waits (0 = plain try_wait spin)
-  int epi_per_quad;   // epilogue warps per TMEM lane quadrant that work (1 .. kEpiPerQuad); the others exit at once.  3: epilogue-bound
-                      //    layers; 2: the MMA-bound 3x3 layers (their 18 KB of staging rows buy one more weight stage: the issuer
-                      //    waits less for weights); 1: upsampling / NCHW epilogues (more warps only fight over the load/store unit)
+  int epi_per_quad;   // epilogue warps per TMEM lane quadrant that work (1 .. kEpiPerQuad); the others exit at once.  3: every layer
+                      //    but the NCHW output (a lane walks its pixel's channels there); 2 / 1: ablations (fewer staging rows buy a weight
+                      //    stage: measured no gain)
   ConvDst dst;
   int* error_flag;
   int debug;          // experiments only: 2 = skip MMA issue (generic issue path)
@@ -784,7 +784,7 @@ static inline int conv_plan_init(ConvPlan* plan, const Geom& src, const __half* 
   // epilogue: both warps of a TMEM lane quadrant - measured never slower (profiles/r01_pair_split_ablation.log), except
   // with the upsampling epilogue (4x the stores: the two warps then only fight over the load/store unit)
   {
-    p.epi_per_quad = (dst.map != MAP_UP2 && dst.map != MAP_NCHW) ? convk::kEpiPerQuad : 1;
+    p.epi_per_quad = dst.map != MAP_NCHW ? convk::kEpiPerQuad : 1;      // (upsampling epilogues too, now that they write whole sectors: -6 %)
     if (const char* e = getenv("SSDN_EPI_SPLIT")) p.epi_per_quad = atoi(e) != 0 ? convk::kEpiPerQuad : 1;
     if (const char* e = getenv("SSDN_EPI_PER_QUAD")) { const int v = atoi(e); if (v >= 1 && v <= convk::kEpiPerQuad && p.epi_per_quad > 1) p.epi_per_quad = v; }
   }
